@@ -1,0 +1,158 @@
+/*
+ * pegncde.h -- C-ABI of the B200-native (sm_100a) hot path of
+ * hits-mli/perm-equiv-graph-neural-cdes: the Tsit5 solve loop that evaluates the
+ * permutation-equivariant graph vector field f_theta(Z_s, A_s) at every stage,
+ * forward and exact-discrete-adjoint backward.
+ *
+ * The reference is pure Python/JAX and has NO FFI for this path; each entry point
+ * below names the reference call it replaces (paths relative to the reference root):
+ *
+ *   pegncde_pack_adj        src/configs/dataset_configs.py:147-173,1073-1100  (coeff layout -> planar planes)
+ *   pegncde_pack_x          src/configs/dataset_configs.py:1073-1100          (node-signal coeffs)
+ *   pegncde_vf_fwd          src/models/vector_fields/perm_equiv_graph_vector_field.py:85-129
+ *                           + cde_wrapper_vector_field.py:19-26  (the ODETerm callable vf(t, y, args))
+ *   pegncde_vf_vjp          jax.vjp of the same callable
+ *   pegncde_step_fwd        one diffrax Tsit5.step (call sites pgt_graph_neural_cde.py:65,
+ *                           graph_neural_cde.py:53) -> y1, y_err, k7 (FSAL) for host-side controllers
+ *   pegncde_solve_fwd       diffrax.diffeqsolve(ODETerm(vf), Tsit5(), ..., ConstantStepSize())
+ *                           src/models/pgt_graph_neural_cde.py:119-129, graph_neural_cde.py:94-104,
+ *                           tgb_graph_neural_cde.py:152-162
+ *   pegncde_solve_bwd       reverse mode through that call (diffrax default RecursiveCheckpointAdjoint,
+ *                           reached via eqx.filter_value_and_grad, src/engine/trainer_pgt.py:346,
+ *                           src/engine/trainer.py:315)
+ *
+ * Conventions
+ *   - every pointer except `step_ts` is a DEVICE pointer owned by the caller (XLA / torch);
+ *     the library never allocates, frees or retains device memory and keeps no global state.
+ *   - functions only ENQUEUE work on `stream` (no device synchronisation, no host callbacks),
+ *     so they are safe inside an XLA custom call and capturable in a CUDA graph.
+ *   - all floating-point data is fp32 (the reference never enables x64), row-major.
+ *   - return value: 0 = ok, otherwise a PEG_ERR_* code; pegncde_strerror() names it.
+ *     Nothing throws or exits across this boundary.
+ */
+#ifndef PEGNCDE_H_
+#define PEGNCDE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* peg_stream_t; /* a cudaStream_t */
+
+enum {
+  PEG_OK = 0,
+  PEG_ERR_BAD_DIMS = 1,      /* a dimension is out of the supported range */
+  PEG_ERR_NULL_POINTER = 2,  /* a required pointer is NULL */
+  PEG_ERR_WORKSPACE = 3,     /* workspace smaller than pegncde_workspace_bytes() */
+  PEG_ERR_CUDA = 4,          /* a CUDA runtime call or launch failed (see pegncde_last_cuda_error) */
+  PEG_ERR_UNSUPPORTED = 5,   /* valid request the library does not implement */
+  PEG_ERR_ALIGNMENT = 6      /* a pointer or pitch breaks the 16-byte alignment contract */
+};
+
+/* flags in PegDims.flags */
+enum {
+  PEG_FLAG_RELU = 0,            /* reserved */
+  PEG_FLAG_TENSOR_CORES = 1,    /* n x n x d contractions on tcgen05 (3xTF32 split: fp32-parity) */
+  PEG_FLAG_TF32_FAST = 2,       /* with TENSOR_CORES: single-pass TF32 (rna-rounded), looser tolerance */
+  PEG_FLAG_STORE_STAGES = 4     /* solve_fwd keeps every stage's layer inputs so solve_bwd skips recompute */
+};
+
+typedef struct PegDims {
+  int32_t B;     /* graphs (trajectories) in the batch; each has its own control path      */
+  int32_t n;     /* nodes                                                                  */
+  int32_t ldn;   /* row pitch of the coefficient planes in floats; >= n, multiple of 4     */
+  int32_t h;     /* hidden_dim = width of the state y [n,h] and of every hidden layer      */
+  int32_t e;     /* data_embed_dim; 0 = plain ODETerm(vector_field) (no CDE wrapper)       */
+  int32_t L;     /* num_layers of ConvEquivFusionLayer                                     */
+  int32_t T;     /* knots of the control path (T-1 cubic pieces)                           */
+  int32_t flags; /* PEG_FLAG_*                                                             */
+} PegDims;
+/* width of the last layer: h if e == 0 else 2*h*e (vector_field_configs.py:71) */
+
+/* Planar control path, built once per batch by pegncde_pack_adj / pegncde_pack_x.
+ * Coefficient order everywhere is (a, b, c, d):  X(t) = a + s(b + s(c + s d)), s = t - ts[i]. */
+typedef struct PegControl {
+  const float* ts;         /* [B, T]            knot times                                         */
+  const float* adj_coef;   /* [B, T-1, 4, n, ldn] adjacency channel of the reference's coeffs       */
+  const float* adj_rowsum; /* [B, T-1, 4, n]    row sums of each plane                              */
+  const float* adj_diag;   /* [B, T-1, 4, n]    diagonal of each plane                              */
+  const float* adj_total;  /* [B, T-1, 4]       total of each plane                                 */
+  const float* tch_coef;   /* [B, T-1, 3, n]    (b,c,d) of the time channel, mean over axis 0       */
+  const float* x_coef;     /* [B, T-1, 3, n, 2e] (b,c,d) of the node-signal path, last axis (l,k)
+                              interleaved like the reference's [n,e,2]; NULL iff e == 0             */
+} PegControl;
+
+/* ---- parameter packing ---------------------------------------------------------------
+ * params / g_params are one flat fp32 buffer, layer after layer:
+ *   weight [d_out, d_in] | bias [d_out] | norm_weight [d_in] | norm_bias [d_in] |
+ *   fusion [8,2] = param1[0],param1[1],param2[0],...,param8[1]
+ * (leaf names: gnn_layers[l].conv_layer.linear.{weight,bias}, .conv_layer.norm.{weight,bias},
+ *  gnn_layers[l].param1..param8 -- src/models/vector_fields/layers.py:19-20,66-74). */
+size_t pegncde_param_count(const PegDims* dims);
+/* offsets[5*l + {0,1,2,3,4}] = float offset of weight, bias, norm_weight, norm_bias, fusion of layer l */
+int pegncde_param_offsets(const PegDims* dims, int64_t* offsets /* [5*L] */);
+
+/* ---- control-path packing (device) ---------------------------------------------------- */
+/* d,c,b,a: the four arrays diffrax.backward_hermite_coefficients returns, each
+ * [B, T-1, n, n, 2] with the last axis (time, adjacency).  Writes every PegControl adj_* / tch_* field. */
+int pegncde_pack_adj(peg_stream_t stream, const PegDims* dims, const float* d, const float* c, const float* b,
+                     const float* a, float* adj_coef, float* adj_rowsum, float* adj_diag, float* adj_total,
+                     float* tch_coef);
+/* same for already-planar adjacency planes (adj_coef given): fills the statistics only;
+ * tch_coef is written as d(time)/dt == 1 (b=1, c=d=0). */
+int pegncde_adj_stats(peg_stream_t stream, const PegDims* dims, const float* adj_coef, float* adj_rowsum,
+                      float* adj_diag, float* adj_total, float* tch_coef);
+/* d,c,b,a each [B, T-1, n, e, 2] -> x_coef [B, T-1, 3, n, 2e] */
+int pegncde_pack_x(peg_stream_t stream, const PegDims* dims, const float* d, const float* c, const float* b,
+                   const float* a, float* x_coef);
+
+/* ---- workspace ------------------------------------------------------------------------- */
+enum { PEG_WS_VF_FWD = 0, PEG_WS_VF_VJP = 1, PEG_WS_SOLVE_FWD = 2, PEG_WS_SOLVE_BWD = 3, PEG_WS_STEP = 4 };
+/* bytes of caller-provided scratch for one call of kind `which` with `steps` solver steps */
+size_t pegncde_workspace_bytes(const PegDims* dims, int32_t which, int32_t steps);
+
+/* ---- vector field ----------------------------------------------------------------------- */
+/* dy[b] = vf(t, y[b], args) for every graph of the batch; t is a host scalar (shared stage time). */
+int pegncde_vf_fwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params, float t,
+                   const float* y /* [B,n,h] */, float* dy /* [B,n,h] */, void* workspace, size_t workspace_bytes);
+/* g_y = (d vf/d y)^T g_dy ; g_params += (d vf/d theta)^T g_dy summed over the batch (caller zeroes it);
+ * g_xdot (nullable) [B,n,2e] = cotangent of control_data.derivative(t). */
+int pegncde_vf_vjp(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params, float t,
+                   const float* y, const float* g_dy, float* g_y, float* g_params, float* g_xdot, void* workspace,
+                   size_t workspace_bytes);
+
+/* ---- one Tsit5 step (adaptive controllers stay on the host) ----------------------------- */
+/* k1 = f(t, y) when k1_valid == 0 (first step) else taken from k1 (FSAL).  Writes y1, y_err
+ * (= dt * sum_i (b_i - bhat_i) k_i) and k7 = f(t + dt, y1). */
+int pegncde_step_fwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params, float t,
+                     float dt, const float* y, float* k1, int32_t k1_valid, float* y1, float* y_err, float* k7,
+                     void* workspace, size_t workspace_bytes);
+
+/* ---- fixed-step solve -------------------------------------------------------------------- */
+/* step_ts: HOST array [steps+1] of fp32 step boundaries, built by the caller with diffrax's
+ * ConstantStepSize + end-clipping rule.  y_ckpt [steps+1, B, n, h] receives y at every boundary
+ * (y_ckpt[0] = y0, y_ckpt[steps] = y(T)); it is the SaveAt(steps) output and the checkpoint set
+ * pegncde_solve_bwd restarts from.  yT (nullable) [B,n,h] = y_ckpt[steps]. */
+int pegncde_solve_fwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params,
+                      const float* step_ts, int32_t steps, const float* y0, float* yT, float* y_ckpt,
+                      void* workspace, size_t workspace_bytes);
+/* g_ckpt (nullable) [steps+1, B, n, h]: cotangents injected at step boundaries (SaveAt(ts=...) losses);
+ * g_yT [B,n,h] cotangent of y(T).  Writes g_y0; accumulates g_params (caller zeroes it). */
+int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params,
+                      const float* step_ts, int32_t steps, const float* y_ckpt, const float* g_yT,
+                      const float* g_ckpt, float* g_y0, float* g_params, void* workspace, size_t workspace_bytes);
+
+/* ---- introspection ------------------------------------------------------------------------ */
+const char* pegncde_strerror(int code);
+int pegncde_last_cuda_error(void); /* cudaError_t of the most recent PEG_ERR_CUDA on this thread */
+const char* pegncde_version(void);
+/* kernels launched by this library since process start (for bench.py's gpu_launches) */
+uint64_t pegncde_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEGNCDE_H_ */

@@ -1,0 +1,419 @@
+"""CPU ORACLE (test infrastructure, NOT product code) -- parity unpinned.
+
+Literal restatement, in PyTorch-CPU, of the one hot path of
+hits-mli/perm-equiv-graph-neural-cdes: the Tsit5 solve loop that evaluates the
+permutation-equivariant graph vector field at every stage.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module; the product package
+``perm_equiv_graph_neural_cdes_b200`` never does.
+
+PARITY UNPINNED: the reference (JAX + Equinox + diffrax) cannot be imported in this
+image (no jax/diffrax/equinox wheels, no network) and the reference ships no test,
+golden vector or fixture for any function on this path (reference ``test/`` covers
+dataset utilities only).  Every function below follows the cited reference lines
+op-for-op -- including materialising the fused n x n adjacency exactly like the
+reference does -- and the diffrax / equinox pieces are restated from their published
+algorithms (diffrax >= 0.5, version unpinned in reference ``environment.yaml:16``).
+``oracle/regen_with_jax.py`` re-derives the goldens from the real packages wherever
+they are installed.
+
+All functions are dtype-generic (fp32 = what the reference computes in; fp64 = truth
+the tolerance is set against) and differentiable with torch autograd, which stands in
+for ``eqx.filter_value_and_grad`` through diffrax's default RecursiveCheckpointAdjoint
+(exact discretise-then-optimise gradients).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+# --------------------------------------------------------------------------------------
+# third-party: diffrax.backward_hermite_coefficients  (call sites
+# src/configs/dataset_configs.py:168-170, 228-230, 1094-1096)
+# --------------------------------------------------------------------------------------
+
+
+def backward_hermite_coefficients(ts: torch.Tensor, ys: torch.Tensor):
+    """Returns (d, c, b, a), each [T-1, ...], like diffrax.backward_hermite_coefficients.
+
+    Per interval i (dt = t[i+1]-t[i], secant m_i = (y[i+1]-y[i])/dt): cubic with
+    p(0)=y_i, p'(0)=m_{i-1} (m_0 for the first interval), p(dt)=y_{i+1}, p'(dt)=m_i.
+    """
+    ts = ts.to(ys.dtype)
+    dt = (ts[1:] - ts[:-1]).reshape((-1,) + (1,) * (ys.dim() - 1))
+    m = (ys[1:] - ys[:-1]) / dt
+    b = torch.cat([m[:1], m[:-1]], dim=0)
+    a = ys[:-1]
+    c = 2.0 * (m - b) / dt
+    d = -(m - b) / (dt * dt)
+    return d, c, b, a
+
+
+class CubicInterpolation:
+    """diffrax.CubicInterpolation(ts, (d, c, b, a)) -- evaluate / derivative.
+
+    Used at src/models/pgt_graph_neural_cde.py:105-107,
+    src/models/graph_neural_cde.py:82-83.
+    """
+
+    def __init__(self, ts: torch.Tensor, coeffs):
+        self.ts = ts
+        self.d, self.c, self.b, self.a = coeffs
+
+    def _interpret_t(self, t):
+        # index = clip(searchsorted(ts, t, side="left") - 1, 0, T-2); frac = t - ts[index]
+        tsf = self.ts.to(torch.float64)
+        idx = int(torch.searchsorted(tsf, torch.as_tensor(float(t), dtype=torch.float64), right=False)) - 1
+        idx = max(0, min(idx, self.ts.numel() - 2))
+        frac = torch.as_tensor(t, dtype=self.a.dtype) - self.ts[idx].to(self.a.dtype)
+        return idx, frac
+
+    def evaluate(self, t):
+        i, s = self._interpret_t(t)
+        return self.a[i] + s * (self.b[i] + s * (self.c[i] + s * self.d[i]))
+
+    def derivative(self, t):
+        i, s = self._interpret_t(t)
+        return self.b[i] + s * (2.0 * self.c[i] + 3.0 * s * self.d[i])
+
+
+# --------------------------------------------------------------------------------------
+# parameters (field names follow the reference pytree: layers.py:19-20, 66-74)
+# --------------------------------------------------------------------------------------
+
+
+@dataclass
+class LayerParams:
+    """One ConvEquivFusionLayer: param1..param8 (each [2]) + conv_layer.{linear,norm}."""
+
+    fusion: torch.Tensor  # [8, 2]  rows = param1..param8
+    weight: torch.Tensor  # [d_out, d_in]   conv_layer.linear.weight
+    bias: torch.Tensor  # [d_out]          conv_layer.linear.bias
+    norm_weight: torch.Tensor  # [d_in]    conv_layer.norm.weight
+    norm_bias: torch.Tensor  # [d_in]      conv_layer.norm.bias
+
+    def tensors(self):
+        return [self.fusion, self.weight, self.bias, self.norm_weight, self.norm_bias]
+
+
+def layer_widths(hidden_dim: int, num_layers: int, data_embed_dim: int, use_control: bool) -> List[int]:
+    """[d_0, ..., d_L]: src/configs/vector_field_configs.py:66-76,100-108 and
+    perm_equiv_graph_vector_field.py:47-61."""
+    out = hidden_dim * data_embed_dim * 2 if use_control else hidden_dim
+    return [hidden_dim] * num_layers + [out]
+
+
+def init_params(widths: Sequence[int], seed: int, dtype=torch.float32, randomize_norm: bool = False) -> List[LayerParams]:
+    """Reference init distributions (layers.py:86-100; eqx.nn.Linear U(+-1/sqrt(in));
+    RMSNorm weight 1 / bias 0).  ``randomize_norm`` perturbs the norm affine so tests
+    exercise those gradients away from the init point."""
+    g = torch.Generator().manual_seed(seed)
+    layers = []
+    for l in range(len(widths) - 1):
+        din, dout = widths[l], widths[l + 1]
+        fusion = (torch.rand((8, 2), generator=g, dtype=torch.float64) * 2 - 1) / 15.0
+        lim = 1.0 / math.sqrt(din)
+        W = (torch.rand((dout, din), generator=g, dtype=torch.float64) * 2 - 1) * lim
+        b = (torch.rand((dout,), generator=g, dtype=torch.float64) * 2 - 1) * lim
+        nw = torch.ones(din, dtype=torch.float64)
+        nb = torch.zeros(din, dtype=torch.float64)
+        if randomize_norm:
+            nw = nw + 0.2 * (torch.rand((din,), generator=g, dtype=torch.float64) * 2 - 1)
+            nb = nb + 0.2 * (torch.rand((din,), generator=g, dtype=torch.float64) * 2 - 1)
+        layers.append(LayerParams(*(x.to(dtype) for x in (fusion, W, b, nw, nb))))
+    return layers
+
+
+def params_to(layers: List[LayerParams], dtype=None, requires_grad=False) -> List[LayerParams]:
+    out = []
+    for lp in layers:
+        ts = [x.detach().clone().to(dtype or x.dtype).requires_grad_(requires_grad) for x in lp.tensors()]
+        out.append(LayerParams(*ts))
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# the vector field (reference, materialised)
+# --------------------------------------------------------------------------------------
+
+
+def fusion(adjacency: torch.Tensor, control_gradient: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
+    """ConvEquivFusionLayer._fusion, src/models/vector_fields/layers.py:102-160.
+
+    ``p`` is [8,2] = param1..param8.  Builds the n x n fused adjacency term by term in
+    the reference's order, INCLUDING the term-7 quirk (both coefficients multiply
+    sum(adjacency), layers.py:144-148)."""
+    n = adjacency.shape[0]
+    one = torch.ones((), dtype=adjacency.dtype)
+    eye = torch.eye(n, dtype=adjacency.dtype)
+    term_1 = (1.0 + p[0, 0]) * adjacency + (1.0 + p[0, 1]) * control_gradient
+    term_2 = p[1, 0] * adjacency.t() + p[1, 1] * control_gradient.t()
+    term_3 = p[2, 0] * torch.diag(torch.diag(adjacency)) + p[2, 1] * torch.diag(torch.diag(control_gradient))
+    rs_a = adjacency.sum(dim=1)
+    rs_c = control_gradient.sum(dim=1)
+    # transpose(tile(rowsum,(n,1)))[i,j] = rowsum[i]
+    term_4 = p[3, 0] / n * rs_a[:, None].expand(n, n) + p[3, 1] / n * rs_c[:, None].expand(n, n)
+    # tile(rowsum,(n,1))[i,j] = rowsum[j]
+    term_5 = p[4, 0] / n * rs_a[None, :].expand(n, n) + p[4, 1] / n * rs_c[None, :].expand(n, n)
+    term_6 = p[5, 0] / n * torch.diag(rs_a) + p[5, 1] / n * torch.diag(rs_c)
+    tot_a = adjacency.sum()
+    term_7 = p[6, 0] / n**2 * (tot_a * one).expand(n, n) + p[6, 1] / n**2 * (tot_a * one).expand(n, n)
+    term_8 = (p[7, 0] * tot_a + p[7, 1] * control_gradient.sum()) / n**2 * eye
+    return term_1 + term_2 + term_3 + term_4 + term_5 + term_6 + term_7 + term_8
+
+
+def rms_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """equinox.nn.RMSNorm(shape) applied per node (jax.vmap(self.norm), layers.py:45):
+    x * rsqrt(mean(x^2) + eps) * weight + bias."""
+    inv = torch.rsqrt((x * x).mean(dim=-1, keepdim=True) + eps)
+    return x * inv * weight + bias
+
+
+def conv_layer(node_feats, adj_matrix, lp: LayerParams):
+    """ConvLayer.__call__, layers.py:36-48: norm -> linear -> m + adj @ m."""
+    z = rms_norm(node_feats, lp.norm_weight, lp.norm_bias)
+    m = z @ lp.weight.t() + lp.bias
+    return m + adj_matrix @ m
+
+
+def perm_equiv_vector_field(t, y, control_adj: CubicInterpolation, layers: List[LayerParams]):
+    """PermEquivGraphVectorField.__call__, perm_equiv_graph_vector_field.py:85-129
+    (enc_idx=False; the enc_idx branch is unreachable in the reference)."""
+    adj = control_adj.evaluate(t)[..., -1]
+    adj_derivative = control_adj.derivative(t)[..., -1]
+    t_gradient = control_adj.derivative(t)[..., 0]
+    node_features = y
+    for i, lp in enumerate(layers):
+        fused = fusion(adj, adj_derivative, lp.fusion)  # layers.py:174
+        node_features = conv_layer(node_features, fused, lp)  # layers.py:176
+        if i < len(layers) - 1:
+            node_features = torch.relu(node_features)
+    t_gradient = t_gradient.mean(dim=0)  # [nodes]
+    return t_gradient[:, None] * node_features
+
+
+def cde_wrapper_vector_field(t, y, control_adj, control_data, layers, hidden_dim, data_embed_dim):
+    """CDEWrapperVectorField.__call__, cde_wrapper_vector_field.py:19-26."""
+    out = perm_equiv_vector_field(t, y, control_adj, layers).reshape(-1, hidden_dim, data_embed_dim, 2)
+    return torch.einsum("nmlk,nlk->nm", out, control_data.derivative(t))
+
+
+# --------------------------------------------------------------------------------------
+# third-party: diffrax Tsit5 + ConstantStepSize + diffeqsolve (fixed step)
+# --------------------------------------------------------------------------------------
+
+# Tsitouras 2011, "Runge-Kutta pairs of order 5(4) satisfying only the first column
+# simplifying assumption" -- the tableau diffrax.Tsit5 uses.
+TSIT5_C = (0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0)
+TSIT5_A = (
+    (),
+    (0.161,),
+    (-0.008480655492356989, 0.335480655492357),
+    (2.8971530571054935, -6.359448489975075, 4.3622954328695815),
+    (5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525),
+    (5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383),
+    (0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774),
+)
+TSIT5_B = TSIT5_A[6] + (0.0,)
+# b_sol - b_hat (error estimate weights); needed only by the adaptive path
+TSIT5_BERR = (
+    -0.00178001105222577714,
+    -0.0008164344596567469,
+    0.007880878010261995,
+    -0.1447110071732629,
+    0.5823571654525552,
+    -0.45808210592918697,
+    0.015151515151515152,
+)
+
+
+def constant_step_table(t0: float, t1: float, dt0: float, rule: str = "state", max_steps: int = 4096) -> np.ndarray:
+    """Step boundaries [S+1] (fp32) of diffeqsolve(..., dt0, ConstantStepSize()).
+
+    fp32 time accumulation with diffrax's end clipping (``_clip_to_end``:
+    ``tnext > t1 - 1e-6  ->  t1`` for non-float64 times).  ``rule="state"`` is
+    ``tnext = t + dt0`` (diffrax >= 0.7 keeps dt0 in the controller state);
+    ``rule="prev_diff"`` is ``tnext = t + (t - tprev)`` (diffrax <= 0.6).  The two
+    differ by ulps in the boundaries and at most by one ~1e-6-long final step."""
+    f = np.float32
+    t0, t1, dt0 = f(t0), f(t1), f(dt0)
+    ts = [t0]
+    tprev, tnext = t0, f(t0 + dt0)
+    tol = f(1e-6)
+    while True:
+        if tnext > f(t1 - tol):
+            tnext = t1
+        ts.append(tnext)
+        if tnext >= t1:
+            break
+        if len(ts) > max_steps:
+            raise RuntimeError("max_steps reached (diffrax throw=True)")
+        step = f(tnext - tprev) if rule == "prev_diff" else dt0
+        tprev, tnext = tnext, f(tnext + step)
+    return np.asarray(ts, dtype=np.float32)
+
+
+def tsit5_solve_fixed(f, y0: torch.Tensor, step_ts: Sequence[float], save_all: bool = False):
+    """Explicit 7-stage Tsit5 with FSAL over a fixed step table.
+
+    k_i = f(t + c_i h, y + h sum_j a_ij k_j);  y1 = y + h sum_i b_i k_i  (b_7 = 0, so
+    the 7th stage only feeds FSAL: it is k_1 of the next step).  Returns y(T) or the
+    list of y at every step boundary."""
+    dt_ = y0.dtype
+    y = y0
+    ys = [y0]
+    k1 = None
+    S = len(step_ts) - 1
+    for s in range(S):
+        t = float(step_ts[s])
+        h_f = np.float32(step_ts[s + 1]) - np.float32(step_ts[s]) if dt_ == torch.float32 else float(step_ts[s + 1]) - float(step_ts[s])
+        h = float(h_f)
+        ks = [k1 if k1 is not None else f(t, y)]
+        for i in range(1, 6):
+            acc = ks[0] * TSIT5_A[i][0]
+            for j in range(1, i):
+                acc = acc + ks[j] * TSIT5_A[i][j]
+            ks.append(f(t + TSIT5_C[i] * h, y + h * acc))
+        acc = ks[0] * TSIT5_B[0]
+        for j in range(1, 6):
+            acc = acc + ks[j] * TSIT5_B[j]
+        y = y + h * acc
+        ys.append(y)
+        k1 = f(float(step_ts[s + 1]), y) if s + 1 < S else None  # FSAL (7th stage)
+    return ys if save_all else y
+
+
+# --------------------------------------------------------------------------------------
+# solve wrappers + losses
+# --------------------------------------------------------------------------------------
+
+
+def solve_cde(step_ts, ts, coeffs_adj, x_coeffs, y0, layers, hidden_dim, data_embed_dim, save_all=False):
+    """The diffeqsolve call of PGTGraphNeuralCDE.__call__ (pgt_graph_neural_cde.py:101-129),
+    from y0 = encoder(x0) to ys[-1]; the encoder/decoder MLPs stay on the host side."""
+    control_adj = CubicInterpolation(ts, coeffs_adj)
+    if x_coeffs is not None:
+        control_data = CubicInterpolation(ts, x_coeffs)
+        f = lambda t, y: cde_wrapper_vector_field(t, y, control_adj, control_data, layers, hidden_dim, data_embed_dim)
+    else:  # GraphNeuralCDE (graph_neural_cde.py:79-104): ODETerm(vector_field), no wrapper
+        f = lambda t, y: perm_equiv_vector_field(t, y, control_adj, layers)
+    return tsit5_solve_fixed(f, y0, step_ts, save_all=save_all)
+
+
+def pgt_mse_loss(y_T, readout_w, label):
+    """mse_loss of src/engine/trainer_pgt.py:45-66 with a linear stand-in decoder:
+    y_pred = sum_nodes(decoder(y_T)) reshaped (feature_dim, 1) against label [n]
+    (broadcast exactly like the reference: (1,1) - (n,) -> (1,n))."""
+    out = y_T @ readout_w  # [n, feature_dim]
+    y_pred = out.sum(dim=0).reshape(-1, 1)
+    return ((y_pred - label) ** 2).mean()
+
+
+# --------------------------------------------------------------------------------------
+# synthetic inputs; shared by tests, smoke and bench
+# --------------------------------------------------------------------------------------
+
+
+def synthetic_graph_path(n: int, T: int, seed: int, scale: float = 1.0, density: Optional[float] = None) -> np.ndarray:
+    """A_k [T, n, n] float64: sparse-ish dynamic weighted digraph, Bernoulli(min(1,16/n))
+    mask with 10% of entries redrawn per knot, LogNormal(0,1) weights, self-loops."""
+    rng = np.random.default_rng(seed)
+    p = min(1.0, 16.0 / n) if density is None else density
+    mask = rng.random((n, n)) < p
+    w = rng.lognormal(0.0, 1.0, size=(n, n))
+    out = np.empty((T, n, n), dtype=np.float64)
+    for k in range(T):
+        if k > 0:
+            redraw = rng.random((n, n)) < 0.10
+            mask = np.where(redraw, rng.random((n, n)) < p, mask)
+            w = np.where(redraw, rng.lognormal(0.0, 1.0, size=(n, n)), w)
+        a = np.where(mask, w, 0.0)
+        np.fill_diagonal(a, 1.0)
+        # row-normalise so the ODE stays O(1) over [0, T-1] (the reference feeds
+        # normalised operators for the dynamical systems; PGT feeds raw weights)
+        a = a / a.sum(axis=1, keepdims=True)
+        out[k] = a * scale
+    return out
+
+
+def reference_layout_coeffs(ts: torch.Tensor, A: torch.Tensor):
+    """get_graph_interpolation_coeffs (dataset_configs.py:147-173 / 1073-1100):
+    X = stack([t broadcast, A], -1) -> backward_hermite_coefficients -> (d,c,b,a),
+    each [T-1, n, n, 2] with the LAST axis interleaved (time, adjacency)."""
+    t_index = ts.to(A.dtype)[:, None, None].expand(A.shape[0], A.shape[1], A.shape[2])
+    X = torch.stack([t_index, A], dim=-1)
+    return backward_hermite_coefficients(ts, X)
+
+
+def reference_layout_xcoeffs(ts: torch.Tensor, x_t: torch.Tensor):
+    """get_interpolation_coeffs for node signals (dataset_configs.py:1073-1100):
+    x_t [T, n, e] -> (d,c,b,a) each [T-1, n, e, 2]."""
+    t_index = ts.to(x_t.dtype)[:, None, None].expand(x_t.shape[0], x_t.shape[1], x_t.shape[2])
+    X = torch.stack([t_index, x_t], dim=-1)
+    return backward_hermite_coefficients(ts, X)
+
+
+@dataclass
+class Problem:
+    """One graph trajectory worth of hot-path inputs, in the reference's layouts."""
+
+    n: int
+    h: int
+    e: int  # 0 = no control wrapper
+    L: int
+    ts: torch.Tensor  # [T]
+    coeffs_adj: tuple  # (d,c,b,a) each [T-1,n,n,2]
+    x_coeffs: Optional[tuple]  # (d,c,b,a) each [T-1,n,e,2] or None
+    y0: torch.Tensor  # [n,h]
+    layers: List[LayerParams]
+    step_ts: np.ndarray  # [S+1] fp32
+    gyT: torch.Tensor  # cotangent [n,h]
+
+
+def make_problem(n, h, e, L, T, t1, dt0, seed, dtype=torch.float32, scale=1.0, randomize_norm=True, float_ts=False, x_scale=0.3) -> Problem:
+    g = torch.Generator().manual_seed(seed + 17)
+    if float_ts:
+        ts = torch.linspace(0.0, float(t1), T, dtype=torch.float64)
+    else:
+        ts = torch.arange(T, dtype=torch.float64) * (float(t1) / (T - 1))
+    A = torch.from_numpy(synthetic_graph_path(n, T, seed, scale=scale))
+    coeffs_adj = tuple(c.to(dtype) for c in reference_layout_coeffs(ts, A))
+    x_coeffs = None
+    if e > 0:
+        x_t = x_scale * torch.randn((T, n, e), generator=g, dtype=torch.float64)
+        x_coeffs = tuple(c.to(dtype) for c in reference_layout_xcoeffs(ts, x_t))
+    y0 = torch.randn((n, h), generator=g, dtype=torch.float64).to(dtype)
+    gyT = torch.randn((n, h), generator=g, dtype=torch.float64).to(dtype)
+    widths = layer_widths(h, L, e, e > 0)
+    layers = init_params(widths, seed, dtype=dtype, randomize_norm=randomize_norm)
+    step_ts = constant_step_table(float(ts[0]), float(ts[-1]), dt0)
+    return Problem(n, h, e, L, ts.to(dtype), coeffs_adj, x_coeffs, y0, layers, step_ts, gyT)
+
+
+def problem_to(p: Problem, dtype) -> Problem:
+    return Problem(
+        p.n, p.h, p.e, p.L, p.ts.to(dtype), tuple(c.to(dtype) for c in p.coeffs_adj),
+        None if p.x_coeffs is None else tuple(c.to(dtype) for c in p.x_coeffs),
+        p.y0.to(dtype), params_to(p.layers, dtype), p.step_ts, p.gyT.to(dtype),
+    )
+
+
+def run_forward(p: Problem, save_all=False):
+    return solve_cde(p.step_ts, p.ts, p.coeffs_adj, p.x_coeffs, p.y0, p.layers, p.h, p.e, save_all=save_all)
+
+
+def run_forward_backward(p: Problem):
+    """y_T, and the exact discrete-adjoint gradients of <gyT, y_T> w.r.t. y0 and every
+    parameter leaf (what eqx.filter_value_and_grad returns through diffrax's default
+    RecursiveCheckpointAdjoint)."""
+    layers = params_to(p.layers, requires_grad=True)
+    y0 = p.y0.detach().clone().requires_grad_(True)
+    yT = solve_cde(p.step_ts, p.ts, p.coeffs_adj, p.x_coeffs, y0, layers, p.h, p.e)
+    (yT * p.gyT).sum().backward()
+    grads = [[t.grad if t.grad is not None else torch.zeros_like(t) for t in lp.tensors()] for lp in layers]
+    return yT.detach(), y0.grad, grads

@@ -1,0 +1,16 @@
+"""B200-native (sm_100a) hot path of hits-mli/perm-equiv-graph-neural-cdes.
+
+The package holds only what the path needs: the CUDA kernels + C-ABI (``csrc/``, built into
+``libpegncde.so``) and the host-side mirror of the reference's vector-field / solve interface.
+Importing it fails loudly when the CUDA extension has not been built -- there is no CPU fallback.
+"""
+from ._lib import LIB_PATH, PegControl, PegDims, PegError, lib  # noqa: F401
+
+lib()  # raise ImportError right here if libpegncde.so is missing
+
+from .control import CubicInterpolation, PackedControl, backward_hermite_coefficients, pack_control, pack_planar  # noqa: E402,F401
+from .models import MLP, GraphNeuralCDE, PGTGraphNeuralCDE  # noqa: E402,F401
+from .solve import ConstantStepSize, ODETerm, SaveAt, Solution, Tsit5, constant_step_table, diffeqsolve, tsit5_step  # noqa: E402,F401
+from .vector_field import CDEWrapperVectorField, ConvEquivFusionLayer, ConvLayer, PermEquivGraphVectorField  # noqa: E402,F401
+
+__version__ = "0.1.0"

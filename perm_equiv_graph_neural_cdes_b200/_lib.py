@@ -1,0 +1,86 @@
+"""ctypes binding of ``libpegncde.so`` (the C-ABI declared in ``include/pegncde.h``).
+
+There is NO fallback: if the shared library is missing the import of this module raises,
+and every compute entry point raises :class:`PegError` on a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpegncde.so")
+
+PEG_FLAG_TENSOR_CORES = 1
+PEG_FLAG_TF32_FAST = 2
+PEG_FLAG_STORE_STAGES = 4
+
+PEG_WS_VF_FWD, PEG_WS_VF_VJP, PEG_WS_SOLVE_FWD, PEG_WS_SOLVE_BWD, PEG_WS_STEP = range(5)
+
+
+class PegDims(Structure):
+    _fields_ = [(k, c_int32) for k in ("B", "n", "ldn", "h", "e", "L", "T", "flags")]
+
+
+class PegControl(Structure):
+    _fields_ = [(k, c_void_p) for k in ("ts", "adj_coef", "adj_rowsum", "adj_diag", "adj_total", "tch_coef", "x_coef")]
+
+
+class PegError(RuntimeError):
+    def __init__(self, code: int, where: str):
+        self.code = code
+        msg = lib().pegncde_strerror(code).decode()
+        extra = ""
+        if code == 4:
+            extra = f" [cudaError {lib().pegncde_last_cuda_error()}]"
+        super().__init__(f"{where}: pegncde error {code}: {msg}{extra}")
+
+
+_lib = None
+
+# name -> (restype, argtypes); mirrors include/pegncde.h one to one
+_P = c_void_p
+_DIMS = POINTER(PegDims)
+_CTL = POINTER(PegControl)
+SIGNATURES = {
+    "pegncde_param_count": (c_size_t, [_DIMS]),
+    "pegncde_param_offsets": (c_int, [_DIMS, POINTER(c_int64)]),
+    "pegncde_pack_adj": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pegncde_adj_stats": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P]),
+    "pegncde_pack_x": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P]),
+    "pegncde_workspace_bytes": (c_size_t, [_DIMS, c_int32, c_int32]),
+    "pegncde_vf_fwd": (c_int, [_P, _DIMS, _CTL, _P, c_float, _P, _P, _P, c_size_t]),
+    "pegncde_vf_vjp": (c_int, [_P, _DIMS, _CTL, _P, c_float, _P, _P, _P, _P, _P, _P, c_size_t]),
+    "pegncde_step_fwd": (c_int, [_P, _DIMS, _CTL, _P, c_float, c_float, _P, _P, c_int32, _P, _P, _P, _P, c_size_t]),
+    "pegncde_solve_fwd": (c_int, [_P, _DIMS, _CTL, _P, POINTER(c_float), c_int32, _P, _P, _P, _P, c_size_t]),
+    "pegncde_solve_bwd": (c_int, [_P, _DIMS, _CTL, _P, POINTER(c_float), c_int32, _P, _P, _P, _P, _P, _P, c_size_t]),
+    "pegncde_strerror": (c_char_p, [c_int]),
+    "pegncde_last_cuda_error": (c_int, []),
+    "pegncde_version": (c_char_p, []),
+    "pegncde_launch_count": (c_uint64, []),
+}
+
+
+def lib() -> ctypes.CDLL:
+    """Loads libpegncde.so (built by ``__graft_entry__.build()`` / ``csrc/Makefile``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: the CUDA extension is mandatory (no CPU fallback). "
+                "Build it with `python -c 'import __graft_entry__ as g; g.build()'` or `make -C "
+                "perm_equiv_graph_neural_cdes_b200/csrc`."
+            )
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(code: int, where: str) -> None:
+    if code != 0:
+        raise PegError(code, where)

@@ -1,0 +1,179 @@
+"""Control paths: the host-side mirror of ``diffrax.backward_hermite_coefficients`` /
+``diffrax.CubicInterpolation`` as the reference uses them
+(src/configs/dataset_configs.py:147-173, 1073-1100; src/models/pgt_graph_neural_cde.py:101-107),
+plus the packed planar device layout the kernels consume.
+
+Coefficient tuples keep diffrax's order ``(d, c, b, a)`` and the reference's layout
+``[..., T-1, n, n, 2]`` with the last axis interleaved (time, adjacency).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import PegControl, PegDims, check, lib
+
+
+def backward_hermite_coefficients(ts: torch.Tensor, ys: torch.Tensor) -> Tuple[torch.Tensor, ...]:
+    """``diffrax.backward_hermite_coefficients(ts, ys)`` -> ``(d, c, b, a)``, each ``[T-1, ...]``.
+
+    Elementwise torch ops (runs on whatever device ``ys`` lives on).  Per interval i with
+    dt = t[i+1]-t[i] and secant m_i: a = y_i, b = m_{i-1} (m_0 first), c = 2(m_i-b)/dt, d = -(m_i-b)/dt^2."""
+    ts = ts.to(ys.dtype)
+    dt = (ts[1:] - ts[:-1]).reshape((-1,) + (1,) * (ys.dim() - 1))
+    m = (ys[1:] - ys[:-1]) / dt
+    b = torch.cat([m[:1], m[:-1]], dim=0)
+    a = ys[:-1]
+    c = 2.0 * (m - b) / dt
+    d = -(m - b) / (dt * dt)
+    return d, c, b, a
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+class CubicInterpolation:
+    """Drop-in for ``diffrax.CubicInterpolation(ts, coeffs)`` on the fused path.
+
+    ``coeffs = (d, c, b, a)``; for the adjacency control each is ``[T-1, n, n, 2]`` (or batched
+    ``[B, T-1, n, n, 2]``), for the node-signal control ``[T-1, n, e, 2]``.  ``evaluate`` /
+    ``derivative`` exist for API parity (torch ops on the device); the solver never calls them --
+    it consumes the packed planes built lazily by :meth:`packed_adj` / :meth:`packed_x`.
+    """
+
+    def __init__(self, ts: torch.Tensor, coeffs: Sequence[torch.Tensor]):
+        if isinstance(coeffs, torch.Tensor):  # the PGT trainer passes the 4 arrays stacked (trainer_pgt.py:203)
+            coeffs = tuple(coeffs[i] for i in range(4))
+        self.ts = ts
+        self.d, self.c, self.b, self.a = coeffs
+        self._packed = None
+
+    # -- diffrax API -------------------------------------------------------------------
+    def _interpret_t(self, t):
+        ts = self.ts.to(torch.float32)
+        t = torch.as_tensor(t, dtype=torch.float32, device=ts.device)
+        idx = torch.searchsorted(ts.contiguous(), t, right=False) - 1
+        idx = int(idx.clamp(0, ts.numel() - 2))
+        return idx, t - ts[idx]
+
+    def evaluate(self, t):
+        i, s = self._interpret_t(t)
+        return self.a[i] + s * (self.b[i] + s * (self.c[i] + s * self.d[i]))
+
+    def derivative(self, t):
+        i, s = self._interpret_t(t)
+        return self.b[i] + s * (2.0 * self.c[i] + 3.0 * s * self.d[i])
+
+
+class PackedControl:
+    """Planar device layout of one batch of control paths (``PegControl`` in pegncde.h).
+
+    Built once per batch; owns the device tensors and hands raw pointers to the C-ABI."""
+
+    def __init__(self, B: int, n: int, T: int, e: int, device):
+        self.B, self.n, self.T, self.e = B, n, T, e
+        self.ldn = _pad4(n)
+        f = dict(dtype=torch.float32, device=device)
+        self.ts = torch.empty((B, T), **f)
+        self.adj_coef = torch.empty((B, T - 1, 4, n, self.ldn), **f)
+        self.adj_rowsum = torch.empty((B, T - 1, 4, n), **f)
+        self.adj_diag = torch.empty((B, T - 1, 4, n), **f)
+        self.adj_total = torch.empty((B, T - 1, 4), **f)
+        self.tch_coef = torch.empty((B, T - 1, 3, n), **f)
+        self.x_coef = torch.empty((B, T - 1, 3, n, 2 * e), **f) if e > 0 else None
+
+    def dims(self, h: int, L: int, flags: int = 0) -> PegDims:
+        return PegDims(self.B, self.n, self.ldn, h, self.e, L, self.T, flags)
+
+    def struct(self) -> PegControl:
+        return PegControl(
+            self.ts.data_ptr(), self.adj_coef.data_ptr(), self.adj_rowsum.data_ptr(), self.adj_diag.data_ptr(),
+            self.adj_total.data_ptr(), self.tch_coef.data_ptr(), self.x_coef.data_ptr() if self.x_coef is not None else None,
+        )
+
+    @property
+    def device(self):
+        return self.ts.device
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _as_batched(x: torch.Tensor, nd_unbatched: int) -> torch.Tensor:
+    return x.unsqueeze(0) if x.dim() == nd_unbatched else x
+
+
+def pack_control(
+    ts: torch.Tensor,
+    coeffs_adj: Sequence[torch.Tensor],
+    x_coeffs: Optional[Sequence[torch.Tensor]] = None,
+    device=None,
+) -> PackedControl:
+    """Reference-layout coefficients -> :class:`PackedControl` (runs ``pegncde_pack_adj`` / ``pegncde_pack_x``).
+
+    ``coeffs_adj``: ``(d,c,b,a)`` each ``[T-1,n,n,2]`` or ``[B,T-1,n,n,2]`` (or the 4 stacked on axis 0);
+    ``x_coeffs``: ``(d,c,b,a)`` each ``[T-1,n,e,2]`` or ``[B,T-1,n,e,2]``; ``ts``: ``[T]`` or ``[B,T]``."""
+    if isinstance(coeffs_adj, torch.Tensor):
+        coeffs_adj = tuple(coeffs_adj[i] for i in range(4))
+    if isinstance(x_coeffs, torch.Tensor):
+        x_coeffs = tuple(x_coeffs[i] for i in range(4))
+    device = torch.device(device if device is not None else coeffs_adj[0].device)
+    if device.type != "cuda":
+        raise RuntimeError("pack_control needs a CUDA device: the fused path has no CPU fallback")
+    cad = [_as_batched(c, 4).to(device=device, dtype=torch.float32).contiguous() for c in coeffs_adj]
+    B, Tm1, n = cad[0].shape[0], cad[0].shape[1], cad[0].shape[2]
+    e = 0
+    cx = None
+    if x_coeffs is not None:
+        cx = [_as_batched(c, 4).to(device=device, dtype=torch.float32).contiguous() for c in x_coeffs]
+        e = cx[0].shape[3]
+    pc = PackedControl(B, n, Tm1 + 1, e, device)
+    tsb = _as_batched(ts, 1).to(device=device, dtype=torch.float32)
+    pc.ts.copy_(tsb.expand(B, Tm1 + 1))
+    dims = pc.dims(h=4, L=1)
+    st = _stream_ptr(device)
+    l = lib()
+    check(
+        l.pegncde_pack_adj(st, dims, cad[0].data_ptr(), cad[1].data_ptr(), cad[2].data_ptr(), cad[3].data_ptr(),
+                           pc.adj_coef.data_ptr(), pc.adj_rowsum.data_ptr(), pc.adj_diag.data_ptr(),
+                           pc.adj_total.data_ptr(), pc.tch_coef.data_ptr()),
+        "pegncde_pack_adj",
+    )
+    if cx is not None:
+        check(
+            l.pegncde_pack_x(st, dims, cx[0].data_ptr(), cx[1].data_ptr(), cx[2].data_ptr(), cx[3].data_ptr(),
+                             pc.x_coef.data_ptr()),
+            "pegncde_pack_x",
+        )
+    # keep the sources alive until the pack kernels have run (stream-ordered)
+    pc._keepalive = (cad, cx)
+    return pc
+
+
+def pack_planar(ts: torch.Tensor, planes: torch.Tensor, x_coef: Optional[torch.Tensor] = None) -> PackedControl:
+    """Already-planar adjacency planes ``[B, T-1, 4(a,b,c,d), n, ldn]`` (zero padded) -> PackedControl
+    (statistics via ``pegncde_adj_stats``; time channel d t/dt == 1).  Used by the benchmark's synthetic
+    inputs, which are generated directly on the device in the kernel layout."""
+    device = planes.device
+    B, Tm1, _, n, ldn = planes.shape
+    e = 0 if x_coef is None else x_coef.shape[-1] // 2
+    pc = PackedControl.__new__(PackedControl)
+    pc.B, pc.n, pc.T, pc.e, pc.ldn = B, n, Tm1 + 1, e, ldn
+    f = dict(dtype=torch.float32, device=device)
+    pc.ts = _as_batched(ts, 1).to(**f).expand(B, Tm1 + 1).contiguous()
+    pc.adj_coef = planes.contiguous()
+    pc.adj_rowsum = torch.empty((B, Tm1, 4, n), **f)
+    pc.adj_diag = torch.empty((B, Tm1, 4, n), **f)
+    pc.adj_total = torch.empty((B, Tm1, 4), **f)
+    pc.tch_coef = torch.empty((B, Tm1, 3, n), **f)
+    pc.x_coef = x_coef.contiguous() if x_coef is not None else None
+    check(
+        lib().pegncde_adj_stats(_stream_ptr(device), pc.dims(h=4, L=1), pc.adj_coef.data_ptr(), pc.adj_rowsum.data_ptr(),
+                                pc.adj_diag.data_ptr(), pc.adj_total.data_ptr(), pc.tch_coef.data_ptr()),
+        "pegncde_adj_stats",
+    )
+    return pc

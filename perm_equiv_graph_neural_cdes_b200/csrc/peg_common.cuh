@@ -1,0 +1,113 @@
+// Shared device/host definitions for the pegncde sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/pegncde.h"
+
+#define PEG_MAX_LAYERS 8
+#define PEG_MAX_H 256      // widest hidden state / layer input
+#define PEG_MAX_T 4096
+
+namespace peg {
+
+struct LayerDesc {
+  int din, dout;
+  long long w_off, b_off, nw_off, nb_off, fus_off;  // float offsets into the packed params
+};
+
+struct Model {
+  int L;
+  int P;  // total parameter count
+  int dmax;
+  LayerDesc layer[PEG_MAX_LAYERS];
+};
+
+// Per-graph, per-stage scalars (device, in workspace).  One per graph of the batch.
+struct StageScalars {
+  int interval;     // cubic piece index
+  float s;          // t - ts[interval]
+  float wA[4];      // A_s   = sum_p wA[p] * plane_p   (a,b,c,d) -> (1, s, s^2, s^3)
+  float wD[4];      // A'_s  = sum_p wD[p] * plane_p            -> (0, 1, 2s, 3s^2)
+  float totA, totD; // sum(A_s), sum(A'_s)
+  float kappa[PEG_MAX_LAYERS];  // (p7_0 + p7_1) * totA / n^2   (reference quirk: both use sum(A))
+  float pad[2];
+};
+
+// Per-graph stage vectors live in one float array `svec` laid out as
+//   [b][ (3*L + 1) * n + n * 2e ]  =  v_l[n], r_l[n], c_l[n] for l < L ; tg[n] ; xd[n, 2e]
+// plus rA, rD, dgA, dgD [4][n] (needed by the fusion-parameter gradients).
+__host__ __device__ inline size_t svec_stride(int n, int L, int e) {
+  return (size_t)(3 * L + 1 + 4) * n + (size_t)n * 2 * e;
+}
+__host__ __device__ inline size_t svec_v(int n, int l) { return (size_t)(3 * l + 0) * n; }
+__host__ __device__ inline size_t svec_r(int n, int l) { return (size_t)(3 * l + 1) * n; }
+__host__ __device__ inline size_t svec_c(int n, int l) { return (size_t)(3 * l + 2) * n; }
+__host__ __device__ inline size_t svec_tg(int n, int L) { return (size_t)(3 * L) * n; }
+__host__ __device__ inline size_t svec_rA(int n, int L) { return (size_t)(3 * L + 1) * n; }
+__host__ __device__ inline size_t svec_rD(int n, int L) { return (size_t)(3 * L + 2) * n; }
+__host__ __device__ inline size_t svec_dgA(int n, int L) { return (size_t)(3 * L + 3) * n; }
+__host__ __device__ inline size_t svec_dgD(int n, int L) { return (size_t)(3 * L + 4) * n; }
+__host__ __device__ inline size_t svec_xd(int n, int L) { return (size_t)(3 * L + 5) * n; }
+
+// Tsit5 tableau (Tsitouras 2011) -- the tableau behind diffrax.Tsit5.
+struct Tsit5 {
+  double c[7];
+  double a[7][6];
+  double b[7];
+  double berr[7];
+};
+inline const Tsit5& tsit5() {
+  static const Tsit5 t = {
+      {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0},
+      {{0, 0, 0, 0, 0, 0},
+       {0.161, 0, 0, 0, 0, 0},
+       {-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0},
+       {2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0, 0},
+       {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0, 0},
+       {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0},
+       {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081,
+        2.324710524099774}},
+      {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774,
+       0.0},
+      {-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
+       0.5823571654525552, -0.45808210592918697, 0.015151515151515152}};
+  return t;
+}
+
+// arguments of the matrix-free contraction (CUDA-core kernel in peg_kernels.cuh, tcgen05 kernel in peg_tc.cu)
+struct ContractArgs {
+  const float* planes;   // adj_coef
+  size_t graph_stride;   // floats per graph = (T-1)*4*n*ldn
+  const StageScalars* sc;
+  const float* svec;
+  size_t sv_stride;
+  size_t rowc_off;       // offset in svec of the per-row coefficient of (1^T V): r_l (fwd) / c_l (bwd)
+  size_t v_off;          // offset of v_l
+  size_t tg_off;
+  const float* fus;      // 16 fusion scalars of this layer
+  const float* V;        // [B,n,d]
+  const float* Mref;     // bwd only: M_l [B,n,d]
+  const float* colbuf;   // [B][2][d]
+  float* out;            // [B,n,d]
+  float* g_fus;          // bwd only: gradient of the 16 fusion scalars (atomicAdd)
+  int n, ldn, d, layer;
+  int relu, scale_tg;
+};
+
+struct Bump {
+  char* base;
+  size_t off;
+  explicit Bump(void* p) : base((char*)p), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* r = base ? (T*)(base + off) : nullptr;
+    off += count * sizeof(T);
+    return r;
+  }
+};
+
+
+}  // namespace peg

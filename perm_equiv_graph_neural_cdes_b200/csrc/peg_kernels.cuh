@@ -1,0 +1,790 @@
+// CUDA-core (fp32 FFMA) kernels of the pegncde hot path.  These are the exact-fp32
+// building blocks; the n x n x d contraction additionally has a tcgen05 (tensor-core)
+// implementation in peg_tc.cu that replaces k_dual_contract when PEG_FLAG_TENSOR_CORES
+// is set and the shape is large enough to be a real dense contraction.
+#pragma once
+#include "peg_common.cuh"
+
+namespace peg {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sum over the whole block (blockDim.x * blockDim.y threads, multiple of 32, <= 1024); result valid in all threads
+__device__ __forceinline__ float block_sum(float v, float* sh /* >= 33 floats */) {
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nw = (blockDim.x * blockDim.y + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if ((tid & 31) == 0) sh[tid >> 5] = v;
+  __syncthreads();
+  if (tid < 32) {
+    float x = tid < nw ? sh[tid] : 0.f;
+    x = warp_sum(x);
+    if (tid == 0) sh[32] = x;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+// =====================================================================================
+// control-path packing (pre-pass, once per batch)
+// reference layout: d,c,b,a each [B, T-1, n, n, 2], last axis (time, adjacency)
+// =====================================================================================
+
+// grid (ceil(n/64), T-1, B), block 256: one warp per row, 8 rows per warp
+__global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, const float* __restrict__ cc,
+                                                  const float* __restrict__ cb, const float* __restrict__ ca,
+                                                  const float* __restrict__ planar_in, int n, int ldn, int Tm1,
+                                                  float* __restrict__ adj_coef, float* __restrict__ rowsum,
+                                                  float* __restrict__ diag, float* __restrict__ total) {
+  const int b = blockIdx.z, iv = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t slab = ((size_t)b * Tm1 + iv);
+  const float* src[4] = {ca, cb, cc, cd};  // (a,b,c,d) order
+  float tot[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int q = 0; q < 8; ++q) {
+    const int r = blockIdx.x * 64 + q * 8 + warp;
+    if (r >= n) break;
+    float rs[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = lane; j < ldn; j += 32) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        float v = 0.f;
+        const size_t po = ((slab * 4 + p) * n + r) * (size_t)ldn + j;
+        if (j < n) {
+          if (planar_in) {
+            v = planar_in[po];
+          } else {
+            const float2 tv = reinterpret_cast<const float2*>(src[p])[(slab * n + r) * (size_t)n + j];
+            v = tv.y;
+          }
+          rs[p] += v;
+          if (j == r) diag[(slab * 4 + p) * n + r] = v;
+        }
+        if (!planar_in) adj_coef[po] = v;
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      rs[p] = warp_sum(rs[p]);
+      if (lane == 0) rowsum[(slab * 4 + p) * n + r] = rs[p];
+      tot[p] += rs[p];
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) atomicAdd(&total[slab * 4 + p], tot[p]);
+  }
+}
+
+// time channel: tch[b,iv,p,j] = mean_i coef_p[b,iv,i,j,0], p in (b,c,d).  grid (ceil(n/256), T-1, B)
+__global__ void __launch_bounds__(256) k_pack_tch(const float* __restrict__ cd, const float* __restrict__ cc,
+                                                  const float* __restrict__ cb, int n, int Tm1,
+                                                  float* __restrict__ tch) {
+  const int b = blockIdx.z, iv = blockIdx.y;
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= n) return;
+  const size_t slab = ((size_t)b * Tm1 + iv);
+  const float* src[3] = {cb, cc, cd};
+  for (int p = 0; p < 3; ++p) {
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) acc += src[p][((slab * n + i) * (size_t)n + j) * 2];
+    tch[(slab * 3 + p) * n + j] = acc / (float)n;
+  }
+}
+
+__global__ void k_fill_tch_unit(float* __restrict__ tch, int n, size_t slabs) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= slabs * 3 * n) return;
+  const int p = (idx / n) % 3;
+  tch[idx] = p == 0 ? 1.f : 0.f;
+}
+
+// x coeffs: d,c,b,a each [B,T-1,n,e,2] -> x_coef [B,T-1,3,n,2e] (b,c,d)
+__global__ void k_pack_x(const float* __restrict__ cd, const float* __restrict__ cc, const float* __restrict__ cb,
+                         int n, int e2, size_t slabs, float* __restrict__ x_coef) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t per = (size_t)n * e2;
+  if (idx >= slabs * per) return;
+  const size_t slab = idx / per, r = idx % per;
+  x_coef[(slab * 3 + 0) * per + r] = cb[idx];
+  x_coef[(slab * 3 + 1) * per + r] = cc[idx];
+  x_coef[(slab * 3 + 2) * per + r] = cd[idx];
+}
+
+// =====================================================================================
+// per-stage scalars and O(n) vectors (control interpolation of everything that is not
+// the n x n planes themselves: row sums, diagonals, totals are linear in the planes)
+// =====================================================================================
+struct PrepArgs {
+  PegControl ctl;
+  const float* params;
+  Model model;
+  int B, n, e, T;
+  float t;
+  StageScalars* sc;
+  float* svec;
+};
+
+__global__ void __launch_bounds__(256) k_stage_prep(PrepArgs a) {
+  __shared__ float sh[40];
+  __shared__ StageScalars S;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = a.n, L = a.model.L, Tm1 = a.T - 1;
+  const float* ts = a.ctl.ts + (size_t)b * a.T;
+  // index = clip(searchsorted(ts, t, 'left') - 1, 0, T-2)  (diffrax CubicInterpolation._interpret_t)
+  float cnt = 0.f;
+  for (int i = tid; i < a.T; i += blockDim.x) cnt += (ts[i] < a.t) ? 1.f : 0.f;
+  cnt = block_sum(cnt, sh);
+  int iv = (int)(cnt + 0.5f) - 1;
+  iv = max(0, min(iv, a.T - 2));
+  const float s = a.t - ts[iv];
+  const float wA[4] = {1.f, s, s * s, s * s * s};
+  const float wD[4] = {0.f, 1.f, 2.f * s, 3.f * s * s};
+  const size_t slab = (size_t)b * Tm1 + iv;
+  const float* tot = a.ctl.adj_total + slab * 4;
+  const float totA = wA[0] * tot[0] + wA[1] * tot[1] + wA[2] * tot[2] + wA[3] * tot[3];
+  const float totD = wD[1] * tot[1] + wD[2] * tot[2] + wD[3] * tot[3];
+  const float inv_n = 1.f / (float)n, inv_n2 = inv_n * inv_n;
+  if (tid == 0) {
+    S.interval = iv;
+    S.s = s;
+    for (int p = 0; p < 4; ++p) { S.wA[p] = wA[p]; S.wD[p] = wD[p]; }
+    S.totA = totA;
+    S.totD = totD;
+    for (int l = 0; l < L; ++l) {
+      const float* f = a.params + a.model.layer[l].fus_off;
+      S.kappa[l] = (f[12] + f[13]) * totA * inv_n2;
+    }
+    a.sc[b] = S;
+  }
+  float* sv = a.svec + (size_t)b * svec_stride(n, L, a.e);
+  const float* rs = a.ctl.adj_rowsum + slab * 4 * n;
+  const float* dg = a.ctl.adj_diag + slab * 4 * n;
+  const float* tc = a.ctl.tch_coef + slab * 3 * n;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const float rA = wA[0] * rs[i] + wA[1] * rs[n + i] + wA[2] * rs[2 * n + i] + wA[3] * rs[3 * n + i];
+    const float rD = wD[1] * rs[n + i] + wD[2] * rs[2 * n + i] + wD[3] * rs[3 * n + i];
+    const float dA = wA[0] * dg[i] + wA[1] * dg[n + i] + wA[2] * dg[2 * n + i] + wA[3] * dg[3 * n + i];
+    const float dD = wD[1] * dg[n + i] + wD[2] * dg[2 * n + i] + wD[3] * dg[3 * n + i];
+    sv[svec_rA(n, L) + i] = rA;
+    sv[svec_rD(n, L) + i] = rD;
+    sv[svec_dgA(n, L) + i] = dA;
+    sv[svec_dgD(n, L) + i] = dD;
+    for (int l = 0; l < L; ++l) {
+      const float* f = a.params + a.model.layer[l].fus_off;
+      sv[svec_v(n, l) + i] = f[4] * dA + f[5] * dD + (f[10] * rA + f[11] * rD) * inv_n + (f[14] * totA + f[15] * totD) * inv_n2;
+      sv[svec_r(n, l) + i] = (f[6] * rA + f[7] * rD) * inv_n;
+      sv[svec_c(n, l) + i] = (f[8] * rA + f[9] * rD) * inv_n;
+    }
+    sv[svec_tg(n, L) + i] = tc[i] + s * (2.f * tc[n + i] + 3.f * s * tc[2 * n + i]);
+  }
+  if (a.e > 0) {
+    const int e2 = 2 * a.e;
+    const size_t per = (size_t)n * e2;
+    const float* xc = a.ctl.x_coef + slab * 3 * per;
+    for (size_t i = tid; i < per; i += blockDim.x)
+      sv[svec_xd(n, L) + i] = xc[i] + s * (2.f * xc[per + i] + 3.f * s * xc[2 * per + i]);
+  }
+}
+
+// =====================================================================================
+// Runge-Kutta linear combinations: out = sum_j c[j] * x[j]   (stage inputs, y update,
+// adjoint stage cotangents).  float4-vectorised; count multiple of 4.
+// =====================================================================================
+struct CombArgs {
+  const float* x[8];
+  float c[8];
+  int cnt;
+  float* out;
+  size_t count4;
+};
+__global__ void __launch_bounds__(256) k_rk_combine(CombArgs a) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.count4) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < a.cnt) {
+      const float4 v = reinterpret_cast<const float4*>(a.x[j])[i];
+      const float c = a.c[j];
+      acc.x = fmaf(c, v.x, acc.x);
+      acc.y = fmaf(c, v.y, acc.y);
+      acc.z = fmaf(c, v.z, acc.z);
+      acc.w = fmaf(c, v.w, acc.w);
+    }
+  }
+  reinterpret_cast<float4*>(a.out)[i] = acc;
+}
+
+// =====================================================================================
+// RMSNorm -> Linear  (layers.py:45-46): M = (w_n * z * rsqrt(mean z^2 + eps) + b_n) W^T + b
+// grid (ceil(n/32), ceil(dout/64), B), block 256, dyn smem 32*(din+1) + 64*33 floats
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_norm_linear(const float* __restrict__ Z, int n, int din, int dout,
+                                                     const float* __restrict__ W, const float* __restrict__ bias,
+                                                     const float* __restrict__ nw, const float* __restrict__ nb,
+                                                     float* __restrict__ M, float* __restrict__ Nout) {
+  extern __shared__ float smem[];
+  const int zs_ld = din + 1;
+  float* zs = smem;                 // [32][din+1]
+  float* ws = smem + 32 * zs_ld;    // [64][33]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z, node0 = blockIdx.x * 32, o0 = blockIdx.y * 64;
+  const float* Zb = Z + (size_t)b * n * din;
+  for (int idx = tid; idx < 32 * din; idx += 256) {
+    const int r = idx / din, c = idx - r * din;
+    zs[r * zs_ld + c] = (node0 + r < n) ? Zb[(size_t)(node0 + r) * din + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int r = warp * 4 + rr;
+    float ss = 0.f;
+    for (int c = lane; c < din; c += 32) { const float z = zs[r * zs_ld + c]; ss = fmaf(z, z, ss); }
+    ss = warp_sum(ss);
+    const float rinv = rsqrtf(ss / (float)din + 1e-5f);
+    for (int c = lane; c < din; c += 32) zs[r * zs_ld + c] = zs[r * zs_ld + c] * rinv * nw[c] + nb[c];
+  }
+  __syncthreads();
+  if (Nout != nullptr && blockIdx.y == 0) {
+    float* Nb = Nout + (size_t)b * n * din;
+    for (int idx = tid; idx < 32 * din; idx += 256) {
+      const int r = idx / din, c = idx - r * din;
+      if (node0 + r < n) Nb[(size_t)(node0 + r) * din + c] = zs[r * zs_ld + c];
+    }
+  }
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < din; k0 += 32) {
+    for (int idx = tid; idx < 64 * 32; idx += 256) {
+      const int o = idx >> 5, k = idx & 31;
+      ws[o * 33 + k] = (o0 + o < dout && k0 + k < din) ? W[(size_t)(o0 + o) * din + k0 + k] : 0.f;
+    }
+    __syncthreads();
+    const int kmax = min(32, din - k0);
+    for (int k = 0; k < kmax; ++k) {
+      const float z0 = zs[(ty * 2) * zs_ld + k0 + k], z1 = zs[(ty * 2 + 1) * zs_ld + k0 + k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float w = ws[(tx * 4 + j) * 33 + k];
+        acc[0][j] = fmaf(z0, w, acc[0][j]);
+        acc[1][j] = fmaf(z1, w, acc[1][j]);
+      }
+    }
+    __syncthreads();
+  }
+  float* Mb = M + (size_t)b * n * dout;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int node = node0 + ty * 2 + i;
+    if (node >= n) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int o = o0 + tx * 4 + j;
+      if (o < dout) Mb[(size_t)node * dout + o] = acc[i][j] + bias[o];
+    }
+  }
+}
+
+// =====================================================================================
+// column reductions: cb[b][0][c] = sum_i V[b,i,c] ; cb[b][1][c] = sum_i vec[b][i] V[b,i,c]
+// grid (ceil(d/32), B), block (32, 8)
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_colsums(const float* __restrict__ V, int n, int d,
+                                                 const float* __restrict__ vec, size_t vec_stride,
+                                                 float* __restrict__ cb) {
+  __shared__ float s0[8][33], s1[8][33];
+  const int b = blockIdx.y, c = blockIdx.x * 32 + threadIdx.x;
+  const float* Vb = V + (size_t)b * n * d;
+  const float* vb = vec ? vec + (size_t)b * vec_stride : nullptr;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < d) {
+    for (int i = threadIdx.y; i < n; i += 8) {
+      const float v = Vb[(size_t)i * d + c];
+      a0 += v;
+      if (vb) a1 = fmaf(vb[i], v, a1);
+    }
+  }
+  s0[threadIdx.y][threadIdx.x] = a0;
+  s1[threadIdx.y][threadIdx.x] = a1;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < d) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { a0 += s0[k][threadIdx.x]; a1 += s1[k][threadIdx.x]; }
+    cb[((size_t)b * 2 + 0) * d + c] = a0;
+    cb[((size_t)b * 2 + 1) * d + c] = a1;
+  }
+}
+
+// =====================================================================================
+// The matrix-free equivariant contraction (never builds the n x n fused adjacency):
+//   forward  (NACC=1): OUT = V(1+v) + X V + Y^T V + rowc (1^T V) + 1 (vec^T V + kappa 1^T V)
+//       with X = (1+p1_0) A_s + (1+p1_1) A'_s,  Y = p2_0 A_s + p2_1 A'_s   (layers.py:114-160)
+//   backward (NACC=4): separate products A V, A'V, A^T V, A'^T V so the same pass also
+//       yields the Frobenius products that are the gradients of param1 / param2.
+// A_s and A'_s are formed on the fly from the four cubic-coefficient planes.
+// grid (ceil(n/64), ceil(d/64), B), block 256; thread tile 4x4
+// =====================================================================================
+
+constexpr int CT_TI = 64, CT_TC = 64, CT_KC = 16, CT_LD = CT_TI + 4;
+
+template <int NACC>
+__global__ void __launch_bounds__(256) k_dual_contract(ContractArgs a) {
+  constexpr int NS = (NACC == 1) ? 2 : 4;
+  __shared__ __align__(16) float S[NS][CT_KC][CT_LD];
+  __shared__ __align__(16) float Vs[CT_KC][CT_TC];
+  __shared__ float red[40];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z, i0 = blockIdx.x * CT_TI, c0 = blockIdx.y * CT_TC;
+  const int n = a.n, ldn = a.ldn, d = a.d;
+  const StageScalars sc = a.sc[b];
+  const float alpha = 1.f + a.fus[0], beta = 1.f + a.fus[1], gamma = a.fus[2], delta = a.fus[3];
+  float wx[4], wy[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    if (NACC == 1) {
+      wx[p] = alpha * sc.wA[p] + beta * sc.wD[p];
+      wy[p] = gamma * sc.wA[p] + delta * sc.wD[p];
+    } else {
+      wx[p] = sc.wA[p];
+      wy[p] = sc.wD[p];
+    }
+  }
+  const float* P = a.planes + (size_t)b * a.graph_stride + (size_t)sc.interval * 4 * n * ldn;
+  const size_t pstride = (size_t)n * ldn;
+  const float* Vb = a.V + (size_t)b * n * d;
+
+  float acc[NACC][4][4];
+#pragma unroll
+  for (int q = 0; q < NACC; ++q)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[q][i][j] = 0.f;
+
+  const int ty = tid >> 4, tx = tid & 15;
+  // direct tile: element (row i, col k);  transposed tile: element (row k, col i)
+  const int drow = tid >> 2, dkq = tid & 3;
+  const int tkr = tid >> 4, tiq = tid & 15;
+
+  for (int k0 = 0; k0 < n; k0 += CT_KC) {
+    {  // direct part
+      const int gi = i0 + drow, gk = k0 + 4 * dkq;
+      float4 p[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) p[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gi < n && gk < ldn) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) p[q] = *reinterpret_cast<const float4*>(P + q * pstride + (size_t)gi * ldn + gk);
+      }
+      float x0[4], x1[4];
+      const float* pf = reinterpret_cast<const float*>(p);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = (gk + j) < n;
+        const float e0 = pf[0 * 4 + j], e1 = pf[1 * 4 + j], e2 = pf[2 * 4 + j], e3 = pf[3 * 4 + j];
+        x0[j] = ok ? (wx[0] * e0 + wx[1] * e1 + wx[2] * e2 + wx[3] * e3) : 0.f;
+        x1[j] = ok ? (wy[0] * e0 + wy[1] * e1 + wy[2] * e2 + wy[3] * e3) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        S[0][4 * dkq + j][drow] = x0[j];
+        if (NACC == 4) S[1][4 * dkq + j][drow] = x1[j];
+      }
+    }
+    {  // transposed part
+      const int gk = k0 + tkr, gi = i0 + 4 * tiq;
+      float4 p[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) p[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gk < n && gi < ldn) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) p[q] = *reinterpret_cast<const float4*>(P + q * pstride + (size_t)gk * ldn + gi);
+      }
+      const float* pf = reinterpret_cast<const float*>(p);
+      float y0[4], y1[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = (gi + j) < n;
+        const float e0 = pf[0 * 4 + j], e1 = pf[1 * 4 + j], e2 = pf[2 * 4 + j], e3 = pf[3 * 4 + j];
+        if (NACC == 1) {
+          y0[j] = ok ? (wy[0] * e0 + wy[1] * e1 + wy[2] * e2 + wy[3] * e3) : 0.f;
+          y1[j] = 0.f;
+        } else {
+          y0[j] = ok ? (wx[0] * e0 + wx[1] * e1 + wx[2] * e2 + wx[3] * e3) : 0.f;
+          y1[j] = ok ? (wy[0] * e0 + wy[1] * e1 + wy[2] * e2 + wy[3] * e3) : 0.f;
+        }
+      }
+      *reinterpret_cast<float4*>(&S[NS / 2][tkr][4 * tiq]) = make_float4(y0[0], y0[1], y0[2], y0[3]);
+      if (NACC == 4) *reinterpret_cast<float4*>(&S[3][tkr][4 * tiq]) = make_float4(y1[0], y1[1], y1[2], y1[3]);
+    }
+    {  // V chunk
+      const int gk = k0 + tkr, gc = c0 + 4 * tiq;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gk < n && gc < d) v = *reinterpret_cast<const float4*>(Vb + (size_t)gk * d + gc);
+      *reinterpret_cast<float4*>(&Vs[tkr][4 * tiq]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < CT_KC; ++k) {
+      const float4 v4 = *reinterpret_cast<const float4*>(&Vs[k][4 * tx]);
+      const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+      if (NACC == 1) {
+        const float4 s0 = *reinterpret_cast<const float4*>(&S[0][k][4 * ty]);
+        const float4 s1 = *reinterpret_cast<const float4*>(&S[1][k][4 * ty]);
+        const float aa[4] = {s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[0][i][j] = fmaf(aa[i], vv[j], acc[0][i][j]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < NACC; ++q) {
+          const float4 s0 = *reinterpret_cast<const float4*>(&S[q][k][4 * ty]);
+          const float aa[4] = {s0.x, s0.y, s0.z, s0.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[q][i][j] = fmaf(aa[i], vv[j], acc[q][i][j]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue ----
+  const float* sv = a.svec + (size_t)b * a.sv_stride;
+  const float* cb0 = a.colbuf + ((size_t)b * 2 + 0) * d;
+  const float* cb1 = a.colbuf + ((size_t)b * 2 + 1) * d;
+  const float kappa = sc.kappa[a.layer];
+  const int gc = c0 + 4 * tx;
+  float g4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (gc < d) {
+    const float4 s4 = *reinterpret_cast<const float4*>(cb0 + gc);
+    const float4 t4 = *reinterpret_cast<const float4*>(cb1 + gc);
+    const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gi = i0 + 4 * ty + i;
+      if (gi >= n) continue;
+      const float vi = 1.f + sv[a.v_off + gi];
+      const float rc = sv[a.rowc_off + gi];
+      const float tg = a.scale_tg ? sv[a.tg_off + gi] : 1.f;
+      const float4 vin = *reinterpret_cast<const float4*>(Vb + (size_t)gi * d + gc);
+      const float vv[4] = {vin.x, vin.y, vin.z, vin.w};
+      float o[4];
+      if (NACC == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float val = vv[j] * vi + acc[0][i][j] + rc * ss[j] + tt[j] + kappa * ss[j];
+          if (a.relu) val = fmaxf(val, 0.f);
+          o[j] = val * tg;
+        }
+      } else {
+        const float4 m4 = *reinterpret_cast<const float4*>(a.Mref + ((size_t)b * n + gi) * d + gc);
+        const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // acc[0]=A V, acc[1]=A'V, acc[2]=A^T V, acc[3]=A'^T V   (V = cotangent of the layer output)
+          o[j] = vv[j] * vi + alpha * acc[2][i][j] + beta * acc[3][i][j] + gamma * acc[0][i][j] +
+                 delta * acc[1][i][j] + rc * ss[j] + tt[j] + kappa * ss[j];
+          g4[0] = fmaf(acc[2][i][j], mm[j], g4[0]);  // d/d param1[0] = <A^T g, M>
+          g4[1] = fmaf(acc[3][i][j], mm[j], g4[1]);  // d/d param1[1] = <A'^T g, M>
+          g4[2] = fmaf(acc[0][i][j], mm[j], g4[2]);  // d/d param2[0] = <A g, M>
+          g4[3] = fmaf(acc[1][i][j], mm[j], g4[3]);  // d/d param2[1] = <A' g, M>
+        }
+      }
+      *reinterpret_cast<float4*>(a.out + ((size_t)b * n + gi) * d + gc) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  if (NACC == 4) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float t = block_sum(g4[q], red);
+      if (tid == 0) atomicAdd(a.g_fus + q, t);
+    }
+  }
+}
+
+// =====================================================================================
+// CDE wrapper (cde_wrapper_vector_field.py:21-25): dy[n,m] = sum_j out[n, m*2e + j] xd[n, j]
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_wrapper_fwd(const float* __restrict__ OL, const float* __restrict__ svec,
+                                                     size_t sv_stride, size_t xd_off, int n, int h, int e2, int B,
+                                                     float* __restrict__ dy) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * n * h) return;
+  const int m = idx % h;
+  const size_t bn = idx / h;
+  const int i = bn % n, b = bn / n;
+  const float* xd = svec + (size_t)b * sv_stride + xd_off + (size_t)i * e2;
+  const float* o = OL + bn * (size_t)h * e2 + (size_t)m * e2;
+  float acc = 0.f;
+  for (int j = 0; j < e2; ++j) acc = fmaf(o[j], xd[j], acc);
+  dy[idx] = acc;
+}
+
+// cotangent of the last layer's output: OLbar[n, m*2e+j] = tg_n kbar[n,m] xd[n,j]   (e2 == 0: tg_n kbar[n,m])
+__global__ void __launch_bounds__(256) k_wrapper_bwd(const float* __restrict__ kbar, const float* __restrict__ svec,
+                                                     size_t sv_stride, size_t xd_off, size_t tg_off, int n, int h,
+                                                     int e2, int B, float* __restrict__ OLbar) {
+  const int dL = e2 > 0 ? h * e2 : h;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * n * dL) return;
+  const int col = idx % dL;
+  const size_t bn = idx / dL;
+  const int i = bn % n, b = bn / n;
+  const float* sv = svec + (size_t)b * sv_stride;
+  const float tg = sv[tg_off + i];
+  if (e2 > 0) {
+    const int m = col / e2, j = col - m * e2;
+    OLbar[idx] = tg * kbar[bn * h + m] * sv[xd_off + (size_t)i * e2 + j];
+  } else {
+    OLbar[idx] = tg * kbar[idx];
+  }
+}
+
+// cotangent of control_data.derivative(t): g_xd[n,j] = sum_m tg_n kbar[n,m] OL[n, m*2e+j]  (OL = unscaled last-layer output)
+__global__ void __launch_bounds__(256) k_wrapper_xbar(const float* __restrict__ kbar, const float* __restrict__ OLtg,
+                                                      int n, int h, int e2, int B, float* __restrict__ gxd) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * n * e2) return;
+  const int j = idx % e2;
+  const size_t bn = idx / e2;
+  float acc = 0.f;
+  for (int m = 0; m < h; ++m) acc = fmaf(kbar[bn * h + m], OLtg[bn * (size_t)h * e2 + (size_t)m * e2 + j], acc);
+  gxd[idx] = acc;
+}
+
+// =====================================================================================
+// gradients of param3..param8 of one layer: O(n d) dot products against row sums /
+// diagonals / totals.  grid (ceil(n/8), B), block 256 (one warp per node)
+// =====================================================================================
+struct FusGradArgs {
+  const float* G;      // cotangent of the layer output [B,n,d]
+  const float* M;      // [B,n,d]
+  const float* cbM;    // [B][2][d] : [0] = 1^T M
+  const float* cbG;    // [B][2][d] : [0] = 1^T G
+  const StageScalars* sc;
+  const float* svec;
+  size_t sv_stride;
+  int n, d, L;
+  float* g_fus;
+};
+__global__ void __launch_bounds__(256) k_fusion_vec_grads(FusGradArgs a) {
+  __shared__ float sh[8][12];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + warp;
+  const int n = a.n, d = a.d;
+  const float* sv = a.svec + (size_t)b * a.sv_stride;
+  const float* sM = a.cbM + (size_t)b * 2 * d;
+  const float* sG = a.cbG + (size_t)b * 2 * d;
+  float part[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) part[k] = 0.f;
+  if (i < n) {
+    const float* g = a.G + ((size_t)b * n + i) * d;
+    const float* m = a.M + ((size_t)b * n + i) * d;
+    float q = 0.f, u = 0.f, w = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      const float gv = g[c], mv = m[c];
+      q = fmaf(gv, mv, q);
+      u = fmaf(gv, sM[c], u);
+      w = fmaf(mv, sG[c], w);
+    }
+    q = warp_sum(q); u = warp_sum(u); w = warp_sum(w);
+    const float rA = sv[svec_rA(n, a.L) + i], rD = sv[svec_rD(n, a.L) + i];
+    const float dA = sv[svec_dgA(n, a.L) + i], dD = sv[svec_dgD(n, a.L) + i];
+    part[0] = dA * q; part[1] = dD * q;      // param3
+    part[2] = rA * u; part[3] = rD * u;      // param4 (/n)
+    part[4] = rA * w; part[5] = rD * w;      // param5 (/n)
+    part[6] = rA * q; part[7] = rD * q;      // param6 (/n)
+    part[8] = q;                              // param8 (* tot / n^2)
+  }
+  if (blockIdx.x == 0 && warp == 0) {        // param7: tot_A / n^2 * (1^T G . 1^T M), once per graph
+    float t = 0.f;
+    for (int c = lane; c < d; c += 32) t = fmaf(sG[c], sM[c], t);
+    part[9] = warp_sum(t);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) sh[warp][k] = part[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 10) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += sh[w8][threadIdx.x];
+    const StageScalars sc = a.sc[b];
+    const float inv_n = 1.f / (float)n, inv_n2 = inv_n * inv_n;
+    const int k = threadIdx.x;
+    if (k < 2) atomicAdd(a.g_fus + 4 + k, t);
+    else if (k < 4) atomicAdd(a.g_fus + 6 + (k - 2), t * inv_n);
+    else if (k < 6) atomicAdd(a.g_fus + 8 + (k - 4), t * inv_n);
+    else if (k < 8) atomicAdd(a.g_fus + 10 + (k - 6), t * inv_n);
+    else if (k == 8) {
+      atomicAdd(a.g_fus + 14, t * sc.totA * inv_n2);
+      atomicAdd(a.g_fus + 15, t * sc.totD * inv_n2);
+    } else if (blockIdx.x == 0) {
+      atomicAdd(a.g_fus + 12, t * sc.totA * inv_n2);
+      atomicAdd(a.g_fus + 13, t * sc.totA * inv_n2);
+    }
+  }
+}
+
+// =====================================================================================
+// backward of Linear + RMSNorm wrt the layer input (and the norm affine parameters):
+//   Nbar = Mbar W ;  Zbar = rinv w Nbar - z rinv^3 <w Nbar, z>/din ;  optional ReLU mask (z > 0)
+// grid (ceil(n/32), B), block 256 (8 threads per node), dyn smem 32*33 + 32*din + 2*din floats
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_linear_bwd(const float* __restrict__ Mbar, const float* __restrict__ W,
+                                                    const float* __restrict__ Z, const float* __restrict__ nw,
+                                                    int n, int din, int dout, int relu_mask,
+                                                    float* __restrict__ Zbar, float* __restrict__ g_nw,
+                                                    float* __restrict__ g_nb) {
+  extern __shared__ float smem[];
+  float* mb = smem;               // [32][33]
+  float* wsm = smem + 32 * 33;    // [32][din]
+  float* gsw = wsm + 32 * din;    // [din]
+  float* gsb = gsw + din;         // [din]
+  const int tid = threadIdx.x, b = blockIdx.y, node0 = blockIdx.x * 32;
+  const int r = tid >> 3, sub = tid & 7;
+  const int node = node0 + r;
+  constexpr int MAXJ = PEG_MAX_H / 8;
+  float acc[MAXJ];
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) acc[j] = 0.f;
+  for (int c = tid; c < din; c += 256) { gsw[c] = 0.f; gsb[c] = 0.f; }
+  const float* Mb = Mbar + (size_t)b * n * dout;
+  for (int o0 = 0; o0 < dout; o0 += 32) {
+    for (int idx = tid; idx < 32 * 32; idx += 256) {
+      const int rr = idx >> 5, o = idx & 31;
+      mb[rr * 33 + o] = (node0 + rr < n && o0 + o < dout) ? Mb[(size_t)(node0 + rr) * dout + o0 + o] : 0.f;
+    }
+    for (int idx = tid; idx < 32 * din; idx += 256) {
+      const int o = idx / din, c = idx - o * din;
+      wsm[idx] = (o0 + o < dout) ? W[(size_t)(o0 + o) * din + c] : 0.f;
+    }
+    __syncthreads();
+    for (int o = 0; o < 32; ++o) {
+      const float m = mb[r * 33 + o];
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        const int c = sub + 8 * j;
+        if (c < din) acc[j] = fmaf(m, wsm[o * din + c], acc[j]);
+      }
+    }
+    __syncthreads();
+  }
+  // norm backward (8 lanes cooperate per node)
+  float z[MAXJ];
+  float ss = 0.f, dot = 0.f;
+  const float* Zr = Z + ((size_t)b * n + (node < n ? node : 0)) * din;
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) {
+    const int c = sub + 8 * j;
+    z[j] = (c < din && node < n) ? Zr[c] : 0.f;
+    ss = fmaf(z[j], z[j], ss);
+    if (c < din) dot = fmaf(nw[c] * acc[j], z[j], dot);
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  }
+  const float rinv = rsqrtf(ss / (float)din + 1e-5f);
+  const float coef = rinv * rinv * rinv * dot / (float)din;
+  if (node < n) {
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      const int c = sub + 8 * j;
+      if (c < din) {
+        float zb = rinv * nw[c] * acc[j] - z[j] * coef;
+        if (relu_mask && !(z[j] > 0.f)) zb = 0.f;
+        Zbar[((size_t)b * n + node) * din + c] = zb;
+        atomicAdd(&gsw[c], acc[j] * z[j] * rinv);
+        atomicAdd(&gsb[c], acc[j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < din; c += 256) {
+    atomicAdd(g_nw + c, gsw[c]);
+    atomicAdd(g_nb + c, gsb[c]);
+  }
+}
+
+// =====================================================================================
+// weight / bias gradient: Wbar[o][c] += sum_nodes Mbar[node][o] N[node][c] ; bbar[o] += sum Mbar[node][o]
+// nodes = all B*n rows, split over gridDim.z.  grid (ceil(dout/64), ceil(din/64), KS), block 256
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_weight_grad(const float* __restrict__ Mbar, const float* __restrict__ N,
+                                                     size_t rows, int din, int dout, int rows_per_slice,
+                                                     float* __restrict__ gW, float* __restrict__ gb) {
+  __shared__ __align__(16) float ms[16][68];
+  __shared__ __align__(16) float ns[16][68];
+  const int tid = threadIdx.x, o0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const size_t r_begin = (size_t)blockIdx.z * rows_per_slice;
+  const size_t r_end = min(rows, r_begin + (size_t)rows_per_slice);
+  const int ty = tid >> 4, tx = tid & 15;
+  const int lk = tid >> 4, lq = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum = 0.f;
+  for (size_t k0 = r_begin; k0 < r_end; k0 += 16) {
+    const size_t row = k0 + lk;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int o = o0 + 4 * lq + j, c = c0 + 4 * lq + j;
+      ms[lk][4 * lq + j] = (row < r_end && o < dout) ? Mbar[row * dout + o] : 0.f;
+      ns[lk][4 * lq + j] = (row < r_end && c < din) ? N[row * din + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 m4 = *reinterpret_cast<const float4*>(&ms[k][4 * ty]);
+      const float4 n4 = *reinterpret_cast<const float4*>(&ns[k][4 * tx]);
+      const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(mm[i], nn[j], acc[i][j]);
+    }
+    if (blockIdx.y == 0 && tid < 64) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) bsum += ms[k][tid];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int o = o0 + 4 * ty + i;
+    if (o >= dout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + 4 * tx + j;
+      if (c < din) atomicAdd(gW + (size_t)o * din + c, acc[i][j]);
+    }
+  }
+  if (blockIdx.y == 0 && tid < 64 && o0 + tid < dout) atomicAdd(gb + o0 + tid, bsum);
+}
+
+// elementwise ReLU mask on a cotangent: out = (z > 0) ? g : 0
+__global__ void __launch_bounds__(256) k_axpy(float* __restrict__ y, const float* __restrict__ x, float a, size_t cnt) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cnt) y[i] = fmaf(a, x[i], y[i]);
+}
+
+}  // namespace peg

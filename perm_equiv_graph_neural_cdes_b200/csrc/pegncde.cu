@@ -1,0 +1,635 @@
+// C-ABI of the pegncde hot path (see include/pegncde.h).  Host code here only validates,
+// carves the caller's workspace and enqueues kernels on the caller's stream.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "peg_kernels.cuh"
+#include "peg_tc.cuh"
+
+namespace peg {
+
+static std::atomic<uint64_t> g_launches{0};
+static thread_local int g_last_cuda = 0;
+
+#define PEG_LAUNCH_CHECK()                         \
+  do {                                             \
+    g_launches.fetch_add(1);                       \
+    cudaError_t _e = cudaPeekAtLastError();        \
+    if (_e != cudaSuccess) {                       \
+      g_last_cuda = (int)_e;                       \
+      (void)cudaGetLastError();                    \
+      return PEG_ERR_CUDA;                         \
+    }                                              \
+  } while (0)
+
+#define PEG_CUDA(call)                             \
+  do {                                             \
+    cudaError_t _e = (call);                       \
+    if (_e != cudaSuccess) {                       \
+      g_last_cuda = (int)_e;                       \
+      return PEG_ERR_CUDA;                         \
+    }                                              \
+  } while (0)
+
+#define PEG_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != PEG_OK) return _rc; \
+  } while (0)
+
+static inline int last_width(const PegDims& d) { return d.e > 0 ? 2 * d.h * d.e : d.h; }
+
+static int check_dims(const PegDims* d) {
+  if (!d) return PEG_ERR_NULL_POINTER;
+  if (d->B < 1 || d->n < 1 || d->L < 1 || d->L > PEG_MAX_LAYERS || d->T < 2 || d->T > PEG_MAX_T || d->e < 0)
+    return PEG_ERR_BAD_DIMS;
+  if (d->h < 4 || d->h > PEG_MAX_H || (d->h % 4) != 0) return PEG_ERR_BAD_DIMS;
+  if (d->ldn < d->n || (d->ldn % 4) != 0) return PEG_ERR_BAD_DIMS;
+  if ((long long)d->B > 65535) return PEG_ERR_BAD_DIMS;
+  return PEG_OK;
+}
+
+static Model make_model(const PegDims& d) {
+  Model m;
+  memset(&m, 0, sizeof(m));
+  m.L = d.L;
+  long long off = 0;
+  int dmax = d.h;
+  for (int l = 0; l < d.L; ++l) {
+    LayerDesc& ld = m.layer[l];
+    ld.din = d.h;
+    ld.dout = (l == d.L - 1) ? last_width(d) : d.h;
+    dmax = ld.dout > dmax ? ld.dout : dmax;
+    ld.w_off = off;  off += (long long)ld.dout * ld.din;
+    ld.b_off = off;  off += ld.dout;
+    ld.nw_off = off; off += ld.din;
+    ld.nb_off = off; off += ld.din;
+    ld.fus_off = off; off += 16;
+  }
+  m.P = (int)off;
+  m.dmax = dmax;
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------
+// workspace carving
+// ------------------------------------------------------------------------------------------
+struct FevalWs {
+  StageScalars* sc;
+  float* svec;
+  float* colM;   // [B][2][dmax]
+  float* colG;   // [B][2][dmax]
+  float* M;      // [B,n,dmax]
+  float* Za;     // [B,n,h] ping
+  float* Zb;     // [B,n,h] pong
+  float* OL;     // [B,n,dmax] last-layer output (control models)
+  // vjp
+  float* Obar;   // [B,n,dmax]
+  float* Mbar;   // [B,n,dmax]
+  float* N;      // [B,n,h]
+  TcWs tc;       // tensor-core operand buffers (peg_tc.cuh)
+};
+
+static void carve_feval(Bump& bp, const PegDims& d, const Model& m, bool vjp, FevalWs& w) {
+  const size_t B = d.B, n = d.n, h = d.h, dm = m.dmax;
+  w.sc = bp.take<StageScalars>(B);
+  w.svec = bp.take<float>(B * svec_stride(d.n, d.L, d.e));
+  w.colM = bp.take<float>(B * 2 * dm);
+  w.colG = bp.take<float>(B * 2 * dm);
+  w.M = bp.take<float>(B * n * dm);
+  w.Za = bp.take<float>(B * n * h);
+  w.Zb = bp.take<float>(B * n * h);
+  w.OL = d.e > 0 ? bp.take<float>(B * n * dm) : nullptr;
+  if (vjp) {
+    w.Obar = bp.take<float>(B * n * dm);
+    w.Mbar = bp.take<float>(B * n * dm);
+    w.N = bp.take<float>(B * n * h);
+  } else {
+    w.Obar = w.Mbar = w.N = nullptr;
+  }
+  tc_carve(bp, d, m.dmax, w.tc);
+}
+
+struct Ctx {
+  cudaStream_t st;
+  PegDims d;
+  PegControl ctl;
+  const float* params;
+  Model m;
+  FevalWs w;
+  size_t sv_stride;
+  bool use_tc;
+};
+
+// ------------------------------------------------------------------------------------------
+// one vector-field evaluation: dy = f(t, yin)
+//   save[l] (nullable array of L pointers): where to keep the input of layer l (l = 0: yin itself is
+//   the input, nothing is copied; save[l>=1] receives relu(O_l)).
+// ------------------------------------------------------------------------------------------
+static int stage_prep(Ctx& c, float t) {
+  PrepArgs a;
+  a.ctl = c.ctl;
+  a.params = c.params;
+  a.model = c.m;
+  a.B = c.d.B; a.n = c.d.n; a.e = c.d.e; a.T = c.d.T;
+  a.t = t;
+  a.sc = c.w.sc;
+  a.svec = c.w.svec;
+  k_stage_prep<<<c.d.B, 256, 0, c.st>>>(a);
+  PEG_LAUNCH_CHECK();
+  return PEG_OK;
+}
+
+static int norm_linear(Ctx& c, int l, const float* Zin, float* M, float* Nout) {
+  const LayerDesc& ld = c.m.layer[l];
+  dim3 grid((c.d.n + 31) / 32, (ld.dout + 63) / 64, c.d.B);
+  const size_t smem = (size_t)(32 * (ld.din + 1) + 64 * 33) * sizeof(float);
+  k_norm_linear<<<grid, 256, smem, c.st>>>(Zin, c.d.n, ld.din, ld.dout, c.params + ld.w_off, c.params + ld.b_off,
+                                           c.params + ld.nw_off, c.params + ld.nb_off, M, Nout);
+  PEG_LAUNCH_CHECK();
+  return PEG_OK;
+}
+
+static int colsums(Ctx& c, const float* V, int dcols, size_t vec_off, bool with_vec, float* cb) {
+  dim3 grid((dcols + 31) / 32, c.d.B), block(32, 8);
+  k_colsums<<<grid, block, 0, c.st>>>(V, c.d.n, dcols, with_vec ? c.w.svec + vec_off : nullptr, c.sv_stride, cb);
+  PEG_LAUNCH_CHECK();
+  return PEG_OK;
+}
+
+static int contract(Ctx& c, int l, bool bwd, const float* V, const float* Mref, const float* colbuf, float* out,
+                    bool relu, bool scale_tg, float* g_fus) {
+  const LayerDesc& ld = c.m.layer[l];
+  ContractArgs a;
+  a.planes = c.ctl.adj_coef;
+  a.graph_stride = (size_t)(c.d.T - 1) * 4 * c.d.n * c.d.ldn;
+  a.sc = c.w.sc;
+  a.svec = c.w.svec;
+  a.sv_stride = c.sv_stride;
+  a.rowc_off = bwd ? svec_c(c.d.n, l) : svec_r(c.d.n, l);
+  a.v_off = svec_v(c.d.n, l);
+  a.tg_off = svec_tg(c.d.n, c.d.L);
+  a.fus = c.params + ld.fus_off;
+  a.V = V;
+  a.Mref = Mref;
+  a.colbuf = colbuf;
+  a.out = out;
+  a.g_fus = g_fus;
+  a.n = c.d.n; a.ldn = c.d.ldn; a.d = ld.dout; a.layer = l;
+  a.relu = relu ? 1 : 0;
+  a.scale_tg = scale_tg ? 1 : 0;
+  if (c.use_tc && tc_supported(c.d, ld.dout)) {
+    int rc = tc_contract(c.st, c.d, c.w.tc, a, bwd);
+    if (rc == PEG_OK) g_launches.fetch_add(tc_launches_per_contract(bwd));
+    return rc;
+  }
+  dim3 grid((c.d.n + CT_TI - 1) / CT_TI, (ld.dout + CT_TC - 1) / CT_TC, c.d.B);
+  if (!bwd)
+    k_dual_contract<1><<<grid, 256, 0, c.st>>>(a);
+  else
+    k_dual_contract<4><<<grid, 256, 0, c.st>>>(a);
+  PEG_LAUNCH_CHECK();
+  return PEG_OK;
+}
+
+static int feval_fwd(Ctx& c, float t, const float* yin, float* dy, float* const* save, int nlayers = -1) {
+  const PegDims& d = c.d;
+  if (nlayers < 0) nlayers = d.L;
+  PEG_TRY(stage_prep(c, t));
+  const float* Zin = yin;
+  for (int l = 0; l < nlayers; ++l) {
+    const LayerDesc& ld = c.m.layer[l];
+    const bool last = (l == d.L - 1);
+    PEG_TRY(norm_linear(c, l, Zin, c.w.M, nullptr));
+    PEG_TRY(colsums(c, c.w.M, ld.dout, svec_c(d.n, l), true, c.w.colM));
+    float* out;
+    if (!last) {
+      out = (save && save[l + 1]) ? save[l + 1] : ((l & 1) ? c.w.Zb : c.w.Za);
+    } else {
+      out = d.e > 0 ? c.w.OL : dy;
+    }
+    PEG_TRY(contract(c, l, false, c.w.M, nullptr, c.w.colM, out, !last, last, nullptr));
+    Zin = out;
+  }
+  if (d.e > 0 && nlayers == d.L) {
+    const size_t cnt = (size_t)d.B * d.n * d.h;
+    k_wrapper_fwd<<<(unsigned)((cnt + 255) / 256), 256, 0, c.st>>>(c.w.OL, c.w.svec, c.sv_stride,
+                                                                   svec_xd(d.n, d.L), d.n, d.h, 2 * d.e, d.B, dy);
+    PEG_LAUNCH_CHECK();
+  }
+  return PEG_OK;
+}
+
+// VJP of one evaluation.  zin[l] = input of layer l (l = 0..L-1) as saved by feval_fwd.
+// kbar: cotangent of dy.  Writes ybar (cotangent of the stage input), accumulates g_params.
+// If g_xd != null (control models) also writes the cotangent of control_data.derivative(t).
+static int feval_vjp(Ctx& c, float t, float* const* zin, const float* kbar, float* ybar, float* g_params,
+                     float* g_xd) {
+  const PegDims& d = c.d;
+  const int dL = last_width(d);
+  PEG_TRY(stage_prep(c, t));
+  if (g_xd != nullptr) {
+    if (d.e == 0) return PEG_ERR_BAD_DIMS;
+    // recompute the (tg-scaled) last-layer output, then contract it with kbar
+    const int l = d.L - 1;
+    PEG_TRY(norm_linear(c, l, zin[l], c.w.M, nullptr));
+    PEG_TRY(colsums(c, c.w.M, dL, svec_c(d.n, l), true, c.w.colM));
+    PEG_TRY(contract(c, l, false, c.w.M, nullptr, c.w.colM, c.w.OL, false, true, nullptr));
+    const size_t cnt = (size_t)d.B * d.n * 2 * d.e;
+    k_wrapper_xbar<<<(unsigned)((cnt + 255) / 256), 256, 0, c.st>>>(kbar, c.w.OL, d.n, d.h, 2 * d.e, d.B, g_xd);
+    PEG_LAUNCH_CHECK();
+  }
+  {
+    const size_t cnt = (size_t)d.B * d.n * dL;
+    k_wrapper_bwd<<<(unsigned)((cnt + 255) / 256), 256, 0, c.st>>>(kbar, c.w.svec, c.sv_stride, svec_xd(d.n, d.L),
+                                                                   svec_tg(d.n, d.L), d.n, d.h, 2 * d.e, d.B,
+                                                                   c.w.Obar);
+    PEG_LAUNCH_CHECK();
+  }
+  for (int l = d.L - 1; l >= 0; --l) {
+    const LayerDesc& ld = c.m.layer[l];
+    float* g_fus = g_params + ld.fus_off;
+    // recompute M_l (and the normalised input N_l) from the saved layer input
+    PEG_TRY(norm_linear(c, l, zin[l], c.w.M, c.w.N));
+    PEG_TRY(colsums(c, c.w.M, ld.dout, 0, false, c.w.colM));
+    PEG_TRY(colsums(c, c.w.Obar, ld.dout, svec_r(d.n, l), true, c.w.colG));
+    PEG_TRY(contract(c, l, true, c.w.Obar, c.w.M, c.w.colG, c.w.Mbar, false, false, g_fus));
+    {
+      FusGradArgs a;
+      a.G = c.w.Obar; a.M = c.w.M; a.cbM = c.w.colM; a.cbG = c.w.colG;
+      a.sc = c.w.sc; a.svec = c.w.svec; a.sv_stride = c.sv_stride;
+      a.n = d.n; a.d = ld.dout; a.L = d.L; a.g_fus = g_fus;
+      dim3 grid((d.n + 7) / 8, d.B);
+      k_fusion_vec_grads<<<grid, 256, 0, c.st>>>(a);
+      PEG_LAUNCH_CHECK();
+    }
+    {
+      const size_t rows = (size_t)d.B * d.n;
+      const int rps = 512;
+      dim3 grid((ld.dout + 63) / 64, (ld.din + 63) / 64, (unsigned)((rows + rps - 1) / rps));
+      k_weight_grad<<<grid, 256, 0, c.st>>>(c.w.Mbar, c.w.N, rows, ld.din, ld.dout, rps, g_params + ld.w_off,
+                                            g_params + ld.b_off);
+      PEG_LAUNCH_CHECK();
+    }
+    {
+      dim3 grid((d.n + 31) / 32, d.B);
+      const size_t smem = (size_t)(32 * 33 + 32 * ld.din + 2 * ld.din) * sizeof(float);
+      float* zb = (l == 0) ? ybar : c.w.Obar;
+      k_linear_bwd<<<grid, 256, smem, c.st>>>(c.w.Mbar, c.params + ld.w_off, zin[l], c.params + ld.nw_off, d.n,
+                                              ld.din, ld.dout, l > 0 ? 1 : 0, zb, g_params + ld.nw_off,
+                                              g_params + ld.nb_off);
+      PEG_LAUNCH_CHECK();
+    }
+  }
+  return PEG_OK;
+}
+
+static int combine(Ctx& c, float* out, int cnt, const float* const* xs, const double* cs) {
+  CombArgs a;
+  memset(&a, 0, sizeof(a));
+  int k = 0;
+  for (int j = 0; j < cnt; ++j) {
+    if (cs[j] == 0.0) continue;
+    a.x[k] = xs[j];
+    a.c[k] = (float)cs[j];
+    ++k;
+  }
+  a.cnt = k;
+  a.out = out;
+  a.count4 = (size_t)c.d.B * c.d.n * c.d.h / 4;
+  k_rk_combine<<<(unsigned)((a.count4 + 255) / 256), 256, 0, c.st>>>(a);
+  PEG_LAUNCH_CHECK();
+  return PEG_OK;
+}
+
+static int make_ctx(Ctx& c, peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params) {
+  PEG_TRY(check_dims(dims));
+  if (!ctl || !params) return PEG_ERR_NULL_POINTER;
+  if (!ctl->ts || !ctl->adj_coef || !ctl->adj_rowsum || !ctl->adj_diag || !ctl->adj_total || !ctl->tch_coef)
+    return PEG_ERR_NULL_POINTER;
+  if (dims->e > 0 && !ctl->x_coef) return PEG_ERR_NULL_POINTER;
+  if (((uintptr_t)ctl->adj_coef & 15) != 0) return PEG_ERR_ALIGNMENT;
+  c.st = (cudaStream_t)stream;
+  c.d = *dims;
+  c.ctl = *ctl;
+  c.params = params;
+  c.m = make_model(*dims);
+  c.sv_stride = svec_stride(dims->n, dims->L, dims->e);
+  c.use_tc = (dims->flags & PEG_FLAG_TENSOR_CORES) != 0;
+  return PEG_OK;
+}
+
+struct SolveWs {
+  float* k[7];
+  float* Z0;         // stage input
+  float* ytmp;
+  // bwd
+  float* save[6][PEG_MAX_LAYERS];  // per stage, per layer input
+  float* Ybar[6];
+  float* kbar;
+  float* gcur;
+  float* gnext;
+};
+
+static size_t plan(const PegDims& d, int which, int steps, void* base, FevalWs* fw, SolveWs* sw) {
+  Model m = make_model(d);
+  Bump bp(base);
+  FevalWs w;
+  SolveWs s;
+  memset(&s, 0, sizeof(s));
+  const size_t st = (size_t)d.B * d.n * d.h;
+  const bool vjp = (which == PEG_WS_VF_VJP || which == PEG_WS_SOLVE_BWD);
+  carve_feval(bp, d, m, vjp, w);
+  if (which == PEG_WS_VF_VJP) {
+    for (int l = 1; l < d.L; ++l) s.save[0][l] = bp.take<float>(st);
+  }
+  if (which == PEG_WS_SOLVE_FWD || which == PEG_WS_STEP) {
+    for (int i = 0; i < 7; ++i) s.k[i] = bp.take<float>(st);
+    s.Z0 = bp.take<float>(st);
+    s.ytmp = bp.take<float>(st);
+  }
+  if (which == PEG_WS_SOLVE_BWD) {
+    for (int i = 0; i < 6; ++i) s.k[i] = bp.take<float>(st);
+    for (int i = 0; i < 6; ++i)
+      for (int l = 0; l < d.L; ++l) s.save[i][l] = bp.take<float>(st);
+    for (int i = 0; i < 6; ++i) s.Ybar[i] = bp.take<float>(st);
+    s.kbar = bp.take<float>(st);
+    s.gcur = bp.take<float>(st);
+    s.gnext = bp.take<float>(st);
+  }
+  (void)steps;
+  if (fw) *fw = w;
+  if (sw) *sw = s;
+  return (bp.off + 255) & ~(size_t)255;
+}
+
+}  // namespace peg
+
+using namespace peg;
+
+extern "C" {
+
+size_t pegncde_param_count(const PegDims* dims) {
+  if (check_dims(dims) != PEG_OK) return 0;
+  return (size_t)make_model(*dims).P;
+}
+
+int pegncde_param_offsets(const PegDims* dims, int64_t* offsets) {
+  PEG_TRY(check_dims(dims));
+  if (!offsets) return PEG_ERR_NULL_POINTER;
+  Model m = make_model(*dims);
+  for (int l = 0; l < m.L; ++l) {
+    offsets[5 * l + 0] = m.layer[l].w_off;
+    offsets[5 * l + 1] = m.layer[l].b_off;
+    offsets[5 * l + 2] = m.layer[l].nw_off;
+    offsets[5 * l + 3] = m.layer[l].nb_off;
+    offsets[5 * l + 4] = m.layer[l].fus_off;
+  }
+  return PEG_OK;
+}
+
+size_t pegncde_workspace_bytes(const PegDims* dims, int32_t which, int32_t steps) {
+  if (check_dims(dims) != PEG_OK) return 0;
+  if (which < PEG_WS_VF_FWD || which > PEG_WS_STEP) return 0;
+  return plan(*dims, which, steps, nullptr, nullptr, nullptr);
+}
+
+static int pack_common(peg_stream_t stream, const PegDims* dims, const float* d, const float* c, const float* b,
+                       const float* a, const float* planar, float* adj_coef, float* adj_rowsum, float* adj_diag,
+                       float* adj_total, float* tch_coef) {
+  PEG_TRY(check_dims(dims));
+  if (!adj_rowsum || !adj_diag || !adj_total || !tch_coef) return PEG_ERR_NULL_POINTER;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Tm1 = dims->T - 1;
+  const size_t slabs = (size_t)dims->B * Tm1;
+  PEG_CUDA(cudaMemsetAsync(adj_total, 0, slabs * 4 * sizeof(float), st));
+  dim3 grid((dims->n + 63) / 64, Tm1, dims->B);
+  k_pack_adj<<<grid, 256, 0, st>>>(d, c, b, a, planar, dims->n, dims->ldn, Tm1, adj_coef, adj_rowsum, adj_diag,
+                                   adj_total);
+  PEG_LAUNCH_CHECK();
+  if (planar) {
+    const size_t cnt = slabs * 3 * dims->n;
+    k_fill_tch_unit<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(tch_coef, dims->n, slabs);
+  } else {
+    dim3 g2((dims->n + 255) / 256, Tm1, dims->B);
+    k_pack_tch<<<g2, 256, 0, st>>>(d, c, b, dims->n, Tm1, tch_coef);
+  }
+  PEG_LAUNCH_CHECK();
+  return PEG_OK;
+}
+
+int pegncde_pack_adj(peg_stream_t stream, const PegDims* dims, const float* d, const float* c, const float* b,
+                     const float* a, float* adj_coef, float* adj_rowsum, float* adj_diag, float* adj_total,
+                     float* tch_coef) {
+  if (!d || !c || !b || !a || !adj_coef) return PEG_ERR_NULL_POINTER;
+  return pack_common(stream, dims, d, c, b, a, nullptr, adj_coef, adj_rowsum, adj_diag, adj_total, tch_coef);
+}
+
+int pegncde_adj_stats(peg_stream_t stream, const PegDims* dims, const float* adj_coef, float* adj_rowsum,
+                      float* adj_diag, float* adj_total, float* tch_coef) {
+  if (!adj_coef) return PEG_ERR_NULL_POINTER;
+  return pack_common(stream, dims, nullptr, nullptr, nullptr, nullptr, adj_coef, nullptr, adj_rowsum, adj_diag,
+                     adj_total, tch_coef);
+}
+
+int pegncde_pack_x(peg_stream_t stream, const PegDims* dims, const float* d, const float* c, const float* b,
+                   const float* a, float* x_coef) {
+  PEG_TRY(check_dims(dims));
+  if (dims->e <= 0) return PEG_ERR_BAD_DIMS;
+  if (!d || !c || !b || !x_coef) return PEG_ERR_NULL_POINTER;
+  (void)a;
+  const size_t slabs = (size_t)dims->B * (dims->T - 1);
+  const size_t cnt = slabs * dims->n * 2 * dims->e;
+  k_pack_x<<<(unsigned)((cnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, c, b, dims->n, 2 * dims->e, slabs,
+                                                                            x_coef);
+  PEG_LAUNCH_CHECK();
+  return PEG_OK;
+}
+
+int pegncde_vf_fwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params, float t,
+                   const float* y, float* dy, void* workspace, size_t workspace_bytes) {
+  Ctx c;
+  PEG_TRY(make_ctx(c, stream, dims, ctl, params));
+  if (!y || !dy || !workspace) return PEG_ERR_NULL_POINTER;
+  if (workspace_bytes < plan(*dims, PEG_WS_VF_FWD, 0, nullptr, nullptr, nullptr)) return PEG_ERR_WORKSPACE;
+  plan(*dims, PEG_WS_VF_FWD, 0, workspace, &c.w, nullptr);
+  return feval_fwd(c, t, y, dy, nullptr);
+}
+
+int pegncde_vf_vjp(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params, float t,
+                   const float* y, const float* g_dy, float* g_y, float* g_params, float* g_xdot, void* workspace,
+                   size_t workspace_bytes) {
+  Ctx c;
+  PEG_TRY(make_ctx(c, stream, dims, ctl, params));
+  if (!y || !g_dy || !g_y || !g_params || !workspace) return PEG_ERR_NULL_POINTER;
+  if (workspace_bytes < plan(*dims, PEG_WS_VF_VJP, 0, nullptr, nullptr, nullptr)) return PEG_ERR_WORKSPACE;
+  SolveWs s;
+  plan(*dims, PEG_WS_VF_VJP, 0, workspace, &c.w, &s);
+  float* save[PEG_MAX_LAYERS];
+  save[0] = const_cast<float*>(y);
+  for (int l = 1; l < dims->L; ++l) save[l] = s.save[0][l];
+  // forward over the first L-1 layers only: the VJP needs the layer inputs, not the evaluation's output
+  PEG_TRY(feval_fwd(c, t, y, nullptr, save, dims->L - 1));
+  return feval_vjp(c, t, save, g_dy, g_y, g_params, g_xdot);
+}
+
+int pegncde_step_fwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params, float t,
+                     float dt, const float* y, float* k1, int32_t k1_valid, float* y1, float* y_err, float* k7,
+                     void* workspace, size_t workspace_bytes) {
+  Ctx c;
+  PEG_TRY(make_ctx(c, stream, dims, ctl, params));
+  if (!y || !k1 || !y1 || !k7 || !workspace) return PEG_ERR_NULL_POINTER;
+  if (workspace_bytes < plan(*dims, PEG_WS_STEP, 0, nullptr, nullptr, nullptr)) return PEG_ERR_WORKSPACE;
+  SolveWs s;
+  plan(*dims, PEG_WS_STEP, 0, workspace, &c.w, &s);
+  const Tsit5& tb = tsit5();
+  float* k[7] = {k1, s.k[1], s.k[2], s.k[3], s.k[4], s.k[5], k7};
+  if (!k1_valid) PEG_TRY(feval_fwd(c, t, y, k[0], nullptr));
+  for (int i = 1; i < 7; ++i) {
+    const float* xs[8];
+    double cs[8];
+    xs[0] = y; cs[0] = 1.0;
+    for (int j = 0; j < i; ++j) { xs[j + 1] = k[j]; cs[j + 1] = (double)dt * tb.a[i][j]; }
+    float* zin = (i == 6) ? y1 : s.Z0;
+    PEG_TRY(combine(c, zin, i + 1, xs, cs));
+    const float ti = (i == 6) ? (t + dt) : (t + (float)tb.c[i] * dt);
+    PEG_TRY(feval_fwd(c, ti, zin, k[i], nullptr));
+  }
+  if (y_err) {
+    const float* xs[8];
+    double cs[8];
+    for (int j = 0; j < 7; ++j) { xs[j] = k[j]; cs[j] = (double)dt * tb.berr[j]; }
+    PEG_TRY(combine(c, y_err, 7, xs, cs));
+  }
+  return PEG_OK;
+}
+
+int pegncde_solve_fwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params,
+                      const float* step_ts, int32_t steps, const float* y0, float* yT, float* y_ckpt,
+                      void* workspace, size_t workspace_bytes) {
+  Ctx c;
+  PEG_TRY(make_ctx(c, stream, dims, ctl, params));
+  if (!step_ts || !y0 || !y_ckpt || !workspace) return PEG_ERR_NULL_POINTER;
+  if (steps < 1) return PEG_ERR_BAD_DIMS;
+  if (workspace_bytes < plan(*dims, PEG_WS_SOLVE_FWD, steps, nullptr, nullptr, nullptr)) return PEG_ERR_WORKSPACE;
+  SolveWs s;
+  plan(*dims, PEG_WS_SOLVE_FWD, steps, workspace, &c.w, &s);
+  const Tsit5& tb = tsit5();
+  const size_t st = (size_t)dims->B * dims->n * dims->h;
+  PEG_CUDA(cudaMemcpyAsync(y_ckpt, y0, st * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+  float* k[7];
+  for (int i = 0; i < 7; ++i) k[i] = s.k[i];
+  for (int sidx = 0; sidx < steps; ++sidx) {
+    const float t = step_ts[sidx];
+    const float dt = step_ts[sidx + 1] - step_ts[sidx];
+    const float* y = y_ckpt + (size_t)sidx * st;
+    float* ynext = y_ckpt + (size_t)(sidx + 1) * st;
+    if (sidx == 0) PEG_TRY(feval_fwd(c, t, y, k[0], nullptr));
+    for (int i = 1; i < 7; ++i) {
+      const float* xs[8];
+      double cs[8];
+      xs[0] = y; cs[0] = 1.0;
+      for (int j = 0; j < i; ++j) { xs[j + 1] = k[j]; cs[j + 1] = (double)dt * tb.a[i][j]; }
+      float* zin = (i == 6) ? ynext : s.Z0;
+      PEG_TRY(combine(c, zin, i + 1, xs, cs));
+      if (i == 6 && sidx == steps - 1) break;  // the 7th stage only feeds FSAL: unused after the last step
+      const float ti = (i == 6) ? step_ts[sidx + 1] : (t + (float)tb.c[i] * dt);
+      PEG_TRY(feval_fwd(c, ti, zin, k[i], nullptr));
+    }
+    float* tmp = k[0]; k[0] = k[6]; k[6] = tmp;  // FSAL
+  }
+  if (yT) PEG_CUDA(cudaMemcpyAsync(yT, y_ckpt + (size_t)steps * st, st * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+  return PEG_OK;
+}
+
+int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params,
+                      const float* step_ts, int32_t steps, const float* y_ckpt, const float* g_yT,
+                      const float* g_ckpt, float* g_y0, float* g_params, void* workspace, size_t workspace_bytes) {
+  Ctx c;
+  PEG_TRY(make_ctx(c, stream, dims, ctl, params));
+  if (!step_ts || !y_ckpt || !g_yT || !g_y0 || !g_params || !workspace) return PEG_ERR_NULL_POINTER;
+  if (steps < 1) return PEG_ERR_BAD_DIMS;
+  if (workspace_bytes < plan(*dims, PEG_WS_SOLVE_BWD, steps, nullptr, nullptr, nullptr)) return PEG_ERR_WORKSPACE;
+  SolveWs s;
+  plan(*dims, PEG_WS_SOLVE_BWD, steps, workspace, &c.w, &s);
+  const Tsit5& tb = tsit5();
+  const size_t st = (size_t)dims->B * dims->n * dims->h;
+  const int L = dims->L;
+  // running cotangent of y_{s+1}
+  {
+    const float* xs[2] = {g_yT, g_ckpt ? g_ckpt + (size_t)steps * st : nullptr};
+    double cs[2] = {1.0, g_ckpt ? 1.0 : 0.0};
+    PEG_TRY(combine(c, s.gcur, 2, xs, cs));
+  }
+  for (int sidx = steps - 1; sidx >= 0; --sidx) {
+    const float t = step_ts[sidx];
+    const float dt = step_ts[sidx + 1] - step_ts[sidx];
+    const float* y = y_ckpt + (size_t)sidx * st;
+    float tis[6];
+    // ---- recompute the six stages of this step, keeping every layer input ----
+    for (int i = 0; i < 6; ++i) {
+      tis[i] = (i == 0) ? t : (t + (float)tb.c[i] * dt);
+      float* zin;
+      if (i == 0) {
+        zin = const_cast<float*>(y);
+      } else {
+        const float* xs[8];
+        double cs[8];
+        xs[0] = y; cs[0] = 1.0;
+        for (int j = 0; j < i; ++j) { xs[j + 1] = s.k[j]; cs[j + 1] = (double)dt * tb.a[i][j]; }
+        zin = s.save[i][0];
+        PEG_TRY(combine(c, zin, i + 1, xs, cs));
+      }
+      float* save[PEG_MAX_LAYERS];
+      save[0] = zin;
+      for (int l = 1; l < L; ++l) save[l] = s.save[i][l];
+      PEG_TRY(feval_fwd(c, tis[i], zin, s.k[i], save));
+    }
+    // ---- reverse sweep over the stages: kbar_i = dt (b_i g + sum_{j>i} a_ji Ybar_j) ; Ybar_i = J_i^T kbar_i ----
+    for (int i = 5; i >= 0; --i) {
+      const float* xs[8];
+      double cs[8];
+      int cnt = 0;
+      xs[cnt] = s.gcur; cs[cnt] = (double)dt * tb.b[i]; ++cnt;
+      for (int j = i + 1; j < 6; ++j) { xs[cnt] = s.Ybar[j]; cs[cnt] = (double)dt * tb.a[j][i]; ++cnt; }
+      PEG_TRY(combine(c, s.kbar, cnt, xs, cs));
+      float* save[PEG_MAX_LAYERS];
+      save[0] = (i == 0) ? const_cast<float*>(y) : s.save[i][0];
+      for (int l = 1; l < L; ++l) save[l] = s.save[i][l];
+      PEG_TRY(feval_vjp(c, tis[i], save, s.kbar, s.Ybar[i], g_params, nullptr));
+    }
+    // ---- ybar_s = g + sum_i Ybar_i (+ injected cotangent at this boundary) ----
+    {
+      const float* xs[8];
+      double cs[8];
+      int cnt = 0;
+      xs[cnt] = s.gcur; cs[cnt] = 1.0; ++cnt;
+      for (int i = 0; i < 6; ++i) { xs[cnt] = s.Ybar[i]; cs[cnt] = 1.0; ++cnt; }
+      if (g_ckpt) { xs[cnt] = g_ckpt + (size_t)sidx * st; cs[cnt] = 1.0; ++cnt; }
+      float* out = (sidx == 0) ? g_y0 : s.gnext;
+      PEG_TRY(combine(c, out, cnt, xs, cs));
+      float* tmp = s.gcur; s.gcur = s.gnext; s.gnext = tmp;
+    }
+  }
+  return PEG_OK;
+}
+
+const char* pegncde_strerror(int code) {
+  switch (code) {
+    case PEG_OK: return "ok";
+    case PEG_ERR_BAD_DIMS: return "dimension out of the supported range";
+    case PEG_ERR_NULL_POINTER: return "required pointer is NULL";
+    case PEG_ERR_WORKSPACE: return "workspace too small (see pegncde_workspace_bytes)";
+    case PEG_ERR_CUDA: return "CUDA runtime call or kernel launch failed (see pegncde_last_cuda_error)";
+    case PEG_ERR_UNSUPPORTED: return "request not implemented by this build";
+    case PEG_ERR_ALIGNMENT: return "pointer or pitch breaks the 16-byte alignment contract";
+    default: return "unknown pegncde error code";
+  }
+}
+
+int pegncde_last_cuda_error(void) { return peg::g_last_cuda; }
+const char* pegncde_version(void) { return "pegncde-b200 0.1 (sm_100a)"; }
+uint64_t pegncde_launch_count(void) { return peg::g_launches.load(); }
+
+}  // extern "C"
