@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- graph-trajectory solver steps/sec (fwd+bwd) of the fused sm_100a hot path.
+
+One bench "step" = one forward + exact-adjoint backward solve of a batch of B graph trajectories
+(S Tsit5 steps each) per GPU.  value = N_gpus * B * S / seconds_per_bench_step  (whole-job aggregate).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); the batch of trajectories is sharded over the
+ranks (weak scaling: B graphs per GPU) and the flat parameter-gradient buffer is all-reduced every step.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# name -> shape.  The C5 sweep points are BASELINE.json configs[4]; sir / england / twitter are configs[1..3].
+WORKLOADS = {
+    "sir": dict(n=100, h=32, e=3, L=3, T=120, t1=1.0, dt0=0.1, B=50, float_ts=True),
+    "england": dict(n=129, h=64, e=8, L=3, T=4, t1=3.0, dt0=0.1, B=1),
+    "twitter": dict(n=1000, h=64, e=16, L=3, T=9, t1=8.0, dt0=0.1, B=1),
+    "sweep_n1024_h64": dict(n=1024, h=64, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=16),
+    "sweep_n2048_h64": dict(n=2048, h=64, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=8),
+    "sweep_n2048_h128": dict(n=2048, h=128, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=8),
+    "sweep_n4096_h128": dict(n=4096, h=128, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=4),
+    "sweep_n4096_h256": dict(n=4096, h=256, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=4),
+    "sweep_n8192_h128": dict(n=8192, h=128, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=2),
+    "sweep_n16384_h256": dict(n=16384, h=256, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=1),
+}
+DEFAULT_WORKLOAD = "sweep_n2048_h64"
+METRIC = "graph-trajectory solver steps/sec (fwd+bwd)"
+UNIT = "solver steps/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops_sustained"]), src="measured")
+    return dict(hbm=6650.0, bf16=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def synth_adjacency(n, T, seed, device):
+    """Device-side synthetic dynamic weighted digraph [T,n,n]: Bernoulli(min(1,16/n)) mask with
+    10% of entries redrawn per knot, LogNormal(0,1) weights, unit self-loops, row-normalised."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    p = min(1.0, 16.0 / n)
+    mask = torch.rand((n, n), generator=g, device=device) < p
+    w = torch.exp(torch.randn((n, n), generator=g, device=device))
+    out = torch.empty((T, n, n), device=device)
+    eye = torch.eye(n, device=device, dtype=torch.bool)
+    for k in range(T):
+        if k > 0:
+            redraw = torch.rand((n, n), generator=g, device=device) < 0.10
+            mask = torch.where(redraw, torch.rand((n, n), generator=g, device=device) < p, mask)
+            w = torch.where(redraw, torch.exp(torch.randn((n, n), generator=g, device=device)), w)
+        a = torch.where(mask, w, torch.zeros_like(w))
+        a = torch.where(eye, torch.ones_like(a), a)
+        out[k] = a / a.sum(dim=1, keepdim=True)
+    return out
+
+
+def make_inputs(wl, seed, device, host_copy):
+    """Reference-layout inputs of one rank: ts [T], coeffs_adj (d,c,b,a) each [B,T-1,n,n,2], x_coeffs, y0, cotangent."""
+    import perm_equiv_graph_neural_cdes_b200 as P
+
+    n, h, e, T, B = wl["n"], wl["h"], wl["e"], wl["T"], wl["B"]
+    ts = torch.linspace(0.0, wl["t1"], T, device=device) if wl.get("float_ts") else torch.arange(T, device=device, dtype=torch.float32) * (wl["t1"] / (T - 1))
+    cadj = [torch.empty((B, T - 1, n, n, 2), device=device) for _ in range(4)]
+    for b in range(B):
+        A = synth_adjacency(n, T, seed * 1000 + b, device)
+        X = torch.stack([ts[:, None, None].expand(T, n, n), A], dim=-1)
+        for dst, src in zip(cadj, P.backward_hermite_coefficients(ts, X)):
+            dst[b].copy_(src)
+        del A, X
+    g = torch.Generator(device=device).manual_seed(seed + 77)
+    xco = None
+    if e > 0:
+        x_t = 0.3 * torch.randn((B, T, n, e), generator=g, device=device)
+        X = torch.stack([ts[None, :, None, None].expand(B, T, n, e), x_t], dim=-1)
+        xco = [torch.stack([P.backward_hermite_coefficients(ts, X[b])[i] for b in range(B)]) for i in range(4)]
+    y0 = torch.randn((B, n, h), generator=g, device=device)
+    gy = torch.randn((B, n, h), generator=g, device=device)
+    host = None
+    if host_copy:
+        pin = lambda t: t.cpu().pin_memory()
+        host = dict(ts=pin(ts), cadj=[pin(c) for c in cadj], xco=None if xco is None else [pin(c) for c in xco], y0=pin(y0))
+    return ts, cadj, xco, y0, gy, host
+
+
+def run_ours(args):
+    import perm_equiv_graph_neural_cdes_b200 as P
+    from perm_equiv_graph_neural_cdes_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["B"] = args.batch
+    n, h, e, L, T, B = wl["n"], wl["h"], wl["e"], wl["L"], wl["T"], wl["B"]
+    flags = 0 if args.no_tensor_cores else _lib.PEG_FLAG_TENSOR_CORES
+    if args.tf32_fast:
+        flags |= _lib.PEG_FLAG_TF32_FAST
+
+    widths_out = 2 * h * e if e > 0 else h
+    vf = P.PermEquivGraphVectorField(h, h, widths_out, L, e, n, key=1234).to(dev)
+    vf.flags = flags
+    term = P.ODETerm(P.CDEWrapperVectorField(vf, h) if e > 0 else vf)
+    ts, cadj, xco, y0, gy, host = make_inputs(wl, 1234 + rank, dev, host_copy=True)
+    pc = P.pack_control(ts, cadj, xco)
+    del cadj, xco
+    torch.cuda.empty_cache()
+    step_ts = P.constant_step_table(0.0, wl["t1"], wl["dt0"])
+    S = len(step_ts) - 1
+    l = _lib.lib()
+
+    def solve_step(pc_, y0_):
+        vf.zero_grad(set_to_none=True)
+        y = y0_.detach().requires_grad_(True)
+        sol = P.diffeqsolve(term, P.Tsit5(), 0.0, wl["t1"], wl["dt0"], y, [pc_, None] if e > 0 else pc_,
+                            stepsize_controller=P.ConstantStepSize(), saveat=P.SaveAt(t1=True))
+        loss = (sol.ys[-1] * gy).sum()
+        loss.backward()
+        flat_g = torch.cat([p.grad.reshape(-1) for p in vf.parameters()])
+        if world > 1:
+            torch.distributed.all_reduce(flat_g)
+        return loss, flat_g
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident leg: `value` ----------------
+    for _ in range(args.warmup):
+        solve_step(pc, y0)
+    barrier()
+    l.pegncde_profile_enable(args.profile_stride)
+    launches0 = l.pegncde_launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        solve_step(pc, y0)
+    e1.record()
+    barrier()
+    clocks = sampler.summary()
+    ms = e0.elapsed_time(e1)
+    launches = l.pegncde_launch_count() - launches0
+    prof = {}
+    for d, nm in ((0, "fwd"), (1, "bwd")):
+        a, b_, c_, by, fl = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        l.pegncde_profile_read(d, a, b_, c_, by, fl)
+        prof[nm] = dict(launches=a.value, timed=b_.value, ms=c_.value, bytes=by.value, flops=fl.value)
+    l.pegncde_profile_enable(0)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = world * B * S / (ms_per_step * 1e-3)
+
+    # ---------------- end-to-end leg: host buffers through the public API ----------------
+    def e2e_step():
+        ts_d = host["ts"].to(dev, non_blocking=True)
+        cadj_d = [c.to(dev, non_blocking=True) for c in host["cadj"]]
+        xco_d = None if host["xco"] is None else [c.to(dev, non_blocking=True) for c in host["xco"]]
+        y0_d = host["y0"].to(dev, non_blocking=True)
+        pc_ = P.pack_control(ts_d, cadj_d, xco_d)
+        loss, flat_g = solve_step(pc_, y0_d)
+        return float(loss.item()), flat_g.cpu()
+
+    h2d = sum(c.numel() * 4 for c in host["cadj"]) + host["y0"].numel() * 4 + host["ts"].numel() * 4
+    if host["xco"] is not None:
+        h2d += sum(c.numel() * 4 for c in host["xco"])
+    e2e_step()
+    barrier()
+    k_e2e = max(1, min(args.steps, args.e2e_steps))
+    e0.record()
+    for _ in range(k_e2e):
+        _, fg = e2e_step()
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t2, op=torch.distributed.ReduceOp.MAX)
+    e2e_val = world * B * S / (float(t2.item()) / k_e2e * 1e-3)
+    d2h = fg.numel() * 4 + 4
+
+    # ---------------- roofline of the dominant kernel (the n x n x d contraction) ----------------
+    pk = peaks()
+    tot_ms = prof["fwd"]["ms"] + prof["bwd"]["ms"]
+    tot_timed = prof["fwd"]["timed"] + prof["bwd"]["timed"]
+    roof = None
+    if tot_timed:
+        by = (prof["fwd"]["bytes"] * prof["fwd"]["timed"] + prof["bwd"]["bytes"] * prof["bwd"]["timed"])
+        fl = (prof["fwd"]["flops"] * prof["fwd"]["timed"] + prof["bwd"]["flops"] * prof["bwd"]["timed"])
+        gbs = by / (tot_ms * 1e-3) / 1e9
+        tfs = fl / (tot_ms * 1e-3) / 1e12
+        # arithmetic intensity decides which roof binds: tf32 dense peak ~ 1/2 of the measured bf16 peak
+        tf32_peak = pk["bf16"] / 2.0
+        t_hbm, t_tc = by / (pk["hbm"] * 1e9), fl / (tf32_peak * 1e12)
+        bound = "hbm" if t_hbm >= t_tc else "tensor"
+        share = tot_ms * (prof["fwd"]["launches"] + prof["bwd"]["launches"]) / max(tot_timed, 1) / (ms_per_step * args.steps)
+        roof = {"bound": bound, "kernel": "dual_contract (fwd+bwd launches)",
+                "achieved": gbs if bound == "hbm" else tfs, "peak": pk["hbm"] if bound == "hbm" else tf32_peak,
+                "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": (gbs / pk["hbm"]) if bound == "hbm" else (tfs / tf32_peak),
+                "peak_source": pk["src"] + (" hbm_gbs" if bound == "hbm" else " bf16_tflops_sustained/2 (tf32)"),
+                "traffic": None, "achieved_gbs": gbs, "achieved_tflops": tfs, "avg_launch_us": tot_ms / tot_timed * 1e3,
+                "launches_timed": tot_timed, "share_of_step": share,
+                "algorithmic_bytes_per_launch": prof["fwd"]["bytes"], "l2_note": "planes %s L2 (126 MB)" % ("fit in" if 16.0 * n * n * B <= 126e6 else "exceed")}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline(wl, args)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" + (" (contraction: 3xTF32 tcgen05, fp32 accumulate)" if flags & 1 and not flags & 2 else
+                               " (contraction: 1xTF32 tcgen05)" if flags & 2 else " (CUDA-core FFMA)"),
+            "data": "synthetic",
+            "config": {"workload": args.workload, "n": n, "hidden": h, "data_embed_dim": e, "layers": L, "knots": T,
+                       "solver": "Tsit5 fixed dt0=%g" % wl["dt0"], "solver_steps": S, "graphs_per_gpu": B,
+                       "parallelism": "batch of trajectories sharded over %d GPU(s); NCCL all-reduce of %d param grads" % (world, vf.flat_params().numel()),
+                       "l2": "inputs per GPU %.0f MB of coefficient planes (> L2 126 MB: %s)" % (pc.adj_coef.numel() * 4 / 1e6, pc.adj_coef.numel() * 4 > 126e6)},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": k_e2e},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def cpu_problem(wl, seed, sample_steps):
+    """The same workload shape for the CPU oracle, restricted to the first `sample_steps` solver steps."""
+    from oracle import reference_path as R
+
+    p = R.make_problem(n=wl["n"], h=wl["h"], e=wl["e"], L=wl["L"], T=wl["T"], t1=wl["t1"], dt0=wl["dt0"], seed=seed,
+                       float_ts=bool(wl.get("float_ts")), randomize_norm=False)
+    p.step_ts = p.step_ts[: sample_steps + 1]
+    return p
+
+
+def time_oracle(wl, sample_steps, repeats, threads):
+    from oracle import reference_path as R
+
+    torch.set_num_threads(threads)
+    p = cpu_problem(wl, 1234, sample_steps)
+    R.run_forward_backward(cpu_problem(wl, 1234, 1))  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        R.run_forward_backward(p)
+    dt = (time.perf_counter() - t0) / repeats
+    return sample_steps / dt, dt
+
+
+def cpu_baseline(wl, args):
+    threads = os.cpu_count() or 1
+    sample_steps = args.cpu_sample_steps
+    v, dt = time_oracle(wl, sample_steps, 1, threads)
+    return {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "1 graph x %d solver steps fwd+bwd of the same workload shape, torch-CPU restatement (oracle), %.1f s" % (sample_steps, dt)}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU algorithm (the oracle port -- JAX/diffrax are not installable here)
+    with all host threads on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = dict(WORKLOADS[args.workload])
+    threads = os.cpu_count() or 1
+    from oracle import reference_path as R
+
+    torch.set_num_threads(threads)
+    sample_steps = args.cpu_sample_steps
+    p = cpu_problem(wl, 1234, sample_steps)
+    for _ in range(min(args.warmup, 1)):
+        R.run_forward_backward(cpu_problem(wl, 1234, 1))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        R.run_forward_backward(p)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = sample_steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "n": wl["n"], "hidden": wl["h"], "data_embed_dim": wl["e"], "layers": wl["L"]},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "each step = 1 graph x %d solver steps fwd+bwd (torch-CPU restatement of the reference path)" % sample_steps},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="graphs per GPU (default: the workload's)")
+    ap.add_argument("--no-tensor-cores", action="store_true")
+    ap.add_argument("--tf32-fast", action="store_true")
+    ap.add_argument("--profile-stride", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample-steps", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

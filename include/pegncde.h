@@ -152,6 +152,16 @@ const char* pegncde_version(void);
 /* kernels launched by this library since process start (for bench.py's gpu_launches) */
 uint64_t pegncde_launch_count(void);
 
+/* ---- measurement hooks (bench.py's roofline) -------------------------------------------------
+ * When enabled, every `stride`-th launch of the dominant kernel (the n x n x d contraction) is
+ * bracketed by CUDA events on the launching stream.  pegncde_profile_read synchronises those events
+ * and returns, per direction (0 = forward contraction, 1 = backward/adjoint contraction): launches seen,
+ * launches timed, summed milliseconds of the timed ones and the algorithmic bytes / flops of one launch.
+ * stride <= 0 disables and frees the events. */
+int pegncde_profile_enable(int32_t stride);
+int pegncde_profile_read(int32_t direction, uint64_t* launches, uint64_t* timed, double* ms_total,
+                         double* bytes_per_launch, double* flops_per_launch);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpegncde.so")
@@ -59,6 +59,8 @@ SIGNATURES = {
     "pegncde_last_cuda_error": (c_int, []),
     "pegncde_version": (c_char_p, []),
     "pegncde_launch_count": (c_uint64, []),
+    "pegncde_profile_enable": (c_int, [c_int32]),
+    "pegncde_profile_read": (c_int, [c_int32, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_double), POINTER(c_double), POINTER(c_double)]),
 }
 
 

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "peg_kernels.cuh"
 #include "peg_tc.cuh"
@@ -37,6 +38,32 @@ static thread_local int g_last_cuda = 0;
     int _rc = (expr);            \
     if (_rc != PEG_OK) return _rc; \
   } while (0)
+
+// ---- optional per-launch timing of the contraction kernel (bench.py roofline) ----
+struct Prof {
+  int stride = 0;
+  std::vector<cudaEvent_t> ev[2];   // pairs (start, stop)
+  uint64_t seen[2] = {0, 0};
+  double bytes[2] = {0, 0}, flops[2] = {0, 0};
+};
+static Prof g_prof;
+static const size_t kMaxProfPairs = 16384;
+
+static inline bool prof_begin(int dir, cudaStream_t st, double bytes, double flops) {
+  Prof& p = g_prof;
+  if (p.stride <= 0) return false;
+  const uint64_t k = p.seen[dir]++;
+  p.bytes[dir] = bytes;
+  p.flops[dir] = flops;
+  if (k % (uint64_t)p.stride != 0 || p.ev[dir].size() >= 2 * kMaxProfPairs) return false;
+  cudaEvent_t e0, e1;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return false;
+  p.ev[dir].push_back(e0);
+  p.ev[dir].push_back(e1);
+  cudaEventRecord(e0, st);
+  return true;
+}
+static inline void prof_end(int dir, cudaStream_t st) { cudaEventRecord(g_prof.ev[dir].back(), st); }
 
 static inline int last_width(const PegDims& d) { return d.e > 0 ? 2 * d.h * d.e : d.h; }
 
@@ -179,18 +206,29 @@ static int contract(Ctx& c, int l, bool bwd, const float* V, const float* Mref, 
   a.n = c.d.n; a.ldn = c.d.ldn; a.d = ld.dout; a.layer = l;
   a.relu = relu ? 1 : 0;
   a.scale_tg = scale_tg ? 1 : 0;
+  // algorithmic work of one launch: the four coefficient planes are traversed once (16 n^2 B per graph),
+  // V is read and OUT written once; 2 (fwd) or 4 (bwd) n x n x d products.
+  const double nn = (double)c.d.n * c.d.n, nd = (double)c.d.n * ld.dout;
+  const double bytes = c.d.B * (16.0 * nn + 4.0 * nd * (bwd ? 3.0 : 2.0));
+  const double flops = c.d.B * (bwd ? 8.0 : 4.0) * nn * ld.dout;
+  const int dir = bwd ? 1 : 0;
+  const bool timed = prof_begin(dir, c.st, bytes, flops);
+  int rc = PEG_OK;
   if (c.use_tc && tc_supported(c.d, ld.dout)) {
-    int rc = tc_contract(c.st, c.d, c.w.tc, a, bwd);
+    rc = tc_contract(c.st, c.d, c.w.tc, a, bwd);
     if (rc == PEG_OK) g_launches.fetch_add(tc_launches_per_contract(bwd));
-    return rc;
+  } else {
+    dim3 grid((c.d.n + CT_TI - 1) / CT_TI, (ld.dout + CT_TC - 1) / CT_TC, c.d.B);
+    if (!bwd)
+      k_dual_contract<1><<<grid, 256, 0, c.st>>>(a);
+    else
+      k_dual_contract<4><<<grid, 256, 0, c.st>>>(a);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) { g_last_cuda = (int)e; (void)cudaGetLastError(); rc = PEG_ERR_CUDA; }
   }
-  dim3 grid((c.d.n + CT_TI - 1) / CT_TI, (ld.dout + CT_TC - 1) / CT_TC, c.d.B);
-  if (!bwd)
-    k_dual_contract<1><<<grid, 256, 0, c.st>>>(a);
-  else
-    k_dual_contract<4><<<grid, 256, 0, c.st>>>(a);
-  PEG_LAUNCH_CHECK();
-  return PEG_OK;
+  if (timed) prof_end(dir, c.st);
+  return rc;
 }
 
 static int feval_fwd(Ctx& c, float t, const float* yin, float* dy, float* const* save, int nlayers = -1) {
@@ -626,6 +664,39 @@ const char* pegncde_strerror(int code) {
     case PEG_ERR_ALIGNMENT: return "pointer or pitch breaks the 16-byte alignment contract";
     default: return "unknown pegncde error code";
   }
+}
+
+int pegncde_profile_enable(int32_t stride) {
+  Prof& p = peg::g_prof;
+  for (int d = 0; d < 2; ++d) {
+    for (cudaEvent_t e : p.ev[d]) cudaEventDestroy(e);
+    p.ev[d].clear();
+    p.seen[d] = 0;
+  }
+  p.stride = stride > 0 ? stride : 0;
+  return PEG_OK;
+}
+
+int pegncde_profile_read(int32_t direction, uint64_t* launches, uint64_t* timed, double* ms_total,
+                         double* bytes_per_launch, double* flops_per_launch) {
+  if (direction < 0 || direction > 1) return PEG_ERR_BAD_DIMS;
+  Prof& p = peg::g_prof;
+  double ms = 0.0;
+  uint64_t cnt = 0;
+  std::vector<cudaEvent_t>& ev = p.ev[direction];
+  for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+    if (cudaEventSynchronize(ev[i + 1]) != cudaSuccess) { peg::g_last_cuda = (int)cudaGetLastError(); return PEG_ERR_CUDA; }
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, ev[i], ev[i + 1]) != cudaSuccess) { peg::g_last_cuda = (int)cudaGetLastError(); return PEG_ERR_CUDA; }
+    ms += t;
+    ++cnt;
+  }
+  if (launches) *launches = p.seen[direction];
+  if (timed) *timed = cnt;
+  if (ms_total) *ms_total = ms;
+  if (bytes_per_launch) *bytes_per_launch = p.bytes[direction];
+  if (flops_per_launch) *flops_per_launch = p.flops[direction];
+  return PEG_OK;
 }
 
 int pegncde_last_cuda_error(void) { return peg::g_last_cuda; }

@@ -1,0 +1,253 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI, via the host mirror of the reference
+API) against the CPU oracle on the same seeded inputs, against the committed goldens, and -- at
+BASELINE sizes -- through size-independent properties.
+
+Tolerances (BASELINE.json north_star): Z_T within 1e-4 relative (max-norm) of the fp64 oracle in
+fp32 mode; gradients within 1e-3 relative per leaf (they are sums of O(steps*stages*n) fp32 terms).
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import perm_equiv_graph_neural_cdes_b200 as P
+from perm_equiv_graph_neural_cdes_b200 import _lib
+from oracle import reference_path as R
+from tests.helpers import GOLDEN_CASES, device_model, product_grads_as_oracle, rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL_Y = 1e-4
+TOL_G = 1e-3
+
+
+def test_extension_is_loaded_and_counts_launches(cuda):
+    before = _lib.lib().pegncde_launch_count()
+    p = R.make_problem(n=12, h=8, e=0, L=2, T=4, t1=3, dt0=0.5, seed=0)
+    vf, term, args = device_model(p, cuda)
+    P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 3.0, 0.5, p.y0.to(cuda), args)
+    torch.cuda.synchronize()
+    assert _lib.lib().pegncde_launch_count() > before
+
+
+@pytest.mark.parametrize("case", ["tiny_nocontrol", "tiny_control", "ragged_n"])
+def test_pack_control_matches_reference_layout(cuda, case):
+    p = R.make_problem(**GOLDEN_CASES[case])
+    xc = p.x_coeffs
+    pc = P.pack_control(p.ts.to(cuda), tuple(c.to(cuda) for c in p.coeffs_adj), None if xc is None else tuple(c.to(cuda) for c in xc))
+    d, c, b, a = p.coeffs_adj
+    ref = torch.stack([a[..., 1], b[..., 1], c[..., 1], d[..., 1]], dim=1)  # [T-1,4,n,n]
+    got = pc.adj_coef[0].cpu()
+    assert torch.equal(got[..., : p.n], ref)                      # byte-exact re-layout
+    assert float(got[..., p.n:].abs().sum()) == 0.0              # zero padding
+    assert torch.allclose(pc.adj_rowsum[0].cpu(), ref.sum(-1), rtol=1e-5, atol=1e-6)
+    assert torch.equal(pc.adj_diag[0].cpu(), torch.diagonal(ref, dim1=-2, dim2=-1))
+    assert torch.allclose(pc.adj_total[0].cpu(), ref.sum((-1, -2)), rtol=1e-5, atol=1e-5)
+    tch = torch.stack([b[..., 0].mean(1), c[..., 0].mean(1), d[..., 0].mean(1)], dim=1)
+    assert torch.allclose(pc.tch_coef[0].cpu(), tch, rtol=1e-6, atol=1e-7)
+    if xc is not None:
+        xd, xcc, xb, xa = xc
+        refx = torch.stack([xb, xcc, xd], dim=1).reshape(p.ts.numel() - 1, 3, p.n, 2 * p.e)
+        assert torch.equal(pc.x_coef[0].cpu(), refx)
+
+
+def _vf_oracle(p64, t, y):
+    ca = R.CubicInterpolation(p64.ts, p64.coeffs_adj)
+    if p64.e > 0:
+        cx = R.CubicInterpolation(p64.ts, p64.x_coeffs)
+        return R.cde_wrapper_vector_field(t, y, ca, cx, p64.layers, p64.h, p64.e)
+    return R.perm_equiv_vector_field(t, y, ca, p64.layers)
+
+
+@pytest.mark.parametrize("case", ["tiny_nocontrol", "tiny_control", "ragged_n", "sir_like"])
+def test_vector_field_forward_and_vjp(cuda, case):
+    p = R.make_problem(**GOLDEN_CASES[case])
+    p64 = R.problem_to(p, torch.float64)
+    vf, term, args = device_model(p, cuda)
+    t_lo, t_hi = float(p.ts[0]), float(p.ts[-1])
+    # interior points, exact knots, and both out-of-range sides (index clipping)
+    times = [t_lo + 0.37 * (t_hi - t_lo), float(p.ts[1]), t_lo, t_hi, t_lo - 0.25, t_hi + 0.25]
+    for t in times:
+        y = p.y0.to(cuda).requires_grad_(True)
+        dy = term(t, y, args)
+        layers = R.params_to(p64.layers, requires_grad=True)
+        q = R.Problem(p64.n, p64.h, p64.e, p64.L, p64.ts, p64.coeffs_adj, p64.x_coeffs, p64.y0, layers, p64.step_ts, p64.gyT)
+        y64 = p64.y0.clone().requires_grad_(True)
+        ref = _vf_oracle(q, t, y64)
+        assert rel_err(dy.detach(), ref.detach()) < 2e-5, (case, t)
+        vf.zero_grad()
+        (dy * p.gyT.to(cuda)).sum().backward()
+        (ref * p64.gyT).sum().backward()
+        assert rel_err(y.grad, y64.grad) < 5e-5, (case, t)
+        for l, (got, lp) in enumerate(zip(product_grads_as_oracle(vf), layers)):
+            for name, g, r in zip(("fusion", "W", "b", "nw", "nb"), got, lp.tensors()):
+                assert rel_err(g, r.grad) < 2e-4, (case, t, l, name)
+
+
+@pytest.mark.parametrize("case", list(GOLDEN_CASES))
+def test_solve_against_goldens(cuda, case):
+    g = np.load(os.path.join(GOLD, f"{case}.npz"))
+    kw = GOLDEN_CASES[case]
+    p = R.make_problem(**kw)
+    vf, term, args = device_model(p, cuda)
+    y0 = p.y0.to(cuda).requires_grad_(True)
+    sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), float(p.ts[0]), float(p.ts[-1]), kw["dt0"], y0, args,
+                        stepsize_controller=P.ConstantStepSize(), saveat=P.SaveAt(t1=True))
+    assert sol.stats["num_steps"] == int(g["steps"])
+    yT = sol.ys[-1]
+    slack = 4.0 * float(g["rel32"])  # the reference's own fp32 rounding noise on this problem
+    assert rel_err(yT.detach(), g["yT64"]) < TOL_Y + slack, case
+    (yT * p.gyT.to(cuda)).sum().backward()
+    assert rel_err(y0.grad, g["gy0_64"]) < TOL_G, case
+    flat = torch.cat([t.reshape(-1) for layer in product_grads_as_oracle(vf) for t in layer]).cpu().double().numpy()
+    ref = g["gparams64"]
+    # per-leaf relative error
+    off = 0
+    for layer in vf.gnn_layers:
+        cl = layer.conv_layer
+        for name, numel in (("fusion", 16), ("W", cl.linear.weight.numel()), ("b", cl.linear.bias.numel()),
+                            ("nw", cl.norm.weight.numel()), ("nb", cl.norm.bias.numel())):
+            a, b = flat[off:off + numel], ref[off:off + numel]
+            assert np.abs(a - b).max() <= TOL_G * max(np.abs(b).max(), 1e-12) + 1e-7, (case, name)
+            off += numel
+
+
+def test_save_steps_matches_oracle_trajectory(cuda):
+    p = R.make_problem(n=20, h=8, e=3, L=3, T=4, t1=3, dt0=0.25, seed=1)
+    ys_ref = torch.stack(R.run_forward(R.problem_to(p, torch.float64), save_all=True))
+    vf, term, args = device_model(p, cuda)
+    sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 3.0, 0.25, p.y0.to(cuda), args, saveat=P.SaveAt(steps=True))
+    assert sol.ys.shape == ys_ref.shape
+    assert rel_err(sol.ys, ys_ref) < TOL_Y
+    # cotangents injected at every saved boundary
+    y0 = p.y0.to(cuda).requires_grad_(True)
+    sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 3.0, 0.25, y0, args, saveat=P.SaveAt(steps=True))
+    w = torch.linspace(0.5, 1.5, sol.ys.shape[0], device=cuda)[:, None, None]
+    (sol.ys * w).sum().backward()
+    p64 = R.problem_to(p, torch.float64)
+    y64 = p64.y0.clone().requires_grad_(True)
+    ys = torch.stack(R.solve_cde(p64.step_ts, p64.ts, p64.coeffs_adj, p64.x_coeffs, y64, p64.layers, p64.h, p64.e, save_all=True))
+    (ys * w.cpu().double()).sum().backward()
+    assert rel_err(y0.grad, y64.grad) < TOL_G
+
+
+def test_batch_of_independent_graphs(cuda):
+    """B graphs with different control paths in one call == each solved alone (the reference's jax.vmap)."""
+    ps = [R.make_problem(n=24, h=8, e=2, L=2, T=4, t1=3, dt0=0.5, seed=s) for s in (0, 1, 3)]
+    base = ps[0]
+    vf, term, _ = device_model(base, cuda)
+    ts = base.ts.to(cuda)
+    cadj = tuple(torch.stack([p.coeffs_adj[i] for p in ps]).to(cuda) for i in range(4))
+    cx = tuple(torch.stack([p.x_coeffs[i] for p in ps]).to(cuda) for i in range(4))
+    y0 = torch.stack([p.y0 for p in ps]).to(cuda).requires_grad_(True)
+    sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 3.0, 0.5, y0, [P.CubicInterpolation(ts, cadj), P.CubicInterpolation(ts, cx)])
+    gy = torch.stack([p.gyT for p in ps]).to(cuda)
+    (sol.ys[-1] * gy).sum().backward()
+    batched_grad = vf.flat_params().detach().clone() * 0
+    batched_grad = torch.cat([t.reshape(-1) for layer in product_grads_as_oracle(vf) for t in layer])
+    acc = torch.zeros_like(batched_grad)
+    for i, p in enumerate(ps):
+        vf.zero_grad()
+        yi = p.y0.to(cuda).requires_grad_(True)
+        args = [P.CubicInterpolation(ts, tuple(c.to(cuda) for c in p.coeffs_adj)), P.CubicInterpolation(ts, tuple(c.to(cuda) for c in p.x_coeffs))]
+        si = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 3.0, 0.5, yi, args)
+        assert rel_err(sol.ys[-1][i].detach(), si.ys[-1].detach()) < 1e-6
+        (si.ys[-1] * p.gyT.to(cuda)).sum().backward()
+        assert rel_err(y0.grad[i], yi.grad) < 1e-5
+        acc += torch.cat([t.reshape(-1) for layer in product_grads_as_oracle(vf) for t in layer])
+    assert rel_err(batched_grad, acc) < 1e-4  # parameter gradients are summed over the batch
+
+
+def test_tsit5_step_and_error_estimate(cuda):
+    p = R.make_problem(n=20, h=8, e=3, L=3, T=4, t1=3, dt0=0.1, seed=1)
+    p64 = R.problem_to(p, torch.float64)
+    vf, term, args = device_model(p, cuda)
+    t, dt = 0.4, 0.3
+    y1, yerr, k7 = P.tsit5_step(P.ODETerm(term), t, dt, p.y0.to(cuda), args)
+    f = lambda tt, y: _vf_oracle(p64, tt, y)
+    ks = [f(t, p64.y0)]
+    for i in range(1, 7):
+        acc = sum(ks[j] * R.TSIT5_A[i][j] for j in range(i))
+        ks.append(f(t + R.TSIT5_C[i] * dt, p64.y0 + dt * acc))
+    y1_ref = p64.y0 + dt * sum(ks[j] * R.TSIT5_B[j] for j in range(6))
+    err_ref = dt * sum(ks[j] * R.TSIT5_BERR[j] for j in range(7))
+    assert rel_err(y1, y1_ref) < 1e-5
+    assert rel_err(k7, ks[6]) < 1e-5
+    assert float((yerr.cpu().double() - err_ref).abs().max()) < 1e-5 * float(y1_ref.abs().max())
+    # FSAL: feeding k7 back as k1 of the next step reproduces a fresh evaluation
+    y2a, _, _ = P.tsit5_step(P.ODETerm(term), t + dt, dt, y1, args, k1=k7)
+    y2b, _, _ = P.tsit5_step(P.ODETerm(term), t + dt, dt, y1, args)
+    assert rel_err(y2a, y2b) < 1e-6
+
+
+def test_workspace_too_small_is_reported(cuda):
+    p = R.make_problem(n=12, h=8, e=0, L=2, T=4, t1=3, dt0=0.5, seed=0)
+    vf, term, args = device_model(p, cuda)
+    pc = P.vector_field.resolve_control(args, None, cuda)
+    dims = vf.dims_for(pc, with_wrapper=False)
+    y = p.y0.to(cuda).unsqueeze(0).contiguous()
+    dy = torch.empty_like(y)
+    ws = torch.empty(256, dtype=torch.uint8, device=cuda)
+    flat = vf.flat_params().detach()
+    rc = _lib.lib().pegncde_vf_fwd(torch.cuda.current_stream().cuda_stream, dims, pc.struct(), flat.data_ptr(), 0.5,
+                                   y.data_ptr(), dy.data_ptr(), ws.data_ptr(), ws.numel())
+    assert rc == 3
+    with pytest.raises(P.PegError):
+        _lib.check(rc, "vf_fwd")
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE-size properties (no CPU oracle at these sizes)
+# ------------------------------------------------------------------------------------------------
+def _device_problem(n, h, e, L, T, seed, device, B=1):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    A = torch.from_numpy(R.synthetic_graph_path(n, T, seed)).to(torch.float32)
+    ts = torch.arange(T, dtype=torch.float32)
+    co = tuple(c.to(device) for c in R.reference_layout_coeffs(ts, A))
+    xco = None
+    if e > 0:
+        x_t = 0.3 * torch.randn((T, n, e), generator=g)
+        xco = tuple(c.to(device) for c in R.reference_layout_xcoeffs(ts, x_t))
+    widths = R.layer_widths(h, L, e, e > 0)
+    vf = P.PermEquivGraphVectorField(h, h, widths[-1], L, e, n, key=seed).to(device)
+    y0 = torch.randn((n, h), generator=g).to(device)
+    return ts.to(device), co, xco, vf, y0
+
+
+@pytest.mark.parametrize("n,h,e", [(1000, 64, 16), (1000, 64, 0)])
+def test_permutation_equivariance_at_twitter_size(cuda, n, h, e):
+    """f(P Z, P A P^T, P X) = P f(Z, A, X) at C4 (Twitter) size: n=1000, h=64, e=16, L=3."""
+    ts, co, xco, vf, y0 = _device_problem(n, h, e, 3, 3, 11, cuda)
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(5)).to(cuda)
+    term = P.CDEWrapperVectorField(vf, h) if e > 0 else vf
+    def run(co_, xco_, y_):
+        ca = P.CubicInterpolation(ts, co_)
+        args = [ca, P.CubicInterpolation(ts, xco_)] if e > 0 else ca
+        return P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 2.0, 0.25, y_, args).ys[-1]
+    out = run(co, xco, y0)
+    cop = tuple(c[:, perm][:, :, perm].contiguous() for c in co)
+    xcop = None if xco is None else tuple(c[:, perm].contiguous() for c in xco)
+    outp = run(cop, xcop, y0[perm].contiguous())
+    assert torch.isfinite(out).all()
+    assert rel_err(outp, out[perm]) < 5e-5
+
+
+def test_vjp_is_adjoint_of_jvp_at_scale(cuda):
+    """<g, f(y + eps v) - f(y - eps v)> / (2 eps)  ==  <J^T g, v>  at n=1000 (finite differences in fp32)."""
+    n, h, e = 1000, 64, 0
+    ts, co, _, vf, y0 = _device_problem(n, h, e, 3, 3, 12, cuda)
+    ca = P.CubicInterpolation(ts, co)
+    gen = torch.Generator().manual_seed(0)
+    v = torch.randn((n, h), generator=gen).to(cuda)
+    g = torch.randn((n, h), generator=gen).to(cuda)
+    y = y0.clone().requires_grad_(True)
+    out = vf(0.7, y, ca)
+    (out * g).sum().backward()
+    lhs = float((y.grad.double() * v.double()).sum())
+    eps = 1e-2
+    fp = vf(0.7, (y0 + eps * v), ca).double()
+    fm = vf(0.7, (y0 - eps * v), ca).double()
+    rhs = float(((fp - fm) * g.double()).sum() / (2 * eps))
+    assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)

@@ -1,0 +1,104 @@
+"""CPU: the oracle against the committed goldens and against the mathematical identities the CUDA
+path relies on (matrix-free fusion, permutation equivariance, Hermite interpolation properties)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_path as R
+from oracle.make_goldens import input_checksum
+from tests.helpers import GOLDEN_CASES
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", ["tiny_nocontrol", "tiny_control", "ragged_n"])
+def test_oracle_reproduces_goldens(name):
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    p = R.make_problem(**GOLDEN_CASES[name])
+    assert abs(input_checksum(p) - float(g["in_checksum"])) < 1e-6 * max(1.0, abs(float(g["in_checksum"])))
+    yT, gy0, grads = R.run_forward_backward(R.problem_to(p, torch.float64))
+    assert np.allclose(yT.numpy(), g["yT64"], rtol=0, atol=1e-10)
+    assert np.allclose(gy0.numpy(), g["gy0_64"], rtol=0, atol=1e-9)
+    flat = np.concatenate([t.numpy().reshape(-1) for layer in grads for t in layer])
+    assert np.allclose(flat, g["gparams64"], rtol=0, atol=1e-8)
+    assert len(p.step_ts) - 1 == int(g["steps"])
+
+
+def test_goldens_are_well_conditioned():
+    for name in GOLDEN_CASES:
+        g = np.load(os.path.join(GOLD, f"{name}.npz"))
+        assert float(g["rel32"]) < 5e-5, (name, float(g["rel32"]))
+
+
+def test_matrix_free_identity():
+    """(I + Abar) M == M + E M + G^T M + v*M + r (1^T M) + 1 (c^T M) + kappa 1 (1^T M)  (SURVEY Q11)."""
+    torch.manual_seed(0)
+    n, d = 23, 7
+    A = torch.randn(n, n, dtype=torch.float64)
+    D = torch.randn(n, n, dtype=torch.float64)
+    p = torch.randn(8, 2, dtype=torch.float64) / 3
+    M = torch.randn(n, d, dtype=torch.float64)
+    ref = M + R.fusion(A, D, p) @ M
+    E = (1 + p[0, 0]) * A + (1 + p[0, 1]) * D
+    G = p[1, 0] * A + p[1, 1] * D
+    rA, rD = A.sum(1), D.sum(1)
+    v = p[2, 0] * A.diag() + p[2, 1] * D.diag() + (p[5, 0] * rA + p[5, 1] * rD) / n + (p[7, 0] * A.sum() + p[7, 1] * D.sum()) / n**2
+    r = (p[3, 0] * rA + p[3, 1] * rD) / n
+    c = (p[4, 0] * rA + p[4, 1] * rD) / n
+    kappa = (p[6, 0] + p[6, 1]) * A.sum() / n**2  # reference quirk: both coefficients use sum(A)
+    s = M.sum(0, keepdim=True)
+    mf = M + E @ M + G.t() @ M + v[:, None] * M + r[:, None] * s + (c @ M)[None, :] + kappa * s
+    assert torch.allclose(ref, mf, atol=1e-12)
+
+
+def test_permutation_equivariance():
+    """f(P Z, P A P^T) = P f(Z, A) for the undirected layer stack."""
+    p = R.problem_to(R.make_problem(n=15, h=8, e=2, L=3, T=4, t1=3, dt0=0.1, seed=2), torch.float64)
+    perm = torch.randperm(p.n, generator=torch.Generator().manual_seed(1))
+    ca = R.CubicInterpolation(p.ts, p.coeffs_adj)
+    cx = R.CubicInterpolation(p.ts, p.x_coeffs)
+    t = 1.37
+    out = R.cde_wrapper_vector_field(t, p.y0, ca, cx, p.layers, p.h, p.e)
+    cap = R.CubicInterpolation(p.ts, tuple(c[:, perm][:, :, perm] for c in p.coeffs_adj))
+    cxp = R.CubicInterpolation(p.ts, tuple(c[:, perm] for c in p.x_coeffs))
+    outp = R.cde_wrapper_vector_field(t, p.y0[perm], cap, cxp, p.layers, p.h, p.e)
+    assert torch.allclose(outp, out[perm], atol=1e-10)
+
+
+def test_backward_hermite_interpolates_knots_and_is_c1():
+    ts = torch.tensor([0.0, 0.7, 1.0, 2.5, 3.0], dtype=torch.float64)
+    ys = torch.randn(5, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    ci = R.CubicInterpolation(ts, R.backward_hermite_coefficients(ts, ys))
+    for k in range(5):
+        assert torch.allclose(ci.evaluate(float(ts[k])), ys[k], atol=1e-12)
+    eps = 1e-9
+    for k in range(1, 4):  # derivative continuous across interior knots
+        assert torch.allclose(ci.derivative(float(ts[k]) - eps), ci.derivative(float(ts[k]) + eps), atol=1e-6)
+    # first piece is linear (b_0 = m_0  =>  c = d = 0)
+    assert float(ci.c[0].abs().max()) == 0.0 and float(ci.d[0].abs().max()) == 0.0
+
+
+def test_time_channel_gradient_is_one():
+    p = R.make_problem(n=6, h=4, e=0, L=1, T=4, t1=3, dt0=0.1, seed=0, dtype=torch.float64)
+    ca = R.CubicInterpolation(p.ts, p.coeffs_adj)
+    assert torch.allclose(ca.derivative(1.3)[..., 0], torch.ones(6, 6, dtype=torch.float64))
+
+
+def test_step_table_rules():
+    for (t1, dt, n_state) in [(3, 0.1, 30), (1, 0.1, 10), (1, 0.01, 100), (8, 0.01, 800)]:
+        tab = R.constant_step_table(0.0, t1, dt)
+        assert len(tab) - 1 == n_state and tab[0] == 0 and tab[-1] == np.float32(t1)
+        assert np.all(np.diff(tab) > 0)
+    with pytest.raises(RuntimeError):
+        R.constant_step_table(0.0, 100.0, 0.001)
+
+
+def test_tsit5_order_on_linear_ode():
+    """y' = -y: 10 steps of 0.1 must reproduce exp(-1) to 5th-order accuracy."""
+    y0 = torch.ones(1, 1, dtype=torch.float64)
+    yT = R.tsit5_solve_fixed(lambda t, y: -y, y0, np.linspace(0, 1, 11))
+    assert abs(float(yT) - np.exp(-1.0)) < 2e-8
+    yT2 = R.tsit5_solve_fixed(lambda t, y: -y, y0, np.linspace(0, 1, 21))
+    assert abs(float(yT2) - np.exp(-1.0)) < abs(float(yT) - np.exp(-1.0)) / 16
