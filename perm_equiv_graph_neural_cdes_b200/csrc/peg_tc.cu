@@ -1,15 +1,560 @@
-// tcgen05 contraction -- placeholder translation unit (kernels land here next).
+// tcgen05 / TMEM / TMA implementation of the matrix-free equivariant contraction (sm_100a).
+//
+//   OUT[I] = sum_kc X[I, kc] V[kc]  +  sum_kc Y[kc, I]^T V[kc]      (+ O(n d) epilogue corrections)
+//
+// X and Y are linear combinations of the four cubic-coefficient planes (the control-path
+// interpolation is fused: A_s, A'_s are never written to memory).  Per CTA: one 128-row output
+// block x ND columns, accumulators in TMEM.  Work items alternate between a "direct" chunk
+// (rows of block I, 32 columns kc) and a "transposed" chunk (32 rows kc, columns of block I);
+// the diagonal schedule kc_d = 4I+s, kc_t = 4I-s makes the two CTAs that need the same plane
+// tile touch it at about the same time, so HBM sees every plane byte once per pass and L2 serves
+// the second reader.
+//
+// Warp roles (320 threads): warps 0-7 converters (LDG.128 planes -> FFMA combine -> 3xTF32 split
+// -> swizzled STS of the K-major A operand tiles) and, at the end, the epilogue (tcgen05.ld);
+// warp 8 = TMA producer of the B operand (V^T hi/lo, SWIZZLE_128B); warp 9 = TMEM allocator +
+// the single thread that issues tcgen05.mma.
+//
+// fp32 parity: 3xTF32 (hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM); PEG_FLAG_TF32_FAST drops
+// the two correction products.
+#include <cuda.h>
+
 #include "peg_tc.cuh"
 
 namespace peg {
 
-void tc_carve(Bump& bp, const PegDims& d, int dmax, TcWs& w) {
-  (void)bp; (void)d; (void)dmax;
-  w.Vt_hi = w.Vt_lo = nullptr;
-  w.npad = 0;
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-bool tc_supported(const PegDims& d, int dcols) { (void)d; (void)dcols; return false; }
-int tc_contract(cudaStream_t, const PegDims&, const TcWs&, const ContractArgs&, bool) { return PEG_ERR_UNSUPPORTED; }
-int tc_launches_per_contract(bool) { return 0; }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------------------------------
+// V [B,n,d] -> V^T split into tf32 hi / lo, [B][d][npad] (zero padded): the K-major B operand
+// grid (npad/32, ceil(d/32), B), block (32, 8)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_split_transpose(const float* __restrict__ V, int n, int d, int npad,
+                                                         float* __restrict__ Thi, float* __restrict__ Tlo) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, i0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* Vb = V + (size_t)b * n * d;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = i0 + r, c = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (i < n && c < d) ? Vb[(size_t)i * d + c] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int c = c0 + r, i = i0 + threadIdx.x;
+    if (c < d) {
+      const float v = tile[threadIdx.x][r];
+      const float hi = tf32_rna(v);
+      const size_t o = ((size_t)b * d + c) * npad + i;
+      Thi[o] = hi;
+      Tlo[o] = v - hi;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// the contraction kernel
+// ------------------------------------------------------------------------------------------
+constexpr int TC_THREADS = 320;
+constexpr int TC_CONV_THREADS = 256;
+constexpr int TC_BM = 128;   // output rows per CTA (UMMA M)
+constexpr int TC_BK = 32;    // K chunk (32 fp32 = 128 B = one swizzle row)
+constexpr int TC_ATILE = TC_BM * TC_BK * 4;  // 16 KB
+
+struct TcParams {
+  ContractArgs a;
+  int nd;        // columns per CTA (UMMA N)
+  int nsplit;    // 3 = 3xTF32, 1 = single pass
+  int stages;
+  int nkc;       // number of 32-wide K chunks = npad / 32
+  int tmem_cols; // power of two >= 32
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int NA = BWD ? 2 : 1;  // A-operand variants per item: fwd = combined X or Y; bwd = (A_s, A'_s)
+  const ContractArgs& a = p.a;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z, I = blockIdx.x, ntile = blockIdx.y;
+  const int n = a.n, ldn = a.ldn, d = a.d, nd = p.nd;
+  const bool split = p.nsplit == 3;
+
+  // ---- shared memory carve-up (1024-B aligned operand tiles) ----
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int a_bytes = NA * (split ? 2 : 1) * TC_ATILE;          // [variant][hi,lo]
+  const int b_tile = nd * TC_BK * 4;
+  const int b_bytes = (split ? 2 : 1) * b_tile;                 // [hi,lo]
+  const int stage_bytes = a_bytes + b_bytes;
+  const uint32_t bar_base = smem_base + p.stages * stage_bytes;  // full_a[s], full_b[s], empty[s], accum_full, tmem slot
+  auto full_a = [&](int s) { return bar_base + 8u * s; };
+  auto full_b = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  auto empty = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };
+  const uint32_t accum_bar = bar_base + 8u * (3 * p.stages);
+  const uint32_t tmem_slot = accum_bar + 8u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_a(s), TC_CONV_THREADS);
+      mbar_init(full_b(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) {  // TMEM allocation (whole warp), address lands in smem
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const StageScalars sc = a.sc[b];
+  const int nkc = p.nkc;
+  const int items = 2 * nkc;
+  const float alpha = 1.f + a.fus[0], beta = 1.f + a.fus[1], gamma = a.fus[2], delta = a.fus[3];
+
+  if (warp < 8) {
+    // =========================== converters ===========================
+    // weights of the four planes for each A-operand variant and item type
+    float wdir[NA][4], wtr[NA][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (BWD) {
+        wdir[0][q] = sc.wA[q]; wdir[NA - 1][q] = sc.wD[q];
+        wtr[0][q] = sc.wA[q];  wtr[NA - 1][q] = sc.wD[q];
+      } else {
+        wdir[0][q] = alpha * sc.wA[q] + beta * sc.wD[q];   // X = (1+p1_0) A + (1+p1_1) A'
+        wtr[0][q] = gamma * sc.wA[q] + delta * sc.wD[q];   // Y = p2_0 A + p2_1 A'
+      }
+    }
+    const float* P = a.planes + (size_t)b * a.graph_stride + (size_t)sc.interval * 4 * n * ldn;
+    const size_t pstride = (size_t)n * ldn;
+    // direct item: thread -> (row r = tid/2, 16 consecutive k starting at 16*(tid&1))
+    const int d_r = tid >> 1, d_half = tid & 1;
+    // transposed item: thread -> (k-quad kq = lane&7, i-quad iq = warp*4 + (lane>>3)) : a 4(k) x 4(i) micro tile
+    const int t_kq = lane & 7, t_iq = warp * 4 + (lane >> 3);
+
+    float4 buf[16];  // prefetched plane data of the next item: [plane][4]
+    auto issue_loads = [&](int j) {
+      const int s = j >> 1, type = j & 1;
+      if (type == 0) {
+        const int kc = (4 * I + s) % nkc;
+        const int gi = I * TC_BM + d_r, gk = kc * TC_BK + d_half * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int k = gk + 4 * c;
+            buf[q * 4 + c] = (gi < n && k < ldn) ? __ldg(reinterpret_cast<const float4*>(P + q * pstride + (size_t)gi * ldn + k))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+      } else {
+        const int kc = ((4 * I - s) % nkc + nkc) % nkc;
+        const int gi = I * TC_BM + 4 * t_iq;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int gk = kc * TC_BK + 4 * t_kq + kk;
+            buf[q * 4 + kk] = (gk < n && gi < ldn) ? __ldg(reinterpret_cast<const float4*>(P + q * pstride + (size_t)gk * ldn + gi))
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+      }
+    };
+
+    issue_loads(0);
+    for (int j = 0; j < items; ++j) {
+      const int st = j % p.stages;
+      const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
+      const int s = j >> 1, type = j & 1;
+      // consume the prefetched registers into local combos BEFORE overwriting buf with the next prefetch
+      float vals[NA][16];
+      if (type == 0) {
+        const int kc = (4 * I + s) % nkc;
+        const int gk = kc * TC_BK + d_half * 16;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 e0 = buf[0 * 4 + c], e1 = buf[1 * 4 + c], e2 = buf[2 * 4 + c], e3 = buf[3 * 4 + c];
+          const float x0[4] = {e0.x, e0.y, e0.z, e0.w}, x1[4] = {e1.x, e1.y, e1.z, e1.w};
+          const float x2[4] = {e2.x, e2.y, e2.z, e2.w}, x3[4] = {e3.x, e3.y, e3.z, e3.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const bool ok = (gk + 4 * c + u) < n;
+#pragma unroll
+            for (int v = 0; v < NA; ++v) {
+              const float val = wdir[v][0] * x0[u] + wdir[v][1] * x1[u] + wdir[v][2] * x2[u] + wdir[v][3] * x3[u];
+              vals[v][c * 4 + u] = ok ? val : 0.f;
+            }
+          }
+        }
+      } else {
+        const int gi = I * TC_BM + 4 * t_iq;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float4 e0 = buf[0 * 4 + kk], e1 = buf[1 * 4 + kk], e2 = buf[2 * 4 + kk], e3 = buf[3 * 4 + kk];
+          const float x0[4] = {e0.x, e0.y, e0.z, e0.w}, x1[4] = {e1.x, e1.y, e1.z, e1.w};
+          const float x2[4] = {e2.x, e2.y, e2.z, e2.w}, x3[4] = {e3.x, e3.y, e3.z, e3.w};
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii) {
+            const bool ok = (gi + ii) < n;
+#pragma unroll
+            for (int v = 0; v < NA; ++v) {
+              const float val = wtr[v][0] * x0[ii] + wtr[v][1] * x1[ii] + wtr[v][2] * x2[ii] + wtr[v][3] * x3[ii];
+              vals[v][ii * 4 + kk] = ok ? val : 0.f;   // transposed in registers: [i][k]
+            }
+          }
+        }
+      }
+      if (j + 1 < items) issue_loads(j + 1);
+
+      // wait until the MMAs that read this stage's previous contents have completed
+      mbar_wait(empty(st), ph ^ 1u);
+      const uint32_t a_base = smem_base + st * stage_bytes;
+#pragma unroll
+      for (int v = 0; v < NA; ++v) {
+        const uint32_t hi_base = a_base + v * (split ? 2 : 1) * TC_ATILE;
+        const uint32_t lo_base = hi_base + TC_ATILE;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          // 16-byte chunk (4 consecutive k) of one row
+          int r, chunk;
+          if (type == 0) { r = d_r; chunk = d_half * 4 + c; }
+          else           { r = 4 * t_iq + c; chunk = t_kq; }
+          const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+          float h4[4], l4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float x = vals[v][c * 4 + u];
+            h4[u] = tf32_rna(x);
+            l4[u] = x - h4[u];
+          }
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "f"(h4[0]), "f"(h4[1]), "f"(h4[2]), "f"(h4[3]) : "memory");
+          if (split)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + off), "f"(l4[0]), "f"(l4[1]), "f"(l4[2]), "f"(l4[3]) : "memory");
+        }
+      }
+      fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(full_a(st));
+    }
+  } else if (warp == 8) {
+    // =========================== TMA producer (B operand) ===========================
+    if (lane == 0) {
+      const int row0 = b * d + ntile * nd;
+      for (int j = 0; j < items; ++j) {
+        const int st = j % p.stages;
+        const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
+        const int s = j >> 1, type = j & 1;
+        const int kc = type == 0 ? (4 * I + s) % nkc : ((4 * I - s) % nkc + nkc) % nkc;
+        mbar_wait(empty(st), ph ^ 1u);
+        const uint32_t b_base = smem_base + st * stage_bytes + a_bytes;
+        mbar_expect_tx(full_b(st), (uint32_t)b_bytes);
+        tma_load_2d(b_base, &map_hi, kc * TC_BK, row0, full_b(st));
+        if (split) tma_load_2d(b_base + b_tile, &map_lo, kc * TC_BK, row0, full_b(st));
+      }
+    }
+  } else {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nd >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      uint32_t started = 0u;  // bit acc set once the accumulator has been written (first MMA overwrites)
+      for (int j = 0; j < items; ++j) {
+        const int st = j % p.stages;
+        const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
+        const int type = j & 1;
+        mbar_wait(full_a(st), ph);
+        mbar_wait(full_b(st), ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_base + st * stage_bytes;
+        const uint32_t b_base = a_base + a_bytes;
+#pragma unroll
+        for (int v = 0; v < NA; ++v) {
+          // fwd: one accumulator; bwd: acc index = type*2 + v  (0: A V, 1: A'V, 2: A^T V, 3: A'^T V)
+          const int acc = BWD ? (type * 2 + v) : 0;
+          const uint32_t tacc = tmem_base + (uint32_t)(acc * nd);
+          const uint32_t ahi = a_base + v * (split ? 2 : 1) * TC_ATILE, alo = ahi + TC_ATILE;
+#pragma unroll
+          for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+            const uint64_t dah = make_desc_sw128(ahi + k8 * 32), dbh = make_desc_sw128(b_base + k8 * 32);
+            umma_tf32(tacc, dah, dbh, idesc, (started >> acc) & 1u);
+            started |= 1u << acc;
+            if (split) {
+              const uint64_t dal = make_desc_sw128(alo + k8 * 32), dbl = make_desc_sw128(b_base + b_tile + k8 * 32);
+              umma_tf32(tacc, dal, dbh, idesc, 1u);
+              umma_tf32(tacc, dah, dbl, idesc, 1u);
+            }
+          }
+        }
+        umma_commit(empty(st));   // frees this smem stage once the MMAs above have read it
+      }
+      umma_commit(accum_bar);     // all accumulators final
+    }
+  }
+
+  // =========================== epilogue (warps 0-7) ===========================
+  if (warp < 8) {
+    mbar_wait(accum_bar, 0u);
+    tc_fence_after();
+    const int q = warp & 3;               // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int gi = I * TC_BM + row;
+    const int half = warp >> 2;           // column half handled by this warp
+    const int cols_per_half = nd / 2;     // nd % 32 == 0 is required by tc_supported
+    const float* sv = a.svec + (size_t)b * a.sv_stride;
+    const float* cb0 = a.colbuf + ((size_t)b * 2 + 0) * d;
+    const float* cb1 = a.colbuf + ((size_t)b * 2 + 1) * d;
+    const float kappa = sc.kappa[a.layer];
+    const bool rowok = gi < n;
+    const float vi = rowok ? 1.f + sv[a.v_off + gi] : 0.f;
+    const float rc = rowok ? sv[a.rowc_off + gi] : 0.f;
+    const float tg = (rowok && a.scale_tg) ? sv[a.tg_off + gi] : 1.f;
+    const float* Vrow = a.V + ((size_t)b * n + (rowok ? gi : 0)) * d;
+    const float* Mrow = BWD ? a.Mref + ((size_t)b * n + (rowok ? gi : 0)) * d : nullptr;
+    float* Orow = a.out + ((size_t)b * n + (rowok ? gi : 0)) * d;
+    float g4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int cc = 0; cc < cols_per_half; cc += 16) {
+      const int col = half * cols_per_half + cc;      // column inside this CTA's ND tile
+      const int gc = ntile * nd + col;                // global feature column
+      uint32_t r0[16], r1[16], r2[16], r3[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
+      tmem_ld16(taddr, r0);
+      if (BWD) {
+        tmem_ld16(taddr + nd, r1);
+        tmem_ld16(taddr + 2 * nd, r2);
+        tmem_ld16(taddr + 3 * nd, r3);
+      }
+      tmem_wait_ld();
+      if (rowok) {
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          const float4 vin = *reinterpret_cast<const float4*>(Vrow + gc + 4 * v4);
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(cb0 + gc + 4 * v4));
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(cb1 + gc + 4 * v4));
+          const float vv[4] = {vin.x, vin.y, vin.z, vin.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
+          float o[4];
+          if (!BWD) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float val = vv[u] * vi + __uint_as_float(r0[4 * v4 + u]) + rc * ss[u] + tt[u] + kappa * ss[u];
+              if (a.relu) val = fmaxf(val, 0.f);
+              o[u] = val * tg;
+            }
+          } else {
+            const float4 m4 = *reinterpret_cast<const float4*>(Mrow + gc + 4 * v4);
+            const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float aV = __uint_as_float(r0[4 * v4 + u]), dV = __uint_as_float(r1[4 * v4 + u]);
+              const float atV = __uint_as_float(r2[4 * v4 + u]), dtV = __uint_as_float(r3[4 * v4 + u]);
+              o[u] = vv[u] * vi + alpha * atV + beta * dtV + gamma * aV + delta * dV + rc * ss[u] + tt[u] + kappa * ss[u];
+              g4[0] = fmaf(atV, mm[u], g4[0]);
+              g4[1] = fmaf(dtV, mm[u], g4[1]);
+              g4[2] = fmaf(aV, mm[u], g4[2]);
+              g4[3] = fmaf(dV, mm[u], g4[3]);
+            }
+          }
+          *reinterpret_cast<float4*>(Orow + gc + 4 * v4) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+    if (BWD) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float t = g4[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) atomicAdd(a.g_fus + k, t);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 9) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int pick_nd(int d, int maxnd) {
+  for (int nd = maxnd; nd >= 32; nd -= 32)
+    if (d % nd == 0) return nd;
+  return 0;
+}
+
+static inline int npad_of(int n) { return (n + 31) / 32 * 32; }
+
+void tc_carve(Bump& bp, const PegDims& d, int dmax, TcWs& w) {
+  w.npad = npad_of(d.n);
+  if ((d.flags & PEG_FLAG_TENSOR_CORES) == 0) {
+    w.Vt_hi = w.Vt_lo = nullptr;
+    return;
+  }
+  const size_t cnt = (size_t)d.B * dmax * w.npad;
+  w.Vt_hi = bp.take<float>(cnt);
+  w.Vt_lo = bp.take<float>(cnt);
+}
+
+bool tc_supported(const PegDims& d, int dcols) {
+  if (d.n < 128) return false;
+  if (dcols % 32 != 0) return false;
+  if (pick_nd(dcols, 256) == 0 || pick_nd(dcols, 128) == 0) return false;
+  return get_encode() != nullptr;
+}
+
+int tc_launches_per_contract(bool) { return 2; }
+
+static int tmem_cols_pow2(int cols) {
+  int c = 32;
+  while (c < cols) c <<= 1;
+  return c;
+}
+
+int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const ContractArgs& a, bool bwd) {
+  const int n = a.n, d = a.d, npad = w.npad;
+  if (!w.Vt_hi || !w.Vt_lo) return PEG_ERR_WORKSPACE;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return PEG_ERR_UNSUPPORTED;
+  {
+    dim3 grid(npad / 32, (d + 31) / 32, dm.B), block(32, 8);
+    k_split_transpose<<<grid, block, 0, st>>>(a.V, n, d, npad, w.Vt_hi, w.Vt_lo);
+    if (cudaPeekAtLastError() != cudaSuccess) return PEG_ERR_CUDA;
+  }
+  TcParams p;
+  p.a = a;
+  p.nd = pick_nd(d, bwd ? 128 : 256);
+  p.nsplit = (dm.flags & PEG_FLAG_TF32_FAST) ? 1 : 3;
+  p.nkc = npad / 32;
+  const int na = bwd ? 2 : 1, sp = p.nsplit == 3 ? 2 : 1;
+  const int stage_bytes = na * sp * TC_ATILE + sp * p.nd * TC_BK * 4;
+  int stages = (200 * 1024) / stage_bytes;
+  stages = stages > 4 ? 4 : stages;
+  if (stages < 2) return PEG_ERR_UNSUPPORTED;
+  p.stages = stages;
+  p.tmem_cols = tmem_cols_pow2((bwd ? 4 : 1) * p.nd);
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (3 * stages + 2) + 64;
+
+  CUtensorMap mhi, mlo;
+  const cuuint64_t gdim[2] = {(cuuint64_t)npad, (cuuint64_t)dm.B * d};
+  const cuuint64_t gstr[1] = {(cuuint64_t)npad * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)p.nd};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(&mhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w.Vt_hi, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return PEG_ERR_CUDA;
+  if (enc(&mlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w.Vt_lo, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return PEG_ERR_CUDA;
+
+  dim3 grid((n + TC_BM - 1) / TC_BM, d / p.nd, dm.B);
+  cudaError_t e;
+  if (bwd) {
+    e = cudaFuncSetAttribute(k_tc_contract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return PEG_ERR_CUDA;
+    k_tc_contract<true><<<grid, TC_THREADS, smem, st>>>(mhi, mlo, p);
+  } else {
+    e = cudaFuncSetAttribute(k_tc_contract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return PEG_ERR_CUDA;
+    k_tc_contract<false><<<grid, TC_THREADS, smem, st>>>(mhi, mlo, p);
+  }
+  if (cudaPeekAtLastError() != cudaSuccess) return PEG_ERR_CUDA;
+  return PEG_OK;
+}
 
 }  // namespace peg

@@ -86,12 +86,15 @@ def test_vector_field_forward_and_vjp(cuda, case):
                 assert rel_err(g, r.grad) < 2e-4, (case, t, l, name)
 
 
+@pytest.mark.parametrize("flags", [0, _lib.PEG_FLAG_TENSOR_CORES], ids=["ffma", "tcgen05"])
 @pytest.mark.parametrize("case", list(GOLDEN_CASES))
-def test_solve_against_goldens(cuda, case):
+def test_solve_against_goldens(cuda, case, flags):
     g = np.load(os.path.join(GOLD, f"{case}.npz"))
     kw = GOLDEN_CASES[case]
     p = R.make_problem(**kw)
-    vf, term, args = device_model(p, cuda)
+    if flags and p.n < 128:
+        pytest.skip("tensor-core contraction is only selected for n >= 128")
+    vf, term, args = device_model(p, cuda, flags=flags)
     y0 = p.y0.to(cuda).requires_grad_(True)
     sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), float(p.ts[0]), float(p.ts[-1]), kw["dt0"], y0, args,
                         stepsize_controller=P.ConstantStepSize(), saveat=P.SaveAt(t1=True))
@@ -234,20 +237,39 @@ def test_permutation_equivariance_at_twitter_size(cuda, n, h, e):
     assert rel_err(outp, out[perm]) < 5e-5
 
 
-def test_vjp_is_adjoint_of_jvp_at_scale(cuda):
-    """<g, f(y + eps v) - f(y - eps v)> / (2 eps)  ==  <J^T g, v>  at n=1000 (finite differences in fp32)."""
-    n, h, e = 1000, 64, 0
-    ts, co, _, vf, y0 = _device_problem(n, h, e, 3, 3, 12, cuda)
-    ca = P.CubicInterpolation(ts, co)
-    gen = torch.Generator().manual_seed(0)
-    v = torch.randn((n, h), generator=gen).to(cuda)
-    g = torch.randn((n, h), generator=gen).to(cuda)
-    y = y0.clone().requires_grad_(True)
-    out = vf(0.7, y, ca)
-    (out * g).sum().backward()
-    lhs = float((y.grad.double() * v.double()).sum())
-    eps = 1e-2
-    fp = vf(0.7, (y0 + eps * v), ca).double()
-    fm = vf(0.7, (y0 - eps * v), ca).double()
-    rhs = float(((fp - fm) * g.double()).sum() / (2 * eps))
-    assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)
+TC = _lib.PEG_FLAG_TENSOR_CORES
+FAST = _lib.PEG_FLAG_TENSOR_CORES | _lib.PEG_FLAG_TF32_FAST
+
+
+@pytest.mark.parametrize("flags", [0, TC], ids=["ffma", "tcgen05"])
+@pytest.mark.parametrize("n,h,e,L", [(1000, 64, 16, 3), (1000, 64, 0, 3), (515, 32, 0, 2), (300, 32, 3, 2), (129, 64, 8, 3)])
+def test_vector_field_and_vjp_at_twitter_size_against_oracle(cuda, n, h, e, L, flags):
+    """One evaluation + VJP at C4 (Twitter) size against the fp64 oracle (a single evaluation is cheap on CPU).
+    flags=tcgen05 runs the n x n x d contractions on the tensor cores (3xTF32 split: same fp32 tolerance)."""
+    p = R.make_problem(n=n, h=h, e=e, L=L, T=3, t1=2, dt0=0.5, seed=21)
+    p64 = R.problem_to(p, torch.float64)
+    vf, term, args = device_model(p, cuda, flags=flags)
+    t = 1.3
+    y = p.y0.to(cuda).requires_grad_(True)
+    dy = term(t, y, args)
+    (dy * p.gyT.to(cuda)).sum().backward()
+    layers = R.params_to(p64.layers, requires_grad=True)
+    q = R.Problem(p64.n, p64.h, p64.e, p64.L, p64.ts, p64.coeffs_adj, p64.x_coeffs, p64.y0, layers, p64.step_ts, p64.gyT)
+    y64 = p64.y0.clone().requires_grad_(True)
+    ref = _vf_oracle(q, t, y64)
+    (ref * p64.gyT).sum().backward()
+    assert rel_err(dy.detach(), ref.detach()) < 2e-5
+    assert rel_err(y.grad, y64.grad) < 5e-5
+    for l, (got, lp) in enumerate(zip(product_grads_as_oracle(vf), layers)):
+        for name, g, r in zip(("fusion", "W", "b", "nw", "nb"), got, lp.tensors()):
+            assert rel_err(g, r.grad) < 3e-4, (l, name)
+
+
+def test_tf32_fast_mode_has_its_own_looser_tolerance(cuda):
+    """PEG_FLAG_TF32_FAST (single-pass TF32, rna-rounded operands): stated tolerance 5e-3 on Z_T."""
+    g = np.load(os.path.join(GOLD, "england_like.npz"))
+    p = R.make_problem(**GOLDEN_CASES["england_like"])
+    vf, term, args = device_model(p, cuda, flags=FAST)
+    sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 3.0, 0.1, p.y0.to(cuda), args)
+    err = rel_err(sol.ys[-1], g["yT64"])
+    assert err < 5e-3, err
