@@ -18,6 +18,7 @@
 // fp32 parity: 3xTF32 (hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM); PEG_FLAG_TF32_FAST drops
 // the two correction products.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "peg_tc.cuh"
 
@@ -525,7 +526,8 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   const int stage_bytes = na * sp * TC_ATILE + sp * p.nd * TC_BK * 4;
   int stages = (200 * 1024) / stage_bytes;
   stages = stages > 4 ? 4 : stages;
-  if (stages < 2) return PEG_ERR_UNSUPPORTED;
+  if (const char* ev = getenv("PEG_TC_STAGES")) { int v = atoi(ev); if (v >= 1 && v <= stages) stages = v; }
+  if (stages < 1) return PEG_ERR_UNSUPPORTED;
   p.stages = stages;
   p.tmem_cols = tmem_cols_pow2((bwd ? 4 : 1) * p.nd);
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (3 * stages + 2) + 64;
