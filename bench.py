@@ -145,6 +145,8 @@ def run_ours(args):
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
         wl["B"] = args.batch
+    if args.t1 > 0:
+        wl["t1_solve"] = args.t1
     n, h, e, L, T, B = wl["n"], wl["h"], wl["e"], wl["L"], wl["T"], wl["B"]
     flags = 0 if args.no_tensor_cores else _lib.PEG_FLAG_TENSOR_CORES
     if args.tf32_fast:
@@ -158,14 +160,15 @@ def run_ours(args):
     pc = P.pack_control(ts, cadj, xco)
     del cadj, xco
     torch.cuda.empty_cache()
-    step_ts = P.constant_step_table(0.0, wl["t1"], wl["dt0"])
+    t1_solve = wl.get("t1_solve", wl["t1"])
+    step_ts = P.constant_step_table(0.0, t1_solve, wl["dt0"])
     S = len(step_ts) - 1
     l = _lib.lib()
 
     def solve_step(pc_, y0_):
         vf.zero_grad(set_to_none=True)
         y = y0_.detach().requires_grad_(True)
-        sol = P.diffeqsolve(term, P.Tsit5(), 0.0, wl["t1"], wl["dt0"], y, [pc_, None] if e > 0 else pc_,
+        sol = P.diffeqsolve(term, P.Tsit5(), 0.0, t1_solve, wl["dt0"], y, [pc_, None] if e > 0 else pc_,
                             stepsize_controller=P.ConstantStepSize(), saveat=P.SaveAt(t1=True))
         loss = (sol.ys[-1] * gy).sum()
         loss.backward()
@@ -256,6 +259,9 @@ def run_ours(args):
                 "peak_source": pk["src"] + (" hbm_gbs" if bound == "hbm" else " bf16_tflops_sustained/2 (tf32)"),
                 "traffic": None, "achieved_gbs": gbs, "achieved_tflops": tfs, "avg_launch_us": tot_ms / tot_timed * 1e3,
                 "launches_timed": tot_timed, "share_of_step": share,
+                "fwd_avg_us": prof["fwd"]["ms"] / max(prof["fwd"]["timed"], 1) * 1e3, "bwd_avg_us": prof["bwd"]["ms"] / max(prof["bwd"]["timed"], 1) * 1e3,
+                "fwd_gbs": prof["fwd"]["bytes"] * prof["fwd"]["timed"] / max(prof["fwd"]["ms"], 1e-9) / 1e6,
+                "bwd_gbs": prof["bwd"]["bytes"] * prof["bwd"]["timed"] / max(prof["bwd"]["ms"], 1e-9) / 1e6,
                 "algorithmic_bytes_per_launch": prof["fwd"]["bytes"], "l2_note": "planes %s L2 (126 MB)" % ("fit in" if 16.0 * n * n * B <= 126e6 else "exceed")}
 
     cpu_base = None
@@ -356,6 +362,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample-steps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--t1", type=float, default=0.0, help="profiling only: shorten the solve to [0, t1] (fewer solver steps)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

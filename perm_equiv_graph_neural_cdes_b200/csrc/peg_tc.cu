@@ -87,6 +87,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// streaming 128-bit load: read-only path, do not allocate in L1 (every plane byte is used once per CTA)
+__device__ __forceinline__ float4 ldg_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -206,24 +213,27 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     }
     const float* P = a.planes + (size_t)b * a.graph_stride + (size_t)sc.interval * 4 * n * ldn;
     const size_t pstride = (size_t)n * ldn;
-    // direct item: thread -> (row r = tid/2, 16 consecutive k starting at 16*(tid&1))
-    const int d_r = tid >> 1, d_half = tid & 1;
-    // transposed item: thread -> (k-quad kq = lane&7, i-quad iq = warp*4 + (lane>>3)) : a 4(k) x 4(i) micro tile
-    const int t_kq = lane & 7, t_iq = warp * 4 + (lane >> 3);
+    // Every warp-level LDG.128 covers four full 128-B lines (the L1TEX tag stage is the scarce resource) and
+    // every quarter-warp STS.128 hits eight distinct 16-B bank groups of the swizzled operand tile.
+    // direct item (128 rows x 32 k): warp w owns rows [16w, 16w+16); per load: 4 rows x 128 B
+    const int d_rsub = lane >> 3, d_chunk = lane & 7;
+    // transposed item (32 k-rows x 128 i): thread owns a 4(k) x 4(i) micro tile; per load: 4 rows x 128 B
+    const int t_iq = 8 * (warp >> 1) + 2 * ((lane >> 3) & 3) + (lane & 1);
+    const int t_kq = 4 * (warp & 1) + ((lane >> 1) & 3);
 
     float4 buf[16];  // prefetched plane data of the next item: [plane][4]
     auto issue_loads = [&](int j) {
       const int s = j >> 1, type = j & 1;
       if (type == 0) {
         const int kc = (4 * I + s) % nkc;
-        const int gi = I * TC_BM + d_r, gk = kc * TC_BK + d_half * 16;
+        const int gk = kc * TC_BK + 4 * d_chunk;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int k = gk + 4 * c;
-            buf[q * 4 + c] = (gi < n && k < ldn) ? __ldg(reinterpret_cast<const float4*>(P + q * pstride + (size_t)gi * ldn + k))
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int it = 0; it < 4; ++it) {
+            const int gi = I * TC_BM + 16 * warp + 4 * it + d_rsub;
+            buf[q * 4 + it] = (gi < n && gk < ldn) ? ldg_stream(P + q * pstride + (size_t)gi * ldn + gk)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
           }
       } else {
         const int kc = ((4 * I - s) % nkc + nkc) % nkc;
@@ -233,7 +243,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const int gk = kc * TC_BK + 4 * t_kq + kk;
-            buf[q * 4 + kk] = (gk < n && gi < ldn) ? __ldg(reinterpret_cast<const float4*>(P + q * pstride + (size_t)gk * ldn + gi))
+            buf[q * 4 + kk] = (gk < n && gi < ldn) ? ldg_stream(P + q * pstride + (size_t)gk * ldn + gi)
                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
           }
       }
@@ -248,15 +258,15 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       float vals[NA][16];
       if (type == 0) {
         const int kc = (4 * I + s) % nkc;
-        const int gk = kc * TC_BK + d_half * 16;
+        const int gk = kc * TC_BK + 4 * d_chunk;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 4; ++c) {   // c = row iteration `it`; the 4 floats are 4 consecutive k
           const float4 e0 = buf[0 * 4 + c], e1 = buf[1 * 4 + c], e2 = buf[2 * 4 + c], e3 = buf[3 * 4 + c];
           const float x0[4] = {e0.x, e0.y, e0.z, e0.w}, x1[4] = {e1.x, e1.y, e1.z, e1.w};
           const float x2[4] = {e2.x, e2.y, e2.z, e2.w}, x3[4] = {e3.x, e3.y, e3.z, e3.w};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const bool ok = (gk + 4 * c + u) < n;
+            const bool ok = (gk + u) < n;
 #pragma unroll
             for (int v = 0; v < NA; ++v) {
               const float val = wdir[v][0] * x0[u] + wdir[v][1] * x1[u] + wdir[v][2] * x2[u] + wdir[v][3] * x3[u];
@@ -295,7 +305,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         for (int c = 0; c < 4; ++c) {
           // 16-byte chunk (4 consecutive k) of one row
           int r, chunk;
-          if (type == 0) { r = d_r; chunk = d_half * 4 + c; }
+          if (type == 0) { r = 16 * warp + 4 * c + d_rsub; chunk = d_chunk; }
           else           { r = 4 * t_iq + c; chunk = t_kq; }
           const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
           float h4[4], l4[4];
