@@ -297,18 +297,20 @@ __global__ void __launch_bounds__(256) k_norm_linear(const float* __restrict__ Z
 
 // =====================================================================================
 // column reductions: cb[b][0][c] = sum_i V[b,i,c] ; cb[b][1][c] = sum_i vec[b][i] V[b,i,c]
-// grid (ceil(d/32), B), block (32, 8)
+// grid (ceil(d/32), ceil(n/CS_ROWS), B), block (32, 8); cb must be zeroed first (partial sums are atomically added)
 // =====================================================================================
+constexpr int CS_ROWS = 256;
 __global__ void __launch_bounds__(256) k_colsums(const float* __restrict__ V, int n, int d,
                                                  const float* __restrict__ vec, size_t vec_stride,
                                                  float* __restrict__ cb) {
   __shared__ float s0[8][33], s1[8][33];
-  const int b = blockIdx.y, c = blockIdx.x * 32 + threadIdx.x;
+  const int b = blockIdx.z, c = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * CS_ROWS, r1 = min(n, r0 + CS_ROWS);
   const float* Vb = V + (size_t)b * n * d;
   const float* vb = vec ? vec + (size_t)b * vec_stride : nullptr;
   float a0 = 0.f, a1 = 0.f;
   if (c < d) {
-    for (int i = threadIdx.y; i < n; i += 8) {
+    for (int i = r0 + threadIdx.y; i < r1; i += 8) {
       const float v = Vb[(size_t)i * d + c];
       a0 += v;
       if (vb) a1 = fmaf(vb[i], v, a1);
@@ -320,8 +322,8 @@ __global__ void __launch_bounds__(256) k_colsums(const float* __restrict__ V, in
   if (threadIdx.y == 0 && c < d) {
 #pragma unroll
     for (int k = 1; k < 8; ++k) { a0 += s0[k][threadIdx.x]; a1 += s1[k][threadIdx.x]; }
-    cb[((size_t)b * 2 + 0) * d + c] = a0;
-    cb[((size_t)b * 2 + 1) * d + c] = a1;
+    atomicAdd(&cb[((size_t)b * 2 + 0) * d + c], a0);
+    if (vb) atomicAdd(&cb[((size_t)b * 2 + 1) * d + c], a1);
   }
 }
 

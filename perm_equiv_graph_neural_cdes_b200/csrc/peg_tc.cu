@@ -221,61 +221,83 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     const int t_iq = 8 * (warp >> 1) + 2 * ((lane >> 3) & 3) + (lane & 1);
     const int t_kq = 4 * (warp & 1) + ((lane >> 1) & 3);
 
-    float4 buf[16];  // prefetched plane data of the next item: [plane][4]
-    auto issue_loads = [&](int j) {
-      const int s = j >> 1, type = j & 1;
-      if (type == 0) {
-        const int kc = (4 * I + s) % nkc;
-        const int gk = kc * TC_BK + 4 * d_chunk;
+    // Two register buffers: buf0 always holds a direct item (even j), buf1 a transposed item (odd j); each is
+    // refilled for item j+2 right after item j has been converted, so ~2 items (128 KB per SM) are in flight.
+    float4 buf0[16], buf1[16];
+    auto load_direct = [&](int j, float4 (&buf)[16]) {
+      const int kc = (4 * I + (j >> 1)) % nkc;
+      const int gk = kc * TC_BK + 4 * d_chunk;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < 4; ++q)
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int gi = I * TC_BM + 16 * warp + 4 * it + d_rsub;
-            buf[q * 4 + it] = (gi < n && gk < ldn) ? ldg_stream(P + q * pstride + (size_t)gi * ldn + gk)
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-      } else {
-        const int kc = ((4 * I - s) % nkc + nkc) % nkc;
-        const int gi = I * TC_BM + 4 * t_iq;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const int gk = kc * TC_BK + 4 * t_kq + kk;
-            buf[q * 4 + kk] = (gk < n && gi < ldn) ? ldg_stream(P + q * pstride + (size_t)gk * ldn + gi)
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-      }
+        for (int it = 0; it < 4; ++it) {
+          const int gi = I * TC_BM + 16 * warp + 4 * it + d_rsub;
+          buf[q * 4 + it] = (gi < n && gk < ldn) ? ldg_stream(P + q * pstride + (size_t)gi * ldn + gk)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     };
-
-    issue_loads(0);
-    for (int j = 0; j < items; ++j) {
+    auto load_transposed = [&](int j, float4 (&buf)[16]) {
+      const int kc = ((4 * I - (j >> 1)) % nkc + nkc) % nkc;
+      const int gi = I * TC_BM + 4 * t_iq;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int gk = kc * TC_BK + 4 * t_kq + kk;
+          buf[q * 4 + kk] = (gk < n && gi < ldn) ? ldg_stream(P + q * pstride + (size_t)gk * ldn + gi)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    // store one 16-byte chunk (4 consecutive k of row r) as tf32 hi (+ lo) into the swizzled K-major tile
+    auto store_chunk = [&](uint32_t hi_base, int r, int chunk, const float (&x)[4]) {
+      const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+      float h4[4], l4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        h4[u] = tf32_rna(x[u]);
+        l4[u] = x[u] - h4[u];
+      }
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "f"(h4[0]), "f"(h4[1]), "f"(h4[2]), "f"(h4[3]) : "memory");
+      if (split)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + TC_ATILE + off), "f"(l4[0]), "f"(l4[1]), "f"(l4[2]), "f"(l4[3]) : "memory");
+    };
+    auto convert_direct = [&](int j, float4 (&buf)[16]) {
       const int st = j % p.stages;
       const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
-      const int s = j >> 1, type = j & 1;
-      // consume the prefetched registers into local combos BEFORE overwriting buf with the next prefetch
-      float vals[NA][16];
-      if (type == 0) {
-        const int kc = (4 * I + s) % nkc;
-        const int gk = kc * TC_BK + 4 * d_chunk;
+      const int kc = (4 * I + (j >> 1)) % nkc;
+      const int gk = kc * TC_BK + 4 * d_chunk;
+      mbar_wait(empty(st), ph ^ 1u);   // the MMAs that read this stage's previous contents have completed
+      const uint32_t a_base = smem_base + st * stage_bytes;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {   // c = row iteration `it`; the 4 floats are 4 consecutive k
-          const float4 e0 = buf[0 * 4 + c], e1 = buf[1 * 4 + c], e2 = buf[2 * 4 + c], e3 = buf[3 * 4 + c];
+      for (int v = 0; v < NA; ++v) {
+        const uint32_t hi_base = a_base + v * (split ? 2 : 1) * TC_ATILE;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const float4 e0 = buf[0 * 4 + it], e1 = buf[1 * 4 + it], e2 = buf[2 * 4 + it], e3 = buf[3 * 4 + it];
           const float x0[4] = {e0.x, e0.y, e0.z, e0.w}, x1[4] = {e1.x, e1.y, e1.z, e1.w};
           const float x2[4] = {e2.x, e2.y, e2.z, e2.w}, x3[4] = {e3.x, e3.y, e3.z, e3.w};
+          float x[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const bool ok = (gk + u) < n;
-#pragma unroll
-            for (int v = 0; v < NA; ++v) {
-              const float val = wdir[v][0] * x0[u] + wdir[v][1] * x1[u] + wdir[v][2] * x2[u] + wdir[v][3] * x3[u];
-              vals[v][c * 4 + u] = ok ? val : 0.f;
-            }
+            const float val = wdir[v][0] * x0[u] + wdir[v][1] * x1[u] + wdir[v][2] * x2[u] + wdir[v][3] * x3[u];
+            x[u] = (gk + u) < n ? val : 0.f;
           }
+          store_chunk(hi_base, 16 * warp + 4 * it + d_rsub, d_chunk, x);
         }
-      } else {
-        const int gi = I * TC_BM + 4 * t_iq;
+      }
+      fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(full_a(st));
+    };
+    auto convert_transposed = [&](int j, float4 (&buf)[16]) {
+      const int st = j % p.stages;
+      const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
+      const int gi = I * TC_BM + 4 * t_iq;
+      mbar_wait(empty(st), ph ^ 1u);
+      const uint32_t a_base = smem_base + st * stage_bytes;
+#pragma unroll
+      for (int v = 0; v < NA; ++v) {
+        const uint32_t hi_base = a_base + v * (split ? 2 : 1) * TC_ATILE;
+        float vals[4][4];  // [i][k]: the 4x4 micro tile transposed in registers
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const float4 e0 = buf[0 * 4 + kk], e1 = buf[1 * 4 + kk], e2 = buf[2 * 4 + kk], e3 = buf[3 * 4 + kk];
@@ -283,45 +305,24 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
           const float x2[4] = {e2.x, e2.y, e2.z, e2.w}, x3[4] = {e3.x, e3.y, e3.z, e3.w};
 #pragma unroll
           for (int ii = 0; ii < 4; ++ii) {
-            const bool ok = (gi + ii) < n;
-#pragma unroll
-            for (int v = 0; v < NA; ++v) {
-              const float val = wtr[v][0] * x0[ii] + wtr[v][1] * x1[ii] + wtr[v][2] * x2[ii] + wtr[v][3] * x3[ii];
-              vals[v][ii * 4 + kk] = ok ? val : 0.f;   // transposed in registers: [i][k]
-            }
+            const float val = wtr[v][0] * x0[ii] + wtr[v][1] * x1[ii] + wtr[v][2] * x2[ii] + wtr[v][3] * x3[ii];
+            vals[ii][kk] = (gi + ii) < n ? val : 0.f;
           }
         }
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) store_chunk(hi_base, 4 * t_iq + ii, t_kq, vals[ii]);
       }
-      if (j + 1 < items) issue_loads(j + 1);
-
-      // wait until the MMAs that read this stage's previous contents have completed
-      mbar_wait(empty(st), ph ^ 1u);
-      const uint32_t a_base = smem_base + st * stage_bytes;
-#pragma unroll
-      for (int v = 0; v < NA; ++v) {
-        const uint32_t hi_base = a_base + v * (split ? 2 : 1) * TC_ATILE;
-        const uint32_t lo_base = hi_base + TC_ATILE;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          // 16-byte chunk (4 consecutive k) of one row
-          int r, chunk;
-          if (type == 0) { r = 16 * warp + 4 * c + d_rsub; chunk = d_chunk; }
-          else           { r = 4 * t_iq + c; chunk = t_kq; }
-          const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
-          float h4[4], l4[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float x = vals[v][c * 4 + u];
-            h4[u] = tf32_rna(x);
-            l4[u] = x - h4[u];
-          }
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "f"(h4[0]), "f"(h4[1]), "f"(h4[2]), "f"(h4[3]) : "memory");
-          if (split)
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + off), "f"(l4[0]), "f"(l4[1]), "f"(l4[2]), "f"(l4[3]) : "memory");
-        }
-      }
-      fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      fence_proxy_async();
       mbar_arrive(full_a(st));
+    };
+
+    load_direct(0, buf0);
+    load_transposed(1, buf1);
+    for (int j = 0; j < items; j += 2) {   // items = 2 * nkc is even: even j direct, odd j transposed
+      convert_direct(j, buf0);
+      if (j + 2 < items) load_direct(j + 2, buf0);
+      convert_transposed(j + 1, buf1);
+      if (j + 3 < items) load_transposed(j + 3, buf1);
     }
   } else if (warp == 8) {
     // =========================== TMA producer (B operand) ===========================

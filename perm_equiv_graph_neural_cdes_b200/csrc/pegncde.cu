@@ -179,7 +179,8 @@ static int norm_linear(Ctx& c, int l, const float* Zin, float* M, float* Nout) {
 }
 
 static int colsums(Ctx& c, const float* V, int dcols, size_t vec_off, bool with_vec, float* cb) {
-  dim3 grid((dcols + 31) / 32, c.d.B), block(32, 8);
+  dim3 grid((dcols + 31) / 32, (c.d.n + CS_ROWS - 1) / CS_ROWS, c.d.B), block(32, 8);
+  PEG_CUDA(cudaMemsetAsync(cb, 0, (size_t)c.d.B * 2 * dcols * sizeof(float), c.st));
   k_colsums<<<grid, block, 0, c.st>>>(V, c.d.n, dcols, with_vec ? c.w.svec + vec_off : nullptr, c.sv_stride, cb);
   PEG_LAUNCH_CHECK();
   return PEG_OK;
