@@ -63,7 +63,7 @@ enum {
 typedef struct PegDims {
   int32_t B;     /* graphs (trajectories) in the batch; each has its own control path      */
   int32_t n;     /* nodes                                                                  */
-  int32_t ldn;   /* row pitch of the coefficient planes in floats; >= n, multiple of 4     */
+  int32_t ldn;   /* padded node count of the tiled coefficient planes: n rounded up to 32   */
   int32_t h;     /* hidden_dim = width of the state y [n,h] and of every hidden layer      */
   int32_t e;     /* data_embed_dim; 0 = plain ODETerm(vector_field) (no CDE wrapper)       */
   int32_t L;     /* num_layers of ConvEquivFusionLayer                                     */
@@ -76,7 +76,10 @@ typedef struct PegDims {
  * Coefficient order everywhere is (a, b, c, d):  X(t) = a + s(b + s(c + s d)), s = t - ts[i]. */
 typedef struct PegControl {
   const float* ts;         /* [B, T]            knot times                                         */
-  const float* adj_coef;   /* [B, T-1, 4, n, ldn] adjacency channel of the reference's coeffs       */
+  const float* adj_coef;   /* [B, T-1, 4*ldn*ldn] adjacency channel of the reference's coeffs, four planes
+                              (a,b,c,d) zero padded to ldn x ldn and stored as 32x32 tiles of 16 KB
+                              (exact element order: peg_tile_off in csrc/peg_common.cuh; written by
+                              pegncde_pack_adj)                                                     */
   const float* adj_rowsum; /* [B, T-1, 4, n]    row sums of each plane                              */
   const float* adj_diag;   /* [B, T-1, 4, n]    diagonal of each plane                              */
   const float* adj_total;  /* [B, T-1, 4]       total of each plane                                 */
@@ -101,7 +104,7 @@ int pegncde_param_offsets(const PegDims* dims, int64_t* offsets /* [5*L] */);
 int pegncde_pack_adj(peg_stream_t stream, const PegDims* dims, const float* d, const float* c, const float* b,
                      const float* a, float* adj_coef, float* adj_rowsum, float* adj_diag, float* adj_total,
                      float* tch_coef);
-/* same for already-planar adjacency planes (adj_coef given): fills the statistics only;
+/* same for already-tiled adjacency planes (adj_coef given): fills the statistics only;
  * tch_coef is written as d(time)/dt == 1 (b=1, c=d=0). */
 int pegncde_adj_stats(peg_stream_t stream, const PegDims* dims, const float* adj_coef, float* adj_rowsum,
                       float* adj_diag, float* adj_total, float* tch_coef);

@@ -8,7 +8,7 @@ from ._lib import LIB_PATH, PegControl, PegDims, PegError, lib  # noqa: F401
 
 lib()  # raise ImportError right here if libpegncde.so is missing
 
-from .control import CubicInterpolation, PackedControl, backward_hermite_coefficients, pack_control, pack_planar  # noqa: E402,F401
+from .control import CubicInterpolation, PackedControl, backward_hermite_coefficients, pack_control  # noqa: E402,F401
 from .models import MLP, GraphNeuralCDE, PGTGraphNeuralCDE  # noqa: E402,F401
 from .solve import ConstantStepSize, ODETerm, SaveAt, Solution, Tsit5, constant_step_table, diffeqsolve, tsit5_step  # noqa: E402,F401
 from .vector_field import CDEWrapperVectorField, ConvEquivFusionLayer, ConvLayer, PermEquivGraphVectorField  # noqa: E402,F401

@@ -31,8 +31,22 @@ def backward_hermite_coefficients(ts: torch.Tensor, ys: torch.Tensor) -> Tuple[t
     return d, c, b, a
 
 
-def _pad4(n: int) -> int:
-    return (n + 3) // 4 * 4
+def _pad32(n: int) -> int:
+    return (n + 31) // 32 * 32
+
+
+def tiled_offsets(npad: int) -> torch.Tensor:
+    """Float offset, inside one slab, of element (plane q, row i, col k) of the 32x32-tiled plane layout
+    (``peg_tile_off`` in csrc/peg_common.cuh) as an int64 tensor [4, npad, npad] -- for inspection / tests."""
+    nt = npad // 32
+    i = torch.arange(npad).view(1, npad, 1)
+    k = torch.arange(npad).view(1, 1, npad)
+    q = torch.arange(4).view(4, 1, 1)
+    rt, ct, r, c = i // 32, k // 32, i % 32, k % 32
+    rq, m, cq, e = r // 4, r % 4, c // 4, c % 4
+    s = (rq - cq) % 8
+    g, lane = s // 4, (s % 4) * 8 + cq
+    return (rt * nt + ct) * 4096 + ((g * 4 + q) * 4 + m) * 128 + lane * 4 + e
 
 
 class CubicInterpolation:
@@ -75,10 +89,10 @@ class PackedControl:
 
     def __init__(self, B: int, n: int, T: int, e: int, device):
         self.B, self.n, self.T, self.e = B, n, T, e
-        self.ldn = _pad4(n)
+        self.ldn = _pad32(n)  # planes are stored as 32x32 tiles, zero padded
         f = dict(dtype=torch.float32, device=device)
         self.ts = torch.empty((B, T), **f)
-        self.adj_coef = torch.empty((B, T - 1, 4, n, self.ldn), **f)
+        self.adj_coef = torch.empty((B, T - 1, 4 * self.ldn * self.ldn), **f)
         self.adj_rowsum = torch.empty((B, T - 1, 4, n), **f)
         self.adj_diag = torch.empty((B, T - 1, 4, n), **f)
         self.adj_total = torch.empty((B, T - 1, 4), **f)
@@ -87,6 +101,12 @@ class PackedControl:
 
     def dims(self, h: int, L: int, flags: int = 0) -> PegDims:
         return PegDims(self.B, self.n, self.ldn, h, self.e, L, self.T, flags)
+
+    def dense_planes(self) -> torch.Tensor:
+        """Un-tiles ``adj_coef`` to [B, T-1, 4(a,b,c,d), n, n] (inspection / tests)."""
+        off = tiled_offsets(self.ldn).to(self.adj_coef.device)
+        dense = self.adj_coef[:, :, off.reshape(-1)].reshape(self.B, self.T - 1, 4, self.ldn, self.ldn)
+        return dense[..., : self.n, : self.n]
 
     def struct(self) -> PegControl:
         return PegControl(
@@ -151,29 +171,4 @@ def pack_control(
         )
     # keep the sources alive until the pack kernels have run (stream-ordered)
     pc._keepalive = (cad, cx)
-    return pc
-
-
-def pack_planar(ts: torch.Tensor, planes: torch.Tensor, x_coef: Optional[torch.Tensor] = None) -> PackedControl:
-    """Already-planar adjacency planes ``[B, T-1, 4(a,b,c,d), n, ldn]`` (zero padded) -> PackedControl
-    (statistics via ``pegncde_adj_stats``; time channel d t/dt == 1).  Used by the benchmark's synthetic
-    inputs, which are generated directly on the device in the kernel layout."""
-    device = planes.device
-    B, Tm1, _, n, ldn = planes.shape
-    e = 0 if x_coef is None else x_coef.shape[-1] // 2
-    pc = PackedControl.__new__(PackedControl)
-    pc.B, pc.n, pc.T, pc.e, pc.ldn = B, n, Tm1 + 1, e, ldn
-    f = dict(dtype=torch.float32, device=device)
-    pc.ts = _as_batched(ts, 1).to(**f).expand(B, Tm1 + 1).contiguous()
-    pc.adj_coef = planes.contiguous()
-    pc.adj_rowsum = torch.empty((B, Tm1, 4, n), **f)
-    pc.adj_diag = torch.empty((B, Tm1, 4, n), **f)
-    pc.adj_total = torch.empty((B, Tm1, 4), **f)
-    pc.tch_coef = torch.empty((B, Tm1, 3, n), **f)
-    pc.x_coef = x_coef.contiguous() if x_coef is not None else None
-    check(
-        lib().pegncde_adj_stats(_stream_ptr(device), pc.dims(h=4, L=1), pc.adj_coef.data_ptr(), pc.adj_rowsum.data_ptr(),
-                                pc.adj_diag.data_ptr(), pc.adj_total.data_ptr(), pc.tch_coef.data_ptr()),
-        "pegncde_adj_stats",
-    )
     return pc

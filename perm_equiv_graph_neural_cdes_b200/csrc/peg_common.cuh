@@ -51,6 +51,23 @@ __host__ __device__ inline size_t svec_dgA(int n, int L) { return (size_t)(3 * L
 __host__ __device__ inline size_t svec_dgD(int n, int L) { return (size_t)(3 * L + 4) * n; }
 __host__ __device__ inline size_t svec_xd(int n, int L) { return (size_t)(3 * L + 5) * n; }
 
+// ---- HBM layout of the cubic-coefficient planes (adjacency channel) -----------------------------------
+// One slab = the four planes (a,b,c,d) of one cubic piece of one graph, npad x npad with npad = n rounded
+// up to 32 (zero padded).  The slab is stored as 32x32 tiles of 16 KB: [row tile][col tile] -> [g][plane][m][lane][e]
+// where the 32x32 plane tile is cut into 8x8 micro tiles of 4x4 floats, micro tile (rq, cq) sits on
+// diagonal s = (rq - cq) & 7, g = s >> 2, lane = ((s & 3) << 3) | cq, m = row inside the micro tile,
+// e = column inside the micro tile.  Consequences (both are what the converters of peg_tc.cu need):
+//   * a warp-level 128-bit load of (g, plane, m) is 512 contiguous bytes, and a whole item is 4 x 16 KB blocks;
+//   * every thread ends up holding a full 4x4 micro tile of all four planes, so the transposed orientation
+//     is free in registers, and both orientations store bank-conflict-free into the swizzled operand tiles.
+__host__ __device__ inline int peg_npad(int n) { return (n + 31) / 32 * 32; }
+__host__ __device__ inline size_t peg_tile_off(int i, int k, int q, int nt) {
+  const int rt = i >> 5, ct = k >> 5, r = i & 31, c = k & 31;
+  const int rq = r >> 2, m = r & 3, cq = c >> 2, e = c & 3;
+  const int s = (rq - cq) & 7, g = s >> 2, lane = ((s & 3) << 3) | cq;
+  return ((size_t)rt * nt + ct) * 4096 + (size_t)(((g * 4 + q) * 4 + m) * 128 + lane * 4 + e);
+}
+
 // Tsit5 tableau (Tsitouras 2011) -- the tableau behind diffrax.Tsit5.
 struct Tsit5 {
   double c[7];
@@ -92,7 +109,7 @@ struct ContractArgs {
   const float* colbuf;   // [B][2][d]
   float* out;            // [B,n,d]
   float* g_fus;          // bwd only: gradient of the 16 fusion scalars (atomicAdd)
-  int n, ldn, d, layer;
+  int n, ldn /* = npad */, d, layer;
   int relu, scale_tg;
 };
 

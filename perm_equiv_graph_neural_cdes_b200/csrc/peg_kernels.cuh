@@ -35,44 +35,43 @@ __device__ __forceinline__ float block_sum(float v, float* sh /* >= 33 floats */
 // reference layout: d,c,b,a each [B, T-1, n, n, 2], last axis (time, adjacency)
 // =====================================================================================
 
-// grid (ceil(n/64), T-1, B), block 256: one warp per row, 8 rows per warp
+// grid (nt*nt tiles, T-1, B), block 256: one block per 32x32 tile.  Source is either the reference layout
+// (d,c,b,a each [B,T-1,n,n,2]) or, for pegncde_adj_stats, the already tiled planes (tiled_in).
 __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, const float* __restrict__ cc,
                                                   const float* __restrict__ cb, const float* __restrict__ ca,
-                                                  const float* __restrict__ planar_in, int n, int ldn, int Tm1,
+                                                  const float* __restrict__ tiled_in, int n, int npad, int Tm1,
                                                   float* __restrict__ adj_coef, float* __restrict__ rowsum,
                                                   float* __restrict__ diag, float* __restrict__ total) {
   const int b = blockIdx.z, iv = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = npad >> 5;
+  const int rt = blockIdx.x / nt, ct = blockIdx.x % nt;
+  const int lane = threadIdx.x & 31;
   const size_t slab = ((size_t)b * Tm1 + iv);
+  const size_t slab_off = slab * 4 * (size_t)npad * npad;
   const float* src[4] = {ca, cb, cc, cd};  // (a,b,c,d) order
   float tot[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int q = 0; q < 8; ++q) {
-    const int r = blockIdx.x * 64 + q * 8 + warp;
-    if (r >= n) break;
-    float rs[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = lane; j < ldn; j += 32) {
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        float v = 0.f;
-        const size_t po = ((slab * 4 + p) * n + r) * (size_t)ldn + j;
-        if (j < n) {
-          if (planar_in) {
-            v = planar_in[po];
-          } else {
-            const float2 tv = reinterpret_cast<const float2*>(src[p])[(slab * n + r) * (size_t)n + j];
-            v = tv.y;
-          }
-          rs[p] += v;
-          if (j == r) diag[(slab * 4 + p) * n + r] = v;
-        }
-        if (!planar_in) adj_coef[po] = v;
-      }
-    }
+  for (int idx = threadIdx.x; idx < 1024; idx += 256) {
+    const int r = idx >> 5, c = idx & 31;      // r is warp-uniform, c == lane
+    const int i = rt * 32 + r, k = ct * 32 + c;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      rs[p] = warp_sum(rs[p]);
-      if (lane == 0) rowsum[(slab * 4 + p) * n + r] = rs[p];
-      tot[p] += rs[p];
+      float v = 0.f;
+      const size_t to = slab_off + peg_tile_off(i, k, p, nt);
+      if (i < n && k < n) {
+        if (tiled_in) {
+          v = tiled_in[to];
+        } else {
+          const float2 tv = reinterpret_cast<const float2*>(src[p])[(slab * n + i) * (size_t)n + k];
+          v = tv.y;
+        }
+        if (i == k) diag[(slab * 4 + p) * n + i] = v;
+      }
+      if (!tiled_in) adj_coef[to] = v;
+      const float rs = warp_sum(v);
+      if (lane == 0 && i < n) {
+        atomicAdd(&rowsum[(slab * 4 + p) * n + i], rs);
+        tot[p] += rs;
+      }
     }
   }
   if (lane == 0) {
@@ -347,7 +346,7 @@ __global__ void __launch_bounds__(256) k_dual_contract(ContractArgs a) {
   __shared__ float red[40];
   const int tid = threadIdx.x;
   const int b = blockIdx.z, i0 = blockIdx.x * CT_TI, c0 = blockIdx.y * CT_TC;
-  const int n = a.n, ldn = a.ldn, d = a.d;
+  const int n = a.n, d = a.d;
   const StageScalars sc = a.sc[b];
   const float alpha = 1.f + a.fus[0], beta = 1.f + a.fus[1], gamma = a.fus[2], delta = a.fus[3];
   float wx[4], wy[4];
@@ -361,8 +360,8 @@ __global__ void __launch_bounds__(256) k_dual_contract(ContractArgs a) {
       wy[p] = sc.wD[p];
     }
   }
-  const float* P = a.planes + (size_t)b * a.graph_stride + (size_t)sc.interval * 4 * n * ldn;
-  const size_t pstride = (size_t)n * ldn;
+  const int npad = a.ldn, nt = npad >> 5;
+  const float* P = a.planes + (size_t)b * a.graph_stride + (size_t)sc.interval * 4 * npad * npad;
   const float* Vb = a.V + (size_t)b * n * d;
 
   float acc[NACC][4][4];
@@ -384,9 +383,9 @@ __global__ void __launch_bounds__(256) k_dual_contract(ContractArgs a) {
       float4 p[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) p[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gi < n && gk < ldn) {
+      if (gi < npad && gk < npad) {   // padding is zero-filled by the pack pre-pass
 #pragma unroll
-        for (int q = 0; q < 4; ++q) p[q] = *reinterpret_cast<const float4*>(P + q * pstride + (size_t)gi * ldn + gk);
+        for (int q = 0; q < 4; ++q) p[q] = *reinterpret_cast<const float4*>(P + peg_tile_off(gi, gk, q, nt));
       }
       float x0[4], x1[4];
       const float* pf = reinterpret_cast<const float*>(p);
@@ -408,9 +407,9 @@ __global__ void __launch_bounds__(256) k_dual_contract(ContractArgs a) {
       float4 p[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) p[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gk < n && gi < ldn) {
+      if (gk < npad && gi < npad) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) p[q] = *reinterpret_cast<const float4*>(P + q * pstride + (size_t)gk * ldn + gi);
+        for (int q = 0; q < 4; ++q) p[q] = *reinterpret_cast<const float4*>(P + peg_tile_off(gk, gi, q, nt));
       }
       const float* pf = reinterpret_cast<const float*>(p);
       float y0[4], y1[4];

@@ -157,7 +157,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   const ContractArgs& a = p.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, I = blockIdx.x, ntile = blockIdx.y;
-  const int n = a.n, ldn = a.ldn, d = a.d, nd = p.nd;
+  const int n = a.n, d = a.d, nd = p.nd;
   const bool split = p.nsplit == 3;
 
   // ---- shared memory carve-up (1024-B aligned operand tiles) ----
@@ -192,7 +192,11 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-  const StageScalars sc = a.sc[b];
+  const StageScalars* scp = a.sc + b;
+  struct { float wA[4], wD[4]; int interval; } sc;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { sc.wA[q] = scp->wA[q]; sc.wD[q] = scp->wD[q]; }
+  sc.interval = scp->interval;
   const int nkc = p.nkc;
   const int items = 2 * nkc;
   const float alpha = 1.f + a.fus[0], beta = 1.f + a.fus[1], gamma = a.fus[2], delta = a.fus[3];
@@ -211,78 +215,55 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         wtr[0][q] = gamma * sc.wA[q] + delta * sc.wD[q];   // Y = p2_0 A + p2_1 A'
       }
     }
-    const float* P = a.planes + (size_t)b * a.graph_stride + (size_t)sc.interval * 4 * n * ldn;
-    const size_t pstride = (size_t)n * ldn;
-    // Every warp-level LDG.128 covers four full 128-B lines (the L1TEX tag stage is the scarce resource) and
-    // every quarter-warp STS.128 hits eight distinct 16-B bank groups of the swizzled operand tile.
-    // direct item (128 rows x 32 k): warp w owns rows [16w, 16w+16); per load: 4 rows x 128 B
-    const int d_rsub = lane >> 3, d_chunk = lane & 7;
-    // transposed item (32 k-rows x 128 i): thread owns a 4(k) x 4(i) micro tile; per load: 4 rows x 128 B
-    const int t_iq = 8 * (warp >> 1) + 2 * ((lane >> 3) & 3) + (lane & 1);
-    const int t_kq = 4 * (warp & 1) + ((lane >> 1) & 3);
+    const int npad = a.ldn, nt = npad >> 5;
+    const float* P = a.planes + (size_t)b * a.graph_stride + (size_t)sc.interval * 4 * npad * npad;
+    // Tiled plane layout (peg_common.cuh): an item is four 16-KB tiles; warp w loads half (g) of tile u, every
+    // warp-level LDG.128 is 512 contiguous bytes and the thread ends up with the 4x4 micro tile (rq, cq) of all
+    // four planes: buf[plane*4 + m] = row 4*rq + m, columns 4*cq .. 4*cq+3 of the 32x32 tile.
+    const int cv_u = warp >> 1, cv_g = warp & 1;
+    const int cv_cq = lane & 7, cv_rq = ((lane & 7) + 4 * cv_g + (lane >> 3)) & 7;
+    const int cv_off = cv_g * 2048 + lane * 4;   // float offset of (g, plane 0, m 0, lane) inside a tile
 
     // Two register buffers: buf0 always holds a direct item (even j), buf1 a transposed item (odd j); each is
     // refilled for item j+2 right after item j has been converted, so ~2 items (128 KB per SM) are in flight.
     float4 buf0[16], buf1[16];
-    auto load_direct = [&](int j, float4 (&buf)[16]) {
-      const int kc = (4 * I + (j >> 1)) % nkc;
-      const int gk = kc * TC_BK + 4 * d_chunk;
+    auto load_tile = [&](int rt, int ct, float4 (&buf)[16]) {
+      if (rt < nt && ct < nt) {
+        const float* base = P + ((size_t)rt * nt + ct) * 4096 + cv_off;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int gi = I * TC_BM + 16 * warp + 4 * it + d_rsub;
-          buf[q * 4 + it] = (gi < n && gk < ldn) ? ldg_stream(P + q * pstride + (size_t)gi * ldn + gk)
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    auto load_transposed = [&](int j, float4 (&buf)[16]) {
-      const int kc = ((4 * I - (j >> 1)) % nkc + nkc) % nkc;
-      const int gi = I * TC_BM + 4 * t_iq;
+          for (int m = 0; m < 4; ++m) buf[q * 4 + m] = ldg_stream(base + (q * 4 + m) * 128);
+      } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const int gk = kc * TC_BK + 4 * t_kq + kk;
-          buf[q * 4 + kk] = (gk < n && gi < ldn) ? ldg_stream(P + q * pstride + (size_t)gk * ldn + gi)
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    // store one 16-byte chunk (4 consecutive k of row r) as tf32 hi (+ lo) into the swizzled K-major tile
-    auto store_chunk = [&](uint32_t hi_base, int r, int chunk, const float (&x)[4]) {
-      const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
-      float h4[4], l4[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        h4[u] = tf32_rna(x[u]);
-        l4[u] = x[u] - h4[u];
+        for (int u = 0; u < 16; ++u) buf[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "f"(h4[0]), "f"(h4[1]), "f"(h4[2]), "f"(h4[3]) : "memory");
+    };
+    auto load_direct = [&](int j, float4 (&buf)[16]) { load_tile(4 * I + cv_u, (4 * I + (j >> 1)) % nkc, buf); };
+    auto load_transposed = [&](int j, float4 (&buf)[16]) { load_tile(((4 * I - (j >> 1)) % nkc + nkc) % nkc, 4 * I + cv_u, buf); };
+    // store one 16-byte chunk (4 consecutive k of row r) as tf32 hi (+ lo) into the swizzled K-major tile
+    auto store_chunk = [&](uint32_t hi_base, int r, int chunk, float x0, float x1, float x2, float x3) {
+      const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+      const float h0 = tf32_rna(x0), h1 = tf32_rna(x1), h2 = tf32_rna(x2), h3 = tf32_rna(x3);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "f"(h0), "f"(h1), "f"(h2), "f"(h3) : "memory");
       if (split)
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + TC_ATILE + off), "f"(l4[0]), "f"(l4[1]), "f"(l4[2]), "f"(l4[3]) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + TC_ATILE + off), "f"(x0 - h0), "f"(x1 - h1), "f"(x2 - h2), "f"(x3 - h3) : "memory");
     };
     auto convert_direct = [&](int j, float4 (&buf)[16]) {
       const int st = j % p.stages;
       const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
-      const int kc = (4 * I + (j >> 1)) % nkc;
-      const int gk = kc * TC_BK + 4 * d_chunk;
       mbar_wait(empty(st), ph ^ 1u);   // the MMAs that read this stage's previous contents have completed
       const uint32_t a_base = smem_base + st * stage_bytes;
 #pragma unroll
       for (int v = 0; v < NA; ++v) {
         const uint32_t hi_base = a_base + v * (split ? 2 : 1) * TC_ATILE;
+        const float w0 = wdir[v][0], w1 = wdir[v][1], w2 = wdir[v][2], w3 = wdir[v][3];
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const float4 e0 = buf[0 * 4 + it], e1 = buf[1 * 4 + it], e2 = buf[2 * 4 + it], e3 = buf[3 * 4 + it];
-          const float x0[4] = {e0.x, e0.y, e0.z, e0.w}, x1[4] = {e1.x, e1.y, e1.z, e1.w};
-          const float x2[4] = {e2.x, e2.y, e2.z, e2.w}, x3[4] = {e3.x, e3.y, e3.z, e3.w};
-          float x[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float val = wdir[v][0] * x0[u] + wdir[v][1] * x1[u] + wdir[v][2] * x2[u] + wdir[v][3] * x3[u];
-            x[u] = (gk + u) < n ? val : 0.f;
-          }
-          store_chunk(hi_base, 16 * warp + 4 * it + d_rsub, d_chunk, x);
+        for (int m = 0; m < 4; ++m) {   // operand row = tile row 4*rq + m, chunk = cq (4 consecutive k)
+          const float4 e0 = buf[0 * 4 + m], e1 = buf[1 * 4 + m], e2 = buf[2 * 4 + m], e3 = buf[3 * 4 + m];
+          store_chunk(hi_base, 32 * cv_u + 4 * cv_rq + m, cv_cq,
+                      w0 * e0.x + w1 * e1.x + w2 * e2.x + w3 * e3.x, w0 * e0.y + w1 * e1.y + w2 * e2.y + w3 * e3.y,
+                      w0 * e0.z + w1 * e1.z + w2 * e2.z + w3 * e3.z, w0 * e0.w + w1 * e1.w + w2 * e2.w + w3 * e3.w);
         }
       }
       fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -291,26 +272,19 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     auto convert_transposed = [&](int j, float4 (&buf)[16]) {
       const int st = j % p.stages;
       const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
-      const int gi = I * TC_BM + 4 * t_iq;
       mbar_wait(empty(st), ph ^ 1u);
       const uint32_t a_base = smem_base + st * stage_bytes;
 #pragma unroll
       for (int v = 0; v < NA; ++v) {
         const uint32_t hi_base = a_base + v * (split ? 2 : 1) * TC_ATILE;
-        float vals[4][4];  // [i][k]: the 4x4 micro tile transposed in registers
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const float4 e0 = buf[0 * 4 + kk], e1 = buf[1 * 4 + kk], e2 = buf[2 * 4 + kk], e3 = buf[3 * 4 + kk];
-          const float x0[4] = {e0.x, e0.y, e0.z, e0.w}, x1[4] = {e1.x, e1.y, e1.z, e1.w};
-          const float x2[4] = {e2.x, e2.y, e2.z, e2.w}, x3[4] = {e3.x, e3.y, e3.z, e3.w};
-#pragma unroll
-          for (int ii = 0; ii < 4; ++ii) {
-            const float val = wtr[v][0] * x0[ii] + wtr[v][1] * x1[ii] + wtr[v][2] * x2[ii] + wtr[v][3] * x3[ii];
-            vals[ii][kk] = (gi + ii) < n ? val : 0.f;
-          }
-        }
-#pragma unroll
-        for (int ii = 0; ii < 4; ++ii) store_chunk(hi_base, 4 * t_iq + ii, t_kq, vals[ii]);
+        const float w0 = wtr[v][0], w1 = wtr[v][1], w2 = wtr[v][2], w3 = wtr[v][3];
+        // operand row = tile column 4*cq + e, chunk = rq: the four k values are the micro tile's rows m = 0..3
+#define PEG_T(comp, m) (w0 * buf[0 * 4 + m].comp + w1 * buf[1 * 4 + m].comp + w2 * buf[2 * 4 + m].comp + w3 * buf[3 * 4 + m].comp)
+        store_chunk(hi_base, 32 * cv_u + 4 * cv_cq + 0, cv_rq, PEG_T(x, 0), PEG_T(x, 1), PEG_T(x, 2), PEG_T(x, 3));
+        store_chunk(hi_base, 32 * cv_u + 4 * cv_cq + 1, cv_rq, PEG_T(y, 0), PEG_T(y, 1), PEG_T(y, 2), PEG_T(y, 3));
+        store_chunk(hi_base, 32 * cv_u + 4 * cv_cq + 2, cv_rq, PEG_T(z, 0), PEG_T(z, 1), PEG_T(z, 2), PEG_T(z, 3));
+        store_chunk(hi_base, 32 * cv_u + 4 * cv_cq + 3, cv_rq, PEG_T(w, 0), PEG_T(w, 1), PEG_T(w, 2), PEG_T(w, 3));
+#undef PEG_T
       }
       fence_proxy_async();
       mbar_arrive(full_a(st));
@@ -390,7 +364,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     const float* sv = a.svec + (size_t)b * a.sv_stride;
     const float* cb0 = a.colbuf + ((size_t)b * 2 + 0) * d;
     const float* cb1 = a.colbuf + ((size_t)b * 2 + 1) * d;
-    const float kappa = sc.kappa[a.layer];
+    const float kappa = scp->kappa[a.layer];
     const bool rowok = gi < n;
     const float vi = rowok ? 1.f + sv[a.v_off + gi] : 0.f;
     const float rc = rowok ? sv[a.rowc_off + gi] : 0.f;
@@ -490,7 +464,7 @@ static int pick_nd(int d, int maxnd) {
   return 0;
 }
 
-static inline int npad_of(int n) { return (n + 31) / 32 * 32; }
+static inline int npad_of(int n) { return peg_npad(n); }
 
 void tc_carve(Bump& bp, const PegDims& d, int dmax, TcWs& w) {
   w.npad = npad_of(d.n);

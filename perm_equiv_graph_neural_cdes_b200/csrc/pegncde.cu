@@ -72,7 +72,7 @@ static int check_dims(const PegDims* d) {
   if (d->B < 1 || d->n < 1 || d->L < 1 || d->L > PEG_MAX_LAYERS || d->T < 2 || d->T > PEG_MAX_T || d->e < 0)
     return PEG_ERR_BAD_DIMS;
   if (d->h < 4 || d->h > PEG_MAX_H || (d->h % 4) != 0) return PEG_ERR_BAD_DIMS;
-  if (d->ldn < d->n || (d->ldn % 4) != 0) return PEG_ERR_BAD_DIMS;
+  if (d->ldn != peg_npad(d->n)) return PEG_ERR_BAD_DIMS;  // planes are tiled 32x32: ldn = n rounded up to 32
   if ((long long)d->B > 65535) return PEG_ERR_BAD_DIMS;
   return PEG_OK;
 }
@@ -191,7 +191,7 @@ static int contract(Ctx& c, int l, bool bwd, const float* V, const float* Mref, 
   const LayerDesc& ld = c.m.layer[l];
   ContractArgs a;
   a.planes = c.ctl.adj_coef;
-  a.graph_stride = (size_t)(c.d.T - 1) * 4 * c.d.n * c.d.ldn;
+  a.graph_stride = (size_t)(c.d.T - 1) * 4 * c.d.ldn * c.d.ldn;
   a.sc = c.w.sc;
   a.svec = c.w.svec;
   a.sv_stride = c.sv_stride;
@@ -443,7 +443,9 @@ static int pack_common(peg_stream_t stream, const PegDims* dims, const float* d,
   const int Tm1 = dims->T - 1;
   const size_t slabs = (size_t)dims->B * Tm1;
   PEG_CUDA(cudaMemsetAsync(adj_total, 0, slabs * 4 * sizeof(float), st));
-  dim3 grid((dims->n + 63) / 64, Tm1, dims->B);
+  PEG_CUDA(cudaMemsetAsync(adj_rowsum, 0, slabs * 4 * dims->n * sizeof(float), st));
+  const int nt = dims->ldn / 32;
+  dim3 grid(nt * nt, Tm1, dims->B);
   k_pack_adj<<<grid, 256, 0, st>>>(d, c, b, a, planar, dims->n, dims->ldn, Tm1, adj_coef, adj_rowsum, adj_diag,
                                    adj_total);
   PEG_LAUNCH_CHECK();

@@ -33,7 +33,7 @@ def test_strerror_and_version():
 
 @pytest.mark.parametrize("n,h,e,L", [(129, 64, 8, 3), (1000, 64, 16, 3), (100, 32, 3, 3), (400, 16, 0, 2)])
 def test_param_count_matches_reference_pytree(n, h, e, L):
-    d = _lib.PegDims(1, n, (n + 3) // 4 * 4, h, e, L, 4, 0)
+    d = _lib.PegDims(1, n, (n + 31) // 32 * 32, h, e, L, 4, 0)
     widths = R.layer_widths(h, L, e, e > 0)
     expect = sum(widths[i + 1] * widths[i] + widths[i + 1] + 2 * widths[i] + 16 for i in range(L))
     assert _lib.lib().pegncde_param_count(d) == expect
@@ -46,8 +46,8 @@ def test_param_count_matches_reference_pytree(n, h, e, L):
 
 def test_bad_dims_are_rejected_without_touching_the_gpu():
     l = _lib.lib()
-    good = dict(B=1, n=10, ldn=12, h=8, e=0, L=2, T=4, flags=0)
-    for k, v in [("ldn", 10), ("ldn", 8), ("h", 6), ("h", 512), ("L", 0), ("L", 9), ("T", 1), ("B", 0), ("n", 0)]:
+    good = dict(B=1, n=10, ldn=32, h=8, e=0, L=2, T=4, flags=0)
+    for k, v in [("ldn", 10), ("ldn", 12), ("ldn", 64), ("h", 6), ("h", 512), ("L", 0), ("L", 9), ("T", 1), ("B", 0), ("n", 0)]:
         d = _lib.PegDims(**{**good, k: v})
         assert l.pegncde_param_count(d) == 0, (k, v)
         assert l.pegncde_workspace_bytes(d, 0, 1) == 0
@@ -61,8 +61,8 @@ def test_bad_dims_are_rejected_without_touching_the_gpu():
 
 def test_workspace_grows_with_problem():
     l = _lib.lib()
-    a = l.pegncde_workspace_bytes(_lib.PegDims(1, 100, 100, 32, 3, 3, 12, 0), _lib.PEG_WS_SOLVE_BWD, 10)
-    b = l.pegncde_workspace_bytes(_lib.PegDims(4, 100, 100, 32, 3, 3, 12, 0), _lib.PEG_WS_SOLVE_BWD, 10)
+    a = l.pegncde_workspace_bytes(_lib.PegDims(1, 100, 128, 32, 3, 3, 12, 0), _lib.PEG_WS_SOLVE_BWD, 10)
+    b = l.pegncde_workspace_bytes(_lib.PegDims(4, 100, 128, 32, 3, 3, 12, 0), _lib.PEG_WS_SOLVE_BWD, 10)
     assert 0 < a < b
 
 
@@ -105,3 +105,17 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("load_oracle_layers", ""), os.path.join(dirpath, f)
+
+
+def test_tiled_layout_is_a_permutation_with_contiguous_warp_loads():
+    """The 32x32-tiled plane layout: a bijection onto [0, 4*npad^2), 16-KB tiles, and every (g, plane, m) warp
+    row of 32 lanes x 4 floats is 512 contiguous bytes."""
+    from perm_equiv_graph_neural_cdes_b200.control import tiled_offsets
+
+    npad = 96
+    off = tiled_offsets(npad)
+    assert sorted(off.reshape(-1).tolist()) == list(range(4 * npad * npad))
+    tile = off[:, 32:64, 64:96]  # tile (1, 2)
+    assert int(tile.min()) == (1 * 3 + 2) * 4096 and int(tile.max()) == (1 * 3 + 2) * 4096 + 4095
+    # elements of one micro-tile row are 4 consecutive floats
+    assert torch.equal(off[2, 5, 8:12] - off[2, 5, 8], torch.arange(4))
