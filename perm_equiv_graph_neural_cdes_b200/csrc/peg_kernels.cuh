@@ -296,15 +296,19 @@ __global__ void __launch_bounds__(256) k_norm_linear(const float* __restrict__ Z
 
 // =====================================================================================
 // column reductions: cb[b][0][c] = sum_i V[b,i,c] ; cb[b][1][c] = sum_i vec[b][i] V[b,i,c]
-// grid (ceil(d/32), ceil(n/CS_ROWS), B), block (32, 8); cb must be zeroed first (partial sums are atomically added)
+// grid (ceil(d/32), ceil(n/CS_ROWS), B), block (32, 8).  Deterministic: every block writes its partial sums,
+// the last block to finish (per column block) adds them in a fixed order; the ticket counter resets itself.
 // =====================================================================================
 constexpr int CS_ROWS = 256;
 __global__ void __launch_bounds__(256) k_colsums(const float* __restrict__ V, int n, int d,
                                                  const float* __restrict__ vec, size_t vec_stride,
-                                                 float* __restrict__ cb) {
+                                                 float* __restrict__ cb, float* __restrict__ partial,
+                                                 unsigned int* __restrict__ tickets) {
   __shared__ float s0[8][33], s1[8][33];
+  __shared__ bool is_last;
   const int b = blockIdx.z, c = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * CS_ROWS, r1 = min(n, r0 + CS_ROWS);
+  const int chunks = gridDim.y;
   const float* Vb = V + (size_t)b * n * d;
   const float* vb = vec ? vec + (size_t)b * vec_stride : nullptr;
   float a0 = 0.f, a1 = 0.f;
@@ -318,11 +322,32 @@ __global__ void __launch_bounds__(256) k_colsums(const float* __restrict__ V, in
   s0[threadIdx.y][threadIdx.x] = a0;
   s1[threadIdx.y][threadIdx.x] = a1;
   __syncthreads();
+  float* part = partial + (((size_t)b * chunks + blockIdx.y) * 2) * d;
   if (threadIdx.y == 0 && c < d) {
 #pragma unroll
     for (int k = 1; k < 8; ++k) { a0 += s0[k][threadIdx.x]; a1 += s1[k][threadIdx.x]; }
-    atomicAdd(&cb[((size_t)b * 2 + 0) * d + c], a0);
-    if (vb) atomicAdd(&cb[((size_t)b * 2 + 1) * d + c], a1);
+    part[c] = a0;
+    part[d + c] = a1;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    unsigned int* tk = tickets + (size_t)b * gridDim.x + blockIdx.x;
+    const unsigned int t = atomicAdd(tk, 1u);
+    is_last = (t == (unsigned int)chunks - 1u);
+    if (is_last) *tk = 0u;
+  }
+  __syncthreads();
+  if (is_last && threadIdx.y == 0 && c < d) {
+    __threadfence();
+    float t0 = 0.f, t1 = 0.f;
+    for (int k = 0; k < chunks; ++k) {
+      const float* pk = partial + (((size_t)b * chunks + k) * 2) * d;
+      t0 += __ldcg(pk + c);
+      t1 += __ldcg(pk + d + c);
+    }
+    cb[((size_t)b * 2 + 0) * d + c] = t0;
+    cb[((size_t)b * 2 + 1) * d + c] = t1;
   }
 }
 

@@ -107,6 +107,9 @@ struct FevalWs {
   float* svec;
   float* colM;   // [B][2][dmax]
   float* colG;   // [B][2][dmax]
+  float* colPart;          // [B][row chunks][2][dmax] partial column sums
+  unsigned int* tickets;   // [B][ceil(dmax/32)] self-resetting arrival counters (zeroed at every API entry)
+  size_t tickets_count;
   float* M;      // [B,n,dmax]
   float* Za;     // [B,n,h] ping
   float* Zb;     // [B,n,h] pong
@@ -124,6 +127,9 @@ static void carve_feval(Bump& bp, const PegDims& d, const Model& m, bool vjp, Fe
   w.svec = bp.take<float>(B * svec_stride(d.n, d.L, d.e));
   w.colM = bp.take<float>(B * 2 * dm);
   w.colG = bp.take<float>(B * 2 * dm);
+  w.colPart = bp.take<float>(B * ((n + CS_ROWS - 1) / CS_ROWS) * 2 * dm);
+  w.tickets_count = B * ((dm + 31) / 32);
+  w.tickets = bp.take<unsigned int>(w.tickets_count);
   w.M = bp.take<float>(B * n * dm);
   w.Za = bp.take<float>(B * n * h);
   w.Zb = bp.take<float>(B * n * h);
@@ -180,8 +186,8 @@ static int norm_linear(Ctx& c, int l, const float* Zin, float* M, float* Nout) {
 
 static int colsums(Ctx& c, const float* V, int dcols, size_t vec_off, bool with_vec, float* cb) {
   dim3 grid((dcols + 31) / 32, (c.d.n + CS_ROWS - 1) / CS_ROWS, c.d.B), block(32, 8);
-  PEG_CUDA(cudaMemsetAsync(cb, 0, (size_t)c.d.B * 2 * dcols * sizeof(float), c.st));
-  k_colsums<<<grid, block, 0, c.st>>>(V, c.d.n, dcols, with_vec ? c.w.svec + vec_off : nullptr, c.sv_stride, cb);
+  k_colsums<<<grid, block, 0, c.st>>>(V, c.d.n, dcols, with_vec ? c.w.svec + vec_off : nullptr, c.sv_stride, cb,
+                                      c.w.colPart, c.w.tickets);
   PEG_LAUNCH_CHECK();
   return PEG_OK;
 }
@@ -359,6 +365,11 @@ static int make_ctx(Ctx& c, peg_stream_t stream, const PegDims* dims, const PegC
   return PEG_OK;
 }
 
+static int reset_tickets(Ctx& c) {
+  PEG_CUDA(cudaMemsetAsync(c.w.tickets, 0, c.w.tickets_count * sizeof(unsigned int), c.st));
+  return PEG_OK;
+}
+
 struct SolveWs {
   float* k[7];
   float* Z0;         // stage input
@@ -495,6 +506,7 @@ int pegncde_vf_fwd(peg_stream_t stream, const PegDims* dims, const PegControl* c
   if (!y || !dy || !workspace) return PEG_ERR_NULL_POINTER;
   if (workspace_bytes < plan(*dims, PEG_WS_VF_FWD, 0, nullptr, nullptr, nullptr)) return PEG_ERR_WORKSPACE;
   plan(*dims, PEG_WS_VF_FWD, 0, workspace, &c.w, nullptr);
+  PEG_TRY(reset_tickets(c));
   return feval_fwd(c, t, y, dy, nullptr);
 }
 
@@ -507,6 +519,7 @@ int pegncde_vf_vjp(peg_stream_t stream, const PegDims* dims, const PegControl* c
   if (workspace_bytes < plan(*dims, PEG_WS_VF_VJP, 0, nullptr, nullptr, nullptr)) return PEG_ERR_WORKSPACE;
   SolveWs s;
   plan(*dims, PEG_WS_VF_VJP, 0, workspace, &c.w, &s);
+  PEG_TRY(reset_tickets(c));
   float* save[PEG_MAX_LAYERS];
   save[0] = const_cast<float*>(y);
   for (int l = 1; l < dims->L; ++l) save[l] = s.save[0][l];
@@ -524,6 +537,7 @@ int pegncde_step_fwd(peg_stream_t stream, const PegDims* dims, const PegControl*
   if (workspace_bytes < plan(*dims, PEG_WS_STEP, 0, nullptr, nullptr, nullptr)) return PEG_ERR_WORKSPACE;
   SolveWs s;
   plan(*dims, PEG_WS_STEP, 0, workspace, &c.w, &s);
+  PEG_TRY(reset_tickets(c));
   const Tsit5& tb = tsit5();
   float* k[7] = {k1, s.k[1], s.k[2], s.k[3], s.k[4], s.k[5], k7};
   if (!k1_valid) PEG_TRY(feval_fwd(c, t, y, k[0], nullptr));
@@ -556,6 +570,7 @@ int pegncde_solve_fwd(peg_stream_t stream, const PegDims* dims, const PegControl
   if (workspace_bytes < plan(*dims, PEG_WS_SOLVE_FWD, steps, nullptr, nullptr, nullptr)) return PEG_ERR_WORKSPACE;
   SolveWs s;
   plan(*dims, PEG_WS_SOLVE_FWD, steps, workspace, &c.w, &s);
+  PEG_TRY(reset_tickets(c));
   const Tsit5& tb = tsit5();
   const size_t st = (size_t)dims->B * dims->n * dims->h;
   PEG_CUDA(cudaMemcpyAsync(y_ckpt, y0, st * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
@@ -594,6 +609,7 @@ int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl
   if (workspace_bytes < plan(*dims, PEG_WS_SOLVE_BWD, steps, nullptr, nullptr, nullptr)) return PEG_ERR_WORKSPACE;
   SolveWs s;
   plan(*dims, PEG_WS_SOLVE_BWD, steps, workspace, &c.w, &s);
+  PEG_TRY(reset_tickets(c));
   const Tsit5& tb = tsit5();
   const size_t st = (size_t)dims->B * dims->n * dims->h;
   const int L = dims->L;
