@@ -56,8 +56,7 @@ enum {
 enum {
   PEG_FLAG_RELU = 0,            /* reserved */
   PEG_FLAG_TENSOR_CORES = 1,    /* n x n x d contractions on tcgen05 (3xTF32 split: fp32-parity) */
-  PEG_FLAG_TF32_FAST = 2,       /* with TENSOR_CORES: single-pass TF32 (rna-rounded), looser tolerance */
-  PEG_FLAG_STORE_STAGES = 4     /* solve_fwd keeps every stage's layer inputs so solve_bwd skips recompute */
+  PEG_FLAG_TF32_FAST = 2        /* with TENSOR_CORES: single-pass TF32 (rna-rounded), looser tolerance */
 };
 
 typedef struct PegDims {
@@ -141,12 +140,17 @@ int pegncde_step_fwd(peg_stream_t stream, const PegDims* dims, const PegControl*
  * pegncde_solve_bwd restarts from.  yT (nullable) [B,n,h] = y_ckpt[steps]. */
 int pegncde_solve_fwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params,
                       const float* step_ts, int32_t steps, const float* y0, float* yT, float* y_ckpt,
-                      void* workspace, size_t workspace_bytes);
+                      float* stage_store, void* workspace, size_t workspace_bytes);
+/* stage_store (nullable, pegncde_stage_store_bytes() bytes): when given, solve_fwd keeps the input of every layer
+ * of every stage there and solve_bwd, handed the same buffer, skips its forward recompute (36 instead of 54 passes
+ * over the coefficient planes per step).  NULL = checkpoint-per-step mode: solve_bwd recomputes each step. */
+size_t pegncde_stage_store_bytes(const PegDims* dims, int32_t steps);
 /* g_ckpt (nullable) [steps+1, B, n, h]: cotangents injected at step boundaries (SaveAt(ts=...) losses);
  * g_yT [B,n,h] cotangent of y(T).  Writes g_y0; accumulates g_params (caller zeroes it). */
 int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params,
-                      const float* step_ts, int32_t steps, const float* y_ckpt, const float* g_yT,
-                      const float* g_ckpt, float* g_y0, float* g_params, void* workspace, size_t workspace_bytes);
+                      const float* step_ts, int32_t steps, const float* y_ckpt, const float* stage_store,
+                      const float* g_yT, const float* g_ckpt, float* g_y0, float* g_params, void* workspace,
+                      size_t workspace_bytes);
 
 /* ---- introspection ------------------------------------------------------------------------ */
 const char* pegncde_strerror(int code);

@@ -14,7 +14,6 @@ LIB_PATH = os.path.join(_HERE, "libpegncde.so")
 
 PEG_FLAG_TENSOR_CORES = 1
 PEG_FLAG_TF32_FAST = 2
-PEG_FLAG_STORE_STAGES = 4
 
 PEG_WS_VF_FWD, PEG_WS_VF_VJP, PEG_WS_SOLVE_FWD, PEG_WS_SOLVE_BWD, PEG_WS_STEP = range(5)
 
@@ -53,8 +52,9 @@ SIGNATURES = {
     "pegncde_vf_fwd": (c_int, [_P, _DIMS, _CTL, _P, c_float, _P, _P, _P, c_size_t]),
     "pegncde_vf_vjp": (c_int, [_P, _DIMS, _CTL, _P, c_float, _P, _P, _P, _P, _P, _P, c_size_t]),
     "pegncde_step_fwd": (c_int, [_P, _DIMS, _CTL, _P, c_float, c_float, _P, _P, c_int32, _P, _P, _P, _P, c_size_t]),
-    "pegncde_solve_fwd": (c_int, [_P, _DIMS, _CTL, _P, POINTER(c_float), c_int32, _P, _P, _P, _P, c_size_t]),
-    "pegncde_solve_bwd": (c_int, [_P, _DIMS, _CTL, _P, POINTER(c_float), c_int32, _P, _P, _P, _P, _P, _P, c_size_t]),
+    "pegncde_solve_fwd": (c_int, [_P, _DIMS, _CTL, _P, POINTER(c_float), c_int32, _P, _P, _P, _P, _P, c_size_t]),
+    "pegncde_stage_store_bytes": (c_size_t, [_DIMS, c_int32]),
+    "pegncde_solve_bwd": (c_int, [_P, _DIMS, _CTL, _P, POINTER(c_float), c_int32, _P, _P, _P, _P, _P, _P, _P, c_size_t]),
     "pegncde_strerror": (c_char_p, [c_int]),
     "pegncde_last_cuda_error": (c_int, []),
     "pegncde_version": (c_char_p, []),

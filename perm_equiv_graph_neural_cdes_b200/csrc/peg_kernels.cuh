@@ -129,10 +129,11 @@ struct PrepArgs {
   float* svec;
 };
 
+// grid (ceil(max(n, n*2e/.. )/256), B): every block redoes the (tiny) interval search, then handles 256 nodes
 __global__ void __launch_bounds__(256) k_stage_prep(PrepArgs a) {
   __shared__ float sh[40];
   __shared__ StageScalars S;
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.y, tid = threadIdx.x;
   const int n = a.n, L = a.model.L, Tm1 = a.T - 1;
   const float* ts = a.ctl.ts + (size_t)b * a.T;
   // index = clip(searchsorted(ts, t, 'left') - 1, 0, T-2)  (diffrax CubicInterpolation._interpret_t)
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(256) k_stage_prep(PrepArgs a) {
   const float totA = wA[0] * tot[0] + wA[1] * tot[1] + wA[2] * tot[2] + wA[3] * tot[3];
   const float totD = wD[1] * tot[1] + wD[2] * tot[2] + wD[3] * tot[3];
   const float inv_n = 1.f / (float)n, inv_n2 = inv_n * inv_n;
-  if (tid == 0) {
+  if (tid == 0 && blockIdx.x == 0) {
     S.interval = iv;
     S.s = s;
     for (int p = 0; p < 4; ++p) { S.wA[p] = wA[p]; S.wD[p] = wD[p]; }
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(256) k_stage_prep(PrepArgs a) {
   const float* rs = a.ctl.adj_rowsum + slab * 4 * n;
   const float* dg = a.ctl.adj_diag + slab * 4 * n;
   const float* tc = a.ctl.tch_coef + slab * 3 * n;
-  for (int i = tid; i < n; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + tid; i < n; i += gridDim.x * blockDim.x) {
     const float rA = wA[0] * rs[i] + wA[1] * rs[n + i] + wA[2] * rs[2 * n + i] + wA[3] * rs[3 * n + i];
     const float rD = wD[1] * rs[n + i] + wD[2] * rs[2 * n + i] + wD[3] * rs[3 * n + i];
     const float dA = wA[0] * dg[i] + wA[1] * dg[n + i] + wA[2] * dg[2 * n + i] + wA[3] * dg[3 * n + i];
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(256) k_stage_prep(PrepArgs a) {
     const int e2 = 2 * a.e;
     const size_t per = (size_t)n * e2;
     const float* xc = a.ctl.x_coef + slab * 3 * per;
-    for (size_t i = tid; i < per; i += blockDim.x)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < per; i += (size_t)gridDim.x * blockDim.x)
       sv[svec_xd(n, L) + i] = xc[i] + s * (2.f * xc[per + i] + 3.f * s * xc[2 * per + i]);
   }
 }
@@ -222,74 +223,81 @@ __global__ void __launch_bounds__(256) k_rk_combine(CombArgs a) {
 
 // =====================================================================================
 // RMSNorm -> Linear  (layers.py:45-46): M = (w_n * z * rsqrt(mean z^2 + eps) + b_n) W^T + b
-// grid (ceil(n/32), ceil(dout/64), B), block 256, dyn smem 32*(din+1) + 64*33 floats
+// grid (ceil(n/64), ceil(dout/64), B), block 256; 64 nodes x 64 outputs per block, 4 x 4 per thread
 // =====================================================================================
 __global__ void __launch_bounds__(256) k_norm_linear(const float* __restrict__ Z, int n, int din, int dout,
                                                      const float* __restrict__ W, const float* __restrict__ bias,
                                                      const float* __restrict__ nw, const float* __restrict__ nb,
                                                      float* __restrict__ M, float* __restrict__ Nout) {
-  extern __shared__ float smem[];
-  const int zs_ld = din + 1;
-  float* zs = smem;                 // [32][din+1]
-  float* ws = smem + 32 * zs_ld;    // [64][33]
+  __shared__ __align__(16) float zt[32][68];   // [k][node]  normalised input chunk
+  __shared__ __align__(16) float wt[32][68];   // [k][out]
+  __shared__ float rinv_s[64];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.z, node0 = blockIdx.x * 32, o0 = blockIdx.y * 64;
+  const int b = blockIdx.z, node0 = blockIdx.x * 64, o0 = blockIdx.y * 64;
   const float* Zb = Z + (size_t)b * n * din;
-  for (int idx = tid; idx < 32 * din; idx += 256) {
-    const int r = idx / din, c = idx - r * din;
-    zs[r * zs_ld + c] = (node0 + r < n) ? Zb[(size_t)(node0 + r) * din + c] : 0.f;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
-    const int r = warp * 4 + rr;
+  // per-node rsqrt(mean z^2 + eps): warp w handles nodes 8w .. 8w+7
+  for (int rr = 0; rr < 8; ++rr) {
+    const int r = warp * 8 + rr, node = node0 + r;
     float ss = 0.f;
-    for (int c = lane; c < din; c += 32) { const float z = zs[r * zs_ld + c]; ss = fmaf(z, z, ss); }
+    if (node < n)
+      for (int c = lane; c < din; c += 32) { const float z = Zb[(size_t)node * din + c]; ss = fmaf(z, z, ss); }
     ss = warp_sum(ss);
-    const float rinv = rsqrtf(ss / (float)din + 1e-5f);
-    for (int c = lane; c < din; c += 32) zs[r * zs_ld + c] = zs[r * zs_ld + c] * rinv * nw[c] + nb[c];
+    if (lane == 0) rinv_s[r] = rsqrtf(ss / (float)din + 1e-5f);
   }
   __syncthreads();
-  if (Nout != nullptr && blockIdx.y == 0) {
-    float* Nb = Nout + (size_t)b * n * din;
-    for (int idx = tid; idx < 32 * din; idx += 256) {
-      const int r = idx / din, c = idx - r * din;
-      if (node0 + r < n) Nb[(size_t)(node0 + r) * din + c] = zs[r * zs_ld + c];
-    }
-  }
   const int ty = tid >> 4, tx = tid & 15;
-  float acc[2][4];
+  float acc[4][4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float* Nb = Nout ? Nout + (size_t)b * n * din : nullptr;
   for (int k0 = 0; k0 < din; k0 += 32) {
-    for (int idx = tid; idx < 64 * 32; idx += 256) {
-      const int o = idx >> 5, k = idx & 31;
-      ws[o * 33 + k] = (o0 + o < dout && k0 + k < din) ? W[(size_t)(o0 + o) * din + k0 + k] : 0.f;
+    // 64 rows x 32 k: thread -> row tid/4, 8 consecutive k
+    {
+      const int r = tid >> 2, kq = (tid & 3) * 8;
+      const int node = node0 + r, o = o0 + r;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + kq + u;
+        float z = 0.f, w = 0.f;
+        if (k < din) {
+          if (node < n) {
+            z = Zb[(size_t)node * din + k] * rinv_s[r] * nw[k] + nb[k];
+            if (Nb != nullptr && blockIdx.y == 0) Nb[(size_t)node * din + k] = z;
+          }
+          if (o < dout) w = W[(size_t)o * din + k];
+        }
+        zt[kq + u][r] = z;
+        wt[kq + u][r] = w;
+      }
     }
     __syncthreads();
-    const int kmax = min(32, din - k0);
-    for (int k = 0; k < kmax; ++k) {
-      const float z0 = zs[(ty * 2) * zs_ld + k0 + k], z1 = zs[(ty * 2 + 1) * zs_ld + k0 + k];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float w = ws[(tx * 4 + j) * 33 + k];
-        acc[0][j] = fmaf(z0, w, acc[0][j]);
-        acc[1][j] = fmaf(z1, w, acc[1][j]);
-      }
+    for (int k = 0; k < 32; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&zt[k][4 * ty]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&wt[k][4 * tx]);
+      const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
     }
     __syncthreads();
   }
   float* Mb = M + (size_t)b * n * dout;
+  const int oc = o0 + 4 * tx;
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int node = node0 + ty * 2 + i;
+  for (int i = 0; i < 4; ++i) {
+    const int node = node0 + 4 * ty + i;
     if (node >= n) continue;
+    if (oc + 3 < dout) {
+      *reinterpret_cast<float4*>(Mb + (size_t)node * dout + oc) =
+          make_float4(acc[i][0] + bias[oc], acc[i][1] + bias[oc + 1], acc[i][2] + bias[oc + 2], acc[i][3] + bias[oc + 3]);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int o = o0 + tx * 4 + j;
-      if (o < dout) Mb[(size_t)node * dout + o] = acc[i][j] + bias[o];
+      for (int j = 0; j < 4; ++j)
+        if (oc + j < dout) Mb[(size_t)node * dout + oc + j] = acc[i][j] + bias[oc + j];
     }
   }
 }
@@ -670,76 +678,116 @@ __global__ void __launch_bounds__(256) k_fusion_vec_grads(FusGradArgs a) {
 // =====================================================================================
 // backward of Linear + RMSNorm wrt the layer input (and the norm affine parameters):
 //   Nbar = Mbar W ;  Zbar = rinv w Nbar - z rinv^3 <w Nbar, z>/din ;  optional ReLU mask (z > 0)
-// grid (ceil(n/32), B), block 256 (8 threads per node), dyn smem 32*33 + 32*din + 2*din floats
+// grid (ceil(n/32), B), block 256: warp ty owns nodes 4ty..4ty+3, lane tx owns columns 4tx..4tx+3 (+128 if din > 128)
 // =====================================================================================
 __global__ void __launch_bounds__(256) k_linear_bwd(const float* __restrict__ Mbar, const float* __restrict__ W,
                                                     const float* __restrict__ Z, const float* __restrict__ nw,
                                                     int n, int din, int dout, int relu_mask,
                                                     float* __restrict__ Zbar, float* __restrict__ g_nw,
                                                     float* __restrict__ g_nb) {
-  extern __shared__ float smem[];
-  float* mb = smem;               // [32][33]
-  float* wsm = smem + 32 * 33;    // [32][din]
-  float* gsw = wsm + 32 * din;    // [din]
-  float* gsb = gsw + din;         // [din]
+  __shared__ __align__(16) float mt[32][36];        // [k (dout chunk)][node]
+  __shared__ __align__(16) float wsm[32][PEG_MAX_H]; // [k][c]
+  __shared__ float gsw[PEG_MAX_H], gsb[PEG_MAX_H];
   const int tid = threadIdx.x, b = blockIdx.y, node0 = blockIdx.x * 32;
-  const int r = tid >> 3, sub = tid & 7;
-  const int node = node0 + r;
-  constexpr int MAXJ = PEG_MAX_H / 8;
-  float acc[MAXJ];
+  const int ty = tid >> 5, tx = tid & 31;
+  constexpr int REPS = PEG_MAX_H / 128;
+  float acc[REPS][4][4];
 #pragma unroll
-  for (int j = 0; j < MAXJ; ++j) acc[j] = 0.f;
+  for (int r = 0; r < REPS; ++r)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[r][i][j] = 0.f;
   for (int c = tid; c < din; c += 256) { gsw[c] = 0.f; gsb[c] = 0.f; }
   const float* Mb = Mbar + (size_t)b * n * dout;
   for (int o0 = 0; o0 < dout; o0 += 32) {
-    for (int idx = tid; idx < 32 * 32; idx += 256) {
-      const int rr = idx >> 5, o = idx & 31;
-      mb[rr * 33 + o] = (node0 + rr < n && o0 + o < dout) ? Mb[(size_t)(node0 + rr) * dout + o0 + o] : 0.f;
+    {  // Mbar chunk: 32 nodes x 32 k, thread -> node tid/8, 4 consecutive k
+      const int r = tid >> 3, kq = (tid & 7) * 4;
+      const int node = node0 + r;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int o = o0 + kq + u;
+        mt[kq + u][r] = (node < n && o < dout) ? Mb[(size_t)node * dout + o] : 0.f;
+      }
     }
-    for (int idx = tid; idx < 32 * din; idx += 256) {
-      const int o = idx / din, c = idx - o * din;
-      wsm[idx] = (o0 + o < dout) ? W[(size_t)(o0 + o) * din + c] : 0.f;
+    for (int idx = tid; idx < 32 * (din >> 2); idx += 256) {   // W chunk: 32 rows x din, float4
+      const int k = idx / (din >> 2), c4 = idx - k * (din >> 2);
+      const int o = o0 + k;
+      const float4 w4 = (o < dout) ? *reinterpret_cast<const float4*>(W + (size_t)o * din + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(&wsm[k][4 * c4]) = w4;
     }
     __syncthreads();
-    for (int o = 0; o < 32; ++o) {
-      const float m = mb[r * 33 + o];
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&mt[k][4 * ty]);
+      const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-      for (int j = 0; j < MAXJ; ++j) {
-        const int c = sub + 8 * j;
-        if (c < din) acc[j] = fmaf(m, wsm[o * din + c], acc[j]);
+      for (int r = 0; r < REPS; ++r) {
+        const int c = 4 * tx + 128 * r;
+        if (c < din) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&wsm[k][c]);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[r][i][j] = fmaf(aa[i], bb[j], acc[r][i][j]);
+        }
       }
     }
     __syncthreads();
   }
-  // norm backward (8 lanes cooperate per node)
-  float z[MAXJ];
-  float ss = 0.f, dot = 0.f;
-  const float* Zr = Z + ((size_t)b * n + (node < n ? node : 0)) * din;
+  // norm backward: one warp holds complete rows of its 4 nodes
+  float gw[REPS][4], gb[REPS][4];
 #pragma unroll
-  for (int j = 0; j < MAXJ; ++j) {
-    const int c = sub + 8 * j;
-    z[j] = (c < din && node < n) ? Zr[c] : 0.f;
-    ss = fmaf(z[j], z[j], ss);
-    if (c < din) dot = fmaf(nw[c] * acc[j], z[j], dot);
-  }
+  for (int r = 0; r < REPS; ++r)
 #pragma unroll
-  for (int o = 1; o < 8; o <<= 1) {
-    ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    dot += __shfl_xor_sync(0xffffffffu, dot, o);
-  }
-  const float rinv = rsqrtf(ss / (float)din + 1e-5f);
-  const float coef = rinv * rinv * rinv * dot / (float)din;
-  if (node < n) {
+    for (int j = 0; j < 4; ++j) { gw[r][j] = 0.f; gb[r][j] = 0.f; }
 #pragma unroll
-    for (int j = 0; j < MAXJ; ++j) {
-      const int c = sub + 8 * j;
-      if (c < din) {
-        float zb = rinv * nw[c] * acc[j] - z[j] * coef;
-        if (relu_mask && !(z[j] > 0.f)) zb = 0.f;
-        Zbar[((size_t)b * n + node) * din + c] = zb;
-        atomicAdd(&gsw[c], acc[j] * z[j] * rinv);
-        atomicAdd(&gsb[c], acc[j]);
+  for (int i = 0; i < 4; ++i) {
+    const int node = node0 + 4 * ty + i;
+    const bool ok = node < n;
+    float z[REPS][4];
+    float ss = 0.f, dot = 0.f;
+#pragma unroll
+    for (int r = 0; r < REPS; ++r) {
+      const int c = 4 * tx + 128 * r;
+      float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok && c < din) z4 = *reinterpret_cast<const float4*>(Z + ((size_t)b * n + node) * din + c);
+      z[r][0] = z4.x; z[r][1] = z4.y; z[r][2] = z4.z; z[r][3] = z4.w;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ss = fmaf(z[r][j], z[r][j], ss);
+        if (c < din) dot = fmaf(nw[c + j] * acc[r][i][j], z[r][j], dot);
       }
+    }
+    ss = warp_sum(ss);
+    dot = warp_sum(dot);
+    const float rinv = rsqrtf(ss / (float)din + 1e-5f);
+    const float coef = rinv * rinv * rinv * dot / (float)din;
+    if (ok) {
+#pragma unroll
+      for (int r = 0; r < REPS; ++r) {
+        const int c = 4 * tx + 128 * r;
+        if (c < din) {
+          float zb[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            zb[j] = rinv * nw[c + j] * acc[r][i][j] - z[r][j] * coef;
+            if (relu_mask && !(z[r][j] > 0.f)) zb[j] = 0.f;
+            gw[r][j] = fmaf(acc[r][i][j] * z[r][j], rinv, gw[r][j]);
+            gb[r][j] += acc[r][i][j];
+          }
+          *reinterpret_cast<float4*>(Zbar + ((size_t)b * n + node) * din + c) = make_float4(zb[0], zb[1], zb[2], zb[3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < REPS; ++r) {
+    const int c = 4 * tx + 128 * r;
+    if (c < din) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { atomicAdd(&gsw[c + j], gw[r][j]); atomicAdd(&gsb[c + j], gb[r][j]); }
     }
   }
   __syncthreads();

@@ -169,16 +169,16 @@ static int stage_prep(Ctx& c, float t) {
   a.t = t;
   a.sc = c.w.sc;
   a.svec = c.w.svec;
-  k_stage_prep<<<c.d.B, 256, 0, c.st>>>(a);
+  dim3 grid((c.d.n + 255) / 256, c.d.B);
+  k_stage_prep<<<grid, 256, 0, c.st>>>(a);
   PEG_LAUNCH_CHECK();
   return PEG_OK;
 }
 
 static int norm_linear(Ctx& c, int l, const float* Zin, float* M, float* Nout) {
   const LayerDesc& ld = c.m.layer[l];
-  dim3 grid((c.d.n + 31) / 32, (ld.dout + 63) / 64, c.d.B);
-  const size_t smem = (size_t)(32 * (ld.din + 1) + 64 * 33) * sizeof(float);
-  k_norm_linear<<<grid, 256, smem, c.st>>>(Zin, c.d.n, ld.din, ld.dout, c.params + ld.w_off, c.params + ld.b_off,
+  dim3 grid((c.d.n + 63) / 64, (ld.dout + 63) / 64, c.d.B);
+  k_norm_linear<<<grid, 256, 0, c.st>>>(Zin, c.d.n, ld.din, ld.dout, c.params + ld.w_off, c.params + ld.b_off,
                                            c.params + ld.nw_off, c.params + ld.nb_off, M, Nout);
   PEG_LAUNCH_CHECK();
   return PEG_OK;
@@ -319,9 +319,8 @@ static int feval_vjp(Ctx& c, float t, float* const* zin, const float* kbar, floa
     }
     {
       dim3 grid((d.n + 31) / 32, d.B);
-      const size_t smem = (size_t)(32 * 33 + 32 * ld.din + 2 * ld.din) * sizeof(float);
       float* zb = (l == 0) ? ybar : c.w.Obar;
-      k_linear_bwd<<<grid, 256, smem, c.st>>>(c.w.Mbar, c.params + ld.w_off, zin[l], c.params + ld.nw_off, d.n,
+      k_linear_bwd<<<grid, 256, 0, c.st>>>(c.w.Mbar, c.params + ld.w_off, zin[l], c.params + ld.nw_off, d.n,
                                               ld.din, ld.dout, l > 0 ? 1 : 0, zb, g_params + ld.nw_off,
                                               g_params + ld.nb_off);
       PEG_LAUNCH_CHECK();
@@ -437,6 +436,11 @@ int pegncde_param_offsets(const PegDims* dims, int64_t* offsets) {
     offsets[5 * l + 4] = m.layer[l].fus_off;
   }
   return PEG_OK;
+}
+
+size_t pegncde_stage_store_bytes(const PegDims* dims, int32_t steps) {
+  if (check_dims(dims) != PEG_OK || steps < 1) return 0;
+  return (size_t)steps * 6 * dims->L * dims->B * dims->n * dims->h * sizeof(float);
 }
 
 size_t pegncde_workspace_bytes(const PegDims* dims, int32_t which, int32_t steps) {
@@ -562,7 +566,7 @@ int pegncde_step_fwd(peg_stream_t stream, const PegDims* dims, const PegControl*
 
 int pegncde_solve_fwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params,
                       const float* step_ts, int32_t steps, const float* y0, float* yT, float* y_ckpt,
-                      void* workspace, size_t workspace_bytes) {
+                      float* stage_store, void* workspace, size_t workspace_bytes) {
   Ctx c;
   PEG_TRY(make_ctx(c, stream, dims, ctl, params));
   if (!step_ts || !y0 || !y_ckpt || !workspace) return PEG_ERR_NULL_POINTER;
@@ -576,22 +580,34 @@ int pegncde_solve_fwd(peg_stream_t stream, const PegDims* dims, const PegControl
   PEG_CUDA(cudaMemcpyAsync(y_ckpt, y0, st * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
   float* k[7];
   for (int i = 0; i < 7; ++i) k[i] = s.k[i];
+  const int L = dims->L;
+  // stage_store[step][stage 0..5][layer 0..L-1][B,n,h]: the input of every layer of every stage (layer 0 of stage 0 is
+  // y_ckpt[step] itself and stays unused), so that solve_bwd needs no forward recompute.
+  auto store_slot = [&](int step, int stage, int l) { return stage_store + (((size_t)step * 6 + stage) * L + l) * st; };
+  float* save_arr[PEG_MAX_LAYERS];
+  auto saves = [&](int step, int stage) -> float* const* {
+    if (!stage_store) return nullptr;
+    save_arr[0] = nullptr;
+    for (int l = 1; l < L; ++l) save_arr[l] = store_slot(step, stage, l);
+    return save_arr;
+  };
   for (int sidx = 0; sidx < steps; ++sidx) {
     const float t = step_ts[sidx];
     const float dt = step_ts[sidx + 1] - step_ts[sidx];
     const float* y = y_ckpt + (size_t)sidx * st;
     float* ynext = y_ckpt + (size_t)(sidx + 1) * st;
-    if (sidx == 0) PEG_TRY(feval_fwd(c, t, y, k[0], nullptr));
+    if (sidx == 0) PEG_TRY(feval_fwd(c, t, y, k[0], saves(0, 0)));
     for (int i = 1; i < 7; ++i) {
       const float* xs[8];
       double cs[8];
       xs[0] = y; cs[0] = 1.0;
       for (int j = 0; j < i; ++j) { xs[j + 1] = k[j]; cs[j + 1] = (double)dt * tb.a[i][j]; }
-      float* zin = (i == 6) ? ynext : s.Z0;
+      float* zin = (i == 6) ? ynext : (stage_store ? store_slot(sidx, i, 0) : s.Z0);
       PEG_TRY(combine(c, zin, i + 1, xs, cs));
       if (i == 6 && sidx == steps - 1) break;  // the 7th stage only feeds FSAL: unused after the last step
       const float ti = (i == 6) ? step_ts[sidx + 1] : (t + (float)tb.c[i] * dt);
-      PEG_TRY(feval_fwd(c, ti, zin, k[i], nullptr));
+      // the 7th stage IS stage 0 of the next step (FSAL): its layer inputs are stored there
+      PEG_TRY(feval_fwd(c, ti, zin, k[i], i == 6 ? saves(sidx + 1, 0) : saves(sidx, i)));
     }
     float* tmp = k[0]; k[0] = k[6]; k[6] = tmp;  // FSAL
   }
@@ -600,8 +616,9 @@ int pegncde_solve_fwd(peg_stream_t stream, const PegDims* dims, const PegControl
 }
 
 int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params,
-                      const float* step_ts, int32_t steps, const float* y_ckpt, const float* g_yT,
-                      const float* g_ckpt, float* g_y0, float* g_params, void* workspace, size_t workspace_bytes) {
+                      const float* step_ts, int32_t steps, const float* y_ckpt, const float* stage_store,
+                      const float* g_yT, const float* g_ckpt, float* g_y0, float* g_params, void* workspace,
+                      size_t workspace_bytes) {
   Ctx c;
   PEG_TRY(make_ctx(c, stream, dims, ctl, params));
   if (!step_ts || !y_ckpt || !g_yT || !g_y0 || !g_params || !workspace) return PEG_ERR_NULL_POINTER;
@@ -624,9 +641,9 @@ int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl
     const float dt = step_ts[sidx + 1] - step_ts[sidx];
     const float* y = y_ckpt + (size_t)sidx * st;
     float tis[6];
-    // ---- recompute the six stages of this step, keeping every layer input ----
-    for (int i = 0; i < 6; ++i) {
-      tis[i] = (i == 0) ? t : (t + (float)tb.c[i] * dt);
+    for (int i = 0; i < 6; ++i) tis[i] = (i == 0) ? t : (t + (float)tb.c[i] * dt);
+    // ---- recompute the six stages of this step, keeping every layer input (skipped when solve_fwd stored them) ----
+    for (int i = 0; i < 6 && !stage_store; ++i) {
       float* zin;
       if (i == 0) {
         zin = const_cast<float*>(y);
@@ -652,8 +669,14 @@ int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl
       for (int j = i + 1; j < 6; ++j) { xs[cnt] = s.Ybar[j]; cs[cnt] = (double)dt * tb.a[j][i]; ++cnt; }
       PEG_TRY(combine(c, s.kbar, cnt, xs, cs));
       float* save[PEG_MAX_LAYERS];
-      save[0] = (i == 0) ? const_cast<float*>(y) : s.save[i][0];
-      for (int l = 1; l < L; ++l) save[l] = s.save[i][l];
+      if (stage_store) {
+        float* base = const_cast<float*>(stage_store) + ((size_t)sidx * 6 + i) * L * st;
+        save[0] = (i == 0) ? const_cast<float*>(y) : base;
+        for (int l = 1; l < L; ++l) save[l] = base + (size_t)l * st;
+      } else {
+        save[0] = (i == 0) ? const_cast<float*>(y) : s.save[i][0];
+        for (int l = 1; l < L; ++l) save[l] = s.save[i][l];
+      }
       PEG_TRY(feval_vjp(c, tis[i], save, s.kbar, s.Ybar[i], g_params, nullptr));
     }
     // ---- ybar_s = g + sum_i Ybar_i (+ injected cotangent at this boundary) ----

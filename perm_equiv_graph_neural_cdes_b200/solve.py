@@ -81,7 +81,7 @@ def constant_step_table(t0: float, t1: float, dt0: float, rule: str = "state", m
 
 class _SolveFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y0, flat, pc, dims, step_ts, save_steps):
+    def forward(ctx, y0, flat, pc, dims, step_ts, save_steps, store_stages):
         y0 = y0.contiguous()
         flat = flat.contiguous()
         S = len(step_ts) - 1
@@ -92,10 +92,19 @@ class _SolveFunction(torch.autograd.Function):
         y_ckpt = torch.empty((S + 1,) + tuple(y0.shape), dtype=torch.float32, device=dev)
         host_ts = np.ascontiguousarray(step_ts, dtype=np.float32)
         ctl = pc.struct()
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        store = None
+        if store_stages and need_grad:
+            nbytes_store = l.pegncde_stage_store_bytes(dims, S)
+            free, _ = torch.cuda.mem_get_info(dev)
+            if nbytes_store < 0.5 * free:   # otherwise fall back to checkpoint-per-step + recompute
+                store = torch.empty(nbytes_store // 4, dtype=torch.float32, device=dev)
         check(l.pegncde_solve_fwd(_stream_ptr(dev), dims, ctl, flat.data_ptr(),
                                   host_ts.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), S, y0.data_ptr(), None,
-                                  y_ckpt.data_ptr(), ws.data_ptr(), ws.numel()), "pegncde_solve_fwd")
+                                  y_ckpt.data_ptr(), store.data_ptr() if store is not None else None, ws.data_ptr(),
+                                  ws.numel()), "pegncde_solve_fwd")
         ctx.save_for_backward(flat, y_ckpt)
+        ctx.store = store
         ctx.pc, ctx.dims, ctx.host_ts, ctx.S, ctx.save_steps = pc, dims, host_ts, S, save_steps
         return y_ckpt if save_steps else y_ckpt[S]
 
@@ -117,11 +126,13 @@ class _SolveFunction(torch.autograd.Function):
         g_y0 = torch.empty_like(y_ckpt[0])
         g_flat = torch.zeros_like(flat)
         ctl = pc.struct()
+        store = ctx.store
         check(l.pegncde_solve_bwd(_stream_ptr(dev), dims, ctl, flat.data_ptr(),
                                   ctx.host_ts.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), S, y_ckpt.data_ptr(),
-                                  g_yT.data_ptr(), g_ckpt.data_ptr() if g_ckpt is not None else None, g_y0.data_ptr(),
+                                  store.data_ptr() if store is not None else None, g_yT.data_ptr(), g_ckpt.data_ptr() if g_ckpt is not None else None, g_y0.data_ptr(),
                                   g_flat.data_ptr(), ws.data_ptr(), ws.numel()), "pegncde_solve_bwd")
-        return g_y0, g_flat, None, None, None, None
+        ctx.store = None
+        return g_y0, g_flat, None, None, None, None, None
 
 
 def _unwrap(term):
@@ -163,7 +174,7 @@ def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: Optional[S
     yb = (y0.unsqueeze(0) if unb else y0).to(torch.float32)
     if yb.shape[0] != pc.B:
         raise ValueError(f"state batch {yb.shape[0]} != control batch {pc.B}")
-    out = _SolveFunction.apply(yb, vf.flat_params(), pc, dims, step_ts, bool(saveat.steps))
+    out = _SolveFunction.apply(yb, vf.flat_params(), pc, dims, step_ts, bool(saveat.steps), bool(getattr(vf, "store_stages", True)))
     S = len(step_ts) - 1
     if saveat.steps:
         ys = out.squeeze(1) if unb else out

@@ -99,6 +99,8 @@ class PermEquivGraphVectorField(nn.Module):
         self.hidden_dim = hidden_dim
         self.output_dim = output_dim
         self.flags = 0
+        # keep every stage's layer inputs in the forward solve so the adjoint needs no recompute (memory permitting)
+        self.store_stages = True
 
     # ---- packing -------------------------------------------------------------------------
     @property

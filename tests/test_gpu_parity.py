@@ -277,3 +277,18 @@ def test_tf32_fast_mode_has_its_own_looser_tolerance(cuda):
     sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 3.0, 0.1, p.y0.to(cuda), args)
     err = rel_err(sol.ys[-1], g["yT64"])
     assert err < 5e-3, err
+
+
+def test_stage_store_and_recompute_adjoints_agree(cuda):
+    """solve_bwd with the forward's stored stage inputs (no recompute) == checkpoint-per-step + recompute."""
+    p = R.make_problem(n=40, h=16, e=2, L=3, T=4, t1=3, dt0=0.25, seed=0)
+    outs = []
+    for store in (True, False):
+        vf, term, args = device_model(p, cuda)
+        vf.store_stages = store
+        y0 = p.y0.to(cuda).requires_grad_(True)
+        sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 3.0, 0.25, y0, args)
+        (sol.ys[-1] * p.gyT.to(cuda)).sum().backward()
+        outs.append((y0.grad.clone(), torch.cat([t.reshape(-1) for layer in product_grads_as_oracle(vf) for t in layer])))
+    assert rel_err(outs[0][0], outs[1][0]) < 1e-6
+    assert rel_err(outs[0][1], outs[1][1]) < 1e-5

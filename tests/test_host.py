@@ -53,9 +53,9 @@ def test_bad_dims_are_rejected_without_touching_the_gpu():
         assert l.pegncde_workspace_bytes(d, 0, 1) == 0
     assert l.pegncde_workspace_bytes(_lib.PegDims(**good), 99, 1) == 0
     # a compute entry point validates before any CUDA call
-    rc = l.pegncde_solve_fwd(None, _lib.PegDims(**{**good, "h": 6}), _lib.PegControl(), None, None, 1, None, None, None, None, 0)
+    rc = l.pegncde_solve_fwd(None, _lib.PegDims(**{**good, "h": 6}), _lib.PegControl(), None, None, 1, None, None, None, None, None, 0)
     assert rc == 1
-    rc = l.pegncde_solve_fwd(None, _lib.PegDims(**good), _lib.PegControl(), None, None, 1, None, None, None, None, 0)
+    rc = l.pegncde_solve_fwd(None, _lib.PegDims(**good), _lib.PegControl(), None, None, 1, None, None, None, None, None, 0)
     assert rc == 2  # null pointers
 
 
