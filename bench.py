@@ -165,7 +165,7 @@ def run_ours(args):
     S = len(step_ts) - 1
     l = _lib.lib()
 
-    def solve_step(pc_, y0_):
+    def solve_step(pc_, y0_, reduce=True):
         vf.zero_grad(set_to_none=True)
         y = y0_.detach().requires_grad_(True)
         sol = P.diffeqsolve(term, P.Tsit5(), 0.0, t1_solve, wl["dt0"], y, [pc_, None] if e > 0 else pc_,
@@ -173,7 +173,7 @@ def run_ours(args):
         loss = (sol.ys[-1] * gy).sum()
         loss.backward()
         flat_g = torch.cat([p.grad.reshape(-1) for p in vf.parameters()])
-        if world > 1:
+        if world > 1 and reduce:
             torch.distributed.all_reduce(flat_g)
         return loss, flat_g
 
@@ -183,28 +183,61 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident leg: `value` ----------------
-    for _ in range(args.warmup):
+    # The C-ABI only enqueues kernels, so one whole forward + adjoint solve is captured once into a CUDA graph and
+    # replayed: ~2.5k dependent launches per step are otherwise host-launch-bound for the smaller shapes.
+    for _ in range(max(args.warmup, 1)):
         solve_step(pc, y0)
     barrier()
+    graph = None
     l.pegncde_profile_enable(args.profile_stride)
     launches0 = l.pegncde_launch_count()
+    if not args.no_graph:
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            solve_step(pc, y0, reduce=False)   # warm the capture stream's workspace
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        l.pegncde_profile_enable(args.profile_stride)
+        launches0 = l.pegncde_launch_count()
+        with torch.cuda.graph(graph):
+            g_loss, g_flat = solve_step(pc, y0, reduce=False)
+        launches_per_step = l.pegncde_launch_count() - launches0
+        for _ in range(2):
+            graph.replay()
+        barrier()
+
+    def timed_step():
+        if graph is not None:
+            graph.replay()
+            if world > 1:
+                torch.distributed.all_reduce(g_flat)
+        else:
+            solve_step(pc, y0)
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    host_t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        solve_step(pc, y0)
+        timed_step()
     e1.record()
+    host_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps
     barrier()
     clocks = sampler.summary()
     ms = e0.elapsed_time(e1)
-    launches = l.pegncde_launch_count() - launches0
+    if graph is None:
+        launches_per_step = (l.pegncde_launch_count() - launches0) // max(args.steps, 1)
+    launches = launches_per_step * args.steps
     prof = {}
     for d, nm in ((0, "fwd"), (1, "bwd")):
         a, b_, c_, by, fl = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
         l.pegncde_profile_read(d, a, b_, c_, by, fl)
         prof[nm] = dict(launches=a.value, timed=b_.value, ms=c_.value, bytes=by.value, flops=fl.value)
     l.pegncde_profile_enable(0)
+    prof_steps = 1 if graph is not None else args.steps   # a replayed graph re-records the same event pairs
     t = torch.tensor([ms], device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -252,7 +285,7 @@ def run_ours(args):
         tf32_peak = pk["bf16"] / 2.0
         t_hbm, t_tc = by / (pk["hbm"] * 1e9), fl / (tf32_peak * 1e12)
         bound = "hbm" if t_hbm >= t_tc else "tensor"
-        share = tot_ms * (prof["fwd"]["launches"] + prof["bwd"]["launches"]) / max(tot_timed, 1) / (ms_per_step * args.steps)
+        share = tot_ms * (prof["fwd"]["launches"] + prof["bwd"]["launches"]) / max(tot_timed, 1) / (ms_per_step * prof_steps)
         roof = {"bound": bound, "kernel": "dual_contract (fwd+bwd launches)",
                 "achieved": gbs if bound == "hbm" else tfs, "peak": pk["hbm"] if bound == "hbm" else tf32_peak,
                 "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": (gbs / pk["hbm"]) if bound == "hbm" else (tfs / tf32_peak),
@@ -280,7 +313,7 @@ def run_ours(args):
                        "parallelism": "batch of trajectories sharded over %d GPU(s); NCCL all-reduce of %d param grads" % (world, vf.flat_params().numel()),
                        "l2": "inputs per GPU %.0f MB of coefficient planes (> L2 126 MB: %s)" % (pc.adj_coef.numel() * 4 / 1e6, pc.adj_coef.numel() * 4 > 126e6)},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": k_e2e},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+            "gpu_launches": int(launches), "cuda_graph": graph is not None, "host_ms_per_step": host_ms, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
         }
         print(json.dumps(line))
     if world > 1:
@@ -362,6 +395,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample-steps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     ap.add_argument("--t1", type=float, default=0.0, help="profiling only: shorten the solve to [0, t1] (fewer solver steps)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -37,36 +37,49 @@ __device__ __forceinline__ float block_sum(float v, float* sh /* >= 33 floats */
 
 // grid (nt*nt tiles, T-1, B), block 256: one block per 32x32 tile.  Source is either the reference layout
 // (d,c,b,a each [B,T-1,n,n,2]) or, for pegncde_adj_stats, the already tiled planes (tiled_in).
+// Reads are coalesced float2 rows of the source, writes are coalesced float4 of the 16-KB tile (staged in smem).
 __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, const float* __restrict__ cc,
                                                   const float* __restrict__ cb, const float* __restrict__ ca,
                                                   const float* __restrict__ tiled_in, int n, int npad, int Tm1,
                                                   float* __restrict__ adj_coef, float* __restrict__ rowsum,
-                                                  float* __restrict__ diag, float* __restrict__ total) {
+                                                  float* __restrict__ diag, float* __restrict__ total,
+                                                  float* __restrict__ tch) {
+  __shared__ __align__(16) float tile[4096];   // the tile in its final element order
+  __shared__ float tcol[3][32];                // column sums of the time channel of (b,c,d)
   const int b = blockIdx.z, iv = blockIdx.y;
   const int nt = npad >> 5;
   const int rt = blockIdx.x / nt, ct = blockIdx.x % nt;
   const int lane = threadIdx.x & 31;
   const size_t slab = ((size_t)b * Tm1 + iv);
-  const size_t slab_off = slab * 4 * (size_t)npad * npad;
+  const size_t tile_base = slab * 4 * (size_t)npad * npad + ((size_t)rt * nt + ct) * 4096;
   const float* src[4] = {ca, cb, cc, cd};  // (a,b,c,d) order
   float tot[4] = {0.f, 0.f, 0.f, 0.f};
+  float tsum[3] = {0.f, 0.f, 0.f};
+  if (threadIdx.x < 96) tcol[threadIdx.x >> 5][lane] = 0.f;
+  __syncthreads();
+  if (tiled_in) {
+    for (int idx = threadIdx.x; idx < 1024; idx += 256)
+      *reinterpret_cast<float4*>(&tile[4 * idx]) = *reinterpret_cast<const float4*>(tiled_in + tile_base + 4 * idx);
+    __syncthreads();
+  }
   for (int idx = threadIdx.x; idx < 1024; idx += 256) {
     const int r = idx >> 5, c = idx & 31;      // r is warp-uniform, c == lane
     const int i = rt * 32 + r, k = ct * 32 + c;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       float v = 0.f;
-      const size_t to = slab_off + peg_tile_off(i, k, p, nt);
+      const int to = (int)peg_tile_off(r, c, p, 1);   // offset inside the tile
       if (i < n && k < n) {
         if (tiled_in) {
-          v = tiled_in[to];
+          v = tile[to];
         } else {
-          const float2 tv = reinterpret_cast<const float2*>(src[p])[(slab * n + i) * (size_t)n + k];
+          const float2 tv = __ldg(reinterpret_cast<const float2*>(src[p]) + (slab * n + i) * (size_t)n + k);
           v = tv.y;
+          if (p > 0) tsum[p - 1] += tv.x;
         }
         if (i == k) diag[(slab * 4 + p) * n + i] = v;
       }
-      if (!tiled_in) adj_coef[to] = v;
+      if (!tiled_in) tile[to] = v;
       const float rs = warp_sum(v);
       if (lane == 0 && i < n) {
         atomicAdd(&rowsum[(slab * 4 + p) * n + i], rs);
@@ -74,25 +87,20 @@ __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, 
       }
     }
   }
+  if (!tiled_in) {
+#pragma unroll
+    for (int p = 0; p < 3; ++p) atomicAdd(&tcol[p][lane], tsum[p]);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 1024; idx += 256)
+      *reinterpret_cast<float4*>(adj_coef + tile_base + 4 * idx) = *reinterpret_cast<const float4*>(&tile[4 * idx]);
+    if (threadIdx.x < 96) {   // tch[b,iv,p,k] = mean over rows of the time channel (accumulated over the row tiles)
+      const int p = threadIdx.x >> 5, k = ct * 32 + lane;
+      if (k < n) atomicAdd(&tch[(slab * 3 + p) * n + k], tcol[p][lane] / (float)n);
+    }
+  }
   if (lane == 0) {
 #pragma unroll
     for (int p = 0; p < 4; ++p) atomicAdd(&total[slab * 4 + p], tot[p]);
-  }
-}
-
-// time channel: tch[b,iv,p,j] = mean_i coef_p[b,iv,i,j,0], p in (b,c,d).  grid (ceil(n/256), T-1, B)
-__global__ void __launch_bounds__(256) k_pack_tch(const float* __restrict__ cd, const float* __restrict__ cc,
-                                                  const float* __restrict__ cb, int n, int Tm1,
-                                                  float* __restrict__ tch) {
-  const int b = blockIdx.z, iv = blockIdx.y;
-  const int j = blockIdx.x * 256 + threadIdx.x;
-  if (j >= n) return;
-  const size_t slab = ((size_t)b * Tm1 + iv);
-  const float* src[3] = {cb, cc, cd};
-  for (int p = 0; p < 3; ++p) {
-    float acc = 0.f;
-    for (int i = 0; i < n; ++i) acc += src[p][((slab * n + i) * (size_t)n + j) * 2];
-    tch[(slab * 3 + p) * n + j] = acc / (float)n;
   }
 }
 

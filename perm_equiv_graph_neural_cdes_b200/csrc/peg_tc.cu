@@ -517,29 +517,48 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   p.tmem_cols = tmem_cols_pow2((bwd ? 4 : 1) * p.nd);
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (3 * stages + 2) + 64;
 
-  CUtensorMap mhi, mlo;
-  const cuuint64_t gdim[2] = {(cuuint64_t)npad, (cuuint64_t)dm.B * d};
-  const cuuint64_t gstr[1] = {(cuuint64_t)npad * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)p.nd};
-  const cuuint32_t estr[2] = {1, 1};
-  if (enc(&mhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w.Vt_hi, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return PEG_ERR_CUDA;
-  if (enc(&mlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w.Vt_lo, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return PEG_ERR_CUDA;
+  // tensor maps depend only on (buffer, rows, npad, box): a tiny per-thread cache keeps the driver call off the hot path
+  struct MapKey { const void* hi; const void* lo; uint64_t rows; int npad, nd; };
+  struct MapEntry { MapKey k; CUtensorMap mhi, mlo; bool valid; };
+  static thread_local MapEntry cache[8];
+  static thread_local int cache_next = 0;
+  const MapKey key = {w.Vt_hi, w.Vt_lo, (uint64_t)dm.B * d, npad, p.nd};
+  MapEntry* ent = nullptr;
+  for (int i = 0; i < 8; ++i)
+    if (cache[i].valid && cache[i].k.hi == key.hi && cache[i].k.lo == key.lo && cache[i].k.rows == key.rows &&
+        cache[i].k.npad == key.npad && cache[i].k.nd == key.nd) { ent = &cache[i]; break; }
+  if (!ent) {
+    ent = &cache[cache_next];
+    cache_next = (cache_next + 1) % 8;
+    ent->valid = false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)npad, (cuuint64_t)dm.B * d};
+    const cuuint64_t gstr[1] = {(cuuint64_t)npad * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)p.nd};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&ent->mhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w.Vt_hi, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return PEG_ERR_CUDA;
+    if (enc(&ent->mlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w.Vt_lo, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return PEG_ERR_CUDA;
+    ent->k = key;
+    ent->valid = true;
+  }
+  const CUtensorMap& mhi = ent->mhi;
+  const CUtensorMap& mlo = ent->mlo;
 
   dim3 grid((n + TC_BM - 1) / TC_BM, d / p.nd, dm.B);
-  cudaError_t e;
-  if (bwd) {
-    e = cudaFuncSetAttribute(k_tc_contract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static thread_local size_t smem_set[2] = {0, 0};   // largest dynamic-smem opt-in already applied per variant
+  if (smem > smem_set[bwd ? 1 : 0]) {
+    const cudaError_t e = bwd ? cudaFuncSetAttribute(k_tc_contract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : cudaFuncSetAttribute(k_tc_contract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return PEG_ERR_CUDA;
-    k_tc_contract<true><<<grid, TC_THREADS, smem, st>>>(mhi, mlo, p);
-  } else {
-    e = cudaFuncSetAttribute(k_tc_contract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return PEG_ERR_CUDA;
-    k_tc_contract<false><<<grid, TC_THREADS, smem, st>>>(mhi, mlo, p);
+    smem_set[bwd ? 1 : 0] = smem;
   }
+  if (bwd)
+    k_tc_contract<true><<<grid, TC_THREADS, smem, st>>>(mhi, mlo, p);
+  else
+    k_tc_contract<false><<<grid, TC_THREADS, smem, st>>>(mhi, mlo, p);
   if (cudaPeekAtLastError() != cudaSuccess) return PEG_ERR_CUDA;
   return PEG_OK;
 }

@@ -60,10 +60,10 @@ static inline bool prof_begin(int dir, cudaStream_t st, double bytes, double flo
   if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return false;
   p.ev[dir].push_back(e0);
   p.ev[dir].push_back(e1);
-  cudaEventRecord(e0, st);
+  cudaEventRecordWithFlags(e0, st, cudaEventRecordExternal);
   return true;
 }
-static inline void prof_end(int dir, cudaStream_t st) { cudaEventRecord(g_prof.ev[dir].back(), st); }
+static inline void prof_end(int dir, cudaStream_t st) { cudaEventRecordWithFlags(g_prof.ev[dir].back(), st, cudaEventRecordExternal); }
 
 static inline int last_width(const PegDims& d) { return d.e > 0 ? 2 * d.h * d.e : d.h; }
 
@@ -311,7 +311,10 @@ static int feval_vjp(Ctx& c, float t, float* const* zin, const float* kbar, floa
     }
     {
       const size_t rows = (size_t)d.B * d.n;
-      const int rps = 512;
+      // slices of the node dimension: enough blocks to fill the GPU even for small d_out x d_in
+      const int tiles = ((ld.dout + 63) / 64) * ((ld.din + 63) / 64);
+      int rps = 512;
+      while (rps > 64 && tiles * ((rows + rps - 1) / rps) < 296) rps >>= 1;
       dim3 grid((ld.dout + 63) / 64, (ld.din + 63) / 64, (unsigned)((rows + rps - 1) / rps));
       k_weight_grad<<<grid, 256, 0, c.st>>>(c.w.Mbar, c.w.N, rows, ld.din, ld.dout, rps, g_params + ld.w_off,
                                             g_params + ld.b_off);
@@ -461,17 +464,15 @@ static int pack_common(peg_stream_t stream, const PegDims* dims, const float* d,
   PEG_CUDA(cudaMemsetAsync(adj_rowsum, 0, slabs * 4 * dims->n * sizeof(float), st));
   const int nt = dims->ldn / 32;
   dim3 grid(nt * nt, Tm1, dims->B);
+  if (!planar) PEG_CUDA(cudaMemsetAsync(tch_coef, 0, slabs * 3 * dims->n * sizeof(float), st));
   k_pack_adj<<<grid, 256, 0, st>>>(d, c, b, a, planar, dims->n, dims->ldn, Tm1, adj_coef, adj_rowsum, adj_diag,
-                                   adj_total);
+                                   adj_total, tch_coef);
   PEG_LAUNCH_CHECK();
   if (planar) {
     const size_t cnt = slabs * 3 * dims->n;
     k_fill_tch_unit<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(tch_coef, dims->n, slabs);
-  } else {
-    dim3 g2((dims->n + 255) / 256, Tm1, dims->B);
-    k_pack_tch<<<g2, 256, 0, st>>>(d, c, b, dims->n, Tm1, tch_coef);
+    PEG_LAUNCH_CHECK();
   }
-  PEG_LAUNCH_CHECK();
   return PEG_OK;
 }
 

@@ -96,7 +96,8 @@ class _SolveFunction(torch.autograd.Function):
         store = None
         if store_stages and need_grad:
             nbytes_store = l.pegncde_stage_store_bytes(dims, S)
-            free, _ = torch.cuda.mem_get_info(dev)
+            capturing = torch.cuda.is_current_stream_capturing()
+            free = torch.cuda.mem_get_info(dev)[0] if not capturing else float("inf")
             if nbytes_store < 0.5 * free:   # otherwise fall back to checkpoint-per-step + recompute
                 store = torch.empty(nbytes_store // 4, dtype=torch.float32, device=dev)
         check(l.pegncde_solve_fwd(_stream_ptr(dev), dims, ctl, flat.data_ptr(),
