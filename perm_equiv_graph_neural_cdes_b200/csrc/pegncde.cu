@@ -49,6 +49,16 @@ struct Prof {
 static Prof g_prof;
 static const size_t kMaxProfPairs = 16384;
 
+// events recorded while the stream is being captured into a CUDA graph must be external event-record nodes
+static inline void record_event(cudaEvent_t e, cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (cs == cudaStreamCaptureStatusActive)
+    cudaEventRecordWithFlags(e, st, cudaEventRecordExternal);
+  else
+    cudaEventRecord(e, st);
+}
+
 static inline bool prof_begin(int dir, cudaStream_t st, double bytes, double flops) {
   Prof& p = g_prof;
   if (p.stride <= 0) return false;
@@ -60,10 +70,10 @@ static inline bool prof_begin(int dir, cudaStream_t st, double bytes, double flo
   if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return false;
   p.ev[dir].push_back(e0);
   p.ev[dir].push_back(e1);
-  cudaEventRecordWithFlags(e0, st, cudaEventRecordExternal);
+  record_event(e0, st);
   return true;
 }
-static inline void prof_end(int dir, cudaStream_t st) { cudaEventRecordWithFlags(g_prof.ev[dir].back(), st, cudaEventRecordExternal); }
+static inline void prof_end(int dir, cudaStream_t st) { record_event(g_prof.ev[dir].back(), st); }
 
 static inline int last_width(const PegDims& d) { return d.e > 0 ? 2 * d.h * d.e : d.h; }
 
