@@ -146,7 +146,8 @@ int pegncde_solve_fwd(peg_stream_t stream, const PegDims* dims, const PegControl
  * over the coefficient planes per step).  NULL = checkpoint-per-step mode: solve_bwd recomputes each step. */
 size_t pegncde_stage_store_bytes(const PegDims* dims, int32_t steps);
 /* g_ckpt (nullable) [steps+1, B, n, h]: cotangents injected at step boundaries (SaveAt(ts=...) losses);
- * g_yT [B,n,h] cotangent of y(T).  Writes g_y0; accumulates g_params (caller zeroes it). */
+ * g_yT [B,n,h] cotangent of y(T) (either of the two may be NULL, not both).  Writes g_y0; accumulates g_params
+ * (caller zeroes it). */
 int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params,
                       const float* step_ts, int32_t steps, const float* y_ckpt, const float* stage_store,
                       const float* g_yT, const float* g_ckpt, float* g_y0, float* g_params, void* workspace,

@@ -632,7 +632,7 @@ int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl
                       size_t workspace_bytes) {
   Ctx c;
   PEG_TRY(make_ctx(c, stream, dims, ctl, params));
-  if (!step_ts || !y_ckpt || !g_yT || !g_y0 || !g_params || !workspace) return PEG_ERR_NULL_POINTER;
+  if (!step_ts || !y_ckpt || (!g_yT && !g_ckpt) || !g_y0 || !g_params || !workspace) return PEG_ERR_NULL_POINTER;
   if (steps < 1) return PEG_ERR_BAD_DIMS;
   if (workspace_bytes < plan(*dims, PEG_WS_SOLVE_BWD, steps, nullptr, nullptr, nullptr)) return PEG_ERR_WORKSPACE;
   SolveWs s;
@@ -644,7 +644,7 @@ int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl
   // running cotangent of y_{s+1}
   {
     const float* xs[2] = {g_yT, g_ckpt ? g_ckpt + (size_t)steps * st : nullptr};
-    double cs[2] = {1.0, g_ckpt ? 1.0 : 0.0};
+    double cs[2] = {g_yT ? 1.0 : 0.0, g_ckpt ? 1.0 : 0.0};
     PEG_TRY(combine(c, s.gcur, 2, xs, cs));
   }
   for (int sidx = steps - 1; sidx >= 0; --sidx) {
