@@ -19,6 +19,7 @@
 // the two correction products.
 #include <cuda.h>
 #include <cstdlib>
+#include <cstring>
 
 #include "peg_tc.cuh"
 
@@ -64,6 +65,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t"
@@ -76,6 +93,10 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -147,6 +168,7 @@ struct TcParams {
   int stages;
   int nkc;       // number of 32-wide K chunks = npad / 32
   int tmem_cols; // power of two >= 32
+  int cluster;   // CTAs per cluster sharing the B operand by TMA multicast (1 = no cluster)
 };
 
 template <bool BWD>
@@ -158,6 +180,12 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, I = blockIdx.x, ntile = blockIdx.y;
   const int n = a.n, d = a.d, nd = p.nd;
+  // CTAs of a cluster walk the K chunks in lockstep (schedule keyed on the cluster's first row block), so one
+  // B tile serves all of them: each CTA fetches 1/C of its rows and multicasts the slice to every peer.
+  const int C = p.cluster;
+  const int crank = C > 1 ? (int)cluster_ctarank() : 0;
+  const int Ibase = (I / C) * C;
+  const uint16_t cmask = (uint16_t)((1u << C) - 1u);
   const bool split = p.nsplit == 3;
 
   // ---- shared memory carve-up (1024-B aligned operand tiles) ----
@@ -178,7 +206,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_a(s), TC_CONV_THREADS);
       mbar_init(full_b(s), 1);
-      mbar_init(empty(s), 1);
+      mbar_init(empty(s), (uint32_t)C);   // one tcgen05.commit arrival from every CTA of the cluster
     }
     mbar_init(accum_bar, 1);
     fence_barrier_init();
@@ -189,6 +217,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (C > 1) cluster_sync_all();   // peers' barriers are initialised before any remote arrive / multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -239,8 +268,8 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         for (int u = 0; u < 16; ++u) buf[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    auto load_direct = [&](int j, float4 (&buf)[16]) { load_tile(4 * I + cv_u, (4 * I + (j >> 1)) % nkc, buf); };
-    auto load_transposed = [&](int j, float4 (&buf)[16]) { load_tile(((4 * I - (j >> 1)) % nkc + nkc) % nkc, 4 * I + cv_u, buf); };
+    auto load_direct = [&](int j, float4 (&buf)[16]) { load_tile(4 * I + cv_u, (4 * Ibase + (j >> 1)) % nkc, buf); };
+    auto load_transposed = [&](int j, float4 (&buf)[16]) { load_tile(((4 * Ibase - (j >> 1)) % nkc + nkc) % nkc, 4 * I + cv_u, buf); };
     // store one 16-byte chunk (4 consecutive k of row r) as tf32 hi (+ lo) into the swizzled K-major tile
     auto store_chunk = [&](uint32_t hi_base, int r, int chunk, float x0, float x1, float x2, float x3) {
       const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
@@ -306,12 +335,19 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         const int st = j % p.stages;
         const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
         const int s = j >> 1, type = j & 1;
-        const int kc = type == 0 ? (4 * I + s) % nkc : ((4 * I - s) % nkc + nkc) % nkc;
-        mbar_wait(empty(st), ph ^ 1u);
+        const int kc = type == 0 ? (4 * Ibase + s) % nkc : ((4 * Ibase - s) % nkc + nkc) % nkc;
+        mbar_wait(empty(st), ph ^ 1u);   // every CTA of the cluster has finished reading this stage
         const uint32_t b_base = smem_base + st * stage_bytes + a_bytes;
         mbar_expect_tx(full_b(st), (uint32_t)b_bytes);
-        tma_load_2d(b_base, &map_hi, kc * TC_BK, row0, full_b(st));
-        if (split) tma_load_2d(b_base + b_tile, &map_lo, kc * TC_BK, row0, full_b(st));
+        if (C == 1) {
+          tma_load_2d(b_base, &map_hi, kc * TC_BK, row0, full_b(st));
+          if (split) tma_load_2d(b_base + b_tile, &map_lo, kc * TC_BK, row0, full_b(st));
+        } else {
+          const int rows = nd / C;                       // this CTA's slice of the B tile (box = 32 x rows)
+          const uint32_t off = (uint32_t)(crank * rows) * 128u;
+          tma_load_2d_mcast(b_base + off, &map_hi, kc * TC_BK, row0 + crank * rows, full_b(st), cmask);
+          if (split) tma_load_2d_mcast(b_base + b_tile + off, &map_lo, kc * TC_BK, row0 + crank * rows, full_b(st), cmask);
+        }
       }
     }
   } else {
@@ -346,7 +382,8 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             }
           }
         }
-        umma_commit(empty(st));   // frees this smem stage once the MMAs above have read it
+        if (C == 1) umma_commit(empty(st));   // frees this smem stage once the MMAs above have read it
+        else umma_commit_mcast(empty(st), cmask);   // ... in every CTA of the cluster (their producers multicast into it)
       }
       umma_commit(accum_bar);     // all accumulators final
     }
@@ -430,6 +467,8 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     tc_fence_before();
   }
   __syncthreads();
+  __syncwarp();
+  if (C > 1) cluster_sync_all();   // no CTA exits while peers may still multicast into it or arrive on its barriers
   if (warp == 9) {
     __syncwarp();
     tc_fence_after();
@@ -515,6 +554,11 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   if (stages < 1) return PEG_ERR_UNSUPPORTED;
   p.stages = stages;
   p.tmem_cols = tmem_cols_pow2((bwd ? 4 : 1) * p.nd);
+  const int nblk = (n + TC_BM - 1) / TC_BM;
+  int cluster = 2;
+  if (const char* ev = getenv("PEG_TC_CLUSTER")) { int v = atoi(ev); if (v == 1 || v == 2 || v == 4 || v == 8) cluster = v; }
+  while (cluster > 1 && (nblk < cluster || (p.nd / cluster) % 8 != 0)) cluster >>= 1;
+  p.cluster = cluster;
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (3 * stages + 2) + 64;
 
   // tensor maps depend only on (buffer, rows, npad, box): a tiny per-thread cache keeps the driver call off the hot path
@@ -522,7 +566,7 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   struct MapEntry { MapKey k; CUtensorMap mhi, mlo; bool valid; };
   static thread_local MapEntry cache[8];
   static thread_local int cache_next = 0;
-  const MapKey key = {w.Vt_hi, w.Vt_lo, (uint64_t)dm.B * d, npad, p.nd};
+  const MapKey key = {w.Vt_hi, w.Vt_lo, (uint64_t)dm.B * d, npad, p.nd / cluster};
   MapEntry* ent = nullptr;
   for (int i = 0; i < 8; ++i)
     if (cache[i].valid && cache[i].k.hi == key.hi && cache[i].k.lo == key.lo && cache[i].k.rows == key.rows &&
@@ -533,7 +577,7 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
     ent->valid = false;
     const cuuint64_t gdim[2] = {(cuuint64_t)npad, (cuuint64_t)dm.B * d};
     const cuuint64_t gstr[1] = {(cuuint64_t)npad * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)p.nd};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.nd / cluster)};
     const cuuint32_t estr[2] = {1, 1};
     if (enc(&ent->mhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w.Vt_hi, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -547,7 +591,7 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   const CUtensorMap& mhi = ent->mhi;
   const CUtensorMap& mlo = ent->mlo;
 
-  dim3 grid((n + TC_BM - 1) / TC_BM, d / p.nd, dm.B);
+  dim3 grid((nblk + cluster - 1) / cluster * cluster, d / p.nd, dm.B);   // padded row blocks only keep the cluster in lockstep
   static thread_local size_t smem_set[2] = {0, 0};   // largest dynamic-smem opt-in already applied per variant
   if (smem > smem_set[bwd ? 1 : 0]) {
     const cudaError_t e = bwd ? cudaFuncSetAttribute(k_tc_contract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
@@ -555,10 +599,22 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
     if (e != cudaSuccess) return PEG_ERR_CUDA;
     smem_set[bwd ? 1 : 0] = smem;
   }
-  if (bwd)
-    k_tc_contract<true><<<grid, TC_THREADS, smem, st>>>(mhi, mlo, p);
-  else
-    k_tc_contract<false><<<grid, TC_THREADS, smem, st>>>(mhi, mlo, p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t le = bwd ? cudaLaunchKernelEx(&cfg, k_tc_contract<true>, mhi, mlo, p)
+                             : cudaLaunchKernelEx(&cfg, k_tc_contract<false>, mhi, mlo, p);
+  if (le != cudaSuccess) return PEG_ERR_CUDA;
   if (cudaPeekAtLastError() != cudaSuccess) return PEG_ERR_CUDA;
   return PEG_OK;
 }
