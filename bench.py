@@ -29,15 +29,17 @@ WORKLOADS = {
     "sir": dict(n=100, h=32, e=3, L=3, T=120, t1=1.0, dt0=0.1, B=50, float_ts=True),
     "england": dict(n=129, h=64, e=8, L=3, T=4, t1=3.0, dt0=0.1, B=1),
     "twitter": dict(n=1000, h=64, e=16, L=3, T=9, t1=8.0, dt0=0.1, B=1),
-    "sweep_n1024_h64": dict(n=1024, h=64, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=16),
-    "sweep_n2048_h64": dict(n=2048, h=64, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=8),
-    "sweep_n2048_h128": dict(n=2048, h=128, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=8),
-    "sweep_n4096_h128": dict(n=4096, h=128, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=4),
+    # graphs per GPU are chosen so that (row blocks of 128) x B is just under a multiple of the 148 SMs
+    "sweep_n1024_h64": dict(n=1024, h=64, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=18),
+    "sweep_n2048_h64": dict(n=2048, h=64, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=9),
+    "sweep_n2048_h128": dict(n=2048, h=128, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=9),
+    "sweep_n4096_h128": dict(n=4096, h=128, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=9),
+    "sweep_n4096_h128_b4": dict(n=4096, h=128, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=4),
     "sweep_n4096_h256": dict(n=4096, h=256, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=4),
     "sweep_n8192_h128": dict(n=8192, h=128, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=2),
     "sweep_n16384_h256": dict(n=16384, h=256, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=1),
 }
-DEFAULT_WORKLOAD = "sweep_n2048_h64"
+DEFAULT_WORKLOAD = "sweep_n2048_h128"
 METRIC = "graph-trajectory solver steps/sec (fwd+bwd)"
 UNIT = "solver steps/s"
 

@@ -555,7 +555,7 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   p.stages = stages;
   p.tmem_cols = tmem_cols_pow2((bwd ? 4 : 1) * p.nd);
   const int nblk = (n + TC_BM - 1) / TC_BM;
-  int cluster = 2;
+  int cluster = 1;   // measured on B200: multicast does not pay (the SM ingress port, not L2, is the limit); PEG_TC_CLUSTER=2|4 enables it
   if (const char* ev = getenv("PEG_TC_CLUSTER")) { int v = atoi(ev); if (v == 1 || v == 2 || v == 4 || v == 8) cluster = v; }
   while (cluster > 1 && (nblk < cluster || (p.nd / cluster) % 8 != 0)) cluster >>= 1;
   p.cluster = cluster;
