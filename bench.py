@@ -44,6 +44,15 @@ METRIC = "graph-trajectory solver steps/sec (fwd+bwd)"
 UNIT = "solver steps/s"
 
 
+def measured_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/r01_traffic.json); None if no capture exists."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get(workload)
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -292,7 +301,7 @@ def run_ours(args):
                 "achieved": gbs if bound == "hbm" else tfs, "peak": pk["hbm"] if bound == "hbm" else tf32_peak,
                 "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": (gbs / pk["hbm"]) if bound == "hbm" else (tfs / tf32_peak),
                 "peak_source": pk["src"] + (" hbm_gbs" if bound == "hbm" else " bf16_tflops_sustained/2 (tf32)"),
-                "traffic": None, "achieved_gbs": gbs, "achieved_tflops": tfs, "avg_launch_us": tot_ms / tot_timed * 1e3,
+                "traffic": measured_traffic(args.workload), "achieved_gbs": gbs, "achieved_tflops": tfs, "avg_launch_us": tot_ms / tot_timed * 1e3,
                 "launches_timed": tot_timed, "share_of_step": share,
                 "fwd_avg_us": prof["fwd"]["ms"] / max(prof["fwd"]["timed"], 1) * 1e3, "bwd_avg_us": prof["bwd"]["ms"] / max(prof["bwd"]["timed"], 1) * 1e3,
                 "fwd_gbs": prof["fwd"]["bytes"] * prof["fwd"]["timed"] / max(prof["fwd"]["ms"], 1e-9) / 1e6,
@@ -395,7 +404,7 @@ def main():
     ap.add_argument("--tf32-fast", action="store_true")
     ap.add_argument("--profile-stride", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample-steps", type=int, default=1)
+    ap.add_argument("--cpu-sample-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     ap.add_argument("--t1", type=float, default=0.0, help="profiling only: shorten the solve to [0, t1] (fewer solver steps)")
