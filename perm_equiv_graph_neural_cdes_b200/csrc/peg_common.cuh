@@ -111,6 +111,7 @@ struct ContractArgs {
   float* g_fus;          // bwd only: gradient of the 16 fusion scalars (atomicAdd)
   int n, ldn /* = npad */, d, layer;
   int relu, scale_tg;
+  int vt_ready;          // the producer kernel already wrote V^T hi/lo (tensor-core path skips its own transpose pass)
 };
 
 struct Bump {

@@ -30,6 +30,56 @@ __device__ __forceinline__ float block_sum(float v, float* sh /* >= 33 floats */
   return sh[32];
 }
 
+// Fused-epilogue outputs of the kernels that PRODUCE the operand V of the next contraction:
+//   * V^T split into tf32 hi / lo, [B][d][npad] (the TMA-loaded K-major B operand of peg_tc.cu), zero padded;
+//   * column sums cb[b][0][c] = sum_i V[b,i,c], cb[b][1][c] = sum_i vec[b][i] V[b,i,c], reduced deterministically:
+//     every block writes its partial, the last block of a column group (ticket) adds them in block order.
+struct ProducerOut {
+  float* Thi;             // nullable
+  float* Tlo;
+  int npad;
+  float* cb;              // nullable
+  float* partial;         // [B][chunks][2][d]
+  unsigned int* tickets;  // self-resetting, one per (b, column group)
+  const float* vec;       // nullable; per-graph stride vec_stride
+  size_t vec_stride;
+};
+
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// called by ALL threads of the block after this block's partial sums for columns [c0, c0+ncols) have been written
+// to partial[b][chunk][*][c]; `is_last` must be a __shared__ bool.
+__device__ __forceinline__ void finalize_colsums(const ProducerOut& po, int b, int chunks, int d, int c0, int ncols,
+                                                 unsigned int* ticket, bool* is_last) {
+  __threadfence();
+  __syncthreads();
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    *is_last = (t == (unsigned int)chunks - 1u);
+    if (*is_last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (*is_last) {
+    __threadfence();
+    for (int c = tid; c < ncols; c += blockDim.x * blockDim.y) {
+      if (c0 + c >= d) continue;
+      float t0 = 0.f, t1 = 0.f;
+      for (int k = 0; k < chunks; ++k) {
+        const float* pk = po.partial + (((size_t)b * chunks + k) * 2) * d;
+        t0 += __ldcg(pk + c0 + c);
+        t1 += __ldcg(pk + d + c0 + c);
+      }
+      po.cb[((size_t)b * 2 + 0) * d + c0 + c] = t0;
+      po.cb[((size_t)b * 2 + 1) * d + c0 + c] = t1;
+    }
+  }
+}
+
 // =====================================================================================
 // control-path packing (pre-pass, once per batch)
 // reference layout: d,c,b,a each [B, T-1, n, n, 2], last axis (time, adjacency)
@@ -236,7 +286,8 @@ __global__ void __launch_bounds__(256) k_rk_combine(CombArgs a) {
 __global__ void __launch_bounds__(256) k_norm_linear(const float* __restrict__ Z, int n, int din, int dout,
                                                      const float* __restrict__ W, const float* __restrict__ bias,
                                                      const float* __restrict__ nw, const float* __restrict__ nb,
-                                                     float* __restrict__ M, float* __restrict__ Nout) {
+                                                     float* __restrict__ M, float* __restrict__ Nout, ProducerOut po) {
+  __shared__ bool is_last;
   __shared__ __align__(16) float zt[32][68];   // [k][node]  normalised input chunk
   __shared__ __align__(16) float wt[32][68];   // [k][out]
   __shared__ float rinv_s[64];
@@ -298,15 +349,57 @@ __global__ void __launch_bounds__(256) k_norm_linear(const float* __restrict__ Z
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int node = node0 + 4 * ty + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = (node < n && oc + j < dout) ? acc[i][j] + bias[oc + j] : 0.f;
     if (node >= n) continue;
     if (oc + 3 < dout) {
-      *reinterpret_cast<float4*>(Mb + (size_t)node * dout + oc) =
-          make_float4(acc[i][0] + bias[oc], acc[i][1] + bias[oc + 1], acc[i][2] + bias[oc + 2], acc[i][3] + bias[oc + 3]);
+      *reinterpret_cast<float4*>(Mb + (size_t)node * dout + oc) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (oc + j < dout) Mb[(size_t)node * dout + oc + j] = acc[i][j] + bias[oc + j];
+        if (oc + j < dout) Mb[(size_t)node * dout + oc + j] = acc[i][j];
     }
+  }
+  // ---- fused producer outputs (acc now holds M, zero outside [0,n) x [0,dout)) ----
+  if (po.Thi != nullptr) {
+    const int nodeq = node0 + 4 * ty;   // 4 consecutive nodes -> one float4 along the node axis of V^T
+    if (nodeq < po.npad) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (oc + j >= dout) continue;
+        const float h0 = tf32_round(acc[0][j]), h1 = tf32_round(acc[1][j]), h2 = tf32_round(acc[2][j]), h3 = tf32_round(acc[3][j]);
+        const size_t o = ((size_t)b * dout + oc + j) * po.npad + nodeq;
+        *reinterpret_cast<float4*>(po.Thi + o) = make_float4(h0, h1, h2, h3);
+        *reinterpret_cast<float4*>(po.Tlo + o) = make_float4(acc[0][j] - h0, acc[1][j] - h1, acc[2][j] - h2, acc[3][j] - h3);
+      }
+    }
+  }
+  if (po.cb != nullptr) {
+    // partial column sums over this block's 64 nodes: reduce the 16 thread rows through smem (zt / wt are free now)
+    float (*r0)[68] = zt;   // [ty][col]
+    float (*r1)[68] = wt;
+    const float* vb = po.vec ? po.vec + (size_t)b * po.vec_stride : nullptr;
+    float v4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vb) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const int node = node0 + 4 * ty + i; v4[i] = node < n ? vb[node] : 0.f; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      r0[ty][4 * tx + j] = acc[0][j] + acc[1][j] + acc[2][j] + acc[3][j];
+      r1[ty][4 * tx + j] = v4[0] * acc[0][j] + v4[1] * acc[1][j] + v4[2] * acc[2][j] + v4[3] * acc[3][j];
+    }
+    __syncthreads();
+    const int chunks = gridDim.x;
+    if (tid < 64 && o0 + tid < dout) {
+      float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { t0 += r0[k][tid]; t1 += r1[k][tid]; }
+      float* part = po.partial + (((size_t)b * chunks + blockIdx.x) * 2) * dout;
+      part[o0 + tid] = t0;
+      part[dout + o0 + tid] = t1;
+    }
+    finalize_colsums(po, b, chunks, dout, o0, 64, po.tickets + (size_t)b * gridDim.y + blockIdx.y, &is_last);
   }
 }
 
@@ -316,6 +409,7 @@ __global__ void __launch_bounds__(256) k_norm_linear(const float* __restrict__ Z
 // the last block to finish (per column block) adds them in a fixed order; the ticket counter resets itself.
 // =====================================================================================
 constexpr int CS_ROWS = 256;
+
 __global__ void __launch_bounds__(256) k_colsums(const float* __restrict__ V, int n, int d,
                                                  const float* __restrict__ vec, size_t vec_stride,
                                                  float* __restrict__ cb, float* __restrict__ partial,
@@ -692,7 +786,8 @@ __global__ void __launch_bounds__(256) k_linear_bwd(const float* __restrict__ Mb
                                                     const float* __restrict__ Z, const float* __restrict__ nw,
                                                     int n, int din, int dout, int relu_mask,
                                                     float* __restrict__ Zbar, float* __restrict__ g_nw,
-                                                    float* __restrict__ g_nb) {
+                                                    float* __restrict__ g_nb, ProducerOut po) {
+  __shared__ bool is_last;
   __shared__ __align__(16) float mt[32][36];        // [k (dout chunk)][node]
   __shared__ __align__(16) float wsm[32][PEG_MAX_H]; // [k][c]
   __shared__ float gsw[PEG_MAX_H], gsb[PEG_MAX_H];
@@ -786,8 +881,15 @@ __global__ void __launch_bounds__(256) k_linear_bwd(const float* __restrict__ Mb
             gb[r][j] += acc[r][i][j];
           }
           *reinterpret_cast<float4*>(Zbar + ((size_t)b * n + node) * din + c) = make_float4(zb[0], zb[1], zb[2], zb[3]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[r][i][j] = zb[j];   // keep Zbar for the fused producer outputs below
         }
       }
+    } else {
+#pragma unroll
+      for (int r = 0; r < REPS; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[r][i][j] = 0.f;
     }
   }
 #pragma unroll
@@ -802,6 +904,56 @@ __global__ void __launch_bounds__(256) k_linear_bwd(const float* __restrict__ Mb
   for (int c = tid; c < din; c += 256) {
     atomicAdd(g_nw + c, gsw[c]);
     atomicAdd(g_nb + c, gsb[c]);
+  }
+  // ---- fused producer outputs: Zbar is the operand V of the next (lower) layer's adjoint contraction ----
+  if (po.Thi != nullptr) {
+    const int nodeq = node0 + 4 * ty;
+    if (nodeq < po.npad) {
+#pragma unroll
+      for (int r = 0; r < REPS; ++r) {
+        const int c = 4 * tx + 128 * r;
+        if (c >= din) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float h0 = tf32_round(acc[r][0][j]), h1 = tf32_round(acc[r][1][j]), h2 = tf32_round(acc[r][2][j]), h3 = tf32_round(acc[r][3][j]);
+          const size_t o = ((size_t)b * din + c + j) * po.npad + nodeq;
+          *reinterpret_cast<float4*>(po.Thi + o) = make_float4(h0, h1, h2, h3);
+          *reinterpret_cast<float4*>(po.Tlo + o) = make_float4(acc[r][0][j] - h0, acc[r][1][j] - h1, acc[r][2][j] - h2, acc[r][3][j] - h3);
+        }
+      }
+    }
+  }
+  if (po.cb != nullptr) {
+    __syncthreads();   // gsw / gsb have been flushed: reuse them as the column accumulators of this block
+    for (int c = tid; c < din; c += 256) { gsw[c] = 0.f; gsb[c] = 0.f; }
+    __syncthreads();
+    const float* vb = po.vec ? po.vec + (size_t)b * po.vec_stride : nullptr;
+    float v4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vb) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const int node = node0 + 4 * ty + i; v4[i] = node < n ? vb[node] : 0.f; }
+    }
+    // deterministic order: warp ty adds its 4-node partial in turn
+    for (int turn = 0; turn < 8; ++turn) {
+      if (ty == turn) {
+#pragma unroll
+        for (int r = 0; r < REPS; ++r) {
+          const int c = 4 * tx + 128 * r;
+          if (c < din) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              gsw[c + j] += acc[r][0][j] + acc[r][1][j] + acc[r][2][j] + acc[r][3][j];
+              gsb[c + j] += v4[0] * acc[r][0][j] + v4[1] * acc[r][1][j] + v4[2] * acc[r][2][j] + v4[3] * acc[r][3][j];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    const int chunks = gridDim.x;
+    float* part = po.partial + (((size_t)b * chunks + blockIdx.x) * 2) * din;
+    for (int c = tid; c < din; c += 256) { part[c] = gsw[c]; part[din + c] = gsb[c]; }
+    finalize_colsums(po, b, chunks, din, 0, din, po.tickets + b, &is_last);
   }
 }
 

@@ -536,7 +536,7 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   if (!w.Vt_hi || !w.Vt_lo) return PEG_ERR_WORKSPACE;
   EncodeTiledFn enc = get_encode();
   if (!enc) return PEG_ERR_UNSUPPORTED;
-  {
+  if (!a.vt_ready) {
     dim3 grid(npad / 32, (d + 31) / 32, dm.B), block(32, 8);
     k_split_transpose<<<grid, block, 0, st>>>(a.V, n, d, npad, w.Vt_hi, w.Vt_lo);
     if (cudaPeekAtLastError() != cudaSuccess) return PEG_ERR_CUDA;

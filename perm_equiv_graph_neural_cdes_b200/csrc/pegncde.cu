@@ -137,7 +137,7 @@ static void carve_feval(Bump& bp, const PegDims& d, const Model& m, bool vjp, Fe
   w.svec = bp.take<float>(B * svec_stride(d.n, d.L, d.e));
   w.colM = bp.take<float>(B * 2 * dm);
   w.colG = bp.take<float>(B * 2 * dm);
-  w.colPart = bp.take<float>(B * ((n + CS_ROWS - 1) / CS_ROWS) * 2 * dm);
+  w.colPart = bp.take<float>(B * ((n + 31) / 32) * 2 * dm);   // chunks: 256 rows (k_colsums), 64 (norm_linear), 32 (linear_bwd)
   w.tickets_count = B * ((dm + 31) / 32);
   w.tickets = bp.take<unsigned int>(w.tickets_count);
   w.M = bp.take<float>(B * n * dm);
@@ -185,11 +185,28 @@ static int stage_prep(Ctx& c, float t) {
   return PEG_OK;
 }
 
-static int norm_linear(Ctx& c, int l, const float* Zin, float* M, float* Nout) {
+// producer-side fused outputs (V^T hi/lo for the tensor-core contraction, deterministic column sums)
+static ProducerOut producer_out(Ctx& c, int dcols, bool want_vt, float* cb, bool with_vec, size_t vec_off) {
+  ProducerOut po;
+  memset(&po, 0, sizeof(po));
+  if (want_vt && c.use_tc && tc_supported(c.d, dcols)) {
+    po.Thi = c.w.tc.Vt_hi;
+    po.Tlo = c.w.tc.Vt_lo;
+    po.npad = c.w.tc.npad;
+  }
+  po.cb = cb;
+  po.partial = c.w.colPart;
+  po.tickets = c.w.tickets;
+  po.vec = with_vec ? c.w.svec + vec_off : nullptr;
+  po.vec_stride = c.sv_stride;
+  return po;
+}
+
+static int norm_linear(Ctx& c, int l, const float* Zin, float* M, float* Nout, const ProducerOut& po) {
   const LayerDesc& ld = c.m.layer[l];
   dim3 grid((c.d.n + 63) / 64, (ld.dout + 63) / 64, c.d.B);
   k_norm_linear<<<grid, 256, 0, c.st>>>(Zin, c.d.n, ld.din, ld.dout, c.params + ld.w_off, c.params + ld.b_off,
-                                           c.params + ld.nw_off, c.params + ld.nb_off, M, Nout);
+                                        c.params + ld.nw_off, c.params + ld.nb_off, M, Nout, po);
   PEG_LAUNCH_CHECK();
   return PEG_OK;
 }
@@ -203,7 +220,7 @@ static int colsums(Ctx& c, const float* V, int dcols, size_t vec_off, bool with_
 }
 
 static int contract(Ctx& c, int l, bool bwd, const float* V, const float* Mref, const float* colbuf, float* out,
-                    bool relu, bool scale_tg, float* g_fus) {
+                    bool relu, bool scale_tg, float* g_fus, bool vt_ready) {
   const LayerDesc& ld = c.m.layer[l];
   ContractArgs a;
   a.planes = c.ctl.adj_coef;
@@ -223,6 +240,7 @@ static int contract(Ctx& c, int l, bool bwd, const float* V, const float* Mref, 
   a.n = c.d.n; a.ldn = c.d.ldn; a.d = ld.dout; a.layer = l;
   a.relu = relu ? 1 : 0;
   a.scale_tg = scale_tg ? 1 : 0;
+  a.vt_ready = vt_ready ? 1 : 0;
   // algorithmic work of one launch: the four coefficient planes are traversed once (16 n^2 B per graph),
   // V is read and OUT written once; 2 (fwd) or 4 (bwd) n x n x d products.
   const double nn = (double)c.d.n * c.d.n, nd = (double)c.d.n * ld.dout;
@@ -233,7 +251,7 @@ static int contract(Ctx& c, int l, bool bwd, const float* V, const float* Mref, 
   int rc = PEG_OK;
   if (c.use_tc && tc_supported(c.d, ld.dout)) {
     rc = tc_contract(c.st, c.d, c.w.tc, a, bwd);
-    if (rc == PEG_OK) g_launches.fetch_add(tc_launches_per_contract(bwd));
+    if (rc == PEG_OK) g_launches.fetch_add(vt_ready ? 1 : 2);
   } else {
     dim3 grid((c.d.n + CT_TI - 1) / CT_TI, (ld.dout + CT_TC - 1) / CT_TC, c.d.B);
     if (!bwd)
@@ -256,15 +274,15 @@ static int feval_fwd(Ctx& c, float t, const float* yin, float* dy, float* const*
   for (int l = 0; l < nlayers; ++l) {
     const LayerDesc& ld = c.m.layer[l];
     const bool last = (l == d.L - 1);
-    PEG_TRY(norm_linear(c, l, Zin, c.w.M, nullptr));
-    PEG_TRY(colsums(c, c.w.M, ld.dout, svec_c(d.n, l), true, c.w.colM));
+    const ProducerOut po = producer_out(c, ld.dout, true, c.w.colM, true, svec_c(d.n, l));
+    PEG_TRY(norm_linear(c, l, Zin, c.w.M, nullptr, po));
     float* out;
     if (!last) {
       out = (save && save[l + 1]) ? save[l + 1] : ((l & 1) ? c.w.Zb : c.w.Za);
     } else {
       out = d.e > 0 ? c.w.OL : dy;
     }
-    PEG_TRY(contract(c, l, false, c.w.M, nullptr, c.w.colM, out, !last, last, nullptr));
+    PEG_TRY(contract(c, l, false, c.w.M, nullptr, c.w.colM, out, !last, last, nullptr, po.Thi != nullptr));
     Zin = out;
   }
   if (d.e > 0 && nlayers == d.L) {
@@ -288,9 +306,9 @@ static int feval_vjp(Ctx& c, float t, float* const* zin, const float* kbar, floa
     if (d.e == 0) return PEG_ERR_BAD_DIMS;
     // recompute the (tg-scaled) last-layer output, then contract it with kbar
     const int l = d.L - 1;
-    PEG_TRY(norm_linear(c, l, zin[l], c.w.M, nullptr));
-    PEG_TRY(colsums(c, c.w.M, dL, svec_c(d.n, l), true, c.w.colM));
-    PEG_TRY(contract(c, l, false, c.w.M, nullptr, c.w.colM, c.w.OL, false, true, nullptr));
+    const ProducerOut po = producer_out(c, dL, true, c.w.colM, true, svec_c(d.n, l));
+    PEG_TRY(norm_linear(c, l, zin[l], c.w.M, nullptr, po));
+    PEG_TRY(contract(c, l, false, c.w.M, nullptr, c.w.colM, c.w.OL, false, true, nullptr, po.Thi != nullptr));
     const size_t cnt = (size_t)d.B * d.n * 2 * d.e;
     k_wrapper_xbar<<<(unsigned)((cnt + 255) / 256), 256, 0, c.st>>>(kbar, c.w.OL, d.n, d.h, 2 * d.e, d.B, g_xd);
     PEG_LAUNCH_CHECK();
@@ -302,14 +320,15 @@ static int feval_vjp(Ctx& c, float t, float* const* zin, const float* kbar, floa
                                                                    c.w.Obar);
     PEG_LAUNCH_CHECK();
   }
+  bool obar_ready = false;   // column sums / V^T of Obar already produced by the previous k_linear_bwd
+  bool obar_vt = false;
   for (int l = d.L - 1; l >= 0; --l) {
     const LayerDesc& ld = c.m.layer[l];
     float* g_fus = g_params + ld.fus_off;
-    // recompute M_l (and the normalised input N_l) from the saved layer input
-    PEG_TRY(norm_linear(c, l, zin[l], c.w.M, c.w.N));
-    PEG_TRY(colsums(c, c.w.M, ld.dout, 0, false, c.w.colM));
-    PEG_TRY(colsums(c, c.w.Obar, ld.dout, svec_r(d.n, l), true, c.w.colG));
-    PEG_TRY(contract(c, l, true, c.w.Obar, c.w.M, c.w.colG, c.w.Mbar, false, false, g_fus));
+    // recompute M_l (and the normalised input N_l) from the saved layer input; 1^T M comes out of the same kernel
+    PEG_TRY(norm_linear(c, l, zin[l], c.w.M, c.w.N, producer_out(c, ld.dout, false, c.w.colM, false, 0)));
+    if (!obar_ready) PEG_TRY(colsums(c, c.w.Obar, ld.dout, svec_r(d.n, l), true, c.w.colG));
+    PEG_TRY(contract(c, l, true, c.w.Obar, c.w.M, c.w.colG, c.w.Mbar, false, false, g_fus, obar_vt));
     {
       FusGradArgs a;
       a.G = c.w.Obar; a.M = c.w.M; a.cbM = c.w.colM; a.cbG = c.w.colG;
@@ -333,10 +352,16 @@ static int feval_vjp(Ctx& c, float t, float* const* zin, const float* kbar, floa
     {
       dim3 grid((d.n + 31) / 32, d.B);
       float* zb = (l == 0) ? ybar : c.w.Obar;
+      // for l > 0 the output is the cotangent Obar of layer l-1: emit its column sums (vec = r_{l-1}) and V^T here
+      ProducerOut po;
+      memset(&po, 0, sizeof(po));
+      if (l > 0) po = producer_out(c, ld.din, true, c.w.colG, true, svec_r(d.n, l - 1));
       k_linear_bwd<<<grid, 256, 0, c.st>>>(c.w.Mbar, c.params + ld.w_off, zin[l], c.params + ld.nw_off, d.n,
                                               ld.din, ld.dout, l > 0 ? 1 : 0, zb, g_params + ld.nw_off,
-                                              g_params + ld.nb_off);
+                                              g_params + ld.nb_off, po);
       PEG_LAUNCH_CHECK();
+      obar_ready = l > 0;
+      obar_vt = po.Thi != nullptr;
     }
   }
   return PEG_OK;
