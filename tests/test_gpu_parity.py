@@ -187,8 +187,9 @@ def test_tsit5_step_and_error_estimate(cuda):
         ks.append(f(t + R.TSIT5_C[i] * dt, p64.y0 + dt * acc))
     y1_ref = p64.y0 + dt * sum(ks[j] * R.TSIT5_B[j] for j in range(6))
     err_ref = dt * sum(ks[j] * R.TSIT5_BERR[j] for j in range(7))
-    assert rel_err(y1, y1_ref) < 1e-5
-    assert rel_err(k7, ks[6]) < 1e-5
+    assert rel_err(y1, y1_ref) < 2e-5
+    assert rel_err(k7, ks[6]) < 5e-5   # k7 = f(t+dt, y1) inherits (and amplifies) the rounding of y1
+    assert rel_err(k7, _vf_oracle(p64, t + dt, y1.cpu().double())) < 2e-6   # the evaluation itself is exact
     assert float((yerr.cpu().double() - err_ref).abs().max()) < 1e-5 * float(y1_ref.abs().max())
     # FSAL: feeding k7 back as k1 of the next step reproduces a fresh evaluation
     y2a, _, _ = P.tsit5_step(P.ODETerm(term), t + dt, dt, y1, args, k1=k7)
