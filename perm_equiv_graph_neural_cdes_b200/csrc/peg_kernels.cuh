@@ -281,76 +281,109 @@ __global__ void __launch_bounds__(256) k_rk_combine(CombArgs a) {
 
 // =====================================================================================
 // RMSNorm -> Linear  (layers.py:45-46): M = (w_n * z * rsqrt(mean z^2 + eps) + b_n) W^T + b
-// grid (ceil(n/64), ceil(dout/64), B), block 256; 64 nodes x 64 outputs per block, 4 x 4 per thread
+// The norm is linear in z up to the per-node scale, so it moves to the epilogue:
+//     M[node][o] = rinv[node] * sum_k z[node][k] (w_n[k] W[o][k])  +  (sum_k b_n[k] W[o][k] + b[o])
+// -> one pass over Z (sum z^2 is accumulated while the K chunks stream through), a plain 128 x 64 x d_in GEMM
+// with 8 x 4 outputs per thread, and a fused epilogue that also emits V^T hi/lo and the column sums.
+// grid (ceil(n/128), ceil(dout/64), B), block 256
 // =====================================================================================
+constexpr int NL_BM = 128, NL_BN = 64, NL_BK = 32;
 __global__ void __launch_bounds__(256) k_norm_linear(const float* __restrict__ Z, int n, int din, int dout,
                                                      const float* __restrict__ W, const float* __restrict__ bias,
                                                      const float* __restrict__ nw, const float* __restrict__ nb,
                                                      float* __restrict__ M, float* __restrict__ Nout, ProducerOut po) {
   __shared__ bool is_last;
-  __shared__ __align__(16) float zt[32][68];   // [k][node]  normalised input chunk
-  __shared__ __align__(16) float wt[32][68];   // [k][out]
-  __shared__ float rinv_s[64];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.z, node0 = blockIdx.x * 64, o0 = blockIdx.y * 64;
+  __shared__ __align__(16) float zt[NL_BK][NL_BM + 4];   // [k][node]  raw input chunk
+  __shared__ __align__(16) float wt[NL_BK][NL_BN + 4];   // [k][out]   W * norm weight
+  __shared__ float rinv_s[NL_BM];
+  __shared__ float cvec_s[NL_BN];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z, node0 = blockIdx.x * NL_BM, o0 = blockIdx.y * NL_BN;
   const float* Zb = Z + (size_t)b * n * din;
-  // per-node rsqrt(mean z^2 + eps): warp w handles nodes 8w .. 8w+7
-  for (int rr = 0; rr < 8; ++rr) {
-    const int r = warp * 8 + rr, node = node0 + r;
-    float ss = 0.f;
-    if (node < n)
-      for (int c = lane; c < din; c += 32) { const float z = Zb[(size_t)node * din + c]; ss = fmaf(z, z, ss); }
-    ss = warp_sum(ss);
-    if (lane == 0) rinv_s[r] = rsqrtf(ss / (float)din + 1e-5f);
-  }
-  __syncthreads();
-  const int ty = tid >> 4, tx = tid & 15;
-  float acc[4][4];
+  const int ty = tid >> 4, tx = tid & 15;       // compute mapping: rows 8ty..8ty+7, cols 4tx..4tx+3
+  const int zr = tid >> 1, zk = (tid & 1) * 16; // Z loader: row zr, 16 consecutive k
+  const int wo = tid >> 2, wk = (tid & 3) * 8;  // W loader: out wo, 8 consecutive k
+  float acc[8][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  float* Nb = Nout ? Nout + (size_t)b * n * din : nullptr;
-  for (int k0 = 0; k0 < din; k0 += 32) {
-    // 64 rows x 32 k: thread -> row tid/4, 8 consecutive k
+  float sumsq = 0.f, cpart = 0.f;
+  const bool zrow_ok = node0 + zr < n, wrow_ok = o0 + wo < dout;
+  for (int k0 = 0; k0 < din; k0 += NL_BK) {
     {
-      const int r = tid >> 2, kq = (tid & 3) * 8;
-      const int node = node0 + r, o = o0 + r;
+      float4 z4[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int k = k0 + kq + u;
-        float z = 0.f, w = 0.f;
-        if (k < din) {
-          if (node < n) {
-            z = Zb[(size_t)node * din + k] * rinv_s[r] * nw[k] + nb[k];
-            if (Nb != nullptr && blockIdx.y == 0) Nb[(size_t)node * din + k] = z;
-          }
-          if (o < dout) w = W[(size_t)o * din + k];
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + zk + 4 * u;
+        z4[u] = (zrow_ok && k < din) ? *reinterpret_cast<const float4*>(Zb + (size_t)(node0 + zr) * din + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float4 w4[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k = k0 + wk + 4 * u;
+        w4[u] = (wrow_ok && k < din) ? *reinterpret_cast<const float4*>(W + (size_t)(o0 + wo) * din + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float zz[4] = {z4[u].x, z4[u].y, z4[u].z, z4[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          sumsq = fmaf(zz[e], zz[e], sumsq);
+          zt[zk + 4 * u + e][zr] = zz[e];
         }
-        zt[kq + u][r] = z;
-        wt[kq + u][r] = w;
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float ww[4] = {w4[u].x, w4[u].y, w4[u].z, w4[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = k0 + wk + 4 * u + e;
+          const float sw = k < din ? nw[k] : 0.f, sb = k < din ? nb[k] : 0.f;
+          cpart = fmaf(sb, ww[e], cpart);
+          wt[wk + 4 * u + e][wo] = ww[e] * sw;
+        }
       }
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&zt[k][4 * ty]);
+    for (int k = 0; k < NL_BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&zt[k][8 * ty]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&zt[k][8 * ty + 4]);
       const float4 b4 = *reinterpret_cast<const float4*>(&wt[k][4 * tx]);
-      const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+      const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
     }
     __syncthreads();
   }
+  // per-node rsqrt(mean z^2 + eps) (2 loader threads per row) and the constant vector (4 loader threads per out)
+  sumsq += __shfl_xor_sync(0xffffffffu, sumsq, 1);
+  cpart += __shfl_xor_sync(0xffffffffu, cpart, 1);
+  cpart += __shfl_xor_sync(0xffffffffu, cpart, 2);
+  if ((tid & 1) == 0) rinv_s[zr] = rsqrtf(sumsq / (float)din + 1e-5f);
+  if ((tid & 3) == 0) cvec_s[wo] = cpart + (wrow_ok ? bias[o0 + wo] : 0.f);
+  __syncthreads();
+  if (Nout != nullptr && blockIdx.y == 0 && zrow_ok) {   // normalised input (needed by the weight gradient)
+    float* Nb = Nout + ((size_t)b * n + node0 + zr) * din;
+    const float* Zr = Zb + (size_t)(node0 + zr) * din;
+    const float ri = rinv_s[zr];
+    for (int k = (tid & 1) * 4; k < din; k += 8) {
+      const float4 z4 = *reinterpret_cast<const float4*>(Zr + k);
+      const float4 s4 = *reinterpret_cast<const float4*>(nw + k), t4 = *reinterpret_cast<const float4*>(nb + k);
+      *reinterpret_cast<float4*>(Nb + k) = make_float4(z4.x * ri * s4.x + t4.x, z4.y * ri * s4.y + t4.y, z4.z * ri * s4.z + t4.z, z4.w * ri * s4.w + t4.w);
+    }
+  }
   float* Mb = M + (size_t)b * n * dout;
   const int oc = o0 + 4 * tx;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int node = node0 + 4 * ty + i;
+  for (int i = 0; i < 8; ++i) {
+    const int node = node0 + 8 * ty + i;
+    const float ri = rinv_s[8 * ty + i];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = (node < n && oc + j < dout) ? acc[i][j] + bias[oc + j] : 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = (node < n && oc + j < dout) ? fmaf(ri, acc[i][j], cvec_s[4 * tx + j]) : 0.f;
     if (node >= n) continue;
     if (oc + 3 < dout) {
       *reinterpret_cast<float4*>(Mb + (size_t)node * dout + oc) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
@@ -362,44 +395,48 @@ __global__ void __launch_bounds__(256) k_norm_linear(const float* __restrict__ Z
   }
   // ---- fused producer outputs (acc now holds M, zero outside [0,n) x [0,dout)) ----
   if (po.Thi != nullptr) {
-    const int nodeq = node0 + 4 * ty;   // 4 consecutive nodes -> one float4 along the node axis of V^T
-    if (nodeq < po.npad) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (oc + j >= dout) continue;
-        const float h0 = tf32_round(acc[0][j]), h1 = tf32_round(acc[1][j]), h2 = tf32_round(acc[2][j]), h3 = tf32_round(acc[3][j]);
-        const size_t o = ((size_t)b * dout + oc + j) * po.npad + nodeq;
-        *reinterpret_cast<float4*>(po.Thi + o) = make_float4(h0, h1, h2, h3);
-        *reinterpret_cast<float4*>(po.Tlo + o) = make_float4(acc[0][j] - h0, acc[1][j] - h1, acc[2][j] - h2, acc[3][j] - h3);
+    for (int hh = 0; hh < 2; ++hh) {
+      const int nodeq = node0 + 8 * ty + 4 * hh;   // 4 consecutive nodes -> one float4 along the node axis of V^T
+      if (nodeq < po.npad) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (oc + j >= dout) continue;
+          const float v0 = acc[4 * hh][j], v1 = acc[4 * hh + 1][j], v2 = acc[4 * hh + 2][j], v3 = acc[4 * hh + 3][j];
+          const float h0 = tf32_round(v0), h1 = tf32_round(v1), h2 = tf32_round(v2), h3 = tf32_round(v3);
+          const size_t o = ((size_t)b * dout + oc + j) * po.npad + nodeq;
+          *reinterpret_cast<float4*>(po.Thi + o) = make_float4(h0, h1, h2, h3);
+          *reinterpret_cast<float4*>(po.Tlo + o) = make_float4(v0 - h0, v1 - h1, v2 - h2, v3 - h3);
+        }
       }
     }
   }
   if (po.cb != nullptr) {
-    // partial column sums over this block's 64 nodes: reduce the 16 thread rows through smem (zt / wt are free now)
-    float (*r0)[68] = zt;   // [ty][col]
-    float (*r1)[68] = wt;
+    // partial column sums over this block's 128 nodes: reduce the 16 thread rows through smem (zt is free now)
+    float (*r0)[NL_BM + 4] = zt;                                  // rows 0..15  : plain sums   [ty][col]
+    float (*r1)[NL_BM + 4] = reinterpret_cast<float (*)[NL_BM + 4]>(&zt[16][0]);   // rows 16..31 : weighted sums
     const float* vb = po.vec ? po.vec + (size_t)b * po.vec_stride : nullptr;
-    float v4[4] = {0.f, 0.f, 0.f, 0.f};
-    if (vb) {
+    float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { const int node = node0 + 4 * ty + i; v4[i] = node < n ? vb[node] : 0.f; }
+    for (int i = 0; i < 8; ++i) {
+      const int node = node0 + 8 * ty + i;
+      const float vv = (vb && node < n) ? vb[node] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { t0[j] += acc[i][j]; t1[j] = fmaf(vv, acc[i][j], t1[j]); }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      r0[ty][4 * tx + j] = acc[0][j] + acc[1][j] + acc[2][j] + acc[3][j];
-      r1[ty][4 * tx + j] = v4[0] * acc[0][j] + v4[1] * acc[1][j] + v4[2] * acc[2][j] + v4[3] * acc[3][j];
-    }
+    for (int j = 0; j < 4; ++j) { r0[ty][4 * tx + j] = t0[j]; r1[ty][4 * tx + j] = t1[j]; }
     __syncthreads();
     const int chunks = gridDim.x;
-    if (tid < 64 && o0 + tid < dout) {
-      float t0 = 0.f, t1 = 0.f;
+    if (tid < NL_BN && o0 + tid < dout) {
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) { t0 += r0[k][tid]; t1 += r1[k][tid]; }
+      for (int k = 0; k < 16; ++k) { s0 += r0[k][tid]; s1 += r1[k][tid]; }
       float* part = po.partial + (((size_t)b * chunks + blockIdx.x) * 2) * dout;
-      part[o0 + tid] = t0;
-      part[dout + o0 + tid] = t1;
+      part[o0 + tid] = s0;
+      part[dout + o0 + tid] = s1;
     }
-    finalize_colsums(po, b, chunks, dout, o0, 64, po.tickets + (size_t)b * gridDim.y + blockIdx.y, &is_last);
+    finalize_colsums(po, b, chunks, dout, o0, NL_BN, po.tickets + (size_t)b * gridDim.y + blockIdx.y, &is_last);
   }
 }
 

@@ -204,7 +204,7 @@ static ProducerOut producer_out(Ctx& c, int dcols, bool want_vt, float* cb, bool
 
 static int norm_linear(Ctx& c, int l, const float* Zin, float* M, float* Nout, const ProducerOut& po) {
   const LayerDesc& ld = c.m.layer[l];
-  dim3 grid((c.d.n + 63) / 64, (ld.dout + 63) / 64, c.d.B);
+  dim3 grid((c.d.n + NL_BM - 1) / NL_BM, (ld.dout + NL_BN - 1) / NL_BN, c.d.B);
   k_norm_linear<<<grid, 256, 0, c.st>>>(Zin, c.d.n, ld.din, ld.dout, c.params + ld.w_off, c.params + ld.b_off,
                                         c.params + ld.nw_off, c.params + ld.nb_off, M, Nout, po);
   PEG_LAUNCH_CHECK();
