@@ -10,10 +10,11 @@
 // tile touch it at about the same time, so HBM sees every plane byte once per pass and L2 serves
 // the second reader.
 //
-// Warp roles (320 threads): warps 0-7 converters (LDG.128 planes -> FFMA combine -> 3xTF32 split
-// -> swizzled STS of the K-major A operand tiles) and, at the end, the epilogue (tcgen05.ld);
-// warp 8 = TMA producer of the B operand (V^T hi/lo, SWIZZLE_128B); warp 9 = TMEM allocator +
-// the single thread that issues tcgen05.mma.
+// Warp roles (576 threads): warps 0-15 converters (LDG.128 planes -> FFMA combine -> 3xTF32 split
+// -> swizzled STS of the K-major A operand tiles) in two groups of 8 that work on alternate items (group 0 the
+// direct items, group 1 the transposed ones), so one group's conversion overlaps the other group's loads;
+// warps 0-7 also run the epilogue (tcgen05.ld); warp 16 = TMA producer of the B operand (V^T hi/lo,
+// SWIZZLE_128B); warp 17 = TMEM allocator + the single thread that issues tcgen05.mma.
 //
 // fp32 parity: 3xTF32 (hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM); PEG_FLAG_TF32_FAST drops
 // the two correction products.
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(256) k_split_transpose(const float* __restrict
 // ------------------------------------------------------------------------------------------
 // the contraction kernel
 // ------------------------------------------------------------------------------------------
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 576;   // 2 converter groups x 8 warps + TMA warp + MMA warp
 constexpr int TC_CONV_THREADS = 256;
 constexpr int TC_BM = 128;   // output rows per CTA (UMMA M)
 constexpr int TC_BK = 32;    // K chunk (32 fp32 = 128 B = one swizzle row)
@@ -169,6 +170,7 @@ struct TcParams {
   int nkc;       // number of 32-wide K chunks = npad / 32
   int tmem_cols; // power of two >= 32
   int cluster;   // CTAs per cluster sharing the B operand by TMA multicast (1 = no cluster)
+  int experiment; // timing experiments only (PEG_TC_EXPERIMENT): 1 = B operand loaded for the first items only, 2 = no MMAs
 };
 
 template <bool BWD>
@@ -211,7 +213,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 9) {  // TMEM allocation (whole warp), address lands in smem
+  if (warp == 17) {  // TMEM allocation (whole warp), address lands in smem
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -230,8 +232,9 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   const int items = 2 * nkc;
   const float alpha = 1.f + a.fus[0], beta = 1.f + a.fus[1], gamma = a.fus[2], delta = a.fus[3];
 
-  if (warp < 8) {
+  if (warp < 16) {
     // =========================== converters ===========================
+    const int grp = warp >> 3, w8 = warp & 7;   // group 0: direct items (even j); group 1: transposed items (odd j)
     // weights of the four planes for each A-operand variant and item type
     float wdir[NA][4], wtr[NA][4];
 #pragma unroll
@@ -249,13 +252,13 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     // Tiled plane layout (peg_common.cuh): an item is four 16-KB tiles; warp w loads half (g) of tile u, every
     // warp-level LDG.128 is 512 contiguous bytes and the thread ends up with the 4x4 micro tile (rq, cq) of all
     // four planes: buf[plane*4 + m] = row 4*rq + m, columns 4*cq .. 4*cq+3 of the 32x32 tile.
-    const int cv_u = warp >> 1, cv_g = warp & 1;
+    const int cv_u = w8 >> 1, cv_g = w8 & 1;
     const int cv_cq = lane & 7, cv_rq = ((lane & 7) + 4 * cv_g + (lane >> 3)) & 7;
     const int cv_off = cv_g * 2048 + lane * 4;   // float offset of (g, plane 0, m 0, lane) inside a tile
 
-    // Two register buffers: buf0 always holds a direct item (even j), buf1 a transposed item (odd j); each is
-    // refilled for item j+2 right after item j has been converted, so ~2 items (128 KB per SM) are in flight.
-    float4 buf0[16], buf1[16];
+    // One register buffer per thread: a group issues the loads of its next item right after converting the current
+    // one; the two groups run out of phase, so ~2 items (128 KB per SM) are in flight while the other group converts.
+    float4 buf0[16];
     auto load_tile = [&](int rt, int ct, float4 (&buf)[16]) {
       if (rt < nt && ct < nt) {
         const float* base = P + ((size_t)rt * nt + ct) * 4096 + cv_off;
@@ -319,15 +322,20 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       mbar_arrive(full_a(st));
     };
 
-    load_direct(0, buf0);
-    load_transposed(1, buf1);
-    for (int j = 0; j < items; j += 2) {   // items = 2 * nkc is even: even j direct, odd j transposed
-      convert_direct(j, buf0);
-      if (j + 2 < items) load_direct(j + 2, buf0);
-      convert_transposed(j + 1, buf1);
-      if (j + 3 < items) load_transposed(j + 3, buf1);
+    if (grp == 0) {
+      load_direct(0, buf0);
+      for (int j = 0; j < items; j += 2) {   // items = 2 * nkc: even j direct, odd j transposed
+        convert_direct(j, buf0);
+        if (j + 2 < items) load_direct(j + 2, buf0);
+      }
+    } else {
+      load_transposed(1, buf0);
+      for (int j = 1; j < items; j += 2) {
+        convert_transposed(j, buf0);
+        if (j + 2 < items) load_transposed(j + 2, buf0);
+      }
     }
-  } else if (warp == 8) {
+  } else if (warp == 16) {
     // =========================== TMA producer (B operand) ===========================
     if (lane == 0) {
       const int row0 = b * d + ntile * nd;
@@ -338,6 +346,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         const int kc = type == 0 ? (4 * Ibase + s) % nkc : ((4 * Ibase - s) % nkc + nkc) % nkc;
         mbar_wait(empty(st), ph ^ 1u);   // every CTA of the cluster has finished reading this stage
         const uint32_t b_base = smem_base + st * stage_bytes + a_bytes;
+        if (p.experiment == 1 && j >= p.stages) { mbar_arrive(full_b(st)); continue; }   // timing experiment: stale B
         mbar_expect_tx(full_b(st), (uint32_t)b_bytes);
         if (C == 1) {
           tma_load_2d(b_base, &map_hi, kc * TC_BK, row0, full_b(st));
@@ -365,7 +374,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         const uint32_t a_base = smem_base + st * stage_bytes;
         const uint32_t b_base = a_base + a_bytes;
 #pragma unroll
-        for (int v = 0; v < NA; ++v) {
+        for (int v = 0; v < NA && !(p.experiment == 2 && j >= 2); ++v) {
           // fwd: one accumulator; bwd: acc index = type*2 + v  (0: A V, 1: A'V, 2: A^T V, 3: A'^T V)
           const int acc = BWD ? (type * 2 + v) : 0;
           const uint32_t tacc = tmem_base + (uint32_t)(acc * nd);
@@ -469,7 +478,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   __syncthreads();
   __syncwarp();
   if (C > 1) cluster_sync_all();   // no CTA exits while peers may still multicast into it or arrive on its barriers
-  if (warp == 9) {
+  if (warp == 17) {
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
@@ -559,6 +568,8 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   if (const char* ev = getenv("PEG_TC_CLUSTER")) { int v = atoi(ev); if (v == 1 || v == 2 || v == 4 || v == 8) cluster = v; }
   while (cluster > 1 && (nblk < cluster || (p.nd / cluster) % 8 != 0)) cluster >>= 1;
   p.cluster = cluster;
+  p.experiment = 0;
+  if (const char* ev = getenv("PEG_TC_EXPERIMENT")) p.experiment = atoi(ev);
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (3 * stages + 2) + 64;
 
   // tensor maps depend only on (buffer, rows, npad, box): a tiny per-thread cache keeps the driver call off the hot path
