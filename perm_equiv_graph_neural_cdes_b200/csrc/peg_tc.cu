@@ -4,11 +4,12 @@
 //
 // X and Y are linear combinations of the four cubic-coefficient planes (the control-path
 // interpolation is fused: A_s, A'_s are never written to memory).  Per CTA: one 128-row output
-// block x ND columns, accumulators in TMEM.  Work items alternate between a "direct" chunk
-// (rows of block I, 32 columns kc) and a "transposed" chunk (32 rows kc, columns of block I);
-// the diagonal schedule kc_d = 4I+s, kc_t = 4I-s makes the two CTAs that need the same plane
-// tile touch it at about the same time, so HBM sees every plane byte once per pass and L2 serves
-// the second reader.
+// block x ND columns, accumulators in TMEM.  Work items come in pairs that share one K chunk kc:
+// a "direct" item (rows of block I, 32 columns kc) and a "transposed" item (32 rows kc, columns of
+// block I) -- both multiply V[kc], so ONE B-operand tile serves the pair.  The chunk order is the
+// round-robin schedule J(S) = (S - I) mod nb over the 128-column blocks: CTA I works on blocks
+// (I,J) and (J,I) exactly when CTA J does, so HBM sees every plane byte once per pass and L2
+// serves the second reader.
 //
 // Warp roles (576 threads): warps 0-15 converters (LDG.128 planes -> FFMA combine -> 3xTF32 split
 // -> swizzled STS of the K-major A operand tiles) in two groups of 8 that work on alternate items (group 0 the
@@ -19,6 +20,8 @@
 // fp32 parity: 3xTF32 (hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM); PEG_FLAG_TF32_FAST drops
 // the two correction products.
 #include <cuda.h>
+#include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -166,11 +169,12 @@ struct TcParams {
   ContractArgs a;
   int nd;        // columns per CTA (UMMA N)
   int nsplit;    // 3 = 3xTF32, 1 = single pass
-  int stages;
+  int stages_a;  // ring depth of the A-operand tiles (one slot per item; even: the two converter groups alternate)
+  int stages_b;  // ring depth of the B-operand tiles (one slot per PAIR of items)
   int nkc;       // number of 32-wide K chunks = npad / 32
   int tmem_cols; // power of two >= 32
   int cluster;   // CTAs per cluster sharing the B operand by TMA multicast (1 = no cluster)
-  int experiment; // timing experiments only (PEG_TC_EXPERIMENT): 1 = B operand loaded for the first items only, 2 = no MMAs
+  int experiment; // timing experiments only (PEG_TC_EXPERIMENT): 1 = B operand loaded for the first pairs only, 2 = no MMAs
 };
 
 template <bool BWD>
@@ -195,20 +199,25 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   const int a_bytes = NA * (split ? 2 : 1) * TC_ATILE;          // [variant][hi,lo]
   const int b_tile = nd * TC_BK * 4;
   const int b_bytes = (split ? 2 : 1) * b_tile;                 // [hi,lo]
-  const int stage_bytes = a_bytes + b_bytes;
-  const uint32_t bar_base = smem_base + p.stages * stage_bytes;  // full_a[s], full_b[s], empty[s], accum_full, tmem slot
+  const int SA = p.stages_a, SB = p.stages_b;
+  const uint32_t b_ring = smem_base + SA * a_bytes;
+  const uint32_t bar_base = b_ring + SB * b_bytes;  // full_a[SA], empty_a[SA], full_b[SB], empty_b[SB], accum_full, tmem slot
   auto full_a = [&](int s) { return bar_base + 8u * s; };
-  auto full_b = [&](int s) { return bar_base + 8u * (p.stages + s); };
-  auto empty = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };
-  const uint32_t accum_bar = bar_base + 8u * (3 * p.stages);
+  auto empty_a = [&](int s) { return bar_base + 8u * (SA + s); };
+  auto full_b = [&](int s) { return bar_base + 8u * (2 * SA + s); };
+  auto empty_b = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * SA + 2 * SB);
   const uint32_t tmem_slot = accum_bar + 8u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
 
   if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) {
+    for (int s = 0; s < SA; ++s) {
       mbar_init(full_a(s), TC_CONV_THREADS);
+      mbar_init(empty_a(s), 1);           // A tiles are CTA-local
+    }
+    for (int s = 0; s < SB; ++s) {
       mbar_init(full_b(s), 1);
-      mbar_init(empty(s), (uint32_t)C);   // one tcgen05.commit arrival from every CTA of the cluster
+      mbar_init(empty_b(s), (uint32_t)C);   // one tcgen05.commit arrival from every CTA of the cluster
     }
     mbar_init(accum_bar, 1);
     fence_barrier_init();
@@ -229,22 +238,33 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   for (int q = 0; q < 4; ++q) { sc.wA[q] = scp->wA[q]; sc.wD[q] = scp->wD[q]; }
   sc.interval = scp->interval;
   const int nkc = p.nkc;
-  const int items = 2 * nkc;
+  const int items = 2 * nkc;   // item j = 2 * pair + type (0 direct, 1 transposed); pair p works on chunk kc_of(p)
+  // chunk order: 128-column blocks J(S) = (S - Ibase) mod nb, four 32-chunks each (the last block may hold fewer)
+  const int nb = (nkc + 3) >> 2, r_last = nkc - 4 * (nb - 1);
+  const int Imod = Ibase % nb, Sstar = (nb - 1 + Imod) % nb;
+  auto kc_of = [&](int pr) -> int {
+    int S, u;
+    if (pr < 4 * Sstar) { S = pr >> 2; u = pr & 3; }
+    else if (pr < 4 * Sstar + r_last) { S = Sstar; u = pr - 4 * Sstar; }
+    else { const int q = pr - 4 * Sstar - r_last; S = Sstar + 1 + (q >> 2); u = q & 3; }
+    int J = S - Imod;
+    if (J < 0) J += nb;
+    return 4 * J + u;
+  };
   const float alpha = 1.f + a.fus[0], beta = 1.f + a.fus[1], gamma = a.fus[2], delta = a.fus[3];
 
   if (warp < 16) {
     // =========================== converters ===========================
     const int grp = warp >> 3, w8 = warp & 7;   // group 0: direct items (even j); group 1: transposed items (odd j)
     // weights of the four planes for each A-operand variant and item type
-    float wdir[NA][4], wtr[NA][4];
+    float w[NA][4];   // this group's weights: direct items use X (fwd) / (A_s, A'_s) (bwd); transposed items use Y / the same pair
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (BWD) {
-        wdir[0][q] = sc.wA[q]; wdir[NA - 1][q] = sc.wD[q];
-        wtr[0][q] = sc.wA[q];  wtr[NA - 1][q] = sc.wD[q];
+        w[0][q] = sc.wA[q]; w[NA - 1][q] = sc.wD[q];
       } else {
-        wdir[0][q] = alpha * sc.wA[q] + beta * sc.wD[q];   // X = (1+p1_0) A + (1+p1_1) A'
-        wtr[0][q] = gamma * sc.wA[q] + delta * sc.wD[q];   // Y = p2_0 A + p2_1 A'
+        w[0][q] = grp == 0 ? alpha * sc.wA[q] + beta * sc.wD[q]     // X = (1+p1_0) A + (1+p1_1) A'
+                           : gamma * sc.wA[q] + delta * sc.wD[q];   // Y = p2_0 A + p2_1 A'
       }
     }
     const int npad = a.ldn, nt = npad >> 5;
@@ -256,10 +276,11 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     const int cv_cq = lane & 7, cv_rq = ((lane & 7) + 4 * cv_g + (lane >> 3)) & 7;
     const int cv_off = cv_g * 2048 + lane * 4;   // float offset of (g, plane 0, m 0, lane) inside a tile
 
-    // One register buffer per thread: a group issues the loads of its next item right after converting the current
-    // one; the two groups run out of phase, so ~2 items (128 KB per SM) are in flight while the other group converts.
-    float4 buf0[16];
-    auto load_tile = [&](int rt, int ct, float4 (&buf)[16]) {
+    // One register buffer per thread (16 x LDG.128 = the thread's 4x4 micro tile of all four planes): a group issues the
+    // loads of its next item right after publishing the current one; the two groups run out of phase, so ~2 items
+    // (128 KB per SM) are in flight while the other group converts.
+    float4 buf[16];
+    auto load_tile = [&](int rt, int ct) {
       if (rt < nt && ct < nt) {
         const float* base = P + ((size_t)rt * nt + ct) * 4096 + cv_off;
 #pragma unroll
@@ -271,9 +292,13 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         for (int u = 0; u < 16; ++u) buf[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    auto load_direct = [&](int j, float4 (&buf)[16]) { load_tile(4 * I + cv_u, (4 * Ibase + (j >> 1)) % nkc, buf); };
-    auto load_transposed = [&](int j, float4 (&buf)[16]) { load_tile(((4 * Ibase - (j >> 1)) % nkc + nkc) % nkc, 4 * I + cv_u, buf); };
-    // store one 16-byte chunk (4 consecutive k of row r) as tf32 hi (+ lo) into the swizzled K-major tile
+    // item j -> its plane tile: direct = rows of block I x chunk kc, transposed = chunk kc x columns of block I
+    auto load_item = [&](int j) {
+      const int kc = kc_of(j >> 1);
+      if ((j & 1) == 0) load_tile(4 * I + cv_u, kc);
+      else load_tile(kc, 4 * I + cv_u);
+    };
+    // store one 16-byte chunk (4 consecutive k of operand row r) as tf32 hi (+ lo) into the swizzled K-major tile
     auto store_chunk = [&](uint32_t hi_base, int r, int chunk, float x0, float x1, float x2, float x3) {
       const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
       const float h0 = tf32_rna(x0), h1 = tf32_rna(x1), h2 = tf32_rna(x2), h3 = tf32_rna(x3);
@@ -281,72 +306,59 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       if (split)
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + TC_ATILE + off), "f"(x0 - h0), "f"(x1 - h1), "f"(x2 - h2), "f"(x3 - h3) : "memory");
     };
-    auto convert_direct = [&](int j, float4 (&buf)[16]) {
-      const int st = j % p.stages;
-      const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
-      mbar_wait(empty(st), ph ^ 1u);   // the MMAs that read this stage's previous contents have completed
-      const uint32_t a_base = smem_base + st * stage_bytes;
+    // Conversion of one item: (1) FFMA-combine the four planes (the fused cubic interpolation + fusion weights) while the
+    // slot may still be busy, (2) wait for the A slot, (3) 3xTF32-split and store the operand tile, publish it,
+    // (4) issue the loads of the group's next item.
+    auto convert = [&](int j, bool transposed) {
+      float t[NA][16];   // t[v][4 m + e] = element (row 4 rq + m, column 4 cq + e) of the combined tile
+#pragma unroll
+      for (int v = 0; v < NA; ++v) {
+        const float w0 = w[v][0], w1 = w[v][1], w2 = w[v][2], w3 = w[v][3];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const float4 e0 = buf[0 * 4 + m], e1 = buf[1 * 4 + m], e2 = buf[2 * 4 + m], e3 = buf[3 * 4 + m];
+          t[v][4 * m + 0] = w0 * e0.x + w1 * e1.x + w2 * e2.x + w3 * e3.x;
+          t[v][4 * m + 1] = w0 * e0.y + w1 * e1.y + w2 * e2.y + w3 * e3.y;
+          t[v][4 * m + 2] = w0 * e0.z + w1 * e1.z + w2 * e2.z + w3 * e3.z;
+          t[v][4 * m + 3] = w0 * e0.w + w1 * e1.w + w2 * e2.w + w3 * e3.w;
+        }
+      }
+      const int st = j % SA;
+      const uint32_t ph = (uint32_t)(j / SA) & 1u;
+      mbar_wait(empty_a(st), ph ^ 1u);   // the MMAs that read this slot's previous contents have completed
+      const uint32_t a_base = smem_base + st * a_bytes;
 #pragma unroll
       for (int v = 0; v < NA; ++v) {
         const uint32_t hi_base = a_base + v * (split ? 2 : 1) * TC_ATILE;
-        const float w0 = wdir[v][0], w1 = wdir[v][1], w2 = wdir[v][2], w3 = wdir[v][3];
+        if (!transposed) {
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {   // operand row = tile row 4*rq + m, chunk = cq (4 consecutive k)
-          const float4 e0 = buf[0 * 4 + m], e1 = buf[1 * 4 + m], e2 = buf[2 * 4 + m], e3 = buf[3 * 4 + m];
-          store_chunk(hi_base, 32 * cv_u + 4 * cv_rq + m, cv_cq,
-                      w0 * e0.x + w1 * e1.x + w2 * e2.x + w3 * e3.x, w0 * e0.y + w1 * e1.y + w2 * e2.y + w3 * e3.y,
-                      w0 * e0.z + w1 * e1.z + w2 * e2.z + w3 * e3.z, w0 * e0.w + w1 * e1.w + w2 * e2.w + w3 * e3.w);
+          for (int m = 0; m < 4; ++m)   // operand row = tile row 4 rq + m, chunk = cq (4 consecutive k)
+            store_chunk(hi_base, 32 * cv_u + 4 * cv_rq + m, cv_cq, t[v][4 * m + 0], t[v][4 * m + 1], t[v][4 * m + 2], t[v][4 * m + 3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)   // operand row = tile column 4 cq + e, chunk = rq: the four k values are the rows m = 0..3
+            store_chunk(hi_base, 32 * cv_u + 4 * cv_cq + e, cv_rq, t[v][e], t[v][4 + e], t[v][8 + e], t[v][12 + e]);
         }
       }
       fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
       mbar_arrive(full_a(st));
-    };
-    auto convert_transposed = [&](int j, float4 (&buf)[16]) {
-      const int st = j % p.stages;
-      const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
-      mbar_wait(empty(st), ph ^ 1u);
-      const uint32_t a_base = smem_base + st * stage_bytes;
-#pragma unroll
-      for (int v = 0; v < NA; ++v) {
-        const uint32_t hi_base = a_base + v * (split ? 2 : 1) * TC_ATILE;
-        const float w0 = wtr[v][0], w1 = wtr[v][1], w2 = wtr[v][2], w3 = wtr[v][3];
-        // operand row = tile column 4*cq + e, chunk = rq: the four k values are the micro tile's rows m = 0..3
-#define PEG_T(comp, m) (w0 * buf[0 * 4 + m].comp + w1 * buf[1 * 4 + m].comp + w2 * buf[2 * 4 + m].comp + w3 * buf[3 * 4 + m].comp)
-        store_chunk(hi_base, 32 * cv_u + 4 * cv_cq + 0, cv_rq, PEG_T(x, 0), PEG_T(x, 1), PEG_T(x, 2), PEG_T(x, 3));
-        store_chunk(hi_base, 32 * cv_u + 4 * cv_cq + 1, cv_rq, PEG_T(y, 0), PEG_T(y, 1), PEG_T(y, 2), PEG_T(y, 3));
-        store_chunk(hi_base, 32 * cv_u + 4 * cv_cq + 2, cv_rq, PEG_T(z, 0), PEG_T(z, 1), PEG_T(z, 2), PEG_T(z, 3));
-        store_chunk(hi_base, 32 * cv_u + 4 * cv_cq + 3, cv_rq, PEG_T(w, 0), PEG_T(w, 1), PEG_T(w, 2), PEG_T(w, 3));
-#undef PEG_T
-      }
-      fence_proxy_async();
-      mbar_arrive(full_a(st));
+      if (j + 2 < items) load_item(j + 2);
     };
 
-    if (grp == 0) {
-      load_direct(0, buf0);
-      for (int j = 0; j < items; j += 2) {   // items = 2 * nkc: even j direct, odd j transposed
-        convert_direct(j, buf0);
-        if (j + 2 < items) load_direct(j + 2, buf0);
-      }
-    } else {
-      load_transposed(1, buf0);
-      for (int j = 1; j < items; j += 2) {
-        convert_transposed(j, buf0);
-        if (j + 2 < items) load_transposed(j + 2, buf0);
-      }
-    }
+    load_item(grp);   // group 0: direct items (even j); group 1: transposed items (odd j)
+    if (grp == 0) for (int j = 0; j < items; j += 2) convert(j, false);
+    else          for (int j = 1; j < items; j += 2) convert(j, true);
   } else if (warp == 16) {
     // =========================== TMA producer (B operand) ===========================
     if (lane == 0) {
       const int row0 = b * d + ntile * nd;
-      for (int j = 0; j < items; ++j) {
-        const int st = j % p.stages;
-        const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
-        const int s = j >> 1, type = j & 1;
-        const int kc = type == 0 ? (4 * Ibase + s) % nkc : ((4 * Ibase - s) % nkc + nkc) % nkc;
-        mbar_wait(empty(st), ph ^ 1u);   // every CTA of the cluster has finished reading this stage
-        const uint32_t b_base = smem_base + st * stage_bytes + a_bytes;
-        if (p.experiment == 1 && j >= p.stages) { mbar_arrive(full_b(st)); continue; }   // timing experiment: stale B
+      for (int pr = 0; pr < nkc; ++pr) {   // one B tile per pair of items
+        const int st = pr % SB;
+        const uint32_t ph = (uint32_t)(pr / SB) & 1u;
+        const int kc = kc_of(pr);
+        mbar_wait(empty_b(st), ph ^ 1u);   // every CTA of the cluster has finished reading this slot
+        const uint32_t b_base = b_ring + st * b_bytes;
+        if (p.experiment == 1 && pr >= SB) { mbar_arrive(full_b(st)); continue; }   // timing experiment: stale B
         mbar_expect_tx(full_b(st), (uint32_t)b_bytes);
         if (C == 1) {
           tma_load_2d(b_base, &map_hi, kc * TC_BK, row0, full_b(st));
@@ -365,14 +377,14 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nd >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       uint32_t started = 0u;  // bit acc set once the accumulator has been written (first MMA overwrites)
       for (int j = 0; j < items; ++j) {
-        const int st = j % p.stages;
-        const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
+        const int st = j % SA, pr = j >> 1, sb = pr % SB;
+        const uint32_t ph = (uint32_t)(j / SA) & 1u;
         const int type = j & 1;
+        if (type == 0) mbar_wait(full_b(sb), (uint32_t)(pr / SB) & 1u);   // the pair's B tile
         mbar_wait(full_a(st), ph);
-        mbar_wait(full_b(st), ph);
         tc_fence_after();
-        const uint32_t a_base = smem_base + st * stage_bytes;
-        const uint32_t b_base = a_base + a_bytes;
+        const uint32_t a_base = smem_base + st * a_bytes;
+        const uint32_t b_base = b_ring + sb * b_bytes;
 #pragma unroll
         for (int v = 0; v < NA && !(p.experiment == 2 && j >= 2); ++v) {
           // fwd: one accumulator; bwd: acc index = type*2 + v  (0: A V, 1: A'V, 2: A^T V, 3: A'^T V)
@@ -391,8 +403,11 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             }
           }
         }
-        if (C == 1) umma_commit(empty(st));   // frees this smem stage once the MMAs above have read it
-        else umma_commit_mcast(empty(st), cmask);   // ... in every CTA of the cluster (their producers multicast into it)
+        umma_commit(empty_a(st));   // frees this A slot once the MMAs above have read it
+        if (type == 1) {            // ... and the pair's B slot, in every CTA of the cluster (their producers multicast into it)
+          if (C == 1) umma_commit(empty_b(sb));
+          else umma_commit_mcast(empty_b(sb), cmask);
+        }
       }
       umma_commit(accum_bar);     // all accumulators final
     }
@@ -548,7 +563,7 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   if (!a.vt_ready) {
     dim3 grid(npad / 32, (d + 31) / 32, dm.B), block(32, 8);
     k_split_transpose<<<grid, block, 0, st>>>(a.V, n, d, npad, w.Vt_hi, w.Vt_lo);
-    if (cudaPeekAtLastError() != cudaSuccess) return PEG_ERR_CUDA;
+    if (cudaPeekAtLastError() != cudaSuccess) { set_last_cuda((int)cudaGetLastError()); fprintf(stderr, "pegncde: k_split_transpose launch failed\n"); return PEG_ERR_CUDA; }
   }
   TcParams p;
   p.a = a;
@@ -556,12 +571,17 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   p.nsplit = (dm.flags & PEG_FLAG_TF32_FAST) ? 1 : 3;
   p.nkc = npad / 32;
   const int na = bwd ? 2 : 1, sp = p.nsplit == 3 ? 2 : 1;
-  const int stage_bytes = na * sp * TC_ATILE + sp * p.nd * TC_BK * 4;
-  int stages = (200 * 1024) / stage_bytes;
-  stages = stages > 4 ? 4 : stages;
-  if (const char* ev = getenv("PEG_TC_STAGES")) { int v = atoi(ev); if (v >= 1 && v <= stages) stages = v; }
-  if (stages < 1) return PEG_ERR_UNSUPPORTED;
-  p.stages = stages;
+  const int a_bytes = na * sp * TC_ATILE, b_bytes = sp * p.nd * TC_BK * 4;
+  // smem rings: two B slots (one per pair in flight), the rest of ~208 KB goes to A slots (even count, at most 4)
+  int sb = 2;
+  int sa = ((208 * 1024 - sb * b_bytes) / a_bytes) & ~1;
+  sa = sa > 4 ? 4 : sa;
+  if (sa < 2) { sb = 1; sa = ((208 * 1024 - sb * b_bytes) / a_bytes) & ~1; }
+  if (const char* ev = getenv("PEG_TC_STAGES_A")) { int v = atoi(ev); if (v >= 2 && v <= sa && (v & 1) == 0) sa = v; }
+  if (const char* ev = getenv("PEG_TC_STAGES_B")) { int v = atoi(ev); if (v >= 1 && (size_t)sa * a_bytes + (size_t)v * b_bytes <= 224 * 1024) sb = v; }
+  if (sa < 2) return PEG_ERR_UNSUPPORTED;
+  p.stages_a = sa;
+  p.stages_b = sb;
   p.tmem_cols = tmem_cols_pow2((bwd ? 4 : 1) * p.nd);
   const int nblk = (n + TC_BM - 1) / TC_BM;
   int cluster = 1;   // measured on B200: multicast does not pay (the SM ingress port, not L2, is the limit); PEG_TC_CLUSTER=2|4 enables it
@@ -570,7 +590,7 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   p.cluster = cluster;
   p.experiment = 0;
   if (const char* ev = getenv("PEG_TC_EXPERIMENT")) p.experiment = atoi(ev);
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (3 * stages + 2) + 64;
+  const size_t smem = (size_t)sa * a_bytes + (size_t)sb * b_bytes + 1024 + 8 * (2 * sa + 2 * sb + 2) + 64;
 
   // tensor maps depend only on (buffer, rows, npad, box): a tiny per-thread cache keeps the driver call off the hot path
   struct MapKey { const void* hi; const void* lo; uint64_t rows; int npad, nd; };
@@ -591,11 +611,15 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
     const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.nd / cluster)};
     const cuuint32_t estr[2] = {1, 1};
     if (enc(&ent->mhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w.Vt_hi, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      fprintf(stderr, "pegncde: cuTensorMapEncodeTiled failed: dims %d x %llu, box 32 x %d\n", npad, (unsigned long long)dm.B * d, p.nd / cluster);
       return PEG_ERR_CUDA;
+    }
     if (enc(&ent->mlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w.Vt_lo, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      fprintf(stderr, "pegncde: cuTensorMapEncodeTiled failed: dims %d x %llu, box 32 x %d\n", npad, (unsigned long long)dm.B * d, p.nd / cluster);
       return PEG_ERR_CUDA;
+    }
     ent->k = key;
     ent->valid = true;
   }
@@ -603,12 +627,24 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   const CUtensorMap& mlo = ent->mlo;
 
   dim3 grid((nblk + cluster - 1) / cluster * cluster, d / p.nd, dm.B);   // padded row blocks only keep the cluster in lockstep
-  static thread_local size_t smem_set[2] = {0, 0};   // largest dynamic-smem opt-in already applied per variant
-  if (smem > smem_set[bwd ? 1 : 0]) {
-    const cudaError_t e = bwd ? cudaFuncSetAttribute(k_tc_contract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                              : cudaFuncSetAttribute(k_tc_contract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return PEG_ERR_CUDA;
-    smem_set[bwd ? 1 : 0] = smem;
+  // dynamic-smem opt-in: the attribute is per function and device (NOT per thread -- autograd launches from its own
+  // worker thread), so it is raised once per device to the device limit and never lowered
+  {
+    static std::atomic<unsigned> optin_done[2] = {{0u}, {0u}};   // bit = device ordinal (< 32)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_last_cuda((int)cudaGetLastError()); return PEG_ERR_CUDA; }
+    const unsigned bit = 1u << (dev & 31);
+    if ((optin_done[bwd ? 1 : 0].load(std::memory_order_acquire) & bit) == 0u) {
+      int lim = 0;
+      cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      const cudaError_t e = bwd ? cudaFuncSetAttribute(k_tc_contract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)
+                                : cudaFuncSetAttribute(k_tc_contract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+      if (e != cudaSuccess) {
+        fprintf(stderr, "pegncde: cudaFuncSetAttribute(smem %d) failed: %s\n", lim, cudaGetErrorString(e));
+        set_last_cuda((int)e); (void)cudaGetLastError(); return PEG_ERR_CUDA;
+      }
+      optin_done[bwd ? 1 : 0].fetch_or(bit, std::memory_order_release);
+    }
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -625,8 +661,12 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   cfg.numAttrs = 1;
   const cudaError_t le = bwd ? cudaLaunchKernelEx(&cfg, k_tc_contract<true>, mhi, mlo, p)
                              : cudaLaunchKernelEx(&cfg, k_tc_contract<false>, mhi, mlo, p);
-  if (le != cudaSuccess) return PEG_ERR_CUDA;
-  if (cudaPeekAtLastError() != cudaSuccess) return PEG_ERR_CUDA;
+  if (le != cudaSuccess) {
+    fprintf(stderr, "pegncde: k_tc_contract<%d> launch failed (%s): grid %u x %u x %u, smem %zu, nd %d, slots A %d B %d, tmem %d\n", (int)bwd,
+            cudaGetErrorString(le), grid.x, grid.y, grid.z, smem, p.nd, sa, sb, p.tmem_cols);
+    set_last_cuda((int)le); (void)cudaGetLastError(); return PEG_ERR_CUDA;
+  }
+  if (cudaPeekAtLastError() != cudaSuccess) { set_last_cuda((int)cudaGetLastError()); return PEG_ERR_CUDA; }
   return PEG_OK;
 }
 

@@ -16,5 +16,6 @@ void tc_carve(Bump& bp, const PegDims& d, int dmax, TcWs& w);
 bool tc_supported(const PegDims& d, int dcols);
 int tc_contract(cudaStream_t st, const PegDims& d, const TcWs& w, const ContractArgs& a, bool bwd);
 int tc_launches_per_contract(bool bwd);
+void set_last_cuda(int err);   // records a cudaError_t for pegncde_last_cuda_error() (defined in pegncde.cu)
 
 }  // namespace peg

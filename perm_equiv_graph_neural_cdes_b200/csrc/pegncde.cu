@@ -12,6 +12,7 @@ namespace peg {
 
 static std::atomic<uint64_t> g_launches{0};
 static thread_local int g_last_cuda = 0;
+void set_last_cuda(int err) { g_last_cuda = err; }
 
 #define PEG_LAUNCH_CHECK()                         \
   do {                                             \
