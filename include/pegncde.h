@@ -128,10 +128,25 @@ int pegncde_vf_vjp(peg_stream_t stream, const PegDims* dims, const PegControl* c
 
 /* ---- one Tsit5 step (adaptive controllers stay on the host) ----------------------------- */
 /* k1 = f(t, y) when k1_valid == 0 (first step) else taken from k1 (FSAL).  Writes y1, y_err
- * (= dt * sum_i (b_i - bhat_i) k_i) and k7 = f(t + dt, y1). */
+ * (= dt * sum_i (b_i - bhat_i) k_i) and k7 = f(t + dt, y1).  k_stages (nullable) [5,B,n,h] receives k2..k6
+ * (needed for dense output). */
 int pegncde_step_fwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params, float t,
                      float dt, const float* y, float* k1, int32_t k1_valid, float* y1, float* y_err, float* k7,
-                     void* workspace, size_t workspace_bytes);
+                     float* k_stages, void* workspace, size_t workspace_bytes);
+
+/* ---- Tsit5 dense output: diffrax SaveAt(ts=...) (call site src/models/graph_neural_cde.py:86-104) ---------- */
+/* out = y + dt * sum_i b_i(theta) k_i with Tsitouras' 4th-order interpolant, theta in [0,1] inside the step
+ * [t, t+dt]; k_stages = k2..k6 as written by pegncde_step_fwd. */
+int pegncde_tsit5_dense(peg_stream_t stream, const PegDims* dims, float dt, float theta, const float* y, const float* k1,
+                        const float* k_stages, const float* k7, float* out);
+/* Scaled error norms of adaptive step-size control -- diffrax PIDController(rtol, atol) (call site
+ * src/models/graph_neural_cde.py:53-54) and its initial-step heuristic:
+ *   out[b] = sum_i ((x - x2)_i / (atol + rtol * max(|s0_i|, |s1_i|)))^2   over the n*h entries of graph b
+ * (x2, s1 nullable: 0 / s0).  The host takes sqrt(out / (n h)) (rms norm) and runs the controller. */
+int pegncde_scaled_sumsq(peg_stream_t stream, const PegDims* dims, const float* x, const float* x2, const float* s0,
+                         const float* s1, float rtol, float atol, float* out /* [B] */);
+/* host helper: the seven weights b_i(theta) */
+void pegncde_tsit5_dense_weights(float theta, float* w /* [7] */);
 
 /* ---- fixed-step solve -------------------------------------------------------------------- */
 /* step_ts: HOST array [steps+1] of fp32 step boundaries, built by the caller with diffrax's
@@ -145,13 +160,16 @@ int pegncde_solve_fwd(peg_stream_t stream, const PegDims* dims, const PegControl
  * of every stage there and solve_bwd, handed the same buffer, skips its forward recompute (36 instead of 54 passes
  * over the coefficient planes per step).  NULL = checkpoint-per-step mode: solve_bwd recomputes each step. */
 size_t pegncde_stage_store_bytes(const PegDims* dims, int32_t steps);
-/* g_ckpt (nullable) [steps+1, B, n, h]: cotangents injected at step boundaries (SaveAt(ts=...) losses);
- * g_yT [B,n,h] cotangent of y(T) (either of the two may be NULL, not both).  Writes g_y0; accumulates g_params
- * (caller zeroes it). */
+/* g_ckpt (nullable) [steps+1, B, n, h]: cotangents injected at step boundaries (SaveAt(steps) losses);
+ * g_yT [B,n,h] cotangent of y(T) (either of the two may be NULL, not both).
+ * g_stage (nullable) [steps, 7, B, n, h]: direct cotangents of the stage slopes k1..k7 of every step -- what a loss
+ * on dense-output samples (SaveAt(ts=...)) contributes: dt * b_i(theta) * g_sample, summed over the samples of the step.
+ * Writes g_y0; accumulates g_params (caller zeroes it).  The step table may be any accepted-step sequence (adaptive
+ * controllers): the adjoint is that of the discrete scheme with the step sizes held fixed. */
 int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params,
                       const float* step_ts, int32_t steps, const float* y_ckpt, const float* stage_store,
-                      const float* g_yT, const float* g_ckpt, float* g_y0, float* g_params, void* workspace,
-                      size_t workspace_bytes);
+                      const float* g_yT, const float* g_ckpt, const float* g_stage, float* g_y0, float* g_params,
+                      void* workspace, size_t workspace_bytes);
 
 /* ---- introspection ------------------------------------------------------------------------ */
 const char* pegncde_strerror(int code);

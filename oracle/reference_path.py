@@ -289,6 +289,145 @@ def tsit5_solve_fixed(f, y0: torch.Tensor, step_ts: Sequence[float], save_all: b
 
 
 # --------------------------------------------------------------------------------------
+# third-party: diffrax Tsit5 dense output + PIDController + initial step selection
+# (call site src/models/graph_neural_cde.py:53-54, 86-104: dt0=None, PIDController(rtol=1e-3,
+# atol=1e-6), SaveAt(ts=ts)).  Restated from diffrax (version unpinned) -- parity unpinned.
+# --------------------------------------------------------------------------------------
+
+
+def tsit5_dense_weights(theta: float):
+    """b_i(theta), i = 1..7: Tsitouras' 4th-order interpolant in the factored form diffrax's
+    ``_Tsit5Interpolation`` uses; y(t + theta h) = y + h sum_i b_i(theta) k_i."""
+    t = float(theta)
+    b1 = -1.0530884977290216 * t * (t - 1.3299890189751412) * (t * t - 1.4364028541716351 * t + 0.7139816917074209)
+    b2 = 0.1017 * t * t * (t * t - 2.1966568338249754 * t + 1.2949852507374631)
+    b3 = 2.490627285651252793 * t * t * (t * t - 2.38535645472061657 * t + 1.57803468208092486)
+    b4 = -16.54810288924490272 * (t - 1.21712927295533244) * (t - 0.61620406037800089) * t * t
+    b5 = 47.37952196281928122 * (t - 1.203071208372362603) * (t - 0.658047292653547382) * t * t
+    b6 = -34.87065786149660974 * (t - 1.2) * (t - 0.666666666666666667) * t * t
+    b7 = 2.5 * (t - 1.0) * (t - 0.6) * t * t
+    return (b1, b2, b3, b4, b5, b6, b7)
+
+
+def tsit5_step_full(f, t, h, y, k1):
+    """One Tsit5 step -> (y1, y_err, [k1..k7]); k7 = f(t + h, y1) (FSAL)."""
+    ks = [k1]
+    for i in range(1, 6):
+        acc = ks[0] * TSIT5_A[i][0]
+        for j in range(1, i):
+            acc = acc + ks[j] * TSIT5_A[i][j]
+        ks.append(f(t + TSIT5_C[i] * h, y + h * acc))
+    acc = ks[0] * TSIT5_B[0]
+    for j in range(1, 6):
+        acc = acc + ks[j] * TSIT5_B[j]
+    y1 = y + h * acc
+    ks.append(f(t + h, y1))
+    err = ks[0] * TSIT5_BERR[0]
+    for j in range(1, 7):
+        err = err + ks[j] * TSIT5_BERR[j]
+    return y1, h * err, ks
+
+
+def _rms(x):
+    return float(torch.sqrt(torch.mean(x.detach() ** 2)))
+
+
+def pid_adapt(scaled_error, dt, keep_floor=1.0, safety=0.9, factormin=0.2, factormax=10.0, error_order=5, f=np.float32):
+    """diffrax PIDController.adapt_step_size with pcoeff=0, icoeff=1, dcoeff=0 (its defaults, and what
+    PIDController(rtol, atol) at graph_neural_cde.py:54 builds): keep = err < 1; factor = clip(safety * err^(-1/5),
+    1 if accepted else factormin, factormax)."""
+    err = f(scaled_error)
+    keep = bool(err < f(1.0))
+    with np.errstate(divide="ignore", over="ignore"):
+        inv = f(1.0) / err
+    if not np.isfinite(inv):
+        inv = f(1.0) if np.isnan(inv) else f(np.finfo(np.float32).max)
+    factor = f(safety) * f(inv ** f(1.0 / error_order))
+    lo = f(keep_floor) if keep else f(factormin)
+    factor = min(max(factor, lo), f(factormax))
+    return keep, f(f(dt) * factor)
+
+
+def clip_to_end(tprev, tnext, t1, keep, f=np.float32):
+    """diffrax _clip_to_end (non-float64 times: tolerance 1e-6)."""
+    if f(tnext) > f(f(t1) - f(1e-6)):
+        return f(t1) if keep else f(f(tprev) + f(0.5) * f(f(t1) - f(tprev)))
+    return f(tnext)
+
+
+def select_initial_step(f_vf, t0, y0, f0, rtol, atol, error_order=5, f=np.float32):
+    """diffrax _select_initial_step (Hairer, Norsett & Wanner, II.4 'Starting Step Size')."""
+    scale = atol + y0.detach().abs() * rtol
+    d0, d1 = f(_rms(y0 / scale)), f(_rms(f0 / scale))
+    small = d0 < f(1e-5) or d1 < f(1e-5)
+    h0 = f(1e-6) if small else f(f(0.01) * f(d0 / d1))
+    f1 = f_vf(float(f(t0) + h0), y0 + float(h0) * f0)
+    d2 = f(f(_rms((f1 - f0) / scale)) / h0)
+    dmax = max(d1, d2)
+    h1 = max(f(1e-6), f(h0 * f(1e-3))) if dmax <= f(1e-15) else f((f(0.01) / dmax) ** f(1.0 / error_order))
+    return min(f(100.0) * h0, h1)
+
+
+def tsit5_solve_adaptive(f_vf, y0, t0, t1, rtol=1e-3, atol=1e-6, dt0=None, save_ts=None, max_steps=4096, forced_steps=None):
+    """diffeqsolve(ODETerm(f), Tsit5(), t0, t1, dt0, y0, stepsize_controller=PIDController(rtol, atol),
+    saveat=SaveAt(ts=save_ts) or SaveAt(t1=True)) with fp32 time arithmetic.  Differentiable with autograd with the
+    accepted step sizes held fixed (discretise-then-optimise).  ``forced_steps`` (a step table) bypasses the
+    controller: every listed step is accepted -- used to compare implementations on an identical step sequence.
+    Returns (ys [M, ...] or y(t1), accepted step table, stats)."""
+    f = np.float32
+    t0, t1 = f(t0), f(t1)
+    y = y0
+    k1 = f_vf(float(t0), y)
+    if forced_steps is not None:
+        dt = f(forced_steps[1]) - f(forced_steps[0])
+    elif dt0 is None:
+        dt = select_initial_step(f_vf, t0, y.detach(), k1.detach(), rtol, atol)
+    else:
+        dt = f(dt0)
+    M = 0 if save_ts is None else len(save_ts)
+    saves, mi, attempts, rejected = [], 0, 0, 0
+    boundaries = [t0]
+    tprev = t0
+    tnext = clip_to_end(tprev, f(tprev + dt), t1, True) if forced_steps is None else f(forced_steps[1])
+    while True:
+        attempts += 1
+        if attempts > max_steps:
+            raise RuntimeError("max_steps reached (diffrax throw=True)")
+        h = f(tnext - tprev)
+        y1, yerr, ks = tsit5_step_full(f_vf, float(tprev), float(h), y, k1)
+        if forced_steps is None:
+            scale = atol + rtol * torch.maximum(y.detach().abs(), y1.detach().abs())
+            keep, dt_new = pid_adapt(_rms(yerr / scale), h)
+        else:
+            keep = True
+        if keep:
+            while mi < M and f(save_ts[mi]) <= tnext:
+                theta = f(min(max(f(f(save_ts[mi]) - tprev) / h, f(0.0)), f(1.0)))
+                w = tsit5_dense_weights(float(theta))
+                acc = ks[0] * w[0]
+                for i in range(1, 7):
+                    acc = acc + ks[i] * w[i]
+                saves.append(y + float(h) * acc)
+                mi += 1
+            y, k1 = y1, ks[6]
+            boundaries.append(tnext)
+            tprev_new = tnext
+        else:
+            rejected += 1
+            tprev_new = tprev
+        if keep and tprev_new >= t1:
+            break
+        if forced_steps is None:
+            tnext = clip_to_end(tprev_new, f(tprev_new + dt_new), t1, keep)
+        else:
+            tnext = f(forced_steps[len(boundaries)])
+        tprev = tprev_new
+    stats = {"num_steps": attempts, "num_accepted_steps": attempts - rejected, "num_rejected_steps": rejected}
+    out = torch.stack(saves) if M else y
+    return out, np.asarray(boundaries, dtype=np.float32), stats
+
+
+# --------------------------------------------------------------------------------------
 # solve wrappers + losses
 # --------------------------------------------------------------------------------------
 

@@ -10,7 +10,8 @@ lib()  # raise ImportError right here if libpegncde.so is missing
 
 from .control import CubicInterpolation, PackedControl, backward_hermite_coefficients, pack_control  # noqa: E402,F401
 from .models import MLP, GraphNeuralCDE, PGTGraphNeuralCDE  # noqa: E402,F401
-from .solve import ConstantStepSize, ODETerm, SaveAt, Solution, Tsit5, constant_step_table, diffeqsolve, tsit5_step  # noqa: E402,F401
+from .solve import (ConstantStepSize, ODETerm, PIDController, SaveAt, Solution, Tsit5, clip_to_end, constant_step_table,  # noqa: E402,F401
+                    dense_weights, diffeqsolve, tsit5_step)  # noqa: E402,F401
 from .vector_field import CDEWrapperVectorField, ConvEquivFusionLayer, ConvLayer, PermEquivGraphVectorField  # noqa: E402,F401
 
 __version__ = "0.1.0"

@@ -99,6 +99,16 @@ class PackedControl:
         self.tch_coef = torch.empty((B, T - 1, 3, n), **f)
         self.x_coef = torch.empty((B, T - 1, 3, n, 2 * e), **f) if e > 0 else None
 
+    def select(self, b: int) -> "PackedControl":
+        """View of graph ``b`` as a batch of one (no copy): adaptive solves step every trajectory on its own."""
+        v = PackedControl.__new__(PackedControl)
+        v.B, v.n, v.T, v.e, v.ldn = 1, self.n, self.T, self.e, self.ldn
+        for name in ("ts", "adj_coef", "adj_rowsum", "adj_diag", "adj_total", "tch_coef"):
+            setattr(v, name, getattr(self, name)[b:b + 1])
+        v.x_coef = self.x_coef[b:b + 1] if self.x_coef is not None else None
+        v._keepalive = self
+        return v
+
     def dims(self, h: int, L: int, flags: int = 0) -> PegDims:
         return PegDims(self.B, self.n, self.ldn, h, self.e, L, self.T, flags)
 

@@ -280,6 +280,27 @@ __global__ void __launch_bounds__(256) k_rk_combine(CombArgs a) {
 }
 
 // =====================================================================================
+// Scaled error norm of adaptive step-size control (diffrax PIDController: rms_norm(err / (atol + rtol max(|y0|,|y1|))),
+// also the three norms of the initial-step heuristic):  out[b] = sum_i ((x - x2) / (atol + rtol max(|s0|, |s1|)))^2.
+// One block per graph, fixed summation order (deterministic accept / reject decisions).  grid (B), block 1024.
+// =====================================================================================
+__global__ void __launch_bounds__(1024) k_scaled_sumsq(const float* __restrict__ x, const float* __restrict__ x2,
+                                                       const float* __restrict__ s0, const float* __restrict__ s1,
+                                                       float rtol, float atol, size_t per_graph, float* __restrict__ out) {
+  __shared__ float sh[33];
+  const size_t base = (size_t)blockIdx.x * per_graph;
+  float acc = 0.f;
+  for (size_t i = threadIdx.x; i < per_graph; i += blockDim.x) {
+    const float a = fabsf(s0[base + i]);
+    const float m = s1 ? fmaxf(a, fabsf(s1[base + i])) : a;
+    const float v = (x[base + i] - (x2 ? x2[base + i] : 0.f)) / (atol + rtol * m);
+    acc = fmaf(v, v, acc);
+  }
+  const float tot = block_sum(acc, sh);
+  if (threadIdx.x == 0) out[blockIdx.x] = tot;
+}
+
+// =====================================================================================
 // RMSNorm -> Linear  (layers.py:45-46): M = (w_n * z * rsqrt(mean z^2 + eps) + b_n) W^T + b
 // The norm is linear in z up to the per-node scale, so it moves to the epilogue:
 //     M[node][o] = rinv[node] * sum_k z[node][k] (w_n[k] W[o][k])  +  (sum_k b_n[k] W[o][k] + b[o])

@@ -571,7 +571,7 @@ int pegncde_vf_vjp(peg_stream_t stream, const PegDims* dims, const PegControl* c
 
 int pegncde_step_fwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params, float t,
                      float dt, const float* y, float* k1, int32_t k1_valid, float* y1, float* y_err, float* k7,
-                     void* workspace, size_t workspace_bytes) {
+                     float* k_stages, void* workspace, size_t workspace_bytes) {
   Ctx c;
   PEG_TRY(make_ctx(c, stream, dims, ctl, params));
   if (!y || !k1 || !y1 || !k7 || !workspace) return PEG_ERR_NULL_POINTER;
@@ -580,7 +580,10 @@ int pegncde_step_fwd(peg_stream_t stream, const PegDims* dims, const PegControl*
   plan(*dims, PEG_WS_STEP, 0, workspace, &c.w, &s);
   PEG_TRY(reset_tickets(c));
   const Tsit5& tb = tsit5();
+  const size_t st = (size_t)dims->B * dims->n * dims->h;
   float* k[7] = {k1, s.k[1], s.k[2], s.k[3], s.k[4], s.k[5], k7};
+  if (k_stages)   // the caller keeps k2..k6 (dense output / SaveAt(ts=...))
+    for (int i = 1; i < 6; ++i) k[i] = k_stages + (size_t)(i - 1) * st;
   if (!k1_valid) PEG_TRY(feval_fwd(c, t, y, k[0], nullptr));
   for (int i = 1; i < 7; ++i) {
     const float* xs[8];
@@ -598,6 +601,53 @@ int pegncde_step_fwd(peg_stream_t stream, const PegDims* dims, const PegControl*
     for (int j = 0; j < 7; ++j) { xs[j] = k[j]; cs[j] = (double)dt * tb.berr[j]; }
     PEG_TRY(combine(c, y_err, 7, xs, cs));
   }
+  return PEG_OK;
+}
+
+// Tsit5 dense output (Tsitouras 2011, the interpolant behind diffrax's SaveAt(ts=...)):
+//   y(t + theta dt) = y + dt sum_i b_i(theta) k_i,  b_1 = theta (r11 + theta (r12 + theta (r13 + theta r14))),
+//   b_i = theta^2 (r_i2 + theta (r_i3 + theta r_i4)) for i >= 2;  b_i(1) = b_i, b_7(1) = 0.
+void pegncde_tsit5_dense_weights(float theta, float* w /* [7] */) {
+  static const double r[7][4] = {
+      {1.0, -2.763706197274826, 2.9132554618219126, -1.0530884977290216},
+      {0.0, 0.13169999999999998, -0.2234, 0.1017},
+      {0.0, 3.9302962368947516, -5.941033872131505, 2.490627285651253},
+      {0.0, -12.411077166933676, 30.33818863028232, -16.548102889244902},
+      {0.0, 37.50931341651104, -88.1789048947664, 47.37952196281928},
+      {0.0, -27.896526289197286, 65.09189467479366, -34.87065786149661},
+      {0.0, 1.5, -4.0, 2.5}};
+  const double th = (double)theta;
+  for (int i = 0; i < 7; ++i) w[i] = (float)(th * (r[i][0] + th * (r[i][1] + th * (r[i][2] + th * r[i][3]))));
+}
+
+int pegncde_tsit5_dense(peg_stream_t stream, const PegDims* dims, float dt, float theta, const float* y, const float* k1,
+                        const float* k_stages, const float* k7, float* out) {
+  PEG_TRY(check_dims(dims));
+  if (!y || !k1 || !k_stages || !k7 || !out) return PEG_ERR_NULL_POINTER;
+  float w[7];
+  pegncde_tsit5_dense_weights(theta, w);
+  const size_t st = (size_t)dims->B * dims->n * dims->h;
+  CombArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x[0] = y; a.c[0] = 1.f;
+  a.x[1] = k1; a.c[1] = dt * w[0];
+  for (int i = 1; i < 6; ++i) { a.x[i + 1] = k_stages + (size_t)(i - 1) * st; a.c[i + 1] = dt * w[i]; }
+  a.x[7] = k7; a.c[7] = dt * w[6];
+  a.cnt = 8;
+  a.out = out;
+  a.count4 = st / 4;
+  k_rk_combine<<<(unsigned)((a.count4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  PEG_LAUNCH_CHECK();
+  return PEG_OK;
+}
+
+int pegncde_scaled_sumsq(peg_stream_t stream, const PegDims* dims, const float* x, const float* x2, const float* s0,
+                         const float* s1, float rtol, float atol, float* out) {
+  PEG_TRY(check_dims(dims));
+  if (!x || !s0 || !out) return PEG_ERR_NULL_POINTER;
+  const size_t per_graph = (size_t)dims->n * dims->h;
+  k_scaled_sumsq<<<dims->B, 1024, 0, (cudaStream_t)stream>>>(x, x2, s0, s1, rtol, atol, per_graph, out);
+  PEG_LAUNCH_CHECK();
   return PEG_OK;
 }
 
@@ -654,8 +704,8 @@ int pegncde_solve_fwd(peg_stream_t stream, const PegDims* dims, const PegControl
 
 int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params,
                       const float* step_ts, int32_t steps, const float* y_ckpt, const float* stage_store,
-                      const float* g_yT, const float* g_ckpt, float* g_y0, float* g_params, void* workspace,
-                      size_t workspace_bytes) {
+                      const float* g_yT, const float* g_ckpt, const float* g_stage, float* g_y0, float* g_params,
+                      void* workspace, size_t workspace_bytes) {
   Ctx c;
   PEG_TRY(make_ctx(c, stream, dims, ctl, params));
   if (!step_ts || !y_ckpt || (!g_yT && !g_ckpt) || !g_y0 || !g_params || !workspace) return PEG_ERR_NULL_POINTER;
@@ -672,6 +722,20 @@ int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl
     const float* xs[2] = {g_yT, g_ckpt ? g_ckpt + (size_t)steps * st : nullptr};
     double cs[2] = {g_yT ? 1.0 : 0.0, g_ckpt ? 1.0 : 0.0};
     PEG_TRY(combine(c, s.gcur, 2, xs, cs));
+  }
+  auto stage_cot = [&](int step, int stage) { return g_stage + ((size_t)step * 7 + stage) * st; };
+  if (g_stage) {
+    // dense output of the last step uses k7 = f(t_S, y_S), which belongs to no later step: its VJP feeds ybar_S directly
+    const float* yS = y_ckpt + (size_t)steps * st;
+    float* save[PEG_MAX_LAYERS];
+    save[0] = const_cast<float*>(yS);
+    for (int l = 1; l < L; ++l) save[l] = s.save[0][l];
+    PEG_TRY(feval_fwd(c, step_ts[steps], yS, nullptr, save, L - 1));
+    PEG_TRY(feval_vjp(c, step_ts[steps], save, stage_cot(steps - 1, 6), s.Ybar[0], g_params, nullptr));
+    const float* xs[2] = {s.gcur, s.Ybar[0]};
+    double cs[2] = {1.0, 1.0};
+    PEG_TRY(combine(c, s.gnext, 2, xs, cs));
+    float* tmp = s.gcur; s.gcur = s.gnext; s.gnext = tmp;
   }
   for (int sidx = steps - 1; sidx >= 0; --sidx) {
     const float t = step_ts[sidx];
@@ -704,6 +768,10 @@ int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl
       int cnt = 0;
       xs[cnt] = s.gcur; cs[cnt] = (double)dt * tb.b[i]; ++cnt;
       for (int j = i + 1; j < 6; ++j) { xs[cnt] = s.Ybar[j]; cs[cnt] = (double)dt * tb.a[j][i]; ++cnt; }
+      if (g_stage) {   // direct cotangents of the stage slopes (dense output); k7 of the previous step IS this step's k1
+        xs[cnt] = stage_cot(sidx, i); cs[cnt] = 1.0; ++cnt;
+        if (i == 0 && sidx > 0) { xs[cnt] = stage_cot(sidx - 1, 6); cs[cnt] = 1.0; ++cnt; }
+      }
       PEG_TRY(combine(c, s.kbar, cnt, xs, cs));
       float* save[PEG_MAX_LAYERS];
       if (stage_store) {

@@ -1,8 +1,7 @@
 """Solve wrappers with the reference's call signatures, running the fused solve.
 
 ``PGTGraphNeuralCDE``  <- src/models/pgt_graph_neural_cde.py:13-136
-``GraphNeuralCDE``     <- src/models/graph_neural_cde.py:13-113 (fixed-step variant; the reference's
-                          PID-controlled adaptive solve is driven through ``solve.tsit5_step``)
+``GraphNeuralCDE``     <- src/models/graph_neural_cde.py:13-113 (PID-controlled adaptive solve + dense output)
 
 Only the ``diffeqsolve`` call is replaced; encoder / decoder MLPs are ordinary device ops
 (host plumbing in the reference too).
@@ -15,7 +14,7 @@ import torch
 from torch import nn
 
 from .control import CubicInterpolation
-from .solve import ConstantStepSize, ODETerm, SaveAt, Tsit5, diffeqsolve
+from .solve import ConstantStepSize, ODETerm, PIDController, SaveAt, Tsit5, diffeqsolve
 from .vector_field import CDEWrapperVectorField, Linear, PermEquivGraphVectorField
 
 
@@ -67,11 +66,15 @@ class PGTGraphNeuralCDE(nn.Module):
 
 
 class GraphNeuralCDE(nn.Module):
-    """model(ts, coeffs_adj, x0): Linear(1->h) encoder, ODETerm(vector_field) without the CDE wrapper,
-    Linear(h->1) read-out at every step boundary (``SaveAt(steps=True)``) or at t1."""
+    """``model(ts, coeffs_adj, x0, evolving_out=True)`` of src/models/graph_neural_cde.py:60-113: Linear(1->h) encoder,
+    ``ODETerm(vector_field)`` without the CDE wrapper, ``dt0=None``, ``PIDController(rtol=1e-3, atol=1e-6)``,
+    ``SaveAt(ts=ts)`` (dense output) or ``SaveAt(t1=True)``, Linear(h->1) read-out.
 
-    def __init__(self, hidden_dim: int, vector_field: PermEquivGraphVectorField, seed: int = 0, dt0: float = 0.1,
-                 return_sequence: bool = True):
+    ``controller=ConstantStepSize()`` + ``dt0`` selects the fixed-step fused solve instead (one C-ABI call; read-out at
+    every step boundary) -- not a reference configuration, kept for benchmarking."""
+
+    def __init__(self, hidden_dim: int, vector_field: PermEquivGraphVectorField, seed: int = 0, dt0: Optional[float] = None,
+                 return_sequence: bool = True, controller=None):
         super().__init__()
         g = torch.Generator().manual_seed(seed)
         self.initial_linear = Linear(1, hidden_dim, g)
@@ -79,12 +82,18 @@ class GraphNeuralCDE(nn.Module):
         self.vector_field = vector_field
         self.dt0 = dt0
         self.return_sequence = return_sequence
+        self.method = Tsit5()
+        self.controller = controller if controller is not None else PIDController(rtol=1e-3, atol=1e-6)
 
-    def forward(self, ts, coeffs_adj, x0):
+    def forward(self, ts, coeffs_adj, x0, evolving_out: bool = True):
         control_adj = coeffs_adj if not isinstance(coeffs_adj, (tuple, list, torch.Tensor)) else CubicInterpolation(ts, coeffs_adj)
         y0 = torch.nn.functional.linear(x0, self.initial_linear.weight, self.initial_linear.bias)
-        sol = diffeqsolve(terms=ODETerm(self.vector_field), solver=Tsit5(), t0=float(ts.reshape(-1)[0]),
-                          t1=float(ts.reshape(-1)[-1]), dt0=self.dt0, y0=y0, args=control_adj,
-                          stepsize_controller=ConstantStepSize(), saveat=SaveAt(steps=self.return_sequence, t1=not self.return_sequence))
+        tsv = ts.reshape(-1, ts.shape[-1])[0]   # a batch shares one time grid (dataset_configs.py:160-170)
+        if isinstance(self.controller, PIDController):
+            saveat = SaveAt(ts=tsv) if evolving_out else SaveAt(t1=True)
+        else:
+            saveat = SaveAt(steps=evolving_out, t1=not evolving_out)
+        sol = diffeqsolve(terms=ODETerm(self.vector_field), solver=self.method, t0=float(tsv[0]), t1=float(tsv[-1]),
+                          dt0=self.dt0, y0=y0, args=control_adj, stepsize_controller=self.controller, saveat=saveat)
         ys = sol.ys if self.return_sequence else sol.ys[-1]
         return torch.nn.functional.linear(ys, self.final_linear.weight, self.final_linear.bias)

@@ -11,6 +11,16 @@ The whole integration (all steps x 7 stages x L layers) is enqueued by ONE C-ABI
 (``pegncde_solve_fwd``); reverse mode (``torch.autograd`` standing in for ``jax.custom_vjp``)
 is ONE call of ``pegncde_solve_bwd`` -- the exact discrete adjoint of Tsit5, i.e. the
 gradients diffrax's default ``RecursiveCheckpointAdjoint`` produces.
+
+The adaptive call of the dynamical-systems models (src/models/graph_neural_cde.py:86-104)::
+
+    diffeqsolve(ODETerm(vf), Tsit5(), t0=ts[0], t1=ts[-1], dt0=None, y0=y0, args=control,
+                stepsize_controller=PIDController(rtol=1e-3, atol=1e-6), saveat=SaveAt(ts=ts))
+
+is driven from the host: the controller logic (a handful of scalars per step) stays here, every
+array operation -- the Tsit5 step, the scaled error norm, the dense output, the adjoint over the
+accepted steps -- is a C-ABI call.  Each trajectory of a batch has its own step sequence
+(``jax.vmap`` of the reference's while-loop), so trajectories are solved one after the other.
 """
 from __future__ import annotations
 
@@ -21,7 +31,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from ._lib import PEG_WS_SOLVE_BWD, PEG_WS_SOLVE_FWD, PEG_WS_STEP, check, lib
+from ._lib import PEG_WS_SOLVE_BWD, PEG_WS_SOLVE_FWD, PEG_WS_STEP, PEG_WS_VF_FWD, check, lib
 from .control import _stream_ptr
 from .vector_field import CDEWrapperVectorField, PermEquivGraphVectorField, resolve_control, workspace
 
@@ -41,6 +51,44 @@ class ConstantStepSize:
 
     def __init__(self, rule: str = "state"):
         self.rule = rule
+
+
+class PIDController:
+    """``diffrax.PIDController(rtol, atol)`` -- with the defaults the reference uses (pcoeff=0, icoeff=1, dcoeff=0,
+    i.e. the classical I-controller) plus diffrax's safety / factormin / factormax defaults.
+
+    Restated from diffrax (unpinned): ``keep = err < 1``; ``factor = clip(safety * err**(-1/5),
+    factormin if rejected else 1, factormax)``; the next step is ``dt * factor`` and is clipped to ``t1``."""
+
+    def __init__(self, rtol: float, atol: float, pcoeff: float = 0.0, icoeff: float = 1.0, dcoeff: float = 0.0,
+                 safety: float = 0.9, factormin: float = 0.2, factormax: float = 10.0, error_order: int = 5):
+        if pcoeff != 0.0 or dcoeff != 0.0 or icoeff != 1.0:
+            raise NotImplementedError("only the I-controller the reference configures (pcoeff=0, icoeff=1, dcoeff=0)")
+        self.rtol, self.atol = float(rtol), float(atol)
+        self.safety, self.factormin, self.factormax, self.error_order = safety, factormin, factormax, error_order
+
+    def adapt(self, scaled_error: float, dt):
+        """-> (keep_step, next dt) for a step of size ``dt`` (np.float32) whose scaled error norm is ``scaled_error``."""
+        f = np.float32
+        err = f(scaled_error)
+        keep = bool(err < f(1.0))
+        with np.errstate(divide="ignore", over="ignore"):
+            inv = f(1.0) / err
+        if not np.isfinite(inv):
+            inv = f(1.0) if np.isnan(inv) else f(np.finfo(np.float32).max)
+        factor = f(self.safety) * f(inv ** f(1.0 / self.error_order))
+        lo = f(1.0) if keep else f(self.factormin)
+        factor = min(max(factor, lo), f(self.factormax))
+        return keep, f(f(dt) * f(factor))
+
+
+def clip_to_end(tprev, tnext, t1, keep_step: bool):
+    """diffrax ``_clip_to_end`` for fp32 times: a step that would end within 1e-6 of (or beyond) ``t1`` ends at ``t1``
+    (after a rejection: half way), so dense output never sees a vanishing last interval."""
+    f = np.float32
+    if f(tnext) > f(f(t1) - f(1e-6)):
+        return f(t1) if keep_step else f(f(tprev) + f(0.5) * f(f(t1) - f(tprev)))
+    return f(tnext)
 
 
 @dataclass
@@ -130,7 +178,7 @@ class _SolveFunction(torch.autograd.Function):
         store = ctx.store
         check(l.pegncde_solve_bwd(_stream_ptr(dev), dims, ctl, flat.data_ptr(),
                                   ctx.host_ts.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), S, y_ckpt.data_ptr(),
-                                  store.data_ptr() if store is not None else None, g_yT.data_ptr(), g_ckpt.data_ptr() if g_ckpt is not None else None, g_y0.data_ptr(),
+                                  store.data_ptr() if store is not None else None, g_yT.data_ptr(), g_ckpt.data_ptr() if g_ckpt is not None else None, None, g_y0.data_ptr(),
                                   g_flat.data_ptr(), ws.data_ptr(), ws.numel()), "pegncde_solve_bwd")
         ctx.store = None
         return g_y0, g_flat, None, None, None, None, None
@@ -147,20 +195,21 @@ def _unwrap(term):
 
 def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: Optional[SaveAt] = None,
                 stepsize_controller=None, max_steps: int = 4096, **unused) -> Solution:
-    """Fused drop-in for ``diffrax.diffeqsolve`` on the hot path (Tsit5 + ConstantStepSize).
+    """Fused drop-in for ``diffrax.diffeqsolve`` on the hot path: Tsit5 with ``ConstantStepSize()`` (one C-ABI call
+    per solve) or ``PIDController(rtol, atol)`` (+ ``SaveAt(ts=...)`` dense output; host-driven step loop).
 
-    ``y0``: ``[n,h]`` or batched ``[B,n,h]`` (the reference's ``jax.vmap(model)`` batch).  Adaptive
-    controllers are driven step by step through :func:`tsit5_step` by the caller."""
+    ``y0``: ``[n,h]`` or batched ``[B,n,h]`` (the reference's ``jax.vmap(model)`` batch)."""
     if not isinstance(solver, Tsit5):
         raise NotImplementedError("only Tsit5 is implemented by the fused kernels")
     controller = stepsize_controller or ConstantStepSize()
-    if not isinstance(controller, ConstantStepSize):
-        raise NotImplementedError("diffeqsolve here is the fixed-step path; use tsit5_step for adaptive control")
-    if dt0 is None:
+    if not isinstance(controller, (ConstantStepSize, PIDController)):
+        raise NotImplementedError("stepsize_controller must be ConstantStepSize() or PIDController(rtol, atol)")
+    adaptive = isinstance(controller, PIDController)
+    if dt0 is None and not adaptive:
         raise ValueError("ConstantStepSize needs dt0")
     saveat = saveat or SaveAt(t1=True)
-    if saveat.ts is not None:
-        raise NotImplementedError("SaveAt(ts=...) needs Tsit5 dense output (adaptive path); use steps=True or t1=True")
+    if saveat.ts is not None and not adaptive:
+        raise NotImplementedError("SaveAt(ts=...) is implemented for the adaptive path (Tsit5 dense output); use steps=True or t1=True")
     vf, wrapped = _unwrap(terms)
     if y0.device.type != "cuda":
         raise RuntimeError("the fused solve runs on CUDA only (no CPU fallback)")
@@ -170,11 +219,13 @@ def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: Optional[S
         control_adj, control_data = (args[0] if isinstance(args, (list, tuple)) else args), None
     pc = resolve_control(control_adj, control_data, y0.device)
     dims = vf.dims_for(pc, with_wrapper=wrapped)
-    step_ts = constant_step_table(float(t0), float(t1), float(dt0), controller.rule, max_steps)
     unb = y0.dim() == 2
     yb = (y0.unsqueeze(0) if unb else y0).to(torch.float32)
     if yb.shape[0] != pc.B:
         raise ValueError(f"state batch {yb.shape[0]} != control batch {pc.B}")
+    if adaptive:
+        return _diffeqsolve_adaptive(vf, wrapped, pc, t0, t1, dt0, yb, unb, controller, saveat, max_steps)
+    step_ts = constant_step_table(float(t0), float(t1), float(dt0), controller.rule, max_steps)
     out = _SolveFunction.apply(yb, vf.flat_params(), pc, dims, step_ts, bool(saveat.steps), bool(getattr(vf, "store_stages", True)))
     S = len(step_ts) - 1
     if saveat.steps:
@@ -186,9 +237,170 @@ def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: Optional[S
     return Solution(ts=ts_out, ys=ys, stats={"num_steps": S, "num_accepted_steps": S, "num_rejected_steps": 0})
 
 
+# ----------------------------------------------------------------------------------------------
+# adaptive path: Tsit5 + PIDController + SaveAt(ts=...)   (graph_neural_cde.py:53-54, 86-104)
+# ----------------------------------------------------------------------------------------------
+def dense_weights(theta: float) -> np.ndarray:
+    """b_i(theta), i = 1..7, of Tsit5's 4th-order interpolant (``pegncde_tsit5_dense_weights``)."""
+    w = (ctypes.c_float * 7)()
+    lib().pegncde_tsit5_dense_weights(float(theta), w)
+    return np.asarray(list(w), dtype=np.float32)
+
+
+def _adaptive_trajectory(dims, pc1, flat, y0, t0, t1, dt0, ctrl: PIDController, save_ts, max_steps):
+    """Forward solve of ONE trajectory (B = 1) under the PID controller.  Returns the accepted step table, the state at
+    every accepted boundary, the dense-output samples and bookkeeping for the adjoint."""
+    l = lib()
+    dev = y0.device
+    f = np.float32
+    st = _stream_ptr(dev)
+    ctl = pc1.struct()
+    ws = workspace(dev, max(l.pegncde_workspace_bytes(dims, PEG_WS_STEP, 1), l.pegncde_workspace_bytes(dims, PEG_WS_VF_FWD, 1)))
+    nh = y0[0].numel()
+    norm_out = torch.empty(1, dtype=torch.float32, device=dev)
+
+    def vf_eval(t, y):
+        dy = torch.empty_like(y)
+        check(l.pegncde_vf_fwd(st, dims, ctl, flat.data_ptr(), float(t), y.data_ptr(), dy.data_ptr(), ws.data_ptr(), ws.numel()), "pegncde_vf_fwd")
+        return dy
+
+    def norm(x, x2, s0, s1):
+        check(l.pegncde_scaled_sumsq(st, dims, x.data_ptr(), x2.data_ptr() if x2 is not None else None, s0.data_ptr(),
+                                     s1.data_ptr() if s1 is not None else None, ctrl.rtol, ctrl.atol, norm_out.data_ptr()), "pegncde_scaled_sumsq")
+        return f(np.sqrt(f(norm_out.item()) / f(nh)))
+
+    t0, t1 = f(t0), f(t1)
+    y = y0.clone()
+    k1 = vf_eval(t0, y)   # FSAL solvers evaluate f(t0, y0) at init
+    if dt0 is None:
+        # diffrax _select_initial_step (Hairer, Norsett & Wanner II.4), error order 5
+        d0, d1 = norm(y, None, y, None), norm(k1, None, y, None)
+        small = d0 < f(1e-5) or d1 < f(1e-5)
+        h0 = f(1e-6) if small else f(f(0.01) * f(d0 / d1))
+        f1 = vf_eval(f(t0 + h0), torch.add(y, k1, alpha=float(h0)))
+        d2 = f(norm(f1, k1, y, None) / h0)
+        dmax = max(d1, d2)
+        h1 = max(f(1e-6), f(h0 * f(1e-3))) if dmax <= f(1e-15) else f((f(0.01) / dmax) ** f(1.0 / ctrl.error_order))
+        dt = min(f(100.0) * h0, h1)
+    else:
+        dt = f(dt0)
+    y1, yerr, k7 = torch.empty_like(y), torch.empty_like(y), torch.empty_like(y)
+    kst = torch.empty((5,) + tuple(y.shape), dtype=torch.float32, device=dev)
+    M = 0 if save_ts is None else len(save_ts)
+    ys_save = torch.empty((M,) + tuple(y.shape), dtype=torch.float32, device=dev) if M else None
+    samples = []   # (save index, accepted-step index, theta)
+    boundaries, ckpt = [t0], [y.clone()]
+    mi, attempts, rejected = 0, 0, 0
+    tprev = t0
+    tnext = clip_to_end(tprev, f(tprev + dt), t1, True)
+    while True:
+        attempts += 1
+        if attempts > max_steps:
+            raise RuntimeError(f"max_steps={max_steps} reached")   # diffrax throw=True
+        h = f(tnext - tprev)
+        check(l.pegncde_step_fwd(st, dims, ctl, flat.data_ptr(), float(tprev), float(h), y.data_ptr(), k1.data_ptr(), 1,
+                                 y1.data_ptr(), yerr.data_ptr(), k7.data_ptr(), kst.data_ptr(), ws.data_ptr(), ws.numel()), "pegncde_step_fwd")
+        keep, dt_new = ctrl.adapt(norm(yerr, None, y, y1), h)
+        if keep:
+            s = len(boundaries) - 1
+            while mi < M and f(save_ts[mi]) <= tnext:
+                theta = f(min(max(f(f(save_ts[mi]) - tprev) / h, f(0.0)), f(1.0)))
+                check(l.pegncde_tsit5_dense(st, dims, float(h), float(theta), y.data_ptr(), k1.data_ptr(), kst.data_ptr(),
+                                            k7.data_ptr(), ys_save[mi].data_ptr()), "pegncde_tsit5_dense")
+                samples.append((mi, s, float(theta)))
+                mi += 1
+            y, y1 = y1, y
+            k1, k7 = k7, k1
+            boundaries.append(tnext)
+            ckpt.append(y.clone())
+            tprev_new = tnext
+        else:
+            rejected += 1
+            tprev_new = tprev
+        tnext = clip_to_end(tprev_new, f(tprev_new + dt_new), t1, keep)
+        tprev = tprev_new
+        if keep and tprev >= t1:
+            break
+    if mi < M:
+        raise ValueError("SaveAt(ts=...) holds times outside [t0, t1]")
+    return dict(step_ts=np.asarray(boundaries, dtype=np.float32), y_ckpt=torch.stack(ckpt), ys_save=ys_save, samples=samples,
+                stats={"num_steps": attempts, "num_accepted_steps": attempts - rejected, "num_rejected_steps": rejected,
+                       "step_ts": np.asarray(boundaries, dtype=np.float32)})
+
+
+class _AdaptiveSolveFunction(torch.autograd.Function):
+    """Adaptive solve of a batch of trajectories (each with its own accepted-step sequence).  Backward = the exact
+    discrete adjoint over the accepted steps with the step sizes held fixed (``pegncde_solve_bwd``), the dense-output
+    samples entering as cotangents of the step's start state and of its seven stage slopes."""
+
+    @staticmethod
+    def forward(ctx, y0, flat, vf, wrapped, pc, t0, t1, dt0, ctrl, save_ts, max_steps, stats_out):
+        y0 = y0.contiguous()
+        flat = flat.contiguous()
+        recs, outs = [], []
+        for b in range(pc.B):
+            pc1 = pc.select(b)
+            dims = vf.dims_for(pc1, with_wrapper=wrapped)
+            rec = _adaptive_trajectory(dims, pc1, flat, y0[b:b + 1], t0, t1, dt0, ctrl, save_ts, max_steps)
+            rec["dims"], rec["pc1"] = dims, pc1
+            recs.append(rec)
+            outs.append(rec["ys_save"] if save_ts is not None else rec["y_ckpt"][-1:])
+            stats_out.append(rec["stats"])
+        ctx.recs, ctx.has_ts = recs, save_ts is not None
+        ctx.save_for_backward(flat)
+        return torch.cat(outs, dim=1)   # [M or 1, B, n, h]
+
+    @staticmethod
+    def backward(ctx, g_out):
+        (flat,) = ctx.saved_tensors
+        l = lib()
+        dev = flat.device
+        g_out = g_out.contiguous().to(torch.float32)
+        g_flat = torch.zeros_like(flat)
+        g_y0s = []
+        for b, rec in enumerate(ctx.recs):
+            dims, pc1, y_ckpt, step_ts = rec["dims"], rec["pc1"], rec["y_ckpt"], rec["step_ts"]
+            S = len(step_ts) - 1
+            ws = workspace(dev, l.pegncde_workspace_bytes(dims, PEG_WS_SOLVE_BWD, S))
+            g_y0 = torch.empty_like(y_ckpt[0])
+            g_ckpt = torch.zeros_like(y_ckpt)
+            g_stage = None
+            if ctx.has_ts:
+                g_stage = torch.zeros((S, 7) + tuple(y_ckpt.shape[1:]), dtype=torch.float32, device=dev)
+                for (m, s, theta) in rec["samples"]:
+                    gm = g_out[m, b:b + 1]
+                    g_ckpt[s] += gm
+                    w = dense_weights(theta) * np.float32(step_ts[s + 1] - step_ts[s])
+                    for i in range(7):
+                        if w[i] != 0.0:
+                            g_stage[s, i].add_(gm, alpha=float(w[i]))
+            else:
+                g_ckpt[S] = g_out[0, b:b + 1]
+            check(l.pegncde_solve_bwd(_stream_ptr(dev), dims, pc1.struct(), flat.data_ptr(),
+                                      step_ts.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), S, y_ckpt.data_ptr(), None, None,
+                                      g_ckpt.data_ptr(), g_stage.data_ptr() if g_stage is not None else None, g_y0.data_ptr(),
+                                      g_flat.data_ptr(), ws.data_ptr(), ws.numel()), "pegncde_solve_bwd")
+            g_y0s.append(g_y0)
+        return (torch.cat(g_y0s, dim=0), g_flat) + (None,) * 10
+
+
+def _diffeqsolve_adaptive(vf, wrapped, pc, t0, t1, dt0, yb, unb, ctrl, saveat, max_steps) -> Solution:
+    if saveat.steps:
+        raise NotImplementedError("SaveAt(steps=True) with an adaptive controller (ragged per trajectory) is not implemented")
+    save_ts = None
+    if saveat.ts is not None:
+        save_ts = np.asarray(torch.as_tensor(saveat.ts).detach().cpu().numpy(), dtype=np.float32)
+    stats_list = []
+    out = _AdaptiveSolveFunction.apply(yb, vf.flat_params(), vf, wrapped, pc, float(t0), float(t1), dt0, ctrl, save_ts, max_steps, stats_list)
+    ys = out.squeeze(1) if unb else out
+    ts_out = torch.from_numpy(save_ts.copy()) if save_ts is not None else torch.tensor([float(t1)])
+    stats = stats_list[0] if unb else {k: [s[k] for s in stats_list] for k in stats_list[0]}
+    return Solution(ts=ts_out, ys=ys, stats=stats)
+
+
 def tsit5_step(vf_term, t: float, dt: float, y: torch.Tensor, args, k1: Optional[torch.Tensor] = None):
-    """One Tsit5 step through ``pegncde_step_fwd`` -> ``(y1, y_err, k7)`` for host-side adaptive
-    controllers (PIDController) -- forward only."""
+    """One Tsit5 step through ``pegncde_step_fwd`` -> ``(y1, y_err, k7)`` (forward only; the adaptive
+    ``diffeqsolve`` path below is built on the same entry point)."""
     vf, wrapped = _unwrap(vf_term)
     if wrapped:
         control_adj, control_data = args
@@ -207,7 +419,7 @@ def tsit5_step(vf_term, t: float, dt: float, y: torch.Tensor, args, k1: Optional
     flat = vf.flat_params().detach().contiguous()
     ctl = pc.struct()
     check(l.pegncde_step_fwd(_stream_ptr(y.device), dims, ctl, flat.data_ptr(), float(t), float(dt), yb.data_ptr(),
-                             k1b.data_ptr(), 1 if k1_valid else 0, y1.data_ptr(), yerr.data_ptr(), k7.data_ptr(),
+                             k1b.data_ptr(), 1 if k1_valid else 0, y1.data_ptr(), yerr.data_ptr(), k7.data_ptr(), None,
                              ws.data_ptr(), ws.numel()), "pegncde_step_fwd")
     if unb:
         return y1.squeeze(0), yerr.squeeze(0), k7.squeeze(0)

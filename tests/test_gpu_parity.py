@@ -300,3 +300,93 @@ def test_stage_store_and_recompute_adjoints_agree(cuda):
         outs.append((y0.grad.clone(), torch.cat([t.reshape(-1) for layer in product_grads_as_oracle(vf) for t in layer])))
     assert rel_err(outs[0][0], outs[1][0]) < 1e-6
     assert rel_err(outs[0][1], outs[1][1]) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# adaptive path (configs 0 / 1 of BASELINE.json: GraphNeuralCDE, dt0=None, PIDController(1e-3, 1e-6), SaveAt(ts=ts))
+# ---------------------------------------------------------------------------------------------------
+def _oracle_vf(p):
+    ca = R.CubicInterpolation(p.ts, p.coeffs_adj)
+    if p.e > 0:
+        cx = R.CubicInterpolation(p.ts, p.x_coeffs)
+        return lambda t, y: R.cde_wrapper_vector_field(t, y, ca, cx, p.layers, p.h, p.e)
+    return lambda t, y: R.perm_equiv_vector_field(t, y, ca, p.layers)
+
+
+@pytest.mark.parametrize("n,h,e,L,T", [(60, 16, 0, 2, 12), (129, 32, 2, 2, 6)])
+def test_adaptive_solve_with_dense_output_against_oracle(cuda, n, h, e, L, T):
+    """PIDController + SaveAt(ts): (i) the CUDA path and the fp32 oracle, each running its own controller, accept
+    (almost) the same step sequence; (ii) with the oracle FORCED onto the CUDA path's accepted step table (fp64), the
+    dense-output samples and the exact discrete-adjoint gradients agree to the fixed-step tolerances."""
+    p = R.make_problem(n=n, h=h, e=e, L=L, T=T, t1=4, dt0=0.1, seed=31)
+    vf, term, args = device_model(p, cuda)
+    t0, t1 = float(p.ts[0]), float(p.ts[-1])
+    save_ts = p.ts.to(torch.float32)
+    y0 = p.y0.to(cuda).requires_grad_(True)
+    sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), t0, t1, None, y0, args, stepsize_controller=P.PIDController(rtol=1e-3, atol=1e-6),
+                        saveat=P.SaveAt(ts=save_ts))
+    assert sol.ys.shape == (T, n, h) and torch.isfinite(sol.ys).all()
+    table = sol.stats["step_ts"]
+    assert sol.stats["num_accepted_steps"] == len(table) - 1 and table[0] == np.float32(t0) and table[-1] == np.float32(t1)
+    G = torch.randn(sol.ys.shape, generator=torch.Generator().manual_seed(3))
+    (sol.ys * G.to(cuda)).sum().backward()
+
+    # (i) independent controllers: fp32 oracle
+    ys32, table32, stats32 = R.tsit5_solve_adaptive(_oracle_vf(p), p.y0, t0, t1, save_ts=save_ts.numpy())
+    # accept / reject decisions at scaled error ~ 1 are rounding-sensitive: counts agree approximately, not exactly
+    assert abs(stats32["num_accepted_steps"] - sol.stats["num_accepted_steps"]) <= max(1, sol.stats["num_accepted_steps"] // 10)
+    assert abs(stats32["num_steps"] - sol.stats["num_steps"]) <= max(2, sol.stats["num_steps"] // 4)
+    assert abs(float(table32[1]) - float(table[1])) < 1e-3 * float(table[1])      # initial step-size heuristic
+    assert rel_err(sol.ys, ys32) < 5e-3                                           # two rtol=1e-3 solves
+
+    # (ii) same accepted steps, fp64 truth
+    p64 = R.problem_to(p, torch.float64)
+    layers = R.params_to(p64.layers, requires_grad=True)
+    q = R.Problem(p64.n, p64.h, p64.e, p64.L, p64.ts, p64.coeffs_adj, p64.x_coeffs, p64.y0, layers, p64.step_ts, p64.gyT)
+    y64 = p64.y0.clone().requires_grad_(True)
+    ys64, table64, _ = R.tsit5_solve_adaptive(_oracle_vf(q), y64, t0, t1, save_ts=save_ts.numpy(), forced_steps=table)
+    assert np.array_equal(table64, table)
+    assert rel_err(sol.ys, ys64) < TOL_Y
+    assert rel_err(sol.ys[0], p.y0) < 1e-6                                        # theta = 0 sample is y0
+    (ys64 * G.double()).sum().backward()
+    assert rel_err(y0.grad, y64.grad) < TOL_G
+    for l, (got, lp) in enumerate(zip(product_grads_as_oracle(vf), layers)):
+        for name, g, r in zip(("fusion", "W", "b", "nw", "nb"), got, lp.tensors()):
+            assert rel_err(g, r.grad) < TOL_G, (l, name)
+
+
+def test_adaptive_batch_steps_every_trajectory_on_its_own(cuda):
+    """jax.vmap(model) over trajectories (loss_configs.py:44): each has its own accepted-step sequence; SaveAt(t1)."""
+    ps = [R.make_problem(n=40, h=16, e=0, L=2, T=6, t1=3, dt0=0.1, seed=s, scale=sc) for s, sc in ((41, 1.0), (42, 3.0))]
+    vf, term, _ = device_model(ps[0], cuda)
+    ts = ps[0].ts.to(torch.float32).to(cuda)
+    co = tuple(torch.stack([p.coeffs_adj[i] for p in ps]).to(cuda) for i in range(4))
+    y0 = torch.stack([p.y0 for p in ps]).to(cuda)
+    ctrl = P.PIDController(rtol=1e-3, atol=1e-6)
+    sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 3.0, None, y0, P.CubicInterpolation(ts, co), stepsize_controller=ctrl)
+    assert sol.ys.shape == (1, 2, 40, 16)
+    assert sol.stats["num_steps"][0] != sol.stats["num_steps"][1]      # the stiffer graph needs more steps
+    for b, p in enumerate(ps):
+        q = R.Problem(p.n, p.h, p.e, p.L, p.ts, p.coeffs_adj, None, p.y0, ps[0].layers, p.step_ts, p.gyT)
+        # the batched call against the fp64 oracle forced onto trajectory b's own accepted step table
+        yT, _, _ = R.tsit5_solve_adaptive(_oracle_vf(R.problem_to(q, torch.float64)), q.y0.double(), 0.0, 3.0,
+                                          forced_steps=sol.stats["step_ts"][b])
+        assert rel_err(sol.ys[0, b], yT) < TOL_Y
+        # ... and against the same trajectory solved alone (the packed row sums are reduced with float atomics, so the two
+        # runs may differ in the last bits and, rarely, in one accept / reject decision)
+        single = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 3.0, None, y0[b], P.CubicInterpolation(ts, tuple(c[b] for c in co)),
+                               stepsize_controller=ctrl)
+        assert abs(single.stats["num_steps"] - sol.stats["num_steps"][b]) <= 1
+        assert rel_err(single.ys[0], sol.ys[0, b]) < 5e-3
+
+
+def test_graph_neural_cde_model_matches_reference_call(cuda):
+    """model(ts, coeffs_adj, x0, evolving_out=True) of graph_neural_cde.py:60-113 -> [T, n, 1]."""
+    p = R.make_problem(n=50, h=16, e=0, L=2, T=8, t1=5, dt0=0.1, seed=7, float_ts=True)
+    vf, _, _ = device_model(p, cuda)
+    model = P.GraphNeuralCDE(16, vf, seed=3).to(cuda)
+    x0 = torch.randn(50, 1, generator=torch.Generator().manual_seed(1)).to(cuda)
+    out = model(p.ts.to(torch.float32).to(cuda), tuple(c.to(cuda) for c in p.coeffs_adj), x0)
+    assert out.shape == (8, 50, 1) and torch.isfinite(out).all()
+    out.square().mean().backward()
+    assert all(q.grad is not None and torch.isfinite(q.grad).all() for q in model.parameters())

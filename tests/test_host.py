@@ -119,3 +119,48 @@ def test_tiled_layout_is_a_permutation_with_contiguous_warp_loads():
     assert int(tile.min()) == (1 * 3 + 2) * 4096 and int(tile.max()) == (1 * 3 + 2) * 4096 + 4095
     # elements of one micro-tile row are 4 consecutive floats
     assert torch.equal(off[2, 5, 8:12] - off[2, 5, 8], torch.arange(4))
+
+
+# ---- adaptive path: controller / dense-output host logic against the oracle's restatement ----
+def test_pid_controller_matches_oracle_restatement():
+    c = P.PIDController(rtol=1e-3, atol=1e-6)
+    for err in [0.0, 1e-12, 1e-4, 0.3, 0.999999, 1.0, 1.0000001, 1.7, 50.0, 1e9, float("inf")]:
+        for dt in [1e-4, 0.037, 0.5]:
+            assert c.adapt(err, np.float32(dt)) == R.pid_adapt(err, np.float32(dt)), (err, dt)
+    keep, dt = c.adapt(0.5, np.float32(0.1))
+    assert keep and dt >= np.float32(0.1)          # an accepted step never shrinks the next one
+    keep, dt = c.adapt(1e6, np.float32(0.1))
+    assert not keep and np.isclose(dt, 0.02)       # factormin
+    keep, dt = c.adapt(1e-30, np.float32(0.1))
+    assert keep and np.isclose(dt, 1.0)            # factormax
+    with pytest.raises(NotImplementedError):
+        P.PIDController(1e-3, 1e-6, pcoeff=0.4)
+
+
+def test_clip_to_end_matches_oracle_restatement():
+    for tprev, tnext, keep in [(0.0, 0.5, True), (4.9, 5.0000005, True), (4.9, 4.9999995, True), (4.0, 5.2, False), (4.0, 4.5, False)]:
+        assert P.clip_to_end(tprev, tnext, 5.0, keep) == R.clip_to_end(tprev, tnext, 5.0, keep)
+    assert P.clip_to_end(4.0, 5.2, 5.0, False) == np.float32(4.5)
+    assert P.clip_to_end(4.9, 4.9999995, 5.0, True) == np.float32(5.0)
+
+
+def test_dense_output_weights():
+    """Host helper of the C-ABI (expanded Horner form) against the oracle's factored form (diffrax's)."""
+    for theta in np.linspace(0.0, 1.0, 21):
+        assert np.allclose(P.dense_weights(theta), np.asarray(R.tsit5_dense_weights(theta)), atol=2e-6), theta
+    assert np.allclose(P.dense_weights(1.0), np.asarray(R.TSIT5_B), atol=1e-7)
+    assert np.allclose(P.dense_weights(0.0), 0.0)
+
+
+def test_oracle_adaptive_solver_on_a_known_ode():
+    """Restated PID + dense output: y' = -(1 + sin(t)/2) y has y = exp(-(t + (1 - cos t)/2))."""
+    f = lambda t, y: -y * (1.0 + 0.5 * np.sin(t))
+    ts = np.linspace(0, 5, 11).astype(np.float32)
+    ys, table, stats = R.tsit5_solve_adaptive(f, torch.ones(3, 2, dtype=torch.float64), 0.0, 5.0, save_ts=ts)
+    exact = np.exp(-(ts + 0.5 * (1 - np.cos(ts))))
+    assert np.abs(ys[:, 0, 0].numpy() - exact).max() < 2e-3
+    assert table[0] == 0 and table[-1] == 5 and np.all(np.diff(table) > 0)
+    assert stats["num_accepted_steps"] == len(table) - 1
+    # forcing the accepted table reproduces the run
+    ys2, table2, _ = R.tsit5_solve_adaptive(f, torch.ones(3, 2, dtype=torch.float64), 0.0, 5.0, save_ts=ts, forced_steps=table)
+    assert np.array_equal(table, table2) and torch.allclose(ys, ys2, atol=1e-12)
