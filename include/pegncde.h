@@ -164,12 +164,15 @@ size_t pegncde_stage_store_bytes(const PegDims* dims, int32_t steps);
  * g_yT [B,n,h] cotangent of y(T) (either of the two may be NULL, not both).
  * g_stage (nullable) [steps, 7, B, n, h]: direct cotangents of the stage slopes k1..k7 of every step -- what a loss
  * on dense-output samples (SaveAt(ts=...)) contributes: dt * b_i(theta) * g_sample, summed over the samples of the step.
+ * g_xcoef (nullable, e > 0) [B, T-1, 3, n, 2e]: ACCUMULATES the cotangent of PegControl.x_coef (caller zeroes it) --
+ * the TGB models learn the node-signal path (src/models/tgb_graph_neural_cde.py:118-137), so reverse mode continues
+ * through backward_hermite_coefficients into their data_encoder.
  * Writes g_y0; accumulates g_params (caller zeroes it).  The step table may be any accepted-step sequence (adaptive
  * controllers): the adjoint is that of the discrete scheme with the step sizes held fixed. */
 int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params,
                       const float* step_ts, int32_t steps, const float* y_ckpt, const float* stage_store,
                       const float* g_yT, const float* g_ckpt, const float* g_stage, float* g_y0, float* g_params,
-                      void* workspace, size_t workspace_bytes);
+                      float* g_xcoef, void* workspace, size_t workspace_bytes);
 
 /* ---- introspection ------------------------------------------------------------------------ */
 const char* pegncde_strerror(int code);

@@ -57,7 +57,7 @@ SIGNATURES = {
     "pegncde_scaled_sumsq": (c_int, [_P, _DIMS, _P, _P, _P, _P, c_float, c_float, _P]),
     "pegncde_solve_fwd": (c_int, [_P, _DIMS, _CTL, _P, POINTER(c_float), c_int32, _P, _P, _P, _P, _P, c_size_t]),
     "pegncde_stage_store_bytes": (c_size_t, [_DIMS, c_int32]),
-    "pegncde_solve_bwd": (c_int, [_P, _DIMS, _CTL, _P, POINTER(c_float), c_int32, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t]),
+    "pegncde_solve_bwd": (c_int, [_P, _DIMS, _CTL, _P, POINTER(c_float), c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t]),
     "pegncde_strerror": (c_char_p, [c_int]),
     "pegncde_last_cuda_error": (c_int, []),
     "pegncde_version": (c_char_p, []),

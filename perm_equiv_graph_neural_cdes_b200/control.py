@@ -98,6 +98,7 @@ class PackedControl:
         self.adj_total = torch.empty((B, T - 1, 4), **f)
         self.tch_coef = torch.empty((B, T - 1, 3, n), **f)
         self.x_coef = torch.empty((B, T - 1, 3, n, 2 * e), **f) if e > 0 else None
+        self.x_packed = None   # differentiable source of x_coef when the node-signal coefficients require grad
 
     def select(self, b: int) -> "PackedControl":
         """View of graph ``b`` as a batch of one (no copy): adaptive solves step every trajectory on its own."""
@@ -106,6 +107,7 @@ class PackedControl:
         for name in ("ts", "adj_coef", "adj_rowsum", "adj_diag", "adj_total", "tch_coef"):
             setattr(v, name, getattr(self, name)[b:b + 1])
         v.x_coef = self.x_coef[b:b + 1] if self.x_coef is not None else None
+        v.x_packed = None
         v._keepalive = self
         return v
 
@@ -173,7 +175,13 @@ def pack_control(
                            pc.adj_total.data_ptr(), pc.tch_coef.data_ptr()),
         "pegncde_pack_adj",
     )
-    if cx is not None:
+    pc.x_packed = None
+    if cx is not None and any(c.requires_grad for c in cx):
+        # learnable node-signal path (TGB models, tgb_graph_neural_cde.py:118-137): the re-layout stays on the autograd
+        # tape so that pegncde_solve_bwd's g_xcoef flows back into backward_hermite_coefficients / the data encoder
+        pc.x_packed = torch.stack([cx[2], cx[1], cx[0]], dim=2).reshape(B, Tm1, 3, n, 2 * e)
+        pc.x_coef = pc.x_packed.detach().contiguous()
+    elif cx is not None:
         check(
             l.pegncde_pack_x(st, dims, cx[0].data_ptr(), cx[1].data_ptr(), cx[2].data_ptr(), cx[3].data_ptr(),
                              pc.x_coef.data_ptr()),

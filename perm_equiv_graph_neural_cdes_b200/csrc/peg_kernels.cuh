@@ -759,6 +759,23 @@ __global__ void __launch_bounds__(256) k_wrapper_xbar(const float* __restrict__ 
   gxd[idx] = acc;
 }
 
+// cotangent of the node-signal coefficient path (TGB models learn it: tgb_graph_neural_cde.py:118-137).  X'(t) = b + s (2 c + 3 s d)
+// on the stage's cubic piece, so g_b += g_xd, g_c += 2 s g_xd, g_d += 3 s^2 g_xd on that piece.  Stages run one after the
+// other on the stream, so plain read-modify-write is race free.  g_xcoef [B, T-1, 3, n, 2e]
+__global__ void __launch_bounds__(256) k_xcoef_accum(const float* __restrict__ gxd, const StageScalars* __restrict__ sc, int n,
+                                                     int e2, int Tm1, int B, float* __restrict__ g_xcoef) {
+  const size_t per = (size_t)n * e2;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * per) return;
+  const int b = (int)(idx / per);
+  const size_t i = idx % per;
+  const float s = sc[b].s, g = gxd[idx];
+  float* slab = g_xcoef + ((size_t)b * Tm1 + sc[b].interval) * 3 * per;
+  slab[i] += g;
+  slab[per + i] += 2.f * s * g;
+  slab[2 * per + i] += 3.f * s * s * g;
+}
+
 // =====================================================================================
 // gradients of param3..param8 of one layer: O(n d) dot products against row sums /
 // diagonals / totals.  grid (ceil(n/8), B), block 256 (one warp per node)

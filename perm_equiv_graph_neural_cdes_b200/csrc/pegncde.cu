@@ -129,6 +129,7 @@ struct FevalWs {
   float* Obar;   // [B,n,dmax]
   float* Mbar;   // [B,n,dmax]
   float* N;      // [B,n,h]
+  float* gxd;    // [B,n,2e] cotangent of control_data.derivative(t) (solve_bwd with g_xcoef)
   TcWs tc;       // tensor-core operand buffers (peg_tc.cuh)
 };
 
@@ -149,8 +150,9 @@ static void carve_feval(Bump& bp, const PegDims& d, const Model& m, bool vjp, Fe
     w.Obar = bp.take<float>(B * n * dm);
     w.Mbar = bp.take<float>(B * n * dm);
     w.N = bp.take<float>(B * n * h);
+    w.gxd = d.e > 0 ? bp.take<float>(B * n * 2 * d.e) : nullptr;
   } else {
-    w.Obar = w.Mbar = w.N = nullptr;
+    w.Obar = w.Mbar = w.N = w.gxd = nullptr;
   }
   tc_carve(bp, d, m.dmax, w.tc);
 }
@@ -705,11 +707,12 @@ int pegncde_solve_fwd(peg_stream_t stream, const PegDims* dims, const PegControl
 int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params,
                       const float* step_ts, int32_t steps, const float* y_ckpt, const float* stage_store,
                       const float* g_yT, const float* g_ckpt, const float* g_stage, float* g_y0, float* g_params,
-                      void* workspace, size_t workspace_bytes) {
+                      float* g_xcoef, void* workspace, size_t workspace_bytes) {
   Ctx c;
   PEG_TRY(make_ctx(c, stream, dims, ctl, params));
   if (!step_ts || !y_ckpt || (!g_yT && !g_ckpt) || !g_y0 || !g_params || !workspace) return PEG_ERR_NULL_POINTER;
   if (steps < 1) return PEG_ERR_BAD_DIMS;
+  if (g_xcoef && dims->e == 0) return PEG_ERR_BAD_DIMS;
   if (workspace_bytes < plan(*dims, PEG_WS_SOLVE_BWD, steps, nullptr, nullptr, nullptr)) return PEG_ERR_WORKSPACE;
   SolveWs s;
   plan(*dims, PEG_WS_SOLVE_BWD, steps, workspace, &c.w, &s);
@@ -717,6 +720,16 @@ int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl
   const Tsit5& tb = tsit5();
   const size_t st = (size_t)dims->B * dims->n * dims->h;
   const int L = dims->L;
+  // one evaluation's VJP; with g_xcoef also the cotangent of the node-signal coefficients of the stage's cubic piece
+  auto stage_vjp = [&](float t, float* const* save, const float* kbar, float* ybar) -> int {
+    PEG_TRY(feval_vjp(c, t, save, kbar, ybar, g_params, g_xcoef ? c.w.gxd : nullptr));
+    if (g_xcoef) {
+      const size_t cnt = (size_t)dims->B * dims->n * 2 * dims->e;
+      k_xcoef_accum<<<(unsigned)((cnt + 255) / 256), 256, 0, c.st>>>(c.w.gxd, c.w.sc, dims->n, 2 * dims->e, dims->T - 1, dims->B, g_xcoef);
+      PEG_LAUNCH_CHECK();
+    }
+    return PEG_OK;
+  };
   // running cotangent of y_{s+1}
   {
     const float* xs[2] = {g_yT, g_ckpt ? g_ckpt + (size_t)steps * st : nullptr};
@@ -731,7 +744,7 @@ int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl
     save[0] = const_cast<float*>(yS);
     for (int l = 1; l < L; ++l) save[l] = s.save[0][l];
     PEG_TRY(feval_fwd(c, step_ts[steps], yS, nullptr, save, L - 1));
-    PEG_TRY(feval_vjp(c, step_ts[steps], save, stage_cot(steps - 1, 6), s.Ybar[0], g_params, nullptr));
+    PEG_TRY(stage_vjp(step_ts[steps], save, stage_cot(steps - 1, 6), s.Ybar[0]));
     const float* xs[2] = {s.gcur, s.Ybar[0]};
     double cs[2] = {1.0, 1.0};
     PEG_TRY(combine(c, s.gnext, 2, xs, cs));
@@ -782,7 +795,7 @@ int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl
         save[0] = (i == 0) ? const_cast<float*>(y) : s.save[i][0];
         for (int l = 1; l < L; ++l) save[l] = s.save[i][l];
       }
-      PEG_TRY(feval_vjp(c, tis[i], save, s.kbar, s.Ybar[i], g_params, nullptr));
+      PEG_TRY(stage_vjp(tis[i], save, s.kbar, s.Ybar[i]));
     }
     // ---- ybar_s = g + sum_i Ybar_i (+ injected cotangent at this boundary) ----
     {

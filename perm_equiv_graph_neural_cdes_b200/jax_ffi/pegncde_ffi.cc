@@ -55,7 +55,7 @@ static ffi::Error SolveBwdImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> params
   // the cotangent of the saved trajectory arrives as g_ckpt [S+1,B,n,h] (its last slab is the cotangent of y(T))
   const int rc = pegncde_solve_bwd(stream, &d, &c, params.typed_data(), step_ts.begin(), steps, y_ckpt.typed_data(),
                                    stage_store.element_count() ? stage_store.typed_data() : nullptr, nullptr,
-                                   g_ckpt.typed_data(), /*g_stage=*/nullptr, g_y0->typed_data(), g_params->typed_data(),
+                                   g_ckpt.typed_data(), /*g_stage=*/nullptr, g_y0->typed_data(), g_params->typed_data(), /*g_xcoef=*/nullptr,
                                    workspace->typed_data(), workspace->element_count());
   if (rc != PEG_OK) return ffi::Error(ffi::ErrorCode::kInternal, pegncde_strerror(rc));
   return ffi::Error::Success();

@@ -1,6 +1,7 @@
 """Solve wrappers with the reference's call signatures, running the fused solve.
 
 ``PGTGraphNeuralCDE``  <- src/models/pgt_graph_neural_cde.py:13-136
+``TGBGraphNeuralCDE``  <- src/models/tgb_graph_neural_cde.py:13-171 (learned node-signal control)
 ``GraphNeuralCDE``     <- src/models/graph_neural_cde.py:13-113 (PID-controlled adaptive solve + dense output)
 
 Only the ``diffeqsolve`` call is replaced; encoder / decoder MLPs are ordinary device ops
@@ -13,7 +14,7 @@ from typing import Optional
 import torch
 from torch import nn
 
-from .control import CubicInterpolation
+from .control import CubicInterpolation, backward_hermite_coefficients
 from .solve import ConstantStepSize, ODETerm, PIDController, SaveAt, Tsit5, diffeqsolve
 from .vector_field import CDEWrapperVectorField, Linear, PermEquivGraphVectorField
 
@@ -63,6 +64,49 @@ class PGTGraphNeuralCDE(nn.Module):
         if global_readout:
             return output.sum(dim=-2)
         return output
+
+
+class TGBGraphNeuralCDE(nn.Module):
+    """``model(ts, coeffs_adj, x_data, x0, start_time, evolving_out=False)`` of src/models/tgb_graph_neural_cde.py:96-171.
+
+    The node-signal control is LEARNED: ``x_data [T, n, num_nodes]`` goes through ``data_encoder`` (Linear
+    num_nodes -> data_embed_dim), is stacked with the time channel and turned into Hermite coefficients inside the model
+    (``:118-137``), so reverse mode continues from the solve (``g_xcoef`` of ``pegncde_solve_bwd``) into the encoder.
+    ConstantStepSize, ``dt0 = 0.01`` (``:143``), ``SaveAt(t1=True)`` (no trainer passes ``evolving_out=True``)."""
+
+    def __init__(self, hidden_dim: int, vector_field: PermEquivGraphVectorField, use_mlps: bool = True, seed: int = 0,
+                 dt0: float = 0.01, return_sequence: bool = False):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        n, e = vector_field.num_nodes, vector_field.data_embed_dim
+        self.hidden_dim, self.dt0, self.return_sequence = hidden_dim, dt0, return_sequence
+        self.vector_field = vector_field
+        if use_mlps:
+            self.encoder, self.decoder = MLP(n, hidden_dim, 16, 2, g), MLP(hidden_dim, n, 16, 2, g)
+        else:
+            self.encoder, self.decoder = Linear(n, hidden_dim, g), Linear(hidden_dim, n, g)
+        self.data_encoder = Linear(n, e, g)
+        self.method, self.controller = Tsit5(), ConstantStepSize()
+        self.wrapped_vector_field = CDEWrapperVectorField(vector_field, hidden_dim)
+
+    @staticmethod
+    def _lin(mod, x):
+        return mod(x) if isinstance(mod, MLP) else torch.nn.functional.linear(x, mod.weight, mod.bias)
+
+    def forward(self, ts, coeffs_adj, x_data, x0, start_time=None, evolving_out: bool = False):
+        if evolving_out:
+            raise NotImplementedError("SaveAt(ts=...) on the fixed-step path is not implemented (no reference trainer uses it)")
+        x_emb = self._lin(self.data_encoder, x_data)                                  # [T, n, e]
+        tsf = ts.to(x_emb.dtype)
+        x_path = torch.stack([tsf[:, None, None].expand_as(x_emb), x_emb], dim=-1)      # [T, n, e, 2] (time, value)
+        coeffs_data = backward_hermite_coefficients(tsf, x_path)
+        control_adj = coeffs_adj if not isinstance(coeffs_adj, (tuple, list, torch.Tensor)) else CubicInterpolation(ts, coeffs_adj)
+        control_data = CubicInterpolation(ts, coeffs_data)
+        y0 = self._lin(self.encoder, x0)
+        sol = diffeqsolve(terms=ODETerm(self.wrapped_vector_field), solver=self.method, t0=float(ts[0]), t1=float(ts[-1]),
+                          dt0=self.dt0, y0=y0, args=[control_adj, control_data], stepsize_controller=self.controller,
+                          saveat=SaveAt(t1=True))
+        return self._lin(self.decoder, sol.ys if self.return_sequence else sol.ys[-1])
 
 
 class GraphNeuralCDE(nn.Module):

@@ -129,7 +129,7 @@ def constant_step_table(t0: float, t1: float, dt0: float, rule: str = "state", m
 
 class _SolveFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y0, flat, pc, dims, step_ts, save_steps, store_stages):
+    def forward(ctx, y0, flat, x_packed, pc, dims, step_ts, save_steps, store_stages):
         y0 = y0.contiguous()
         flat = flat.contiguous()
         S = len(step_ts) - 1
@@ -140,7 +140,7 @@ class _SolveFunction(torch.autograd.Function):
         y_ckpt = torch.empty((S + 1,) + tuple(y0.shape), dtype=torch.float32, device=dev)
         host_ts = np.ascontiguousarray(step_ts, dtype=np.float32)
         ctl = pc.struct()
-        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        need_grad = any(ctx.needs_input_grad[:3])
         store = None
         if store_stages and need_grad:
             nbytes_store = l.pegncde_stage_store_bytes(dims, S)
@@ -174,14 +174,15 @@ class _SolveFunction(torch.autograd.Function):
             g_yT = g_out
         g_y0 = torch.empty_like(y_ckpt[0])
         g_flat = torch.zeros_like(flat)
+        g_x = torch.zeros_like(pc.x_coef) if ctx.needs_input_grad[2] else None
         ctl = pc.struct()
         store = ctx.store
         check(l.pegncde_solve_bwd(_stream_ptr(dev), dims, ctl, flat.data_ptr(),
                                   ctx.host_ts.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), S, y_ckpt.data_ptr(),
                                   store.data_ptr() if store is not None else None, g_yT.data_ptr(), g_ckpt.data_ptr() if g_ckpt is not None else None, None, g_y0.data_ptr(),
-                                  g_flat.data_ptr(), ws.data_ptr(), ws.numel()), "pegncde_solve_bwd")
+                                  g_flat.data_ptr(), g_x.data_ptr() if g_x is not None else None, ws.data_ptr(), ws.numel()), "pegncde_solve_bwd")
         ctx.store = None
-        return g_y0, g_flat, None, None, None, None, None
+        return g_y0, g_flat, g_x, None, None, None, None, None
 
 
 def _unwrap(term):
@@ -226,7 +227,7 @@ def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: Optional[S
     if adaptive:
         return _diffeqsolve_adaptive(vf, wrapped, pc, t0, t1, dt0, yb, unb, controller, saveat, max_steps)
     step_ts = constant_step_table(float(t0), float(t1), float(dt0), controller.rule, max_steps)
-    out = _SolveFunction.apply(yb, vf.flat_params(), pc, dims, step_ts, bool(saveat.steps), bool(getattr(vf, "store_stages", True)))
+    out = _SolveFunction.apply(yb, vf.flat_params(), pc.x_packed, pc, dims, step_ts, bool(saveat.steps), bool(getattr(vf, "store_stages", True)))
     S = len(step_ts) - 1
     if saveat.steps:
         ys = out.squeeze(1) if unb else out
@@ -379,7 +380,7 @@ class _AdaptiveSolveFunction(torch.autograd.Function):
             check(l.pegncde_solve_bwd(_stream_ptr(dev), dims, pc1.struct(), flat.data_ptr(),
                                       step_ts.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), S, y_ckpt.data_ptr(), None, None,
                                       g_ckpt.data_ptr(), g_stage.data_ptr() if g_stage is not None else None, g_y0.data_ptr(),
-                                      g_flat.data_ptr(), ws.data_ptr(), ws.numel()), "pegncde_solve_bwd")
+                                      g_flat.data_ptr(), None, ws.data_ptr(), ws.numel()), "pegncde_solve_bwd")
             g_y0s.append(g_y0)
         return (torch.cat(g_y0s, dim=0), g_flat) + (None,) * 10
 

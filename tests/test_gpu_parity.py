@@ -390,3 +390,57 @@ def test_graph_neural_cde_model_matches_reference_call(cuda):
     assert out.shape == (8, 50, 1) and torch.isfinite(out).all()
     out.square().mean().backward()
     assert all(q.grad is not None and torch.isfinite(q.grad).all() for q in model.parameters())
+
+
+# ---------------------------------------------------------------------------------------------------
+# learned node-signal control (TGB models): cotangent of the x coefficients through the solve
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flags", [0, TC], ids=["ffma", "tcgen05"])
+def test_solve_gradient_wrt_node_signal_coefficients(cuda, flags):
+    """tgb_graph_neural_cde.py:118-137 builds coeffs_data inside the model, so d loss / d x_coeffs must come out of the
+    solve: pegncde_solve_bwd's g_xcoef against autograd through the fp64 oracle (b, c, d arrays; `a` is unused by X')."""
+    p = R.make_problem(n=130 if flags else 37, h=32 if flags else 16, e=2, L=2, T=5, t1=2, dt0=0.1, seed=13)
+    vf, term, _ = device_model(p, cuda, flags=flags)
+    ts = p.ts.to(torch.float32).to(cuda)
+    xco = tuple(c.to(cuda).requires_grad_(True) for c in p.x_coeffs)
+    args = [P.CubicInterpolation(ts, tuple(c.to(cuda) for c in p.coeffs_adj)), P.CubicInterpolation(ts, xco)]
+    sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 2.0, 0.1, p.y0.to(cuda), args)
+    (sol.ys[-1] * p.gyT.to(cuda)).sum().backward()
+    p64 = R.problem_to(p, torch.float64)
+    x64 = tuple(c.clone().requires_grad_(True) for c in p64.x_coeffs)
+    yT = R.solve_cde(p64.step_ts, p64.ts, p64.coeffs_adj, x64, p64.y0, p64.layers, p64.h, p64.e)
+    (yT * p64.gyT).sum().backward()
+    assert rel_err(sol.ys[-1], yT) < TOL_Y
+    for name, got, ref in zip("dcb", xco[:3], x64[:3]):
+        # the time channel [..., 0] of the coefficients does not enter X' of the data channel
+        assert rel_err(got.grad, ref.grad) < TOL_G, name
+    assert xco[3].grad is None or float(xco[3].grad.abs().max()) == 0.0
+
+
+def test_tgb_model_trains_its_data_encoder(cuda):
+    """model(ts, coeffs_adj, x_data, x0, start_time) of tgb_graph_neural_cde.py:96-171: gradients reach data_encoder."""
+    n, h, e, T = 48, 16, 4, 5
+    p = R.make_problem(n=n, h=h, e=e, L=2, T=T, t1=T - 1, dt0=0.1, seed=23)
+    vf, _, _ = device_model(p, cuda)
+    model = P.TGBGraphNeuralCDE(h, vf, use_mlps=True, seed=2, dt0=0.05).to(cuda)
+    g = torch.Generator().manual_seed(9)
+    x_data = torch.randn(T, n, n, generator=g).to(cuda)
+    x0 = torch.randn(n, n, generator=g).to(cuda)
+    out = model(torch.arange(T, device=cuda), tuple(c.to(cuda) for c in p.coeffs_adj), x_data, x0, None)
+    assert out.shape == (n, n) and torch.isfinite(out).all()
+    out.square().mean().backward()
+    for name, q in model.named_parameters():
+        assert q.grad is not None and torch.isfinite(q.grad).all(), name
+    assert float(model.data_encoder.weight.grad.abs().max()) > 0
+    # finite-difference check of one data-encoder weight through the whole model
+    w = model.data_encoder.weight
+    idx = (1, 3)
+    ga = float(w.grad[idx])
+    def loss():
+        with torch.no_grad():
+            return float(model(torch.arange(T, device=cuda), tuple(c.to(cuda) for c in p.coeffs_adj), x_data, x0, None).double().square().mean())
+    eps = 2e-2
+    with torch.no_grad():
+        w[idx] += eps; lp = loss(); w[idx] -= 2 * eps; lm = loss(); w[idx] += eps
+    fd = (lp - lm) / (2 * eps)
+    assert abs(fd - ga) < 5e-2 * max(abs(fd), abs(ga), 1e-4), (fd, ga)
