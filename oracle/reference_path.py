@@ -197,6 +197,20 @@ def perm_equiv_vector_field(t, y, control_adj: CubicInterpolation, layers: List[
     return t_gradient[:, None] * node_features
 
 
+def plain_graph_vector_field(t, y, control_adj: CubicInterpolation, layers: List[LayerParams], with_derivative: bool):
+    """GraphVectorField.__call__ (graph_vector_field.py:80-115, enc_idx=False; message passing matrix A + A') and
+    GNODEVectorField.__call__ (gnode_vector_field.py:57-81; A only): plain ConvLayers, ReLU between, time-gradient scale."""
+    adj, adj_derivative = control_adj.evaluate(t), control_adj.derivative(t)
+    mp = adj[..., -1] + adj_derivative[..., -1] if with_derivative else adj[..., -1]
+    z = y
+    for i, lp in enumerate(layers):
+        z = conv_layer(z, mp, lp)
+        if i < len(layers) - 1:
+            z = torch.relu(z)
+    t_gradient = adj_derivative[:, :, 0].mean(dim=0)
+    return t_gradient[:, None] * z
+
+
 def cde_wrapper_vector_field(t, y, control_adj, control_data, layers, hidden_dim, data_embed_dim):
     """CDEWrapperVectorField.__call__, cde_wrapper_vector_field.py:19-26."""
     out = perm_equiv_vector_field(t, y, control_adj, layers).reshape(-1, hidden_dim, data_embed_dim, 2)

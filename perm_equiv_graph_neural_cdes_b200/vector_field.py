@@ -72,6 +72,25 @@ class ConvEquivFusionLayer(nn.Module):
         return torch.cat([getattr(self, f"param{i}") for i in range(1, 9)])
 
 
+class _FixedFusionConvLayer(ConvLayer):
+    """A plain ``ConvLayer`` (layers.py:11-48) run through the equivariant kernel with CONSTANT fusion scalars:
+    ``m + (c0 A + c1 A') m`` is the fused form with ``param1 = (c0 - 1, c1 - 1)`` and ``param2..8 = 0``.  Leaf names stay
+    the reference's (``gnn_layers[i].linear`` / ``.norm``); the fusion vector is a buffer, so it gets no gradient."""
+
+    def __init__(self, input_dim: int, output_dim: int, generator, c0: float, c1: float):
+        super().__init__(input_dim, output_dim, generator)
+        fus = torch.zeros(16)
+        fus[0], fus[1] = c0 - 1.0, c1 - 1.0
+        self.register_buffer("fusion_const", fus)
+
+    @property
+    def conv_layer(self):
+        return self
+
+    def fusion_params(self) -> torch.Tensor:
+        return self.fusion_const
+
+
 class PermEquivGraphVectorField(nn.Module):
     """src/models/vector_fields/perm_equiv_graph_vector_field.py:10-129 (enc_idx=False).
 
@@ -89,9 +108,9 @@ class PermEquivGraphVectorField(nn.Module):
             gen = torch.Generator().manual_seed(int(key))
         layers = []
         for _ in range(num_layers - 1):
-            layers.append(ConvEquivFusionLayer(input_dim, hidden_dim, gen))
+            layers.append(self._make_layer(input_dim, hidden_dim, gen))
             input_dim = hidden_dim
-        layers.append(ConvEquivFusionLayer(input_dim, output_dim, gen))
+        layers.append(self._make_layer(input_dim, output_dim, gen))
         self.gnn_layers = nn.ModuleList(layers)
         self.data_embed_dim = data_embed_dim
         self.num_nodes = num_nodes
@@ -101,6 +120,9 @@ class PermEquivGraphVectorField(nn.Module):
         self.flags = 0
         # keep every stage's layer inputs in the forward solve so the adjoint needs no recompute (memory permitting)
         self.store_stages = True
+
+    def _make_layer(self, input_dim: int, output_dim: int, gen) -> nn.Module:
+        return ConvEquivFusionLayer(input_dim, output_dim, gen)
 
     # ---- packing -------------------------------------------------------------------------
     @property
@@ -144,6 +166,21 @@ class PermEquivGraphVectorField(nn.Module):
     # ---- the ODETerm callable ------------------------------------------------------------
     def forward(self, t, y: torch.Tensor, args) -> torch.Tensor:
         return fused_vector_field(self, t, y, args, None)
+
+
+class GraphVectorField(PermEquivGraphVectorField):
+    """src/models/vector_fields/graph_vector_field.py:80-115 (enc_idx=False): the plain GN-CDE field, message passing
+    matrix ``A_s + A'_s`` -- the degenerate case of the same kernels."""
+
+    def _make_layer(self, input_dim: int, output_dim: int, gen) -> nn.Module:
+        return _FixedFusionConvLayer(input_dim, output_dim, gen, 1.0, 1.0)
+
+
+class GNODEVectorField(PermEquivGraphVectorField):
+    """src/models/vector_fields/gnode_vector_field.py:57-81: message passing matrix ``A_s`` only."""
+
+    def _make_layer(self, input_dim: int, output_dim: int, gen) -> nn.Module:
+        return _FixedFusionConvLayer(input_dim, output_dim, gen, 1.0, 0.0)
 
 
 class CDEWrapperVectorField(nn.Module):
