@@ -9,6 +9,7 @@
  *
  *   pegncde_pack_adj        src/configs/dataset_configs.py:147-173,1073-1100  (coeff layout -> planar planes)
  *   pegncde_pack_x          src/configs/dataset_configs.py:1073-1100          (node-signal coeffs)
+ *   pegncde_build_adj       get_graph_interpolation_coeffs, dataset_configs.py:147-173,1073-1100 (snapshots -> planes)
  *   pegncde_vf_fwd          src/models/vector_fields/perm_equiv_graph_vector_field.py:85-129
  *                           + cde_wrapper_vector_field.py:19-26  (the ODETerm callable vf(t, y, args))
  *   pegncde_vf_vjp          jax.vjp of the same callable
@@ -107,6 +108,12 @@ int pegncde_pack_adj(peg_stream_t stream, const PegDims* dims, const float* d, c
  * tch_coef is written as d(time)/dt == 1 (b=1, c=d=0). */
 int pegncde_adj_stats(peg_stream_t stream, const PegDims* dims, const float* adj_coef, float* adj_rowsum,
                       float* adj_diag, float* adj_total, float* tch_coef);
+/* Control-path builder: graph snapshots A_k [B, T, n, n] + knot times ts [B, T] (device) -> the same
+ * outputs as pegncde_pack_adj, with diffrax.backward_hermite_coefficients (call sites
+ * src/configs/dataset_configs.py:168-170, 1094-1096) fused in: 4 n^2 T bytes cross the bus instead of 32 n^2 (T-1).
+ * The time channel is implied (X_time(t) = t): tch_coef is written as (1, 0, 0). */
+int pegncde_build_adj(peg_stream_t stream, const PegDims* dims, const float* ts, const float* snapshots, float* adj_coef,
+                      float* adj_rowsum, float* adj_diag, float* adj_total, float* tch_coef);
 /* d,c,b,a each [B, T-1, n, e, 2] -> x_coef [B, T-1, 3, n, 2e] */
 int pegncde_pack_x(peg_stream_t stream, const PegDims* dims, const float* d, const float* c, const float* b,
                    const float* a, float* x_coef);

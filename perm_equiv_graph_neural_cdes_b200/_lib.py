@@ -47,6 +47,7 @@ SIGNATURES = {
     "pegncde_param_offsets": (c_int, [_DIMS, POINTER(c_int64)]),
     "pegncde_pack_adj": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pegncde_adj_stats": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P]),
+    "pegncde_build_adj": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P, _P, _P]),
     "pegncde_pack_x": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P]),
     "pegncde_workspace_bytes": (c_size_t, [_DIMS, c_int32, c_int32]),
     "pegncde_vf_fwd": (c_int, [_P, _DIMS, _CTL, _P, c_float, _P, _P, _P, c_size_t]),

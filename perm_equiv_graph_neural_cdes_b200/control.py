@@ -190,3 +190,40 @@ def pack_control(
     # keep the sources alive until the pack kernels have run (stream-ordered)
     pc._keepalive = (cad, cx)
     return pc
+
+
+def build_control(ts: torch.Tensor, snapshots: torch.Tensor, x_t: Optional[torch.Tensor] = None, device=None) -> PackedControl:
+    """Graph snapshots -> :class:`PackedControl` in one device pass (``pegncde_build_adj``): the fused replacement of
+    ``get_graph_interpolation_coeffs`` (src/configs/dataset_configs.py:147-173, 1073-1100), which stacks a time channel
+    onto ``A_k``, calls ``diffrax.backward_hermite_coefficients`` on the host and ships four ``[T-1,n,n,2]`` arrays.
+
+    ``snapshots``: ``[T,n,n]`` or ``[B,T,n,n]``; ``ts``: ``[T]`` or ``[B,T]``; ``x_t`` (optional node signals
+    ``[T,n,e]`` / ``[B,T,n,e]``): their coefficients are small and are built with :func:`backward_hermite_coefficients`."""
+    device = torch.device(device if device is not None else snapshots.device)
+    if device.type != "cuda":
+        raise RuntimeError("build_control needs a CUDA device: the fused path has no CPU fallback")
+    A = _as_batched(snapshots, 3).to(device=device, dtype=torch.float32).contiguous()
+    B, T, n = A.shape[0], A.shape[1], A.shape[2]
+    e = 0
+    cx = None
+    if x_t is not None:
+        xb = _as_batched(x_t, 3).to(device=device, dtype=torch.float32)
+        e = xb.shape[-1]
+        tsx = _as_batched(ts, 1).to(device=device, dtype=torch.float32).expand(B, T)
+        per = []
+        for b in range(B):
+            X = torch.stack([tsx[b][:, None, None].expand(T, n, e), xb[b]], dim=-1)
+            per.append(backward_hermite_coefficients(tsx[b], X))
+        cx = [torch.stack([per[b][i] for b in range(B)]).contiguous() for i in range(4)]
+    pc = PackedControl(B, n, T, e, device)
+    pc.ts.copy_(_as_batched(ts, 1).to(device=device, dtype=torch.float32).expand(B, T))
+    dims = pc.dims(h=4, L=1)
+    st = _stream_ptr(device)
+    l = lib()
+    check(l.pegncde_build_adj(st, dims, pc.ts.data_ptr(), A.data_ptr(), pc.adj_coef.data_ptr(), pc.adj_rowsum.data_ptr(),
+                              pc.adj_diag.data_ptr(), pc.adj_total.data_ptr(), pc.tch_coef.data_ptr()), "pegncde_build_adj")
+    if cx is not None:
+        check(l.pegncde_pack_x(st, dims, cx[0].data_ptr(), cx[1].data_ptr(), cx[2].data_ptr(), cx[3].data_ptr(),
+                               pc.x_coef.data_ptr()), "pegncde_pack_x")
+    pc._keepalive = (A, cx)
+    return pc

@@ -85,12 +85,15 @@ __device__ __forceinline__ void finalize_colsums(const ProducerOut& po, int b, i
 // reference layout: d,c,b,a each [B, T-1, n, n, 2], last axis (time, adjacency)
 // =====================================================================================
 
-// grid (nt*nt tiles, T-1, B), block 256: one block per 32x32 tile.  Source is either the reference layout
-// (d,c,b,a each [B,T-1,n,n,2]) or, for pegncde_adj_stats, the already tiled planes (tiled_in).
+// grid (nt*nt tiles, T-1, B), block 256: one block per 32x32 tile.  Source is the reference layout
+// (d,c,b,a each [B,T-1,n,n,2]), or the already tiled planes (tiled_in, pegncde_adj_stats), or the raw graph
+// snapshots A_k [B,T,n,n] + knot times (snap / ts, pegncde_build_adj: backward_hermite_coefficients fused in,
+// same operation order as the host formula so both routes give identical planes).
 // Reads are coalesced float2 rows of the source, writes are coalesced float4 of the 16-KB tile (staged in smem).
 __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, const float* __restrict__ cc,
                                                   const float* __restrict__ cb, const float* __restrict__ ca,
-                                                  const float* __restrict__ tiled_in, int n, int npad, int Tm1,
+                                                  const float* __restrict__ tiled_in, const float* __restrict__ snap,
+                                                  const float* __restrict__ ts, int n, int npad, int Tm1,
                                                   float* __restrict__ adj_coef, float* __restrict__ rowsum,
                                                   float* __restrict__ diag, float* __restrict__ total,
                                                   float* __restrict__ tch) {
@@ -103,7 +106,6 @@ __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, 
   const size_t slab = ((size_t)b * Tm1 + iv);
   const size_t tile_base = slab * 4 * (size_t)npad * npad + ((size_t)rt * nt + ct) * 4096;
   const float* src[4] = {ca, cb, cc, cd};  // (a,b,c,d) order
-  float tot[4] = {0.f, 0.f, 0.f, 0.f};
   float tsum[3] = {0.f, 0.f, 0.f};
   if (threadIdx.x < 96) tcol[threadIdx.x >> 5][lane] = 0.f;
   __syncthreads();
@@ -112,9 +114,29 @@ __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, 
       *reinterpret_cast<float4*>(&tile[4 * idx]) = *reinterpret_cast<const float4*>(tiled_in + tile_base + 4 * idx);
     __syncthreads();
   }
+  float dt = 1.f, dtp = 1.f;
+  if (snap) {
+    const float* tb = ts + (size_t)b * (Tm1 + 1);
+    dt = tb[iv + 1] - tb[iv];
+    dtp = iv > 0 ? tb[iv] - tb[iv - 1] : dt;
+  }
   for (int idx = threadIdx.x; idx < 1024; idx += 256) {
     const int r = idx >> 5, c = idx & 31;      // r is warp-uniform, c == lane
     const int i = rt * 32 + r, k = ct * 32 + c;
+    float hv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (snap && i < n && k < n) {
+      // diffrax.backward_hermite_coefficients per element: a = y_i, b = previous secant (first piece: own secant),
+      // c = 2 (m - b) / dt, d = -(m - b) / dt^2
+      const float* Ab = snap + ((size_t)b * (Tm1 + 1) * n + i) * (size_t)n + k;
+      const size_t knot = (size_t)n * n;
+      const float y0 = __ldg(Ab + (size_t)iv * knot), y1 = __ldg(Ab + (size_t)(iv + 1) * knot);
+      const float m = (y1 - y0) / dt;
+      const float bb = iv > 0 ? (y0 - __ldg(Ab + (size_t)(iv - 1) * knot)) / dtp : m;
+      hv[0] = y0;
+      hv[1] = bb;
+      hv[2] = 2.0f * (m - bb) / dt;
+      hv[3] = -(m - bb) / (dt * dt);
+    }
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       float v = 0.f;
@@ -122,6 +144,8 @@ __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, 
       if (i < n && k < n) {
         if (tiled_in) {
           v = tile[to];
+        } else if (snap) {
+          v = hv[p];
         } else {
           const float2 tv = __ldg(reinterpret_cast<const float2*>(src[p]) + (slab * n + i) * (size_t)n + k);
           v = tv.y;
@@ -130,11 +154,6 @@ __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, 
         if (i == k) diag[(slab * 4 + p) * n + i] = v;
       }
       if (!tiled_in) tile[to] = v;
-      const float rs = warp_sum(v);
-      if (lane == 0 && i < n) {
-        atomicAdd(&rowsum[(slab * 4 + p) * n + i], rs);
-        tot[p] += rs;
-      }
     }
   }
   if (!tiled_in) {
@@ -143,15 +162,57 @@ __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, 
     __syncthreads();
     for (int idx = threadIdx.x; idx < 1024; idx += 256)
       *reinterpret_cast<float4*>(adj_coef + tile_base + 4 * idx) = *reinterpret_cast<const float4*>(&tile[4 * idx]);
-    if (threadIdx.x < 96) {   // tch[b,iv,p,k] = mean over rows of the time channel (accumulated over the row tiles)
+    if (!snap && threadIdx.x < 96) {   // tch[b,iv,p,k] = mean over rows of the time channel (accumulated over the row tiles)
       const int p = threadIdx.x >> 5, k = ct * 32 + lane;
       if (k < n) atomicAdd(&tch[(slab * 3 + p) * n + k], tcol[p][lane] / (float)n);
     }
   }
+}
+
+// Row sums of the four tiled planes, deterministic: one block per 32-row tile walks the column tiles in order
+// (fixed-order warp reductions, no float atomics), so the packed control -- and every accept / reject decision of an
+// adaptive solve built on it -- is reproducible run to run.  grid (nt, T-1, B), block 256.
+__global__ void __launch_bounds__(256) k_adj_rowsums(const float* __restrict__ adj_coef, int n, int npad, int Tm1,
+                                                     float* __restrict__ rowsum) {
+  __shared__ __align__(16) float tile[4096];
+  const int b = blockIdx.z, iv = blockIdx.y, rt = blockIdx.x;
+  const int nt = npad >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t slab = (size_t)b * Tm1 + iv;
+  const float* base = adj_coef + slab * 4 * (size_t)npad * npad + (size_t)rt * nt * 4096;
+  float acc[4][4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) acc[p][rr] = 0.f;
+  for (int ct = 0; ct < nt; ++ct) {
+    for (int idx = threadIdx.x; idx < 1024; idx += 256)
+      *reinterpret_cast<float4*>(&tile[4 * idx]) = *reinterpret_cast<const float4*>(base + (size_t)ct * 4096 + 4 * idx);
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) acc[p][rr] += warp_sum(tile[peg_tile_off(4 * warp + rr, lane, p, 1)]);
+    __syncthreads();
+  }
   if (lane == 0) {
 #pragma unroll
-    for (int p = 0; p < 4; ++p) atomicAdd(&total[slab * 4 + p], tot[p]);
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int i = rt * 32 + 4 * warp + rr;
+        if (i < n) rowsum[(slab * 4 + p) * n + i] = acc[p][rr];
+      }
   }
+}
+
+// total[slab][p] = sum_i rowsum[slab][p][i] in a fixed order.  grid (slabs * 4), block 256.
+__global__ void __launch_bounds__(256) k_adj_totals(const float* __restrict__ rowsum, int n, float* __restrict__ total) {
+  __shared__ float sh[33];
+  const float* r = rowsum + (size_t)blockIdx.x * n;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) acc += r[i];
+  const float t = block_sum(acc, sh);
+  if (threadIdx.x == 0) total[blockIdx.x] = t;
 }
 
 __global__ void k_fill_tch_unit(float* __restrict__ tch, int n, size_t slabs) {

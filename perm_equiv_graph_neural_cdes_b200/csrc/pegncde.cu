@@ -491,22 +491,28 @@ size_t pegncde_workspace_bytes(const PegDims* dims, int32_t which, int32_t steps
 }
 
 static int pack_common(peg_stream_t stream, const PegDims* dims, const float* d, const float* c, const float* b,
-                       const float* a, const float* planar, float* adj_coef, float* adj_rowsum, float* adj_diag,
-                       float* adj_total, float* tch_coef) {
+                       const float* a, const float* planar, const float* snap, const float* ts, float* adj_coef,
+                       float* adj_rowsum, float* adj_diag, float* adj_total, float* tch_coef) {
   PEG_TRY(check_dims(dims));
   if (!adj_rowsum || !adj_diag || !adj_total || !tch_coef) return PEG_ERR_NULL_POINTER;
   cudaStream_t st = (cudaStream_t)stream;
   const int Tm1 = dims->T - 1;
   const size_t slabs = (size_t)dims->B * Tm1;
-  PEG_CUDA(cudaMemsetAsync(adj_total, 0, slabs * 4 * sizeof(float), st));
-  PEG_CUDA(cudaMemsetAsync(adj_rowsum, 0, slabs * 4 * dims->n * sizeof(float), st));
   const int nt = dims->ldn / 32;
   dim3 grid(nt * nt, Tm1, dims->B);
-  if (!planar) PEG_CUDA(cudaMemsetAsync(tch_coef, 0, slabs * 3 * dims->n * sizeof(float), st));
-  k_pack_adj<<<grid, 256, 0, st>>>(d, c, b, a, planar, dims->n, dims->ldn, Tm1, adj_coef, adj_rowsum, adj_diag,
+  const bool unit_time = planar || snap;   // no time channel in the source: d(time)/dt == 1
+  if (!unit_time) PEG_CUDA(cudaMemsetAsync(tch_coef, 0, slabs * 3 * dims->n * sizeof(float), st));
+  k_pack_adj<<<grid, 256, 0, st>>>(d, c, b, a, planar, snap, ts, dims->n, dims->ldn, Tm1, adj_coef, adj_rowsum, adj_diag,
                                    adj_total, tch_coef);
   PEG_LAUNCH_CHECK();
-  if (planar) {
+  {   // row sums and totals of the tiled planes, reduced in a fixed order (deterministic)
+    const float* tiled = planar ? planar : adj_coef;
+    k_adj_rowsums<<<dim3(nt, Tm1, dims->B), 256, 0, st>>>(tiled, dims->n, dims->ldn, Tm1, adj_rowsum);
+    PEG_LAUNCH_CHECK();
+    k_adj_totals<<<(unsigned)(slabs * 4), 256, 0, st>>>(adj_rowsum, dims->n, adj_total);
+    PEG_LAUNCH_CHECK();
+  }
+  if (unit_time) {
     const size_t cnt = slabs * 3 * dims->n;
     k_fill_tch_unit<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(tch_coef, dims->n, slabs);
     PEG_LAUNCH_CHECK();
@@ -518,14 +524,21 @@ int pegncde_pack_adj(peg_stream_t stream, const PegDims* dims, const float* d, c
                      const float* a, float* adj_coef, float* adj_rowsum, float* adj_diag, float* adj_total,
                      float* tch_coef) {
   if (!d || !c || !b || !a || !adj_coef) return PEG_ERR_NULL_POINTER;
-  return pack_common(stream, dims, d, c, b, a, nullptr, adj_coef, adj_rowsum, adj_diag, adj_total, tch_coef);
+  return pack_common(stream, dims, d, c, b, a, nullptr, nullptr, nullptr, adj_coef, adj_rowsum, adj_diag, adj_total, tch_coef);
 }
 
 int pegncde_adj_stats(peg_stream_t stream, const PegDims* dims, const float* adj_coef, float* adj_rowsum,
                       float* adj_diag, float* adj_total, float* tch_coef) {
   if (!adj_coef) return PEG_ERR_NULL_POINTER;
-  return pack_common(stream, dims, nullptr, nullptr, nullptr, nullptr, adj_coef, nullptr, adj_rowsum, adj_diag,
-                     adj_total, tch_coef);
+  return pack_common(stream, dims, nullptr, nullptr, nullptr, nullptr, adj_coef, nullptr, nullptr, nullptr, adj_rowsum,
+                     adj_diag, adj_total, tch_coef);
+}
+
+int pegncde_build_adj(peg_stream_t stream, const PegDims* dims, const float* ts, const float* snapshots, float* adj_coef,
+                      float* adj_rowsum, float* adj_diag, float* adj_total, float* tch_coef) {
+  if (!ts || !snapshots || !adj_coef) return PEG_ERR_NULL_POINTER;
+  return pack_common(stream, dims, nullptr, nullptr, nullptr, nullptr, nullptr, snapshots, ts, adj_coef, adj_rowsum,
+                     adj_diag, adj_total, tch_coef);
 }
 
 int pegncde_pack_x(peg_stream_t stream, const PegDims* dims, const float* d, const float* c, const float* b,
