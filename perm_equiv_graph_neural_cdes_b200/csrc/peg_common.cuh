@@ -128,4 +128,81 @@ struct Bump {
 };
 
 
+// ---- device helpers shared by the CUDA-core kernels (peg_kernels.cuh) and the tensor-core kernels (peg_tc.cu) ----
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sum over the whole block (blockDim.x * blockDim.y threads, multiple of 32, <= 1024); result valid in all threads
+__device__ __forceinline__ float block_sum(float v, float* sh /* >= 33 floats */) {
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nw = (blockDim.x * blockDim.y + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if ((tid & 31) == 0) sh[tid >> 5] = v;
+  __syncthreads();
+  if (tid < 32) {
+    float x = tid < nw ? sh[tid] : 0.f;
+    x = warp_sum(x);
+    if (tid == 0) sh[32] = x;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+// Fused-epilogue outputs of the kernels that PRODUCE the operand V of the next contraction:
+//   * V^T split into tf32 hi / lo, [B][d][npad] (the TMA-loaded K-major B operand of peg_tc.cu), zero padded;
+//   * column sums cb[b][0][c] = sum_i V[b,i,c], cb[b][1][c] = sum_i vec[b][i] V[b,i,c], reduced deterministically:
+//     every block writes its partial, the last block of a column group (ticket) adds them in block order.
+struct ProducerOut {
+  float* Thi;             // nullable
+  float* Tlo;
+  int npad;
+  float* cb;              // nullable
+  float* partial;         // [B][chunks][2][d]
+  unsigned int* tickets;  // self-resetting, one per (b, column group)
+  const float* vec;       // nullable; per-graph stride vec_stride
+  size_t vec_stride;
+};
+
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// called by ALL threads of the block after this block's partial sums for columns [c0, c0+ncols) have been written
+// to partial[b][chunk][*][c]; `is_last` must be a __shared__ bool.
+__device__ __forceinline__ void finalize_colsums(const ProducerOut& po, int b, int chunks, int d, int c0, int ncols,
+                                                 unsigned int* ticket, bool* is_last) {
+  __threadfence();
+  __syncthreads();
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    *is_last = (t == (unsigned int)chunks - 1u);
+    if (*is_last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (*is_last) {
+    __threadfence();
+    for (int c = tid; c < ncols; c += blockDim.x * blockDim.y) {
+      if (c0 + c >= d) continue;
+      float t0 = 0.f, t1 = 0.f;
+      for (int k = 0; k < chunks; ++k) {
+        const float* pk = po.partial + (((size_t)b * chunks + k) * 2) * d;
+        t0 += __ldcg(pk + c0 + c);
+        t1 += __ldcg(pk + d + c0 + c);
+      }
+      po.cb[((size_t)b * 2 + 0) * d + c0 + c] = t0;
+      po.cb[((size_t)b * 2 + 1) * d + c0 + c] = t1;
+    }
+  }
+}
+
+#endif  // __CUDACC__
+
 }  // namespace peg

@@ -521,6 +521,73 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+#define PEG_TC_TRY(expr)              \
+  do {                                \
+    int _rc = (expr);                 \
+    if (_rc != PEG_OK) return _rc;    \
+  } while (0)
+
+// Tensor maps of a K-major fp32 hi / lo operand pair [rows][cols] (cols contiguous), box = 32 cols x box_rows rows,
+// SWIZZLE_128B.  They depend only on (buffers, shape, box): a small per-thread cache keeps the driver call off the
+// hot path.  The returned pointers stay valid until 16 further distinct maps have been requested on this thread.
+static int get_maps(const float* hi, const float* lo, uint64_t cols, uint64_t rows, int box_rows, const CUtensorMap** mhi,
+                    const CUtensorMap** mlo) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return PEG_ERR_UNSUPPORTED;
+  struct MapKey { const void* hi; const void* lo; uint64_t rows, cols; int box; };
+  struct MapEntry { MapKey k; CUtensorMap mhi, mlo; bool valid; };
+  constexpr int NC = 16;
+  static thread_local MapEntry cache[NC];
+  static thread_local int cache_next = 0;
+  MapEntry* ent = nullptr;
+  for (int i = 0; i < NC; ++i)
+    if (cache[i].valid && cache[i].k.hi == hi && cache[i].k.lo == lo && cache[i].k.rows == rows && cache[i].k.cols == cols &&
+        cache[i].k.box == box_rows) { ent = &cache[i]; break; }
+  if (!ent) {
+    ent = &cache[cache_next];
+    cache_next = (cache_next + 1) % NC;
+    ent->valid = false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)cols * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int which = 0; which < 2; ++which) {
+      if (enc(which ? &ent->mlo : &ent->mhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)(which ? lo : hi), gdim, gstr, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+        fprintf(stderr, "pegncde: cuTensorMapEncodeTiled failed: dims %llu x %llu, box 32 x %d\n", (unsigned long long)cols,
+                (unsigned long long)rows, box_rows);
+        return PEG_ERR_CUDA;
+      }
+    }
+    ent->k = MapKey{hi, lo, rows, cols, box_rows};
+    ent->valid = true;
+  }
+  *mhi = &ent->mhi;
+  *mlo = &ent->mlo;
+  return PEG_OK;
+}
+
+// raises the dynamic-smem limit of a kernel once per device (the attribute is per function and device, NOT per thread)
+template <typename K>
+static int optin_smem(K kernel, std::atomic<unsigned>& done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { set_last_cuda((int)cudaGetLastError()); return PEG_ERR_CUDA; }
+  const unsigned bit = 1u << (dev & 31);
+  if ((done.load(std::memory_order_acquire) & bit) != 0u) return PEG_OK;
+  int lim = 0;
+  cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess) lim -= (int)fa.sharedSizeBytes;   // static smem counts against the limit
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "pegncde: cudaFuncSetAttribute(smem %d) failed: %s\n", lim, cudaGetErrorString(e));
+    set_last_cuda((int)e); (void)cudaGetLastError(); return PEG_ERR_CUDA;
+  }
+  done.fetch_or(bit, std::memory_order_release);
+  return PEG_OK;
+}
+
 static int pick_nd(int d, int maxnd) {
   for (int nd = maxnd; nd >= 32; nd -= 32)
     if (d % nd == 0) return nd;
@@ -558,8 +625,7 @@ static int tmem_cols_pow2(int cols) {
 int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const ContractArgs& a, bool bwd) {
   const int n = a.n, d = a.d, npad = w.npad;
   if (!w.Vt_hi || !w.Vt_lo) return PEG_ERR_WORKSPACE;
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return PEG_ERR_UNSUPPORTED;
+  if (!get_encode()) return PEG_ERR_UNSUPPORTED;
   if (!a.vt_ready) {
     dim3 grid(npad / 32, (d + 31) / 32, dm.B), block(32, 8);
     k_split_transpose<<<grid, block, 0, st>>>(a.V, n, d, npad, w.Vt_hi, w.Vt_lo);
@@ -592,59 +658,17 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   if (const char* ev = getenv("PEG_TC_EXPERIMENT")) p.experiment = atoi(ev);
   const size_t smem = (size_t)sa * a_bytes + (size_t)sb * b_bytes + 1024 + 8 * (2 * sa + 2 * sb + 2) + 64;
 
-  // tensor maps depend only on (buffer, rows, npad, box): a tiny per-thread cache keeps the driver call off the hot path
-  struct MapKey { const void* hi; const void* lo; uint64_t rows; int npad, nd; };
-  struct MapEntry { MapKey k; CUtensorMap mhi, mlo; bool valid; };
-  static thread_local MapEntry cache[8];
-  static thread_local int cache_next = 0;
-  const MapKey key = {w.Vt_hi, w.Vt_lo, (uint64_t)dm.B * d, npad, p.nd / cluster};
-  MapEntry* ent = nullptr;
-  for (int i = 0; i < 8; ++i)
-    if (cache[i].valid && cache[i].k.hi == key.hi && cache[i].k.lo == key.lo && cache[i].k.rows == key.rows &&
-        cache[i].k.npad == key.npad && cache[i].k.nd == key.nd) { ent = &cache[i]; break; }
-  if (!ent) {
-    ent = &cache[cache_next];
-    cache_next = (cache_next + 1) % 8;
-    ent->valid = false;
-    const cuuint64_t gdim[2] = {(cuuint64_t)npad, (cuuint64_t)dm.B * d};
-    const cuuint64_t gstr[1] = {(cuuint64_t)npad * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.nd / cluster)};
-    const cuuint32_t estr[2] = {1, 1};
-    if (enc(&ent->mhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w.Vt_hi, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
-      fprintf(stderr, "pegncde: cuTensorMapEncodeTiled failed: dims %d x %llu, box 32 x %d\n", npad, (unsigned long long)dm.B * d, p.nd / cluster);
-      return PEG_ERR_CUDA;
-    }
-    if (enc(&ent->mlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w.Vt_lo, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
-      fprintf(stderr, "pegncde: cuTensorMapEncodeTiled failed: dims %d x %llu, box 32 x %d\n", npad, (unsigned long long)dm.B * d, p.nd / cluster);
-      return PEG_ERR_CUDA;
-    }
-    ent->k = key;
-    ent->valid = true;
-  }
-  const CUtensorMap& mhi = ent->mhi;
-  const CUtensorMap& mlo = ent->mlo;
+  const CUtensorMap* mhi_p = nullptr;
+  const CUtensorMap* mlo_p = nullptr;
+  PEG_TC_TRY(get_maps(w.Vt_hi, w.Vt_lo, (uint64_t)npad, (uint64_t)dm.B * d, p.nd / cluster, &mhi_p, &mlo_p));
+  const CUtensorMap& mhi = *mhi_p;
+  const CUtensorMap& mlo = *mlo_p;
 
   dim3 grid((nblk + cluster - 1) / cluster * cluster, d / p.nd, dm.B);   // padded row blocks only keep the cluster in lockstep
-  // dynamic-smem opt-in: the attribute is per function and device (NOT per thread -- autograd launches from its own
-  // worker thread), so it is raised once per device to the device limit and never lowered
   {
-    static std::atomic<unsigned> optin_done[2] = {{0u}, {0u}};   // bit = device ordinal (< 32)
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { set_last_cuda((int)cudaGetLastError()); return PEG_ERR_CUDA; }
-    const unsigned bit = 1u << (dev & 31);
-    if ((optin_done[bwd ? 1 : 0].load(std::memory_order_acquire) & bit) == 0u) {
-      int lim = 0;
-      cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-      const cudaError_t e = bwd ? cudaFuncSetAttribute(k_tc_contract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)
-                                : cudaFuncSetAttribute(k_tc_contract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-      if (e != cudaSuccess) {
-        fprintf(stderr, "pegncde: cudaFuncSetAttribute(smem %d) failed: %s\n", lim, cudaGetErrorString(e));
-        set_last_cuda((int)e); (void)cudaGetLastError(); return PEG_ERR_CUDA;
-      }
-      optin_done[bwd ? 1 : 0].fetch_or(bit, std::memory_order_release);
-    }
+    static std::atomic<unsigned> done[2] = {{0u}, {0u}};
+    if (bwd) PEG_TC_TRY(optin_smem(k_tc_contract<true>, done[1]));
+    else PEG_TC_TRY(optin_smem(k_tc_contract<false>, done[0]));
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -667,6 +691,335 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
     set_last_cuda((int)le); (void)cudaGetLastError(); return PEG_ERR_CUDA;
   }
   if (cudaPeekAtLastError() != cudaSuccess) { set_last_cuda((int)cudaGetLastError()); return PEG_ERR_CUDA; }
+  return PEG_OK;
+}
+
+
+// ==========================================================================================
+// RMSNorm -> Linear on tcgen05 (3xTF32):  M = rinv (Z Wn^T) + cvec,  Wn = W diag(norm.weight),
+// cvec = W norm.bias + bias (tc_prep_weights), rinv = rsqrt(mean z^2 + eps) per node.
+// One CTA per 128 nodes x ND outputs: M = 128 (nodes), N = ND, K = din in chunks of 32.
+//   warps 0-7 : load Z rows (coalesced LDG.128, all K chunks of a 128-wide super chunk in flight at once), accumulate
+//               sum z^2, 3xTF32-split into the swizzled K-major A tiles; afterwards the epilogue (tcgen05.ld):
+//               norm scale + bias, M, V^T hi/lo (coalesced: lane = node), deterministic column sums, optional N
+//   warp 8    : TMA producer of the weight tiles (hi / lo, SWIZZLE_128B);  warp 9: TMEM allocator + MMA issuer
+// grid (ceil(n/128), dout/ND, B), block 320
+// ==========================================================================================
+constexpr int NL_THREADS = 320;
+
+struct NlParams {
+  const float* Z;      // [B,n,din]
+  const float* cvec;   // [dout]
+  const float* nw;     // norm weight / bias (only for Nout)
+  const float* nb;
+  float* M;            // [B,n,dout]
+  float* Nout;         // nullable [B,n,din]
+  ProducerOut po;
+  int n, din, dout, nd, stages, tmem_cols, nsplit;
+};
+
+__global__ void __launch_bounds__(NL_THREADS, 1)
+k_tc_norm_linear(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const NlParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ float rinv_s[128];
+  __shared__ bool is_last;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z, rb = blockIdx.x, ntile = blockIdx.y;
+  const int n = p.n, din = p.din, dout = p.dout, nd = p.nd, S = p.stages;
+  const bool split = p.nsplit == 3;
+  const int row0 = rb * 128;
+  const int nchunks = din >> 5;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int a_bytes = (split ? 2 : 1) * TC_ATILE;
+  const int b_tile = nd * TC_BK * 4;
+  const int b_bytes = (split ? 2 : 1) * b_tile;
+  const int stage_bytes = a_bytes + b_bytes;
+  const uint32_t bar_base = smem_base + S * stage_bytes;
+  auto full_a = [&](int s) { return bar_base + 8u * s; };
+  auto full_b = [&](int s) { return bar_base + 8u * (S + s); };
+  auto empty = [&](int s) { return bar_base + 8u * (2 * S + s); };
+  const uint32_t accum_bar = bar_base + 8u * (3 * S);
+  const uint32_t tmem_slot = accum_bar + 8u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* csum = reinterpret_cast<float*>(smem_gen);   // [4 row quarters][2][nd]: reuses stage 0 after the MMAs are done
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_a(s), 256);
+      mbar_init(full_b(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  const float* Zb = p.Z + (size_t)b * n * din;
+
+  if (warp < 8) {
+    // ---- loaders / converters: thread -> rows 32 i + (tid >> 3), 16-byte chunk (tid & 7) of every K chunk ----
+    const int lr = tid >> 3, lc = tid & 7;
+    float rsq[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int sc0 = 0; sc0 < nchunks; sc0 += 4) {
+      float4 buf[4][4];
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = row0 + 32 * i + lr;
+          buf[kc][i] = (sc0 + kc < nchunks && row < n) ? __ldg(reinterpret_cast<const float4*>(Zb + (size_t)row * din + (sc0 + kc) * 32 + lc * 4))
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        const int j = sc0 + kc;
+        if (j >= nchunks) break;
+        const int st = j % S;
+        mbar_wait(empty(st), ((uint32_t)(j / S) & 1u) ^ 1u);
+        const uint32_t a_base = smem_base + st * stage_bytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = buf[kc][i];
+          rsq[i] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, rsq[i]))));
+          const int r = 32 * i + lr;
+          const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((lc ^ (r & 7)) << 4);
+          const float h0 = tf32_rna(v.x), h1 = tf32_rna(v.y), h2 = tf32_rna(v.z), h3 = tf32_rna(v.w);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + off), "f"(h0), "f"(h1), "f"(h2), "f"(h3) : "memory");
+          if (split)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + TC_ATILE + off), "f"(v.x - h0), "f"(v.y - h1),
+                         "f"(v.z - h2), "f"(v.w - h3) : "memory");
+        }
+        fence_proxy_async();
+        mbar_arrive(full_a(st));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {   // the 8 lanes that share a row
+      float v = rsq[i];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      if (lc == 0) rinv_s[32 * i + lr] = rsqrtf(v / (float)din + 1e-5f);
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      const int wrow0 = ntile * nd;
+      for (int j = 0; j < nchunks; ++j) {
+        const int st = j % S;
+        mbar_wait(empty(st), ((uint32_t)(j / S) & 1u) ^ 1u);
+        const uint32_t b_base = smem_base + st * stage_bytes + a_bytes;
+        mbar_expect_tx(full_b(st), (uint32_t)b_bytes);
+        tma_load_2d(b_base, &map_hi, j * TC_BK, wrow0, full_b(st));
+        if (split) tma_load_2d(b_base + b_tile, &map_lo, j * TC_BK, wrow0, full_b(st));
+      }
+    }
+  } else {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nd >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int j = 0; j < nchunks; ++j) {
+        const int st = j % S;
+        const uint32_t ph = (uint32_t)(j / S) & 1u;
+        mbar_wait(full_b(st), ph);
+        mbar_wait(full_a(st), ph);
+        tc_fence_after();
+        const uint32_t ahi = smem_base + st * stage_bytes, alo = ahi + TC_ATILE;
+        const uint32_t bhi = ahi + a_bytes, blo = bhi + b_tile;
+#pragma unroll
+        for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+          const uint64_t dah = make_desc_sw128(ahi + k8 * 32), dbh = make_desc_sw128(bhi + k8 * 32);
+          umma_tf32(tmem_base, dah, dbh, idesc, (j > 0 || k8 > 0) ? 1u : 0u);
+          if (split) {
+            umma_tf32(tmem_base, make_desc_sw128(alo + k8 * 32), dbh, idesc, 1u);
+            umma_tf32(tmem_base, dah, make_desc_sw128(blo + k8 * 32), idesc, 1u);
+          }
+        }
+        umma_commit(empty(st));
+      }
+      umma_commit(accum_bar);
+    }
+  }
+
+  // ---- epilogue (warps 0-7): TMEM lane = node, columns = outputs ----
+  if (warp < 8) {
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // rinv_s complete (loader warps only)
+    mbar_wait(accum_bar, 0u);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane, gi = row0 + row;
+    const bool rowok = gi < n;
+    const float ri = rinv_s[row];
+    const float vv = (p.po.vec && rowok) ? p.po.vec[(size_t)b * p.po.vec_stride + gi] : 0.f;
+    float* Mrow = p.M + ((size_t)b * n + (rowok ? gi : 0)) * dout;
+    const int cols_per_half = nd / 2;
+    for (int cc = 0; cc < cols_per_half; cc += 16) {
+      const int col = half * cols_per_half + cc, gc = ntile * nd + col;
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
+      tmem_wait_ld();
+      float m[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) m[u] = rowok ? fmaf(ri, __uint_as_float(r[u]), __ldg(p.cvec + gc + u)) : 0.f;
+      if (rowok) {
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4)
+          *reinterpret_cast<float4*>(Mrow + gc + 4 * v4) = make_float4(m[4 * v4], m[4 * v4 + 1], m[4 * v4 + 2], m[4 * v4 + 3]);
+      }
+      if (p.po.Thi != nullptr && gi < p.po.npad) {   // V^T hi/lo: the 32 lanes of a warp are 32 consecutive nodes
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const float hi = tf32_rna(m[u]);
+          const size_t o = ((size_t)b * dout + gc + u) * p.po.npad + gi;
+          p.po.Thi[o] = hi;
+          p.po.Tlo[o] = m[u] - hi;
+        }
+      }
+      if (p.po.cb != nullptr) {   // column sums over this warp's 32 nodes (fixed shuffle order)
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          float s0 = m[u], s1 = vv * m[u];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          }
+          if (lane == 0) {
+            csum[(q * 2 + 0) * nd + col + u] = s0;
+            csum[(q * 2 + 1) * nd + col + u] = s1;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    if (p.Nout != nullptr && ntile == 0) {   // normalised input, needed by the weight gradient
+      float* Nb = p.Nout + (size_t)b * n * din;
+      const int lr = tid >> 3, lc = tid & 7;
+      for (int i = 0; i < 4; ++i) {
+        const int rr = 32 * i + lr, rowg = row0 + rr;
+        if (rowg >= n) continue;
+        const float rv = rinv_s[rr];
+        for (int k = lc * 4; k < din; k += 32) {
+          const float4 z4 = __ldg(reinterpret_cast<const float4*>(Zb + (size_t)rowg * din + k));
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.nw + k)), t4 = __ldg(reinterpret_cast<const float4*>(p.nb + k));
+          *reinterpret_cast<float4*>(Nb + (size_t)rowg * din + k) =
+              make_float4(z4.x * rv * s4.x + t4.x, z4.y * rv * s4.y + t4.y, z4.z * rv * s4.z + t4.z, z4.w * rv * s4.w + t4.w);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (p.po.cb != nullptr) {
+    const int chunks = gridDim.x;
+    if (tid < nd) {
+      float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { t0 += csum[(q * 2 + 0) * nd + tid]; t1 += csum[(q * 2 + 1) * nd + tid]; }
+      float* part = p.po.partial + (((size_t)b * chunks + rb) * 2) * dout;
+      part[ntile * nd + tid] = t0;
+      part[dout + ntile * nd + tid] = t1;
+    }
+    finalize_colsums(p.po, b, chunks, dout, ntile * nd, nd, p.po.tickets + (size_t)b * gridDim.y + ntile, &is_last);
+  }
+  if (warp == 9) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+  }
+}
+
+// weights of one layer -> Wn hi/lo [dout][din] and cvec [dout].  grid (dout), block 128
+__global__ void __launch_bounds__(128) k_prep_weights(const float* __restrict__ W, const float* __restrict__ bias,
+                                                      const float* __restrict__ nw, const float* __restrict__ nb, int din,
+                                                      float* __restrict__ Wn_hi, float* __restrict__ Wn_lo, float* __restrict__ cvec) {
+  __shared__ float sh[33];
+  const int o = blockIdx.x;
+  float c = 0.f;
+  for (int k = threadIdx.x; k < din; k += 128) {
+    const float w = W[(size_t)o * din + k];
+    const float wn = w * nw[k];
+    const float hi = tf32_rna(wn);
+    Wn_hi[(size_t)o * din + k] = hi;
+    Wn_lo[(size_t)o * din + k] = wn - hi;
+    c = fmaf(nb[k], w, c);
+  }
+  const float t = block_sum(c, sh);
+  if (threadIdx.x == 0) cvec[o] = t + bias[o];
+}
+
+void tc_carve_linear(Bump& bp, const PegDims& d, const Model& m, TcLinear& w) {
+  memset(&w, 0, sizeof(w));
+  if ((d.flags & PEG_FLAG_TENSOR_CORES) == 0) return;
+  for (int l = 0; l < m.L; ++l) {
+    const size_t cnt = (size_t)m.layer[l].dout * m.layer[l].din;
+    w.Wn_hi[l] = bp.take<float>(cnt);
+    w.Wn_lo[l] = bp.take<float>(cnt);
+    w.cvec[l] = bp.take<float>(m.layer[l].dout);
+  }
+  w.ready = true;
+}
+
+static int nl_pick_nd(int dout) {
+  for (int nd = 256; nd >= 32; nd -= 32)
+    if (dout % nd == 0) return nd;
+  return 0;
+}
+
+bool tc_linear_supported(int din, int dout) {
+  if (getenv("PEG_TC_NO_LINEAR")) return false;
+  return din % 32 == 0 && din >= 32 && nl_pick_nd(dout) != 0 && get_encode() != nullptr;
+}
+
+int tc_prep_weights(cudaStream_t st, const Model& m, const float* params, const TcLinear& w) {
+  if (!w.ready) return PEG_OK;
+  for (int l = 0; l < m.L; ++l) {
+    const LayerDesc& ld = m.layer[l];
+    if (!tc_linear_supported(ld.din, ld.dout)) continue;
+    k_prep_weights<<<ld.dout, 128, 0, st>>>(params + ld.w_off, params + ld.b_off, params + ld.nw_off, params + ld.nb_off, ld.din,
+                                            w.Wn_hi[l], w.Wn_lo[l], w.cvec[l]);
+    if (cudaPeekAtLastError() != cudaSuccess) { set_last_cuda((int)cudaGetLastError()); return PEG_ERR_CUDA; }
+  }
+  return PEG_OK;
+}
+
+int tc_norm_linear(cudaStream_t st, const PegDims& dm, const TcLinear& w, int layer, const float* Z, int din, int dout,
+                   const float* nw, const float* nb, float* M, float* Nout, const ProducerOut& po) {
+  if (!w.ready) return PEG_ERR_WORKSPACE;
+  NlParams p;
+  memset(&p, 0, sizeof(p));
+  p.Z = Z; p.cvec = w.cvec[layer]; p.nw = nw; p.nb = nb; p.M = M; p.Nout = Nout; p.po = po;
+  p.n = dm.n; p.din = din; p.dout = dout;
+  p.nd = nl_pick_nd(dout);
+  p.nsplit = (dm.flags & PEG_FLAG_TF32_FAST) ? 1 : 3;
+  const int sp = p.nsplit == 3 ? 2 : 1;
+  const int stage_bytes = sp * TC_ATILE + sp * p.nd * TC_BK * 4;
+  int stages = (200 * 1024) / stage_bytes;
+  const int nchunks = din / 32;
+  stages = stages > nchunks ? nchunks : stages;
+  stages = stages > 4 ? 4 : stages;
+  if (stages < 1) return PEG_ERR_UNSUPPORTED;
+  p.stages = stages;
+  p.tmem_cols = tmem_cols_pow2(p.nd);
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (3 * stages + 2) + 64;
+  const CUtensorMap* mhi = nullptr;
+  const CUtensorMap* mlo = nullptr;
+  PEG_TC_TRY(get_maps(w.Wn_hi[layer], w.Wn_lo[layer], (uint64_t)din, (uint64_t)dout, p.nd, &mhi, &mlo));
+  static std::atomic<unsigned> done{0u};
+  PEG_TC_TRY(optin_smem(k_tc_norm_linear, done));
+  dim3 grid((dm.n + 127) / 128, dout / p.nd, dm.B);
+  k_tc_norm_linear<<<grid, NL_THREADS, smem, st>>>(*mhi, *mlo, p);
+  if (cudaPeekAtLastError() != cudaSuccess) {
+    const cudaError_t e = cudaGetLastError();
+    fprintf(stderr, "pegncde: k_tc_norm_linear launch failed (%s): grid %u x %u x %u, smem %zu, nd %d, stages %d\n",
+            cudaGetErrorString(e), grid.x, grid.y, grid.z, smem, p.nd, stages);
+    set_last_cuda((int)e);
+    return PEG_ERR_CUDA;
+  }
   return PEG_OK;
 }
 

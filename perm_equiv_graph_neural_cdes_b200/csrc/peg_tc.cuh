@@ -12,7 +12,24 @@ struct TcWs {
   int npad;
 };
 
+// per-layer tf32 hi/lo copies of the Linear weights (built once per API call by tc_prep_weights):
+//   Wn = W diag(norm.weight)  [dout][din]  (B operand of RMSNorm -> Linear; the norm scale rides in the epilogue)
+//   cvec[o] = sum_k norm.bias[k] W[o][k] + bias[o]
+struct TcLinear {
+  float* Wn_hi[PEG_MAX_LAYERS];
+  float* Wn_lo[PEG_MAX_LAYERS];
+  float* cvec[PEG_MAX_LAYERS];
+  bool ready;   // carved (tensor-core flag set)
+};
+
 void tc_carve(Bump& bp, const PegDims& d, int dmax, TcWs& w);
+void tc_carve_linear(Bump& bp, const PegDims& d, const Model& m, TcLinear& w);
+bool tc_linear_supported(int din, int dout);
+// splits the weights of every layer (enqueue only); call once per API entry before the first evaluation
+int tc_prep_weights(cudaStream_t st, const Model& m, const float* params, const TcLinear& w);
+// M = rmsnorm(Z) W^T + b on tcgen05 (3xTF32), fused producer outputs as k_norm_linear (peg_kernels.cuh)
+int tc_norm_linear(cudaStream_t st, const PegDims& d, const TcLinear& w, int layer, const float* Z, int din, int dout,
+                   const float* nw, const float* nb, float* M, float* Nout, const ProducerOut& po);
 bool tc_supported(const PegDims& d, int dcols);
 int tc_contract(cudaStream_t st, const PegDims& d, const TcWs& w, const ContractArgs& a, bool bwd);
 int tc_launches_per_contract(bool bwd);

@@ -131,6 +131,7 @@ struct FevalWs {
   float* N;      // [B,n,h]
   float* gxd;    // [B,n,2e] cotangent of control_data.derivative(t) (solve_bwd with g_xcoef)
   TcWs tc;       // tensor-core operand buffers (peg_tc.cuh)
+  TcLinear lin;  // tf32 hi/lo copies of the Linear weights (tensor-core RMSNorm -> Linear)
 };
 
 static void carve_feval(Bump& bp, const PegDims& d, const Model& m, bool vjp, FevalWs& w) {
@@ -155,6 +156,7 @@ static void carve_feval(Bump& bp, const PegDims& d, const Model& m, bool vjp, Fe
     w.Obar = w.Mbar = w.N = w.gxd = nullptr;
   }
   tc_carve(bp, d, m.dmax, w.tc);
+  tc_carve_linear(bp, d, m, w.lin);
 }
 
 struct Ctx {
@@ -207,6 +209,11 @@ static ProducerOut producer_out(Ctx& c, int dcols, bool want_vt, float* cb, bool
 
 static int norm_linear(Ctx& c, int l, const float* Zin, float* M, float* Nout, const ProducerOut& po) {
   const LayerDesc& ld = c.m.layer[l];
+  if (c.use_tc && c.w.lin.ready && tc_linear_supported(ld.din, ld.dout)) {
+    const int rc = tc_norm_linear(c.st, c.d, c.w.lin, l, Zin, ld.din, ld.dout, c.params + ld.nw_off, c.params + ld.nb_off, M, Nout, po);
+    if (rc == PEG_OK) g_launches.fetch_add(1);
+    return rc;
+  }
   dim3 grid((c.d.n + NL_BM - 1) / NL_BM, (ld.dout + NL_BN - 1) / NL_BN, c.d.B);
   k_norm_linear<<<grid, 256, 0, c.st>>>(Zin, c.d.n, ld.din, ld.dout, c.params + ld.w_off, c.params + ld.b_off,
                                         c.params + ld.nw_off, c.params + ld.nb_off, M, Nout, po);
@@ -405,8 +412,14 @@ static int make_ctx(Ctx& c, peg_stream_t stream, const PegDims* dims, const PegC
   return PEG_OK;
 }
 
+// start of every compute entry point: arrival counters zeroed, tensor-core weight copies refreshed (params may have
+// changed since the previous call; the copies live in the caller's workspace)
 static int reset_tickets(Ctx& c) {
   PEG_CUDA(cudaMemsetAsync(c.w.tickets, 0, c.w.tickets_count * sizeof(unsigned int), c.st));
+  if (c.use_tc) {
+    PEG_TRY(tc_prep_weights(c.st, c.m, c.params, c.w.lin));
+    g_launches.fetch_add(c.m.L);
+  }
   return PEG_OK;
 }
 

@@ -452,7 +452,10 @@ def test_tgb_model_trains_its_data_encoder(cuda):
 @pytest.mark.parametrize("cls,with_derivative", [("GraphVectorField", True), ("GNODEVectorField", False)])
 @pytest.mark.parametrize("flags", [0, TC], ids=["ffma", "tcgen05"])
 def test_sibling_vector_fields_against_oracle(cuda, cls, with_derivative, flags):
-    p = R.make_problem(n=140 if flags else 33, h=32, e=0, L=3, T=4, t1=3, dt0=0.25, seed=17)
+    # Few steps on purpose: the exact gradient of a ReLU network jumps when a hidden unit sits within rounding distance
+    # of its kink (seed 17 with 12 steps has one such unit: a 1e-7 perturbation of y0 moves d loss / d y0 by 7e-3 in
+    # the fp32 CUDA-core path too), and the chance of meeting one grows with units x stages x steps.
+    p = R.make_problem(n=140 if flags else 33, h=32, e=0, L=3, T=4, t1=3, dt0=0.75, seed=19)
     vf = getattr(P, cls)(p.h, p.h, p.h, p.L, 0, p.n, key=0)
     with torch.no_grad():
         for mine, lp in zip(vf.gnn_layers, p.layers):
@@ -464,13 +467,13 @@ def test_sibling_vector_fields_against_oracle(cuda, cls, with_derivative, flags)
     ts = p.ts.to(torch.float32).to(cuda)
     ca = P.CubicInterpolation(ts, tuple(c.to(cuda) for c in p.coeffs_adj))
     y0 = p.y0.to(cuda).requires_grad_(True)
-    sol = P.diffeqsolve(P.ODETerm(vf), P.Tsit5(), 0.0, 3.0, 0.25, y0, ca)
+    sol = P.diffeqsolve(P.ODETerm(vf), P.Tsit5(), 0.0, 3.0, 0.75, y0, ca)
     (sol.ys[-1] * p.gyT.to(cuda)).sum().backward()
     p64 = R.problem_to(p, torch.float64)
     layers = R.params_to(p64.layers, requires_grad=True)
     c64 = R.CubicInterpolation(p64.ts, p64.coeffs_adj)
     y64 = p64.y0.clone().requires_grad_(True)
-    yT = R.tsit5_solve_fixed(lambda t, y: R.plain_graph_vector_field(t, y, c64, layers, with_derivative), y64, R.constant_step_table(0.0, 3.0, 0.25))
+    yT = R.tsit5_solve_fixed(lambda t, y: R.plain_graph_vector_field(t, y, c64, layers, with_derivative), y64, R.constant_step_table(0.0, 3.0, 0.75))
     (yT * p64.gyT).sum().backward()
     assert rel_err(sol.ys[-1], yT) < TOL_Y
     assert rel_err(y0.grad, y64.grad) < TOL_G
