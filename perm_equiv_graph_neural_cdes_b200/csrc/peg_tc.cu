@@ -705,6 +705,37 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
 //   warp 8    : TMA producer of the weight tiles (hi / lo, SWIZZLE_128B);  warp 9: TMEM allocator + MMA issuer
 // grid (ceil(n/128), dout/ND, B), block 320
 // ==========================================================================================
+// Sums, over the 32 lanes of a warp, 16 per-lane values at once with a transpose-reduce butterfly (16 shuffles instead
+// of 80): on return v[0] of lane L holds the full sum of column warp_col16(L) (each column lands in two lanes).
+// Fixed order, hence deterministic.
+__device__ __forceinline__ int warp_col16(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+__device__ __forceinline__ void warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = (lane & 16) != 0;
+    const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = (lane & 8) != 0;
+    const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = (lane & 4) != 0;
+    const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const bool up = (lane & 2) != 0;
+    const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 constexpr int NL_THREADS = 320;
 
 struct NlParams {
@@ -880,19 +911,15 @@ k_tc_norm_linear(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
           p.po.Tlo[o] = m[u] - hi;
         }
       }
-      if (p.po.cb != nullptr) {   // column sums over this warp's 32 nodes (fixed shuffle order)
+      if (p.po.cb != nullptr) {   // column sums over this warp's 32 nodes (fixed butterfly order)
+        float s1[16];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          float s0 = m[u], s1 = vv * m[u];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-          }
-          if (lane == 0) {
-            csum[(q * 2 + 0) * nd + col + u] = s0;
-            csum[(q * 2 + 1) * nd + col + u] = s1;
-          }
+        for (int u = 0; u < 16; ++u) s1[u] = vv * m[u];
+        warp_colsum16(m, lane);
+        warp_colsum16(s1, lane);
+        if ((lane & 1) == 0) {
+          csum[(q * 2 + 0) * nd + col + warp_col16(lane)] = m[0];
+          csum[(q * 2 + 1) * nd + col + warp_col16(lane)] = s1[0];
         }
       }
     }
@@ -936,9 +963,10 @@ k_tc_norm_linear(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
 // weights of one layer -> Wn hi/lo [dout][din] and cvec [dout].  grid (dout), block 128
 __global__ void __launch_bounds__(128) k_prep_weights(const float* __restrict__ W, const float* __restrict__ bias,
                                                       const float* __restrict__ nw, const float* __restrict__ nb, int din,
-                                                      float* __restrict__ Wn_hi, float* __restrict__ Wn_lo, float* __restrict__ cvec) {
+                                                      float* __restrict__ Wn_hi, float* __restrict__ Wn_lo, float* __restrict__ cvec,
+                                                      float* __restrict__ Wt_hi, float* __restrict__ Wt_lo) {
   __shared__ float sh[33];
-  const int o = blockIdx.x;
+  const int o = blockIdx.x, dout = gridDim.x;
   float c = 0.f;
   for (int k = threadIdx.x; k < din; k += 128) {
     const float w = W[(size_t)o * din + k];
@@ -946,6 +974,9 @@ __global__ void __launch_bounds__(128) k_prep_weights(const float* __restrict__ 
     const float hi = tf32_rna(wn);
     Wn_hi[(size_t)o * din + k] = hi;
     Wn_lo[(size_t)o * din + k] = wn - hi;
+    const float wh = tf32_rna(w);
+    Wt_hi[(size_t)k * dout + o] = wh;
+    Wt_lo[(size_t)k * dout + o] = w - wh;
     c = fmaf(nb[k], w, c);
   }
   const float t = block_sum(c, sh);
@@ -960,6 +991,8 @@ void tc_carve_linear(Bump& bp, const PegDims& d, const Model& m, TcLinear& w) {
     w.Wn_hi[l] = bp.take<float>(cnt);
     w.Wn_lo[l] = bp.take<float>(cnt);
     w.cvec[l] = bp.take<float>(m.layer[l].dout);
+    w.Wt_hi[l] = bp.take<float>(cnt);
+    w.Wt_lo[l] = bp.take<float>(cnt);
   }
   w.ready = true;
 }
@@ -979,9 +1012,9 @@ int tc_prep_weights(cudaStream_t st, const Model& m, const float* params, const 
   if (!w.ready) return PEG_OK;
   for (int l = 0; l < m.L; ++l) {
     const LayerDesc& ld = m.layer[l];
-    if (!tc_linear_supported(ld.din, ld.dout)) continue;
+    if (!tc_linear_supported(ld.din, ld.dout) && !tc_linear_bwd_supported(ld.din, ld.dout)) continue;
     k_prep_weights<<<ld.dout, 128, 0, st>>>(params + ld.w_off, params + ld.b_off, params + ld.nw_off, params + ld.nb_off, ld.din,
-                                            w.Wn_hi[l], w.Wn_lo[l], w.cvec[l]);
+                                            w.Wn_hi[l], w.Wn_lo[l], w.cvec[l], w.Wt_hi[l], w.Wt_lo[l]);
     if (cudaPeekAtLastError() != cudaSuccess) { set_last_cuda((int)cudaGetLastError()); return PEG_ERR_CUDA; }
   }
   return PEG_OK;
@@ -1017,6 +1050,299 @@ int tc_norm_linear(cudaStream_t st, const PegDims& dm, const TcLinear& w, int la
     const cudaError_t e = cudaGetLastError();
     fprintf(stderr, "pegncde: k_tc_norm_linear launch failed (%s): grid %u x %u x %u, smem %zu, nd %d, stages %d\n",
             cudaGetErrorString(e), grid.x, grid.y, grid.z, smem, p.nd, stages);
+    set_last_cuda((int)e);
+    return PEG_ERR_CUDA;
+  }
+  return PEG_OK;
+}
+
+
+// ==========================================================================================
+// Backward of Linear + RMSNorm wrt the layer input on tcgen05 (3xTF32):
+//   Nbar = Mbar W   (M = 128 nodes, N = din, K = dout in chunks of 32; A = Mbar rows converted in flight, B = W^T hi/lo by TMA)
+//   Zbar = rinv w Nbar - z rinv^3 <w Nbar, z> / din ; optional ReLU mask (z > 0) ; g_nw += sum Nbar zhat ; g_nb += sum Nbar
+// plus the producer outputs of Zbar (V^T hi/lo, deterministic column sums) for the next adjoint contraction.
+// A thread of the epilogue owns one node: the per-node reductions are thread-local apart from one exchange between the
+// two column halves; per-column reductions use the butterfly above.  grid (ceil(n/128), 1, B), block 320
+// ==========================================================================================
+struct LbParams {
+  const float* Mbar;   // [B,n,dout]
+  const float* Z;      // [B,n,din]
+  const float* nw;     // [din]
+  float* Zbar;         // [B,n,din]
+  float* g_nw;
+  float* g_nb;
+  ProducerOut po;
+  int n, din, dout, stages, tmem_cols, nsplit, relu_mask;
+};
+
+__global__ void __launch_bounds__(NL_THREADS, 1)
+k_tc_linear_bwd(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const LbParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ float red_s[2][2][128];   // [column half][ss, dot][node]
+  __shared__ bool is_last;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z, rb = blockIdx.x;
+  const int n = p.n, din = p.din, dout = p.dout, nd = din, S = p.stages;
+  const bool split = p.nsplit == 3;
+  const int row0 = rb * 128;
+  const int nchunks = dout >> 5;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int a_bytes = (split ? 2 : 1) * TC_ATILE;
+  const int b_tile = nd * TC_BK * 4;
+  const int b_bytes = (split ? 2 : 1) * b_tile;
+  const int stage_bytes = a_bytes + b_bytes;
+  const uint32_t bar_base = smem_base + S * stage_bytes;
+  auto full_a = [&](int s) { return bar_base + 8u * s; };
+  auto full_b = [&](int s) { return bar_base + 8u * (S + s); };
+  auto empty = [&](int s) { return bar_base + 8u * (2 * S + s); };
+  const uint32_t accum_bar = bar_base + 8u * (3 * S);
+  const uint32_t tmem_slot = accum_bar + 8u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* csum = reinterpret_cast<float*>(smem_gen);   // [4 row quarters][4 sums][din]: reuses stage 0 after the MMAs
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_a(s), 256);
+      mbar_init(full_b(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  const float* Mb = p.Mbar + (size_t)b * n * dout;
+  const float* Zb = p.Z + (size_t)b * n * din;
+
+  if (warp < 8) {
+    const int lr = tid >> 3, lc = tid & 7;
+    for (int sc0 = 0; sc0 < nchunks; sc0 += 4) {
+      float4 buf[4][4];
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = row0 + 32 * i + lr;
+          buf[kc][i] = (sc0 + kc < nchunks && row < n) ? __ldg(reinterpret_cast<const float4*>(Mb + (size_t)row * dout + (sc0 + kc) * 32 + lc * 4))
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        const int j = sc0 + kc;
+        if (j >= nchunks) break;
+        const int st = j % S;
+        mbar_wait(empty(st), ((uint32_t)(j / S) & 1u) ^ 1u);
+        const uint32_t a_base = smem_base + st * stage_bytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = buf[kc][i];
+          const int r = 32 * i + lr;
+          const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((lc ^ (r & 7)) << 4);
+          const float h0 = tf32_rna(v.x), h1 = tf32_rna(v.y), h2 = tf32_rna(v.z), h3 = tf32_rna(v.w);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + off), "f"(h0), "f"(h1), "f"(h2), "f"(h3) : "memory");
+          if (split)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + TC_ATILE + off), "f"(v.x - h0), "f"(v.y - h1),
+                         "f"(v.z - h2), "f"(v.w - h3) : "memory");
+        }
+        fence_proxy_async();
+        mbar_arrive(full_a(st));
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      for (int j = 0; j < nchunks; ++j) {
+        const int st = j % S;
+        mbar_wait(empty(st), ((uint32_t)(j / S) & 1u) ^ 1u);
+        const uint32_t b_base = smem_base + st * stage_bytes + a_bytes;
+        mbar_expect_tx(full_b(st), (uint32_t)b_bytes);
+        tma_load_2d(b_base, &map_hi, j * TC_BK, 0, full_b(st));
+        if (split) tma_load_2d(b_base + b_tile, &map_lo, j * TC_BK, 0, full_b(st));
+      }
+    }
+  } else {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nd >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int j = 0; j < nchunks; ++j) {
+        const int st = j % S;
+        const uint32_t ph = (uint32_t)(j / S) & 1u;
+        mbar_wait(full_b(st), ph);
+        mbar_wait(full_a(st), ph);
+        tc_fence_after();
+        const uint32_t ahi = smem_base + st * stage_bytes, alo = ahi + TC_ATILE;
+        const uint32_t bhi = ahi + a_bytes, blo = bhi + b_tile;
+#pragma unroll
+        for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+          const uint64_t dah = make_desc_sw128(ahi + k8 * 32), dbh = make_desc_sw128(bhi + k8 * 32);
+          umma_tf32(tmem_base, dah, dbh, idesc, (j > 0 || k8 > 0) ? 1u : 0u);
+          if (split) {
+            umma_tf32(tmem_base, make_desc_sw128(alo + k8 * 32), dbh, idesc, 1u);
+            umma_tf32(tmem_base, dah, make_desc_sw128(blo + k8 * 32), idesc, 1u);
+          }
+        }
+        umma_commit(empty(st));
+      }
+      umma_commit(accum_bar);
+    }
+  }
+
+  if (warp < 8) {
+    mbar_wait(accum_bar, 0u);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane, gi = row0 + row;
+    const bool rowok = gi < n;
+    const float* Zrow = Zb + (size_t)(rowok ? gi : 0) * din;
+    const int cols_per_half = nd / 2;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    // pass 1: this half's share of sum z^2 and <w Nbar, z>
+    float ss = 0.f, dot = 0.f;
+    for (int cc = 0; cc < cols_per_half; cc += 16) {
+      const int col = half * cols_per_half + cc;
+      uint32_t r[16];
+      tmem_ld16(trow + (uint32_t)col, r);
+      tmem_wait_ld();
+      if (rowok) {
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          const float4 z4 = *reinterpret_cast<const float4*>(Zrow + col + 4 * v4);
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.nw + col + 4 * v4));
+          const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            ss = fmaf(zz[u], zz[u], ss);
+            dot = fmaf(ww[u] * __uint_as_float(r[4 * v4 + u]), zz[u], dot);
+          }
+        }
+      }
+    }
+    red_s[half][0][row] = ss;
+    red_s[half][1][row] = dot;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    ss = red_s[0][0][row] + red_s[1][0][row];
+    dot = red_s[0][1][row] + red_s[1][1][row];
+    const float rinv = rsqrtf(ss / (float)din + 1e-5f);
+    const float coef = rinv * rinv * rinv * dot / (float)din;
+    const float vv = (p.po.vec && rowok) ? p.po.vec[(size_t)b * p.po.vec_stride + gi] : 0.f;
+    float* Zbrow = p.Zbar + ((size_t)b * n + (rowok ? gi : 0)) * din;
+    // pass 2: Zbar, its producer outputs, and the per-column sums (g_nw, g_nb, column sums of Zbar)
+    for (int cc = 0; cc < cols_per_half; cc += 16) {
+      const int col = half * cols_per_half + cc;
+      uint32_t r[16];
+      tmem_ld16(trow + (uint32_t)col, r);
+      tmem_wait_ld();
+      float zb[16], gw[16], gb[16], s1[16];
+#pragma unroll
+      for (int v4 = 0; v4 < 4; ++v4) {
+        float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rowok) z4 = *reinterpret_cast<const float4*>(Zrow + col + 4 * v4);
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.nw + col + 4 * v4));
+        const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = 4 * v4 + u;
+          const float nbar = rowok ? __uint_as_float(r[e]) : 0.f;
+          float v = rinv * ww[u] * nbar - zz[u] * coef;
+          if (!rowok || (p.relu_mask && !(zz[u] > 0.f))) v = 0.f;
+          zb[e] = v;
+          gw[e] = nbar * zz[u] * rinv;
+          gb[e] = nbar;
+          s1[e] = vv * v;
+        }
+      }
+      if (rowok) {
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4)
+          *reinterpret_cast<float4*>(Zbrow + col + 4 * v4) = make_float4(zb[4 * v4], zb[4 * v4 + 1], zb[4 * v4 + 2], zb[4 * v4 + 3]);
+      }
+      if (p.po.Thi != nullptr && gi < p.po.npad) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const float hi = tf32_rna(zb[u]);
+          const size_t o = ((size_t)b * din + col + u) * p.po.npad + gi;
+          p.po.Thi[o] = hi;
+          p.po.Tlo[o] = zb[u] - hi;
+        }
+      }
+      warp_colsum16(gw, lane);
+      warp_colsum16(gb, lane);
+      warp_colsum16(zb, lane);
+      warp_colsum16(s1, lane);
+      if ((lane & 1) == 0) {
+        const int c = col + warp_col16(lane);
+        csum[(q * 4 + 0) * nd + c] = gw[0];
+        csum[(q * 4 + 1) * nd + c] = gb[0];
+        csum[(q * 4 + 2) * nd + c] = zb[0];
+        csum[(q * 4 + 3) * nd + c] = s1[0];
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (tid < nd) {
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t[k] += csum[(q * 4 + k) * nd + tid];
+    atomicAdd(p.g_nw + tid, t[0]);
+    atomicAdd(p.g_nb + tid, t[1]);
+    if (p.po.cb != nullptr) {
+      float* part = p.po.partial + (((size_t)b * gridDim.x + rb) * 2) * din;
+      part[tid] = t[2];
+      part[din + tid] = t[3];
+    }
+  }
+  if (p.po.cb != nullptr)
+    finalize_colsums(p.po, b, gridDim.x, din, 0, nd, p.po.tickets + (size_t)b, &is_last);
+  if (warp == 9) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+  }
+}
+
+bool tc_linear_bwd_supported(int din, int dout) {
+  if (getenv("PEG_TC_NO_LINEAR")) return false;
+  return din % 32 == 0 && din >= 32 && din <= 256 && dout % 32 == 0 && dout >= 32 && get_encode() != nullptr;
+}
+
+int tc_linear_bwd(cudaStream_t st, const PegDims& dm, const TcLinear& w, int layer, const float* Mbar, const float* Z,
+                  const float* nw, int din, int dout, int relu_mask, float* Zbar, float* g_nw, float* g_nb, const ProducerOut& po) {
+  if (!w.ready) return PEG_ERR_WORKSPACE;
+  LbParams p;
+  memset(&p, 0, sizeof(p));
+  p.Mbar = Mbar; p.Z = Z; p.nw = nw; p.Zbar = Zbar; p.g_nw = g_nw; p.g_nb = g_nb; p.po = po;
+  p.n = dm.n; p.din = din; p.dout = dout; p.relu_mask = relu_mask;
+  p.nsplit = (dm.flags & PEG_FLAG_TF32_FAST) ? 1 : 3;
+  const int sp = p.nsplit == 3 ? 2 : 1;
+  const int stage_bytes = sp * TC_ATILE + sp * din * TC_BK * 4;
+  int stages = (200 * 1024) / stage_bytes;
+  const int nchunks = dout / 32;
+  stages = stages > nchunks ? nchunks : stages;
+  stages = stages > 4 ? 4 : stages;
+  if (stages < 1 || (size_t)16 * din * 4 > (size_t)stage_bytes) return PEG_ERR_UNSUPPORTED;
+  p.stages = stages;
+  p.tmem_cols = tmem_cols_pow2(din);
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (3 * stages + 2) + 64;
+  const CUtensorMap* mhi = nullptr;
+  const CUtensorMap* mlo = nullptr;
+  PEG_TC_TRY(get_maps(w.Wt_hi[layer], w.Wt_lo[layer], (uint64_t)dout, (uint64_t)din, din, &mhi, &mlo));
+  static std::atomic<unsigned> done{0u};
+  PEG_TC_TRY(optin_smem(k_tc_linear_bwd, done));
+  dim3 grid((dm.n + 127) / 128, 1, dm.B);
+  k_tc_linear_bwd<<<grid, NL_THREADS, smem, st>>>(*mhi, *mlo, p);
+  if (cudaPeekAtLastError() != cudaSuccess) {
+    const cudaError_t e = cudaGetLastError();
+    fprintf(stderr, "pegncde: k_tc_linear_bwd launch failed (%s): grid %u x %u, smem %zu, din %d, stages %d\n", cudaGetErrorString(e),
+            grid.x, grid.z, smem, din, stages);
     set_last_cuda((int)e);
     return PEG_ERR_CUDA;
   }

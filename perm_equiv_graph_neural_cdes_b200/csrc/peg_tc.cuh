@@ -19,6 +19,8 @@ struct TcLinear {
   float* Wn_hi[PEG_MAX_LAYERS];
   float* Wn_lo[PEG_MAX_LAYERS];
   float* cvec[PEG_MAX_LAYERS];
+  float* Wt_hi[PEG_MAX_LAYERS];   // W^T [din][dout] (B operand of the Linear backward: Nbar = Mbar W)
+  float* Wt_lo[PEG_MAX_LAYERS];
   bool ready;   // carved (tensor-core flag set)
 };
 
@@ -28,6 +30,10 @@ bool tc_linear_supported(int din, int dout);
 // splits the weights of every layer (enqueue only); call once per API entry before the first evaluation
 int tc_prep_weights(cudaStream_t st, const Model& m, const float* params, const TcLinear& w);
 // M = rmsnorm(Z) W^T + b on tcgen05 (3xTF32), fused producer outputs as k_norm_linear (peg_kernels.cuh)
+// backward of Linear + RMSNorm wrt the layer input on tcgen05, epilogue as k_linear_bwd (peg_kernels.cuh)
+int tc_linear_bwd(cudaStream_t st, const PegDims& d, const TcLinear& w, int layer, const float* Mbar, const float* Z,
+                  const float* nw, int din, int dout, int relu_mask, float* Zbar, float* g_nw, float* g_nb, const ProducerOut& po);
+bool tc_linear_bwd_supported(int din, int dout);
 int tc_norm_linear(cudaStream_t st, const PegDims& d, const TcLinear& w, int layer, const float* Z, int din, int dout,
                    const float* nw, const float* nb, float* M, float* Nout, const ProducerOut& po);
 bool tc_supported(const PegDims& d, int dcols);

@@ -366,10 +366,16 @@ static int feval_vjp(Ctx& c, float t, float* const* zin, const float* kbar, floa
       ProducerOut po;
       memset(&po, 0, sizeof(po));
       if (l > 0) po = producer_out(c, ld.din, true, c.w.colG, true, svec_r(d.n, l - 1));
-      k_linear_bwd<<<grid, 256, 0, c.st>>>(c.w.Mbar, c.params + ld.w_off, zin[l], c.params + ld.nw_off, d.n,
-                                              ld.din, ld.dout, l > 0 ? 1 : 0, zb, g_params + ld.nw_off,
-                                              g_params + ld.nb_off, po);
-      PEG_LAUNCH_CHECK();
+      if (c.use_tc && c.w.lin.ready && tc_linear_bwd_supported(ld.din, ld.dout)) {
+        PEG_TRY(tc_linear_bwd(c.st, c.d, c.w.lin, l, c.w.Mbar, zin[l], c.params + ld.nw_off, ld.din, ld.dout, l > 0 ? 1 : 0, zb,
+                              g_params + ld.nw_off, g_params + ld.nb_off, po));
+        g_launches.fetch_add(1);
+      } else {
+        k_linear_bwd<<<grid, 256, 0, c.st>>>(c.w.Mbar, c.params + ld.w_off, zin[l], c.params + ld.nw_off, d.n,
+                                                ld.din, ld.dout, l > 0 ? 1 : 0, zb, g_params + ld.nw_off,
+                                                g_params + ld.nb_off, po);
+        PEG_LAUNCH_CHECK();
+      }
       obar_ready = l > 0;
       obar_vt = po.Thi != nullptr;
     }
