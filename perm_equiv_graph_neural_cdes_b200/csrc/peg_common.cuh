@@ -107,9 +107,11 @@ struct ContractArgs {
   const float* V;        // [B,n,d]
   const float* Mref;     // bwd only: M_l [B,n,d]
   const float* colbuf;   // [B][2][d]
+  const float* cbM;      // bwd, tensor-core path only (nullable): [B][2][d] column sums of M -> the epilogue also emits the
+                         // param3..8 gradients (otherwise k_fusion_vec_grads does)
   float* out;            // [B,n,d]
   float* g_fus;          // bwd only: gradient of the 16 fusion scalars (atomicAdd)
-  int n, ldn /* = npad */, d, layer;
+  int n, ldn /* = npad */, d, layer, L;
   int relu, scale_tg;
   int vt_ready;          // the producer kernel already wrote V^T hi/lo (tensor-core path skips its own transpose pass)
 };

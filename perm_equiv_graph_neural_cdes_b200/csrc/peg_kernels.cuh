@@ -1044,11 +1044,11 @@ __global__ void __launch_bounds__(256) k_weight_grad(const float* __restrict__ M
   float bsum = 0.f;
   for (size_t k0 = r_begin; k0 < r_end; k0 += 16) {
     const size_t row = k0 + lk;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int o = o0 + 4 * lq + j, c = c0 + 4 * lq + j;
-      ms[lk][4 * lq + j] = (row < r_end && o < dout) ? Mbar[row * dout + o] : 0.f;
-      ns[lk][4 * lq + j] = (row < r_end && c < din) ? N[row * din + c] : 0.f;
+    {   // din, dout are multiples of 4 (check_dims): one 128-bit load / store per operand
+      const int o = o0 + 4 * lq, c = c0 + 4 * lq;
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(&ms[lk][4 * lq]) = (row < r_end && o < dout) ? __ldg(reinterpret_cast<const float4*>(Mbar + row * dout + o)) : zero4;
+      *reinterpret_cast<float4*>(&ns[lk][4 * lq]) = (row < r_end && c < din) ? __ldg(reinterpret_cast<const float4*>(N + row * din + c)) : zero4;
     }
     __syncthreads();
 #pragma unroll

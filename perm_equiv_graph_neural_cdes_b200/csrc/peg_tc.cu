@@ -181,6 +181,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ float fsum[8][16];    // adjoint epilogue: per-warp partials of the fusion-scalar gradients
   constexpr int NA = BWD ? 2 : 1;  // A-operand variants per item: fwd = combined X or Y; bwd = (A_s, A'_s)
   const ContractArgs& a = p.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -434,6 +435,10 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     const float* Mrow = BWD ? a.Mref + ((size_t)b * n + (rowok ? gi : 0)) * d : nullptr;
     float* Orow = a.out + ((size_t)b * n + (rowok ? gi : 0)) * d;
     float g4[4] = {0.f, 0.f, 0.f, 0.f};
+    // adjoint only: the O(n d) fusion-parameter gradients (param3..8) ride along -- per node q = <G_i, M_i>,
+    // u = <G_i, 1^T M>, w = <M_i, 1^T G> (k_fusion_vec_grads of the CUDA-core path, fused here)
+    float fq = 0.f, fu = 0.f, fw = 0.f;
+    const float* cbM = (BWD && a.cbM) ? a.cbM + (size_t)b * 2 * d : nullptr;
     for (int cc = 0; cc < cols_per_half; cc += 16) {
       const int col = half * cols_per_half + cc;      // column inside this CTA's ND tile
       const int gc = ntile * nd + col;                // global feature column
@@ -473,6 +478,12 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
               g4[1] = fmaf(dtV, mm[u], g4[1]);
               g4[2] = fmaf(aV, mm[u], g4[2]);
               g4[3] = fmaf(dV, mm[u], g4[3]);
+              fq = fmaf(vv[u], mm[u], fq);
+              fw = fmaf(mm[u], ss[u], fw);
+            }
+            if (cbM) {
+              const float4 c4 = __ldg(reinterpret_cast<const float4*>(cbM + gc + 4 * v4));
+              fu = fmaf(vv[0], c4.x, fmaf(vv[1], c4.y, fmaf(vv[2], c4.z, fmaf(vv[3], c4.w, fu))));
             }
           }
           *reinterpret_cast<float4*>(Orow + gc + 4 * v4) = make_float4(o[0], o[1], o[2], o[3]);
@@ -480,17 +491,49 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       }
     }
     if (BWD) {
+      // per-thread partials of the 16 fusion-scalar gradients this CTA contributes to (layout of g_fus: param1..8 x 2)
+      float part[14];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float t = g4[k];
+      for (int k = 0; k < 4; ++k) part[k] = g4[k];
+#pragma unroll
+      for (int k = 4; k < 14; ++k) part[k] = 0.f;
+      if (cbM && rowok) {
+        const float rA = sv[svec_rA(n, a.L) + gi], rD = sv[svec_rD(n, a.L) + gi];
+        const float dA = sv[svec_dgA(n, a.L) + gi], dD = sv[svec_dgD(n, a.L) + gi];
+        part[4] = dA * fq; part[5] = dD * fq;      // param3
+        part[6] = rA * fu; part[7] = rD * fu;      // param4 (/n)
+        part[8] = rA * fw; part[9] = rD * fw;      // param5 (/n)
+        part[10] = rA * fq; part[11] = rD * fq;    // param6 (/n)
+        part[12] = fq;                              // param8 (* tot / n^2)
+      }
+      if (cbM && I == 0 && q == 0) {               // param7: tot_A / n^2 * <1^T G, 1^T M>, this CTA's columns once
+        float t = 0.f;
+        for (int c = half * cols_per_half + lane; c < (half + 1) * cols_per_half; c += 32) t = fmaf(cb0[ntile * nd + c], cbM[ntile * nd + c], t);
+        part[13] = t;
+      }
+      const int nred = cbM ? 14 : 4;
+      for (int k = 0; k < nred; ++k) {
+        float t = part[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) atomicAdd(a.g_fus + k, t);
+        if (lane == 0) fsum[warp][k] = t;
       }
     }
     tc_fence_before();
   }
   __syncthreads();
+  if (BWD && tid < (a.cbM ? 14 : 4)) {   // one atomic per scalar and CTA
+    float t = 0.f;
+#pragma unroll
+    for (int w8i = 0; w8i < 8; ++w8i) t += fsum[w8i][tid];
+    const float inv_n = 1.f / (float)n, inv_n2 = inv_n * inv_n;
+    const float totA = scp->totA, totD = scp->totD;
+    if (tid < 4) atomicAdd(a.g_fus + tid, t);
+    else if (tid < 6) atomicAdd(a.g_fus + tid, t);                     // param3: indices 4, 5
+    else if (tid < 12) atomicAdd(a.g_fus + tid, t * inv_n);            // param4..6: indices 6..11
+    else if (tid == 12) { atomicAdd(a.g_fus + 14, t * totA * inv_n2); atomicAdd(a.g_fus + 15, t * totD * inv_n2); }
+    else { atomicAdd(a.g_fus + 12, t * totA * inv_n2); atomicAdd(a.g_fus + 13, t * totA * inv_n2); }   // reference quirk: both use sum(A)
+  }
   __syncwarp();
   if (C > 1) cluster_sync_all();   // no CTA exits while peers may still multicast into it or arrive on its barriers
   if (warp == 17) {

@@ -229,8 +229,10 @@ static int colsums(Ctx& c, const float* V, int dcols, size_t vec_off, bool with_
   return PEG_OK;
 }
 
+static bool contract_on_tc(const Ctx& c, int l) { return c.use_tc && tc_supported(c.d, c.m.layer[l].dout); }
+
 static int contract(Ctx& c, int l, bool bwd, const float* V, const float* Mref, const float* colbuf, float* out,
-                    bool relu, bool scale_tg, float* g_fus, bool vt_ready) {
+                    bool relu, bool scale_tg, float* g_fus, bool vt_ready, const float* cbM = nullptr) {
   const LayerDesc& ld = c.m.layer[l];
   ContractArgs a;
   a.planes = c.ctl.adj_coef;
@@ -245,6 +247,8 @@ static int contract(Ctx& c, int l, bool bwd, const float* V, const float* Mref, 
   a.V = V;
   a.Mref = Mref;
   a.colbuf = colbuf;
+  a.cbM = cbM;
+  a.L = c.d.L;
   a.out = out;
   a.g_fus = g_fus;
   a.n = c.d.n; a.ldn = c.d.ldn; a.d = ld.dout; a.layer = l;
@@ -338,8 +342,9 @@ static int feval_vjp(Ctx& c, float t, float* const* zin, const float* kbar, floa
     // recompute M_l (and the normalised input N_l) from the saved layer input; 1^T M comes out of the same kernel
     PEG_TRY(norm_linear(c, l, zin[l], c.w.M, c.w.N, producer_out(c, ld.dout, false, c.w.colM, false, 0)));
     if (!obar_ready) PEG_TRY(colsums(c, c.w.Obar, ld.dout, svec_r(d.n, l), true, c.w.colG));
-    PEG_TRY(contract(c, l, true, c.w.Obar, c.w.M, c.w.colG, c.w.Mbar, false, false, g_fus, obar_vt));
-    {
+    const bool fused_vec_grads = contract_on_tc(c, l);   // the tcgen05 adjoint epilogue also emits the param3..8 gradients
+    PEG_TRY(contract(c, l, true, c.w.Obar, c.w.M, c.w.colG, c.w.Mbar, false, false, g_fus, obar_vt, fused_vec_grads ? c.w.colM : nullptr));
+    if (!fused_vec_grads) {
       FusGradArgs a;
       a.G = c.w.Obar; a.M = c.w.M; a.cbM = c.w.colM; a.cbG = c.w.colG;
       a.sc = c.w.sc; a.svec = c.w.svec; a.sv_stride = c.sv_stride;
