@@ -508,3 +508,24 @@ def test_build_control_from_snapshots_matches_pack_of_host_coefficients(cuda, n,
     # batched + the solve accepts the built control directly
     gb = P.build_control(ts.to(cuda), torch.stack([A, A]).to(cuda))
     assert torch.equal(gb.adj_coef[1], ref.adj_coef[0]) and gb.B == 2
+
+
+def test_adaptive_solve_at_c1_heat_shape(cuda):
+    """BASELINE.json configs[0] shape (configs/dynamical_systems/perm_equiv_gncde_config.yaml: n=400, hidden 16, 2 layers,
+    80 knots on [0,5], no control wrapper, PIDController(1e-3, 1e-6), SaveAt(ts=ts)): forward + gradient against the fp64
+    oracle forced onto the accepted step table."""
+    p = R.make_problem(n=400, h=16, e=0, L=2, T=80, t1=5, dt0=0.1, seed=101, float_ts=True)
+    vf, term, args = device_model(p, cuda)
+    save_ts = p.ts.to(torch.float32)
+    y0 = p.y0.to(cuda).requires_grad_(True)
+    sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 5.0, None, y0, args, stepsize_controller=P.PIDController(rtol=1e-3, atol=1e-6),
+                        saveat=P.SaveAt(ts=save_ts))
+    assert sol.ys.shape == (80, 400, 16)
+    G = torch.randn(sol.ys.shape, generator=torch.Generator().manual_seed(5)) / 80
+    (sol.ys * G.to(cuda)).sum().backward()
+    p64 = R.problem_to(p, torch.float64)
+    y64 = p64.y0.clone().requires_grad_(True)
+    ys64, _, _ = R.tsit5_solve_adaptive(_oracle_vf(p64), y64, 0.0, 5.0, save_ts=save_ts.numpy(), forced_steps=sol.stats["step_ts"])
+    (ys64 * G.double()).sum().backward()
+    assert rel_err(sol.ys, ys64) < TOL_Y
+    assert rel_err(y0.grad, y64.grad) < TOL_G
