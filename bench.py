@@ -322,11 +322,13 @@ def run_ours(args):
         fl = (prof["fwd"]["flops"] * prof["fwd"]["timed"] + prof["bwd"]["flops"] * prof["bwd"]["timed"])
         gbs = by / (tot_ms * 1e-3) / 1e9
         tfs = fl / (tot_ms * 1e-3) / 1e12
-        # Which roof binds: the planes stream from HBM once per launch; the tensor pipe executes `passes` tf32 MMAs per
-        # algorithmic product (3xTF32 split = fp32 parity; 1 with --tf32-fast).  tf32 dense peak ~ 1/2 of the measured bf16 peak.
+        # The planes stream from HBM once per launch; the tensor pipe executes `passes` tf32 MMAs per algorithmic product
+        # (3xTF32 split = fp32 parity; 1 with --tf32-fast).  tf32 dense peak ~ 1/2 of the measured bf16 peak.
         tf32_peak = pk["bf16"] / 2.0
         passes = 1 if (flags & 2) or not (flags & 1) else 3
-        t_hbm, t_tc = by / (pk["hbm"] * 1e9), passes * fl / (tf32_peak * 1e12)
+        # the bound is decided by ALGORITHMIC intensity (flops / bytes against the tf32 ridge); the executed tensor work
+        # (passes x) is reported beside it: with 3xTF32 the adjoint (four products) is co-limited by the tensor pipe
+        t_hbm, t_tc = by / (pk["hbm"] * 1e9), fl / (tf32_peak * 1e12)
         bound = "hbm" if t_hbm >= t_tc else "tensor"
         share = tot_ms * (prof["fwd"]["launches"] + prof["bwd"]["launches"]) / max(tot_timed, 1) / (ms_per_step * prof_steps)
         roof = {"bound": bound, "kernel": "k_tc_contract<fwd> + k_tc_contract<adjoint> (the n x n x d contraction)" if flags & 1 else "k_dual_contract (FFMA)",
@@ -335,6 +337,8 @@ def run_ours(args):
                 "peak_source": pk["src"] + (" hbm_gbs" if bound == "hbm" else " bf16_tflops_sustained/2 (tf32)"),
                 "traffic": measured_traffic(args.workload), "achieved_gbs": gbs, "achieved_tflops": tfs,
                 "tensor_passes": passes, "executed_tflops": passes * tfs, "executed_tensor_frac": passes * tfs / tf32_peak,
+                "fwd_executed_tensor_frac": passes * prof["fwd"]["flops"] * prof["fwd"]["timed"] / max(prof["fwd"]["ms"], 1e-9) / 1e9 / tf32_peak,
+                "bwd_executed_tensor_frac": passes * prof["bwd"]["flops"] * prof["bwd"]["timed"] / max(prof["bwd"]["ms"], 1e-9) / 1e9 / tf32_peak,
                 "avg_launch_us": tot_ms / tot_timed * 1e3,
                 "launches_timed": tot_timed, "share_of_step": share,
                 "fwd_avg_us": prof["fwd"]["ms"] / max(prof["fwd"]["timed"], 1) * 1e3, "bwd_avg_us": prof["bwd"]["ms"] / max(prof["bwd"]["timed"], 1) * 1e3,

@@ -112,10 +112,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// streaming 128-bit load: read-only path, do not allocate in L1 (every plane byte is used once per CTA)
+// streaming 128-bit plane loads.  Measured on B200 (n=2048, d=128, B=9, forward launch): ld.global.cg 137.6 us, ld.global.nc 139.6,
+// ld.global.nc.L1::no_allocate 156.1, ld.global.cs 159.8, ...no_allocate.L2::256B 156.7 -- the adjoint is insensitive (217 us)
+#ifndef PEG_LDG_VARIANT
+#define PEG_LDG_VARIANT 2
+#endif
 __device__ __forceinline__ float4 ldg_stream(const float* p) {
   float4 r;
+#if PEG_LDG_VARIANT == 0
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+#elif PEG_LDG_VARIANT == 1
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+#elif PEG_LDG_VARIANT == 2
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+#elif PEG_LDG_VARIANT == 3
+  asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+#elif PEG_LDG_VARIANT == 4
+  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+#endif
   return r;
 }
 
