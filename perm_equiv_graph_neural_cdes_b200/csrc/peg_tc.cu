@@ -173,6 +173,9 @@ __global__ void __launch_bounds__(256) k_split_transpose(const float* __restrict
 // ------------------------------------------------------------------------------------------
 // the contraction kernel
 // ------------------------------------------------------------------------------------------
+#ifndef PEG_TC_EARLY_RELOAD
+#define PEG_TC_EARLY_RELOAD 0   // measured: earlier re-issue makes the forward launch slower (159 vs 137 us at n=2048, d=128, B=9)
+#endif
 constexpr int TC_THREADS = 576;   // 2 converter groups x 8 warps + TMA warp + MMA warp
 constexpr int TC_CONV_THREADS = 256;
 constexpr int TC_BM = 128;   // output rows per CTA (UMMA M)
@@ -338,6 +341,9 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
           t[v][4 * m + 3] = w0 * e0.w + w1 * e1.w + w2 * e2.w + w3 * e3.w;
         }
       }
+      // forward: the plane registers are dead now -> re-issue the group's next loads before the slot wait and the stores
+      // (the adjoint keeps 32 combined values live and would spill at 96 registers: it reloads after publishing)
+      if (PEG_TC_EARLY_RELOAD && !BWD && j + 2 < items) load_item(j + 2);
       const int st = j % SA;
       const uint32_t ph = (uint32_t)(j / SA) & 1u;
       mbar_wait(empty_a(st), ph ^ 1u);   // the MMAs that read this slot's previous contents have completed
@@ -357,7 +363,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       }
       fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
       mbar_arrive(full_a(st));
-      if (j + 2 < items) load_item(j + 2);
+      if (!(PEG_TC_EARLY_RELOAD && !BWD) && j + 2 < items) load_item(j + 2);
     };
 
     load_item(grp);   // group 0: direct items (even j); group 1: transposed items (odd j)

@@ -164,3 +164,35 @@ def test_oracle_adaptive_solver_on_a_known_ode():
     # forcing the accepted table reproduces the run
     ys2, table2, _ = R.tsit5_solve_adaptive(f, torch.ones(3, 2, dtype=torch.float64), 0.0, 5.0, save_ts=ts, forced_steps=table)
     assert np.array_equal(table, table2) and torch.allclose(ys, ys2, atol=1e-12)
+
+
+def test_new_entry_points_validate_before_touching_the_gpu():
+    """build_adj / tsit5_dense / scaled_sumsq / step_fwd / solve_bwd: bad dims -> 1, missing pointers -> 2 (no CUDA call made)."""
+    l = _lib.lib()
+    good = _lib.PegDims(1, 10, 32, 8, 0, 2, 4, 0)
+    bad = _lib.PegDims(1, 10, 32, 6, 0, 2, 4, 0)
+    assert l.pegncde_build_adj(None, bad, None, None, None, None, None, None, None) in (1, 2)
+    assert l.pegncde_build_adj(None, good, None, None, None, None, None, None, None) == 2
+    assert l.pegncde_tsit5_dense(None, bad, 0.1, 0.5, None, None, None, None, None) == 1
+    assert l.pegncde_tsit5_dense(None, good, 0.1, 0.5, None, None, None, None, None) == 2
+    assert l.pegncde_scaled_sumsq(None, bad, None, None, None, None, 1e-3, 1e-6, None) == 1
+    assert l.pegncde_scaled_sumsq(None, good, None, None, None, None, 1e-3, 1e-6, None) == 2
+    assert l.pegncde_step_fwd(None, good, _lib.PegControl(), None, 0.0, 0.1, None, None, 0, None, None, None, None, None, 0) == 2
+    assert l.pegncde_solve_bwd(None, good, _lib.PegControl(), None, None, 1, None, None, None, None, None, None, None, None, None, 0) == 2
+    # g_xcoef without a node-signal control is a dimension error, not a crash (needs every other pointer non-null to reach the check)
+    w = (ctypes.c_float * 7)()
+    l.pegncde_tsit5_dense_weights(0.5, w)
+    assert abs(sum(w) - 0.5) < 1e-6      # sum_i b_i(theta) = theta (the interpolant reproduces y' = const exactly)
+
+
+def test_packed_control_select_is_a_view():
+    """PackedControl.select(b) (adaptive solves step each trajectory alone) must not copy: same storage, B = 1."""
+    pc = P.PackedControl.__new__(P.PackedControl)
+    pc.B, pc.n, pc.T, pc.e, pc.ldn = 3, 5, 4, 0, 32
+    for name, shape in (("ts", (3, 4)), ("adj_coef", (3, 3, 4 * 32 * 32)), ("adj_rowsum", (3, 3, 4, 5)), ("adj_diag", (3, 3, 4, 5)),
+                        ("adj_total", (3, 3, 4)), ("tch_coef", (3, 3, 3, 5))):
+        setattr(pc, name, torch.zeros(shape))
+    pc.x_coef = None
+    v = pc.select(1)
+    assert v.B == 1 and v.n == 5 and v.adj_coef.data_ptr() == pc.adj_coef[1].data_ptr() and v.ts.shape == (1, 4)
+    assert v.dims(8, 2).B == 1
