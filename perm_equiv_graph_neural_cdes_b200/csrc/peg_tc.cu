@@ -1412,4 +1412,213 @@ int tc_linear_bwd(cudaStream_t st, const PegDims& dm, const TcLinear& w, int lay
   return PEG_OK;
 }
 
+
+// ==========================================================================================
+// Weight / bias gradient of the Linear on tcgen05 (3xTF32):  Wbar[o][k] += sum_r Mbar[r][o] N[r][k],  bbar[o] += sum_r Mbar[r][o]
+// over all B*n rows.  The reduction runs along the rows, so BOTH operands are needed row(K)-major: 8 loader warps read
+// 4x4 micro tiles (4 rows x 4 columns, 4 LDG.128) and store them transposed (16-byte chunk = 4 consecutive rows of one
+// column) into the swizzled K-major tiles -- lanes of a store phase hold 8 different row quads of the same column, which
+// makes the transposed stores bank-conflict-free.  M = 128 outputs o, N = din, K = 32 rows per chunk, one accumulator in
+// TMEM per CTA; every CTA owns a slice of the rows and adds its 128 x din partial with vector atomics.
+// grid (row slices, dout/128), block 288
+// ==========================================================================================
+constexpr int WG_THREADS = 288;
+
+struct WgParams {
+  const float* Mbar;   // [rows, dout]
+  const float* N;      // [rows, din]
+  float* gW;           // [dout, din]
+  float* gb;           // [dout]
+  size_t rows;
+  int rows_per_slice;  // multiple of 32
+  int din, dout, stages, tmem_cols, nsplit;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) k_tc_weight_grad(const WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int din = p.din, dout = p.dout, S = p.stages;
+  const bool split = p.nsplit == 3;
+  const int o0 = blockIdx.y * 128;
+  const size_t r_begin = (size_t)blockIdx.x * p.rows_per_slice;
+  const size_t r_end = min(p.rows, r_begin + (size_t)p.rows_per_slice);
+  const int nchunks = (int)((r_end - r_begin + 31) / 32);
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int a_bytes = (split ? 2 : 1) * TC_ATILE;
+  const int b_tile = din * TC_BK * 4;
+  const int b_bytes = (split ? 2 : 1) * b_tile;
+  const int stage_bytes = a_bytes + b_bytes;
+  const uint32_t bar_base = smem_base + S * stage_bytes;
+  auto full = [&](int s) { return bar_base + 8u * s; };
+  auto empty = [&](int s) { return bar_base + 8u * (S + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * S);
+  const uint32_t tmem_slot = accum_bar + 8u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full(s), 256); mbar_init(empty(s), 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp < 8) {
+    // micro tile of this thread: row quad rq (rows 4 rq .. 4 rq + 3 of the chunk), column quad cq (+ 32 per pass for N)
+    const int rq = lane & 7, cq = 4 * warp + (lane >> 3);
+    const int npass = (din + 127) / 128;
+    float bs[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < nchunks; ++j) {
+      const size_t rbase = r_begin + (size_t)j * 32 + 4 * rq;
+      float4 a[4], bq[2][4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const size_t row = rbase + m;
+        const bool ok = row < r_end;
+        a[m] = ok ? __ldg(reinterpret_cast<const float4*>(p.Mbar + row * dout + o0 + 4 * cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {
+          const int c = 4 * (cq + 32 * ps);
+          bq[ps][m] = (ok && ps < npass && c < din) ? __ldg(reinterpret_cast<const float4*>(p.N + row * din + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      const int st = j % S;
+      mbar_wait(empty(st), ((uint32_t)(j / S) & 1u) ^ 1u);
+      const uint32_t a_base = smem_base + st * stage_bytes, b_base = a_base + a_bytes;
+      auto put = [&](uint32_t hi_tile, uint32_t lo_off, int row, float x0, float x1, float x2, float x3) {
+        const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((rq ^ (row & 7)) << 4);
+        const float h0 = tf32_rna(x0), h1 = tf32_rna(x1), h2 = tf32_rna(x2), h3 = tf32_rna(x3);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_tile + off), "f"(h0), "f"(h1), "f"(h2), "f"(h3) : "memory");
+        if (split)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_tile + lo_off + off), "f"(x0 - h0), "f"(x1 - h1), "f"(x2 - h2),
+                       "f"(x3 - h3) : "memory");
+      };
+      // A' = Mbar^T: operand row = output o = 4 cq + e, chunk rq = rows 4 rq .. 4 rq + 3
+      put(a_base, TC_ATILE, 4 * cq + 0, a[0].x, a[1].x, a[2].x, a[3].x);
+      put(a_base, TC_ATILE, 4 * cq + 1, a[0].y, a[1].y, a[2].y, a[3].y);
+      put(a_base, TC_ATILE, 4 * cq + 2, a[0].z, a[1].z, a[2].z, a[3].z);
+      put(a_base, TC_ATILE, 4 * cq + 3, a[0].w, a[1].w, a[2].w, a[3].w);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) { bs[0] += a[m].x; bs[1] += a[m].y; bs[2] += a[m].z; bs[3] += a[m].w; }
+      // B' = N^T: operand row = input k = 4 (cq + 32 ps) + e
+#pragma unroll
+      for (int ps = 0; ps < 2; ++ps) {
+        const int r4 = 4 * (cq + 32 * ps);
+        if (ps < npass && r4 < din) {
+          put(b_base, b_tile, r4 + 0, bq[ps][0].x, bq[ps][1].x, bq[ps][2].x, bq[ps][3].x);
+          put(b_base, b_tile, r4 + 1, bq[ps][0].y, bq[ps][1].y, bq[ps][2].y, bq[ps][3].y);
+          put(b_base, b_tile, r4 + 2, bq[ps][0].z, bq[ps][1].z, bq[ps][2].z, bq[ps][3].z);
+          put(b_base, b_tile, r4 + 3, bq[ps][0].w, bq[ps][1].w, bq[ps][2].w, bq[ps][3].w);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(full(st));
+    }
+    // bias gradient: the 8 row-quad lanes (lane & 7) of one column quad
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v = bs[e];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      if (rq == 0 && p.gb != nullptr) atomicAdd(p.gb + o0 + 4 * cq + e, v);
+    }
+  } else {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(din >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int j = 0; j < nchunks; ++j) {
+        const int st = j % S;
+        mbar_wait(full(st), (uint32_t)(j / S) & 1u);
+        tc_fence_after();
+        const uint32_t ahi = smem_base + st * stage_bytes, alo = ahi + TC_ATILE;
+        const uint32_t bhi = ahi + a_bytes, blo = bhi + b_tile;
+#pragma unroll
+        for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+          const uint64_t dah = make_desc_sw128(ahi + k8 * 32), dbh = make_desc_sw128(bhi + k8 * 32);
+          umma_tf32(tmem_base, dah, dbh, idesc, (j > 0 || k8 > 0) ? 1u : 0u);
+          if (split) {
+            umma_tf32(tmem_base, make_desc_sw128(alo + k8 * 32), dbh, idesc, 1u);
+            umma_tf32(tmem_base, dah, make_desc_sw128(blo + k8 * 32), idesc, 1u);
+          }
+        }
+        umma_commit(empty(st));
+      }
+      umma_commit(accum_bar);
+    }
+  }
+
+  if (warp < 8 && nchunks > 0) {
+    mbar_wait(accum_bar, 0u);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const int o = o0 + q * 32 + lane;
+    float* grow = p.gW + (size_t)o * din;
+    const int cols_per_half = din / 2;
+    for (int cc = 0; cc < cols_per_half; cc += 16) {
+      const int col = half * cols_per_half + cc;
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int v4 = 0; v4 < 4; ++v4)
+        atomicAdd(reinterpret_cast<float4*>(grow + col + 4 * v4),
+                  make_float4(__uint_as_float(r[4 * v4]), __uint_as_float(r[4 * v4 + 1]), __uint_as_float(r[4 * v4 + 2]), __uint_as_float(r[4 * v4 + 3])));
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+  }
+}
+
+bool tc_weight_grad_supported(int din, int dout) {
+  if (getenv("PEG_TC_NO_LINEAR")) return false;
+  return dout % 128 == 0 && din % 32 == 0 && din >= 32 && din <= 256;
+}
+
+int tc_weight_grad(cudaStream_t st, const PegDims& dm, const float* Mbar, const float* N, size_t rows, int din, int dout,
+                   float* gW, float* gb) {
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.Mbar = Mbar; p.N = N; p.gW = gW; p.gb = gb; p.rows = rows; p.din = din; p.dout = dout;
+  p.nsplit = (dm.flags & PEG_FLAG_TF32_FAST) ? 1 : 3;
+  const int sp = p.nsplit == 3 ? 2 : 1;
+  const int stage_bytes = sp * TC_ATILE + sp * din * TC_BK * 4;
+  int stages = (200 * 1024) / stage_bytes;
+  stages = stages > 4 ? 4 : stages;
+  if (stages < 1) return PEG_ERR_UNSUPPORTED;
+  p.stages = stages;
+  p.tmem_cols = tmem_cols_pow2(din);
+  // row slices: about half a wave of CTAs (each adds a 128 x din partial with atomics, so fewer, fatter slices are cheaper)
+  const int otiles = dout / 128;
+  int slices = 74 / otiles;
+  slices = slices < 1 ? 1 : slices;
+  size_t rps = (rows + slices - 1) / slices;
+  rps = (rps + 31) / 32 * 32;
+  rps = rps < 64 ? 64 : rps;
+  p.rows_per_slice = (int)rps;
+  const unsigned nsl = (unsigned)((rows + rps - 1) / rps);
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 2) + 64;
+  static std::atomic<unsigned> done{0u};
+  PEG_TC_TRY(optin_smem(k_tc_weight_grad, done));
+  k_tc_weight_grad<<<dim3(nsl, otiles), WG_THREADS, smem, st>>>(p);
+  if (cudaPeekAtLastError() != cudaSuccess) {
+    const cudaError_t e = cudaGetLastError();
+    fprintf(stderr, "pegncde: k_tc_weight_grad launch failed (%s): grid %u x %d, smem %zu\n", cudaGetErrorString(e), nsl, otiles, smem);
+    set_last_cuda((int)e);
+    return PEG_ERR_CUDA;
+  }
+  return PEG_OK;
+}
+
 }  // namespace peg

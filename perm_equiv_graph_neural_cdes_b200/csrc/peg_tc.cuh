@@ -34,6 +34,10 @@ int tc_prep_weights(cudaStream_t st, const Model& m, const float* params, const 
 int tc_linear_bwd(cudaStream_t st, const PegDims& d, const TcLinear& w, int layer, const float* Mbar, const float* Z,
                   const float* nw, int din, int dout, int relu_mask, float* Zbar, float* g_nw, float* g_nb, const ProducerOut& po);
 bool tc_linear_bwd_supported(int din, int dout);
+// Wbar += Mbar^T N, bbar += 1^T Mbar over all rows, on tcgen05 (both operands transposed in the loaders)
+bool tc_weight_grad_supported(int din, int dout);
+int tc_weight_grad(cudaStream_t st, const PegDims& d, const float* Mbar, const float* N, size_t rows, int din, int dout, float* gW,
+                   float* gb);
 int tc_norm_linear(cudaStream_t st, const PegDims& d, const TcLinear& w, int layer, const float* Z, int din, int dout,
                    const float* nw, const float* nb, float* M, float* Nout, const ProducerOut& po);
 bool tc_supported(const PegDims& d, int dcols);

@@ -355,6 +355,10 @@ static int feval_vjp(Ctx& c, float t, float* const* zin, const float* kbar, floa
     }
     {
       const size_t rows = (size_t)d.B * d.n;
+      if (c.use_tc && tc_weight_grad_supported(ld.din, ld.dout)) {
+        PEG_TRY(tc_weight_grad(c.st, c.d, c.w.Mbar, c.w.N, rows, ld.din, ld.dout, g_params + ld.w_off, g_params + ld.b_off));
+        g_launches.fetch_add(1);
+      } else {
       // slices of the node dimension: enough blocks to fill the GPU even for small d_out x d_in
       const int tiles = ((ld.dout + 63) / 64) * ((ld.din + 63) / 64);
       int rps = 512;
@@ -363,6 +367,7 @@ static int feval_vjp(Ctx& c, float t, float* const* zin, const float* kbar, floa
       k_weight_grad<<<grid, 256, 0, c.st>>>(c.w.Mbar, c.w.N, rows, ld.din, ld.dout, rps, g_params + ld.w_off,
                                             g_params + ld.b_off);
       PEG_LAUNCH_CHECK();
+      }
     }
     {
       dim3 grid((d.n + 31) / 32, d.B);
