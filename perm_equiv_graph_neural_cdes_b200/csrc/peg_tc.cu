@@ -1482,7 +1482,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_weight_grad(const WgParams
       for (int m = 0; m < 4; ++m) {
         const size_t row = rbase + m;
         const bool ok = row < r_end;
-        a[m] = ok ? __ldg(reinterpret_cast<const float4*>(p.Mbar + row * dout + o0 + 4 * cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        a[m] = (ok && o0 + 4 * cq < dout) ? __ldg(reinterpret_cast<const float4*>(p.Mbar + row * dout + o0 + 4 * cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int ps = 0; ps < 2; ++ps) {
           const int c = 4 * (cq + 32 * ps);
@@ -1528,7 +1528,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_weight_grad(const WgParams
       v += __shfl_xor_sync(0xffffffffu, v, 1);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
       v += __shfl_xor_sync(0xffffffffu, v, 4);
-      if (rq == 0 && p.gb != nullptr) atomicAdd(p.gb + o0 + 4 * cq + e, v);
+      if (rq == 0 && p.gb != nullptr && o0 + 4 * cq < dout) atomicAdd(p.gb + o0 + 4 * cq + e, v);
     }
   } else {
     if (lane == 0) {
@@ -1559,13 +1559,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_weight_grad(const WgParams
     tc_fence_after();
     const int q = warp & 3, half = warp >> 2;
     const int o = o0 + q * 32 + lane;
-    float* grow = p.gW + (size_t)o * din;
+    float* grow = p.gW + (size_t)(o < dout ? o : 0) * din;
     const int cols_per_half = din / 2;
     for (int cc = 0; cc < cols_per_half; cc += 16) {
       const int col = half * cols_per_half + cc;
       uint32_t r[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
       tmem_wait_ld();
+      if (o >= dout) continue;   // rows of the last 128-row tile beyond dout (zero operand rows)
 #pragma unroll
       for (int v4 = 0; v4 < 4; ++v4)
         atomicAdd(reinterpret_cast<float4*>(grow + col + 4 * v4),
@@ -1583,7 +1584,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_weight_grad(const WgParams
 
 bool tc_weight_grad_supported(int din, int dout) {
   if (getenv("PEG_TC_NO_LINEAR")) return false;
-  return dout % 128 == 0 && din % 32 == 0 && din >= 32 && din <= 256;
+  return dout % 4 == 0 && dout >= 32 && din % 32 == 0 && din >= 32 && din <= 256;
 }
 
 int tc_weight_grad(cudaStream_t st, const PegDims& dm, const float* Mbar, const float* N, size_t rows, int din, int dout,
@@ -1600,7 +1601,7 @@ int tc_weight_grad(cudaStream_t st, const PegDims& dm, const float* Mbar, const 
   p.stages = stages;
   p.tmem_cols = tmem_cols_pow2(din);
   // row slices: about half a wave of CTAs (each adds a 128 x din partial with atomics, so fewer, fatter slices are cheaper)
-  const int otiles = dout / 128;
+  const int otiles = (dout + 127) / 128;
   int slices = 74 / otiles;
   slices = slices < 1 ? 1 : slices;
   size_t rps = (rows + slices - 1) / slices;
