@@ -104,6 +104,12 @@ int pegncde_param_offsets(const PegDims* dims, int64_t* offsets /* [5*L] */);
 int pegncde_pack_adj(peg_stream_t stream, const PegDims* dims, const float* d, const float* c, const float* b,
                      const float* a, float* adj_coef, float* adj_rowsum, float* adj_diag, float* adj_total,
                      float* tch_coef);
+/* Streaming variant: d,c,b,a hold only the cubic pieces [piece_begin, piece_begin + piece_count) -- each
+ * [B, piece_count, n, n, 2] -- and only those pieces of the (full-size) outputs are written.  A fixed-step solve walks the
+ * pieces in order, so the host can copy and pack piece i+1 while the steps inside piece i run (solve.py, streamed controls). */
+int pegncde_pack_adj_range(peg_stream_t stream, const PegDims* dims, int32_t piece_begin, int32_t piece_count, const float* d,
+                           const float* c, const float* b, const float* a, float* adj_coef, float* adj_rowsum, float* adj_diag,
+                           float* adj_total, float* tch_coef);
 /* same for already-tiled adjacency planes (adj_coef given): fills the statistics only;
  * tch_coef is written as d(time)/dt == 1 (b=1, c=d=0). */
 int pegncde_adj_stats(peg_stream_t stream, const PegDims* dims, const float* adj_coef, float* adj_rowsum,

@@ -46,6 +46,7 @@ SIGNATURES = {
     "pegncde_param_count": (c_size_t, [_DIMS]),
     "pegncde_param_offsets": (c_int, [_DIMS, POINTER(c_int64)]),
     "pegncde_pack_adj": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pegncde_pack_adj_range": (c_int, [_P, _DIMS, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pegncde_adj_stats": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P]),
     "pegncde_build_adj": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P, _P, _P]),
     "pegncde_pack_x": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P]),

@@ -99,6 +99,25 @@ class PackedControl:
         self.tch_coef = torch.empty((B, T - 1, 3, n), **f)
         self.x_coef = torch.empty((B, T - 1, 3, n, 2 * e), **f) if e > 0 else None
         self.x_packed = None   # differentiable source of x_coef when the node-signal coefficients require grad
+        self.pending = None    # host (d,c,b,a) arrays whose adjacency planes have not been copied / packed yet (streamed)
+        self.host_ts = None    # knot times shared by the batch (streaming needs one time grid), numpy fp32
+
+    def pack_pieces(self, begin: int, count: int, staging, stream_ptr: int) -> None:
+        """Packs cubic pieces [begin, begin+count) from device staging arrays (d,c,b,a each [B,count,n,n,2])."""
+        check(lib().pegncde_pack_adj_range(stream_ptr, self.dims(h=4, L=1), begin, count, staging[0].data_ptr(), staging[1].data_ptr(),
+                                           staging[2].data_ptr(), staging[3].data_ptr(), self.adj_coef.data_ptr(),
+                                           self.adj_rowsum.data_ptr(), self.adj_diag.data_ptr(), self.adj_total.data_ptr(),
+                                           self.tch_coef.data_ptr()), "pegncde_pack_adj_range")
+
+    def materialize(self) -> "PackedControl":
+        """Copies and packs every pending piece now (adaptive solves, single evaluations, ragged time grids)."""
+        if self.pending is not None:
+            dev = self.device
+            for iv in range(self.T - 1):
+                staging = [c[:, iv:iv + 1].to(dev, non_blocking=True).contiguous() for c in self.pending]
+                self.pack_pieces(iv, 1, staging, _stream_ptr(dev))
+            self.pending = None
+        return self
 
     def select(self, b: int) -> "PackedControl":
         """View of graph ``b`` as a batch of one (no copy): adaptive solves step every trajectory on its own."""
@@ -108,6 +127,7 @@ class PackedControl:
             setattr(v, name, getattr(self, name)[b:b + 1])
         v.x_coef = self.x_coef[b:b + 1] if self.x_coef is not None else None
         v.x_packed = None
+        v.pending, v.host_ts = None, None
         v._keepalive = self
         return v
 
@@ -156,6 +176,8 @@ def pack_control(
     device = torch.device(device if device is not None else coeffs_adj[0].device)
     if device.type != "cuda":
         raise RuntimeError("pack_control needs a CUDA device: the fused path has no CPU fallback")
+    if all(c.device.type == "cpu" for c in coeffs_adj):
+        return _pack_control_streamed(ts, coeffs_adj, x_coeffs, device)
     cad = [_as_batched(c, 4).to(device=device, dtype=torch.float32).contiguous() for c in coeffs_adj]
     B, Tm1, n = cad[0].shape[0], cad[0].shape[1], cad[0].shape[2]
     e = 0
@@ -188,6 +210,37 @@ def pack_control(
             "pegncde_pack_x",
         )
     # keep the sources alive until the pack kernels have run (stream-ordered)
+    pc._keepalive = (cad, cx)
+    return pc
+
+
+def _pack_control_streamed(ts, coeffs_adj, x_coeffs, device) -> PackedControl:
+    """HOST coefficient arrays (what the reference's trainers hold: numpy / torch-CPU batches, trainer_pgt.py:201-207): the
+    adjacency planes are NOT copied here.  The returned control is *pending*: a fixed-step solve copies and packs cubic piece
+    i+1 (``pegncde_pack_adj_range``, side stream) while the steps inside piece i run; anything else calls
+    :meth:`PackedControl.materialize` first.  The node-signal coefficients (small) are packed right away."""
+    cad = []
+    for c in coeffs_adj:
+        c = _as_batched(c, 4).to(torch.float32).contiguous()
+        cad.append(c if c.is_pinned() else c.pin_memory())
+    B, Tm1, n = cad[0].shape[0], cad[0].shape[1], cad[0].shape[2]
+    e = 0
+    cx = None
+    if x_coeffs is not None:
+        cx = [_as_batched(c, 4).to(device=device, dtype=torch.float32, non_blocking=True).contiguous() for c in x_coeffs]
+        e = cx[0].shape[3]
+    pc = PackedControl(B, n, Tm1 + 1, e, device)
+    tsb = _as_batched(ts, 1).to(torch.float32)
+    pc.ts.copy_(tsb.expand(B, Tm1 + 1), non_blocking=True)
+    pc.x_packed = None
+    if cx is not None and any(c.requires_grad for c in cx):
+        pc.x_packed = torch.stack([cx[2], cx[1], cx[0]], dim=2).reshape(B, Tm1, 3, n, 2 * e)
+        pc.x_coef = pc.x_packed.detach().contiguous()
+    elif cx is not None:
+        check(lib().pegncde_pack_x(_stream_ptr(device), pc.dims(h=4, L=1), cx[0].data_ptr(), cx[1].data_ptr(), cx[2].data_ptr(),
+                                   cx[3].data_ptr(), pc.x_coef.data_ptr()), "pegncde_pack_x")
+    pc.pending = cad
+    pc.host_ts = tsb.reshape(-1, Tm1 + 1)[0].cpu().numpy().copy() if bool((tsb.reshape(-1, Tm1 + 1) == tsb.reshape(-1, Tm1 + 1)[0]).all()) else None
     pc._keepalive = (cad, cx)
     return pc
 

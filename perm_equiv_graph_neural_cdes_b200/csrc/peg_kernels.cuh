@@ -22,17 +22,20 @@ namespace peg {
 __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, const float* __restrict__ cc,
                                                   const float* __restrict__ cb, const float* __restrict__ ca,
                                                   const float* __restrict__ tiled_in, const float* __restrict__ snap,
-                                                  const float* __restrict__ ts, int n, int npad, int Tm1,
-                                                  float* __restrict__ adj_coef, float* __restrict__ rowsum,
+                                                  const float* __restrict__ ts, int n, int npad, int Tm1, int piece0,
+                                                  int in_Tm1, float* __restrict__ adj_coef, float* __restrict__ rowsum,
                                                   float* __restrict__ diag, float* __restrict__ total,
                                                   float* __restrict__ tch) {
   __shared__ __align__(16) float tile[4096];   // the tile in its final element order
   __shared__ float tcol[3][32];                // column sums of the time channel of (b,c,d)
-  const int b = blockIdx.z, iv = blockIdx.y;
+  // blockIdx.y walks `gridDim.y` cubic pieces starting at piece0; the reference-layout source holds in_Tm1 pieces per
+  // graph (== Tm1 for a whole path, == the count of a streamed range: pegncde_pack_adj_range)
+  const int b = blockIdx.z, iv = piece0 + blockIdx.y;
   const int nt = npad >> 5;
   const int rt = blockIdx.x / nt, ct = blockIdx.x % nt;
   const int lane = threadIdx.x & 31;
   const size_t slab = ((size_t)b * Tm1 + iv);
+  const size_t in_slab = (size_t)b * in_Tm1 + blockIdx.y;
   const size_t tile_base = slab * 4 * (size_t)npad * npad + ((size_t)rt * nt + ct) * 4096;
   const float* src[4] = {ca, cb, cc, cd};  // (a,b,c,d) order
   float tsum[3] = {0.f, 0.f, 0.f};
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, 
         } else if (snap) {
           v = hv[p];
         } else {
-          const float2 tv = __ldg(reinterpret_cast<const float2*>(src[p]) + (slab * n + i) * (size_t)n + k);
+          const float2 tv = __ldg(reinterpret_cast<const float2*>(src[p]) + (in_slab * n + i) * (size_t)n + k);
           v = tv.y;
           if (p > 0) tsum[p - 1] += tv.x;
         }
@@ -101,10 +104,10 @@ __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, 
 // Row sums of the four tiled planes, deterministic: one block per 32-row tile walks the column tiles in order
 // (fixed-order warp reductions, no float atomics), so the packed control -- and every accept / reject decision of an
 // adaptive solve built on it -- is reproducible run to run.  grid (nt, T-1, B), block 256.
-__global__ void __launch_bounds__(256) k_adj_rowsums(const float* __restrict__ adj_coef, int n, int npad, int Tm1,
+__global__ void __launch_bounds__(256) k_adj_rowsums(const float* __restrict__ adj_coef, int n, int npad, int Tm1, int piece0,
                                                      float* __restrict__ rowsum) {
   __shared__ __align__(16) float tile[4096];
-  const int b = blockIdx.z, iv = blockIdx.y, rt = blockIdx.x;
+  const int b = blockIdx.z, iv = piece0 + blockIdx.y, rt = blockIdx.x;
   const int nt = npad >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t slab = (size_t)b * Tm1 + iv;
   const float* base = adj_coef + slab * 4 * (size_t)npad * npad + (size_t)rt * nt * 4096;
@@ -134,14 +137,16 @@ __global__ void __launch_bounds__(256) k_adj_rowsums(const float* __restrict__ a
   }
 }
 
-// total[slab][p] = sum_i rowsum[slab][p][i] in a fixed order.  grid (slabs * 4), block 256.
-__global__ void __launch_bounds__(256) k_adj_totals(const float* __restrict__ rowsum, int n, float* __restrict__ total) {
+// total[slab][p] = sum_i rowsum[slab][p][i] in a fixed order.  grid (4 * pieces, B), block 256.
+__global__ void __launch_bounds__(256) k_adj_totals(const float* __restrict__ rowsum, int n, int Tm1, int piece0,
+                                                    float* __restrict__ total) {
   __shared__ float sh[33];
-  const float* r = rowsum + (size_t)blockIdx.x * n;
+  const size_t idx = ((size_t)blockIdx.y * Tm1 + piece0) * 4 + blockIdx.x;   // (slab, plane)
+  const float* r = rowsum + idx * n;
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += 256) acc += r[i];
   const float t = block_sum(acc, sh);
-  if (threadIdx.x == 0) total[blockIdx.x] = t;
+  if (threadIdx.x == 0) total[idx] = t;
 }
 
 __global__ void k_fill_tch_unit(float* __restrict__ tch, int n, size_t slabs) {

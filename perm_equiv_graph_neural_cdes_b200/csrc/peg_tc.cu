@@ -696,7 +696,9 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   }
   TcParams p;
   p.a = a;
-  p.nd = pick_nd(d, bwd ? 128 : 256);
+  int nd_max = bwd ? 128 : 256;
+  if (const char* ev = getenv("PEG_TC_ND_MAX")) { int v = atoi(ev); if (v >= 32 && v <= nd_max) nd_max = v; }
+  p.nd = pick_nd(d, nd_max);
   p.nsplit = (dm.flags & PEG_FLAG_TF32_FAST) ? 1 : 3;
   p.nkc = npad / 32;
   const int na = bwd ? 2 : 1, sp = p.nsplit == 3 ? 2 : 1;

@@ -521,27 +521,31 @@ size_t pegncde_workspace_bytes(const PegDims* dims, int32_t which, int32_t steps
 
 static int pack_common(peg_stream_t stream, const PegDims* dims, const float* d, const float* c, const float* b,
                        const float* a, const float* planar, const float* snap, const float* ts, float* adj_coef,
-                       float* adj_rowsum, float* adj_diag, float* adj_total, float* tch_coef) {
+                       float* adj_rowsum, float* adj_diag, float* adj_total, float* tch_coef, int piece0 = 0, int count = -1) {
   PEG_TRY(check_dims(dims));
   if (!adj_rowsum || !adj_diag || !adj_total || !tch_coef) return PEG_ERR_NULL_POINTER;
   cudaStream_t st = (cudaStream_t)stream;
   const int Tm1 = dims->T - 1;
-  const size_t slabs = (size_t)dims->B * Tm1;
+  if (count < 0) count = Tm1;
+  if (piece0 < 0 || count < 1 || piece0 + count > Tm1) return PEG_ERR_BAD_DIMS;
   const int nt = dims->ldn / 32;
-  dim3 grid(nt * nt, Tm1, dims->B);
+  dim3 grid(nt * nt, count, dims->B);
   const bool unit_time = planar || snap;   // no time channel in the source: d(time)/dt == 1
-  if (!unit_time) PEG_CUDA(cudaMemsetAsync(tch_coef, 0, slabs * 3 * dims->n * sizeof(float), st));
-  k_pack_adj<<<grid, 256, 0, st>>>(d, c, b, a, planar, snap, ts, dims->n, dims->ldn, Tm1, adj_coef, adj_rowsum, adj_diag,
-                                   adj_total, tch_coef);
+  if (!unit_time)   // column means of the time channel are accumulated over the row tiles: zero the pieces of this range
+    PEG_CUDA(cudaMemset2DAsync(tch_coef + (size_t)piece0 * 3 * dims->n, (size_t)Tm1 * 3 * dims->n * sizeof(float), 0,
+                               (size_t)count * 3 * dims->n * sizeof(float), dims->B, st));
+  k_pack_adj<<<grid, 256, 0, st>>>(d, c, b, a, planar, snap, ts, dims->n, dims->ldn, Tm1, piece0, count, adj_coef, adj_rowsum,
+                                   adj_diag, adj_total, tch_coef);
   PEG_LAUNCH_CHECK();
   {   // row sums and totals of the tiled planes, reduced in a fixed order (deterministic)
     const float* tiled = planar ? planar : adj_coef;
-    k_adj_rowsums<<<dim3(nt, Tm1, dims->B), 256, 0, st>>>(tiled, dims->n, dims->ldn, Tm1, adj_rowsum);
+    k_adj_rowsums<<<dim3(nt, count, dims->B), 256, 0, st>>>(tiled, dims->n, dims->ldn, Tm1, piece0, adj_rowsum);
     PEG_LAUNCH_CHECK();
-    k_adj_totals<<<(unsigned)(slabs * 4), 256, 0, st>>>(adj_rowsum, dims->n, adj_total);
+    k_adj_totals<<<dim3(4 * count, dims->B), 256, 0, st>>>(adj_rowsum, dims->n, Tm1, piece0, adj_total);
     PEG_LAUNCH_CHECK();
   }
   if (unit_time) {
+    const size_t slabs = (size_t)dims->B * Tm1;
     const size_t cnt = slabs * 3 * dims->n;
     k_fill_tch_unit<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(tch_coef, dims->n, slabs);
     PEG_LAUNCH_CHECK();
@@ -554,6 +558,14 @@ int pegncde_pack_adj(peg_stream_t stream, const PegDims* dims, const float* d, c
                      float* tch_coef) {
   if (!d || !c || !b || !a || !adj_coef) return PEG_ERR_NULL_POINTER;
   return pack_common(stream, dims, d, c, b, a, nullptr, nullptr, nullptr, adj_coef, adj_rowsum, adj_diag, adj_total, tch_coef);
+}
+
+int pegncde_pack_adj_range(peg_stream_t stream, const PegDims* dims, int32_t piece_begin, int32_t piece_count, const float* d,
+                           const float* c, const float* b, const float* a, float* adj_coef, float* adj_rowsum, float* adj_diag,
+                           float* adj_total, float* tch_coef) {
+  if (!d || !c || !b || !a || !adj_coef) return PEG_ERR_NULL_POINTER;
+  return pack_common(stream, dims, d, c, b, a, nullptr, nullptr, nullptr, adj_coef, adj_rowsum, adj_diag, adj_total, tch_coef,
+                     piece_begin, piece_count);
 }
 
 int pegncde_adj_stats(peg_stream_t stream, const PegDims* dims, const float* adj_coef, float* adj_rowsum,

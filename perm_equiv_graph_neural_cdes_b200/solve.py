@@ -148,10 +148,22 @@ class _SolveFunction(torch.autograd.Function):
             free = torch.cuda.mem_get_info(dev)[0] if not capturing else float("inf")
             if nbytes_store < 0.5 * free:   # otherwise fall back to checkpoint-per-step + recompute
                 store = torch.empty(nbytes_store // 4, dtype=torch.float32, device=dev)
-        check(l.pegncde_solve_fwd(_stream_ptr(dev), dims, ctl, flat.data_ptr(),
-                                  host_ts.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), S, y0.data_ptr(), None,
-                                  y_ckpt.data_ptr(), store.data_ptr() if store is not None else None, ws.data_ptr(),
-                                  ws.numel()), "pegncde_solve_fwd")
+        def run_steps(s0, s1):   # solver steps [s0, s1) -- the whole table in one call unless the control is streamed
+            start = y0 if s0 == 0 else y_ckpt[s0].clone()
+            seg_ts = np.ascontiguousarray(host_ts[s0:s1 + 1])
+            st_elems = y0.numel()
+            store_ptr = None if store is None else store.data_ptr() + 4 * s0 * 6 * dims.L * st_elems
+            check(l.pegncde_solve_fwd(_stream_ptr(dev), dims, ctl, flat.data_ptr(),
+                                      seg_ts.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), s1 - s0, start.data_ptr(), None,
+                                      y_ckpt[s0].data_ptr(), store_ptr, ws.data_ptr(), ws.numel()), "pegncde_solve_fwd")
+
+        if pc.pending is None:
+            run_steps(0, S)
+        elif pc.host_ts is None:
+            pc.materialize()
+            run_steps(0, S)
+        else:
+            _stream_pieces(pc, host_ts, run_steps)
         ctx.save_for_backward(flat, y_ckpt)
         ctx.store = store
         ctx.pc, ctx.dims, ctx.host_ts, ctx.S, ctx.save_steps = pc, dims, host_ts, S, save_steps
@@ -183,6 +195,48 @@ class _SolveFunction(torch.autograd.Function):
                                   g_flat.data_ptr(), g_x.data_ptr() if g_x is not None else None, ws.data_ptr(), ws.numel()), "pegncde_solve_bwd")
         ctx.store = None
         return g_y0, g_flat, g_x, None, None, None, None, None
+
+
+def _stream_pieces(pc, step_ts, run_steps) -> None:
+    """Streamed control (host coefficient arrays): copy + pack cubic piece i+1 on a side stream while the solver steps that
+    end inside piece i run on the main stream.  A step may start once the piece holding its end time is packed (the lookup
+    is left-continuous like diffrax's: index = searchsorted(ts, t, 'left') - 1)."""
+    dev = pc.device
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(main)
+    B, Tm1, n = pc.B, pc.T - 1, pc.n
+    S = len(step_ts) - 1
+    piece_of_step = np.clip(np.searchsorted(pc.host_ts, step_ts[1:], side="left") - 1, 0, Tm1 - 1)
+    staging = [[torch.empty((B, 1, n, n, 2), dtype=torch.float32, device=dev) for _ in range(4)] for _ in range(2)]
+    packed_ev = [None, None]
+    done = 0
+    for iv in range(Tm1):
+        buf = staging[iv & 1]
+        with torch.cuda.stream(side):
+            if packed_ev[iv & 1] is not None:
+                side.wait_event(packed_ev[iv & 1])          # the pack that last read this staging buffer has finished
+            for q in range(4):
+                for b in range(B):
+                    buf[q][b, 0].copy_(pc.pending[q][b, iv], non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(side)
+        main.wait_event(copied)
+        pc.pack_pieces(iv, 1, buf, main.cuda_stream)
+        packed_ev[iv & 1] = torch.cuda.Event()
+        packed_ev[iv & 1].record(main)
+        end = done
+        while end < S and piece_of_step[end] <= iv:
+            end += 1
+        if end > done:
+            run_steps(done, end)
+            done = end
+    if done < S:
+        run_steps(done, S)
+    for buf in staging:
+        for t in buf:
+            t.record_stream(side)
+    pc.pending = None
 
 
 def _unwrap(term):
@@ -225,6 +279,7 @@ def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: Optional[S
     if yb.shape[0] != pc.B:
         raise ValueError(f"state batch {yb.shape[0]} != control batch {pc.B}")
     if adaptive:
+        pc.materialize()
         return _diffeqsolve_adaptive(vf, wrapped, pc, t0, t1, dt0, yb, unb, controller, saveat, max_steps)
     step_ts = constant_step_table(float(t0), float(t1), float(dt0), controller.rule, max_steps)
     out = _SolveFunction.apply(yb, vf.flat_params(), pc.x_packed, pc, dims, step_ts, bool(saveat.steps), bool(getattr(vf, "store_stages", True)))
@@ -407,7 +462,7 @@ def tsit5_step(vf_term, t: float, dt: float, y: torch.Tensor, args, k1: Optional
         control_adj, control_data = args
     else:
         control_adj, control_data = (args[0] if isinstance(args, (list, tuple)) else args), None
-    pc = resolve_control(control_adj, control_data, y.device)
+    pc = resolve_control(control_adj, control_data, y.device).materialize()
     dims = vf.dims_for(pc, with_wrapper=wrapped)
     unb = y.dim() == 2
     yb = (y.unsqueeze(0) if unb else y).to(torch.float32).contiguous()

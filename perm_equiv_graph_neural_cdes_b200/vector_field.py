@@ -248,7 +248,7 @@ class _VFFunction(torch.autograd.Function):
 def fused_vector_field(vf: PermEquivGraphVectorField, t, y: torch.Tensor, control_adj, control_data) -> torch.Tensor:
     if y.device.type != "cuda":
         raise RuntimeError("the fused vector field runs on CUDA only (no CPU fallback)")
-    pc = resolve_control(control_adj, control_data, y.device)
+    pc = resolve_control(control_adj, control_data, y.device).materialize()
     dims = vf.dims_for(pc, with_wrapper=control_data is not None or (isinstance(control_adj, PackedControl) and vf.uses_control()))
     unb = y.dim() == 2
     yb = y.unsqueeze(0) if unb else y

@@ -544,3 +544,48 @@ def test_adaptive_solve_at_c1_heat_shape(cuda):
     g = y0.grad.detach().double().cpu()
     assert float((g - g64).norm() / g64.norm()) < 5e-3
     assert rel_err(g, g64) < 3e-2
+
+
+# ---------------------------------------------------------------------------------------------------
+# streamed control: host coefficient arrays, copy + pack of piece i+1 overlapped with the steps inside piece i
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["england_like", "sir_like", "ragged_n"])
+def test_streamed_host_control_is_bit_identical_to_the_resident_one(cuda, case):
+    """pack_control on HOST tensors defers the adjacency planes; the fixed-step solve packs them piece by piece
+    (pegncde_pack_adj_range) and runs the step table in segments.  Same bits as the all-at-once path, forward and backward
+    (sir_like has knots inside the steps, ragged_n a partial last tile)."""
+    p = R.make_problem(**GOLDEN_CASES[case])
+    kw = GOLDEN_CASES[case]
+    outs = []
+    for streamed in (False, True):
+        vf, term, _ = device_model(p, cuda, flags=TC if p.n >= 128 else 0)
+        place = (lambda t: t.to(torch.float32)) if streamed else (lambda t: t.to(torch.float32).to(cuda))
+        ts = p.ts.to(torch.float32)
+        cadj = P.CubicInterpolation(place(ts), tuple(place(c) for c in p.coeffs_adj))
+        args = [cadj, P.CubicInterpolation(place(ts), tuple(place(c) for c in p.x_coeffs))] if p.e > 0 else cadj
+        y0 = p.y0.to(cuda).requires_grad_(True)
+        sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), float(p.ts[0]), float(p.ts[-1]), kw["dt0"], y0, args, saveat=P.SaveAt(steps=True))
+        if streamed:
+            assert cadj._packed.pending is None        # every piece has been packed by the end of the forward solve
+        (sol.ys[-1] * p.gyT.to(cuda)).sum().backward()
+        outs.append((sol.ys.detach().clone(), y0.grad.clone(), cadj._packed.adj_coef.clone(), cadj._packed.adj_rowsum.clone(),
+                     cadj._packed.tch_coef.clone()))
+    a, b = outs
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
+    assert torch.equal(a[0], b[0])
+    assert rel_err(b[1], a[1]) < 1e-6      # parameter-gradient atomics aside, the adjoint sees identical inputs
+
+
+def test_streamed_control_materialises_for_adaptive_and_single_evaluations(cuda):
+    p = R.make_problem(n=40, h=16, e=0, L=2, T=5, t1=2, dt0=0.1, seed=3)
+    vf, term, _ = device_model(p, cuda)
+    ts = p.ts.to(torch.float32)
+    host = P.CubicInterpolation(ts, tuple(c.to(torch.float32) for c in p.coeffs_adj))
+    dev = P.CubicInterpolation(ts.to(cuda), tuple(c.to(torch.float32).to(cuda) for c in p.coeffs_adj))
+    y = p.y0.to(cuda)
+    assert torch.equal(term(0.7, y, host), term(0.7, y, dev))
+    ctrl = P.PIDController(rtol=1e-3, atol=1e-6)
+    host2 = P.CubicInterpolation(ts, tuple(c.to(torch.float32) for c in p.coeffs_adj))
+    s1 = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 2.0, None, y, host2, stepsize_controller=ctrl)
+    s2 = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 2.0, None, y, dev, stepsize_controller=ctrl)
+    assert torch.equal(s1.ys, s2.ys)
