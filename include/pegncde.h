@@ -57,7 +57,9 @@ enum {
 enum {
   PEG_FLAG_RELU = 0,            /* reserved */
   PEG_FLAG_TENSOR_CORES = 1,    /* n x n x d contractions on tcgen05 (3xTF32 split: fp32-parity) */
-  PEG_FLAG_TF32_FAST = 2        /* with TENSOR_CORES: single-pass TF32 (rna-rounded), looser tolerance */
+  PEG_FLAG_TF32_FAST = 2,       /* with TENSOR_CORES: single-pass TF32 (rna-rounded), looser tolerance */
+  PEG_FLAG_DIRECTED = 4         /* ConvEquivFusionDirectedLayer (layers.py:180-362): 11 parameter pairs, row AND column sums;
+                                   needs PegControl.adj_colsum; fusion block = 22 (+2 pad) scalars (see parameter packing) */
 };
 
 typedef struct PegDims {
@@ -86,12 +88,16 @@ typedef struct PegControl {
   const float* tch_coef;   /* [B, T-1, 3, n]    (b,c,d) of the time channel, mean over axis 0       */
   const float* x_coef;     /* [B, T-1, 3, n, 2e] (b,c,d) of the node-signal path, last axis (l,k)
                               interleaved like the reference's [n,e,2]; NULL iff e == 0             */
+  const float* adj_colsum; /* [B, T-1, 4, n]    column sums of each plane (pegncde_adj_colsums); only read with
+                              PEG_FLAG_DIRECTED, NULL otherwise                                     */
 } PegControl;
 
 /* ---- parameter packing ---------------------------------------------------------------
  * params / g_params are one flat fp32 buffer, layer after layer:
  *   weight [d_out, d_in] | bias [d_out] | norm_weight [d_in] | norm_bias [d_in] |
  *   fusion [8,2] = param1[0],param1[1],param2[0],...,param8[1]
+ *   (PEG_FLAG_DIRECTED: fusion [12,2] = param1..param8 as above, then param4_prime, param5_prime, param6_prime and one
+ *    unused pair that keeps the next layer 16-byte aligned)
  * (leaf names: gnn_layers[l].conv_layer.linear.{weight,bias}, .conv_layer.norm.{weight,bias},
  *  gnn_layers[l].param1..param8 -- src/models/vector_fields/layers.py:19-20,66-74). */
 size_t pegncde_param_count(const PegDims* dims);
@@ -120,6 +126,8 @@ int pegncde_adj_stats(peg_stream_t stream, const PegDims* dims, const float* adj
  * The time channel is implied (X_time(t) = t): tch_coef is written as (1, 0, 0). */
 int pegncde_build_adj(peg_stream_t stream, const PegDims* dims, const float* ts, const float* snapshots, float* adj_coef,
                       float* adj_rowsum, float* adj_diag, float* adj_total, float* tch_coef);
+/* column sums of the tiled planes (fixed summation order) -> adj_colsum [B, T-1, 4, n]; needed by PEG_FLAG_DIRECTED only */
+int pegncde_adj_colsums(peg_stream_t stream, const PegDims* dims, const float* adj_coef, float* adj_colsum);
 /* d,c,b,a each [B, T-1, n, e, 2] -> x_coef [B, T-1, 3, n, 2e] */
 int pegncde_pack_x(peg_stream_t stream, const PegDims* dims, const float* d, const float* c, const float* b,
                    const float* a, float* x_coef);

@@ -197,6 +197,44 @@ def perm_equiv_vector_field(t, y, control_adj: CubicInterpolation, layers: List[
     return t_gradient[:, None] * node_features
 
 
+def fusion_directed(adjacency: torch.Tensor, control_gradient: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
+    """ConvEquivFusionDirectedLayer._fusion, layers.py:256-345, term by term.  p [11, 2] rows = param1, param2, param3, param4,
+    param4_prime, param5, param5_prime, param6, param6_prime, param7, param8 (the class's field order).  Quirks kept: term 4'
+    pairs rowsum(A) with colsum(A') (``:288-292``), term 7 uses sum(adjacency) for both coefficients (``:317-321``)."""
+    n = adjacency.shape[0]
+    A, D = adjacency, control_gradient
+    eye = torch.eye(n, dtype=A.dtype)
+    ones = torch.ones((n, n), dtype=A.dtype)
+    col = lambda X: X.sum(dim=0)   # jnp.sum(., axis=0)
+    row = lambda X: X.sum(dim=1)   # jnp.sum(., axis=1)
+    tile = lambda v: v[None, :].expand(n, n)          # jnp.tile(v, (n, 1)): every row is v
+    term_1 = (1.0 + p[0, 0]) * A + (1.0 + p[0, 1]) * D
+    term_2 = p[1, 0] * A.t() + p[1, 1] * D.t()
+    term_3 = p[2, 0] * torch.diag(torch.diag(A)) + p[2, 1] * torch.diag(torch.diag(D))
+    term_4 = p[3, 0] / n * tile(col(A)).t() + p[3, 1] / n * tile(col(D)).t()
+    term_4p = p[4, 0] / n * tile(row(A)) + p[4, 1] / n * tile(col(D))
+    term_5 = p[5, 0] / n * tile(col(A)) + p[5, 1] / n * tile(col(D))
+    term_5p = p[6, 0] / n * tile(row(A)) + p[6, 1] / n * tile(row(D))
+    term_6 = p[7, 0] / n * torch.diag(col(A)) + p[7, 1] / n * torch.diag(col(D))
+    term_6p = p[8, 0] / n * torch.diag(row(A)) + p[8, 1] / n * torch.diag(row(D))
+    term_7 = p[9, 0] / n**2 * ones * A.sum() + p[9, 1] / n**2 * ones * A.sum()
+    term_8 = (p[10, 0] * A.sum() + p[10, 1] * D.sum()) / n**2 * eye
+    return term_1 + term_2 + term_3 + term_4 + term_4p + term_5 + term_5p + term_6 + term_6p + term_7 + term_8
+
+
+def perm_equiv_dir_vector_field(t, y, control_adj: CubicInterpolation, layers: List[LayerParams], fusions: Sequence[torch.Tensor]):
+    """PermEquivDirGraphVectorField.__call__ (perm_equiv_dir_graph_vector_field.py:86-130, enc_idx=False); ``fusions[l]`` is
+    the [11, 2] parameter table of layer l (``layers[l].fusion`` is ignored)."""
+    value, deriv = control_adj.evaluate(t), control_adj.derivative(t)
+    adj, adj_derivative, t_gradient = value[..., -1], deriv[..., -1], deriv[..., 0]
+    z = y
+    for i, (lp, pf) in enumerate(zip(layers, fusions)):
+        z = conv_layer(z, fusion_directed(adj, adj_derivative, pf), lp)
+        if i < len(layers) - 1:
+            z = torch.relu(z)
+    return t_gradient.mean(dim=0)[:, None] * z
+
+
 def plain_graph_vector_field(t, y, control_adj: CubicInterpolation, layers: List[LayerParams], with_derivative: bool):
     """GraphVectorField.__call__ (graph_vector_field.py:80-115, enc_idx=False; message passing matrix A + A') and
     GNODEVectorField.__call__ (gnode_vector_field.py:57-81; A only): plain ConvLayers, ReLU between, time-gradient scale."""

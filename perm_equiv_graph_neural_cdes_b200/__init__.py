@@ -12,7 +12,7 @@ from .control import CubicInterpolation, PackedControl, backward_hermite_coeffic
 from .models import MLP, GraphNeuralCDE, PGTGraphNeuralCDE, TGBGraphNeuralCDE  # noqa: E402,F401
 from .solve import (ConstantStepSize, ODETerm, PIDController, SaveAt, Solution, Tsit5, clip_to_end, constant_step_table,  # noqa: E402,F401
                     dense_weights, diffeqsolve, tsit5_step)  # noqa: E402,F401
-from .vector_field import (CDEWrapperVectorField, ConvEquivFusionLayer, ConvLayer, GNODEVectorField, GraphVectorField,  # noqa: E402,F401
-                           PermEquivGraphVectorField)  # noqa: E402,F401
+from .vector_field import (CDEWrapperVectorField, ConvEquivFusionDirectedLayer, ConvEquivFusionLayer, ConvLayer,  # noqa: E402,F401
+                           GNODEVectorField, GraphVectorField, PermEquivDirGraphVectorField, PermEquivGraphVectorField)  # noqa: E402,F401
 
 __version__ = "0.1.0"

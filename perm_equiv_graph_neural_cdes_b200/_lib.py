@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libpegncde.so")
 
 PEG_FLAG_TENSOR_CORES = 1
 PEG_FLAG_TF32_FAST = 2
+PEG_FLAG_DIRECTED = 4
 
 PEG_WS_VF_FWD, PEG_WS_VF_VJP, PEG_WS_SOLVE_FWD, PEG_WS_SOLVE_BWD, PEG_WS_STEP = range(5)
 
@@ -23,7 +24,7 @@ class PegDims(Structure):
 
 
 class PegControl(Structure):
-    _fields_ = [(k, c_void_p) for k in ("ts", "adj_coef", "adj_rowsum", "adj_diag", "adj_total", "tch_coef", "x_coef")]
+    _fields_ = [(k, c_void_p) for k in ("ts", "adj_coef", "adj_rowsum", "adj_diag", "adj_total", "tch_coef", "x_coef", "adj_colsum")]
 
 
 class PegError(RuntimeError):
@@ -49,6 +50,7 @@ SIGNATURES = {
     "pegncde_pack_adj_range": (c_int, [_P, _DIMS, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pegncde_adj_stats": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P]),
     "pegncde_build_adj": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P, _P, _P]),
+    "pegncde_adj_colsums": (c_int, [_P, _DIMS, _P, _P]),
     "pegncde_pack_x": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P]),
     "pegncde_workspace_bytes": (c_size_t, [_DIMS, c_int32, c_int32]),
     "pegncde_vf_fwd": (c_int, [_P, _DIMS, _CTL, _P, c_float, _P, _P, _P, c_size_t]),

@@ -99,6 +99,7 @@ class PackedControl:
         self.tch_coef = torch.empty((B, T - 1, 3, n), **f)
         self.x_coef = torch.empty((B, T - 1, 3, n, 2 * e), **f) if e > 0 else None
         self.x_packed = None   # differentiable source of x_coef when the node-signal coefficients require grad
+        self.adj_colsum = None  # [B,T-1,4,n] column sums of the planes: built on demand (directed fusion layer only)
         self.pending = None    # host (d,c,b,a) arrays whose adjacency planes have not been copied / packed yet (streamed)
         self.host_ts = None    # knot times shared by the batch (streaming needs one time grid), numpy fp32
 
@@ -127,6 +128,8 @@ class PackedControl:
             setattr(v, name, getattr(self, name)[b:b + 1])
         v.x_coef = self.x_coef[b:b + 1] if self.x_coef is not None else None
         v.x_packed = None
+        cs = getattr(self, "adj_colsum", None)
+        v.adj_colsum = cs[b:b + 1] if cs is not None else None
         v.pending, v.host_ts = None, None
         v._keepalive = self
         return v
@@ -144,7 +147,17 @@ class PackedControl:
         return PegControl(
             self.ts.data_ptr(), self.adj_coef.data_ptr(), self.adj_rowsum.data_ptr(), self.adj_diag.data_ptr(),
             self.adj_total.data_ptr(), self.tch_coef.data_ptr(), self.x_coef.data_ptr() if self.x_coef is not None else None,
+            self.adj_colsum.data_ptr() if self.adj_colsum is not None else None,
         )
+
+    def ensure_colsums(self) -> "PackedControl":
+        """Column sums of the planes (``pegncde_adj_colsums``), needed by ``PEG_FLAG_DIRECTED`` only; computed once."""
+        if self.adj_colsum is None:
+            self.materialize()
+            self.adj_colsum = torch.empty((self.B, self.T - 1, 4, self.n), dtype=torch.float32, device=self.device)
+            check(lib().pegncde_adj_colsums(_stream_ptr(self.device), self.dims(h=4, L=1), self.adj_coef.data_ptr(),
+                                            self.adj_colsum.data_ptr()), "pegncde_adj_colsums")
+        return self
 
     @property
     def device(self):

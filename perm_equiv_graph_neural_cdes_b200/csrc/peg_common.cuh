@@ -19,6 +19,7 @@ struct LayerDesc {
 
 struct Model {
   int L;
+  int directed;  // ConvEquivFusionDirectedLayer: fusion block of 22 scalars (param4', 5', 6' appended)
   int P;  // total parameter count
   int dmax;
   LayerDesc layer[PEG_MAX_LAYERS];
@@ -37,9 +38,9 @@ struct StageScalars {
 
 // Per-graph stage vectors live in one float array `svec` laid out as
 //   [b][ (3*L + 1) * n + n * 2e ]  =  v_l[n], r_l[n], c_l[n] for l < L ; tg[n] ; xd[n, 2e]
-// plus rA, rD, dgA, dgD [4][n] (needed by the fusion-parameter gradients).
+// plus rA, rD, dgA, dgD, cA, cD [6][n] (needed by the fusion-parameter gradients; cA, cD = column sums, directed only).
 __host__ __device__ inline size_t svec_stride(int n, int L, int e) {
-  return (size_t)(3 * L + 1 + 4) * n + (size_t)n * 2 * e;
+  return (size_t)(3 * L + 1 + 6) * n + (size_t)n * 2 * e;
 }
 __host__ __device__ inline size_t svec_v(int n, int l) { return (size_t)(3 * l + 0) * n; }
 __host__ __device__ inline size_t svec_r(int n, int l) { return (size_t)(3 * l + 1) * n; }
@@ -49,7 +50,9 @@ __host__ __device__ inline size_t svec_rA(int n, int L) { return (size_t)(3 * L 
 __host__ __device__ inline size_t svec_rD(int n, int L) { return (size_t)(3 * L + 2) * n; }
 __host__ __device__ inline size_t svec_dgA(int n, int L) { return (size_t)(3 * L + 3) * n; }
 __host__ __device__ inline size_t svec_dgD(int n, int L) { return (size_t)(3 * L + 4) * n; }
-__host__ __device__ inline size_t svec_xd(int n, int L) { return (size_t)(3 * L + 5) * n; }
+__host__ __device__ inline size_t svec_cA(int n, int L) { return (size_t)(3 * L + 5) * n; }   // column sums (directed layer only)
+__host__ __device__ inline size_t svec_cD(int n, int L) { return (size_t)(3 * L + 6) * n; }
+__host__ __device__ inline size_t svec_xd(int n, int L) { return (size_t)(3 * L + 7) * n; }
 
 // ---- HBM layout of the cubic-coefficient planes (adjacency channel) -----------------------------------
 // One slab = the four planes (a,b,c,d) of one cubic piece of one graph, npad x npad with npad = n rounded

@@ -156,6 +156,40 @@ __global__ void k_fill_tch_unit(float* __restrict__ tch, int n, size_t slabs) {
   tch[idx] = p == 0 ? 1.f : 0.f;
 }
 
+// Column sums of the four tiled planes (directed fusion layer: layers.py:256-345 uses jnp.sum(., axis=0)), deterministic:
+// one block per 32-column tile walks the row tiles in order; thread (warp w, lane c) keeps rows 4w..4w+3 of column c.
+// grid (nt, T-1, B), block 256.
+__global__ void __launch_bounds__(256) k_adj_colsums(const float* __restrict__ adj_coef, int n, int npad, int Tm1,
+                                                     float* __restrict__ colsum) {
+  __shared__ __align__(16) float tile[4096];
+  __shared__ float part[8][4][32];
+  const int b = blockIdx.z, iv = blockIdx.y, ct = blockIdx.x;
+  const int nt = npad >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t slab = (size_t)b * Tm1 + iv;
+  const float* base = adj_coef + slab * 4 * (size_t)npad * npad;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int rt = 0; rt < nt; ++rt) {
+    for (int idx = threadIdx.x; idx < 1024; idx += 256)
+      *reinterpret_cast<float4*>(&tile[4 * idx]) = *reinterpret_cast<const float4*>(base + ((size_t)rt * nt + ct) * 4096 + 4 * idx);
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) acc[p] += tile[peg_tile_off(4 * warp + rr, lane, p, 1)];
+    __syncthreads();
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) part[warp][p][lane] = acc[p];
+  __syncthreads();
+  if (warp < 4) {   // plane = warp, column = lane: add the 8 row groups in a fixed order
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += part[w8][warp][lane];
+    const int k = ct * 32 + lane;
+    if (k < n) colsum[(slab * 4 + warp) * n + k] = t;
+  }
+}
+
 // x coeffs: d,c,b,a each [B,T-1,n,e,2] -> x_coef [B,T-1,3,n,2e] (b,c,d)
 __global__ void k_pack_x(const float* __restrict__ cd, const float* __restrict__ cc, const float* __restrict__ cb,
                          int n, int e2, size_t slabs, float* __restrict__ x_coef) {
@@ -219,6 +253,7 @@ __global__ void __launch_bounds__(256) k_stage_prep(PrepArgs a) {
   const float* rs = a.ctl.adj_rowsum + slab * 4 * n;
   const float* dg = a.ctl.adj_diag + slab * 4 * n;
   const float* tc = a.ctl.tch_coef + slab * 3 * n;
+  const float* cs = a.model.directed ? a.ctl.adj_colsum + slab * 4 * n : nullptr;
   for (int i = blockIdx.x * blockDim.x + tid; i < n; i += gridDim.x * blockDim.x) {
     const float rA = wA[0] * rs[i] + wA[1] * rs[n + i] + wA[2] * rs[2 * n + i] + wA[3] * rs[3 * n + i];
     const float rD = wD[1] * rs[n + i] + wD[2] * rs[2 * n + i] + wD[3] * rs[3 * n + i];
@@ -228,11 +263,27 @@ __global__ void __launch_bounds__(256) k_stage_prep(PrepArgs a) {
     sv[svec_rD(n, L) + i] = rD;
     sv[svec_dgA(n, L) + i] = dA;
     sv[svec_dgD(n, L) + i] = dD;
+    float cA = 0.f, cD = 0.f;
+    if (cs) {
+      cA = wA[0] * cs[i] + wA[1] * cs[n + i] + wA[2] * cs[2 * n + i] + wA[3] * cs[3 * n + i];
+      cD = wD[1] * cs[n + i] + wD[2] * cs[2 * n + i] + wD[3] * cs[3 * n + i];
+      sv[svec_cA(n, L) + i] = cA;
+      sv[svec_cD(n, L) + i] = cD;
+    }
     for (int l = 0; l < L; ++l) {
       const float* f = a.params + a.model.layer[l].fus_off;
-      sv[svec_v(n, l) + i] = f[4] * dA + f[5] * dD + (f[10] * rA + f[11] * rD) * inv_n + (f[14] * totA + f[15] * totD) * inv_n2;
-      sv[svec_r(n, l) + i] = (f[6] * rA + f[7] * rD) * inv_n;
-      sv[svec_c(n, l) + i] = (f[8] * rA + f[9] * rD) * inv_n;
+      if (!cs) {   // ConvEquivFusionLayer (layers.py:102-160): row sums only
+        sv[svec_v(n, l) + i] = f[4] * dA + f[5] * dD + (f[10] * rA + f[11] * rD) * inv_n + (f[14] * totA + f[15] * totD) * inv_n2;
+        sv[svec_r(n, l) + i] = (f[6] * rA + f[7] * rD) * inv_n;
+        sv[svec_c(n, l) + i] = (f[8] * rA + f[9] * rD) * inv_n;
+      } else {     // ConvEquivFusionDirectedLayer (layers.py:256-345); f[16..21] = param4', param5', param6'
+        // term 6 / 6': diag(colsum), diag(rowsum); term 4: colsum_i on row i; term 4': rowsum(A)_j, colsum(A')_j (reference quirk:
+        // axis=0 for the derivative) on column j; term 5: colsum_j; term 5': rowsum_j
+        sv[svec_v(n, l) + i] = f[4] * dA + f[5] * dD + (f[10] * cA + f[11] * cD) * inv_n + (f[20] * rA + f[21] * rD) * inv_n +
+                               (f[14] * totA + f[15] * totD) * inv_n2;
+        sv[svec_r(n, l) + i] = (f[6] * cA + f[7] * cD) * inv_n;
+        sv[svec_c(n, l) + i] = (f[16] * rA + f[17] * cD) * inv_n + (f[8] * cA + f[9] * cD) * inv_n + (f[18] * rA + f[19] * rD) * inv_n;
+      }
     }
     sv[svec_tg(n, L) + i] = tc[i] + s * (2.f * tc[n + i] + 3.f * s * tc[2 * n + i]);
   }
@@ -784,19 +835,20 @@ struct FusGradArgs {
   const float* svec;
   size_t sv_stride;
   int n, d, L;
+  int directed;
   float* g_fus;
 };
 __global__ void __launch_bounds__(256) k_fusion_vec_grads(FusGradArgs a) {
-  __shared__ float sh[8][12];
+  __shared__ float sh[8][16];
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + warp;
   const int n = a.n, d = a.d;
   const float* sv = a.svec + (size_t)b * a.sv_stride;
   const float* sM = a.cbM + (size_t)b * 2 * d;
   const float* sG = a.cbG + (size_t)b * 2 * d;
-  float part[11];
+  float part[16];
 #pragma unroll
-  for (int k = 0; k < 11; ++k) part[k] = 0.f;
+  for (int k = 0; k < 16; ++k) part[k] = 0.f;
   if (i < n) {
     const float* g = a.G + ((size_t)b * n + i) * d;
     const float* m = a.M + ((size_t)b * n + i) * d;
@@ -811,10 +863,20 @@ __global__ void __launch_bounds__(256) k_fusion_vec_grads(FusGradArgs a) {
     const float rA = sv[svec_rA(n, a.L) + i], rD = sv[svec_rD(n, a.L) + i];
     const float dA = sv[svec_dgA(n, a.L) + i], dD = sv[svec_dgD(n, a.L) + i];
     part[0] = dA * q; part[1] = dD * q;      // param3
-    part[2] = rA * u; part[3] = rD * u;      // param4 (/n)
-    part[4] = rA * w; part[5] = rD * w;      // param5 (/n)
-    part[6] = rA * q; part[7] = rD * q;      // param6 (/n)
     part[8] = q;                              // param8 (* tot / n^2)
+    if (!a.directed) {
+      part[2] = rA * u; part[3] = rD * u;      // param4 (/n)
+      part[4] = rA * w; part[5] = rD * w;      // param5 (/n)
+      part[6] = rA * q; part[7] = rD * q;      // param6 (/n)
+    } else {
+      const float cA = sv[svec_cA(n, a.L) + i], cD = sv[svec_cD(n, a.L) + i];
+      part[2] = cA * u; part[3] = cD * u;      // param4: colsum_i (1^T M) on row i
+      part[4] = cA * w; part[5] = cD * w;      // param5: colsum_j on column j
+      part[6] = cA * q; part[7] = cD * q;      // param6: diag(colsum)
+      part[10] = rA * w; part[11] = cD * w;    // param4': rowsum(A)_j, colsum(A')_j on column j
+      part[12] = rA * w; part[13] = rD * w;    // param5': rowsum_j on column j
+      part[14] = rA * q; part[15] = rD * q;    // param6': diag(rowsum)
+    }
   }
   if (blockIdx.x == 0 && warp == 0) {        // param7: tot_A / n^2 * (1^T G . 1^T M), once per graph
     float t = 0.f;
@@ -823,9 +885,15 @@ __global__ void __launch_bounds__(256) k_fusion_vec_grads(FusGradArgs a) {
   }
   if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < 10; ++k) sh[warp][k] = part[k];
+    for (int k = 0; k < 16; ++k) sh[warp][k] = part[k];
   }
   __syncthreads();
+  if (a.directed && threadIdx.x >= 10 && threadIdx.x < 16) {   // param4', param5', param6' live at g_fus[16..21]
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += sh[w8][threadIdx.x];
+    atomicAdd(a.g_fus + 16 + (threadIdx.x - 10), t / (float)n);
+  }
   if (threadIdx.x < 10) {
     float t = 0.f;
 #pragma unroll

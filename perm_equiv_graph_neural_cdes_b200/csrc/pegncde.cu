@@ -92,6 +92,7 @@ static Model make_model(const PegDims& d) {
   Model m;
   memset(&m, 0, sizeof(m));
   m.L = d.L;
+  m.directed = (d.flags & PEG_FLAG_DIRECTED) ? 1 : 0;
   long long off = 0;
   int dmax = d.h;
   for (int l = 0; l < d.L; ++l) {
@@ -103,7 +104,7 @@ static Model make_model(const PegDims& d) {
     ld.b_off = off;  off += ld.dout;
     ld.nw_off = off; off += ld.din;
     ld.nb_off = off; off += ld.din;
-    ld.fus_off = off; off += 16;
+    ld.fus_off = off; off += m.directed ? 24 : 16;   // 22 scalars + 2 of padding: every block stays 16-byte aligned
   }
   m.P = (int)off;
   m.dmax = dmax;
@@ -342,13 +343,14 @@ static int feval_vjp(Ctx& c, float t, float* const* zin, const float* kbar, floa
     // recompute M_l (and the normalised input N_l) from the saved layer input; 1^T M comes out of the same kernel
     PEG_TRY(norm_linear(c, l, zin[l], c.w.M, c.w.N, producer_out(c, ld.dout, false, c.w.colM, false, 0)));
     if (!obar_ready) PEG_TRY(colsums(c, c.w.Obar, ld.dout, svec_r(d.n, l), true, c.w.colG));
-    const bool fused_vec_grads = contract_on_tc(c, l);   // the tcgen05 adjoint epilogue also emits the param3..8 gradients
+    // the tcgen05 adjoint epilogue also emits the param3..8 gradients (undirected layer; the directed one keeps the separate kernel)
+    const bool fused_vec_grads = contract_on_tc(c, l) && !c.m.directed;
     PEG_TRY(contract(c, l, true, c.w.Obar, c.w.M, c.w.colG, c.w.Mbar, false, false, g_fus, obar_vt, fused_vec_grads ? c.w.colM : nullptr));
     if (!fused_vec_grads) {
       FusGradArgs a;
       a.G = c.w.Obar; a.M = c.w.M; a.cbM = c.w.colM; a.cbG = c.w.colG;
       a.sc = c.w.sc; a.svec = c.w.svec; a.sv_stride = c.sv_stride;
-      a.n = d.n; a.d = ld.dout; a.L = d.L; a.g_fus = g_fus;
+      a.n = d.n; a.d = ld.dout; a.L = d.L; a.g_fus = g_fus; a.directed = c.m.directed;
       dim3 grid((d.n + 7) / 8, d.B);
       k_fusion_vec_grads<<<grid, 256, 0, c.st>>>(a);
       PEG_LAUNCH_CHECK();
@@ -417,6 +419,7 @@ static int make_ctx(Ctx& c, peg_stream_t stream, const PegDims* dims, const PegC
   if (!ctl->ts || !ctl->adj_coef || !ctl->adj_rowsum || !ctl->adj_diag || !ctl->adj_total || !ctl->tch_coef)
     return PEG_ERR_NULL_POINTER;
   if (dims->e > 0 && !ctl->x_coef) return PEG_ERR_NULL_POINTER;
+  if ((dims->flags & PEG_FLAG_DIRECTED) && !ctl->adj_colsum) return PEG_ERR_NULL_POINTER;
   if (((uintptr_t)ctl->adj_coef & 15) != 0) return PEG_ERR_ALIGNMENT;
   c.st = (cudaStream_t)stream;
   c.d = *dims;
@@ -580,6 +583,15 @@ int pegncde_build_adj(peg_stream_t stream, const PegDims* dims, const float* ts,
   if (!ts || !snapshots || !adj_coef) return PEG_ERR_NULL_POINTER;
   return pack_common(stream, dims, nullptr, nullptr, nullptr, nullptr, nullptr, snapshots, ts, adj_coef, adj_rowsum,
                      adj_diag, adj_total, tch_coef);
+}
+
+int pegncde_adj_colsums(peg_stream_t stream, const PegDims* dims, const float* adj_coef, float* adj_colsum) {
+  PEG_TRY(check_dims(dims));
+  if (!adj_coef || !adj_colsum) return PEG_ERR_NULL_POINTER;
+  const int nt = dims->ldn / 32;
+  k_adj_colsums<<<dim3(nt, dims->T - 1, dims->B), 256, 0, (cudaStream_t)stream>>>(adj_coef, dims->n, dims->ldn, dims->T - 1, adj_colsum);
+  PEG_LAUNCH_CHECK();
+  return PEG_OK;
 }
 
 int pegncde_pack_x(peg_stream_t stream, const PegDims* dims, const float* d, const float* c, const float* b,

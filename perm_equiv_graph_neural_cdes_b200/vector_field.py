@@ -15,7 +15,7 @@ from typing import List, Optional, Sequence
 import torch
 from torch import nn
 
-from ._lib import PEG_WS_VF_FWD, PEG_WS_VF_VJP, PegDims, check, lib
+from ._lib import PEG_FLAG_DIRECTED, PEG_WS_VF_FWD, PEG_WS_VF_VJP, PegDims, check, lib
 from .control import CubicInterpolation, PackedControl, _stream_ptr, pack_control
 
 _WS_CACHE = {}
@@ -91,6 +91,24 @@ class _FixedFusionConvLayer(ConvLayer):
         return self.fusion_const
 
 
+class ConvEquivFusionDirectedLayer(nn.Module):
+    """src/models/vector_fields/layers.py:180-362: 11 parameter pairs ~ U(-1,1)/15 (row AND column sums of A, A') plus a
+    ConvLayer.  Reference quirks kept: ``param6_prime`` is drawn with ``param5_prime``'s key (init only), term 4' mixes
+    rowsum(A) with colsum(A'), term 7 uses sum(A) twice."""
+
+    NAMES = ("param1", "param2", "param3", "param4", "param5", "param6", "param7", "param8", "param4_prime", "param5_prime", "param6_prime")
+
+    def __init__(self, input_dim: int, output_dim: int, generator=None):
+        super().__init__()
+        for name in ("param1", "param2", "param3", "param4", "param4_prime", "param5", "param5_prime", "param6", "param6_prime", "param7", "param8"):
+            setattr(self, name, nn.Parameter((torch.rand((2,), generator=generator) * 2 - 1) / 15.0))
+        self.conv_layer = ConvLayer(input_dim, output_dim, generator)
+
+    def fusion_params(self) -> torch.Tensor:
+        """Kernel order (pegncde.h): param1..param8, then param4', param5', param6' and one pair of padding."""
+        return torch.cat([getattr(self, name) for name in self.NAMES] + [torch.zeros(2, device=self.param1.device, dtype=self.param1.dtype)])
+
+
 class PermEquivGraphVectorField(nn.Module):
     """src/models/vector_fields/perm_equiv_graph_vector_field.py:10-129 (enc_idx=False).
 
@@ -120,6 +138,8 @@ class PermEquivGraphVectorField(nn.Module):
         self.flags = 0
         # keep every stage's layer inputs in the forward solve so the adjoint needs no recompute (memory permitting)
         self.store_stages = True
+
+    directed = False   # PEG_FLAG_DIRECTED: 22 fusion scalars per layer, column sums in the control
 
     def _make_layer(self, input_dim: int, output_dim: int, gen) -> nn.Module:
         return ConvEquivFusionLayer(input_dim, output_dim, gen)
@@ -159,13 +179,27 @@ class PermEquivGraphVectorField(nn.Module):
             raise ValueError(f"output_dim {self.output_dim} does not match hidden_dim*data_embed_dim*2 = {expect}")
         if pc.n != self.num_nodes:
             raise ValueError(f"control has {pc.n} nodes, vector field was built for {self.num_nodes}")
-        d = pc.dims(self.hidden_dim, self.num_layers, self.flags)
+        flags = self.flags
+        if self.directed:
+            flags |= PEG_FLAG_DIRECTED
+            pc.ensure_colsums()
+        d = pc.dims(self.hidden_dim, self.num_layers, flags)
         d.e = e
         return d
 
     # ---- the ODETerm callable ------------------------------------------------------------
     def forward(self, t, y: torch.Tensor, args) -> torch.Tensor:
         return fused_vector_field(self, t, y, args, None)
+
+
+class PermEquivDirGraphVectorField(PermEquivGraphVectorField):
+    """src/models/vector_fields/perm_equiv_dir_graph_vector_field.py:86-130 (enc_idx=False): the directed equivariant field --
+    ``ConvEquivFusionDirectedLayer``s, ReLU between, time-gradient row scale; same kernels, different O(n) correction tables."""
+
+    directed = True
+
+    def _make_layer(self, input_dim: int, output_dim: int, gen) -> nn.Module:
+        return ConvEquivFusionDirectedLayer(input_dim, output_dim, gen)
 
 
 class GraphVectorField(PermEquivGraphVectorField):

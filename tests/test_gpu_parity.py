@@ -589,3 +589,46 @@ def test_streamed_control_materialises_for_adaptive_and_single_evaluations(cuda)
     s1 = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 2.0, None, y, host2, stepsize_controller=ctrl)
     s2 = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 2.0, None, y, dev, stepsize_controller=ctrl)
     assert torch.equal(s1.ys, s2.ys)
+
+
+# ---------------------------------------------------------------------------------------------------
+# directed equivariant field: ConvEquivFusionDirectedLayer, 11 parameter pairs, row and column sums
+# ---------------------------------------------------------------------------------------------------
+DIR_FIELDS = ("param1", "param2", "param3", "param4", "param4_prime", "param5", "param5_prime", "param6", "param6_prime", "param7", "param8")
+
+
+@pytest.mark.parametrize("flags", [0, TC], ids=["ffma", "tcgen05"])
+def test_directed_vector_field_against_oracle(cuda, flags):
+    p = R.make_problem(n=140 if flags else 33, h=32, e=0, L=2, T=4, t1=3, dt0=0.75, seed=29)
+    vf = P.PermEquivDirGraphVectorField(p.h, p.h, p.h, p.L, 0, p.n, key=4)
+    with torch.no_grad():
+        for mine, lp in zip(vf.gnn_layers, p.layers):
+            mine.conv_layer.linear.weight.copy_(lp.weight); mine.conv_layer.linear.bias.copy_(lp.bias)
+            mine.conv_layer.norm.weight.copy_(lp.norm_weight); mine.conv_layer.norm.bias.copy_(lp.norm_bias)
+    fus64 = [torch.stack([getattr(m, f).detach().double() for f in DIR_FIELDS]).requires_grad_(True) for m in vf.gnn_layers]
+    vf = vf.to(cuda)
+    vf.flags = flags
+    assert vf.flat_params().numel() == sum(32 * 32 + 32 + 64 + 24 for _ in range(p.L))
+    ts = p.ts.to(torch.float32).to(cuda)
+    ca = P.CubicInterpolation(ts, tuple(c.to(cuda) for c in p.coeffs_adj))
+    y0 = p.y0.to(cuda).requires_grad_(True)
+    # one evaluation + VJP
+    dy = vf(1.3, y0, ca)
+    p64 = R.problem_to(p, torch.float64)
+    layers = R.params_to(p64.layers, requires_grad=True)
+    c64 = R.CubicInterpolation(p64.ts, p64.coeffs_adj)
+    ref = R.perm_equiv_dir_vector_field(1.3, p64.y0, c64, layers, fus64)
+    assert rel_err(dy, ref) < 2e-5
+    # the solve, forward + exact adjoint, every leaf
+    sol = P.diffeqsolve(P.ODETerm(vf), P.Tsit5(), 0.0, 3.0, 0.75, y0, ca)
+    (sol.ys[-1] * p.gyT.to(cuda)).sum().backward()
+    y64 = p64.y0.clone().requires_grad_(True)
+    yT = R.tsit5_solve_fixed(lambda t, y: R.perm_equiv_dir_vector_field(t, y, c64, layers, fus64), y64, R.constant_step_table(0.0, 3.0, 0.75))
+    (yT * p64.gyT).sum().backward()
+    assert rel_err(sol.ys[-1], yT) < TOL_Y
+    assert rel_err(y0.grad, y64.grad) < TOL_G
+    for mine, lp, f64 in zip(vf.gnn_layers, layers, fus64):
+        got = torch.stack([getattr(mine, f).grad for f in DIR_FIELDS])
+        assert rel_err(got, f64.grad) < TOL_G
+        assert rel_err(mine.conv_layer.linear.weight.grad, lp.weight.grad) < TOL_G
+        assert rel_err(mine.conv_layer.norm.weight.grad, lp.norm_weight.grad) < TOL_G

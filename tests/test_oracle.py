@@ -102,3 +102,26 @@ def test_tsit5_order_on_linear_ode():
     assert abs(float(yT) - np.exp(-1.0)) < 2e-8
     yT2 = R.tsit5_solve_fixed(lambda t, y: -y, y0, np.linspace(0, 1, 21))
     assert abs(float(yT2) - np.exp(-1.0)) < abs(float(yT) - np.exp(-1.0)) / 16
+
+
+def test_directed_fusion_matrix_free_identity():
+    """(I + A_bar_dir) M with the directed layer's 11 terms equals the matrix-free form the kernels use: E M + G^T M + v.M +
+    r (1^T M) + 1 (c^T M) + kappa 1 (1^T M), with v, r, c built from row sums, COLUMN sums, diagonals and totals (k_stage_prep)."""
+    g = torch.Generator().manual_seed(2)
+    n, d = 9, 5
+    A = torch.rand(n, n, generator=g, dtype=torch.float64)
+    D = torch.randn(n, n, generator=g, dtype=torch.float64)
+    M = torch.randn(n, d, generator=g, dtype=torch.float64)
+    p = torch.randn(11, 2, generator=g, dtype=torch.float64) / 3
+    lit = M + R.fusion_directed(A, D, p) @ M
+    rA, rD, cA, cD = A.sum(1), D.sum(1), A.sum(0), D.sum(0)
+    E = (1 + p[0, 0]) * A + (1 + p[0, 1]) * D
+    G = p[1, 0] * A + p[1, 1] * D
+    v = p[2, 0] * torch.diag(A) + p[2, 1] * torch.diag(D) + (p[7, 0] * cA + p[7, 1] * cD) / n + (p[8, 0] * rA + p[8, 1] * rD) / n \
+        + (p[10, 0] * A.sum() + p[10, 1] * D.sum()) / n**2
+    r = (p[3, 0] * cA + p[3, 1] * cD) / n
+    c = (p[4, 0] * rA + p[4, 1] * cD) / n + (p[5, 0] * cA + p[5, 1] * cD) / n + (p[6, 0] * rA + p[6, 1] * rD) / n
+    kappa = (p[9, 0] + p[9, 1]) * A.sum() / n**2
+    ones = torch.ones(n, dtype=torch.float64)
+    mf = M + E @ M + G.t() @ M + v[:, None] * M + r[:, None] * (ones @ M)[None, :] + ones[:, None] * (c @ M)[None, :] + kappa * ones[:, None] * (ones @ M)[None, :]
+    assert torch.allclose(lit, mf, atol=1e-12)
