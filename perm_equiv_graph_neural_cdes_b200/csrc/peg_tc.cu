@@ -191,6 +191,11 @@ struct TcParams {
   int nkc;       // number of 32-wide K chunks = npad / 32
   int tmem_cols; // power of two >= 32
   int cluster;   // CTAs per cluster sharing the B operand by TMA multicast (1 = no cluster)
+  int mode;      // 0 = whole K range + epilogue; 1 = one K slice of `ksplit`, accumulators added into `partial` (no epilogue);
+                 // 2 = epilogue only, accumulators read from `partial`  (split-K for grids far smaller than the GPU)
+  int ksplit;    // K slices per row block in mode 1 (blockIdx.x = row block * ksplit + slice)
+  int pairs_per_slice;
+  float* partial; // [B][accumulators][n][d] fp32, zeroed by the host before mode 1
   int experiment; // timing experiments only (PEG_TC_EXPERIMENT): 1 = B operand loaded for the first pairs only, 2 = no MMAs
 };
 
@@ -202,7 +207,8 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   constexpr int NA = BWD ? 2 : 1;  // A-operand variants per item: fwd = combined X or Y; bwd = (A_s, A'_s)
   const ContractArgs& a = p.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.z, I = blockIdx.x, ntile = blockIdx.y;
+  const int kslice = p.mode == 1 ? (int)blockIdx.x % p.ksplit : 0;
+  const int b = blockIdx.z, I = p.mode == 1 ? (int)blockIdx.x / p.ksplit : (int)blockIdx.x, ntile = blockIdx.y;
   const int n = a.n, d = a.d, nd = p.nd;
   // CTAs of a cluster walk the K chunks in lockstep (schedule keyed on the cluster's first row block), so one
   // B tile serves all of them: each CTA fetches 1/C of its rows and multicasts the slice to every peer.
@@ -256,7 +262,10 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   for (int q = 0; q < 4; ++q) { sc.wA[q] = scp->wA[q]; sc.wD[q] = scp->wD[q]; }
   sc.interval = scp->interval;
   const int nkc = p.nkc;
-  const int items = 2 * nkc;   // item j = 2 * pair + type (0 direct, 1 transposed); pair p works on chunk kc_of(p)
+  // this CTA's pairs: all of them, or one contiguous slice of the schedule (mode 1); none in mode 2
+  const int pr0 = p.mode == 1 ? kslice * p.pairs_per_slice : 0;
+  const int npairs = p.mode == 2 ? 0 : (p.mode == 1 ? max(0, min(nkc, pr0 + p.pairs_per_slice) - pr0) : nkc);
+  const int items = 2 * npairs;   // local item j = 2 * local pair + type (0 direct, 1 transposed); pair works on chunk kc_of(pr0 + pair)
   // chunk order: 128-column blocks J(S) = (S - Ibase) mod nb, four 32-chunks each (the last block may hold fewer)
   const int nb = (nkc + 3) >> 2, r_last = nkc - 4 * (nb - 1);
   const int Imod = Ibase % nb, Sstar = (nb - 1 + Imod) % nb;
@@ -312,7 +321,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     };
     // item j -> its plane tile: direct = rows of block I x chunk kc, transposed = chunk kc x columns of block I
     auto load_item = [&](int j) {
-      const int kc = kc_of(j >> 1);
+      const int kc = kc_of(pr0 + (j >> 1));
       if ((j & 1) == 0) load_tile(4 * I + cv_u, kc);
       else load_tile(kc, 4 * I + cv_u);
     };
@@ -366,17 +375,17 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       if (!(PEG_TC_EARLY_RELOAD && !BWD) && j + 2 < items) load_item(j + 2);
     };
 
-    load_item(grp);   // group 0: direct items (even j); group 1: transposed items (odd j)
+    if (items > 0) load_item(grp);   // group 0: direct items (even j); group 1: transposed items (odd j)
     if (grp == 0) for (int j = 0; j < items; j += 2) convert(j, false);
     else          for (int j = 1; j < items; j += 2) convert(j, true);
   } else if (warp == 16) {
     // =========================== TMA producer (B operand) ===========================
     if (lane == 0) {
       const int row0 = b * d + ntile * nd;
-      for (int pr = 0; pr < nkc; ++pr) {   // one B tile per pair of items
+      for (int pr = 0; pr < npairs; ++pr) {   // one B tile per pair of items
         const int st = pr % SB;
         const uint32_t ph = (uint32_t)(pr / SB) & 1u;
-        const int kc = kc_of(pr);
+        const int kc = kc_of(pr0 + pr);
         mbar_wait(empty_b(st), ph ^ 1u);   // every CTA of the cluster has finished reading this slot
         const uint32_t b_base = b_ring + st * b_bytes;
         if (p.experiment == 1 && pr >= SB) { mbar_arrive(full_b(st)); continue; }   // timing experiment: stale B
@@ -430,14 +439,16 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
           else umma_commit_mcast(empty_b(sb), cmask);
         }
       }
-      umma_commit(accum_bar);     // all accumulators final
+      if (items > 0) umma_commit(accum_bar);     // all accumulators final
     }
   }
 
   // =========================== epilogue (warps 0-7) ===========================
   if (warp < 8) {
-    mbar_wait(accum_bar, 0u);
-    tc_fence_after();
+    if (items > 0) {
+      mbar_wait(accum_bar, 0u);
+      tc_fence_after();
+    }
     const int q = warp & 3;               // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
     const int gi = I * TC_BM + row;
@@ -464,13 +475,41 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       const int gc = ntile * nd + col;                // global feature column
       uint32_t r0[16], r1[16], r2[16], r3[16];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
-      tmem_ld16(taddr, r0);
-      if (BWD) {
-        tmem_ld16(taddr + nd, r1);
-        tmem_ld16(taddr + 2 * nd, r2);
-        tmem_ld16(taddr + 3 * nd, r3);
+      constexpr int NACC = BWD ? 4 : 1;
+      float* prow = p.partial ? p.partial + (((size_t)b * NACC) * n + (rowok ? gi : 0)) * d + gc : nullptr;   // accumulator 0
+      const size_t pacc = (size_t)n * d;                                                                      // next accumulator
+      if (p.mode == 2) {   // split-K: the summed accumulators come from global memory
+        auto ld16 = [&](int acc, uint32_t (&r)[16]) {
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            const float4 x = rowok ? __ldcg(reinterpret_cast<const float4*>(prow + acc * pacc + 4 * v4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            r[4 * v4] = __float_as_uint(x.x); r[4 * v4 + 1] = __float_as_uint(x.y); r[4 * v4 + 2] = __float_as_uint(x.z); r[4 * v4 + 3] = __float_as_uint(x.w);
+          }
+        };
+        ld16(0, r0);
+        if (BWD) { ld16(1, r1); ld16(2, r2); ld16(3, r3); }
+      } else {
+        tmem_ld16(taddr, r0);
+        if (BWD) {
+          tmem_ld16(taddr + nd, r1);
+          tmem_ld16(taddr + 2 * nd, r2);
+          tmem_ld16(taddr + 3 * nd, r3);
+        }
+        tmem_wait_ld();
       }
-      tmem_wait_ld();
+      if (p.mode == 1) {   // split-K: add this slice's accumulators into the partial buffer, epilogue runs in the mode-2 launch
+        if (rowok && items > 0) {
+          auto add16 = [&](int acc, const uint32_t (&r)[16]) {
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4)
+              atomicAdd(reinterpret_cast<float4*>(prow + acc * pacc + 4 * v4),
+                        make_float4(__uint_as_float(r[4 * v4]), __uint_as_float(r[4 * v4 + 1]), __uint_as_float(r[4 * v4 + 2]), __uint_as_float(r[4 * v4 + 3])));
+          };
+          add16(0, r0);
+          if (BWD) { add16(1, r1); add16(2, r2); add16(3, r3); }
+        }
+        continue;
+      }
       if (rowok) {
 #pragma unroll
         for (int v4 = 0; v4 < 4; ++v4) {
@@ -510,7 +549,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         }
       }
     }
-    if (BWD) {
+    if (BWD && p.mode != 1) {
       // per-thread partials of the 16 fusion-scalar gradients this CTA contributes to (layout of g_fus: param1..8 x 2)
       float part[14];
 #pragma unroll
@@ -542,7 +581,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     tc_fence_before();
   }
   __syncthreads();
-  if (BWD && tid < (a.cbM ? 14 : 4)) {   // one atomic per scalar and CTA
+  if (BWD && p.mode != 1 && tid < (a.cbM ? 14 : 4)) {   // one atomic per scalar and CTA
     float t = 0.f;
 #pragma unroll
     for (int w8i = 0; w8i < 8; ++w8i) t += fsum[w8i][tid];
@@ -662,12 +701,13 @@ static inline int npad_of(int n) { return peg_npad(n); }
 void tc_carve(Bump& bp, const PegDims& d, int dmax, TcWs& w) {
   w.npad = npad_of(d.n);
   if ((d.flags & PEG_FLAG_TENSOR_CORES) == 0) {
-    w.Vt_hi = w.Vt_lo = nullptr;
+    w.Vt_hi = w.Vt_lo = w.partial = nullptr;
     return;
   }
   const size_t cnt = (size_t)d.B * dmax * w.npad;
   w.Vt_hi = bp.take<float>(cnt);
   w.Vt_lo = bp.take<float>(cnt);
+  w.partial = bp.take<float>((size_t)d.B * 4 * d.n * dmax);   // split-K accumulators (small grids only)
 }
 
 bool tc_supported(const PegDims& d, int dcols) {
@@ -729,7 +769,30 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   const CUtensorMap& mhi = *mhi_p;
   const CUtensorMap& mlo = *mlo_p;
 
+  // Split-K for grids far smaller than the GPU (one graph of ~1k nodes: 8 row blocks on 148 SMs): every row block's chunk
+  // schedule is cut into `ksplit` slices that run on their own SMs and add their accumulators into `partial` (vector
+  // atomics); a second, epilogue-only launch finishes the layer.  Costs a memset and a launch, so only when it pays.
+  p.mode = 0; p.ksplit = 1; p.pairs_per_slice = p.nkc; p.partial = nullptr;
+  {
+    const int total = nblk * (d / p.nd) * dm.B;
+    int S = 148 / (total > 0 ? total : 1);
+    S = S > 8 ? 8 : S;
+    S = S > p.nkc / 4 ? p.nkc / 4 : S;
+    if (S >= 2 && p.nkc >= 16 && cluster == 1 && w.partial != nullptr && !getenv("PEG_TC_NO_SPLITK")) {
+      p.pairs_per_slice = (p.nkc + S - 1) / S;
+      p.ksplit = (p.nkc + p.pairs_per_slice - 1) / p.pairs_per_slice;   // every slice non-empty
+      p.partial = w.partial;
+      p.mode = 1;
+    }
+  }
   dim3 grid((nblk + cluster - 1) / cluster * cluster, d / p.nd, dm.B);   // padded row blocks only keep the cluster in lockstep
+  if (p.mode == 1) {
+    grid.x = (unsigned)(nblk * p.ksplit);
+    if (cudaMemsetAsync(w.partial, 0, (size_t)dm.B * (bwd ? 4 : 1) * n * d * sizeof(float), st) != cudaSuccess) {
+      set_last_cuda((int)cudaGetLastError());
+      return PEG_ERR_CUDA;
+    }
+  }
   {
     static std::atomic<unsigned> done[2] = {{0u}, {0u}};
     if (bwd) PEG_TC_TRY(optin_smem(k_tc_contract<true>, done[1]));
@@ -756,6 +819,13 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
     set_last_cuda((int)le); (void)cudaGetLastError(); return PEG_ERR_CUDA;
   }
   if (cudaPeekAtLastError() != cudaSuccess) { set_last_cuda((int)cudaGetLastError()); return PEG_ERR_CUDA; }
+  if (p.mode == 1) {   // epilogue-only launch over the row blocks
+    p.mode = 2;
+    cfg.gridDim = dim3((unsigned)nblk, d / p.nd, dm.B);
+    const cudaError_t le2 = bwd ? cudaLaunchKernelEx(&cfg, k_tc_contract<true>, mhi, mlo, p)
+                                : cudaLaunchKernelEx(&cfg, k_tc_contract<false>, mhi, mlo, p);
+    if (le2 != cudaSuccess) { set_last_cuda((int)le2); (void)cudaGetLastError(); return PEG_ERR_CUDA; }
+  }
   return PEG_OK;
 }
 

@@ -9,6 +9,7 @@ namespace peg {
 struct TcWs {
   float* Vt_hi;  // [B][dmax][npad]  tf32-rounded V^T (K-major B operand)
   float* Vt_lo;  // [B][dmax][npad]  residual V - tf32(V)
+  float* partial;  // [B][4][n][dmax] split-K accumulators (grids far smaller than the GPU)
   int npad;
 };
 
