@@ -114,9 +114,12 @@ class PackedControl:
         """Copies and packs every pending piece now (adaptive solves, single evaluations, ragged time grids)."""
         if self.pending is not None:
             dev = self.device
-            for iv in range(self.T - 1):
-                staging = [c[:, iv:iv + 1].to(dev, non_blocking=True).contiguous() for c in self.pending]
-                self.pack_pieces(iv, 1, staging, _stream_ptr(dev))
+            total = 4 * self.pending[0].numel() * 4
+            chunk = self.T - 1 if total <= (8 << 30) else max(1, (self.T - 1) * (8 << 30) // total)   # <= 8 GB of staging at a time
+            for iv in range(0, self.T - 1, chunk):
+                cnt = min(chunk, self.T - 1 - iv)
+                staging = [c[:, iv:iv + cnt].to(dev, non_blocking=True).contiguous() for c in self.pending]
+                self.pack_pieces(iv, cnt, staging, _stream_ptr(dev))
             self.pending = None
         return self
 

@@ -36,6 +36,9 @@ from .control import _stream_ptr
 from .vector_field import CDEWrapperVectorField, PermEquivGraphVectorField, resolve_control, workspace
 
 
+STREAM_MIN_PIECE_BYTES = 128 << 20   # host coefficient arrays are streamed piece by piece above this size per cubic piece
+
+
 class Tsit5:
     """Marker for ``diffrax.Tsit5()`` -- the only solver the fused kernels implement."""
 
@@ -157,10 +160,13 @@ class _SolveFunction(torch.autograd.Function):
                                       seg_ts.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), s1 - s0, start.data_ptr(), None,
                                       y_ckpt[s0].data_ptr(), store_ptr, ws.data_ptr(), ws.numel()), "pegncde_solve_fwd")
 
+        if pc.pending is not None:
+            # streaming pays when a cubic piece is big (its copy hides behind the steps inside the previous piece); many small
+            # pieces (SIR: 119 pieces of 16 MB) are cheaper to copy in one go
+            piece_bytes = 4 * pc.B * pc.n * pc.n * 2 * 4
+            if pc.host_ts is None or piece_bytes < STREAM_MIN_PIECE_BYTES:
+                pc.materialize()
         if pc.pending is None:
-            run_steps(0, S)
-        elif pc.host_ts is None:
-            pc.materialize()
             run_steps(0, S)
         else:
             _stream_pieces(pc, host_ts, run_steps)

@@ -550,13 +550,14 @@ def test_adaptive_solve_at_c1_heat_shape(cuda):
 # streamed control: host coefficient arrays, copy + pack of piece i+1 overlapped with the steps inside piece i
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("case", ["england_like", "sir_like", "ragged_n"])
-def test_streamed_host_control_is_bit_identical_to_the_resident_one(cuda, case):
+def test_streamed_host_control_is_bit_identical_to_the_resident_one(cuda, case, monkeypatch):
     """pack_control on HOST tensors defers the adjacency planes; the fixed-step solve packs them piece by piece
     (pegncde_pack_adj_range) and runs the step table in segments.  Same bits as the all-at-once path, forward and backward
     (sir_like has knots inside the steps, ragged_n a partial last tile)."""
     p = R.make_problem(**GOLDEN_CASES[case])
     kw = GOLDEN_CASES[case]
     outs = []
+    monkeypatch.setattr(P.solve, "STREAM_MIN_PIECE_BYTES", 0)     # these cases are tiny: force the streamed path
     for streamed in (False, True):
         vf, term, _ = device_model(p, cuda, flags=TC if p.n >= 128 else 0)
         place = (lambda t: t.to(torch.float32)) if streamed else (lambda t: t.to(torch.float32).to(cuda))
