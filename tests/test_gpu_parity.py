@@ -633,3 +633,23 @@ def test_directed_vector_field_against_oracle(cuda, flags):
         assert rel_err(got, f64.grad) < TOL_G
         assert rel_err(mine.conv_layer.linear.weight.grad, lp.weight.grad) < TOL_G
         assert rel_err(mine.conv_layer.norm.weight.grad, lp.norm_weight.grad) < TOL_G
+
+
+def test_split_k_matches_the_single_pass_contraction(cuda, monkeypatch):
+    """Launches far smaller than the GPU (one graph, n = 1000: 8 row blocks) run the contraction split-K (K slices on their
+    own SMs, vector-atomic accumulation, epilogue-only second launch).  Same result as the single-pass kernel up to the
+    fp32 summation order of the slices."""
+    p = R.make_problem(n=1000, h=64, e=0, L=2, T=3, t1=2, dt0=0.5, seed=8)
+    outs = []
+    for no_split in ("1", None):
+        if no_split:
+            monkeypatch.setenv("PEG_TC_NO_SPLITK", no_split)
+        else:
+            monkeypatch.delenv("PEG_TC_NO_SPLITK", raising=False)
+        vf, term, args = device_model(p, cuda, flags=TC)
+        y = p.y0.to(cuda).requires_grad_(True)
+        dy = term(1.3, y, args)
+        (dy * p.gyT.to(cuda)).sum().backward()
+        outs.append((dy.detach().clone(), y.grad.clone(), torch.cat([t.reshape(-1) for layer in product_grads_as_oracle(vf) for t in layer])))
+    for a, b in zip(*outs):
+        assert rel_err(a, b) < 5e-6
