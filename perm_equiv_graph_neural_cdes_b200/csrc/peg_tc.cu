@@ -344,10 +344,17 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           const float4 e0 = buf[0 * 4 + m], e1 = buf[1 * 4 + m], e2 = buf[2 * 4 + m], e3 = buf[3 * 4 + m];
-          t[v][4 * m + 0] = w0 * e0.x + w1 * e1.x + w2 * e2.x + w3 * e3.x;
-          t[v][4 * m + 1] = w0 * e0.y + w1 * e1.y + w2 * e2.y + w3 * e3.y;
-          t[v][4 * m + 2] = w0 * e0.z + w1 * e1.z + w2 * e2.z + w3 * e3.z;
-          t[v][4 * m + 3] = w0 * e0.w + w1 * e1.w + w2 * e2.w + w3 * e3.w;
+          if (BWD && v == NA - 1) {   // A'_s = b + 2 s c + 3 s^2 d: the derivative has no `a` term (wD[0] == 0)
+            t[v][4 * m + 0] = w1 * e1.x + w2 * e2.x + w3 * e3.x;
+            t[v][4 * m + 1] = w1 * e1.y + w2 * e2.y + w3 * e3.y;
+            t[v][4 * m + 2] = w1 * e1.z + w2 * e2.z + w3 * e3.z;
+            t[v][4 * m + 3] = w1 * e1.w + w2 * e2.w + w3 * e3.w;
+          } else {
+            t[v][4 * m + 0] = w0 * e0.x + w1 * e1.x + w2 * e2.x + w3 * e3.x;
+            t[v][4 * m + 1] = w0 * e0.y + w1 * e1.y + w2 * e2.y + w3 * e3.y;
+            t[v][4 * m + 2] = w0 * e0.z + w1 * e1.z + w2 * e2.z + w3 * e3.z;
+            t[v][4 * m + 3] = w0 * e0.w + w1 * e1.w + w2 * e2.w + w3 * e3.w;
+          }
         }
       }
       // forward: the plane registers are dead now -> re-issue the group's next loads before the slot wait and the stores
