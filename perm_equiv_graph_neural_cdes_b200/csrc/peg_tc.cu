@@ -783,8 +783,11 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   {
     const int total = nblk * (d / p.nd) * dm.B;
     int S = 148 / (total > 0 ? total : 1);
-    S = S > 8 ? 8 : S;
-    S = S > p.nkc / 4 ? p.nkc / 4 : S;
+    int smax = 16, minpairs = 2;   // measured on the Twitter shape: 8/4 -> 288, 16/2 -> 298 solver steps/s
+    if (const char* ev = getenv("PEG_TC_SPLIT_MAX")) { int v = atoi(ev); if (v >= 2 && v <= 32) smax = v; }
+    if (const char* ev = getenv("PEG_TC_SPLIT_MINPAIRS")) { int v = atoi(ev); if (v >= 1 && v <= 16) minpairs = v; }
+    S = S > smax ? smax : S;
+    S = S > p.nkc / minpairs ? p.nkc / minpairs : S;
     if (S >= 2 && p.nkc >= 16 && cluster == 1 && w.partial != nullptr && !getenv("PEG_TC_NO_SPLITK")) {
       p.pairs_per_slice = (p.nkc + S - 1) / S;
       p.ksplit = (p.nkc + p.pairs_per_slice - 1) / p.pairs_per_slice;   // every slice non-empty
