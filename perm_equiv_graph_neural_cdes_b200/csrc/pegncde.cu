@@ -185,7 +185,11 @@ static int stage_prep(Ctx& c, float t) {
   a.t = t;
   a.sc = c.w.sc;
   a.svec = c.w.svec;
-  dim3 grid((c.d.n + 255) / 256, c.d.B);
+  // enough blocks for the widest loop of the kernel (the node-signal derivative, n * 2e elements) to be one or two passes
+  const size_t work = (size_t)c.d.n * (c.d.e > 0 ? 2 * c.d.e : 1);
+  size_t gx = (work + 255) / 256;
+  gx = gx > 64 ? 64 : gx;
+  dim3 grid((unsigned)gx, c.d.B);
   k_stage_prep<<<grid, 256, 0, c.st>>>(a);
   PEG_LAUNCH_CHECK();
   return PEG_OK;
