@@ -630,6 +630,28 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// Environment knobs, parsed once per API call (tc_refresh_env from make_ctx) instead of per kernel launch: a getenv walks
+// the whole environment, and a solve enqueues thousands of launches.
+struct TcEnv {
+  int nd_max = 0, stages_a = 0, stages_b = 0, cluster = 0, experiment = 0, split_max = 0, split_minpairs = 0;
+  bool no_splitk = false, no_linear = false;
+};
+static TcEnv g_env;
+static int env_int(const char* name) { const char* ev = getenv(name); return ev ? atoi(ev) : 0; }
+void tc_refresh_env() {
+  TcEnv e;
+  e.nd_max = env_int("PEG_TC_ND_MAX");
+  e.stages_a = env_int("PEG_TC_STAGES_A");
+  e.stages_b = env_int("PEG_TC_STAGES_B");
+  e.cluster = env_int("PEG_TC_CLUSTER");
+  e.experiment = env_int("PEG_TC_EXPERIMENT");
+  e.split_max = env_int("PEG_TC_SPLIT_MAX");
+  e.split_minpairs = env_int("PEG_TC_SPLIT_MINPAIRS");
+  e.no_splitk = getenv("PEG_TC_NO_SPLITK") != nullptr;
+  e.no_linear = getenv("PEG_TC_NO_LINEAR") != nullptr;
+  g_env = e;
+}
+
 #define PEG_TC_TRY(expr)              \
   do {                                \
     int _rc = (expr);                 \
@@ -744,7 +766,7 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   TcParams p;
   p.a = a;
   int nd_max = bwd ? 128 : 256;
-  if (const char* ev = getenv("PEG_TC_ND_MAX")) { int v = atoi(ev); if (v >= 32 && v <= nd_max) nd_max = v; }
+  { const int v = g_env.nd_max; if (v >= 32 && v <= nd_max) nd_max = v; }
   p.nd = pick_nd(d, nd_max);
   p.nsplit = (dm.flags & PEG_FLAG_TF32_FAST) ? 1 : 3;
   p.nkc = npad / 32;
@@ -755,19 +777,19 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   int sa = ((208 * 1024 - sb * b_bytes) / a_bytes) & ~1;
   sa = sa > 4 ? 4 : sa;
   if (sa < 2) { sb = 1; sa = ((208 * 1024 - sb * b_bytes) / a_bytes) & ~1; }
-  if (const char* ev = getenv("PEG_TC_STAGES_A")) { int v = atoi(ev); if (v >= 2 && v <= sa && (v & 1) == 0) sa = v; }
-  if (const char* ev = getenv("PEG_TC_STAGES_B")) { int v = atoi(ev); if (v >= 1 && (size_t)sa * a_bytes + (size_t)v * b_bytes <= 224 * 1024) sb = v; }
+  { const int v = g_env.stages_a; if (v >= 2 && v <= sa && (v & 1) == 0) sa = v; }
+  { const int v = g_env.stages_b; if (v >= 1 && (size_t)sa * a_bytes + (size_t)v * b_bytes <= 224 * 1024) sb = v; }
   if (sa < 2) return PEG_ERR_UNSUPPORTED;
   p.stages_a = sa;
   p.stages_b = sb;
   p.tmem_cols = tmem_cols_pow2((bwd ? 4 : 1) * p.nd);
   const int nblk = (n + TC_BM - 1) / TC_BM;
   int cluster = 1;   // measured on B200: multicast does not pay (the SM ingress port, not L2, is the limit); PEG_TC_CLUSTER=2|4 enables it
-  if (const char* ev = getenv("PEG_TC_CLUSTER")) { int v = atoi(ev); if (v == 1 || v == 2 || v == 4 || v == 8) cluster = v; }
+  { const int v = g_env.cluster; if (v == 1 || v == 2 || v == 4 || v == 8) cluster = v; }
   while (cluster > 1 && (nblk < cluster || (p.nd / cluster) % 8 != 0)) cluster >>= 1;
   p.cluster = cluster;
   p.experiment = 0;
-  if (const char* ev = getenv("PEG_TC_EXPERIMENT")) p.experiment = atoi(ev);
+  p.experiment = g_env.experiment;
   const size_t smem = (size_t)sa * a_bytes + (size_t)sb * b_bytes + 1024 + 8 * (2 * sa + 2 * sb + 2) + 64;
 
   const CUtensorMap* mhi_p = nullptr;
@@ -784,11 +806,11 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
     const int total = nblk * (d / p.nd) * dm.B;
     int S = 148 / (total > 0 ? total : 1);
     int smax = 16, minpairs = 2;   // measured on the Twitter shape: 8/4 -> 288, 16/2 -> 298 solver steps/s
-    if (const char* ev = getenv("PEG_TC_SPLIT_MAX")) { int v = atoi(ev); if (v >= 2 && v <= 32) smax = v; }
-    if (const char* ev = getenv("PEG_TC_SPLIT_MINPAIRS")) { int v = atoi(ev); if (v >= 1 && v <= 16) minpairs = v; }
+    { const int v = g_env.split_max; if (v >= 2 && v <= 32) smax = v; }
+    { const int v = g_env.split_minpairs; if (v >= 1 && v <= 16) minpairs = v; }
     S = S > smax ? smax : S;
     S = S > p.nkc / minpairs ? p.nkc / minpairs : S;
-    if (S >= 2 && p.nkc >= 16 && cluster == 1 && w.partial != nullptr && !getenv("PEG_TC_NO_SPLITK")) {
+    if (S >= 2 && p.nkc >= 16 && cluster == 1 && w.partial != nullptr && !g_env.no_splitk) {
       p.pairs_per_slice = (p.nkc + S - 1) / S;
       p.ksplit = (p.nkc + p.pairs_per_slice - 1) / p.pairs_per_slice;   // every slice non-empty
       p.partial = w.partial;
@@ -1149,7 +1171,7 @@ static int nl_pick_nd(int dout) {
 }
 
 bool tc_linear_supported(int din, int dout) {
-  if (getenv("PEG_TC_NO_LINEAR")) return false;
+  if (g_env.no_linear) return false;
   return din % 32 == 0 && din >= 32 && nl_pick_nd(dout) != 0 && get_encode() != nullptr;
 }
 
@@ -1455,7 +1477,7 @@ k_tc_linear_bwd(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
 }
 
 bool tc_linear_bwd_supported(int din, int dout) {
-  if (getenv("PEG_TC_NO_LINEAR")) return false;
+  if (g_env.no_linear) return false;
   return din % 32 == 0 && din >= 32 && din <= 256 && dout % 32 == 0 && dout >= 32 && get_encode() != nullptr;
 }
 
@@ -1665,7 +1687,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_weight_grad(const WgParams
 }
 
 bool tc_weight_grad_supported(int din, int dout) {
-  if (getenv("PEG_TC_NO_LINEAR")) return false;
+  if (g_env.no_linear) return false;
   return dout % 4 == 0 && dout >= 32 && din % 32 == 0 && din >= 32 && din <= 256;
 }
 

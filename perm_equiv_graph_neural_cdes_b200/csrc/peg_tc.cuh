@@ -25,6 +25,7 @@ struct TcLinear {
   bool ready;   // carved (tensor-core flag set)
 };
 
+void tc_refresh_env();   // re-reads the PEG_TC_* environment knobs (once per API call)
 void tc_carve(Bump& bp, const PegDims& d, int dmax, TcWs& w);
 void tc_carve_linear(Bump& bp, const PegDims& d, const Model& m, TcLinear& w);
 bool tc_linear_supported(int din, int dout);

@@ -432,6 +432,7 @@ static int make_ctx(Ctx& c, peg_stream_t stream, const PegDims* dims, const PegC
   c.m = make_model(*dims);
   c.sv_stride = svec_stride(dims->n, dims->L, dims->e);
   c.use_tc = (dims->flags & PEG_FLAG_TENSOR_CORES) != 0;
+  if (c.use_tc) tc_refresh_env();
   return PEG_OK;
 }
 
