@@ -640,7 +640,7 @@ def test_split_k_matches_the_single_pass_contraction(cuda, monkeypatch):
     own SMs, vector-atomic accumulation, epilogue-only second launch).  Same result as the single-pass kernel up to the
     fp32 summation order of the slices."""
     # seed 21: no hidden unit within fp32 rounding of its ReLU kink at t = 1.3 (seed 8 has one at |z| = 3.5e-7, where the
-    # two summation orders legitimately pick different masks and d loss / d y differs by 7 % -- tests/split_probe2.py)
+    # two summation orders legitimately pick different masks and d loss / d y differs by 7 % -- tools/probes/split_probe2.py)
     p = R.make_problem(n=1000, h=64, e=0, L=2, T=3, t1=2, dt0=0.5, seed=21)
     outs = []
     for no_split in ("1", None):

@@ -1,6 +1,6 @@
 """Diagnostic (not a pytest test): tensor-core vs CUDA-core RMSNorm->Linear inside a full solve."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import perm_equiv_graph_neural_cdes_b200 as P
 from oracle import reference_path as R

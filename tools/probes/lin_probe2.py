@@ -1,6 +1,6 @@
 """Diagnostic: gradient sensitivity of the GNODE sibling case to 1e-7 relative perturbations of y0 (FFMA linear)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import perm_equiv_graph_neural_cdes_b200 as P
 from oracle import reference_path as R

@@ -1,6 +1,6 @@
 """Diagnostic: single-pass TC contraction vs FFMA under different settings (n=1000, h=64, L=2)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import perm_equiv_graph_neural_cdes_b200 as P
 from oracle import reference_path as R
