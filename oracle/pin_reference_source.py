@@ -1,0 +1,305 @@
+"""Pins the oracle against the reference's OWN source files (test infrastructure, NOT product code).
+
+The reference's vector-field modules are plain Python over a handful of jax.numpy / equinox calls
+(`jnp.tile/diag/eye/full/sum/transpose/einsum/mean`, `jax.vmap`, `jax.nn.relu`, `jr.split/uniform`,
+`eqx.Module`, `eqx.nn.Linear/RMSNorm`).  jax / equinox are not installable in this image, so this script
+installs a small numpy-backed stand-in for exactly those third-party names into ``sys.modules``,
+imports the UNMODIFIED reference files from ``/root/reference/src/models/vector_fields`` and executes
+their ``__call__`` methods in fp64:
+
+    layers.py                               ConvLayer, ConvEquivFusionLayer(._fusion), ConvEquivFusionDirectedLayer
+    perm_equiv_graph_vector_field.py        PermEquivGraphVectorField.__call__
+    cde_wrapper_vector_field.py             CDEWrapperVectorField.__call__
+    graph_vector_field.py / gnode_vector_field.py / perm_equiv_dir_graph_vector_field.py   (sibling fields)
+
+What this pins: every line of the reference's own code on the path (SURVEY 8a rows a4-a7 and the N3 siblings),
+including its quirks (term-7 bug, directed term-4' pairing, `1.0 +` offset, residual, no final ReLU,
+time-gradient scaling, the `[n,h,e,2]` wrapper reshape).  What stays restated: the third-party pieces --
+`eqx.nn.Linear` / `RMSNorm` arithmetic (stand-ins below), diffrax's CubicInterpolation (the control objects handed
+to the reference code are the oracle's) and the Tsit5 loop (the whole-solve fixture runs the oracle's
+fixed-step Tsit5 over the REFERENCE's vector-field callable).
+
+Outputs: ``tests/golden/refsrc_<case>.npz`` (small, committed).  ``tests/test_oracle.py`` checks the oracle's
+restatement against them on CPU; the GPU parity tests compare the CUDA path with them directly.
+The reference tree does not travel to the GPU box -- only these fixtures do.
+
+Run (in the build container, where /root/reference exists):   python -m oracle.pin_reference_source
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE_SRC = os.environ.get("PEG_REFERENCE_SRC", "/root/reference/src")
+
+# case name -> (oracle make_problem kwargs, evaluation times).  Small on purpose: the stand-in for jax.vmap is a Python loop.
+REFSRC_CASES = {
+    "nocontrol": dict(n=14, h=8, e=0, L=2, T=4, t1=3, dt0=0.25, seed=11),
+    "control": dict(n=18, h=8, e=3, L=3, T=4, t1=3, dt0=0.25, seed=12),
+    "ragged": dict(n=33, h=16, e=2, L=3, T=5, t1=2, dt0=0.2, seed=13),
+    "wide_dynamic_range": dict(n=21, h=8, e=2, L=3, T=4, t1=3, dt0=0.25, seed=14, scale=1.0e4),
+    # n >= 128 and widths that are multiples of 32: the shapes the tcgen05 kernels are selected for
+    "tc_control": dict(n=130, h=32, e=2, L=3, T=4, t1=3, dt0=0.5, seed=15),
+    "tc_nocontrol": dict(n=160, h=64, e=0, L=2, T=4, t1=3, dt0=0.5, seed=16),
+}
+EVAL_TIMES = (0.0, 0.37, 1.0, 1.61, 2.0)
+DIRECTED_SEED_OFFSET = 1000
+
+
+# --------------------------------------------------------------------------------------
+# numpy stand-ins for the third-party names the reference files import
+# --------------------------------------------------------------------------------------
+
+
+def _install_shims():
+    if "jax" in sys.modules and not getattr(sys.modules["jax"], "_peg_numpy_standin", False):
+        raise RuntimeError("a real jax is importable here: use oracle/regen_with_jax.py instead")
+
+    jnp = types.ModuleType("jax.numpy")
+    for name in ("tile", "diag", "eye", "full", "sum", "transpose", "einsum", "mean", "squeeze", "ones", "zeros", "sqrt",
+                 "asarray", "array", "stack", "concatenate", "reshape", "float32", "float64", "ndarray"):
+        setattr(jnp, name, getattr(np, name))
+    jnp.concat = np.concatenate
+
+    jnn = types.ModuleType("jax.nn")
+    jnn.relu = lambda x: np.maximum(x, 0.0)
+
+    jr = types.ModuleType("jax.random")
+    jr.PRNGKey = lambda seed: np.random.SeedSequence(int(seed))
+
+    def split(key, num=2):
+        return list(key.spawn(int(num)))
+
+    def uniform(key, shape=(), dtype=np.float64, minval=0.0, maxval=1.0):
+        return np.random.default_rng(key).uniform(minval, maxval, size=shape).astype(np.float64)
+
+    jr.split, jr.uniform = split, uniform
+
+    jax = types.ModuleType("jax")
+    jax._peg_numpy_standin = True
+    jax.numpy, jax.nn, jax.random = jnp, jnn, jr
+    jax.Array = np.ndarray
+    jax.vmap = lambda f: (lambda x: np.stack([f(xi) for xi in x]))   # jax.vmap(f)(x): f over axis 0
+
+    class Module:
+        """equinox.Module: the reference assigns its fields in __init__; nothing else of the base class is used here."""
+
+        def __init__(self, **kwargs):
+            pass
+
+    class Linear(Module):
+        """eqx.nn.Linear(in, out, key=): y = W x + b, W [out, in], init U(+-1/sqrt(in))."""
+
+        def __init__(self, in_features, out_features, use_bias=True, *, key, **kwargs):
+            lim = 1.0 / np.sqrt(in_features)
+            wkey, bkey = key.spawn(2)
+            self.weight = np.random.default_rng(wkey).uniform(-lim, lim, size=(out_features, in_features))
+            self.bias = np.random.default_rng(bkey).uniform(-lim, lim, size=(out_features,))
+
+        def __call__(self, x, *, key=None):
+            return self.weight @ x + self.bias
+
+    class RMSNorm(Module):
+        """eqx.nn.RMSNorm(shape): x * rsqrt(mean(x^2) + eps) * weight + bias, eps = 1e-5, weight 1, bias 0."""
+
+        def __init__(self, shape, eps=1e-5, use_weight=True, use_bias=True, **kwargs):
+            shape = (shape,) if isinstance(shape, int) else tuple(shape)
+            self.eps = eps
+            self.weight, self.bias = np.ones(shape), np.zeros(shape)
+
+        def __call__(self, x, *, key=None):
+            inv_rms = 1.0 / np.sqrt(np.mean(x * x) + self.eps)
+            return self.weight * (x * inv_rms) + self.bias
+
+    class MLP(Module):
+        """eqx.nn.MLP: the directed field constructs two of them for its enc_idx branch (never called with enc_idx=False)."""
+
+        def __init__(self, *a, **k):
+            pass
+
+        def __call__(self, *a, **k):
+            raise NotImplementedError("eqx.nn.MLP is not on the pinned path (enc_idx branch / encoders)")
+
+    eqx = types.ModuleType("equinox")
+    eqx_nn = types.ModuleType("equinox.nn")
+    eqx.Module = Module
+    eqx.field = lambda *a, **k: None
+    eqx_nn.Linear, eqx_nn.RMSNorm, eqx_nn.MLP = Linear, RMSNorm, MLP
+    eqx.nn = eqx_nn
+
+    jaxtyping = types.ModuleType("jaxtyping")
+    jaxtyping.Array = np.ndarray
+
+    sys.modules.update({"jax": jax, "jax.numpy": jnp, "jax.nn": jnn, "jax.random": jr, "equinox": eqx,
+                        "equinox.nn": eqx_nn, "jaxtyping": jaxtyping})
+
+
+_SHIM_NAMES = ("jax", "jax.numpy", "jax.nn", "jax.random", "equinox", "equinox.nn", "jaxtyping", "refsrc_models",
+               "refsrc_models.vector_fields", "refsrc_models.neural_nets")
+
+
+def uninstall_shims():
+    """Removes the stand-ins (and the reference modules imported on top of them) from sys.modules again."""
+    if not getattr(sys.modules.get("jax"), "_peg_numpy_standin", False):
+        return
+    for name in list(sys.modules):
+        if name in _SHIM_NAMES or name.startswith("refsrc_models."):
+            del sys.modules[name]
+
+
+def load_reference_vector_fields():
+    """Imports the reference's vector-field files by their real module names without running the package __init__ files
+    (those import every model of the repository, most of which need diffrax / pydantic configs)."""
+    _install_shims()
+    sys.dont_write_bytecode = True     # never write __pycache__ into the (read-only) reference tree
+    vf_dir = os.path.join(REFERENCE_SRC, "models", "vector_fields")
+    if not os.path.isdir(vf_dir):
+        raise FileNotFoundError(f"{vf_dir} not found: the reference tree exists only in the build container")
+    pkg_models = types.ModuleType("refsrc_models")
+    pkg_models.__path__ = [os.path.join(REFERENCE_SRC, "models")]
+    pkg_vf = types.ModuleType("refsrc_models.vector_fields")
+    pkg_vf.__path__ = [vf_dir]
+    pkg_nn = types.ModuleType("refsrc_models.neural_nets")      # `from ..neural_nets import IdxEncoder`: dead import
+    pkg_nn.IdxEncoder = type("IdxEncoder", (), {"__init__": lambda self, *a, **k: None})
+    sys.modules.update({"refsrc_models": pkg_models, "refsrc_models.vector_fields": pkg_vf, "refsrc_models.neural_nets": pkg_nn})
+    out = {}
+    for mod in ("layers", "perm_equiv_graph_vector_field", "cde_wrapper_vector_field", "graph_vector_field",
+                "gnode_vector_field", "perm_equiv_dir_graph_vector_field"):
+        out[mod] = importlib.import_module(f"refsrc_models.vector_fields.{mod}")
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# glue: oracle parameters / control objects -> reference objects
+# --------------------------------------------------------------------------------------
+
+
+class NumpyControl:
+    """The oracle's CubicInterpolation (restated diffrax) behind the `.evaluate(t)` / `.derivative(t)` protocol, as numpy."""
+
+    def __init__(self, ctrl):
+        self.ctrl = ctrl
+
+    def evaluate(self, t):
+        return self.ctrl.evaluate(t).numpy()
+
+    def derivative(self, t):
+        return self.ctrl.derivative(t).numpy()
+
+
+DIRECTED_FIELDS = ("param1", "param2", "param3", "param4", "param4_prime", "param5", "param5_prime", "param6",
+                   "param6_prime", "param7", "param8")
+
+
+def directed_fusion_tables(L: int, seed: int):
+    """[L][11, 2] parameter tables for the directed layer, reference init distribution U(-1,1)/15 (layers.py:230-250)."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed + DIRECTED_SEED_OFFSET)
+    return [(torch.rand((11, 2), generator=g, dtype=torch.float64) * 2 - 1) / 15.0 for _ in range(L)]
+
+
+def _set_conv(conv_layer, lp):
+    conv_layer.linear.weight = lp.weight.numpy().copy()
+    conv_layer.linear.bias = lp.bias.numpy().copy()
+    conv_layer.norm.weight = lp.norm_weight.numpy().copy()
+    conv_layer.norm.bias = lp.norm_bias.numpy().copy()
+
+
+def build_reference_fields(mods, p64, dir_tables):
+    """Reference modules constructed through their own __init__ and loaded with the oracle problem's parameters."""
+    import jax.random as jr   # the stand-in
+
+    import oracle.reference_path as R
+
+    widths = R.layer_widths(p64.h, p64.L, p64.e, p64.e > 0)
+    key = jr.PRNGKey(0)
+    kw = dict(input_dim=p64.h, hidden_dim=p64.h, output_dim=widths[-1], num_layers=p64.L, data_embed_dim=p64.e, num_nodes=p64.n)
+    pe = mods["perm_equiv_graph_vector_field"].PermEquivGraphVectorField(**kw, key=key)
+    pd = mods["perm_equiv_dir_graph_vector_field"].PermEquivDirGraphVectorField(**kw, key=key)
+    gv = mods["graph_vector_field"].GraphVectorField(**kw, key=key)
+    gn = mods["gnode_vector_field"].GNODEVectorField(**kw, key=key)
+    for l, lp in enumerate(p64.layers):
+        for i in range(8):
+            setattr(pe.gnn_layers[l], f"param{i + 1}", lp.fusion[i].numpy().copy())
+        _set_conv(pe.gnn_layers[l].conv_layer, lp)
+        for i, name in enumerate(DIRECTED_FIELDS):
+            setattr(pd.gnn_layers[l], name, dir_tables[l][i].numpy().copy())
+        _set_conv(pd.gnn_layers[l].conv_layer, lp)
+        _set_conv(gv.gnn_layers[l], lp)
+        _set_conv(gn.gnn_layers[l], lp)
+    return pe, pd, gv, gn
+
+
+def main():
+    import torch
+
+    sys.path.insert(0, ROOT)
+    import oracle.reference_path as R
+
+    mods = load_reference_vector_fields()
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    worst = 0.0
+    for name, kw in REFSRC_CASES.items():
+        p64 = R.problem_to(R.make_problem(**kw), torch.float64)
+        dir_tables = directed_fusion_tables(p64.L, kw["seed"])
+        pe, pd, gv, gn = build_reference_fields(mods, p64, dir_tables)
+        cadj = R.CubicInterpolation(p64.ts, p64.coeffs_adj)
+        ncadj = NumpyControl(cadj)
+        y = p64.y0.numpy()
+        rec = {}
+        # layer-level: the reference's _fusion on the interpolated (A, A') of the first evaluation time after a knot
+        adj = ncadj.evaluate(EVAL_TIMES[1])[..., -1]
+        dadj = ncadj.derivative(EVAL_TIMES[1])[..., -1]
+        fus, fus_dir = pe.gnn_layers[0]._fusion(adj, dadj), pd.gnn_layers[0]._fusion(adj, dadj)
+        if p64.n <= 40:
+            rec["fusion_t1"], rec["fusion_dir_t1"] = fus, fus_dir
+        # checksums that see every entry with a different weight (kept for all sizes)
+        wgt = np.cos(np.arange(p64.n * p64.n, dtype=np.float64)).reshape(p64.n, p64.n)
+        rec["fusion_t1_wsum"], rec["fusion_dir_t1_wsum"] = float((fus * wgt).sum()), float((fus_dir * wgt).sum())
+        times = [t for t in EVAL_TIMES if t <= float(p64.ts[-1])]
+        if p64.n > 40:
+            times = [times[0], times[1], times[3]]      # a knot, an interior point of the linear piece, one of a cubic piece
+        rec["times"] = np.asarray(times)
+        fields = {"perm_equiv": pe, "perm_equiv_dir": pd, "graph": gv, "gnode": gn}
+        if p64.e > 0:
+            # control shapes: every field behind the reference's CDEWrapperVectorField ([n, 2he] -> [n, h])
+            ncx = NumpyControl(R.CubicInterpolation(p64.ts, p64.x_coeffs))
+            Wrapper = mods["cde_wrapper_vector_field"].CDEWrapperVectorField
+            for key, field in fields.items():
+                if key == "gnode":      # the reference's GNODEVectorField keeps no data_embed_dim: it cannot sit behind the wrapper
+                    continue
+                wrapped_field = Wrapper(field, p64.h)
+                rec[f"vf_{key}"] = np.stack([wrapped_field(t, y, [ncadj, ncx]) for t in times])
+            wrapped = Wrapper(pe, p64.h)
+            f_ref = lambda t, yy: torch.from_numpy(wrapped(float(t), yy.numpy(), [ncadj, ncx]))
+        else:
+            for key, field in fields.items():
+                rec[f"vf_{key}"] = np.stack([field(t, y, ncadj) for t in times])
+            f_ref = lambda t, yy: torch.from_numpy(pe(float(t), yy.numpy(), ncadj))
+        # whole solve: the oracle's restated Tsit5 (third-party arithmetic) over the REFERENCE's vector-field callable
+        rec["yT"] = R.tsit5_solve_fixed(f_ref, p64.y0, p64.step_ts).numpy()
+        rec["steps"] = len(p64.step_ts) - 1
+        from oracle.make_goldens import input_checksum
+
+        rec["in_checksum"] = input_checksum(R.make_problem(**kw))
+        # report how far the restatement is from the reference source (the CPU test asserts this stays < 1e-11)
+        yT_restated = R.run_forward(p64).numpy()
+        err = float(np.abs(yT_restated - rec["yT"]).max() / np.abs(rec["yT"]).max())
+        worst = max(worst, err)
+        np.savez_compressed(os.path.join(out_dir, f"refsrc_{name}.npz"), **rec)
+        print(f"refsrc_{name}: n={p64.n} h={p64.h} e={p64.e} L={p64.L} steps={rec['steps']}  |yT|max={np.abs(rec['yT']).max():.4g}  "
+              f"restatement vs reference source: {err:.2e}")
+    print("worst", worst)
+    uninstall_shims()
+    return 0 if worst < 1e-11 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,4 +1,5 @@
-"""CPU ORACLE (test infrastructure, NOT product code) -- parity unpinned.
+"""CPU ORACLE (test infrastructure, NOT product code) -- reference-owned code pinned, third-party
+solver arithmetic unpinned.
 
 Literal restatement, in PyTorch-CPU, of the one hot path of
 hits-mli/perm-equiv-graph-neural-cdes: the Tsit5 solve loop that evaluates the
@@ -8,15 +9,19 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 ``--impl reference`` legs may import this module; the product package
 ``perm_equiv_graph_neural_cdes_b200`` never does.
 
-PARITY UNPINNED: the reference (JAX + Equinox + diffrax) cannot be imported in this
-image (no jax/diffrax/equinox wheels, no network) and the reference ships no test,
-golden vector or fixture for any function on this path (reference ``test/`` covers
-dataset utilities only).  Every function below follows the cited reference lines
-op-for-op -- including materialising the fused n x n adjacency exactly like the
-reference does -- and the diffrax / equinox pieces are restated from their published
-algorithms (diffrax >= 0.5, version unpinned in reference ``environment.yaml:16``).
-``oracle/regen_with_jax.py`` re-derives the goldens from the real packages wherever
-they are installed.
+PINNED: the vector-field functions below (fusion, conv_layer, perm_equiv_vector_field,
+cde_wrapper_vector_field, the directed / plain sibling fields) reproduce, to 2e-15, fp64
+executions of the reference's UNMODIFIED source files on numpy stand-ins for jax.numpy / equinox
+(``oracle/pin_reference_source.py`` -> ``tests/golden/refsrc_*.npz``, checked by
+``tests/test_oracle.py``).
+PARITY UNPINNED for the third-party pieces: the real stack (JAX + Equinox + diffrax) cannot be
+imported in this image (no wheels, no network) and the reference ships no test, golden vector or
+fixture for any function on this path (reference ``test/`` covers dataset utilities only).  The
+diffrax / equinox pieces (Hermite coefficients, cubic interpolation, Tsit5, step-size controllers,
+RMSNorm / Linear arithmetic) are restated from their published algorithms (diffrax >= 0.5, version
+unpinned in reference ``environment.yaml:16``).  ``oracle/regen_with_jax.py`` re-derives the goldens
+from the real packages wherever they are installed.  Every function follows the cited reference
+lines op-for-op -- including materialising the fused n x n adjacency exactly like the reference.
 
 All functions are dtype-generic (fp32 = what the reference computes in; fp64 = truth
 the tolerance is set against) and differentiable with torch autograd, which stands in

@@ -655,3 +655,63 @@ def test_split_k_matches_the_single_pass_contraction(cuda, monkeypatch):
         outs.append((dy.detach().clone(), y.grad.clone(), torch.cat([t.reshape(-1) for layer in product_grads_as_oracle(vf) for t in layer])))
     for a, b in zip(*outs):
         assert rel_err(a, b) < 5e-6
+
+
+# ---------------------------------------------------------------------------------------------------
+# the CUDA path against fixtures produced by executing the reference's OWN source files
+# (oracle/pin_reference_source.py -> tests/golden/refsrc_*.npz; the reference tree is not needed at test time)
+# ---------------------------------------------------------------------------------------------------
+from oracle import pin_reference_source as PIN  # noqa: E402
+
+
+def _refsrc_flag_cases():
+    out = []
+    for name, kw in PIN.REFSRC_CASES.items():
+        out.append(pytest.param(name, 0, id=f"{name}-ffma"))
+        if kw["n"] >= 128:
+            out.append(pytest.param(name, TC, id=f"{name}-tcgen05"))
+    return out
+
+
+@pytest.mark.parametrize("name,flags", _refsrc_flag_cases())
+def test_cuda_path_against_reference_source_fixtures(cuda, name, flags):
+    """PermEquivGraphVectorField / CDEWrapperVectorField / the sibling fields as the reference FILES compute them (fp64 execution
+    of the unmodified sources, oracle/pin_reference_source.py), and the fixed-step solve over the reference's callable."""
+    g = np.load(os.path.join(GOLD, f"refsrc_{name}.npz"))
+    kw = PIN.REFSRC_CASES[name]
+    p = R.make_problem(**kw)
+    vf, term, args = device_model(p, cuda, flags=flags)
+    y0 = p.y0.to(cuda)
+    times = [float(t) for t in g["times"]]
+    for k, t in enumerate(times):
+        assert rel_err(term(t, y0, args), g["vf_perm_equiv"][k]) < 2e-5, (name, t)
+    sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), float(p.ts[0]), float(p.ts[-1]), kw["dt0"], y0, args,
+                        stepsize_controller=P.ConstantStepSize(), saveat=P.SaveAt(t1=True))
+    assert sol.stats["num_steps"] == int(g["steps"])
+    assert rel_err(sol.ys[-1], g["yT"]) < TOL_Y, name
+    # sibling fields on the same parameters (behind the wrapper on control shapes, like the fixtures)
+    widths = R.layer_widths(p.h, p.L, p.e, p.e > 0)
+    as_term = (lambda f: P.CDEWrapperVectorField(f, p.h)) if p.e > 0 else (lambda f: f)
+    siblings = [("GraphVectorField", "vf_graph")] + ([("GNODEVectorField", "vf_gnode")] if p.e == 0 else [])
+    for cls, key in siblings:
+        sv = getattr(P, cls)(p.h, p.h, widths[-1], p.L, p.e, p.n, key=0)
+        with torch.no_grad():
+            for mine, lp in zip(sv.gnn_layers, p.layers):
+                mine.linear.weight.copy_(lp.weight); mine.linear.bias.copy_(lp.bias)
+                mine.norm.weight.copy_(lp.norm_weight); mine.norm.bias.copy_(lp.norm_bias)
+        sv = sv.to(cuda)
+        sv.flags = flags
+        for k, t in enumerate(times):
+            assert rel_err(as_term(sv)(t, y0, args), g[key][k]) < 2e-5, (name, cls, t)
+    dv = P.PermEquivDirGraphVectorField(p.h, p.h, widths[-1], p.L, p.e, p.n, key=0)
+    tables = PIN.directed_fusion_tables(p.L, kw["seed"])
+    with torch.no_grad():
+        for mine, lp, tab in zip(dv.gnn_layers, p.layers, tables):
+            mine.conv_layer.linear.weight.copy_(lp.weight); mine.conv_layer.linear.bias.copy_(lp.bias)
+            mine.conv_layer.norm.weight.copy_(lp.norm_weight); mine.conv_layer.norm.bias.copy_(lp.norm_bias)
+            for i, f in enumerate(PIN.DIRECTED_FIELDS):
+                getattr(mine, f).copy_(tab[i].to(torch.float32))
+    dv = dv.to(cuda)
+    dv.flags = flags
+    for k, t in enumerate(times):
+        assert rel_err(as_term(dv)(t, y0, args), g["vf_perm_equiv_dir"][k]) < 2e-5, (name, "directed", t)

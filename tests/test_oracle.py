@@ -125,3 +125,83 @@ def test_directed_fusion_matrix_free_identity():
     ones = torch.ones(n, dtype=torch.float64)
     mf = M + E @ M + G.t() @ M + v[:, None] * M + r[:, None] * (ones @ M)[None, :] + ones[:, None] * (c @ M)[None, :] + kappa * ones[:, None] * (ones @ M)[None, :]
     assert torch.allclose(lit, mf, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the restatement against the reference's OWN source files (fixtures made by oracle/pin_reference_source.py)
+# ---------------------------------------------------------------------------------------------------
+from oracle import pin_reference_source as PIN  # noqa: E402
+
+REFSRC_TOL = 1e-11   # fp64 restatement vs fp64 execution of the reference source: different summation orders only
+
+
+def _close(got, ref, what):
+    ref = np.asarray(ref)
+    err = float(np.abs(np.asarray(got) - ref).max() / max(float(np.abs(ref).max()), 1e-300))
+    assert err < REFSRC_TOL, (what, err)
+
+
+def _oracle_outputs_for_refsrc(name):
+    """What oracle/pin_reference_source.py records, computed by the oracle's restatement instead of the reference files."""
+    kw = PIN.REFSRC_CASES[name]
+    p = R.problem_to(R.make_problem(**kw), torch.float64)
+    ca = R.CubicInterpolation(p.ts, p.coeffs_adj)
+    dir_tables = PIN.directed_fusion_tables(p.L, kw["seed"])
+    return p, ca, dir_tables
+
+
+@pytest.mark.parametrize("name", list(PIN.REFSRC_CASES))
+def test_oracle_matches_reference_source_fixtures(name):
+    g = np.load(os.path.join(GOLD, f"refsrc_{name}.npz"))
+    p, ca, dir_tables = _oracle_outputs_for_refsrc(name)
+    assert abs(input_checksum(R.make_problem(**PIN.REFSRC_CASES[name])) - float(g["in_checksum"])) < 1e-6 * max(1.0, abs(float(g["in_checksum"])))
+    # layer level: ConvEquivFusionLayer._fusion / ConvEquivFusionDirectedLayer._fusion (layers.py:102-160, 256-345)
+    t1 = PIN.EVAL_TIMES[1]
+    adj, dadj = ca.evaluate(t1)[..., -1], ca.derivative(t1)[..., -1]
+    fus, fus_dir = R.fusion(adj, dadj, p.layers[0].fusion).numpy(), R.fusion_directed(adj, dadj, dir_tables[0]).numpy()
+    wgt = np.cos(np.arange(p.n * p.n, dtype=np.float64)).reshape(p.n, p.n)
+    scale = float(np.abs(fus).sum())
+    assert abs(float((fus * wgt).sum()) - float(g["fusion_t1_wsum"])) < REFSRC_TOL * scale
+    assert abs(float((fus_dir * wgt).sum()) - float(g["fusion_dir_t1_wsum"])) < REFSRC_TOL * scale
+    if "fusion_t1" in g:
+        _close(fus, g["fusion_t1"], "fusion")
+        _close(fus_dir, g["fusion_dir_t1"], "fusion_directed")
+    # field level: every reference __call__ on the path and its siblings (behind CDEWrapperVectorField on control shapes)
+    times = [float(t) for t in g["times"]]
+    if p.e > 0:
+        cx = R.CubicInterpolation(p.ts, p.x_coeffs)
+        wrap = lambda out, t: torch.einsum("nmlk,nlk->nm", out.reshape(-1, p.h, p.e, 2), cx.derivative(t))   # cde_wrapper_vector_field.py:21-25
+        _close(torch.stack([R.cde_wrapper_vector_field(t, p.y0, ca, cx, p.layers, p.h, p.e) for t in times]), g["vf_perm_equiv"], "wrapper")
+    else:
+        wrap = lambda out, t: out
+        _close(torch.stack([R.perm_equiv_vector_field(t, p.y0, ca, p.layers) for t in times]), g["vf_perm_equiv"], "perm_equiv")
+        _close(torch.stack([R.plain_graph_vector_field(t, p.y0, ca, p.layers, False) for t in times]), g["vf_gnode"], "gnode")
+    _close(torch.stack([wrap(R.perm_equiv_dir_vector_field(t, p.y0, ca, p.layers, dir_tables), t) for t in times]), g["vf_perm_equiv_dir"], "directed")
+    _close(torch.stack([wrap(R.plain_graph_vector_field(t, p.y0, ca, p.layers, True), t) for t in times]), g["vf_graph"], "graph")
+    # the whole fixed-step solve over the reference's callable
+    assert len(p.step_ts) - 1 == int(g["steps"])
+    _close(R.run_forward(p), g["yT"], "yT")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(PIN.REFERENCE_SRC, "models", "vector_fields")),
+                    reason="the reference tree exists only in the build container")
+def test_reference_source_fixtures_are_reproducible_from_the_reference_tree():
+    """Re-executes the unmodified reference files (numpy stand-ins for jax / equinox) and compares with the committed fixture."""
+    name = "control"
+    g = np.load(os.path.join(GOLD, f"refsrc_{name}.npz"))
+    mods = PIN.load_reference_vector_fields()
+    try:
+        p, ca, dir_tables = _oracle_outputs_for_refsrc(name)
+        pe, pd, gv, gn = PIN.build_reference_fields(mods, p, dir_tables)
+        nca, ncx = PIN.NumpyControl(ca), PIN.NumpyControl(R.CubicInterpolation(p.ts, p.x_coeffs))
+        wrapped = mods["cde_wrapper_vector_field"].CDEWrapperVectorField(pe, p.h)
+        wrapped_dir = mods["cde_wrapper_vector_field"].CDEWrapperVectorField(pd, p.h)
+        assert mods["layers"].__file__.startswith(PIN.REFERENCE_SRC)     # the code under test is the reference's file
+        y = p.y0.numpy()
+        for k, t in enumerate(float(t) for t in g["times"]):
+            assert np.array_equal(wrapped(t, y, [nca, ncx]), g["vf_perm_equiv"][k])
+            assert np.array_equal(wrapped_dir(t, y, [nca, ncx]), g["vf_perm_equiv_dir"][k])
+    finally:
+        PIN.uninstall_shims()
+    import sys
+    assert "jax" not in sys.modules
