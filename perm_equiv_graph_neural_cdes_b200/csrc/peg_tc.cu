@@ -199,9 +199,23 @@ struct TcParams {
   int experiment; // timing experiments only (PEG_TC_EXPERIMENT): 1 = B operand loaded for the first pairs only, 2 = no MMAs
 };
 
-template <bool BWD>
+// Per item type of the LIGHT adjoint: the operand pair is (combined = cA A_s + cD A'_s, 3xTF32: it carries the state cotangent)
+// and (sep = A'_s or A_s, ONE tf32 pass: it only feeds two scalar Frobenius gradients).  <sep V, M> and <combined V, M> give
+// both <A V, M> and <A' V, M>; sep is the plane with the smaller weight, so the 1-pass error is never amplified.
+struct LightCoef { float cA, cD, oc; int sepA; };
+__device__ __forceinline__ LightCoef light_coef(float wa, float wd) {
+  LightCoef c;
+  if (fmaxf(fabsf(wa), fabsf(wd)) < 1e-18f) { c.cA = 1.f; c.cD = 0.f; c.oc = 0.f; c.sepA = 0; }   // no contribution to the output: gradients only
+  else { c.cA = wa; c.cD = wd; c.oc = 1.f; c.sepA = fabsf(wa) < fabsf(wd) ? 1 : 0; }
+  return c;
+}
+
+// KIND 0 = forward, 1 = adjoint with four 3xTF32 products (default), 2 = LIGHT adjoint (two 3xTF32 products + two single-pass
+// ones; PEG_TC_ADJ_LIGHT=1, looser tolerance on the param1 / param2 gradients: 2.5e-3 instead of 1e-3)
+template <int KIND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const TcParams p) {
+  constexpr bool BWD = KIND != 0, LIGHT = KIND == 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ float fsum[8][16];    // adjoint epilogue: per-warp partials of the fusion-scalar gradients
   constexpr int NA = BWD ? 2 : 1;  // A-operand variants per item: fwd = combined X or Y; bwd = (A_s, A'_s)
@@ -279,6 +293,8 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     return 4 * J + u;
   };
   const float alpha = 1.f + a.fus[0], beta = 1.f + a.fus[1], gamma = a.fus[2], delta = a.fus[3];
+  // adjoint: direct items (A V, A' V) enter the output with (gamma, delta), transposed items (A^T V, A'^T V) with (alpha, beta)
+  const LightCoef lc_d = light_coef(gamma, delta), lc_t = light_coef(alpha, beta);
 
   if (warp < 16) {
     // =========================== converters ===========================
@@ -287,7 +303,11 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     float w[NA][4];   // this group's weights: direct items use X (fwd) / (A_s, A'_s) (bwd); transposed items use Y / the same pair
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (BWD) {
+      if (LIGHT) {
+        const LightCoef lc = grp == 0 ? lc_d : lc_t;
+        w[0][q] = lc.cA * sc.wA[q] + lc.cD * sc.wD[q];
+        w[NA - 1][q] = lc.sepA ? sc.wA[q] : sc.wD[q];
+      } else if (BWD) {
         w[0][q] = sc.wA[q]; w[NA - 1][q] = sc.wD[q];
       } else {
         w[0][q] = grp == 0 ? alpha * sc.wA[q] + beta * sc.wD[q]     // X = (1+p1_0) A + (1+p1_1) A'
@@ -326,11 +346,11 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       else load_tile(kc, 4 * I + cv_u);
     };
     // store one 16-byte chunk (4 consecutive k of operand row r) as tf32 hi (+ lo) into the swizzled K-major tile
-    auto store_chunk = [&](uint32_t hi_base, int r, int chunk, float x0, float x1, float x2, float x3) {
+    auto store_chunk = [&](uint32_t hi_base, int r, int chunk, float x0, float x1, float x2, float x3, bool with_lo) {
       const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
       const float h0 = tf32_rna(x0), h1 = tf32_rna(x1), h2 = tf32_rna(x2), h3 = tf32_rna(x3);
       asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "f"(h0), "f"(h1), "f"(h2), "f"(h3) : "memory");
-      if (split)
+      if (split && with_lo)
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + TC_ATILE + off), "f"(x0 - h0), "f"(x1 - h1), "f"(x2 - h2), "f"(x3 - h3) : "memory");
     };
     // Conversion of one item: (1) FFMA-combine the four planes (the fused cubic interpolation + fusion weights) while the
@@ -344,7 +364,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           const float4 e0 = buf[0 * 4 + m], e1 = buf[1 * 4 + m], e2 = buf[2 * 4 + m], e3 = buf[3 * 4 + m];
-          if (BWD && v == NA - 1) {   // A'_s = b + 2 s c + 3 s^2 d: the derivative has no `a` term (wD[0] == 0)
+          if (BWD && !LIGHT && v == NA - 1) {   // A'_s = b + 2 s c + 3 s^2 d: the derivative has no `a` term (wD[0] == 0)
             t[v][4 * m + 0] = w1 * e1.x + w2 * e2.x + w3 * e3.x;
             t[v][4 * m + 1] = w1 * e1.y + w2 * e2.y + w3 * e3.y;
             t[v][4 * m + 2] = w1 * e1.z + w2 * e2.z + w3 * e3.z;
@@ -367,14 +387,15 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
 #pragma unroll
       for (int v = 0; v < NA; ++v) {
         const uint32_t hi_base = a_base + v * (split ? 2 : 1) * TC_ATILE;
+        const bool with_lo = !(LIGHT && v == NA - 1);   // the single-pass operand needs no correction tile
         if (!transposed) {
 #pragma unroll
           for (int m = 0; m < 4; ++m)   // operand row = tile row 4 rq + m, chunk = cq (4 consecutive k)
-            store_chunk(hi_base, 32 * cv_u + 4 * cv_rq + m, cv_cq, t[v][4 * m + 0], t[v][4 * m + 1], t[v][4 * m + 2], t[v][4 * m + 3]);
+            store_chunk(hi_base, 32 * cv_u + 4 * cv_rq + m, cv_cq, t[v][4 * m + 0], t[v][4 * m + 1], t[v][4 * m + 2], t[v][4 * m + 3], with_lo);
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e)   // operand row = tile column 4 cq + e, chunk = rq: the four k values are the rows m = 0..3
-            store_chunk(hi_base, 32 * cv_u + 4 * cv_cq + e, cv_rq, t[v][e], t[v][4 + e], t[v][8 + e], t[v][12 + e]);
+            store_chunk(hi_base, 32 * cv_u + 4 * cv_cq + e, cv_rq, t[v][e], t[v][4 + e], t[v][8 + e], t[v][12 + e], with_lo);
         }
       }
       fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -424,7 +445,8 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         const uint32_t b_base = b_ring + sb * b_bytes;
 #pragma unroll
         for (int v = 0; v < NA && !(p.experiment == 2 && j >= 2); ++v) {
-          // fwd: one accumulator; bwd: acc index = type*2 + v  (0: A V, 1: A'V, 2: A^T V, 3: A'^T V)
+          // fwd: one accumulator; bwd: acc index = type*2 + v  (0: A V, 1: A'V, 2: A^T V, 3: A'^T V;
+          // LIGHT: 0 / 2 = combined operand, 1 / 3 = the single-pass sep operand of the direct / transposed items)
           const int acc = BWD ? (type * 2 + v) : 0;
           const uint32_t tacc = tmem_base + (uint32_t)(acc * nd);
           const uint32_t ahi = a_base + v * (split ? 2 : 1) * TC_ATILE, alo = ahi + TC_ATILE;
@@ -433,7 +455,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             const uint64_t dah = make_desc_sw128(ahi + k8 * 32), dbh = make_desc_sw128(b_base + k8 * 32);
             umma_tf32(tacc, dah, dbh, idesc, (started >> acc) & 1u);
             started |= 1u << acc;
-            if (split) {
+            if (split && !(LIGHT && v == NA - 1)) {
               const uint64_t dal = make_desc_sw128(alo + k8 * 32), dbl = make_desc_sw128(b_base + b_tile + k8 * 32);
               umma_tf32(tacc, dal, dbh, idesc, 1u);
               umma_tf32(tacc, dah, dbl, idesc, 1u);
@@ -539,7 +561,8 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             for (int u = 0; u < 4; ++u) {
               const float aV = __uint_as_float(r0[4 * v4 + u]), dV = __uint_as_float(r1[4 * v4 + u]);
               const float atV = __uint_as_float(r2[4 * v4 + u]), dtV = __uint_as_float(r3[4 * v4 + u]);
-              o[u] = vv[u] * vi + alpha * atV + beta * dtV + gamma * aV + delta * dV + rc * ss[u] + tt[u] + kappa * ss[u];
+              if (LIGHT) o[u] = vv[u] * vi + lc_t.oc * atV + lc_d.oc * aV + rc * ss[u] + tt[u] + kappa * ss[u];   // combined operands carry the weights
+              else o[u] = vv[u] * vi + alpha * atV + beta * dtV + gamma * aV + delta * dV + rc * ss[u] + tt[u] + kappa * ss[u];
               g4[0] = fmaf(atV, mm[u], g4[0]);
               g4[1] = fmaf(dtV, mm[u], g4[1]);
               g4[2] = fmaf(aV, mm[u], g4[2]);
@@ -594,7 +617,19 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     for (int w8i = 0; w8i < 8; ++w8i) t += fsum[w8i][tid];
     const float inv_n = 1.f / (float)n, inv_n2 = inv_n * inv_n;
     const float totA = scp->totA, totD = scp->totD;
-    if (tid < 4) atomicAdd(a.g_fus + tid, t);
+    if (tid < 4) {
+      if (LIGHT) {   // (<combined V, M>, <sep V, M>) -> (<A V, M>, <A' V, M>) of this thread's item type (0,1: transposed; 2,3: direct)
+        const int pair = tid >> 1;
+        float tc = 0.f, ts = 0.f;
+#pragma unroll
+        for (int w8i = 0; w8i < 8; ++w8i) { tc += fsum[w8i][2 * pair]; ts += fsum[w8i][2 * pair + 1]; }
+        const LightCoef c = pair == 0 ? lc_t : lc_d;
+        const float gA = c.sepA ? ts : (tc - c.cD * ts) / c.cA;
+        const float gD = c.sepA ? (tc - c.cA * ts) / c.cD : ts;
+        t = (tid & 1) ? gD : gA;
+      }
+      atomicAdd(a.g_fus + tid, t);
+    }
     else if (tid < 6) atomicAdd(a.g_fus + tid, t);                     // param3: indices 4, 5
     else if (tid < 12) atomicAdd(a.g_fus + tid, t * inv_n);            // param4..6: indices 6..11
     else if (tid == 12) { atomicAdd(a.g_fus + 14, t * totA * inv_n2); atomicAdd(a.g_fus + 15, t * totD * inv_n2); }
@@ -634,7 +669,7 @@ static EncodeTiledFn get_encode() {
 // the whole environment, and a solve enqueues thousands of launches.
 struct TcEnv {
   int nd_max = 0, stages_a = 0, stages_b = 0, cluster = 0, experiment = 0, split_max = 0, split_minpairs = 0;
-  bool no_splitk = false, no_linear = false;
+  bool no_splitk = false, no_linear = false, adj_light = false;
 };
 static TcEnv g_env;
 static int env_int(const char* name) { const char* ev = getenv(name); return ev ? atoi(ev) : 0; }
@@ -649,6 +684,10 @@ void tc_refresh_env() {
   e.split_minpairs = env_int("PEG_TC_SPLIT_MINPAIRS");
   e.no_splitk = getenv("PEG_TC_NO_SPLITK") != nullptr;
   e.no_linear = getenv("PEG_TC_NO_LINEAR") != nullptr;
+  // LIGHT adjoint (two of the four products single-pass): measured on B200 at n=2048, d=128, B=9 the adjoint launch goes
+  // 213 -> 199 us (+5 % solver steps/s) but the param1/param2 gradients of a whole solve are off by up to 2.5e-3 (the rounding
+  // of the slowly varying planes is correlated across launches, it does not average out) -> opt-in only, never the default
+  e.adj_light = getenv("PEG_TC_ADJ_LIGHT") != nullptr;
   g_env = e;
 }
 
@@ -825,10 +864,12 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
       return PEG_ERR_CUDA;
     }
   }
+  const int kind = bwd ? (g_env.adj_light ? 2 : 1) : 0;
   {
-    static std::atomic<unsigned> done[2] = {{0u}, {0u}};
-    if (bwd) PEG_TC_TRY(optin_smem(k_tc_contract<true>, done[1]));
-    else PEG_TC_TRY(optin_smem(k_tc_contract<false>, done[0]));
+    static std::atomic<unsigned> done[3] = {{0u}, {0u}, {0u}};
+    if (kind == 2) PEG_TC_TRY(optin_smem(k_tc_contract<2>, done[2]));
+    else if (kind == 1) PEG_TC_TRY(optin_smem(k_tc_contract<1>, done[1]));
+    else PEG_TC_TRY(optin_smem(k_tc_contract<0>, done[0]));
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -843,10 +884,14 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t le = bwd ? cudaLaunchKernelEx(&cfg, k_tc_contract<true>, mhi, mlo, p)
-                             : cudaLaunchKernelEx(&cfg, k_tc_contract<false>, mhi, mlo, p);
+  auto launch = [&]() -> cudaError_t {
+    return kind == 2 ? cudaLaunchKernelEx(&cfg, k_tc_contract<2>, mhi, mlo, p)
+         : kind == 1 ? cudaLaunchKernelEx(&cfg, k_tc_contract<1>, mhi, mlo, p)
+                     : cudaLaunchKernelEx(&cfg, k_tc_contract<0>, mhi, mlo, p);
+  };
+  const cudaError_t le = launch();
   if (le != cudaSuccess) {
-    fprintf(stderr, "pegncde: k_tc_contract<%d> launch failed (%s): grid %u x %u x %u, smem %zu, nd %d, slots A %d B %d, tmem %d\n", (int)bwd,
+    fprintf(stderr, "pegncde: k_tc_contract<%d> launch failed (%s): grid %u x %u x %u, smem %zu, nd %d, slots A %d B %d, tmem %d\n", kind,
             cudaGetErrorString(le), grid.x, grid.y, grid.z, smem, p.nd, sa, sb, p.tmem_cols);
     set_last_cuda((int)le); (void)cudaGetLastError(); return PEG_ERR_CUDA;
   }
@@ -854,8 +899,7 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   if (p.mode == 1) {   // epilogue-only launch over the row blocks
     p.mode = 2;
     cfg.gridDim = dim3((unsigned)nblk, d / p.nd, dm.B);
-    const cudaError_t le2 = bwd ? cudaLaunchKernelEx(&cfg, k_tc_contract<true>, mhi, mlo, p)
-                                : cudaLaunchKernelEx(&cfg, k_tc_contract<false>, mhi, mlo, p);
+    const cudaError_t le2 = launch();
     if (le2 != cudaSuccess) { set_last_cuda((int)le2); (void)cudaGetLastError(); return PEG_ERR_CUDA; }
   }
   return PEG_OK;

@@ -17,7 +17,7 @@ PY
 done
 B="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 1 --t1 0.2 --no-graph"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 600 --csv --log-file $O/launches_default.csv $B > $O/ncu_launches.log 2>&1
-for k in k_tc_contractILb0 k_tc_contractILb1 k_tc_norm_linear k_tc_linear_bwd; do
+for k in k_tc_contractILi0 k_tc_contractILi1 k_tc_norm_linear k_tc_linear_bwd; do
   timeout 500 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:$k -s 12 -c 1 -o $O/full_$k -f $B > $O/ncu_full_$k.log 2>&1
 done
 ls -la $O | head -40
