@@ -176,6 +176,9 @@ __global__ void __launch_bounds__(256) k_split_transpose(const float* __restrict
 #ifndef PEG_TC_EARLY_RELOAD
 #define PEG_TC_EARLY_RELOAD 0   // measured: earlier re-issue makes the forward launch slower (159 vs 137 us at n=2048, d=128, B=9)
 #endif
+#ifndef PEG_TC_BWD_HALF_EARLY
+#define PEG_TC_BWD_HALF_EARLY 0
+#endif
 constexpr int TC_THREADS = 576;   // 2 converter groups x 8 warps + TMA warp + MMA warp
 constexpr int TC_CONV_THREADS = 256;
 constexpr int TC_BM = 128;   // output rows per CTA (UMMA M)
@@ -327,23 +330,31 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     // loads of its next item right after publishing the current one; the two groups run out of phase, so ~2 items
     // (128 KB per SM) are in flight while the other group converts.
     float4 buf[16];
-    auto load_tile = [&](int rt, int ct) {
+    // `half`: 0 = the first PEG_TC_BWD_HALF_EARLY rows m of the micro tile, 1 = the remaining rows, 2 = all four (the adjoint can
+    // issue the two parts at different times)
+    auto load_tile = [&](int rt, int ct, int half) {
+      constexpr int ME = PEG_TC_BWD_HALF_EARLY > 0 ? PEG_TC_BWD_HALF_EARLY : 2;
+      const int m0 = half == 1 ? ME : 0, m1 = half == 0 ? ME : 4;
       if (rt < nt && ct < nt) {
         const float* base = P + ((size_t)rt * nt + ct) * 4096 + cv_off;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
-          for (int m = 0; m < 4; ++m) buf[q * 4 + m] = ldg_stream(base + (q * 4 + m) * 128);
+          for (int m = 0; m < 4; ++m)
+            if (m >= m0 && m < m1) buf[q * 4 + m] = ldg_stream(base + (q * 4 + m) * 128);
       } else {
 #pragma unroll
-        for (int u = 0; u < 16; ++u) buf[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+            if (m >= m0 && m < m1) buf[q * 4 + m] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     // item j -> its plane tile: direct = rows of block I x chunk kc, transposed = chunk kc x columns of block I
-    auto load_item = [&](int j) {
+    auto load_item = [&](int j, int half) {
       const int kc = kc_of(pr0 + (j >> 1));
-      if ((j & 1) == 0) load_tile(4 * I + cv_u, kc);
-      else load_tile(kc, 4 * I + cv_u);
+      if ((j & 1) == 0) load_tile(4 * I + cv_u, kc, half);
+      else load_tile(kc, 4 * I + cv_u, half);
     };
     // store one 16-byte chunk (4 consecutive k of operand row r) as tf32 hi (+ lo) into the swizzled K-major tile
     auto store_chunk = [&](uint32_t hi_base, int r, int chunk, float x0, float x1, float x2, float x3, bool with_lo) {
@@ -379,7 +390,10 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       }
       // forward: the plane registers are dead now -> re-issue the group's next loads before the slot wait and the stores
       // (the adjoint keeps 32 combined values live and would spill at 96 registers: it reloads after publishing)
-      if (PEG_TC_EARLY_RELOAD && !BWD && j + 2 < items) load_item(j + 2);
+      if (PEG_TC_EARLY_RELOAD && !BWD && j + 2 < items) load_item(j + 2, 2);
+      // adjoint, PEG_TC_BWD_HALF_EARLY: half of the next item's loads go out here (32 registers), under the slot wait and the stores
+      constexpr bool half_early = BWD && PEG_TC_BWD_HALF_EARLY > 0;
+      if (half_early && j + 2 < items) load_item(j + 2, 0);
       const int st = j % SA;
       const uint32_t ph = (uint32_t)(j / SA) & 1u;
       mbar_wait(empty_a(st), ph ^ 1u);   // the MMAs that read this slot's previous contents have completed
@@ -400,10 +414,10 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       }
       fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
       mbar_arrive(full_a(st));
-      if (!(PEG_TC_EARLY_RELOAD && !BWD) && j + 2 < items) load_item(j + 2);
+      if (!(PEG_TC_EARLY_RELOAD && !BWD) && j + 2 < items) load_item(j + 2, half_early ? 1 : 2);
     };
 
-    if (items > 0) load_item(grp);   // group 0: direct items (even j); group 1: transposed items (odd j)
+    if (items > 0) load_item(grp, 2);   // group 0: direct items (even j); group 1: transposed items (odd j)
     if (grp == 0) for (int j = 0; j < items; j += 2) convert(j, false);
     else          for (int j = 1; j < items; j += 2) convert(j, true);
   } else if (warp == 16) {
