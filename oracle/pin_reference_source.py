@@ -62,7 +62,7 @@ def _install_shims():
 
     jnp = types.ModuleType("jax.numpy")
     for name in ("tile", "diag", "eye", "full", "sum", "transpose", "einsum", "mean", "squeeze", "ones", "zeros", "sqrt",
-                 "asarray", "array", "stack", "concatenate", "reshape", "float32", "float64", "ndarray"):
+                 "asarray", "array", "stack", "concatenate", "reshape", "float32", "float64", "ndarray", "broadcast_to"):
         setattr(jnp, name, getattr(np, name))
     jnp.concat = np.concatenate
 
@@ -84,7 +84,7 @@ def _install_shims():
     jax._peg_numpy_standin = True
     jax.numpy, jax.nn, jax.random = jnp, jnn, jr
     jax.Array = np.ndarray
-    jax.vmap = lambda f: (lambda x: np.stack([f(xi) for xi in x]))   # jax.vmap(f)(x): f over axis 0
+    jax.vmap = lambda f, in_axes=0: (lambda x: np.stack([f(xi) for xi in x]))   # jax.vmap(f)(x): f over axis 0
 
     class Module:
         """equinox.Module: the reference assigns its fields in __init__; nothing else of the base class is used here."""
@@ -117,13 +117,19 @@ def _install_shims():
             return self.weight * (x * inv_rms) + self.bias
 
     class MLP(Module):
-        """eqx.nn.MLP: the directed field constructs two of them for its enc_idx branch (never called with enc_idx=False)."""
+        """eqx.nn.MLP(in_size, out_size, width_size, depth, key=): `depth` hidden Linear layers with ReLU, identity output."""
 
-        def __init__(self, *a, **k):
-            pass
+        def __init__(self, in_size, out_size, width_size, depth, *, key, **kwargs):
+            sizes = [in_size] + [width_size] * depth + [out_size]
+            keys = key.spawn(len(sizes) - 1)
+            self.layers = [Linear(sizes[i], sizes[i + 1], key=keys[i]) for i in range(len(sizes) - 1)]
 
-        def __call__(self, *a, **k):
-            raise NotImplementedError("eqx.nn.MLP is not on the pinned path (enc_idx branch / encoders)")
+        def __call__(self, x, *, key=None):
+            for i, layer in enumerate(self.layers):
+                x = layer(x)
+                if i < len(self.layers) - 1:
+                    x = np.maximum(x, 0.0)
+            return x
 
     eqx = types.ModuleType("equinox")
     eqx_nn = types.ModuleType("equinox.nn")
@@ -139,7 +145,7 @@ def _install_shims():
                         "equinox.nn": eqx_nn, "jaxtyping": jaxtyping})
 
 
-_SHIM_NAMES = ("jax", "jax.numpy", "jax.nn", "jax.random", "equinox", "equinox.nn", "jaxtyping", "refsrc_models",
+_SHIM_NAMES = ("jax", "jax.numpy", "jax.nn", "jax.random", "equinox", "equinox.nn", "jaxtyping", "diffrax", "refsrc_models",
                "refsrc_models.vector_fields", "refsrc_models.neural_nets")
 
 
@@ -148,7 +154,7 @@ def uninstall_shims():
     if not getattr(sys.modules.get("jax"), "_peg_numpy_standin", False):
         return
     for name in list(sys.modules):
-        if name in _SHIM_NAMES or name.startswith("refsrc_models."):
+        if name in _SHIM_NAMES or name.startswith("refsrc_models."):    # a stand-in jax means every one of these is ours
             del sys.modules[name]
 
 
@@ -172,6 +178,89 @@ def load_reference_vector_fields():
                 "gnode_vector_field", "perm_equiv_dir_graph_vector_field"):
         out[mod] = importlib.import_module(f"refsrc_models.vector_fields.{mod}")
     return out
+
+
+def _install_diffrax_standin():
+    """`diffrax` for the reference's solve wrappers: every name they use, backed by the ORACLE's restatement of the
+    third-party arithmetic (so the model-level fixtures pin the reference's own glue code -- encoders, the arguments of the
+    diffeqsolve call, read-outs -- not diffrax itself)."""
+    import torch
+
+    import oracle.reference_path as R
+
+    dfx = types.ModuleType("diffrax")
+    to_t = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64)))
+
+    class CubicInterpolation:
+        def __init__(self, ts, coeffs):
+            self.ctrl = R.CubicInterpolation(to_t(ts), tuple(to_t(c) for c in coeffs))
+
+        def evaluate(self, t):
+            return self.ctrl.evaluate(t).numpy()
+
+        def derivative(self, t):
+            return self.ctrl.derivative(t).numpy()
+
+    def backward_hermite_coefficients(ts, ys):
+        return tuple(c.numpy() for c in R.backward_hermite_coefficients(to_t(ts), to_t(ys)))
+
+    class ODETerm:
+        def __init__(self, vector_field):
+            self.vector_field = vector_field
+
+    class Tsit5:
+        pass
+
+    class ConstantStepSize:
+        pass
+
+    class PIDController:
+        def __init__(self, rtol, atol):
+            self.rtol, self.atol = rtol, atol
+
+    class SaveAt:
+        def __init__(self, ts=None, t1=False):
+            self.ts, self.t1 = ts, t1
+
+    class Solution:
+        def __init__(self, ys, stats):
+            self.ys, self.stats = ys, stats
+
+    def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, stepsize_controller=None, saveat=None, **kwargs):
+        assert isinstance(solver, Tsit5) and not kwargs, "the reference passes nothing else (default adjoint / max_steps)"
+        f = lambda t, y: torch.from_numpy(np.asarray(terms.vector_field(float(t), y.numpy(), args), dtype=np.float64))
+        y0 = to_t(y0)
+        if isinstance(stepsize_controller, ConstantStepSize):
+            assert saveat.ts is None and saveat.t1
+            table = R.constant_step_table(float(t0), float(t1), float(dt0))
+            return Solution(R.tsit5_solve_fixed(f, y0, table).numpy()[None], {"num_steps": len(table) - 1})
+        assert isinstance(stepsize_controller, PIDController) and dt0 is None
+        save_ts = None if saveat.ts is None else [float(t) for t in np.asarray(saveat.ts)]
+        ys, table, stats = R.tsit5_solve_adaptive(f, y0, float(t0), float(t1), rtol=stepsize_controller.rtol,
+                                                  atol=stepsize_controller.atol, dt0=None, save_ts=save_ts)
+        ys = ys.numpy() if save_ts is not None else ys.numpy()[None]
+        return Solution(ys, dict(stats, table=table))
+
+    for name, obj in dict(CubicInterpolation=CubicInterpolation, backward_hermite_coefficients=backward_hermite_coefficients,
+                          ODETerm=ODETerm, Tsit5=Tsit5, ConstantStepSize=ConstantStepSize, PIDController=PIDController,
+                          SaveAt=SaveAt, diffeqsolve=diffeqsolve).items():
+        setattr(dfx, name, obj)
+    dfx._peg_numpy_standin = True
+    sys.modules["diffrax"] = dfx
+
+
+def load_reference_models():
+    """The reference's solve wrappers (src/models/{pgt_,tgb_,}graph_neural_cde.py), imported unmodified on top of the stand-ins."""
+    mods = load_reference_vector_fields()
+    _install_diffrax_standin()
+    mods["gnode_floor_vector_field"] = importlib.import_module("refsrc_models.vector_fields.gnode_floor_vector_field")
+    pkg_vf = sys.modules["refsrc_models.vector_fields"]        # what `from . import vector_fields` resolves to
+    pkg_vf.CDEWrapperVectorField = mods["cde_wrapper_vector_field"].CDEWrapperVectorField
+    pkg_vf.GNODEFloorVectorField = mods["gnode_floor_vector_field"].GNODEFloorVectorField
+    sys.modules["refsrc_models"].vector_fields = pkg_vf
+    for mod in ("pgt_graph_neural_cde", "tgb_graph_neural_cde", "graph_neural_cde"):
+        mods[mod] = importlib.import_module(f"refsrc_models.{mod}")
+    return mods
 
 
 # --------------------------------------------------------------------------------------
@@ -236,6 +325,104 @@ def build_reference_fields(mods, p64, dir_tables):
     return pe, pd, gv, gn
 
 
+# model-level cases: name -> (kind, oracle make_problem kwargs, extra sizes)
+MODEL_CASES = {
+    "pgt": ("pgt", dict(n=24, h=8, e=3, L=3, T=4, t1=3, dt0=0.1, seed=31), dict(data_dim=5, feature_dim=1)),
+    "tgb_mlp": ("tgb", dict(n=20, h=8, e=4, L=2, T=3, t1=2, dt0=0.01, seed=32), dict(use_mlps=True)),
+    "tgb_linear": ("tgb", dict(n=16, h=8, e=2, L=2, T=3, t1=2, dt0=0.01, seed=33), dict(use_mlps=False)),
+    "dyn": ("dyn", dict(n=30, h=8, e=0, L=2, T=8, t1=5, dt0=0.1, seed=34, float_ts=True), dict()),
+}
+
+
+def model_inputs(name):
+    """Seeded extra inputs of a model-level case (node features, raw node signals): shared by this script and the tests."""
+    kind, kw, extra = MODEL_CASES[name]
+    rng = np.random.default_rng(kw["seed"] + 7000)
+    n, T = kw["n"], kw["T"]
+    if kind == "pgt":
+        return {"x0": rng.standard_normal((n, extra["data_dim"]))}
+    if kind == "tgb":
+        return {"x0": rng.standard_normal((n, n)), "x_data": 0.5 * rng.standard_normal((T, n, n))}
+    return {"x0": rng.standard_normal((n, 1))}
+
+
+def _linear_params(lin):
+    return [lin.weight.copy(), lin.bias.copy()]
+
+
+def _module_params(mod):
+    """[(W, b), ...] of a stand-in MLP or Linear."""
+    layers = mod.layers if hasattr(mod, "layers") else [mod]
+    return [_linear_params(l) for l in layers]
+
+
+def main_models():
+    """Model-level fixtures: the reference's solve wrappers executed on the stand-ins (diffrax backed by the oracle)."""
+    import types as _types
+
+    import torch
+
+    sys.path.insert(0, ROOT)
+    import oracle.reference_path as R
+    import jax.random as jr
+
+    mods = load_reference_models()
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    worst = 0.0
+    for name, (kind, kw, extra) in MODEL_CASES.items():
+        p64 = R.problem_to(R.make_problem(**kw), torch.float64)
+        widths = R.layer_widths(p64.h, p64.L, p64.e, p64.e > 0)
+        vf = mods["perm_equiv_graph_vector_field"].PermEquivGraphVectorField(
+            input_dim=p64.h, hidden_dim=p64.h, output_dim=widths[-1], num_layers=p64.L, data_embed_dim=p64.e, num_nodes=p64.n, key=jr.PRNGKey(0))
+        for l, lp in enumerate(p64.layers):
+            for i in range(8):
+                setattr(vf.gnn_layers[l], f"param{i + 1}", lp.fusion[i].numpy().copy())
+            _set_conv(vf.gnn_layers[l].conv_layer, lp)
+        inp = model_inputs(name)
+        coeffs_adj = tuple(c.numpy() for c in p64.coeffs_adj)
+        rec = {}
+        tt = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float64))
+        lay = lambda ps: [(tt(W), tt(b)) for W, b in ps]
+        if kind == "pgt":
+            cfg = _types.SimpleNamespace(data_dim=extra["data_dim"], hidden_dim=p64.h, feature_dim=extra["feature_dim"], method="Tsit5", return_sequence=False)
+            model = mods["pgt_graph_neural_cde"].PGTGraphNeuralCDE(cfg, vf, "cubic", jr.PRNGKey(kw["seed"]))
+            ts = np.arange(kw["T"], dtype=np.int32)                                   # torch.arange in dataset_configs.py:1108
+            x_coeffs = np.stack([c.numpy() for c in p64.x_coeffs])                    # stacked [4, T-1, n, e, 2] like trainer_pgt.py:203
+            rec["out_global"] = model(ts, np.stack(coeffs_adj), x_coeffs, inp["x0"])
+            rec["out_nodes"] = model(ts, np.stack(coeffs_adj), x_coeffs, inp["x0"], global_readout=False)
+            enc, dec = _module_params(model.encoder), _module_params(model.decoder)
+            ora = R.pgt_graph_neural_cde(p64.ts, p64.coeffs_adj, p64.x_coeffs, tt(inp["x0"]), lay(enc), lay(dec), p64.layers, p64.h, p64.e)
+            err = float((ora - tt(rec["out_global"])).abs().max() / tt(rec["out_global"]).abs().max())
+        elif kind == "tgb":
+            cfg = _types.SimpleNamespace(hidden_dim=p64.h, use_mlps=extra["use_mlps"], method="Tsit5", return_sequence=False)
+            model = mods["tgb_graph_neural_cde"].TGBGraphNeuralCDE(cfg, vf, "cubic", jr.PRNGKey(kw["seed"]))
+            ts = np.arange(kw["T"], dtype=np.int32)
+            rec["out"] = model(ts, coeffs_adj, inp["x_data"], inp["x0"], None)
+            enc, dec = _module_params(model.encoder), _module_params(model.decoder)
+            rec["data_encoder_W"], rec["data_encoder_b"] = _linear_params(model.data_encoder)
+            ora = R.tgb_graph_neural_cde(p64.ts, p64.coeffs_adj, tt(inp["x_data"]), tt(inp["x0"]), lay(enc), lay(dec),
+                                         (tt(rec["data_encoder_W"]), tt(rec["data_encoder_b"])), p64.layers, p64.h, p64.e)
+            err = float((ora - tt(rec["out"])).abs().max() / tt(rec["out"]).abs().max())
+        else:
+            cfg = _types.SimpleNamespace(hidden_dim=p64.h, method="Tsit5", return_sequence=True)
+            model = mods["graph_neural_cde"].GraphNeuralCDE(cfg, vf, "cubic", jr.PRNGKey(kw["seed"]))
+            ts = p64.ts.numpy()
+            rec["out"] = model(ts, coeffs_adj, inp["x0"])                              # evolving_out=True -> [T, n, 1]
+            enc, dec = _module_params(model.initial_linear), _module_params(model.final_linear)
+            ora, table = R.graph_neural_cde(p64.ts, p64.coeffs_adj, tt(inp["x0"]), lay(enc)[0], lay(dec)[0], p64.layers)
+            rec["accepted_steps"] = len(table) - 1
+            err = float((ora - tt(rec["out"])).abs().max() / tt(rec["out"]).abs().max())
+        for i, (W, b) in enumerate(enc):
+            rec[f"enc_W{i}"], rec[f"enc_b{i}"] = W, b
+        for i, (W, b) in enumerate(dec):
+            rec[f"dec_W{i}"], rec[f"dec_b{i}"] = W, b
+        worst = max(worst, err)
+        np.savez_compressed(os.path.join(out_dir, f"refsrc_model_{name}.npz"), **rec)
+        print(f"refsrc_model_{name}: restated model vs reference source: {err:.2e}")
+    print("worst (models)", worst)
+    return worst
+
+
 def main():
     import torch
 
@@ -297,6 +484,7 @@ def main():
         print(f"refsrc_{name}: n={p64.n} h={p64.h} e={p64.e} L={p64.L} steps={rec['steps']}  |yT|max={np.abs(rec['yT']).max():.4g}  "
               f"restatement vs reference source: {err:.2e}")
     print("worst", worst)
+    worst = max(worst, main_models())
     uninstall_shims()
     return 0 if worst < 1e-11 else 1
 

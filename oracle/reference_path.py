@@ -501,6 +501,54 @@ def solve_cde(step_ts, ts, coeffs_adj, x_coeffs, y0, layers, hidden_dim, data_em
     return tsit5_solve_fixed(f, y0, step_ts, save_all=save_all)
 
 
+def mlp(x, layers):
+    """equinox.nn.MLP / equinox.nn.Linear applied per node (``jax.vmap``): ``layers`` = [(W, b), ...]; ReLU between the
+    layers, identity after the last (a one-element list is a plain Linear)."""
+    for i, (W, b) in enumerate(layers):
+        x = x @ W.t() + b
+        if i < len(layers) - 1:
+            x = torch.relu(x)
+    return x
+
+
+def pgt_graph_neural_cde(ts, coeffs_adj, x_coeffs, x0, encoder, decoder, vf_layers, hidden_dim, data_embed_dim,
+                         global_readout=True, dt0=0.1):
+    """PGTGraphNeuralCDE.__call__, src/models/pgt_graph_neural_cde.py:78-136 (cubic interpolation, evolving_out=False):
+    y0 = vmap(encoder)(x0); diffeqsolve(ODETerm(wrapped_vf), Tsit5, ts[0], ts[-1], dt0=0.1, ConstantStepSize, SaveAt(t1));
+    vmap(decoder)(ys[-1]); sum over the nodes when ``global_readout``."""
+    y0 = mlp(x0, encoder)
+    step_ts = constant_step_table(float(ts[0]), float(ts[-1]), dt0)
+    y_T = solve_cde(step_ts, ts, coeffs_adj, x_coeffs, y0, vf_layers, hidden_dim, data_embed_dim)
+    out = mlp(y_T, decoder)
+    return out.sum(dim=0) if global_readout else out
+
+
+def tgb_graph_neural_cde(ts, coeffs_adj, x_data, x0, encoder, decoder, data_encoder, vf_layers, hidden_dim, data_embed_dim, dt0=0.01):
+    """TGBGraphNeuralCDE.__call__, src/models/tgb_graph_neural_cde.py:96-171 (cubic, evolving_out=False,
+    return_sequence=False): the node signal is embedded by ``data_encoder`` (:118), stacked behind a time channel
+    (:120-125), turned into Hermite coefficients INSIDE the model (:130) and used as the second control; dt0 = 0.01 (:143)."""
+    x_emb = mlp(x_data, [data_encoder])                                             # [T, n, e]
+    tsf = ts.to(x_emb.dtype)
+    x_path = torch.stack([tsf[:, None, None].expand_as(x_emb), x_emb], dim=-1)       # [T, n, e, 2]
+    coeffs_data = backward_hermite_coefficients(tsf, x_path)
+    y0 = mlp(x0, encoder)
+    step_ts = constant_step_table(float(ts[0]), float(ts[-1]), dt0)
+    y_T = solve_cde(step_ts, ts, coeffs_adj, coeffs_data, y0, vf_layers, hidden_dim, data_embed_dim)
+    return mlp(y_T, decoder)
+
+
+def graph_neural_cde(ts, coeffs_adj, x0, initial_linear, final_linear, vf_layers, rtol=1e-3, atol=1e-6):
+    """GraphNeuralCDE.__call__, src/models/graph_neural_cde.py:60-113 (cubic, evolving_out=True, return_sequence=True):
+    Linear(1 -> h) encoder, ODETerm(vector_field) without the CDE wrapper, dt0=None, PIDController(1e-3, 1e-6),
+    SaveAt(ts=ts), Linear(h -> 1) on every saved state.  Returns ([T, n, 1], accepted step table)."""
+    y0 = mlp(x0, [initial_linear])
+    control_adj = CubicInterpolation(ts, coeffs_adj)
+    f = lambda t, y: perm_equiv_vector_field(t, y, control_adj, vf_layers)
+    ys, table, _ = tsit5_solve_adaptive(f, y0, float(ts[0]), float(ts[-1]), rtol=rtol, atol=atol, dt0=None,
+                                        save_ts=[float(t) for t in ts])
+    return mlp(ys, [final_linear]), table
+
+
 def pgt_mse_loss(y_T, readout_w, label):
     """mse_loss of src/engine/trainer_pgt.py:45-66 with a linear stand-in decoder:
     y_pred = sum_nodes(decoder(y_T)) reshaped (feature_dim, 1) against label [n]

@@ -715,3 +715,48 @@ def test_cuda_path_against_reference_source_fixtures(cuda, name, flags):
     dv.flags = flags
     for k, t in enumerate(times):
         assert rel_err(as_term(dv)(t, y0, args), g["vf_perm_equiv_dir"][k]) < 2e-5, (name, "directed", t)
+
+
+def _load_linear_stack(mod, g, pre):
+    """Copies fixture parameters <pre>_W{i} / <pre>_b{i} into a product MLP (``.layers``) or Linear."""
+    layers = list(mod.layers) if hasattr(mod, "layers") else [mod]
+    with torch.no_grad():
+        for i, lin in enumerate(layers):
+            lin.weight.copy_(torch.from_numpy(g[f"{pre}_W{i}"]).to(torch.float32))
+            lin.bias.copy_(torch.from_numpy(g[f"{pre}_b{i}"]).to(torch.float32))
+    assert f"{pre}_W{len(layers)}" not in g.files
+
+
+@pytest.mark.parametrize("name", list(PIN.MODEL_CASES))
+def test_models_against_reference_source_fixtures(cuda, name):
+    """The host mirrors of the reference's solve wrappers (models.py) against fp64 executions of the reference's own
+    pgt_ / tgb_ / graph_neural_cde.py (oracle/pin_reference_source.py: diffrax backed by the oracle's restatement)."""
+    g = np.load(os.path.join(GOLD, f"refsrc_model_{name}.npz"))
+    kind, kw, extra = PIN.MODEL_CASES[name]
+    p = R.make_problem(**kw)
+    vf, _, _ = device_model(p, cuda)
+    inp = {k: torch.from_numpy(v).to(torch.float32).to(cuda) for k, v in PIN.model_inputs(name).items()}
+    coeffs_adj = tuple(c.to(cuda) for c in p.coeffs_adj)
+    if kind == "pgt":
+        model = P.PGTGraphNeuralCDE(p.h, extra["data_dim"], extra["feature_dim"], vf, "cubic", seed=0).to(cuda)
+        _load_linear_stack(model.encoder, g, "enc"); _load_linear_stack(model.decoder, g, "dec")
+        ts = torch.arange(kw["T"], device=cuda)
+        x_coeffs = tuple(c.to(cuda) for c in p.x_coeffs)
+        assert rel_err(model(ts, coeffs_adj, x_coeffs, inp["x0"]), g["out_global"]) < TOL_Y
+        assert rel_err(model(ts, coeffs_adj, x_coeffs, inp["x0"], global_readout=False), g["out_nodes"]) < TOL_Y
+    elif kind == "tgb":
+        model = P.TGBGraphNeuralCDE(p.h, vf, use_mlps=extra["use_mlps"], seed=0).to(cuda)      # dt0 = 0.01 like the reference
+        _load_linear_stack(model.encoder, g, "enc"); _load_linear_stack(model.decoder, g, "dec")
+        with torch.no_grad():
+            model.data_encoder.weight.copy_(torch.from_numpy(g["data_encoder_W"]).to(torch.float32))
+            model.data_encoder.bias.copy_(torch.from_numpy(g["data_encoder_b"]).to(torch.float32))
+        out = model(torch.arange(kw["T"], device=cuda), coeffs_adj, inp["x_data"], inp["x0"], None)
+        assert rel_err(out, g["out"]) < TOL_Y
+    else:
+        model = P.GraphNeuralCDE(p.h, vf, seed=0).to(cuda)
+        _load_linear_stack(model.initial_linear, g, "enc"); _load_linear_stack(model.final_linear, g, "dec")
+        out = model(p.ts.to(torch.float32).to(cuda), coeffs_adj, inp["x0"])
+        assert out.shape == g["out"].shape
+        # adaptive: PIDController(rtol=1e-3).  The fp64 fixture accepts 8 steps, an fp32 solve 9 (the CPU oracle in fp32 does the
+        # same), and two accepted-step sequences differ by the controller tolerance: 1e-3 in fp32 on the CPU; bound 5e-3
+        assert rel_err(out, g["out"]) < 5e-3

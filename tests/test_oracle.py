@@ -205,3 +205,64 @@ def test_reference_source_fixtures_are_reproducible_from_the_reference_tree():
         PIN.uninstall_shims()
     import sys
     assert "jax" not in sys.modules
+
+
+# ---------------------------------------------------------------------------------------------------
+# model level: the reference's solve wrappers (pgt_ / tgb_ / graph_neural_cde.py) executed unmodified, diffrax backed by the oracle
+# ---------------------------------------------------------------------------------------------------
+def _model_fixture(name):
+    g = np.load(os.path.join(GOLD, f"refsrc_model_{name}.npz"))
+    kind, kw, extra = PIN.MODEL_CASES[name]
+    p = R.problem_to(R.make_problem(**kw), torch.float64)
+    tt = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float64))
+    stack = lambda pre: [(tt(g[f"{pre}_W{i}"]), tt(g[f"{pre}_b{i}"])) for i in range(sum(k.startswith(f"{pre}_W") for k in g.files))]
+    inp = {k: tt(v) for k, v in PIN.model_inputs(name).items()}
+    return g, kind, p, stack("enc"), stack("dec"), inp, tt
+
+
+@pytest.mark.parametrize("name", list(PIN.MODEL_CASES))
+def test_oracle_models_match_reference_source_fixtures(name):
+    g, kind, p, enc, dec, inp, tt = _model_fixture(name)
+    if kind == "pgt":
+        _close(R.pgt_graph_neural_cde(p.ts, p.coeffs_adj, p.x_coeffs, inp["x0"], enc, dec, p.layers, p.h, p.e), g["out_global"], "pgt global")
+        _close(R.pgt_graph_neural_cde(p.ts, p.coeffs_adj, p.x_coeffs, inp["x0"], enc, dec, p.layers, p.h, p.e, global_readout=False), g["out_nodes"], "pgt nodes")
+        assert g["out_global"].shape == (1,) and g["out_nodes"].shape == (p.n, 1)
+    elif kind == "tgb":
+        out = R.tgb_graph_neural_cde(p.ts, p.coeffs_adj, inp["x_data"], inp["x0"], enc, dec, (tt(g["data_encoder_W"]), tt(g["data_encoder_b"])), p.layers, p.h, p.e)
+        _close(out, g["out"], "tgb")
+        assert g["out"].shape == (p.n, p.n)
+    else:
+        out, table = R.graph_neural_cde(p.ts, p.coeffs_adj, inp["x0"], enc[0], dec[0], p.layers)
+        _close(out, g["out"], "dyn")
+        assert len(table) - 1 == int(g["accepted_steps"]) and g["out"].shape == (p.ts.numel(), p.n, 1)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(PIN.REFERENCE_SRC, "models", "vector_fields")),
+                    reason="the reference tree exists only in the build container")
+def test_reference_model_fixture_is_reproducible_from_the_reference_tree():
+    """Re-runs the unmodified reference PGTGraphNeuralCDE on the stand-ins and requires the committed fixture bit for bit."""
+    import types
+
+    g, kind, p, enc, dec, inp, tt = _model_fixture("pgt")
+    kind, kw, extra = PIN.MODEL_CASES["pgt"]
+    mods = PIN.load_reference_models()
+    try:
+        import jax.random as jr   # the stand-in
+
+        widths = R.layer_widths(p.h, p.L, p.e, True)
+        vf = mods["perm_equiv_graph_vector_field"].PermEquivGraphVectorField(
+            input_dim=p.h, hidden_dim=p.h, output_dim=widths[-1], num_layers=p.L, data_embed_dim=p.e, num_nodes=p.n, key=jr.PRNGKey(0))
+        for l, lp in enumerate(p.layers):
+            for i in range(8):
+                setattr(vf.gnn_layers[l], f"param{i + 1}", lp.fusion[i].numpy().copy())
+            PIN._set_conv(vf.gnn_layers[l].conv_layer, lp)
+        cfg = types.SimpleNamespace(data_dim=extra["data_dim"], hidden_dim=p.h, feature_dim=extra["feature_dim"], method="Tsit5", return_sequence=False)
+        model = mods["pgt_graph_neural_cde"].PGTGraphNeuralCDE(cfg, vf, "cubic", jr.PRNGKey(kw["seed"]))
+        assert mods["pgt_graph_neural_cde"].__file__.startswith(PIN.REFERENCE_SRC)
+        out = model(np.arange(kw["T"], dtype=np.int32), np.stack([c.numpy() for c in p.coeffs_adj]),
+                    np.stack([c.numpy() for c in p.x_coeffs]), inp["x0"].numpy())
+        assert np.array_equal(out, g["out_global"])
+    finally:
+        PIN.uninstall_shims()
+    import sys
+    assert "jax" not in sys.modules and "diffrax" not in sys.modules
