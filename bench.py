@@ -449,7 +449,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "n": wl["n"], "hidden": wl["h"], "data_embed_dim": wl["e"], "layers": wl["L"]},
+            "config": {"workload": args.workload, "n": wl["n"], "hidden": wl["h"], "data_embed_dim": wl["e"], "layers": wl["L"],
+                       "knots": wl["T"], "solver": "Tsit5 fixed dt0=%g" % wl["dt0"],
+                       "solver_steps": len(R.constant_step_table(0.0, wl["t1"], wl["dt0"])) - 1, "graphs_per_gpu": wl["B"],
+                       "parallelism": "host threads of one box (the reference has no multi-device path)"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "each step = 1 graph x %d solver steps fwd+bwd (torch-CPU restatement of the reference path)" % sample_steps},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

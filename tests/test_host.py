@@ -196,3 +196,34 @@ def test_packed_control_select_is_a_view():
     v = pc.select(1)
     assert v.B == 1 and v.n == 5 and v.adj_coef.data_ptr() == pc.adj_coef[1].data_ptr() and v.ts.shape == (1, 4)
     assert v.dims(8, 2).B == 1
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (CPU arm, no GPU needed): one JSON line with the contract's keys, config matching our arm's."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "england", "--steps", "1",
+                          "--warmup", "1", "--cpu-sample-steps", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["config"]["workload"] == "england" and line["config"]["n"] == 129 and line["config"]["solver_steps"] == 30
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_reference_arm_is_silent_on_nonzero_ranks():
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "england", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
