@@ -179,6 +179,12 @@ __global__ void __launch_bounds__(256) k_split_transpose(const float* __restrict
 #ifndef PEG_TC_BWD_HALF_EARLY
 #define PEG_TC_BWD_HALF_EARLY 0
 #endif
+// Experiment, NOT YET RUN ON A GPU (round-1 GPU budget was spent): full / empty barriers per operand VARIANT of an adjoint A slot
+// (A_s and A'_s tiles, 32 KB each) instead of per slot, so a converter group may store A_s of item j+2 while the MMAs on A'_s of
+// item j are still running and the MMA thread may start on A_s while A'_s is still being stored.
+#ifndef PEG_TC_VARIANT_SLOTS
+#define PEG_TC_VARIANT_SLOTS 0
+#endif
 constexpr int TC_THREADS = 576;   // 2 converter groups x 8 warps + TMA warp + MMA warp
 constexpr int TC_CONV_THREADS = 256;
 constexpr int TC_BM = 128;   // output rows per CTA (UMMA M)
@@ -242,20 +248,23 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   const int b_bytes = (split ? 2 : 1) * b_tile;                 // [hi,lo]
   const int SA = p.stages_a, SB = p.stages_b;
   const uint32_t b_ring = smem_base + SA * a_bytes;
-  const uint32_t bar_base = b_ring + SB * b_bytes;  // full_a[SA], empty_a[SA], full_b[SB], empty_b[SB], accum_full, tmem slot
-  auto full_a = [&](int s) { return bar_base + 8u * s; };
-  auto empty_a = [&](int s) { return bar_base + 8u * (SA + s); };
-  auto full_b = [&](int s) { return bar_base + 8u * (2 * SA + s); };
-  auto empty_b = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
-  const uint32_t accum_bar = bar_base + 8u * (2 * SA + 2 * SB);
+  constexpr int NV = PEG_TC_VARIANT_SLOTS ? NA : 1;   // barrier pairs per A slot (1: the whole slot is published / released at once)
+  const int SAV = SA * NV;
+  const uint32_t bar_base = b_ring + SB * b_bytes;  // full_a[SA*NV], empty_a[SA*NV], full_b[SB], empty_b[SB], accum_full, tmem slot
+  auto full_a = [&](int s, int v) { return bar_base + 8u * (s * NV + (NV > 1 ? v : 0)); };
+  auto empty_a = [&](int s, int v) { return bar_base + 8u * (SAV + s * NV + (NV > 1 ? v : 0)); };
+  auto full_b = [&](int s) { return bar_base + 8u * (2 * SAV + s); };
+  auto empty_b = [&](int s) { return bar_base + 8u * (2 * SAV + SB + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * SAV + 2 * SB);
   const uint32_t tmem_slot = accum_bar + 8u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
 
   if (tid == 0) {
-    for (int s = 0; s < SA; ++s) {
-      mbar_init(full_a(s), TC_CONV_THREADS);
-      mbar_init(empty_a(s), 1);           // A tiles are CTA-local
-    }
+    for (int s = 0; s < SA; ++s)
+      for (int v = 0; v < NV; ++v) {
+        mbar_init(full_a(s, v), TC_CONV_THREADS);
+        mbar_init(empty_a(s, v), 1);           // A tiles are CTA-local
+      }
     for (int s = 0; s < SB; ++s) {
       mbar_init(full_b(s), 1);
       mbar_init(empty_b(s), (uint32_t)C);   // one tcgen05.commit arrival from every CTA of the cluster
@@ -396,10 +405,10 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       if (half_early && j + 2 < items) load_item(j + 2, 0);
       const int st = j % SA;
       const uint32_t ph = (uint32_t)(j / SA) & 1u;
-      mbar_wait(empty_a(st), ph ^ 1u);   // the MMAs that read this slot's previous contents have completed
       const uint32_t a_base = smem_base + st * a_bytes;
 #pragma unroll
       for (int v = 0; v < NA; ++v) {
+        if (v == 0 || NV > 1) mbar_wait(empty_a(st, v), ph ^ 1u);   // the MMAs that read this slot's (variant's) previous contents have completed
         const uint32_t hi_base = a_base + v * (split ? 2 : 1) * TC_ATILE;
         const bool with_lo = !(LIGHT && v == NA - 1);   // the single-pass operand needs no correction tile
         if (!transposed) {
@@ -411,9 +420,11 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
           for (int e = 0; e < 4; ++e)   // operand row = tile column 4 cq + e, chunk = rq: the four k values are the rows m = 0..3
             store_chunk(hi_base, 32 * cv_u + 4 * cv_cq + e, cv_rq, t[v][e], t[v][4 + e], t[v][8 + e], t[v][12 + e], with_lo);
         }
+        if (NV > 1 || v == NA - 1) {
+          fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          mbar_arrive(full_a(st, v));
+        }
       }
-      fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(full_a(st));
       if (!(PEG_TC_EARLY_RELOAD && !BWD) && j + 2 < items) load_item(j + 2, half_early ? 1 : 2);
     };
 
@@ -453,19 +464,21 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         const uint32_t ph = (uint32_t)(j / SA) & 1u;
         const int type = j & 1;
         if (type == 0) mbar_wait(full_b(sb), (uint32_t)(pr / SB) & 1u);   // the pair's B tile
-        mbar_wait(full_a(st), ph);
-        tc_fence_after();
         const uint32_t a_base = smem_base + st * a_bytes;
         const uint32_t b_base = b_ring + sb * b_bytes;
 #pragma unroll
-        for (int v = 0; v < NA && !(p.experiment == 2 && j >= 2); ++v) {
+        for (int v = 0; v < NA; ++v) {
+          if (v == 0 || NV > 1) {
+            mbar_wait(full_a(st, v), ph);
+            tc_fence_after();
+          }
           // fwd: one accumulator; bwd: acc index = type*2 + v  (0: A V, 1: A'V, 2: A^T V, 3: A'^T V;
           // LIGHT: 0 / 2 = combined operand, 1 / 3 = the single-pass sep operand of the direct / transposed items)
           const int acc = BWD ? (type * 2 + v) : 0;
           const uint32_t tacc = tmem_base + (uint32_t)(acc * nd);
           const uint32_t ahi = a_base + v * (split ? 2 : 1) * TC_ATILE, alo = ahi + TC_ATILE;
 #pragma unroll
-          for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+          for (int k8 = 0; k8 < TC_BK / 8 && !(p.experiment == 2 && j >= 2); ++k8) {
             const uint64_t dah = make_desc_sw128(ahi + k8 * 32), dbh = make_desc_sw128(b_base + k8 * 32);
             umma_tf32(tacc, dah, dbh, idesc, (started >> acc) & 1u);
             started |= 1u << acc;
@@ -475,8 +488,8 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
               umma_tf32(tacc, dah, dbl, idesc, 1u);
             }
           }
+          if (NV > 1 || v == NA - 1) umma_commit(empty_a(st, v));   // frees this A slot (variant) once the MMAs above have read it
         }
-        umma_commit(empty_a(st));   // frees this A slot once the MMAs above have read it
         if (type == 1) {            // ... and the pair's B slot, in every CTA of the cluster (their producers multicast into it)
           if (C == 1) umma_commit(empty_b(sb));
           else umma_commit_mcast(empty_b(sb), cmask);
@@ -843,7 +856,8 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   p.cluster = cluster;
   p.experiment = 0;
   p.experiment = g_env.experiment;
-  const size_t smem = (size_t)sa * a_bytes + (size_t)sb * b_bytes + 1024 + 8 * (2 * sa + 2 * sb + 2) + 64;
+  const int nv = PEG_TC_VARIANT_SLOTS ? na : 1;   // barrier pairs per A slot (see the kernel)
+  const size_t smem = (size_t)sa * a_bytes + (size_t)sb * b_bytes + 1024 + 8 * (2 * sa * nv + 2 * sb + 2) + 64;
 
   const CUtensorMap* mhi_p = nullptr;
   const CUtensorMap* mlo_p = nullptr;
