@@ -18,7 +18,6 @@ import sys
 import threading
 import time
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

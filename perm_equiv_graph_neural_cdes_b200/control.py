@@ -12,7 +12,6 @@ from typing import Optional, Sequence, Tuple
 
 import torch
 
-from . import _lib
 from ._lib import PegControl, PegDims, check, lib
 
 

@@ -10,12 +10,11 @@ would sit here in a JAX environment is in ``jax_ffi/``).  All arithmetic runs in
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Sequence
 
 import torch
 from torch import nn
 
-from ._lib import PEG_FLAG_DIRECTED, PEG_WS_VF_FWD, PEG_WS_VF_VJP, PegDims, check, lib
+from ._lib import PEG_FLAG_DIRECTED, PEG_WS_VF_VJP, PegDims, check, lib
 from .control import CubicInterpolation, PackedControl, _stream_ptr, pack_control
 
 _WS_CACHE = {}

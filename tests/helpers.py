@@ -1,5 +1,4 @@
 """Glue between the oracle's Problem objects and the product's host API (tests only)."""
-import numpy as np
 import torch
 
 from oracle import reference_path as R

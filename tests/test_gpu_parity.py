@@ -5,7 +5,6 @@ BASELINE sizes -- through size-independent properties.
 Tolerances (BASELINE.json north_star): Z_T within 1e-4 relative (max-norm) of the fp64 oracle in
 fp32 mode; gradients within 1e-3 relative per leaf (they are sums of O(steps*stages*n) fp32 terms).
 """
-import ctypes
 import os
 
 import numpy as np
