@@ -423,6 +423,92 @@ def main_models():
     return worst
 
 
+def load_reference_dataset_configs():
+    """src/configs/dataset_configs.py imported unmodified.  Its heavy imports (torch_geometric, tgb, the reference's own
+    `dataset` package) only serve type annotations and loaders that the control-path builders below never touch, so they are
+    empty placeholder modules here."""
+    load_reference_models()          # jax / equinox / diffrax stand-ins
+    placeholders = {
+        "torch_geometric": {}, "torch_geometric.data": {"Data": object, "TemporalData": object},
+        "torch_geometric.utils": {"to_dense_adj": None}, "tgb": {}, "tgb.nodeproppred": {},
+        "tgb.nodeproppred.dataset_pyg": {"PyGNodePropPredDataset": object},
+        "dataset": {"ODEDataset": object, "misc": types.ModuleType("dataset.misc")},
+        "dataset.tgb_dataset": {"SlidingWindowTemporalLoader": object},
+    }
+    added = []
+    for name, attrs in placeholders.items():
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m._peg_placeholder = True
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[name] = m
+            added.append(name)
+    import importlib.util
+
+    path = os.path.join(REFERENCE_SRC, "configs", "dataset_configs.py")
+    spec = importlib.util.spec_from_file_location("refsrc_models.dataset_configs", path)   # lives under the prefix uninstall_shims() clears
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        for name in added:
+            sys.modules.pop(name, None)
+    return mod
+
+
+DATASET_CASE = dict(n=11, e=3, window=5, seed=41)     # England-like window: 5 snapshots, the last one is the label
+
+
+def dataset_window(case=DATASET_CASE):
+    """A seeded window of graph snapshots (objects with .x [n,e], .adj [n,n], .y [n]) like PGTDataSetCfg.process_window receives."""
+    import torch
+
+    import oracle.reference_path as R
+
+    A = torch.from_numpy(R.synthetic_graph_path(case["n"], case["window"], case["seed"]))
+    g = torch.Generator().manual_seed(case["seed"])
+    return [types.SimpleNamespace(x=torch.randn((case["n"], case["e"]), generator=g, dtype=torch.float64), adj=A[k],
+                                  y=torch.randn((case["n"],), generator=g, dtype=torch.float64)) for k in range(case["window"])]
+
+
+def main_dataset():
+    """The reference's control-path builders (what the trainers feed the models, trainer_pgt.py:201-207 / trainer.py:121-144)."""
+    import torch
+
+    sys.path.insert(0, ROOT)
+    import oracle.reference_path as R
+
+    mod = load_reference_dataset_configs()
+    window = dataset_window()
+    cfg = types.SimpleNamespace(interpolation="cubic")
+    cfg.get_interpolation_coeffs = lambda ts, sig: mod.PGTDataSetCfg.get_interpolation_coeffs(cfg, ts, sig)
+    d = mod.PGTDataSetCfg.process_window(cfg, window)                                   # dataset_configs.py:1103-1131
+    rec = {"t": d["t"].numpy(), "true_y": d["true_y"].numpy(), "true_y0": d["true_y0"].numpy()}
+    for i, nm in enumerate("dcba"):
+        rec[f"graph_{nm}"] = d["graph_path_coeffs"][i].numpy()
+        rec[f"x_{nm}"] = d["x_coeffs"][i].numpy()
+    ts = torch.arange(len(window) - 1)
+    A = torch.stack([w.adj for w in window[:-1]])
+    x_t = torch.stack([w.x for w in window[:-1]])
+    worst = 0.0
+    for i, (mine_g, mine_x) in enumerate(zip(R.reference_layout_coeffs(ts, A), R.reference_layout_xcoeffs(ts, x_t))):
+        worst = max(worst, float((mine_g - d["graph_path_coeffs"][i]).abs().max()), float((mine_x - d["x_coeffs"][i]).abs().max()))
+    # dynamical-systems config: float time stamps, dataset_configs.py:147-173
+    ode_cfg = types.SimpleNamespace(interpolation="cubic")
+    ts_f = np.linspace(0.0, 5.0, 6)
+    A_f = R.synthetic_graph_path(9, 6, DATASET_CASE["seed"] + 1)
+    co = mod.ODEDataSetCfg.get_graph_interpolation_coeffs(ode_cfg, ts_f, A_f)
+    for i, nm in enumerate("dcba"):
+        rec[f"ode_graph_{nm}"] = np.asarray(co[i])
+    for i, mine in enumerate(R.reference_layout_coeffs(torch.from_numpy(ts_f), torch.from_numpy(A_f))):
+        worst = max(worst, float((mine - torch.from_numpy(np.asarray(co[i]))).abs().max()))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "refsrc_dataset.npz"), **rec)
+    print(f"refsrc_dataset: graph coeffs {tuple(rec['graph_d'].shape)} x coeffs {tuple(rec['x_d'].shape)}  restated layout vs reference source: {worst:.2e}")
+    return worst
+
+
 def main():
     import torch
 
@@ -485,6 +571,7 @@ def main():
               f"restatement vs reference source: {err:.2e}")
     print("worst", worst)
     worst = max(worst, main_models())
+    worst = max(worst, main_dataset())
     uninstall_shims()
     return 0 if worst < 1e-11 else 1
 

@@ -266,3 +266,60 @@ def test_reference_model_fixture_is_reproducible_from_the_reference_tree():
         PIN.uninstall_shims()
     import sys
     assert "jax" not in sys.modules and "diffrax" not in sys.modules
+
+
+# ---------------------------------------------------------------------------------------------------
+# data side of the boundary: the reference's control-path builders (src/configs/dataset_configs.py, executed unmodified)
+# ---------------------------------------------------------------------------------------------------
+def test_reference_layout_matches_reference_source_fixture():
+    """What the trainers hand to the models (trainer_pgt.py:201-207): PGTDataSetCfg.process_window -> graph_path_coeffs /
+    x_coeffs as (d, c, b, a), each [T-1, n, n|e, 2] with the last axis (time, value); ODEDataSetCfg for float time stamps."""
+    g = np.load(os.path.join(GOLD, "refsrc_dataset.npz"))
+    window = PIN.dataset_window()
+    ts = torch.arange(len(window) - 1)
+    A = torch.stack([w.adj for w in window[:-1]])
+    x_t = torch.stack([w.x for w in window[:-1]])
+    assert np.array_equal(g["t"], ts.numpy()) and np.array_equal(g["true_y"], window[-1].y.numpy()) and np.array_equal(g["true_y0"], window[0].x.numpy())
+    for nm, mine_g, mine_x in zip("dcba", R.reference_layout_coeffs(ts, A), R.reference_layout_xcoeffs(ts, x_t)):
+        assert g[f"graph_{nm}"].shape == (len(window) - 2, PIN.DATASET_CASE["n"], PIN.DATASET_CASE["n"], 2)
+        assert np.array_equal(mine_g.numpy(), g[f"graph_{nm}"]), nm
+        assert np.array_equal(mine_x.numpy(), g[f"x_{nm}"]), nm
+    assert np.array_equal(g["graph_a"][..., 0], np.broadcast_to(np.arange(3.0)[:, None, None], (3, 11, 11)))   # time channel
+    ts_f = torch.from_numpy(np.linspace(0.0, 5.0, 6))
+    A_f = torch.from_numpy(R.synthetic_graph_path(9, 6, PIN.DATASET_CASE["seed"] + 1))
+    for nm, mine in zip("dcba", R.reference_layout_coeffs(ts_f, A_f)):
+        assert np.allclose(mine.numpy(), g[f"ode_graph_{nm}"], rtol=0, atol=1e-12), nm
+
+
+def test_product_hermite_builder_matches_reference_source_fixture():
+    """The product's host-side builder (control.backward_hermite_coefficients, used by TGBGraphNeuralCDE) on the same window."""
+    import perm_equiv_graph_neural_cdes_b200 as P
+
+    g = np.load(os.path.join(GOLD, "refsrc_dataset.npz"))
+    window = PIN.dataset_window()
+    ts = torch.arange(len(window) - 1, dtype=torch.float64)
+    x_t = torch.stack([w.x for w in window[:-1]])
+    x_path = torch.stack([ts[:, None, None].expand_as(x_t), x_t], dim=-1)
+    for nm, mine in zip("dcba", P.backward_hermite_coefficients(ts, x_path)):
+        assert np.allclose(mine.numpy(), g[f"x_{nm}"], rtol=0, atol=1e-12), nm
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(PIN.REFERENCE_SRC, "models", "vector_fields")),
+                    reason="the reference tree exists only in the build container")
+def test_reference_dataset_fixture_is_reproducible_from_the_reference_tree():
+    import types
+
+    g = np.load(os.path.join(GOLD, "refsrc_dataset.npz"))
+    mod = PIN.load_reference_dataset_configs()
+    try:
+        assert mod.__file__.startswith(PIN.REFERENCE_SRC)
+        cfg = types.SimpleNamespace(interpolation="cubic")
+        cfg.get_interpolation_coeffs = lambda ts, sig: mod.PGTDataSetCfg.get_interpolation_coeffs(cfg, ts, sig)
+        d = mod.PGTDataSetCfg.process_window(cfg, PIN.dataset_window())
+        for i, nm in enumerate("dcba"):
+            assert np.array_equal(d["graph_path_coeffs"][i].numpy(), g[f"graph_{nm}"])
+            assert np.array_equal(d["x_coeffs"][i].numpy(), g[f"x_{nm}"])
+    finally:
+        PIN.uninstall_shims()
+    import sys
+    assert "jax" not in sys.modules and "torch_geometric" not in sys.modules
