@@ -458,6 +458,28 @@ def load_reference_dataset_configs():
     return mod
 
 
+def load_reference_function(rel_path, func_name, namespace):
+    """One top-level function of a reference file, compiled from its own (unmodified) source lines -- for modules whose
+    import pulls in the whole training stack (wandb, exca, optax, every config class): src/engine/trainer_pgt.py."""
+    import ast
+
+    path = os.path.join(REFERENCE_SRC, rel_path)
+    tree = ast.parse(open(path).read(), filename=path)
+    node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == func_name)
+    module = ast.Module(body=[node], type_ignores=[])
+    exec(compile(module, path, "exec"), namespace)
+    return namespace[func_name]
+
+
+def reference_pgt_mse_loss():
+    """mse_loss of src/engine/trainer_pgt.py:45-66 on the numpy stand-in for jax.numpy."""
+    _install_shims()
+    import jax.numpy as jnp   # the stand-in
+
+    return load_reference_function(os.path.join("engine", "trainer_pgt.py"), "mse_loss",
+                                   {"jnp": jnp, "PGTGraphNeuralODE": type("PGTGraphNeuralODE", (), {})})
+
+
 DATASET_CASE = dict(n=11, e=3, window=5, seed=41)     # England-like window: 5 snapshots, the last one is the label
 
 
@@ -504,6 +526,15 @@ def main_dataset():
         rec[f"ode_graph_{nm}"] = np.asarray(co[i])
     for i, mine in enumerate(R.reference_layout_coeffs(torch.from_numpy(ts_f), torch.from_numpy(A_f))):
         worst = max(worst, float((mine - torch.from_numpy(np.asarray(co[i]))).abs().max()))
+    # the loss the PGT trainer differentiates (trainer_pgt.py:45-66): the model's global read-out [feature_dim] reshaped to
+    # (feature_dim, 1) against label [n] -- broadcast (1,1) - (n,) -> (1,n), kept as the reference computes it
+    mse = reference_pgt_mse_loss()
+    rng = np.random.default_rng(DATASET_CASE["seed"])
+    y_pred, label = rng.standard_normal((1,)), rng.standard_normal((DATASET_CASE["n"],))
+    rec["loss_y_pred"], rec["loss_label"] = y_pred, label
+    rec["loss"] = mse(lambda t, a, x, x0: y_pred, (None, None, None, None, label))
+    mine = R.pgt_mse_loss(torch.ones(1, 1, dtype=torch.float64), torch.from_numpy(y_pred).reshape(1, 1), torch.from_numpy(label))
+    worst = max(worst, abs(float(mine) - float(rec["loss"])))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "refsrc_dataset.npz"), **rec)
     print(f"refsrc_dataset: graph coeffs {tuple(rec['graph_d'].shape)} x coeffs {tuple(rec['x_d'].shape)}  restated layout vs reference source: {worst:.2e}")
     return worst

@@ -323,3 +323,18 @@ def test_reference_dataset_fixture_is_reproducible_from_the_reference_tree():
         PIN.uninstall_shims()
     import sys
     assert "jax" not in sys.modules and "torch_geometric" not in sys.modules
+
+
+def test_pgt_mse_loss_matches_reference_source_fixture():
+    """mse_loss of src/engine/trainer_pgt.py:45-66 (compiled from the reference's own lines): the (1,1) - (n,) broadcast is kept."""
+    g = np.load(os.path.join(GOLD, "refsrc_dataset.npz"))
+    y_pred, label = torch.from_numpy(g["loss_y_pred"]), torch.from_numpy(g["loss_label"])
+    mine = R.pgt_mse_loss(torch.ones(1, 1, dtype=torch.float64), y_pred.reshape(1, 1), label)
+    assert abs(float(mine) - float(g["loss"])) < 1e-14
+    assert abs(float(g["loss"]) - float(((y_pred.reshape(1, 1) - label) ** 2).mean())) < 1e-14
+    if os.path.isdir(os.path.join(PIN.REFERENCE_SRC, "engine")):
+        try:
+            mse = PIN.reference_pgt_mse_loss()
+            assert float(mse(lambda t, a, x, x0: g["loss_y_pred"], (None, None, None, None, g["loss_label"]))) == float(g["loss"])
+        finally:
+            PIN.uninstall_shims()
