@@ -227,3 +227,16 @@ def test_bench_reference_arm_is_silent_on_nonzero_ranks():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "england", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_c_abi_dense_weights_satisfy_the_continuous_order_conditions():
+    """pegncde_tsit5_dense_weights (fp32, expanded Horner form) against the order-4 conditions of the interpolant -- a check that
+    does not go through the oracle's (factored) restatement of the same polynomials."""
+    from tests.test_oracle import _tsit5_trees
+
+    A, c, trees = _tsit5_trees()
+    for theta in (0.0, 0.1, 0.35, 0.5, 0.77, 1.0):
+        w = P.dense_weights(theta).astype(np.float64)
+        for order, phi, gamma in trees:
+            if order <= 4:
+                assert abs(w @ phi - theta**order / gamma) < 3e-6, (theta, order, gamma)

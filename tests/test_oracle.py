@@ -338,3 +338,52 @@ def test_pgt_mse_loss_matches_reference_source_fixture():
             assert float(mse(lambda t, a, x, x0: g["loss_y_pred"], (None, None, None, None, g["loss_label"]))) == float(g["loss"])
         finally:
             PIN.uninstall_shims()
+
+
+# ---------------------------------------------------------------------------------------------------
+# third-party arithmetic pinned against mathematics: the Tsit5 constants must satisfy the Runge-Kutta order conditions
+# ---------------------------------------------------------------------------------------------------
+def _tsit5_trees():
+    """Elementary weights Phi(tree) and densities gamma(tree) of the 17 rooted trees up to order 5, for weights w: sum_i w_i Phi_i."""
+    A = np.zeros((7, 7))
+    for i, row in enumerate(R.TSIT5_A):
+        A[i, :len(row)] = row
+    c = np.array(R.TSIT5_C)
+    Ac, Ac2 = A @ c, A @ (c * c)
+    AAc = A @ Ac
+    one = np.ones(7)
+    trees = [  # (order, Phi, gamma)
+        (1, one, 1), (2, c, 2), (3, c**2, 3), (3, Ac, 6),
+        (4, c**3, 4), (4, c * Ac, 8), (4, Ac2, 12), (4, AAc, 24),
+        (5, c**4, 5), (5, c * c * Ac, 10), (5, c * Ac2, 15), (5, c * AAc, 30), (5, Ac * Ac, 20),
+        (5, A @ c**3, 20), (5, A @ (c * Ac), 40), (5, A @ Ac2, 60), (5, A @ AAc, 120),
+    ]
+    return A, c, trees
+
+
+def test_tsit5_tableau_satisfies_the_order_conditions():
+    """The restated tableau (diffrax.Tsit5 = Tsitouras 2011) is a 5th-order method with a 4th-order embedded estimate:
+    all 17 order-5 conditions for b, all 8 order-4 conditions for b_hat = b - b_err, row sums = c, FSAL row = b."""
+    A, c, trees = _tsit5_trees()
+    b, berr = np.array(R.TSIT5_B), np.array(R.TSIT5_BERR)
+    assert np.abs(A.sum(1) - c).max() < 2e-15
+    assert np.array_equal(A[6, :6], b[:6]) and b[6] == 0.0                       # FSAL: the 7th stage is evaluated at y1
+    for order, phi, gamma in trees:
+        assert abs(b @ phi - 1.0 / gamma) < 3e-15, (order, gamma)
+        if order <= 4:
+            assert abs((b - berr) @ phi - 1.0 / gamma) < 3e-15, ("embedded", order, gamma)
+    # ... and the embedded weights are genuinely 4th order only (the estimate does not vanish)
+    assert max(abs((b - berr) @ phi - 1.0 / gamma) for order, phi, gamma in trees if order == 5) > 1e-4
+
+
+def test_tsit5_dense_output_satisfies_the_continuous_order_conditions():
+    """b_i(theta) of the interpolant: sum_i b_i(theta) Phi_i(tree) = theta^order / gamma(tree) for every tree up to order 4,
+    b_i(0) = 0 and b_i(1) = b_i."""
+    A, c, trees = _tsit5_trees()
+    assert np.abs(np.array(R.tsit5_dense_weights(0.0), dtype=float)).max() == 0.0
+    assert np.abs(np.array(R.tsit5_dense_weights(1.0), dtype=float) - np.array(R.TSIT5_B)).max() < 5e-15
+    for theta in (0.05, 0.1, 0.35, 0.5, 0.77, 0.9, 1.0):
+        w = np.array(R.tsit5_dense_weights(theta), dtype=float)
+        for order, phi, gamma in trees:
+            if order <= 4:
+                assert abs(w @ phi - theta**order / gamma) < 5e-15, (theta, order, gamma)
