@@ -387,3 +387,20 @@ def test_tsit5_dense_output_satisfies_the_continuous_order_conditions():
         for order, phi, gamma in trees:
             if order <= 4:
                 assert abs(w @ phi - theta**order / gamma) < 5e-15, (theta, order, gamma)
+
+
+def test_initial_step_heuristic_matches_scipy():
+    """diffrax picks dt0=None steps with Hairer-Norsett-Wanner's starting-step algorithm (II.4); scipy.integrate ships an
+    independent implementation of the same published algorithm (order + 1 = error_order = 5 for a 5(4) pair)."""
+    from scipy.integrate._ivp.common import select_initial_step as scipy_select
+
+    rng = np.random.default_rng(0)
+    for trial in range(4):
+        M = torch.from_numpy(rng.standard_normal((6, 6)) * (0.3 + 0.4 * trial))
+        f = lambda t, y: torch.tanh(y @ M) * (1 + 0.1 * t)
+        y0 = torch.from_numpy(rng.standard_normal((4, 6)))
+        f0 = f(0.0, y0)
+        mine = float(R.select_initial_step(f, 0.0, y0, f0, 1e-3, 1e-6))
+        theirs = float(scipy_select(lambda t, y: f(t, torch.from_numpy(y.reshape(4, 6))).numpy().reshape(-1), 0.0, y0.numpy().reshape(-1),
+                                    5.0, np.inf, f0.numpy().reshape(-1), 1.0, 4, 1e-3, 1e-6))
+        assert abs(mine - theirs) < 2e-6 * theirs, (trial, mine, theirs)      # the oracle follows diffrax and works in fp32
