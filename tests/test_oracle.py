@@ -404,3 +404,29 @@ def test_initial_step_heuristic_matches_scipy():
         theirs = float(scipy_select(lambda t, y: f(t, torch.from_numpy(y.reshape(4, 6))).numpy().reshape(-1), 0.0, y0.numpy().reshape(-1),
                                     5.0, np.inf, f0.numpy().reshape(-1), 1.0, 4, 1e-3, 1e-6))
         assert abs(mine - theirs) < 2e-6 * theirs, (trial, mine, theirs)      # the oracle follows diffrax and works in fp32
+
+
+def test_hermite_path_matches_scipy_cubic_hermite_spline():
+    """backward_hermite_coefficients + CubicInterpolation == the cubic Hermite spline through the knots whose slope at knot k is the
+    backward difference m_{k-1} (m_0 at the first knot), evaluated by scipy's independent implementation."""
+    from scipy.interpolate import CubicHermiteSpline
+
+    rng = np.random.default_rng(3)
+    ts = np.array([0.0, 0.6, 1.0, 2.5, 3.0, 4.2])
+    ys = rng.standard_normal((6, 5))
+    m = (ys[1:] - ys[:-1]) / (ts[1:] - ts[:-1])[:, None]
+    spline = CubicHermiteSpline(ts, ys, np.concatenate([m[:1], m], axis=0))
+    ci = R.CubicInterpolation(torch.from_numpy(ts), R.backward_hermite_coefficients(torch.from_numpy(ts), torch.from_numpy(ys)))
+    for t in (0.0, 0.3, 0.6, 0.61, 1.7, 2.5, 2.9, 3.0, 4.0, 4.2):
+        assert np.allclose(ci.evaluate(t).numpy(), spline(t), rtol=0, atol=1e-13), t
+        if t not in ts:     # at a knot scipy returns the right-hand piece's derivative, diffrax's lookup the left-hand one (they agree: C1)
+            assert np.allclose(ci.derivative(t).numpy(), spline(t, 1), rtol=0, atol=1e-12), t
+
+
+def test_rms_norm_matches_torch_rms_norm():
+    """equinox.nn.RMSNorm arithmetic (x * rsqrt(mean(x^2) + eps) * weight, then + bias) against torch's independent rms_norm."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(7, 16, generator=g, dtype=torch.float64)
+    w, b = torch.randn(16, generator=g, dtype=torch.float64), torch.randn(16, generator=g, dtype=torch.float64)
+    ref = torch.nn.functional.rms_norm(x, (16,), weight=w, eps=1e-5) + b
+    assert torch.allclose(R.rms_norm(x, w, b), ref, rtol=0, atol=1e-14)
