@@ -1,7 +1,8 @@
 """Re-derives the goldens from the REAL reference stack (jax + equinox + diffrax + the reference's own
 src/models) wherever those packages are installed, and diffs them against the restatement in
 oracle/reference_path.py.  It cannot run in this repository's build image (no jax/diffrax/equinox wheels, no
-network) -- until it has been run somewhere, parity stays "unpinned" (see DESIGN.md (c)).
+network) -- until it has been run somewhere, the THIRD-PARTY half of the oracle (diffrax / equinox arithmetic) stays "unpinned";
+the reference's own code is pinned by oracle/pin_reference_source.py.
 
 Usage (in an environment with the reference's dependencies, from the repo root):
     PYTHONPATH=/path/to/reference/src JAX_PLATFORMS=cpu python -m oracle.regen_with_jax
@@ -20,7 +21,7 @@ def main():
         import jax.numpy as jnp
         from models.vector_fields import CDEWrapperVectorField, PermEquivGraphVectorField  # reference src/
     except Exception as exc:  # pragma: no cover - the whole point is that this cannot run here
-        print(f"reference stack unavailable ({exc!r}); parity stays unpinned")
+        print(f"reference stack unavailable ({exc!r}); the third-party half of the oracle stays unpinned")
         return 2
     import torch
 
