@@ -186,21 +186,29 @@ def test_oracle_matches_reference_source_fixtures(name):
 @pytest.mark.skipif(not os.path.isdir(os.path.join(PIN.REFERENCE_SRC, "models", "vector_fields")),
                     reason="the reference tree exists only in the build container")
 def test_reference_source_fixtures_are_reproducible_from_the_reference_tree():
-    """Re-executes the unmodified reference files (numpy stand-ins for jax / equinox) and compares with the committed fixture."""
-    name = "control"
-    g = np.load(os.path.join(GOLD, f"refsrc_{name}.npz"))
+    """Re-executes the unmodified reference files (numpy stand-ins for jax / equinox) and compares with the committed fixtures."""
     mods = PIN.load_reference_vector_fields()
     try:
-        p, ca, dir_tables = _oracle_outputs_for_refsrc(name)
-        pe, pd, gv, gn = PIN.build_reference_fields(mods, p, dir_tables)
-        nca, ncx = PIN.NumpyControl(ca), PIN.NumpyControl(R.CubicInterpolation(p.ts, p.x_coeffs))
-        wrapped = mods["cde_wrapper_vector_field"].CDEWrapperVectorField(pe, p.h)
-        wrapped_dir = mods["cde_wrapper_vector_field"].CDEWrapperVectorField(pd, p.h)
         assert mods["layers"].__file__.startswith(PIN.REFERENCE_SRC)     # the code under test is the reference's file
-        y = p.y0.numpy()
-        for k, t in enumerate(float(t) for t in g["times"]):
-            assert np.array_equal(wrapped(t, y, [nca, ncx]), g["vf_perm_equiv"][k])
-            assert np.array_equal(wrapped_dir(t, y, [nca, ncx]), g["vf_perm_equiv_dir"][k])
+        Wrapper = mods["cde_wrapper_vector_field"].CDEWrapperVectorField
+        for name, kw in PIN.REFSRC_CASES.items():
+            if kw["n"] > 40:
+                continue
+            g = np.load(os.path.join(GOLD, f"refsrc_{name}.npz"))
+            p, ca, dir_tables = _oracle_outputs_for_refsrc(name)
+            pe, pd, gv, gn = PIN.build_reference_fields(mods, p, dir_tables)
+            nca = PIN.NumpyControl(ca)
+            y = p.y0.numpy()
+            if p.e > 0:
+                ncx = PIN.NumpyControl(R.CubicInterpolation(p.ts, p.x_coeffs))
+                fields = {"perm_equiv": Wrapper(pe, p.h), "perm_equiv_dir": Wrapper(pd, p.h), "graph": Wrapper(gv, p.h)}
+                args = [nca, ncx]
+            else:
+                fields = {"perm_equiv": pe, "perm_equiv_dir": pd, "graph": gv, "gnode": gn}
+                args = nca
+            for k, t in enumerate(float(t) for t in g["times"]):
+                for key, field in fields.items():
+                    assert np.array_equal(field(t, y, args), g[f"vf_{key}"][k]), (name, key, t)
     finally:
         PIN.uninstall_shims()
     import sys
