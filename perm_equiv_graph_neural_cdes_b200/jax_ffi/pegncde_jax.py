@@ -17,6 +17,8 @@ _shim = ctypes.CDLL(os.path.join(_HERE, "libpegncde_ffi.so"))
 _core = ctypes.CDLL(os.path.join(os.path.dirname(_HERE), "libpegncde.so"))
 jax.ffi.register_ffi_target("peg_solve_fwd", jax.ffi.pycapsule(_shim.PegSolveFwd), platform="CUDA")
 jax.ffi.register_ffi_target("peg_solve_bwd", jax.ffi.pycapsule(_shim.PegSolveBwd), platform="CUDA")
+jax.ffi.register_ffi_target("peg_pack_adj", jax.ffi.pycapsule(_shim.PegPackAdj), platform="CUDA")
+jax.ffi.register_ffi_target("peg_pack_x", jax.ffi.pycapsule(_shim.PegPackX), platform="CUDA")
 
 
 def pack_params(vector_field):
@@ -32,6 +34,24 @@ def pack_params(vector_field):
 
 def _call(name, out_types, *args, **attrs):
     return jax.ffi.ffi_call(name, out_types, vmap_method="sequential")(*args, **attrs)
+
+
+def pack_control(ts, coeffs_adj, x_coeffs, dims):
+    """Once per batch: the reference-layout arrays the trainer passes to the model (``coeffs_adj`` = (d, c, b, a), each
+    ``[B, T-1, n, n, 2]``; ``x_coeffs`` likewise ``[B, T-1, n, e, 2]`` or None) -> the control tuple of ``make_fused_solve``
+    (ts, adj_coef, adj_rowsum, adj_diag, adj_total, tch_coef, x_coef) = the fields of ``PegControl`` in pegncde.h."""
+    B, n, e, T = dims["B"], dims["n"], dims["e"], dims["T"]
+    ldn = (n + 31) // 32 * 32
+    attrs = {k: np.int32(v) for k, v in dims.items()}
+    f32 = lambda *shape: jax.ShapeDtypeStruct(shape, jnp.float32)
+    outs = (f32(B, T - 1, 4 * ldn * ldn), f32(B, T - 1, 4, n), f32(B, T - 1, 4, n), f32(B, T - 1, 4), f32(B, T - 1, 3, n))
+    adj = _call("peg_pack_adj", outs, *[jnp.asarray(c, jnp.float32) for c in coeffs_adj], **attrs)
+    if e > 0:
+        (x_coef,) = _call("peg_pack_x", (f32(B, T - 1, 3, n, 2 * e),), *[jnp.asarray(c, jnp.float32) for c in x_coeffs], **attrs)
+    else:
+        x_coef = jnp.zeros((1,), jnp.float32)      # placeholder operand: the shim passes NULL when e == 0
+    ts_b = jnp.broadcast_to(jnp.asarray(ts, jnp.float32).reshape(-1, T)[:1] if jnp.ndim(ts) == 1 else jnp.asarray(ts, jnp.float32), (B, T))
+    return (ts_b, *adj, x_coef)
 
 
 def make_fused_solve(dims, step_ts, ws_bytes, store_elems):

@@ -240,3 +240,28 @@ def test_c_abi_dense_weights_satisfy_the_continuous_order_conditions():
         for order, phi, gamma in trees:
             if order <= 4:
                 assert abs(w @ phi - theta**order / gamma) < 3e-6, (theta, order, gamma)
+
+
+def test_jax_ffi_shim_type_checks_against_the_c_abi():
+    """jax_ffi/pegncde_ffi.cc cannot be built for real here (no XLA FFI headers), but it must stay consistent with
+    include/pegncde.h: compiled (syntax + types only) against tests/mock_xla_ffi, whose XLA_FFI_DEFINE_HANDLER_SYMBOL
+    static_asserts that every handler is invocable with exactly the types its binding declares."""
+    import shutil
+    import subprocess
+
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime_api.h")):
+        pytest.skip("no CUDA headers")
+    src = os.path.join(root, "perm_equiv_graph_neural_cdes_b200", "jax_ffi", "pegncde_ffi.cc")
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I" + os.path.join(root, "tests", "mock_xla_ffi"), "-I" + os.path.join(root, "include"),
+           "-I" + cuda_inc, src]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-3000:]
+    # ... and the mock does reject a binding that disagrees with its handler
+    bad = open(src).read().replace('.Attr<int32_t>("B")', '.Attr<float>("B")', 1)
+    assert bad != open(src).read()
+    out = subprocess.run(cmd[:-1] + ["-x", "c++", "-"], input=bad, capture_output=True, text=True, timeout=300)
+    assert out.returncode != 0 and "does not match its binding" in out.stderr
