@@ -265,3 +265,78 @@ def test_jax_ffi_shim_type_checks_against_the_c_abi():
     assert bad != open(src).read()
     out = subprocess.run(cmd[:-1] + ["-x", "c++", "-"], input=bad, capture_output=True, text=True, timeout=300)
     assert out.returncode != 0 and "does not match its binding" in out.stderr
+
+
+def test_jax_wrapper_operands_match_the_shim_bindings(monkeypatch):
+    """jax_ffi/pegncde_jax.py cannot run for real here (no jax).  Imported on a recording stand-in for `jax`, every ffi_call it
+    makes must hand the handler exactly as many operands / results / attributes as the binding in pegncde_ffi.cc declares."""
+    import importlib.util
+    import sys
+    import types
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cc = open(os.path.join(root, "perm_equiv_graph_neural_cdes_b200", "jax_ffi", "pegncde_ffi.cc")).read()
+    cc = cc.replace(".PEG_DIM_ATTRS()", "".join(f'.Attr<int32_t>("{k}")' for k in ("B", "n", "h", "e", "L", "T", "flags")))
+    bindings = {}
+    for m in re.finditer(r"XLA_FFI_DEFINE_HANDLER_SYMBOL\((\w+),\s*\w+,(.*?)\);", cc, flags=re.S):
+        body = m.group(2)
+        bindings[m.group(1)] = (body.count(".Arg<"), body.count(".Ret<"), sorted(re.findall(r'\.Attr<[^>]*>+\("(\w+)"\)', body)))
+    assert set(bindings) == {"PegSolveFwd", "PegSolveBwd", "PegPackAdj", "PegPackX"}
+
+    calls, targets = [], {}
+
+    class Struct:
+        def __init__(self, shape, dtype):
+            self.shape, self.dtype = tuple(shape), dtype
+
+    def ffi_call(name, out_types, vmap_method=None):
+        def run(*args, **attrs):
+            calls.append((name, len(args), len(out_types), sorted(attrs)))
+            return tuple(np.zeros(o.shape, o.dtype) for o in out_types)
+        return run
+
+    jax = types.ModuleType("jax")
+    jnp = types.ModuleType("jax.numpy")
+    for nm in ("asarray", "zeros", "zeros_like", "broadcast_to", "concatenate", "ndim", "float32", "uint8"):
+        setattr(jnp, nm, getattr(np, nm))
+    jax.numpy = jnp
+    jax.ShapeDtypeStruct = Struct
+    jax.ffi = types.SimpleNamespace(register_ffi_target=lambda name, capsule, platform=None: targets.__setitem__(name, capsule),
+                                    pycapsule=lambda sym: sym, ffi_call=ffi_call)
+    jax.tree_util = types.SimpleNamespace(tree_map=lambda f, t: tuple(f(x) for x in t))
+
+    class custom_vjp:
+        def __init__(self, fn):
+            self.fn = fn
+
+        def defvjp(self, fwd, bwd):
+            self.fwd, self.bwd = fwd, bwd
+
+        def __call__(self, *a):
+            return self.fn(*a)
+
+    jax.custom_vjp = custom_vjp
+    monkeypatch.setitem(sys.modules, "jax", jax)
+    monkeypatch.setitem(sys.modules, "jax.numpy", jnp)
+    real_cdll = ctypes.CDLL
+    monkeypatch.setattr(ctypes, "CDLL", lambda path, *a, **k: types.SimpleNamespace(PegSolveFwd="PegSolveFwd", PegSolveBwd="PegSolveBwd", PegPackAdj="PegPackAdj", PegPackX="PegPackX")
+                        if str(path).endswith("libpegncde_ffi.so") else real_cdll(path, *a, **k))
+    spec = importlib.util.spec_from_file_location("pegncde_jax_under_test", os.path.join(root, "perm_equiv_graph_neural_cdes_b200", "jax_ffi", "pegncde_jax.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert targets == {"peg_solve_fwd": "PegSolveFwd", "peg_solve_bwd": "PegSolveBwd", "peg_pack_adj": "PegPackAdj", "peg_pack_x": "PegPackX"}
+
+    dims = dict(B=2, n=40, h=8, e=3, L=2, T=4, flags=0)
+    f = lambda *s: np.zeros(s, np.float32)
+    control = mod.pack_control(np.arange(4), [f(2, 3, 40, 40, 2)] * 4, [f(2, 3, 40, 3, 2)] * 4, dims)
+    assert len(control) == 7 and control[0].shape == (2, 4) and control[1].shape == (2, 3, 4 * 64 * 64) and control[6].shape == (2, 3, 3, 40, 6)
+    solve = mod.make_fused_solve(dims, np.linspace(0, 3, 31), ws_bytes=1024, store_elems=16)
+    params, y0 = f(100), f(2, 40, 8)
+    y_ckpt, res = solve.fwd(params, control, y0)
+    assert y_ckpt.shape == (31, 2, 40, 8) and solve(params, control, y0).shape == (31, 2, 40, 8)
+    g_params, g_control, g_y0 = solve.bwd(res, np.zeros_like(y_ckpt))
+    assert g_params.shape == params.shape and g_y0.shape == y0.shape and len(g_control) == 7
+    seen = {}
+    for name, nargs, nouts, attrs in calls:
+        seen[targets[name]] = (nargs, nouts, attrs)
+    assert seen == bindings, (seen, bindings)
