@@ -24,7 +24,11 @@
  *
  * Conventions
  *   - every pointer except `step_ts` is a DEVICE pointer owned by the caller (XLA / torch);
- *     the library never allocates, frees or retains device memory and keeps no global state.
+ *     the library never allocates, frees or retains device memory.  Host-side state is limited to: the process-wide
+ *     launch counter and the optional profiling hooks (pegncde_profile_*, off by default), and two PER-THREAD caches
+ *     (TMA descriptors keyed on buffer address and shape; a snapshot of the PEG_TC_* schedule-tuning environment
+ *     variables taken at the start of every API call).  Nothing a call computes depends on an earlier call; accuracy
+ *     modes are selected through PegDims.flags only, never through the environment.
  *   - functions only ENQUEUE work on `stream` (no device synchronisation, no host callbacks),
  *     so they are safe inside an XLA custom call and capturable in a CUDA graph.
  *   - all floating-point data is fp32 (the reference never enables x64), row-major.
@@ -56,10 +60,16 @@ enum {
 /* flags in PegDims.flags */
 enum {
   PEG_FLAG_RELU = 0,            /* reserved */
-  PEG_FLAG_TENSOR_CORES = 1,    /* n x n x d contractions on tcgen05 (3xTF32 split: fp32-parity) */
+  PEG_FLAG_TENSOR_CORES = 1,    /* n x n x d contractions on tcgen05 (split operands, fp32 accumulation: fp32-parity) */
   PEG_FLAG_TF32_FAST = 2,       /* with TENSOR_CORES: single-pass TF32 (rna-rounded), looser tolerance */
-  PEG_FLAG_DIRECTED = 4         /* ConvEquivFusionDirectedLayer (layers.py:180-362): 11 parameter pairs, row AND column sums;
+  PEG_FLAG_DIRECTED = 4,        /* ConvEquivFusionDirectedLayer (layers.py:180-362): 11 parameter pairs, row AND column sums;
                                    needs PegControl.adj_colsum; fusion block = 22 (+2 pad) scalars (see parameter packing) */
+  PEG_FLAG_TF32X3 = 16,         /* with TENSOR_CORES: operands of the n x n x d contraction split as 3xTF32 (rounding ~2^-22 per product)
+                                   instead of the default bf16x2 split (x = hi + lo, both bf16, three products on kind::f16 at twice
+                                   the tf32 rate: rounding ~2^-17 per product, fp32 accumulation; still inside the fp32 parity
+                                   tolerance) */
+  PEG_FLAG_ADJ_LIGHT = 8        /* with TENSOR_CORES: the adjoint contraction runs two of its four products single-pass; looser
+                                   stated tolerance on the param1 / param2 gradients (2.5e-3 instead of 1e-3).  Off by default. */
 };
 
 typedef struct PegDims {

@@ -15,6 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libpegncde.so")
 PEG_FLAG_TENSOR_CORES = 1
 PEG_FLAG_TF32_FAST = 2
 PEG_FLAG_DIRECTED = 4
+PEG_FLAG_ADJ_LIGHT = 8
+PEG_FLAG_TF32X3 = 16
 
 PEG_WS_VF_FWD, PEG_WS_VF_VJP, PEG_WS_SOLVE_FWD, PEG_WS_SOLVE_BWD, PEG_WS_STEP = range(5)
 

@@ -98,9 +98,26 @@ class PackedControl:
         self.tch_coef = torch.empty((B, T - 1, 3, n), **f)
         self.x_coef = torch.empty((B, T - 1, 3, n, 2 * e), **f) if e > 0 else None
         self.x_packed = None   # differentiable source of x_coef when the node-signal coefficients require grad
-        self.adj_colsum = None  # [B,T-1,4,n] column sums of the planes: built on demand (directed fusion layer only)
-        self.pending = None    # host (d,c,b,a) arrays whose adjacency planes have not been copied / packed yet (streamed)
-        self.host_ts = None    # knot times shared by the batch (streaming needs one time grid), numpy fp32
+        # state of the adjacency part, SHARED by every view made with with_x(): column sums of the planes ([B,T-1,4,n], built on
+        # demand for the directed fusion layer), the host (d,c,b,a) arrays whose planes have not been copied / packed yet
+        # (streamed controls) and the knot times shared by the batch (streaming needs one time grid; numpy fp32)
+        self._adj = {"colsum": None, "pending": None, "host_ts": None}
+
+    adj_colsum = property(lambda self: self._adj["colsum"], lambda self, v: self._adj.__setitem__("colsum", v))
+    pending = property(lambda self: self._adj["pending"], lambda self, v: self._adj.__setitem__("pending", v))
+    host_ts = property(lambda self: self._adj["host_ts"], lambda self, v: self._adj.__setitem__("host_ts", v))
+
+    def with_x(self, x_coeffs) -> "PackedControl":
+        """The same adjacency planes (shared tensors, shared streaming state -- no copy, no re-pack) paired with the
+        node-signal coefficients ``x_coeffs = (d,c,b,a)``, each ``[T-1,n,e,2]`` or ``[B,T-1,n,e,2]``."""
+        v = PackedControl.__new__(PackedControl)
+        v.B, v.n, v.T, v.ldn = self.B, self.n, self.T, self.ldn
+        for name in ("ts", "adj_coef", "adj_rowsum", "adj_diag", "adj_total", "tch_coef"):
+            setattr(v, name, getattr(self, name))
+        v._adj = self._adj
+        v._keepalive = self
+        _attach_x(v, x_coeffs, self.device)
+        return v
 
     def pack_pieces(self, begin: int, count: int, staging, stream_ptr: int) -> None:
         """Packs cubic pieces [begin, begin+count) from device staging arrays (d,c,b,a each [B,count,n,n,2])."""
@@ -130,9 +147,8 @@ class PackedControl:
             setattr(v, name, getattr(self, name)[b:b + 1])
         v.x_coef = self.x_coef[b:b + 1] if self.x_coef is not None else None
         v.x_packed = None
-        cs = getattr(self, "adj_colsum", None)
-        v.adj_colsum = cs[b:b + 1] if cs is not None else None
-        v.pending, v.host_ts = None, None
+        cs = self.adj_colsum
+        v._adj = {"colsum": cs[b:b + 1] if cs is not None else None, "pending": None, "host_ts": None}
         v._keepalive = self
         return v
 
@@ -174,6 +190,31 @@ def _as_batched(x: torch.Tensor, nd_unbatched: int) -> torch.Tensor:
     return x.unsqueeze(0) if x.dim() == nd_unbatched else x
 
 
+def _attach_x(pc: "PackedControl", x_coeffs, device) -> None:
+    """Sets the node-signal part (e, x_coef, x_packed) of ``pc`` from reference-layout coefficients (or clears it)."""
+    pc.x_packed = None
+    if x_coeffs is None:
+        pc.e, pc.x_coef = 0, None
+        return
+    if isinstance(x_coeffs, torch.Tensor):
+        x_coeffs = tuple(x_coeffs[i] for i in range(4))
+    cx = [_as_batched(c, 4).to(device=device, dtype=torch.float32, non_blocking=True).contiguous() for c in x_coeffs]
+    B, Tm1, n, e = cx[0].shape[0], cx[0].shape[1], cx[0].shape[2], cx[0].shape[3]
+    if (B, Tm1, n) != (pc.B, pc.T - 1, pc.n):
+        raise ValueError(f"node-signal coefficients [B={B},T-1={Tm1},n={n}] do not match the adjacency control [B={pc.B},T-1={pc.T - 1},n={pc.n}]")
+    pc.e = e
+    if any(c.requires_grad for c in cx):
+        # learnable node-signal path (TGB models, tgb_graph_neural_cde.py:118-137): the re-layout stays on the autograd
+        # tape so that pegncde_solve_bwd's g_xcoef flows back into backward_hermite_coefficients / the data encoder
+        pc.x_packed = torch.stack([cx[2], cx[1], cx[0]], dim=2).reshape(B, Tm1, 3, n, 2 * e)
+        pc.x_coef = pc.x_packed.detach().contiguous()
+    else:
+        pc.x_coef = torch.empty((B, Tm1, 3, n, 2 * e), dtype=torch.float32, device=device)
+        check(lib().pegncde_pack_x(_stream_ptr(device), pc.dims(h=4, L=1), cx[0].data_ptr(), cx[1].data_ptr(), cx[2].data_ptr(),
+                                   cx[3].data_ptr(), pc.x_coef.data_ptr()), "pegncde_pack_x")
+        pc._x_keepalive = cx   # sources stay alive until the pack kernel has run (stream-ordered)
+
+
 def pack_control(
     ts: torch.Tensor,
     coeffs_adj: Sequence[torch.Tensor],
@@ -195,37 +236,17 @@ def pack_control(
         return _pack_control_streamed(ts, coeffs_adj, x_coeffs, device)
     cad = [_as_batched(c, 4).to(device=device, dtype=torch.float32).contiguous() for c in coeffs_adj]
     B, Tm1, n = cad[0].shape[0], cad[0].shape[1], cad[0].shape[2]
-    e = 0
-    cx = None
-    if x_coeffs is not None:
-        cx = [_as_batched(c, 4).to(device=device, dtype=torch.float32).contiguous() for c in x_coeffs]
-        e = cx[0].shape[3]
-    pc = PackedControl(B, n, Tm1 + 1, e, device)
+    pc = PackedControl(B, n, Tm1 + 1, 0, device)
     tsb = _as_batched(ts, 1).to(device=device, dtype=torch.float32)
     pc.ts.copy_(tsb.expand(B, Tm1 + 1))
-    dims = pc.dims(h=4, L=1)
-    st = _stream_ptr(device)
-    l = lib()
     check(
-        l.pegncde_pack_adj(st, dims, cad[0].data_ptr(), cad[1].data_ptr(), cad[2].data_ptr(), cad[3].data_ptr(),
-                           pc.adj_coef.data_ptr(), pc.adj_rowsum.data_ptr(), pc.adj_diag.data_ptr(),
-                           pc.adj_total.data_ptr(), pc.tch_coef.data_ptr()),
+        lib().pegncde_pack_adj(_stream_ptr(device), pc.dims(h=4, L=1), cad[0].data_ptr(), cad[1].data_ptr(), cad[2].data_ptr(),
+                               cad[3].data_ptr(), pc.adj_coef.data_ptr(), pc.adj_rowsum.data_ptr(), pc.adj_diag.data_ptr(),
+                               pc.adj_total.data_ptr(), pc.tch_coef.data_ptr()),
         "pegncde_pack_adj",
     )
-    pc.x_packed = None
-    if cx is not None and any(c.requires_grad for c in cx):
-        # learnable node-signal path (TGB models, tgb_graph_neural_cde.py:118-137): the re-layout stays on the autograd
-        # tape so that pegncde_solve_bwd's g_xcoef flows back into backward_hermite_coefficients / the data encoder
-        pc.x_packed = torch.stack([cx[2], cx[1], cx[0]], dim=2).reshape(B, Tm1, 3, n, 2 * e)
-        pc.x_coef = pc.x_packed.detach().contiguous()
-    elif cx is not None:
-        check(
-            l.pegncde_pack_x(st, dims, cx[0].data_ptr(), cx[1].data_ptr(), cx[2].data_ptr(), cx[3].data_ptr(),
-                             pc.x_coef.data_ptr()),
-            "pegncde_pack_x",
-        )
-    # keep the sources alive until the pack kernels have run (stream-ordered)
-    pc._keepalive = (cad, cx)
+    _attach_x(pc, x_coeffs, device)
+    pc._keepalive = cad   # keep the sources alive until the pack kernels have run (stream-ordered)
     return pc
 
 
@@ -239,24 +260,14 @@ def _pack_control_streamed(ts, coeffs_adj, x_coeffs, device) -> PackedControl:
         c = _as_batched(c, 4).to(torch.float32).contiguous()
         cad.append(c if c.is_pinned() else c.pin_memory())
     B, Tm1, n = cad[0].shape[0], cad[0].shape[1], cad[0].shape[2]
-    e = 0
-    cx = None
-    if x_coeffs is not None:
-        cx = [_as_batched(c, 4).to(device=device, dtype=torch.float32, non_blocking=True).contiguous() for c in x_coeffs]
-        e = cx[0].shape[3]
-    pc = PackedControl(B, n, Tm1 + 1, e, device)
+    pc = PackedControl(B, n, Tm1 + 1, 0, device)
     tsb = _as_batched(ts, 1).to(torch.float32)
     pc.ts.copy_(tsb.expand(B, Tm1 + 1), non_blocking=True)
-    pc.x_packed = None
-    if cx is not None and any(c.requires_grad for c in cx):
-        pc.x_packed = torch.stack([cx[2], cx[1], cx[0]], dim=2).reshape(B, Tm1, 3, n, 2 * e)
-        pc.x_coef = pc.x_packed.detach().contiguous()
-    elif cx is not None:
-        check(lib().pegncde_pack_x(_stream_ptr(device), pc.dims(h=4, L=1), cx[0].data_ptr(), cx[1].data_ptr(), cx[2].data_ptr(),
-                                   cx[3].data_ptr(), pc.x_coef.data_ptr()), "pegncde_pack_x")
+    _attach_x(pc, x_coeffs, device)
     pc.pending = cad
-    pc.host_ts = tsb.reshape(-1, Tm1 + 1)[0].cpu().numpy().copy() if bool((tsb.reshape(-1, Tm1 + 1) == tsb.reshape(-1, Tm1 + 1)[0]).all()) else None
-    pc._keepalive = (cad, cx)
+    grid = tsb.reshape(-1, Tm1 + 1)
+    pc.host_ts = grid[0].cpu().numpy().copy() if bool((grid == grid[0]).all()) else None
+    pc._keepalive = cad
     return pc
 
 
@@ -283,15 +294,11 @@ def build_control(ts: torch.Tensor, snapshots: torch.Tensor, x_t: Optional[torch
             X = torch.stack([tsx[b][:, None, None].expand(T, n, e), xb[b]], dim=-1)
             per.append(backward_hermite_coefficients(tsx[b], X))
         cx = [torch.stack([per[b][i] for b in range(B)]).contiguous() for i in range(4)]
-    pc = PackedControl(B, n, T, e, device)
+    pc = PackedControl(B, n, T, 0, device)
     pc.ts.copy_(_as_batched(ts, 1).to(device=device, dtype=torch.float32).expand(B, T))
-    dims = pc.dims(h=4, L=1)
-    st = _stream_ptr(device)
-    l = lib()
-    check(l.pegncde_build_adj(st, dims, pc.ts.data_ptr(), A.data_ptr(), pc.adj_coef.data_ptr(), pc.adj_rowsum.data_ptr(),
-                              pc.adj_diag.data_ptr(), pc.adj_total.data_ptr(), pc.tch_coef.data_ptr()), "pegncde_build_adj")
-    if cx is not None:
-        check(l.pegncde_pack_x(st, dims, cx[0].data_ptr(), cx[1].data_ptr(), cx[2].data_ptr(), cx[3].data_ptr(),
-                               pc.x_coef.data_ptr()), "pegncde_pack_x")
-    pc._keepalive = (A, cx)
+    check(lib().pegncde_build_adj(_stream_ptr(device), pc.dims(h=4, L=1), pc.ts.data_ptr(), A.data_ptr(), pc.adj_coef.data_ptr(),
+                                  pc.adj_rowsum.data_ptr(), pc.adj_diag.data_ptr(), pc.adj_total.data_ptr(), pc.tch_coef.data_ptr()),
+          "pegncde_build_adj")
+    _attach_x(pc, cx, device)
+    pc._keepalive = A
     return pc

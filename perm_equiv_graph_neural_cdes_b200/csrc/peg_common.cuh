@@ -163,9 +163,10 @@ __device__ __forceinline__ float block_sum(float v, float* sh /* >= 33 floats */
 //   * column sums cb[b][0][c] = sum_i V[b,i,c], cb[b][1][c] = sum_i vec[b][i] V[b,i,c], reduced deterministically:
 //     every block writes its partial, the last block of a column group (ticket) adds them in block order.
 struct ProducerOut {
-  float* Thi;             // nullable
+  float* Thi;             // nullable; t16 == 0: fp32 words holding tf32-rounded values, t16 == 1: packed bf16 (same buffer)
   float* Tlo;
   int npad;
+  int t16;                // operand format of the contraction that will read V^T: 0 = 3xTF32 (peg_tc.cu), 1 = bf16x2 (peg_tc16.cu)
   float* cb;              // nullable
   float* partial;         // [B][chunks][2][d]
   unsigned int* tickets;  // self-resetting, one per (b, column group)
@@ -177,6 +178,38 @@ __device__ __forceinline__ float tf32_round(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+
+__device__ __forceinline__ unsigned short bf16_bits_rn(float x) {
+  unsigned short r;
+  asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return r;
+}
+// one element of V^T (hi + lo parts) at element offset o of the [B][d][npad] operand arrays, in the format the contraction reads
+__device__ __forceinline__ void store_vt(const ProducerOut& po, size_t o, float v) {
+  if (po.t16) {
+    const unsigned short h = bf16_bits_rn(v);
+    reinterpret_cast<unsigned short*>(po.Thi)[o] = h;
+    reinterpret_cast<unsigned short*>(po.Tlo)[o] = bf16_bits_rn(v - __uint_as_float((uint32_t)h << 16));
+  } else {
+    const float h = tf32_round(v);
+    po.Thi[o] = h;
+    po.Tlo[o] = v - h;
+  }
+}
+// four consecutive elements along the node axis (o multiple of 4)
+__device__ __forceinline__ void store_vt4(const ProducerOut& po, size_t o, float v0, float v1, float v2, float v3) {
+  if (po.t16) {
+    const uint32_t h0 = bf16_bits_rn(v0), h1 = bf16_bits_rn(v1), h2 = bf16_bits_rn(v2), h3 = bf16_bits_rn(v3);
+    const uint32_t l0 = bf16_bits_rn(v0 - __uint_as_float(h0 << 16)), l1 = bf16_bits_rn(v1 - __uint_as_float(h1 << 16));
+    const uint32_t l2 = bf16_bits_rn(v2 - __uint_as_float(h2 << 16)), l3 = bf16_bits_rn(v3 - __uint_as_float(h3 << 16));
+    *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(po.Thi) + o) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+    *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(po.Tlo) + o) = make_uint2(l0 | (l1 << 16), l2 | (l3 << 16));
+  } else {
+    const float h0 = tf32_round(v0), h1 = tf32_round(v1), h2 = tf32_round(v2), h3 = tf32_round(v3);
+    *reinterpret_cast<float4*>(po.Thi + o) = make_float4(h0, h1, h2, h3);
+    *reinterpret_cast<float4*>(po.Tlo + o) = make_float4(v0 - h0, v1 - h1, v2 - h2, v3 - h3);
+  }
 }
 
 // called by ALL threads of the block after this block's partial sums for columns [c0, c0+ncols) have been written

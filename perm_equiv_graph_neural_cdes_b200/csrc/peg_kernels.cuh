@@ -14,11 +14,13 @@ namespace peg {
 // reference layout: d,c,b,a each [B, T-1, n, n, 2], last axis (time, adjacency)
 // =====================================================================================
 
-// grid (nt*nt tiles, T-1, B), block 256: one block per 32x32 tile.  Source is the reference layout
-// (d,c,b,a each [B,T-1,n,n,2]), or the already tiled planes (tiled_in, pegncde_adj_stats), or the raw graph
+// grid (nt column tiles, T-1, B), block 256: one block per COLUMN of 32x32 tiles, walked top to bottom.  Source is the
+// reference layout (d,c,b,a each [B,T-1,n,n,2]), or the already tiled planes (tiled_in, pegncde_adj_stats), or the raw graph
 // snapshots A_k [B,T,n,n] + knot times (snap / ts, pegncde_build_adj: backward_hermite_coefficients fused in,
 // same operation order as the host formula so both routes give identical planes).
 // Reads are coalesced float2 rows of the source, writes are coalesced float4 of the 16-KB tile (staged in smem).
+// The column means of the time channel (tch) are summed by the block that owns the column tile, rows in ascending order and
+// the 8 warps in a fixed order: no float atomics, so the packed control is reproducible bit for bit.
 __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, const float* __restrict__ cc,
                                                   const float* __restrict__ cb, const float* __restrict__ ca,
                                                   const float* __restrict__ tiled_in, const float* __restrict__ snap,
@@ -27,76 +29,83 @@ __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, 
                                                   float* __restrict__ diag, float* __restrict__ total,
                                                   float* __restrict__ tch) {
   __shared__ __align__(16) float tile[4096];   // the tile in its final element order
-  __shared__ float tcol[3][32];                // column sums of the time channel of (b,c,d)
+  __shared__ float tcol[8][3][32];             // per-warp column sums of the time channel of (b,c,d)
   // blockIdx.y walks `gridDim.y` cubic pieces starting at piece0; the reference-layout source holds in_Tm1 pieces per
   // graph (== Tm1 for a whole path, == the count of a streamed range: pegncde_pack_adj_range)
   const int b = blockIdx.z, iv = piece0 + blockIdx.y;
   const int nt = npad >> 5;
-  const int rt = blockIdx.x / nt, ct = blockIdx.x % nt;
-  const int lane = threadIdx.x & 31;
+  const int ct = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t slab = ((size_t)b * Tm1 + iv);
   const size_t in_slab = (size_t)b * in_Tm1 + blockIdx.y;
-  const size_t tile_base = slab * 4 * (size_t)npad * npad + ((size_t)rt * nt + ct) * 4096;
   const float* src[4] = {ca, cb, cc, cd};  // (a,b,c,d) order
   float tsum[3] = {0.f, 0.f, 0.f};
-  if (threadIdx.x < 96) tcol[threadIdx.x >> 5][lane] = 0.f;
-  __syncthreads();
-  if (tiled_in) {
-    for (int idx = threadIdx.x; idx < 1024; idx += 256)
-      *reinterpret_cast<float4*>(&tile[4 * idx]) = *reinterpret_cast<const float4*>(tiled_in + tile_base + 4 * idx);
-    __syncthreads();
-  }
   float dt = 1.f, dtp = 1.f;
   if (snap) {
     const float* tb = ts + (size_t)b * (Tm1 + 1);
     dt = tb[iv + 1] - tb[iv];
     dtp = iv > 0 ? tb[iv] - tb[iv - 1] : dt;
   }
-  for (int idx = threadIdx.x; idx < 1024; idx += 256) {
-    const int r = idx >> 5, c = idx & 31;      // r is warp-uniform, c == lane
-    const int i = rt * 32 + r, k = ct * 32 + c;
-    float hv[4] = {0.f, 0.f, 0.f, 0.f};
-    if (snap && i < n && k < n) {
-      // diffrax.backward_hermite_coefficients per element: a = y_i, b = previous secant (first piece: own secant),
-      // c = 2 (m - b) / dt, d = -(m - b) / dt^2
-      const float* Ab = snap + ((size_t)b * (Tm1 + 1) * n + i) * (size_t)n + k;
-      const size_t knot = (size_t)n * n;
-      const float y0 = __ldg(Ab + (size_t)iv * knot), y1 = __ldg(Ab + (size_t)(iv + 1) * knot);
-      const float m = (y1 - y0) / dt;
-      const float bb = iv > 0 ? (y0 - __ldg(Ab + (size_t)(iv - 1) * knot)) / dtp : m;
-      hv[0] = y0;
-      hv[1] = bb;
-      hv[2] = 2.0f * (m - bb) / dt;
-      hv[3] = -(m - bb) / (dt * dt);
+  for (int rt = 0; rt < nt; ++rt) {
+    const size_t tile_base = slab * 4 * (size_t)npad * npad + ((size_t)rt * nt + ct) * 4096;
+    if (tiled_in) {
+      for (int idx = threadIdx.x; idx < 1024; idx += 256)
+        *reinterpret_cast<float4*>(&tile[4 * idx]) = *reinterpret_cast<const float4*>(tiled_in + tile_base + 4 * idx);
+      __syncthreads();
     }
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      float v = 0.f;
-      const int to = (int)peg_tile_off(r, c, p, 1);   // offset inside the tile
-      if (i < n && k < n) {
-        if (tiled_in) {
-          v = tile[to];
-        } else if (snap) {
-          v = hv[p];
-        } else {
-          const float2 tv = __ldg(reinterpret_cast<const float2*>(src[p]) + (in_slab * n + i) * (size_t)n + k);
-          v = tv.y;
-          if (p > 0) tsum[p - 1] += tv.x;
-        }
-        if (i == k) diag[(slab * 4 + p) * n + i] = v;
+    for (int idx = threadIdx.x; idx < 1024; idx += 256) {
+      const int r = idx >> 5, c = idx & 31;      // r is warp-uniform, c == lane
+      const int i = rt * 32 + r, k = ct * 32 + c;
+      float hv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (snap && i < n && k < n) {
+        // diffrax.backward_hermite_coefficients per element: a = y_i, b = previous secant (first piece: own secant),
+        // c = 2 (m - b) / dt, d = -(m - b) / dt^2
+        const float* Ab = snap + ((size_t)b * (Tm1 + 1) * n + i) * (size_t)n + k;
+        const size_t knot = (size_t)n * n;
+        const float y0 = __ldg(Ab + (size_t)iv * knot), y1 = __ldg(Ab + (size_t)(iv + 1) * knot);
+        const float m = (y1 - y0) / dt;
+        const float bb = iv > 0 ? (y0 - __ldg(Ab + (size_t)(iv - 1) * knot)) / dtp : m;
+        hv[0] = y0;
+        hv[1] = bb;
+        hv[2] = 2.0f * (m - bb) / dt;
+        hv[3] = -(m - bb) / (dt * dt);
       }
-      if (!tiled_in) tile[to] = v;
-    }
-  }
-  if (!tiled_in) {
 #pragma unroll
-    for (int p = 0; p < 3; ++p) atomicAdd(&tcol[p][lane], tsum[p]);
+      for (int p = 0; p < 4; ++p) {
+        float v = 0.f;
+        const int to = (int)peg_tile_off(r, c, p, 1);   // offset inside the tile
+        if (i < n && k < n) {
+          if (tiled_in) {
+            v = tile[to];
+          } else if (snap) {
+            v = hv[p];
+          } else {
+            const float2 tv = __ldg(reinterpret_cast<const float2*>(src[p]) + (in_slab * n + i) * (size_t)n + k);
+            v = tv.y;
+            if (p > 0) tsum[p - 1] += tv.x;
+          }
+          if (i == k) diag[(slab * 4 + p) * n + i] = v;
+        }
+        if (!tiled_in) tile[to] = v;
+      }
+    }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < 1024; idx += 256)
-      *reinterpret_cast<float4*>(adj_coef + tile_base + 4 * idx) = *reinterpret_cast<const float4*>(&tile[4 * idx]);
-    if (!snap && threadIdx.x < 96) {   // tch[b,iv,p,k] = mean over rows of the time channel (accumulated over the row tiles)
+    if (!tiled_in) {
+      for (int idx = threadIdx.x; idx < 1024; idx += 256)
+        *reinterpret_cast<float4*>(adj_coef + tile_base + 4 * idx) = *reinterpret_cast<const float4*>(&tile[4 * idx]);
+    }
+    __syncthreads();
+  }
+  if (!tiled_in && !snap) {   // tch[b,iv,p,k] = mean over all rows of the time channel
+#pragma unroll
+    for (int p = 0; p < 3; ++p) tcol[warp][p][lane] = tsum[p];
+    __syncthreads();
+    if (threadIdx.x < 96) {
       const int p = threadIdx.x >> 5, k = ct * 32 + lane;
-      if (k < n) atomicAdd(&tch[(slab * 3 + p) * n + k], tcol[p][lane] / (float)n);
+      float t = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) t += tcol[w8][p][lane];
+      if (k < n) tch[(slab * 3 + p) * n + k] = t / (float)n;
     }
   }
 }
@@ -469,11 +478,8 @@ __global__ void __launch_bounds__(256) k_norm_linear(const float* __restrict__ Z
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (oc + j >= dout) continue;
-          const float v0 = acc[4 * hh][j], v1 = acc[4 * hh + 1][j], v2 = acc[4 * hh + 2][j], v3 = acc[4 * hh + 3][j];
-          const float h0 = tf32_round(v0), h1 = tf32_round(v1), h2 = tf32_round(v2), h3 = tf32_round(v3);
           const size_t o = ((size_t)b * dout + oc + j) * po.npad + nodeq;
-          *reinterpret_cast<float4*>(po.Thi + o) = make_float4(h0, h1, h2, h3);
-          *reinterpret_cast<float4*>(po.Tlo + o) = make_float4(v0 - h0, v1 - h1, v2 - h2, v3 - h3);
+          store_vt4(po, o, acc[4 * hh][j], acc[4 * hh + 1][j], acc[4 * hh + 2][j], acc[4 * hh + 3][j]);
         }
       }
     }
@@ -1053,10 +1059,8 @@ __global__ void __launch_bounds__(256) k_linear_bwd(const float* __restrict__ Mb
         if (c >= din) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float h0 = tf32_round(acc[r][0][j]), h1 = tf32_round(acc[r][1][j]), h2 = tf32_round(acc[r][2][j]), h3 = tf32_round(acc[r][3][j]);
           const size_t o = ((size_t)b * din + c + j) * po.npad + nodeq;
-          *reinterpret_cast<float4*>(po.Thi + o) = make_float4(h0, h1, h2, h3);
-          *reinterpret_cast<float4*>(po.Tlo + o) = make_float4(acc[r][0][j] - h0, acc[r][1][j] - h1, acc[r][2][j] - h2, acc[r][3][j] - h3);
+          store_vt4(po, o, acc[r][0][j], acc[r][1][j], acc[r][2][j], acc[r][3][j]);
         }
       }
     }

@@ -26,130 +26,18 @@
 #include <cstring>
 
 #include "peg_tc.cuh"
+#include "peg_tc_ptx.cuh"
 
 namespace peg {
-
-// ------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t"
-      "}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-
-__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// streaming 128-bit plane loads.  Measured on B200 (n=2048, d=128, B=9, forward launch): ld.global.cg 137.6 us, ld.global.nc 139.6,
-// ld.global.nc.L1::no_allocate 156.1, ld.global.cs 159.8, ...no_allocate.L2::256B 156.7 -- the adjoint is insensitive (217 us)
-#ifndef PEG_LDG_VARIANT
-#define PEG_LDG_VARIANT 2
-#endif
-__device__ __forceinline__ float4 ldg_stream(const float* p) {
-  float4 r;
-#if PEG_LDG_VARIANT == 0
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-#elif PEG_LDG_VARIANT == 1
-  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-#elif PEG_LDG_VARIANT == 2
-  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-#elif PEG_LDG_VARIANT == 3
-  asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-#elif PEG_LDG_VARIANT == 4
-  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-#endif
-  return r;
-}
-
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart)
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
 
 // ------------------------------------------------------------------------------------------
 // V [B,n,d] -> V^T split into tf32 hi / lo, [B][d][npad] (zero padded): the K-major B operand
 // grid (npad/32, ceil(d/32), B), block (32, 8)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_split_transpose(const float* __restrict__ V, int n, int d, int npad,
-                                                         float* __restrict__ Thi, float* __restrict__ Tlo) {
+                                                         float* __restrict__ Thi, float* __restrict__ Tlo, int t16) {
+  ProducerOut po;
+  po.Thi = Thi; po.Tlo = Tlo; po.t16 = t16;
   __shared__ float tile[32][33];
   const int b = blockIdx.z, i0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const float* Vb = V + (size_t)b * n * d;
@@ -161,11 +49,7 @@ __global__ void __launch_bounds__(256) k_split_transpose(const float* __restrict
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int c = c0 + r, i = i0 + threadIdx.x;
     if (c < d) {
-      const float v = tile[threadIdx.x][r];
-      const float hi = tf32_rna(v);
-      const size_t o = ((size_t)b * d + c) * npad + i;
-      Thi[o] = hi;
-      Tlo[o] = v - hi;
+      store_vt(po, ((size_t)b * d + c) * npad + i, tile[threadIdx.x][r]);
     }
   }
 }
@@ -205,8 +89,14 @@ struct TcParams {
   int ksplit;    // K slices per row block in mode 1 (blockIdx.x = row block * ksplit + slice)
   int pairs_per_slice;
   float* partial; // [B][accumulators][n][d] fp32, zeroed by the host before mode 1
-  int experiment; // timing experiments only (PEG_TC_EXPERIMENT): 1 = B operand loaded for the first pairs only, 2 = no MMAs
+  int experiment; // timing experiments, compiled in only with -DPEG_TC_EXPERIMENTS (never in the shipped library):
+                  // 1 = B operand loaded for the first pairs only, 2 = no MMAs.  Always 0 otherwise.
 };
+#ifdef PEG_TC_EXPERIMENTS
+#define PEG_EXPERIMENT(p, k) ((p).experiment == (k))
+#else
+#define PEG_EXPERIMENT(p, k) false
+#endif
 
 // Per item type of the LIGHT adjoint: the operand pair is (combined = cA A_s + cD A'_s, 3xTF32: it carries the state cotangent)
 // and (sep = A'_s or A_s, ONE tf32 pass: it only feeds two scalar Frobenius gradients).  <sep V, M> and <combined V, M> give
@@ -221,10 +111,17 @@ __device__ __forceinline__ LightCoef light_coef(float wa, float wd) {
 
 // KIND 0 = forward, 1 = adjoint with four 3xTF32 products (default), 2 = LIGHT adjoint (two 3xTF32 products + two single-pass
 // ones; PEG_TC_ADJ_LIGHT=1, looser tolerance on the param1 / param2 gradients: 2.5e-3 instead of 1e-3)
-template <int KIND>
+// FMT 0 = 3xTF32 operands (fp32 words, SWIZZLE_128B tiles, kind::tf32: error ~2^-22 per product);
+// FMT 1 = bf16x2 operands (x = hi + lo, both bf16; hi*hi + lo*hi + hi*lo on kind::f16 at twice the tf32 rate and half the
+//         shared-memory traffic; SWIZZLE_64B tiles of 8 KB; error ~2^-17 per product, fp32 accumulate in TMEM)
+template <int KIND, int FMT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const TcParams p) {
   constexpr bool BWD = KIND != 0, LIGHT = KIND == 2;
+  constexpr bool F16 = FMT == 1;
+  static_assert(!(F16 && LIGHT), "the LIGHT adjoint exists for the tf32 operand format only");
+  constexpr int ATILE = F16 ? TC_BM * TC_BK * 2 : TC_ATILE;   // one A-operand tile (hi or lo part)
+  constexpr int ESZ = F16 ? 2 : 4;                            // operand element size
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ float fsum[8][16];    // adjoint epilogue: per-warp partials of the fusion-scalar gradients
   constexpr int NA = BWD ? 2 : 1;  // A-operand variants per item: fwd = combined X or Y; bwd = (A_s, A'_s)
@@ -239,12 +136,12 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   const int crank = C > 1 ? (int)cluster_ctarank() : 0;
   const int Ibase = (I / C) * C;
   const uint16_t cmask = (uint16_t)((1u << C) - 1u);
-  const bool split = p.nsplit == 3;
+  const bool split = F16 || p.nsplit == 3;
 
   // ---- shared memory carve-up (1024-B aligned operand tiles) ----
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int a_bytes = NA * (split ? 2 : 1) * TC_ATILE;          // [variant][hi,lo]
-  const int b_tile = nd * TC_BK * 4;
+  const int a_bytes = NA * (split ? 2 : 1) * ATILE;             // [variant][hi,lo]
+  const int b_tile = nd * TC_BK * ESZ;
   const int b_bytes = (split ? 2 : 1) * b_tile;                 // [hi,lo]
   const int SA = p.stages_a, SB = p.stages_b;
   const uint32_t b_ring = smem_base + SA * a_bytes;
@@ -365,13 +262,24 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       if ((j & 1) == 0) load_tile(4 * I + cv_u, kc, half);
       else load_tile(kc, 4 * I + cv_u, half);
     };
-    // store one 16-byte chunk (4 consecutive k of operand row r) as tf32 hi (+ lo) into the swizzled K-major tile
+    // store 4 consecutive k (k = 4 * chunk .. 4 * chunk + 3) of operand row r as hi (+ lo) parts into the swizzled K-major tile:
+    // tf32: one 16-byte chunk of a 128-byte row (SWIZZLE_128B); bf16x2: 8 bytes of a 64-byte row (SWIZZLE_64B: 16-byte chunk
+    // index ^= (row >> 1) & 3 inside 8-row x 64-byte atoms)
     auto store_chunk = [&](uint32_t hi_base, int r, int chunk, float x0, float x1, float x2, float x3, bool with_lo) {
-      const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
-      const float h0 = tf32_rna(x0), h1 = tf32_rna(x1), h2 = tf32_rna(x2), h3 = tf32_rna(x3);
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "f"(h0), "f"(h1), "f"(h2), "f"(h3) : "memory");
-      if (split && with_lo)
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + TC_ATILE + off), "f"(x0 - h0), "f"(x1 - h1), "f"(x2 - h2), "f"(x3 - h3) : "memory");
+      if constexpr (F16) {
+        const uint32_t off = (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u + (uint32_t)(((chunk >> 1) ^ ((r >> 1) & 3)) << 4) + (uint32_t)(chunk & 1) * 8u;
+        uint32_t h01, l01, h23, l23;
+        split_bf16x2(x0, x1, h01, l01);
+        split_bf16x2(x2, x3, h23, l23);
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(hi_base + off), "r"(h01), "r"(h23) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(hi_base + ATILE + off), "r"(l01), "r"(l23) : "memory");
+      } else {
+        const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+        const float h0 = tf32_rna(x0), h1 = tf32_rna(x1), h2 = tf32_rna(x2), h3 = tf32_rna(x3);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "f"(h0), "f"(h1), "f"(h2), "f"(h3) : "memory");
+        if (split && with_lo)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + ATILE + off), "f"(x0 - h0), "f"(x1 - h1), "f"(x2 - h2), "f"(x3 - h3) : "memory");
+      }
     };
     // Conversion of one item: (1) FFMA-combine the four planes (the fused cubic interpolation + fusion weights) while the
     // slot may still be busy, (2) wait for the A slot, (3) 3xTF32-split and store the operand tile, publish it,
@@ -409,7 +317,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
 #pragma unroll
       for (int v = 0; v < NA; ++v) {
         if (v == 0 || NV > 1) mbar_wait(empty_a(st, v), ph ^ 1u);   // the MMAs that read this slot's (variant's) previous contents have completed
-        const uint32_t hi_base = a_base + v * (split ? 2 : 1) * TC_ATILE;
+        const uint32_t hi_base = a_base + v * (split ? 2 : 1) * ATILE;
         const bool with_lo = !(LIGHT && v == NA - 1);   // the single-pass operand needs no correction tile
         if (!transposed) {
 #pragma unroll
@@ -441,14 +349,14 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         const int kc = kc_of(pr0 + pr);
         mbar_wait(empty_b(st), ph ^ 1u);   // every CTA of the cluster has finished reading this slot
         const uint32_t b_base = b_ring + st * b_bytes;
-        if (p.experiment == 1 && pr >= SB) { mbar_arrive(full_b(st)); continue; }   // timing experiment: stale B
+        if (PEG_EXPERIMENT(p, 1) && pr >= SB) { mbar_arrive(full_b(st)); continue; }   // timing experiment: stale B
         mbar_expect_tx(full_b(st), (uint32_t)b_bytes);
         if (C == 1) {
           tma_load_2d(b_base, &map_hi, kc * TC_BK, row0, full_b(st));
           if (split) tma_load_2d(b_base + b_tile, &map_lo, kc * TC_BK, row0, full_b(st));
         } else {
           const int rows = nd / C;                       // this CTA's slice of the B tile (box = 32 x rows)
-          const uint32_t off = (uint32_t)(crank * rows) * 128u;
+          const uint32_t off = (uint32_t)(crank * rows) * (uint32_t)(TC_BK * ESZ);
           tma_load_2d_mcast(b_base + off, &map_hi, kc * TC_BK, row0 + crank * rows, full_b(st), cmask);
           if (split) tma_load_2d_mcast(b_base + b_tile + off, &map_lo, kc * TC_BK, row0 + crank * rows, full_b(st), cmask);
         }
@@ -457,7 +365,9 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   } else {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nd >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      // instruction descriptor: fp32 accumulate, K-major A and B, N = nd, M = 128; operand format tf32 (2) or bf16 (1)
+      const uint32_t fmt = F16 ? 1u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nd >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       uint32_t started = 0u;  // bit acc set once the accumulator has been written (first MMA overwrites)
       for (int j = 0; j < items; ++j) {
         const int st = j % SA, pr = j >> 1, sb = pr % SB;
@@ -476,16 +386,29 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
           // LIGHT: 0 / 2 = combined operand, 1 / 3 = the single-pass sep operand of the direct / transposed items)
           const int acc = BWD ? (type * 2 + v) : 0;
           const uint32_t tacc = tmem_base + (uint32_t)(acc * nd);
-          const uint32_t ahi = a_base + v * (split ? 2 : 1) * TC_ATILE, alo = ahi + TC_ATILE;
+          const uint32_t ahi = a_base + v * (split ? 2 : 1) * ATILE, alo = ahi + ATILE;
+          if constexpr (F16) {
+            // one MMA consumes K = 16 bf16 = 32 bytes of every operand row: two K steps per 32-wide chunk, three products each
 #pragma unroll
-          for (int k8 = 0; k8 < TC_BK / 8 && !(p.experiment == 2 && j >= 2); ++k8) {
-            const uint64_t dah = make_desc_sw128(ahi + k8 * 32), dbh = make_desc_sw128(b_base + k8 * 32);
-            umma_tf32(tacc, dah, dbh, idesc, (started >> acc) & 1u);
-            started |= 1u << acc;
-            if (split && !(LIGHT && v == NA - 1)) {
-              const uint64_t dal = make_desc_sw128(alo + k8 * 32), dbl = make_desc_sw128(b_base + b_tile + k8 * 32);
-              umma_tf32(tacc, dal, dbh, idesc, 1u);
-              umma_tf32(tacc, dah, dbl, idesc, 1u);
+            for (int k16 = 0; k16 < TC_BK / 16 && !(PEG_EXPERIMENT(p, 2) && j >= 2); ++k16) {
+              const uint64_t dah = make_desc_sw64(ahi + k16 * 32), dbh = make_desc_sw64(b_base + k16 * 32);
+              const uint64_t dal = make_desc_sw64(alo + k16 * 32), dbl = make_desc_sw64(b_base + b_tile + k16 * 32);
+              umma_bf16(tacc, dah, dbh, idesc, (started >> acc) & 1u);
+              started |= 1u << acc;
+              umma_bf16(tacc, dal, dbh, idesc, 1u);
+              umma_bf16(tacc, dah, dbl, idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int k8 = 0; k8 < TC_BK / 8 && !(PEG_EXPERIMENT(p, 2) && j >= 2); ++k8) {
+              const uint64_t dah = make_desc_sw128(ahi + k8 * 32), dbh = make_desc_sw128(b_base + k8 * 32);
+              umma_tf32(tacc, dah, dbh, idesc, (started >> acc) & 1u);
+              started |= 1u << acc;
+              if (split && !(LIGHT && v == NA - 1)) {
+                const uint64_t dal = make_desc_sw128(alo + k8 * 32), dbl = make_desc_sw128(b_base + b_tile + k8 * 32);
+                umma_tf32(tacc, dal, dbh, idesc, 1u);
+                umma_tf32(tacc, dah, dbl, idesc, 1u);
+              }
             }
           }
           if (NV > 1 || v == NA - 1) umma_commit(empty_a(st, v));   // frees this A slot (variant) once the MMAs above have read it
@@ -692,13 +615,15 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// Environment knobs, parsed once per API call (tc_refresh_env from make_ctx) instead of per kernel launch: a getenv walks
-// the whole environment, and a solve enqueues thousands of launches.
+// Tuning knobs from the environment (PEG_TC_*): schedule shapes only -- none of them changes what is computed or how
+// accurately (accuracy modes are PegDims.flags).  They are parsed once per API call (tc_refresh_env from make_ctx; a getenv
+// walks the whole environment and a solve enqueues thousands of launches) into a PER-THREAD snapshot: API calls on different
+// threads never share or overwrite each other's copy.
 struct TcEnv {
   int nd_max = 0, stages_a = 0, stages_b = 0, cluster = 0, experiment = 0, split_max = 0, split_minpairs = 0;
-  bool no_splitk = false, no_linear = false, adj_light = false;
+  bool no_splitk = false, no_linear = false;
 };
-static TcEnv g_env;
+static thread_local TcEnv g_env;
 static int env_int(const char* name) { const char* ev = getenv(name); return ev ? atoi(ev) : 0; }
 void tc_refresh_env() {
   TcEnv e;
@@ -706,15 +631,13 @@ void tc_refresh_env() {
   e.stages_a = env_int("PEG_TC_STAGES_A");
   e.stages_b = env_int("PEG_TC_STAGES_B");
   e.cluster = env_int("PEG_TC_CLUSTER");
+#ifdef PEG_TC_EXPERIMENTS
   e.experiment = env_int("PEG_TC_EXPERIMENT");
+#endif
   e.split_max = env_int("PEG_TC_SPLIT_MAX");
   e.split_minpairs = env_int("PEG_TC_SPLIT_MINPAIRS");
   e.no_splitk = getenv("PEG_TC_NO_SPLITK") != nullptr;
   e.no_linear = getenv("PEG_TC_NO_LINEAR") != nullptr;
-  // LIGHT adjoint (two of the four products single-pass): measured on B200 at n=2048, d=128, B=9 the adjoint launch goes
-  // 213 -> 199 us (+5 % solver steps/s) but the param1/param2 gradients of a whole solve are off by up to 2.5e-3 (the rounding
-  // of the slowly varying planes is correlated across launches, it does not average out) -> opt-in only, never the default
-  e.adj_light = getenv("PEG_TC_ADJ_LIGHT") != nullptr;
   g_env = e;
 }
 
@@ -728,10 +651,10 @@ void tc_refresh_env() {
 // SWIZZLE_128B.  They depend only on (buffers, shape, box): a small per-thread cache keeps the driver call off the
 // hot path.  The returned pointers stay valid until 16 further distinct maps have been requested on this thread.
 static int get_maps(const float* hi, const float* lo, uint64_t cols, uint64_t rows, int box_rows, const CUtensorMap** mhi,
-                    const CUtensorMap** mlo) {
+                    const CUtensorMap** mlo, int fmt16 = 0) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return PEG_ERR_UNSUPPORTED;
-  struct MapKey { const void* hi; const void* lo; uint64_t rows, cols; int box; };
+  struct MapKey { const void* hi; const void* lo; uint64_t rows, cols; int box; int fmt16; };
   struct MapEntry { MapKey k; CUtensorMap mhi, mlo; bool valid; };
   constexpr int NC = 16;
   static thread_local MapEntry cache[NC];
@@ -739,25 +662,25 @@ static int get_maps(const float* hi, const float* lo, uint64_t cols, uint64_t ro
   MapEntry* ent = nullptr;
   for (int i = 0; i < NC; ++i)
     if (cache[i].valid && cache[i].k.hi == hi && cache[i].k.lo == lo && cache[i].k.rows == rows && cache[i].k.cols == cols &&
-        cache[i].k.box == box_rows) { ent = &cache[i]; break; }
+        cache[i].k.box == box_rows && cache[i].k.fmt16 == fmt16) { ent = &cache[i]; break; }
   if (!ent) {
     ent = &cache[cache_next];
     cache_next = (cache_next + 1) % NC;
     ent->valid = false;
     const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t gstr[1] = {(cuuint64_t)cols * 4};
+    const cuuint64_t gstr[1] = {(cuuint64_t)cols * (fmt16 ? 2 : 4)};   // bf16x2 operands: packed bf16, 64-byte box rows, SWIZZLE_64B
     const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     for (int which = 0; which < 2; ++which) {
-      if (enc(which ? &ent->mlo : &ent->mhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)(which ? lo : hi), gdim, gstr, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      if (enc(which ? &ent->mlo : &ent->mhi, fmt16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)(which ? lo : hi), gdim, gstr, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, fmt16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
         fprintf(stderr, "pegncde: cuTensorMapEncodeTiled failed: dims %llu x %llu, box 32 x %d\n", (unsigned long long)cols,
                 (unsigned long long)rows, box_rows);
         return PEG_ERR_CUDA;
       }
     }
-    ent->k = MapKey{hi, lo, rows, cols, box_rows};
+    ent->k = MapKey{hi, lo, rows, cols, box_rows, fmt16};
     ent->valid = true;
   }
   *mhi = &ent->mhi;
@@ -805,6 +728,10 @@ void tc_carve(Bump& bp, const PegDims& d, int dmax, TcWs& w) {
   w.partial = bp.take<float>((size_t)d.B * 4 * d.n * dmax);   // split-K accumulators (small grids only)
 }
 
+// operand format of the n x n x d contraction: bf16x2 unless the caller asks for 3xTF32 operands (PEG_FLAG_TF32X3) or for one of
+// the tf32-only accuracy modes
+bool tc_fmt16(int flags) { return (flags & (PEG_FLAG_TF32X3 | PEG_FLAG_TF32_FAST | PEG_FLAG_ADJ_LIGHT)) == 0; }
+
 bool tc_supported(const PegDims& d, int dcols) {
   if (d.n < 128) return false;
   if (dcols % 32 != 0) return false;
@@ -824,9 +751,10 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   const int n = a.n, d = a.d, npad = w.npad;
   if (!w.Vt_hi || !w.Vt_lo) return PEG_ERR_WORKSPACE;
   if (!get_encode()) return PEG_ERR_UNSUPPORTED;
+  const int f16 = tc_fmt16(dm.flags) ? 1 : 0;
   if (!a.vt_ready) {
     dim3 grid(npad / 32, (d + 31) / 32, dm.B), block(32, 8);
-    k_split_transpose<<<grid, block, 0, st>>>(a.V, n, d, npad, w.Vt_hi, w.Vt_lo);
+    k_split_transpose<<<grid, block, 0, st>>>(a.V, n, d, npad, w.Vt_hi, w.Vt_lo, f16);
     if (cudaPeekAtLastError() != cudaSuccess) { set_last_cuda((int)cudaGetLastError()); fprintf(stderr, "pegncde: k_split_transpose launch failed\n"); return PEG_ERR_CUDA; }
   }
   TcParams p;
@@ -836,13 +764,17 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   p.nd = pick_nd(d, nd_max);
   p.nsplit = (dm.flags & PEG_FLAG_TF32_FAST) ? 1 : 3;
   p.nkc = npad / 32;
-  const int na = bwd ? 2 : 1, sp = p.nsplit == 3 ? 2 : 1;
-  const int a_bytes = na * sp * TC_ATILE, b_bytes = sp * p.nd * TC_BK * 4;
+  const int na = bwd ? 2 : 1, sp = (f16 || p.nsplit == 3) ? 2 : 1;
+  const int a_bytes = na * sp * (f16 ? TC_ATILE / 2 : TC_ATILE), b_bytes = sp * p.nd * TC_BK * (f16 ? 2 : 4);
   // smem rings: two B slots (one per pair in flight), the rest of ~208 KB goes to A slots (even count, at most 4)
   int sb = 2;
   int sa = ((208 * 1024 - sb * b_bytes) / a_bytes) & ~1;
   sa = sa > 4 ? 4 : sa;
   if (sa < 2) { sb = 1; sa = ((208 * 1024 - sb * b_bytes) / a_bytes) & ~1; }
+  if (f16) {   // half-size tiles: four A slots always fit, the rest goes to B slots (at most 4)
+    sb = (208 * 1024 - sa * a_bytes) / b_bytes;
+    sb = sb > 4 ? 4 : sb;
+  }
   { const int v = g_env.stages_a; if (v >= 2 && v <= sa && (v & 1) == 0) sa = v; }
   { const int v = g_env.stages_b; if (v >= 1 && (size_t)sa * a_bytes + (size_t)v * b_bytes <= 224 * 1024) sb = v; }
   if (sa < 2) return PEG_ERR_UNSUPPORTED;
@@ -854,14 +786,13 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   { const int v = g_env.cluster; if (v == 1 || v == 2 || v == 4 || v == 8) cluster = v; }
   while (cluster > 1 && (nblk < cluster || (p.nd / cluster) % 8 != 0)) cluster >>= 1;
   p.cluster = cluster;
-  p.experiment = 0;
   p.experiment = g_env.experiment;
   const int nv = PEG_TC_VARIANT_SLOTS ? na : 1;   // barrier pairs per A slot (see the kernel)
   const size_t smem = (size_t)sa * a_bytes + (size_t)sb * b_bytes + 1024 + 8 * (2 * sa * nv + 2 * sb + 2) + 64;
 
   const CUtensorMap* mhi_p = nullptr;
   const CUtensorMap* mlo_p = nullptr;
-  PEG_TC_TRY(get_maps(w.Vt_hi, w.Vt_lo, (uint64_t)npad, (uint64_t)dm.B * d, p.nd / cluster, &mhi_p, &mlo_p));
+  PEG_TC_TRY(get_maps(w.Vt_hi, w.Vt_lo, (uint64_t)npad, (uint64_t)dm.B * d, p.nd / cluster, &mhi_p, &mlo_p, f16));
   const CUtensorMap& mhi = *mhi_p;
   const CUtensorMap& mlo = *mlo_p;
 
@@ -892,12 +823,17 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
       return PEG_ERR_CUDA;
     }
   }
-  const int kind = bwd ? (g_env.adj_light ? 2 : 1) : 0;
+  // PEG_FLAG_ADJ_LIGHT (two of the four adjoint products single-pass): measured on B200 at n=2048, d=128, B=9 the adjoint launch
+  // goes 213 -> 199 us (+5 % solver steps/s) but the param1/param2 gradients of a whole solve are off by up to 2.5e-3 (the rounding
+  // of the slowly varying planes is correlated across launches, it does not average out) -> an accuracy mode the caller asks for
+  const int kind = bwd ? ((dm.flags & PEG_FLAG_ADJ_LIGHT) ? 2 : 1) : 0;   // tc_fmt16() is false whenever ADJ_LIGHT is set
   {
-    static std::atomic<unsigned> done[3] = {{0u}, {0u}, {0u}};
-    if (kind == 2) PEG_TC_TRY(optin_smem(k_tc_contract<2>, done[2]));
-    else if (kind == 1) PEG_TC_TRY(optin_smem(k_tc_contract<1>, done[1]));
-    else PEG_TC_TRY(optin_smem(k_tc_contract<0>, done[0]));
+    static std::atomic<unsigned> done[5] = {{0u}, {0u}, {0u}, {0u}, {0u}};
+    if (kind == 2) PEG_TC_TRY(optin_smem(k_tc_contract<2, 0>, done[2]));
+    else if (kind == 1 && f16) PEG_TC_TRY(optin_smem(k_tc_contract<1, 1>, done[4]));
+    else if (kind == 1) PEG_TC_TRY(optin_smem(k_tc_contract<1, 0>, done[1]));
+    else if (f16) PEG_TC_TRY(optin_smem(k_tc_contract<0, 1>, done[3]));
+    else PEG_TC_TRY(optin_smem(k_tc_contract<0, 0>, done[0]));
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -913,9 +849,9 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   auto launch = [&]() -> cudaError_t {
-    return kind == 2 ? cudaLaunchKernelEx(&cfg, k_tc_contract<2>, mhi, mlo, p)
-         : kind == 1 ? cudaLaunchKernelEx(&cfg, k_tc_contract<1>, mhi, mlo, p)
-                     : cudaLaunchKernelEx(&cfg, k_tc_contract<0>, mhi, mlo, p);
+    return kind == 2 ? cudaLaunchKernelEx(&cfg, k_tc_contract<2, 0>, mhi, mlo, p)
+         : kind == 1 ? (f16 ? cudaLaunchKernelEx(&cfg, k_tc_contract<1, 1>, mhi, mlo, p) : cudaLaunchKernelEx(&cfg, k_tc_contract<1, 0>, mhi, mlo, p))
+                     : (f16 ? cudaLaunchKernelEx(&cfg, k_tc_contract<0, 1>, mhi, mlo, p) : cudaLaunchKernelEx(&cfg, k_tc_contract<0, 0>, mhi, mlo, p));
   };
   const cudaError_t le = launch();
   if (le != cudaSuccess) {
@@ -1144,10 +1080,7 @@ k_tc_norm_linear(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
       if (p.po.Thi != nullptr && gi < p.po.npad) {   // V^T hi/lo: the 32 lanes of a warp are 32 consecutive nodes
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-          const float hi = tf32_rna(m[u]);
-          const size_t o = ((size_t)b * dout + gc + u) * p.po.npad + gi;
-          p.po.Thi[o] = hi;
-          p.po.Tlo[o] = m[u] - hi;
+          store_vt(p.po, ((size_t)b * dout + gc + u) * p.po.npad + gi, m[u]);
         }
       }
       if (p.po.cb != nullptr) {   // column sums over this warp's 32 nodes (fixed butterfly order)
@@ -1504,10 +1437,7 @@ k_tc_linear_bwd(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       if (p.po.Thi != nullptr && gi < p.po.npad) {
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-          const float hi = tf32_rna(zb[u]);
-          const size_t o = ((size_t)b * din + col + u) * p.po.npad + gi;
-          p.po.Thi[o] = hi;
-          p.po.Tlo[o] = zb[u] - hi;
+          store_vt(p.po, ((size_t)b * din + col + u) * p.po.npad + gi, zb[u]);
         }
       }
       warp_colsum16(gw, lane);

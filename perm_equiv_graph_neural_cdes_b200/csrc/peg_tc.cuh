@@ -7,8 +7,8 @@ namespace peg {
 
 // operand buffers the tensor-core path needs in the caller's workspace
 struct TcWs {
-  float* Vt_hi;  // [B][dmax][npad]  tf32-rounded V^T (K-major B operand)
-  float* Vt_lo;  // [B][dmax][npad]  residual V - tf32(V)
+  float* Vt_hi;  // [B][dmax][npad]  V^T, high part (K-major B operand): tf32-rounded fp32 words, or packed bf16 (tc_fmt16)
+  float* Vt_lo;  // [B][dmax][npad]  residual V - high part, same format
   float* partial;  // [B][4][n][dmax] split-K accumulators (grids far smaller than the GPU)
   int npad;
 };
@@ -43,6 +43,7 @@ int tc_weight_grad(cudaStream_t st, const PegDims& d, const float* Mbar, const f
 int tc_norm_linear(cudaStream_t st, const PegDims& d, const TcLinear& w, int layer, const float* Z, int din, int dout,
                    const float* nw, const float* nb, float* M, float* Nout, const ProducerOut& po);
 bool tc_supported(const PegDims& d, int dcols);
+bool tc_fmt16(int flags);   // contraction operands as bf16x2 (default) rather than 3xTF32
 int tc_contract(cudaStream_t st, const PegDims& d, const TcWs& w, const ContractArgs& a, bool bwd);
 int tc_launches_per_contract(bool bwd);
 void set_last_cuda(int err);   // records a cudaError_t for pegncde_last_cuda_error() (defined in pegncde.cu)

@@ -203,6 +203,7 @@ static ProducerOut producer_out(Ctx& c, int dcols, bool want_vt, float* cb, bool
     po.Thi = c.w.tc.Vt_hi;
     po.Tlo = c.w.tc.Vt_lo;
     po.npad = c.w.tc.npad;
+    po.t16 = tc_fmt16(c.d.flags) ? 1 : 0;
   }
   po.cb = cb;
   po.partial = c.w.colPart;
@@ -537,11 +538,8 @@ static int pack_common(peg_stream_t stream, const PegDims* dims, const float* d,
   if (count < 0) count = Tm1;
   if (piece0 < 0 || count < 1 || piece0 + count > Tm1) return PEG_ERR_BAD_DIMS;
   const int nt = dims->ldn / 32;
-  dim3 grid(nt * nt, count, dims->B);
+  dim3 grid(nt, count, dims->B);   // one block per column of tiles (fixed-order column means of the time channel)
   const bool unit_time = planar || snap;   // no time channel in the source: d(time)/dt == 1
-  if (!unit_time)   // column means of the time channel are accumulated over the row tiles: zero the pieces of this range
-    PEG_CUDA(cudaMemset2DAsync(tch_coef + (size_t)piece0 * 3 * dims->n, (size_t)Tm1 * 3 * dims->n * sizeof(float), 0,
-                               (size_t)count * 3 * dims->n * sizeof(float), dims->B, st));
   k_pack_adj<<<grid, 256, 0, st>>>(d, c, b, a, planar, snap, ts, dims->n, dims->ldn, Tm1, piece0, count, adj_coef, adj_rowsum,
                                    adj_diag, adj_total, tch_coef);
   PEG_LAUNCH_CHECK();

@@ -288,7 +288,7 @@ def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: Optional[S
         pc.materialize()
         return _diffeqsolve_adaptive(vf, wrapped, pc, t0, t1, dt0, yb, unb, controller, saveat, max_steps)
     step_ts = constant_step_table(float(t0), float(t1), float(dt0), controller.rule, max_steps)
-    out = _SolveFunction.apply(yb, vf.flat_params(), pc.x_packed, pc, dims, step_ts, bool(saveat.steps), bool(getattr(vf, "store_stages", True)))
+    out = _SolveFunction.apply(yb, vf.checked_flat_params(dims), pc.x_packed, pc, dims, step_ts, bool(saveat.steps), bool(getattr(vf, "store_stages", True)))
     S = len(step_ts) - 1
     if saveat.steps:
         ys = out.squeeze(1) if unb else out

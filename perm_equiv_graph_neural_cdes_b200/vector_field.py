@@ -14,7 +14,7 @@ import math
 import torch
 from torch import nn
 
-from ._lib import PEG_FLAG_DIRECTED, PEG_WS_VF_VJP, PegDims, check, lib
+from ._lib import PEG_FLAG_DIRECTED, PEG_FLAG_TENSOR_CORES, PEG_WS_VF_VJP, PegDims, check, lib
 from .control import CubicInterpolation, PackedControl, _stream_ptr, pack_control
 
 _WS_CACHE = {}
@@ -80,7 +80,7 @@ class _FixedFusionConvLayer(ConvLayer):
         super().__init__(input_dim, output_dim, generator)
         fus = torch.zeros(16)
         fus[0], fus[1] = c0 - 1.0, c1 - 1.0
-        self.register_buffer("fusion_const", fus)
+        self.register_buffer("fusion_const", fus, persistent=False)   # not a checkpoint key: the reference has no such leaf
 
     @property
     def conv_layer(self):
@@ -116,10 +116,14 @@ class PermEquivGraphVectorField(nn.Module):
 
     def __init__(self, input_dim: int, hidden_dim: int, output_dim: int, num_layers: int, data_embed_dim: int,
                  num_nodes: int, enc_idx: bool = False, enc_type: str = "mlp", idx_dim: int = 512, *, key=None,
-                 **kwargs):
+                 flags=None, **kwargs):
         super().__init__()
         if enc_idx:
             raise NotImplementedError("enc_idx=True is unreachable in the reference (fields commented out)")
+        if input_dim != hidden_dim:
+            # every reference config builds the field with input_dim == hidden_dim (vector_field_configs.py:62-75), and the
+            # kernels' parameter packing (pegncde_param_count) assumes it
+            raise NotImplementedError(f"the fused kernels need input_dim == hidden_dim (got {input_dim} and {hidden_dim})")
         gen = None
         if key is not None:
             gen = torch.Generator().manual_seed(int(key))
@@ -134,7 +138,9 @@ class PermEquivGraphVectorField(nn.Module):
         self.enc_idx = enc_idx
         self.hidden_dim = hidden_dim
         self.output_dim = output_dim
-        self.flags = 0
+        # tcgen05 contraction wherever the shape is a real dense contraction (n >= 128, widths multiples of 32): the library
+        # falls back per layer to the CUDA-core kernels otherwise (tc_supported).  0 selects the CUDA-core path everywhere.
+        self.flags = PEG_FLAG_TENSOR_CORES if flags is None else int(flags)
         # keep every stage's layer inputs in the forward solve so the adjoint needs no recompute (memory permitting)
         self.store_stages = True
 
@@ -186,6 +192,15 @@ class PermEquivGraphVectorField(nn.Module):
         d.e = e
         return d
 
+    def checked_flat_params(self, dims: PegDims) -> torch.Tensor:
+        """``flat_params()`` after checking its length against the library's packing for ``dims`` (a mismatch would make the
+        kernels read weights at wrong offsets)."""
+        flat = self.flat_params()
+        want = lib().pegncde_param_count(dims)
+        if flat.numel() != want:
+            raise ValueError(f"packed parameter buffer has {flat.numel()} floats, pegncde_param_count says {want}")
+        return flat
+
     # ---- the ODETerm callable ------------------------------------------------------------
     def forward(self, t, y: torch.Tensor, args) -> torch.Tensor:
         return fused_vector_field(self, t, y, args, None)
@@ -230,20 +245,23 @@ class CDEWrapperVectorField(nn.Module):
 
 
 def resolve_control(control_adj, control_data, device) -> PackedControl:
-    """Accepts the reference's ``args`` (CubicInterpolation objects) or a PackedControl; packs lazily and
-    caches the packed planes on the adjacency control object (one pre-pass per batch)."""
+    """Accepts the reference's ``args`` (CubicInterpolation objects) or a PackedControl.  The adjacency planes (the expensive
+    pre-pass) are packed once and cached on the adjacency control object; the node-signal coefficients are taken from the
+    ``control_data`` of THIS call every time (the TGB models rebuild them from their data encoder at every iteration, and a
+    trainer may pair one adjacency window with different node signals)."""
     if isinstance(control_adj, PackedControl):
-        return control_adj
-    if not isinstance(control_adj, CubicInterpolation):
+        base = control_adj
+    elif isinstance(control_adj, CubicInterpolation):
+        if control_adj._packed is None:
+            control_adj._packed = pack_control(control_adj.ts, (control_adj.d, control_adj.c, control_adj.b, control_adj.a), None, device=device)
+        base = control_adj._packed
+    else:
         raise TypeError("args must be CubicInterpolation / PackedControl objects")
-    if control_adj._packed is None:
-        xc = None
-        if control_data is not None:
-            xc = (control_data.d, control_data.c, control_data.b, control_data.a)
-        control_adj._packed = pack_control(
-            control_adj.ts, (control_adj.d, control_adj.c, control_adj.b, control_adj.a), xc, device=device
-        )
-    return control_adj._packed
+    if control_data is None:
+        return base
+    if isinstance(control_data, PackedControl):
+        raise TypeError("control_data must be a CubicInterpolation (a PackedControl already carries its node-signal part)")
+    return base.with_x((control_data.d, control_data.c, control_data.b, control_data.a))
 
 
 class _VFFunction(torch.autograd.Function):
@@ -287,5 +305,5 @@ def fused_vector_field(vf: PermEquivGraphVectorField, t, y: torch.Tensor, contro
     yb = y.unsqueeze(0) if unb else y
     if yb.shape[0] != pc.B:
         raise ValueError(f"state batch {yb.shape[0]} != control batch {pc.B}")
-    out = _VFFunction.apply(yb.to(torch.float32), vf.flat_params(), vf, pc, dims, t)
+    out = _VFFunction.apply(yb.to(torch.float32), vf.checked_flat_params(dims), vf, pc, dims, t)
     return out.squeeze(0) if unb else out

@@ -13,7 +13,7 @@ GOLDEN_CASES = {
 }
 
 
-def device_model(p, device, flags=0):
+def device_model(p, device, flags=None):
     """(vf, wrapped_vf_or_vf, control objects) of the product API for an oracle Problem."""
     import perm_equiv_graph_neural_cdes_b200 as P
 
@@ -21,7 +21,8 @@ def device_model(p, device, flags=0):
     vf = P.PermEquivGraphVectorField(p.h, p.h, widths[-1], p.L, p.e, p.n, key=0)
     vf.load_oracle_layers([lp.tensors() for lp in p.layers])
     vf = vf.to(device)
-    vf.flags = flags
+    if flags is not None:   # None = the product default (tcgen05 wherever the shape allows it)
+        vf.flags = flags
     ts = p.ts.to(torch.float32)
     cadj = P.CubicInterpolation(ts.to(device), tuple(c.to(torch.float32).to(device) for c in p.coeffs_adj))
     cx = None

@@ -85,7 +85,7 @@ def test_vector_field_forward_and_vjp(cuda, case):
                 assert rel_err(g, r.grad) < 2e-4, (case, t, l, name)
 
 
-@pytest.mark.parametrize("flags", [0, _lib.PEG_FLAG_TENSOR_CORES], ids=["ffma", "tcgen05"])
+@pytest.mark.parametrize("flags", [0, _lib.PEG_FLAG_TENSOR_CORES, _lib.PEG_FLAG_TENSOR_CORES | _lib.PEG_FLAG_TF32X3], ids=["ffma", "tcgen05", "tcgen05-tf32x3"])
 @pytest.mark.parametrize("case", list(GOLDEN_CASES))
 def test_solve_against_goldens(cuda, case, flags):
     g = np.load(os.path.join(GOLD, f"{case}.npz"))
@@ -102,15 +102,21 @@ def test_solve_against_goldens(cuda, case, flags):
     slack = 4.0 * float(g["rel32"])  # the reference's own fp32 rounding noise on this problem
     assert rel_err(yT.detach(), g["yT64"]) < TOL_Y + slack, case
     (yT * p.gyT.to(cuda)).sum().backward()
-    # gradient tolerance: 1e-3 on well-conditioned problems.  sir_like is the deliberately stiff case (knots inside
-    # every step, |dyT/dy0| ~ 150): in the fp64 ORACLE ITSELF a 1e-6 relative perturbation of y0 moves the exact
-    # gradient by 3e-3 (y0) / 5e-2 (parameters) because ReLU masks flip (see DESIGN.md "conditioning"), so an fp32
-    # solve gradient cannot be compared pointwise there; that case checks the forward, finiteness and the
-    # per-evaluation VJPs (test_vector_field_forward_and_vjp[sir_like], 1e-6) instead.
+    # gradient tolerance: 1e-3 per leaf (max-norm) on well-conditioned problems.  sir_like is the deliberately stiff case (knots
+    # inside every step, |dyT/dy0| ~ 150).  Its exact gradient is piecewise smooth: the fp32 ORACLE reproduces the fp64 one to
+    # 2.5e-5 (relative L2, y0 and parameters alike), but a 1e-6 relative perturbation of y0 flips ReLU masks and moves the fp64
+    # oracle's own gradient by 3.9e-3 (y0) / 4.1e-3 (parameters) -- measured with oracle/reference_path.py, see DESIGN.md
+    # "conditioning".  Two fp32 implementations with different rounding may sit on different sides of such a kink, so the bound
+    # is a small multiple of that measured kink size: relative L2 <= 2e-2 for y0 AND for the flat parameter gradient (the
+    # per-evaluation VJPs of this case are checked to 5e-5 in test_vector_field_forward_and_vjp[sir_like]).
     if float(g["cond"]) >= 50:
         assert torch.isfinite(y0.grad).all()
         rel_l2 = float((y0.grad.cpu().double() - torch.from_numpy(g["gy0_64"])).norm() / torch.from_numpy(g["gy0_64"]).norm())
-        assert rel_l2 < 0.25, rel_l2
+        flat = torch.cat([t.reshape(-1) for layer in product_grads_as_oracle(vf) for t in layer]).cpu().double()
+        ref = torch.from_numpy(g["gparams64"])
+        rel_l2_p = float((flat - ref).norm() / ref.norm())
+        print(f"\n[{case}] stiff-case gradient error, relative L2: y0 {rel_l2:.2e}, parameters {rel_l2_p:.2e}")
+        assert rel_l2 < 2e-2 and rel_l2_p < 2e-2, (rel_l2, rel_l2_p)
         return
     tol_g = TOL_G
     assert rel_err(y0.grad, g["gy0_64"]) < tol_g, case
@@ -250,9 +256,10 @@ def test_permutation_equivariance_at_twitter_size(cuda, n, h, e):
 
 TC = _lib.PEG_FLAG_TENSOR_CORES
 FAST = _lib.PEG_FLAG_TENSOR_CORES | _lib.PEG_FLAG_TF32_FAST
+X3 = _lib.PEG_FLAG_TENSOR_CORES | _lib.PEG_FLAG_TF32X3
 
 
-@pytest.mark.parametrize("flags", [0, TC], ids=["ffma", "tcgen05"])
+@pytest.mark.parametrize("flags", [0, TC, X3], ids=["ffma", "tcgen05", "tcgen05-tf32x3"])
 @pytest.mark.parametrize("n,h,e,L", [(1000, 64, 16, 3), (1000, 64, 0, 3), (515, 32, 0, 2), (300, 32, 3, 2), (129, 64, 8, 3)])
 def test_vector_field_and_vjp_at_twitter_size_against_oracle(cuda, n, h, e, L, flags):
     """One evaluation + VJP at C4 (Twitter) size against the fp64 oracle (a single evaluation is cheap on CPU).
@@ -669,6 +676,7 @@ def _refsrc_flag_cases():
         out.append(pytest.param(name, 0, id=f"{name}-ffma"))
         if kw["n"] >= 128:
             out.append(pytest.param(name, TC, id=f"{name}-tcgen05"))
+            out.append(pytest.param(name, X3, id=f"{name}-tcgen05-tf32x3"))
     return out
 
 
@@ -759,3 +767,123 @@ def test_models_against_reference_source_fixtures(cuda, name):
         # adaptive: PIDController(rtol=1e-3).  The fp64 fixture accepts 8 steps, an fp32 solve 9 (the CPU oracle in fp32 does the
         # same), and two accepted-step sequences differ by the controller tolerance: 1e-3 in fp32 on the CPU; bound 5e-3
         assert rel_err(out, g["out"]) < 5e-3
+
+
+# ---------------------------------------------------------------------------------------------------
+# The kernel instantiations bench.py measures (BASELINE.json configs[4]: n >= 1k, h = 128 / 256, batched graphs; configs[3]-style
+# wide last layer) against the fp64 oracle: every graph of the batch has its own control path, parameter gradients are
+# summed over the batch.  Both operand formats of the tcgen05 contraction are checked against the SAME tolerances:
+# default = bf16x2 split, PEG_FLAG_TF32X3 = 3xTF32 split.
+# ---------------------------------------------------------------------------------------------------
+def _batched_problems(n, h, e, L, T, t1, dt0, seeds):
+    ps = [R.make_problem(n=n, h=h, e=e, L=L, T=T, t1=t1, dt0=dt0, seed=s) for s in seeds]
+    for p in ps[1:]:
+        p.layers = ps[0].layers          # one parameter set for the whole batch (the reference's jax.vmap(model))
+    return ps
+
+
+def _batched_device_args(ps, cuda):
+    ts = ps[0].ts.to(torch.float32).to(cuda)
+    cadj = P.CubicInterpolation(ts, tuple(torch.stack([p.coeffs_adj[i] for p in ps]).to(cuda) for i in range(4)))
+    if ps[0].e == 0:
+        return cadj
+    return [cadj, P.CubicInterpolation(ts, tuple(torch.stack([p.x_coeffs[i] for p in ps]).to(cuda) for i in range(4)))]
+
+
+@pytest.mark.parametrize("flags", [TC, X3], ids=["bf16x2", "tf32x3"])
+@pytest.mark.parametrize("n,h,e,B", [(2048, 128, 0, 3), (2048, 256, 0, 2), (1024, 128, 8, 2)], ids=["n2048_h128_B3", "n2048_h256_B2", "n1024_h128_e8_B2"])
+def test_benchmarked_instantiations_one_evaluation_and_vjp(cuda, n, h, e, B, flags):
+    ps = _batched_problems(n, h, e, 3, 3, 2, 0.5, seeds=[31 + i for i in range(B)])
+    vf, term, _ = device_model(ps[0], cuda, flags=flags)
+    args = _batched_device_args(ps, cuda)
+    t = 1.3
+    y = torch.stack([p.y0 for p in ps]).to(cuda).requires_grad_(True)
+    dy = term(t, y, args)
+    (dy * torch.stack([p.gyT for p in ps]).to(cuda)).sum().backward()
+    got = product_grads_as_oracle(vf)
+    layers = R.params_to(R.params_to(ps[0].layers, torch.float64), requires_grad=True)
+    for b, p in enumerate(ps):
+        p64 = R.problem_to(p, torch.float64)
+        q = R.Problem(p64.n, p64.h, p64.e, p64.L, p64.ts, p64.coeffs_adj, p64.x_coeffs, p64.y0, layers, p64.step_ts, p64.gyT)
+        y64 = p64.y0.clone().requires_grad_(True)
+        ref = _vf_oracle(q, t, y64)
+        (ref * p64.gyT).sum().backward()       # parameter gradients accumulate over the batch in `layers`
+        assert rel_err(dy[b].detach(), ref.detach()) < 2e-5, b
+        assert rel_err(y.grad[b], y64.grad) < 5e-5, b
+    for l, (g_l, lp) in enumerate(zip(got, layers)):
+        for name, g, r in zip(("fusion", "W", "b", "nw", "nb"), g_l, lp.tensors()):
+            assert rel_err(g, r.grad) < 3e-4, (l, name)
+
+
+@pytest.mark.parametrize("flags", [TC, X3], ids=["bf16x2", "tf32x3"])
+def test_benchmarked_instantiation_whole_solve(cuda, flags):
+    """A 5-step forward + adjoint solve at n=1024, h=128, B=2 (two row-block waves, K = d_in = 128 in every tcgen05 kernel):
+    Z_T within 1e-4, every gradient leaf within 1e-3 of the fp64 oracle."""
+    ps = _batched_problems(1024, 128, 0, 3, 3, 2, 0.1, seeds=[41, 42])
+    t_end = 0.5
+    vf, term, _ = device_model(ps[0], cuda, flags=flags)
+    args = _batched_device_args(ps, cuda)
+    y0 = torch.stack([p.y0 for p in ps]).to(cuda).requires_grad_(True)
+    sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, t_end, 0.1, y0, args)
+    assert sol.stats["num_steps"] == 5
+    (sol.ys[-1] * torch.stack([p.gyT for p in ps]).to(cuda)).sum().backward()
+    got = product_grads_as_oracle(vf)
+    layers = R.params_to(R.params_to(ps[0].layers, torch.float64), requires_grad=True)
+    table = R.constant_step_table(0.0, t_end, 0.1)
+    for b, p in enumerate(ps):
+        p64 = R.problem_to(p, torch.float64)
+        y64 = p64.y0.clone().requires_grad_(True)
+        yT = R.solve_cde(table, p64.ts, p64.coeffs_adj, None, y64, layers, p64.h, 0)
+        (yT * p64.gyT).sum().backward()
+        assert rel_err(sol.ys[-1][b].detach(), yT.detach()) < TOL_Y, b
+        assert rel_err(y0.grad[b], y64.grad) < TOL_G, b
+    for l, (g_l, lp) in enumerate(zip(got, layers)):
+        for name, g, r in zip(("fusion", "W", "b", "nw", "nb"), g_l, lp.tensors()):
+            assert rel_err(g, r.grad) < TOL_G, (l, name)
+
+
+@pytest.mark.parametrize("flags", [TC, X3], ids=["bf16x2", "tf32x3"])
+def test_batch_of_independent_graphs_on_tensor_cores(cuda, flags):
+    """test_batch_of_independent_graphs at a tcgen05 shape (n = 300: three row blocks, ragged last one; B = 3)."""
+    ps = _batched_problems(300, 64, 2, 2, 4, 3, 0.5, seeds=[0, 1, 3])
+    vf, term, _ = device_model(ps[0], cuda, flags=flags)
+    y0 = torch.stack([p.y0 for p in ps]).to(cuda).requires_grad_(True)
+    sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 3.0, 0.5, y0, _batched_device_args(ps, cuda))
+    (sol.ys[-1] * torch.stack([p.gyT for p in ps]).to(cuda)).sum().backward()
+    batched_grad = torch.cat([t.reshape(-1) for layer in product_grads_as_oracle(vf) for t in layer])
+    acc = torch.zeros_like(batched_grad)
+    for i, p in enumerate(ps):
+        vf.zero_grad()
+        yi = p.y0.to(cuda).requires_grad_(True)
+        si = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 3.0, 0.5, yi, _batched_device_args([p], cuda))
+        assert rel_err(sol.ys[-1][i].detach(), si.ys[-1][0].detach()) < 1e-6
+        (si.ys[-1][0] * p.gyT.to(cuda)).sum().backward()
+        assert rel_err(y0.grad[i], yi.grad) < 1e-5
+        acc += torch.cat([t.reshape(-1) for layer in product_grads_as_oracle(vf) for t in layer])
+    assert rel_err(batched_grad, acc) < 1e-4
+
+
+def test_reused_adjacency_control_takes_the_node_signal_of_every_call(cuda):
+    """Two training iterations with ONE adjacency control object and different node-signal controls (what the TGB model does at
+    every step, tgb_graph_neural_cde.py:118-137): the adjacency planes are packed once, the node signal is never stale."""
+    pa = R.make_problem(n=40, h=16, e=2, L=2, T=4, t1=3, dt0=0.5, seed=2)
+    pb = R.make_problem(n=40, h=16, e=2, L=2, T=4, t1=3, dt0=0.5, seed=2, x_scale=0.9)
+    vf, term, (cadj, cxa) = device_model(pa, cuda)
+    cxb = P.CubicInterpolation(cadj.ts, tuple(c.to(cuda) for c in pb.x_coeffs))
+    outs = []
+    for cx in (cxa, cxb, cxa):
+        y0 = pa.y0.to(cuda).requires_grad_(True)
+        sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 3.0, 0.5, y0, [cadj, cx])
+        sol.ys[-1].sum().backward()
+        outs.append((sol.ys[-1].detach().clone(), y0.grad.clone()))
+    packed = cadj._packed
+    assert packed is not None and packed.e == 0                      # the cache holds the adjacency part only
+    fresh = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 3.0, 0.5, pa.y0.to(cuda),
+                          [P.CubicInterpolation(cadj.ts, (cadj.d, cadj.c, cadj.b, cadj.a)), cxb]).ys[-1]
+    assert torch.equal(outs[1][0], fresh)                             # second iteration used ITS node signal
+    assert not torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][0], outs[2][0]) and torch.equal(outs[0][1], outs[2][1])
+    assert cadj._packed is packed                                     # and the planes were not re-packed
+    # a PackedControl handed in as the adjacency control behaves the same way
+    again = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 3.0, 0.5, pa.y0.to(cuda), [packed, cxb]).ys[-1]
+    assert torch.equal(again, fresh)

@@ -193,6 +193,7 @@ def test_packed_control_select_is_a_view():
                         ("adj_total", (3, 3, 4)), ("tch_coef", (3, 3, 3, 5))):
         setattr(pc, name, torch.zeros(shape))
     pc.x_coef = None
+    pc._adj = {"colsum": None, "pending": None, "host_ts": None}
     v = pc.select(1)
     assert v.B == 1 and v.n == 5 and v.adj_coef.data_ptr() == pc.adj_coef[1].data_ptr() and v.ts.shape == (1, 4)
     assert v.dims(8, 2).B == 1
