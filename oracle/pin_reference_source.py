@@ -204,6 +204,27 @@ def _install_diffrax_standin():
     def backward_hermite_coefficients(ts, ys):
         return tuple(c.numpy() for c in R.backward_hermite_coefficients(to_t(ts), to_t(ys)))
 
+    class LinearInterpolation:
+        """diffrax.LinearInterpolation(ts, ys), restated: piecewise linear between the knot values, left-continuous lookup
+        (index = clip(searchsorted(ts, t, 'left') - 1, 0, T-2)) like CubicInterpolation."""
+
+        def __init__(self, ts, ys):
+            self.ts, self.ys = np.asarray(ts, dtype=np.float64), np.asarray(ys, dtype=np.float64)
+
+        def _piece(self, t):
+            i = int(np.clip(np.searchsorted(self.ts, float(t), side="left") - 1, 0, len(self.ts) - 2))
+            return i, (self.ys[i + 1] - self.ys[i]) / (self.ts[i + 1] - self.ts[i])
+
+        def evaluate(self, t):
+            i, slope = self._piece(t)
+            return self.ys[i] + slope * (float(t) - self.ts[i])
+
+        def derivative(self, t):
+            return self._piece(t)[1]
+
+    def linear_interpolation(ts, ys):
+        return np.asarray(ys)       # no NaNs to fill in
+
     class ODETerm:
         def __init__(self, vector_field):
             self.vector_field = vector_field
@@ -231,8 +252,12 @@ def _install_diffrax_standin():
         f = lambda t, y: torch.from_numpy(np.asarray(terms.vector_field(float(t), y.numpy(), args), dtype=np.float64))
         y0 = to_t(y0)
         if isinstance(stepsize_controller, ConstantStepSize):
-            assert saveat.ts is None and saveat.t1
             table = R.constant_step_table(float(t0), float(t1), float(dt0))
+            if saveat.ts is not None:     # evolving_out=True: dense output of every step that holds a save time
+                ys, _, _ = R.tsit5_solve_adaptive(f, y0, float(t0), float(t1), save_ts=[float(t) for t in np.asarray(saveat.ts)],
+                                                  forced_steps=table)
+                return Solution(ys.numpy(), {"num_steps": len(table) - 1})
+            assert saveat.t1
             return Solution(R.tsit5_solve_fixed(f, y0, table).numpy()[None], {"num_steps": len(table) - 1})
         assert isinstance(stepsize_controller, PIDController) and dt0 is None
         save_ts = None if saveat.ts is None else [float(t) for t in np.asarray(saveat.ts)]
@@ -242,6 +267,7 @@ def _install_diffrax_standin():
         return Solution(ys, dict(stats, table=table))
 
     for name, obj in dict(CubicInterpolation=CubicInterpolation, backward_hermite_coefficients=backward_hermite_coefficients,
+                          LinearInterpolation=LinearInterpolation, linear_interpolation=linear_interpolation,
                           ODETerm=ODETerm, Tsit5=Tsit5, ConstantStepSize=ConstantStepSize, PIDController=PIDController,
                           SaveAt=SaveAt, diffeqsolve=diffeqsolve).items():
         setattr(dfx, name, obj)
@@ -331,7 +357,26 @@ MODEL_CASES = {
     "tgb_mlp": ("tgb", dict(n=20, h=8, e=4, L=2, T=3, t1=2, dt0=0.01, seed=32), dict(use_mlps=True)),
     "tgb_linear": ("tgb", dict(n=16, h=8, e=2, L=2, T=3, t1=2, dt0=0.01, seed=33), dict(use_mlps=False)),
     "dyn": ("dyn", dict(n=30, h=8, e=0, L=2, T=8, t1=5, dt0=0.1, seed=34, float_ts=True), dict()),
+    # evolving_out=True (SaveAt(ts=ts) on the fixed-step path, pgt_graph_neural_cde.py:114-117 / tgb_graph_neural_cde.py:147-150,164-167)
+    "pgt_evolving": ("pgt", dict(n=18, h=8, e=2, L=2, T=4, t1=3, dt0=0.1, seed=35), dict(data_dim=4, feature_dim=2, evolving_out=True)),
+    "tgb_sequence": ("tgb", dict(n=14, h=8, e=2, L=2, T=3, t1=2, dt0=0.01, seed=36), dict(use_mlps=True, evolving_out=True, return_sequence=True)),
+    # interpolation="linear" (pgt_graph_neural_cde.py:101-103): the knot VALUES [T,n,n,2] / [T,n,e,2] are the "coefficients"
+    "pgt_linear": ("pgt", dict(n=18, h=8, e=2, L=2, T=4, t1=3, dt0=0.1, seed=37), dict(data_dim=4, feature_dim=1, interpolation="linear")),
 }
+
+
+def linear_knot_values(p64):
+    """Knot values of the paths whose Hermite coefficients an oracle Problem holds: ``a`` of every piece plus the end point of the
+    last piece -- the arrays a ``linear`` config hands to the model (dataset_configs.py builds them with diffrax.linear_interpolation)."""
+    import torch
+
+    def knots(coeffs, ts):
+        d, c, b, a = coeffs
+        h = (ts[-1] - ts[-2]).to(a.dtype)
+        last = a[-1] + h * (b[-1] + h * (c[-1] + h * d[-1]))
+        return torch.cat([a, last[None]], dim=0)
+
+    return knots(p64.coeffs_adj, p64.ts), knots(p64.x_coeffs, p64.ts)
 
 
 def model_inputs(name):
@@ -385,23 +430,37 @@ def main_models():
         lay = lambda ps: [(tt(W), tt(b)) for W, b in ps]
         if kind == "pgt":
             cfg = _types.SimpleNamespace(data_dim=extra["data_dim"], hidden_dim=p64.h, feature_dim=extra["feature_dim"], method="Tsit5", return_sequence=False)
-            model = mods["pgt_graph_neural_cde"].PGTGraphNeuralCDE(cfg, vf, "cubic", jr.PRNGKey(kw["seed"]))
+            interp = extra.get("interpolation", "cubic")
+            model = mods["pgt_graph_neural_cde"].PGTGraphNeuralCDE(cfg, vf, interp, jr.PRNGKey(kw["seed"]))
             ts = np.arange(kw["T"], dtype=np.int32)                                   # torch.arange in dataset_configs.py:1108
-            x_coeffs = np.stack([c.numpy() for c in p64.x_coeffs])                    # stacked [4, T-1, n, e, 2] like trainer_pgt.py:203
-            rec["out_global"] = model(ts, np.stack(coeffs_adj), x_coeffs, inp["x0"])
-            rec["out_nodes"] = model(ts, np.stack(coeffs_adj), x_coeffs, inp["x0"], global_readout=False)
+            ev = dict(evolving_out=True) if extra.get("evolving_out") else {}
+            if interp == "linear":
+                A_k, X_k = linear_knot_values(p64)
+                rec["adj_knots"], rec["x_knots"] = A_k.numpy(), X_k.numpy()
+                c_adj, x_coeffs = rec["adj_knots"], rec["x_knots"]
+                ora_adj = (torch.zeros_like(p64.coeffs_adj[0]), torch.zeros_like(p64.coeffs_adj[0]), (A_k[1:] - A_k[:-1]), A_k[:-1])   # unit knot spacing
+                ora_x = (torch.zeros_like(p64.x_coeffs[0]), torch.zeros_like(p64.x_coeffs[0]), (X_k[1:] - X_k[:-1]), X_k[:-1])
+            else:
+                c_adj = np.stack(coeffs_adj)
+                x_coeffs = np.stack([c.numpy() for c in p64.x_coeffs])                # stacked [4, T-1, n, e, 2] like trainer_pgt.py:203
+                ora_adj, ora_x = p64.coeffs_adj, p64.x_coeffs
+            rec["out_global"] = model(ts, c_adj, x_coeffs, inp["x0"], **ev)
+            rec["out_nodes"] = model(ts, c_adj, x_coeffs, inp["x0"], global_readout=False, **ev)
             enc, dec = _module_params(model.encoder), _module_params(model.decoder)
-            ora = R.pgt_graph_neural_cde(p64.ts, p64.coeffs_adj, p64.x_coeffs, tt(inp["x0"]), lay(enc), lay(dec), p64.layers, p64.h, p64.e)
+            ora = R.pgt_graph_neural_cde(p64.ts, ora_adj, ora_x, tt(inp["x0"]), lay(enc), lay(dec), p64.layers, p64.h, p64.e,
+                                         evolving_out=bool(ev))
             err = float((ora - tt(rec["out_global"])).abs().max() / tt(rec["out_global"]).abs().max())
         elif kind == "tgb":
-            cfg = _types.SimpleNamespace(hidden_dim=p64.h, use_mlps=extra["use_mlps"], method="Tsit5", return_sequence=False)
+            seq = bool(extra.get("return_sequence"))
+            cfg = _types.SimpleNamespace(hidden_dim=p64.h, use_mlps=extra["use_mlps"], method="Tsit5", return_sequence=seq)
             model = mods["tgb_graph_neural_cde"].TGBGraphNeuralCDE(cfg, vf, "cubic", jr.PRNGKey(kw["seed"]))
             ts = np.arange(kw["T"], dtype=np.int32)
-            rec["out"] = model(ts, coeffs_adj, inp["x_data"], inp["x0"], None)
+            rec["out"] = model(ts, coeffs_adj, inp["x_data"], inp["x0"], None, **(dict(evolving_out=True) if extra.get("evolving_out") else {}))
             enc, dec = _module_params(model.encoder), _module_params(model.decoder)
             rec["data_encoder_W"], rec["data_encoder_b"] = _linear_params(model.data_encoder)
             ora = R.tgb_graph_neural_cde(p64.ts, p64.coeffs_adj, tt(inp["x_data"]), tt(inp["x0"]), lay(enc), lay(dec),
-                                         (tt(rec["data_encoder_W"]), tt(rec["data_encoder_b"])), p64.layers, p64.h, p64.e)
+                                         (tt(rec["data_encoder_W"]), tt(rec["data_encoder_b"])), p64.layers, p64.h, p64.e,
+                                         evolving_out=bool(extra.get("evolving_out")), return_sequence=seq)
             err = float((ora - tt(rec["out"])).abs().max() / tt(rec["out"]).abs().max())
         else:
             cfg = _types.SimpleNamespace(hidden_dim=p64.h, method="Tsit5", return_sequence=True)

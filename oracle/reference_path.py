@@ -511,19 +511,36 @@ def mlp(x, layers):
     return x
 
 
+def solve_cde_dense(step_ts, ts, coeffs_adj, x_coeffs, y0, layers, hidden_dim, data_embed_dim, save_ts):
+    """The same call with ``SaveAt(ts=save_ts)`` (evolving_out=True, pgt_graph_neural_cde.py:114-115): fixed step table, every
+    save time sampled with Tsit5's interpolant inside the step that holds it."""
+    control_adj = CubicInterpolation(ts, coeffs_adj)
+    if x_coeffs is not None:
+        control_data = CubicInterpolation(ts, x_coeffs)
+        f = lambda t, y: cde_wrapper_vector_field(t, y, control_adj, control_data, layers, hidden_dim, data_embed_dim)
+    else:
+        f = lambda t, y: perm_equiv_vector_field(t, y, control_adj, layers)
+    ys, _, _ = tsit5_solve_adaptive(f, y0, float(step_ts[0]), float(step_ts[-1]), save_ts=[float(t) for t in save_ts], forced_steps=step_ts)
+    return ys
+
+
 def pgt_graph_neural_cde(ts, coeffs_adj, x_coeffs, x0, encoder, decoder, vf_layers, hidden_dim, data_embed_dim,
-                         global_readout=True, dt0=0.1):
+                         global_readout=True, dt0=0.1, evolving_out=False):
     """PGTGraphNeuralCDE.__call__, src/models/pgt_graph_neural_cde.py:78-136 (cubic interpolation, evolving_out=False):
     y0 = vmap(encoder)(x0); diffeqsolve(ODETerm(wrapped_vf), Tsit5, ts[0], ts[-1], dt0=0.1, ConstantStepSize, SaveAt(t1));
     vmap(decoder)(ys[-1]); sum over the nodes when ``global_readout``."""
     y0 = mlp(x0, encoder)
     step_ts = constant_step_table(float(ts[0]), float(ts[-1]), dt0)
-    y_T = solve_cde(step_ts, ts, coeffs_adj, x_coeffs, y0, vf_layers, hidden_dim, data_embed_dim)
+    if evolving_out:   # SaveAt(ts=ts); the read-out still takes ys[-1] (:131), i.e. the dense-output sample at ts[-1]
+        y_T = solve_cde_dense(step_ts, ts, coeffs_adj, x_coeffs, y0, vf_layers, hidden_dim, data_embed_dim, ts)[-1]
+    else:
+        y_T = solve_cde(step_ts, ts, coeffs_adj, x_coeffs, y0, vf_layers, hidden_dim, data_embed_dim)
     out = mlp(y_T, decoder)
     return out.sum(dim=0) if global_readout else out
 
 
-def tgb_graph_neural_cde(ts, coeffs_adj, x_data, x0, encoder, decoder, data_encoder, vf_layers, hidden_dim, data_embed_dim, dt0=0.01):
+def tgb_graph_neural_cde(ts, coeffs_adj, x_data, x0, encoder, decoder, data_encoder, vf_layers, hidden_dim, data_embed_dim, dt0=0.01,
+                         evolving_out=False, return_sequence=False):
     """TGBGraphNeuralCDE.__call__, src/models/tgb_graph_neural_cde.py:96-171 (cubic, evolving_out=False,
     return_sequence=False): the node signal is embedded by ``data_encoder`` (:118), stacked behind a time channel
     (:120-125), turned into Hermite coefficients INSIDE the model (:130) and used as the second control; dt0 = 0.01 (:143)."""
@@ -533,8 +550,11 @@ def tgb_graph_neural_cde(ts, coeffs_adj, x_data, x0, encoder, decoder, data_enco
     coeffs_data = backward_hermite_coefficients(tsf, x_path)
     y0 = mlp(x0, encoder)
     step_ts = constant_step_table(float(ts[0]), float(ts[-1]), dt0)
-    y_T = solve_cde(step_ts, ts, coeffs_adj, coeffs_data, y0, vf_layers, hidden_dim, data_embed_dim)
-    return mlp(y_T, decoder)
+    if evolving_out:
+        ys = solve_cde_dense(step_ts, ts, coeffs_adj, coeffs_data, y0, vf_layers, hidden_dim, data_embed_dim, ts)
+    else:
+        ys = solve_cde(step_ts, ts, coeffs_adj, coeffs_data, y0, vf_layers, hidden_dim, data_embed_dim)[None]
+    return mlp(ys if return_sequence else ys[-1], decoder)      # :164-169
 
 
 def graph_neural_cde(ts, coeffs_adj, x0, initial_linear, final_linear, vf_layers, rtol=1e-3, atol=1e-6):

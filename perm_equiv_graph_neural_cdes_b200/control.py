@@ -81,6 +81,27 @@ class CubicInterpolation:
         return self.b[i] + s * (2.0 * self.c[i] + 3.0 * s * self.d[i])
 
 
+class LinearInterpolation(CubicInterpolation):
+    """Drop-in for ``diffrax.LinearInterpolation(ts, ys)`` (``interpolation="linear"`` of the PGT / TGB models,
+    src/models/pgt_graph_neural_cde.py:101-103): ``ys`` are the knot values ``[T, n, n, 2]`` (what ``diffrax.linear_interpolation``
+    returns for data without NaNs).  A piecewise-linear path is the cubic path with ``a = y_i``, ``b = (y_{i+1} - y_i) / dt``,
+    ``c = d = 0``, so the fused kernels run it unchanged (same left-continuous piece lookup)."""
+
+    def __init__(self, ts: torch.Tensor, ys: torch.Tensor):
+        tsv = ts.to(ys.dtype)
+        batched = ys.dim() == 5 or (ys.dim() == 4 and ts.dim() == 2)
+        t_axis = 1 if batched else 0
+        dt = (tsv[..., 1:] - tsv[..., :-1])
+        shape = [1] * ys.dim()
+        shape[t_axis] = -1
+        if tsv.dim() == 2:
+            shape[0] = tsv.shape[0]
+        a = ys.narrow(t_axis, 0, ys.shape[t_axis] - 1)
+        b = (ys.narrow(t_axis, 1, ys.shape[t_axis] - 1) - a) / dt.reshape(shape)
+        z = torch.zeros_like(a)
+        super().__init__(ts, (z, z, b, a))
+
+
 class PackedControl:
     """Planar device layout of one batch of control paths (``PegControl`` in pegncde.h).
 

@@ -236,6 +236,10 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     // loads of its next item right after publishing the current one; the two groups run out of phase, so ~2 items
     // (128 KB per SM) are in flight while the other group converts.
     float4 buf[16];
+    // 16-bit operand formats, direct items: the 8-byte operand stores of one instruction must hit rows of both parities to be
+    // bank-conflict-free (rows are 64 bytes), so the lanes with sw = 1 keep the rows of their micro tile in swapped order
+    // (register row m holds tile row m ^ 1).  It costs nothing: only the load addresses and the store offsets change.
+    const int sw = (F16 && grp == 0) ? ((lane >> 3) & 1) : 0;
     // `half`: 0 = the first PEG_TC_BWD_HALF_EARLY rows m of the micro tile, 1 = the remaining rows, 2 = all four (the adjoint can
     // issue the two parts at different times)
     auto load_tile = [&](int rt, int ct, int half) {
@@ -243,11 +247,13 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       const int m0 = half == 1 ? ME : 0, m1 = half == 0 ? ME : 4;
       if (rt < nt && ct < nt) {
         const float* base = P + ((size_t)rt * nt + ct) * 4096 + cv_off;
+        const float* base_even = base + sw * 128;   // register row m <- tile row m ^ sw: even m read one row up, odd m one row down
+        const float* base_odd = base - sw * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
           for (int m = 0; m < 4; ++m)
-            if (m >= m0 && m < m1) buf[q * 4 + m] = ldg_stream(base + (q * 4 + m) * 128);
+            if (m >= m0 && m < m1) buf[q * 4 + m] = ldg_stream(((m & 1) ? base_odd : base_even) + (q * 4 + m) * 128);
       } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -336,9 +342,82 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       if (!(PEG_TC_EARLY_RELOAD && !BWD) && j + 2 < items) load_item(j + 2, half_early ? 1 : 2);
     };
 
+    // ---- 16-bit operand formats: streaming conversion ----
+    // With 8-KB tiles there are four A slots, so the slot wait rarely blocks and the conversion needs no staging array: wait for the
+    // slot, then combine -> split -> store row by row while the plane registers die (the 3xTF32 path above combines ahead of its
+    // slot wait and keeps 32 combined values live, which spills at the 96 registers 18 warps allow).
+    // Operand-tile offsets (SWIZZLE_64B): row r, 16-byte chunk c, half hf -> (r >> 3) * 512 + (r & 7) * 64 + ((c ^ ((r >> 1) & 3)) << 4)
+    // + 8 hf.  For the four rows r0 + m' (r0 multiple of 4) of one micro tile only (m' >> 1) enters the XOR: two base offsets.
+    const int r0 = 32 * cv_u + 4 * (grp == 0 ? cv_rq : cv_cq);     // first operand row of this thread (direct: tile rows, transposed: tile columns)
+    const int kq = grp == 0 ? cv_cq : cv_rq;                        // its K quad: k = 4 kq .. 4 kq + 3
+    const uint32_t o_row = (uint32_t)(r0 >> 3) * 512u + (uint32_t)(r0 & 7) * 64u + (uint32_t)(kq & 1) * 8u;
+    const uint32_t o_lo = o_row + (uint32_t)(((kq >> 1) ^ ((r0 >> 1) & 3)) << 4);          // rows r0, r0 + 1
+    const uint32_t o_hi = o_row + (uint32_t)(((kq >> 1) ^ (((r0 >> 1) & 3) + 1)) << 4);    // rows r0 + 2, r0 + 3
+    // store of row r0 + (m ^ sw) (held in register row m)
+    const uint32_t o_m[4] = {o_lo + (uint32_t)(0 ^ sw) * 64u, o_lo + (uint32_t)(1 ^ sw) * 64u, o_hi + (uint32_t)(2 ^ sw) * 64u, o_hi + (uint32_t)(3 ^ sw) * 64u};
+    auto put16 = [&](uint32_t addr, float x0, float x1, float x2, float x3) {
+      uint32_t h01, l01, h23, l23;
+      split_bf16x2(x0, x1, h01, l01);
+      split_bf16x2(x2, x3, h23, l23);
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(h01), "r"(h23) : "memory");
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr + ATILE), "r"(l01), "r"(l23) : "memory");
+    };
+    auto comb = [&](int v, float e0, float e1, float e2, float e3) -> float {
+      if (BWD && v == NA - 1) return w[v][1] * e1 + w[v][2] * e2 + w[v][3] * e3;    // A'_s has no `a` term (wD[0] == 0)
+      return w[v][0] * e0 + w[v][1] * e1 + w[v][2] * e2 + w[v][3] * e3;
+    };
+    auto convert16 = [&](int j, bool transposed) {
+      const int st = j % SA;
+      const uint32_t a_base = smem_base + st * a_bytes;
+      mbar_wait(empty_a(st, 0), ((uint32_t)(j / SA) & 1u) ^ 1u);   // the MMAs that read this slot's previous contents have completed
+      if (!transposed) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {   // operand row = tile row, the four k values are the columns 4 cq .. 4 cq + 3
+          const float4 e0 = buf[0 * 4 + m], e1 = buf[1 * 4 + m], e2 = buf[2 * 4 + m], e3 = buf[3 * 4 + m];
+#pragma unroll
+          for (int v = 0; v < NA; ++v)
+            put16(a_base + v * 2 * ATILE + o_m[m], comb(v, e0.x, e1.x, e2.x, e3.x), comb(v, e0.y, e1.y, e2.y, e3.y),
+                  comb(v, e0.z, e1.z, e2.z, e3.z), comb(v, e0.w, e1.w, e2.w, e3.w));
+        }
+      } else {
+        // operand row = tile column 4 cq + e, the four k values are the tile rows 4 rq + m: rows (0,1) and (2,3) are packed as they
+        // are combined, so only 16 packed registers per variant outlive the plane registers
+        uint32_t ph[NA][4][2], pl[NA][4][2];   // [variant][column e][row pair]
+#pragma unroll
+        for (int mp = 0; mp < 2; ++mp) {
+          const float4 a0 = buf[0 * 4 + 2 * mp], a1 = buf[1 * 4 + 2 * mp], a2 = buf[2 * 4 + 2 * mp], a3 = buf[3 * 4 + 2 * mp];
+          const float4 c0 = buf[0 * 4 + 2 * mp + 1], c1 = buf[1 * 4 + 2 * mp + 1], c2 = buf[2 * 4 + 2 * mp + 1], c3 = buf[3 * 4 + 2 * mp + 1];
+#pragma unroll
+          for (int v = 0; v < NA; ++v) {
+            split_bf16x2(comb(v, a0.x, a1.x, a2.x, a3.x), comb(v, c0.x, c1.x, c2.x, c3.x), ph[v][0][mp], pl[v][0][mp]);
+            split_bf16x2(comb(v, a0.y, a1.y, a2.y, a3.y), comb(v, c0.y, c1.y, c2.y, c3.y), ph[v][1][mp], pl[v][1][mp]);
+            split_bf16x2(comb(v, a0.z, a1.z, a2.z, a3.z), comb(v, c0.z, c1.z, c2.z, c3.z), ph[v][2][mp], pl[v][2][mp]);
+            split_bf16x2(comb(v, a0.w, a1.w, a2.w, a3.w), comb(v, c0.w, c1.w, c2.w, c3.w), ph[v][3][mp], pl[v][3][mp]);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < NA; ++v)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t addr = a_base + v * 2 * ATILE + o_m[e];
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(ph[v][e][0]), "r"(ph[v][e][1]) : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr + ATILE), "r"(pl[v][e][0]), "r"(pl[v][e][1]) : "memory");
+          }
+      }
+      fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(full_a(st, 0));
+      if (j + 2 < items) load_item(j + 2, 2);
+    };
+
     if (items > 0) load_item(grp, 2);   // group 0: direct items (even j); group 1: transposed items (odd j)
-    if (grp == 0) for (int j = 0; j < items; j += 2) convert(j, false);
-    else          for (int j = 1; j < items; j += 2) convert(j, true);
+    if constexpr (F16) {
+      static_assert(!F16 || PEG_TC_VARIANT_SLOTS == 0, "per-variant slot barriers exist for the 3xTF32 format only");
+      if (grp == 0) for (int j = 0; j < items; j += 2) convert16(j, false);
+      else          for (int j = 1; j < items; j += 2) convert16(j, true);
+    } else {
+      if (grp == 0) for (int j = 0; j < items; j += 2) convert(j, false);
+      else          for (int j = 1; j < items; j += 2) convert(j, true);
+    }
   } else if (warp == 16) {
     // =========================== TMA producer (B operand) ===========================
     if (lane == 0) {

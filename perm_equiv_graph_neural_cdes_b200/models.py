@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 from torch import nn
 
-from .control import CubicInterpolation, backward_hermite_coefficients
+from .control import CubicInterpolation, LinearInterpolation, backward_hermite_coefficients
 from .solve import ConstantStepSize, ODETerm, PIDController, SaveAt, Tsit5, diffeqsolve
 from .vector_field import CDEWrapperVectorField, Linear, PermEquivGraphVectorField
 
@@ -41,10 +41,11 @@ class PGTGraphNeuralCDE(nn.Module):
     def __init__(self, hidden_dim: int, data_dim: int, feature_dim: int, vector_field: PermEquivGraphVectorField,
                  interpolation: str = "cubic", seed: int = 0, dt0: float = 0.1):
         super().__init__()
-        if interpolation != "cubic":
-            raise NotImplementedError("the fused path implements interpolation='cubic'")
+        if interpolation not in ("cubic", "linear"):
+            raise ValueError("interpolation must be 'cubic' or 'linear' (pgt_graph_neural_cde.py:101-107)")
         g = torch.Generator().manual_seed(seed)
         self.hidden_dim = hidden_dim
+        self.interpolation = interpolation
         self.vector_field = vector_field
         self.encoder = MLP(data_dim, hidden_dim, 16, 2, g)
         self.decoder = MLP(hidden_dim, feature_dim, 16, 2, g)
@@ -54,12 +55,15 @@ class PGTGraphNeuralCDE(nn.Module):
         self.dt0 = dt0
 
     def forward(self, ts, coeffs_adj, x_coeffs, x0, evolving_out: bool = False, global_readout: bool = True):
-        control_adj = coeffs_adj if not isinstance(coeffs_adj, (tuple, list, torch.Tensor)) else CubicInterpolation(ts, coeffs_adj)
-        control_data = x_coeffs if not isinstance(x_coeffs, (tuple, list, torch.Tensor)) else CubicInterpolation(ts, x_coeffs)
+        interp = LinearInterpolation if self.interpolation == "linear" else CubicInterpolation
+        control_adj = coeffs_adj if not isinstance(coeffs_adj, (tuple, list, torch.Tensor)) else interp(ts, coeffs_adj)
+        control_data = x_coeffs if not isinstance(x_coeffs, (tuple, list, torch.Tensor)) else interp(ts, x_coeffs)
         y0 = self.encoder(x0)
-        sol = diffeqsolve(terms=ODETerm(self.wrapped_vector_field), solver=self.method, t0=float(ts.reshape(-1)[0]),
-                          t1=float(ts.reshape(-1)[-1]), dt0=self.dt0, y0=y0, args=[control_adj, control_data],
-                          stepsize_controller=self.controller, saveat=SaveAt(t1=True))
+        ts_host = ts.detach().reshape(-1).cpu()     # one host copy: t0, t1 and the save times are host scalars of the C-ABI
+        saveat = SaveAt(ts=ts_host) if evolving_out else SaveAt(t1=True)   # pgt_graph_neural_cde.py:114-117
+        sol = diffeqsolve(terms=ODETerm(self.wrapped_vector_field), solver=self.method, t0=float(ts_host[0]),
+                          t1=float(ts_host[-1]), dt0=self.dt0, y0=y0, args=[control_adj, control_data],
+                          stepsize_controller=self.controller, saveat=saveat)
         output = self.decoder(sol.ys[-1])
         if global_readout:
             return output.sum(dim=-2)
@@ -72,7 +76,7 @@ class TGBGraphNeuralCDE(nn.Module):
     The node-signal control is LEARNED: ``x_data [T, n, num_nodes]`` goes through ``data_encoder`` (Linear
     num_nodes -> data_embed_dim), is stacked with the time channel and turned into Hermite coefficients inside the model
     (``:118-137``), so reverse mode continues from the solve (``g_xcoef`` of ``pegncde_solve_bwd``) into the encoder.
-    ConstantStepSize, ``dt0 = 0.01`` (``:143``), ``SaveAt(t1=True)`` (no trainer passes ``evolving_out=True``)."""
+    ConstantStepSize, ``dt0 = 0.01`` (``:143``); ``SaveAt(t1=True)``, or ``SaveAt(ts=ts)`` with ``evolving_out=True`` (``:147-150``)."""
 
     def __init__(self, hidden_dim: int, vector_field: PermEquivGraphVectorField, use_mlps: bool = True, seed: int = 0,
                  dt0: float = 0.01, return_sequence: bool = False):
@@ -94,8 +98,6 @@ class TGBGraphNeuralCDE(nn.Module):
         return mod(x) if isinstance(mod, MLP) else torch.nn.functional.linear(x, mod.weight, mod.bias)
 
     def forward(self, ts, coeffs_adj, x_data, x0, start_time=None, evolving_out: bool = False):
-        if evolving_out:
-            raise NotImplementedError("SaveAt(ts=...) on the fixed-step path is not implemented (no reference trainer uses it)")
         x_emb = self._lin(self.data_encoder, x_data)                                  # [T, n, e]
         tsf = ts.to(x_emb.dtype)
         x_path = torch.stack([tsf[:, None, None].expand_as(x_emb), x_emb], dim=-1)      # [T, n, e, 2] (time, value)
@@ -103,9 +105,11 @@ class TGBGraphNeuralCDE(nn.Module):
         control_adj = coeffs_adj if not isinstance(coeffs_adj, (tuple, list, torch.Tensor)) else CubicInterpolation(ts, coeffs_adj)
         control_data = CubicInterpolation(ts, coeffs_data)
         y0 = self._lin(self.encoder, x0)
-        sol = diffeqsolve(terms=ODETerm(self.wrapped_vector_field), solver=self.method, t0=float(ts[0]), t1=float(ts[-1]),
+        ts_host = ts.detach().reshape(-1).cpu()
+        saveat = SaveAt(ts=ts_host) if evolving_out else SaveAt(t1=True)   # tgb_graph_neural_cde.py:147-150
+        sol = diffeqsolve(terms=ODETerm(self.wrapped_vector_field), solver=self.method, t0=float(ts_host[0]), t1=float(ts_host[-1]),
                           dt0=self.dt0, y0=y0, args=[control_adj, control_data], stepsize_controller=self.controller,
-                          saveat=SaveAt(t1=True))
+                          saveat=saveat)
         return self._lin(self.decoder, sol.ys if self.return_sequence else sol.ys[-1])
 
 

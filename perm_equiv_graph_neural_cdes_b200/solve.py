@@ -203,6 +203,89 @@ class _SolveFunction(torch.autograd.Function):
         return g_y0, g_flat, g_x, None, None, None, None, None
 
 
+def dense_samples_of_table(step_ts: np.ndarray, save_ts: np.ndarray):
+    """For every save time the step that produces it and the position inside the step, as diffrax's SaveAt(ts=...) does
+    it: a save time t is emitted by the step with ``tprev < t <= tnext`` (``t == t0`` by the first step, theta = 0).
+    -> list of (save index, step index, theta)."""
+    f = np.float32
+    out = []
+    S = len(step_ts) - 1
+    for m, t in enumerate(save_ts):
+        t = f(t)
+        if t < step_ts[0] or t > step_ts[-1]:
+            raise ValueError("SaveAt(ts=...) holds times outside [t0, t1]")
+        s = int(np.searchsorted(step_ts, t, side="left")) - 1
+        s = min(max(s, 0), S - 1)
+        h = f(step_ts[s + 1] - step_ts[s])
+        theta = f(min(max(f(t - step_ts[s]) / h, f(0.0)), f(1.0)))
+        out.append((m, s, float(theta)))
+    return out
+
+
+class _FixedDenseFunction(torch.autograd.Function):
+    """Fixed-step solve with ``SaveAt(ts=...)`` (src/models/pgt_graph_neural_cde.py:114-117, tgb_graph_neural_cde.py:147-150):
+    the forward solve keeps y at every step boundary; every step that holds a save time is re-evaluated once with
+    ``pegncde_step_fwd`` (all seven slopes) and sampled with Tsit5's interpolant (``pegncde_tsit5_dense``).  Backward = the exact
+    discrete adjoint over the step table, the samples entering as cotangents of their step's start state and stage slopes."""
+
+    @staticmethod
+    def forward(ctx, y0, flat, x_packed, pc, dims, step_ts, save_ts):
+        y0 = y0.contiguous()
+        flat = flat.contiguous()
+        l = lib()
+        dev = y0.device
+        S = len(step_ts) - 1
+        pc.materialize()
+        ws = workspace(dev, max(l.pegncde_workspace_bytes(dims, PEG_WS_SOLVE_FWD, S), l.pegncde_workspace_bytes(dims, PEG_WS_SOLVE_BWD, S),
+                                l.pegncde_workspace_bytes(dims, PEG_WS_STEP, 1)))
+        host_ts = np.ascontiguousarray(step_ts, dtype=np.float32)
+        y_ckpt = torch.empty((S + 1,) + tuple(y0.shape), dtype=torch.float32, device=dev)
+        ctl = pc.struct()
+        st = _stream_ptr(dev)
+        check(l.pegncde_solve_fwd(st, dims, ctl, flat.data_ptr(), host_ts.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), S,
+                                  y0.data_ptr(), None, y_ckpt.data_ptr(), None, ws.data_ptr(), ws.numel()), "pegncde_solve_fwd")
+        samples = dense_samples_of_table(host_ts, save_ts)
+        ys = torch.empty((len(save_ts),) + tuple(y0.shape), dtype=torch.float32, device=dev)
+        k1, k7, y1 = torch.empty_like(y0), torch.empty_like(y0), torch.empty_like(y0)
+        kst = torch.empty((5,) + tuple(y0.shape), dtype=torch.float32, device=dev)
+        done_step = -1
+        for (m, s, theta) in sorted(samples, key=lambda r: r[1]):
+            h = float(np.float32(host_ts[s + 1] - host_ts[s]))
+            if s != done_step:
+                check(l.pegncde_step_fwd(st, dims, ctl, flat.data_ptr(), float(host_ts[s]), h, y_ckpt[s].data_ptr(), k1.data_ptr(), 0,
+                                         y1.data_ptr(), None, k7.data_ptr(), kst.data_ptr(), ws.data_ptr(), ws.numel()), "pegncde_step_fwd")
+                done_step = s
+            check(l.pegncde_tsit5_dense(st, dims, h, theta, y_ckpt[s].data_ptr(), k1.data_ptr(), kst.data_ptr(), k7.data_ptr(),
+                                        ys[m].data_ptr()), "pegncde_tsit5_dense")
+        ctx.save_for_backward(flat, y_ckpt)
+        ctx.pc, ctx.dims, ctx.host_ts, ctx.S, ctx.samples = pc, dims, host_ts, S, samples
+        return ys
+
+    @staticmethod
+    def backward(ctx, g_out):
+        flat, y_ckpt = ctx.saved_tensors
+        l = lib()
+        dims, pc, S, host_ts = ctx.dims, ctx.pc, ctx.S, ctx.host_ts
+        dev = flat.device
+        ws = workspace(dev, l.pegncde_workspace_bytes(dims, PEG_WS_SOLVE_BWD, S))
+        g_out = g_out.contiguous().to(torch.float32)
+        g_ckpt = torch.zeros_like(y_ckpt)
+        g_stage = torch.zeros((S, 7) + tuple(y_ckpt.shape[1:]), dtype=torch.float32, device=dev)
+        for (m, s, theta) in ctx.samples:
+            g_ckpt[s] += g_out[m]
+            w = dense_weights(theta) * np.float32(host_ts[s + 1] - host_ts[s])
+            for i in range(7):
+                if w[i] != 0.0:
+                    g_stage[s, i].add_(g_out[m], alpha=float(w[i]))
+        g_y0 = torch.empty_like(y_ckpt[0])
+        g_flat = torch.zeros_like(flat)
+        g_x = torch.zeros_like(pc.x_coef) if ctx.needs_input_grad[2] else None
+        check(l.pegncde_solve_bwd(_stream_ptr(dev), dims, pc.struct(), flat.data_ptr(), host_ts.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), S,
+                                  y_ckpt.data_ptr(), None, None, g_ckpt.data_ptr(), g_stage.data_ptr(), g_y0.data_ptr(), g_flat.data_ptr(),
+                                  g_x.data_ptr() if g_x is not None else None, ws.data_ptr(), ws.numel()), "pegncde_solve_bwd")
+        return g_y0, g_flat, g_x, None, None, None, None
+
+
 def _stream_pieces(pc, step_ts, run_steps) -> None:
     """Streamed control (host coefficient arrays): copy + pack cubic piece i+1 on a side stream while the solver steps that
     end inside piece i run on the main stream.  A step may start once the piece holding its end time is packed (the lookup
@@ -269,8 +352,6 @@ def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: Optional[S
     if dt0 is None and not adaptive:
         raise ValueError("ConstantStepSize needs dt0")
     saveat = saveat or SaveAt(t1=True)
-    if saveat.ts is not None and not adaptive:
-        raise NotImplementedError("SaveAt(ts=...) is implemented for the adaptive path (Tsit5 dense output); use steps=True or t1=True")
     vf, wrapped = _unwrap(terms)
     if y0.device.type != "cuda":
         raise RuntimeError("the fused solve runs on CUDA only (no CPU fallback)")
@@ -288,6 +369,12 @@ def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: Optional[S
         pc.materialize()
         return _diffeqsolve_adaptive(vf, wrapped, pc, t0, t1, dt0, yb, unb, controller, saveat, max_steps)
     step_ts = constant_step_table(float(t0), float(t1), float(dt0), controller.rule, max_steps)
+    if saveat.ts is not None:   # SaveAt(ts=...) with ConstantStepSize: evolving_out=True of the PGT / TGB models
+        save_ts = np.asarray(torch.as_tensor(saveat.ts).detach().cpu().numpy(), dtype=np.float32).reshape(-1)
+        out = _FixedDenseFunction.apply(yb, vf.checked_flat_params(dims), pc.x_packed, pc, dims, step_ts, save_ts)
+        S = len(step_ts) - 1
+        return Solution(ts=torch.from_numpy(save_ts.copy()), ys=out.squeeze(1) if unb else out,
+                        stats={"num_steps": S, "num_accepted_steps": S, "num_rejected_steps": 0})
     out = _SolveFunction.apply(yb, vf.checked_flat_params(dims), pc.x_packed, pc, dims, step_ts, bool(saveat.steps), bool(getattr(vf, "store_stages", True)))
     S = len(step_ts) - 1
     if saveat.steps:

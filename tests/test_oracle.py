@@ -231,14 +231,23 @@ def _model_fixture(name):
 @pytest.mark.parametrize("name", list(PIN.MODEL_CASES))
 def test_oracle_models_match_reference_source_fixtures(name):
     g, kind, p, enc, dec, inp, tt = _model_fixture(name)
+    extra = PIN.MODEL_CASES[name][2]
+    ev = bool(extra.get("evolving_out"))
     if kind == "pgt":
-        _close(R.pgt_graph_neural_cde(p.ts, p.coeffs_adj, p.x_coeffs, inp["x0"], enc, dec, p.layers, p.h, p.e), g["out_global"], "pgt global")
-        _close(R.pgt_graph_neural_cde(p.ts, p.coeffs_adj, p.x_coeffs, inp["x0"], enc, dec, p.layers, p.h, p.e, global_readout=False), g["out_nodes"], "pgt nodes")
-        assert g["out_global"].shape == (1,) and g["out_nodes"].shape == (p.n, 1)
+        cadj, cx = p.coeffs_adj, p.x_coeffs
+        if extra.get("interpolation") == "linear":   # piecewise-linear control = cubic pieces with c = d = 0 (unit knot spacing)
+            A_k, X_k = tt(g["adj_knots"]), tt(g["x_knots"])
+            cadj = (torch.zeros_like(cadj[0]), torch.zeros_like(cadj[0]), A_k[1:] - A_k[:-1], A_k[:-1])
+            cx = (torch.zeros_like(cx[0]), torch.zeros_like(cx[0]), X_k[1:] - X_k[:-1], X_k[:-1])
+        _close(R.pgt_graph_neural_cde(p.ts, cadj, cx, inp["x0"], enc, dec, p.layers, p.h, p.e, evolving_out=ev), g["out_global"], "pgt global")
+        _close(R.pgt_graph_neural_cde(p.ts, cadj, cx, inp["x0"], enc, dec, p.layers, p.h, p.e, global_readout=False, evolving_out=ev), g["out_nodes"], "pgt nodes")
+        assert g["out_global"].shape == (extra["feature_dim"],) and g["out_nodes"].shape == (p.n, extra["feature_dim"])
     elif kind == "tgb":
-        out = R.tgb_graph_neural_cde(p.ts, p.coeffs_adj, inp["x_data"], inp["x0"], enc, dec, (tt(g["data_encoder_W"]), tt(g["data_encoder_b"])), p.layers, p.h, p.e)
+        seq = bool(extra.get("return_sequence"))
+        out = R.tgb_graph_neural_cde(p.ts, p.coeffs_adj, inp["x_data"], inp["x0"], enc, dec, (tt(g["data_encoder_W"]), tt(g["data_encoder_b"])), p.layers, p.h, p.e,
+                                     evolving_out=ev, return_sequence=seq)
         _close(out, g["out"], "tgb")
-        assert g["out"].shape == (p.n, p.n)
+        assert g["out"].shape == ((p.ts.numel(), p.n, p.n) if seq else (p.n, p.n))
     else:
         out, table = R.graph_neural_cde(p.ts, p.coeffs_adj, inp["x0"], enc[0], dec[0], p.layers)
         _close(out, g["out"], "dyn")
