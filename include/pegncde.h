@@ -64,10 +64,14 @@ enum {
   PEG_FLAG_TF32_FAST = 2,       /* with TENSOR_CORES: single-pass TF32 (rna-rounded), looser tolerance */
   PEG_FLAG_DIRECTED = 4,        /* ConvEquivFusionDirectedLayer (layers.py:180-362): 11 parameter pairs, row AND column sums;
                                    needs PegControl.adj_colsum; fusion block = 22 (+2 pad) scalars (see parameter packing) */
-  PEG_FLAG_TF32X3 = 16,         /* with TENSOR_CORES: operands of the n x n x d contraction split as 3xTF32 (rounding ~2^-22 per product)
-                                   instead of the default bf16x2 split (x = hi + lo, both bf16, three products on kind::f16 at twice
-                                   the tf32 rate: rounding ~2^-17 per product, fp32 accumulation; still inside the fp32 parity
-                                   tolerance) */
+  PEG_FLAG_TF32X3 = 16,         /* with TENSOR_CORES: operands of the n x n x d contraction split as 3xTF32 (x = hi + lo, both tf32,
+                                   hi*hi + lo*hi + hi*lo on kind::tf32: rounding ~2^-22 per product).  The DEFAULT is the same three-product
+                                   split with fp16 parts and block exponents ("fp16x2", 11 + 11 mantissa bits: the same ~2^-22 per
+                                   product, fp32 accumulation) on kind::f16 at twice the tf32 rate and half the shared-memory traffic;
+                                   it needs PegControl.adj_absmax and falls back to 3xTF32 when that pointer is NULL */
+  PEG_FLAG_BF16X2 = 32,         /* with TENSOR_CORES: x = hi + lo with bf16 parts (no block exponents needed; 8 + 8 mantissa bits:
+                                   rounding ~2^-17 per product).  A separately stated looser-tolerance mode: Z_T within 1e-4,
+                                   gradients within 2e-3 */
   PEG_FLAG_ADJ_LIGHT = 8        /* with TENSOR_CORES: the adjoint contraction runs two of its four products single-pass; looser
                                    stated tolerance on the param1 / param2 gradients (2.5e-3 instead of 1e-3).  Off by default. */
 };
@@ -100,6 +104,8 @@ typedef struct PegControl {
                               interleaved like the reference's [n,e,2]; NULL iff e == 0             */
   const float* adj_colsum; /* [B, T-1, 4, n]    column sums of each plane (pegncde_adj_colsums); only read with
                               PEG_FLAG_DIRECTED, NULL otherwise                                     */
+  const float* adj_absmax; /* [B, T-1, 4]       max |entry| of each plane (pegncde_adj_absmax): the range bound the fp16x2 operand
+                              format scales the interpolated adjacency with; NULL = not available (3xTF32 operands are used) */
 } PegControl;
 
 /* ---- parameter packing ---------------------------------------------------------------
@@ -138,6 +144,10 @@ int pegncde_build_adj(peg_stream_t stream, const PegDims* dims, const float* ts,
                       float* adj_rowsum, float* adj_diag, float* adj_total, float* tch_coef);
 /* column sums of the tiled planes (fixed summation order) -> adj_colsum [B, T-1, 4, n]; needed by PEG_FLAG_DIRECTED only */
 int pegncde_adj_colsums(peg_stream_t stream, const PegDims* dims, const float* adj_coef, float* adj_colsum);
+/* max |entry| of the tiled planes of the cubic pieces [piece_begin, piece_begin + piece_count) -> adj_absmax [B, T-1, 4] (order
+ * independent, hence reproducible) */
+int pegncde_adj_absmax(peg_stream_t stream, const PegDims* dims, int32_t piece_begin, int32_t piece_count, const float* adj_coef,
+                       float* adj_absmax);
 /* d,c,b,a each [B, T-1, n, e, 2] -> x_coef [B, T-1, 3, n, 2e] */
 int pegncde_pack_x(peg_stream_t stream, const PegDims* dims, const float* d, const float* c, const float* b,
                    const float* a, float* x_coef);

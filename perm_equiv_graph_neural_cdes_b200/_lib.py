@@ -17,6 +17,7 @@ PEG_FLAG_TF32_FAST = 2
 PEG_FLAG_DIRECTED = 4
 PEG_FLAG_ADJ_LIGHT = 8
 PEG_FLAG_TF32X3 = 16
+PEG_FLAG_BF16X2 = 32
 
 PEG_WS_VF_FWD, PEG_WS_VF_VJP, PEG_WS_SOLVE_FWD, PEG_WS_SOLVE_BWD, PEG_WS_STEP = range(5)
 
@@ -26,7 +27,7 @@ class PegDims(Structure):
 
 
 class PegControl(Structure):
-    _fields_ = [(k, c_void_p) for k in ("ts", "adj_coef", "adj_rowsum", "adj_diag", "adj_total", "tch_coef", "x_coef", "adj_colsum")]
+    _fields_ = [(k, c_void_p) for k in ("ts", "adj_coef", "adj_rowsum", "adj_diag", "adj_total", "tch_coef", "x_coef", "adj_colsum", "adj_absmax")]
 
 
 class PegError(RuntimeError):
@@ -53,6 +54,7 @@ SIGNATURES = {
     "pegncde_adj_stats": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P]),
     "pegncde_build_adj": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P, _P, _P]),
     "pegncde_adj_colsums": (c_int, [_P, _DIMS, _P, _P]),
+    "pegncde_adj_absmax": (c_int, [_P, _DIMS, c_int32, c_int32, _P, _P]),
     "pegncde_pack_x": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P]),
     "pegncde_workspace_bytes": (c_size_t, [_DIMS, c_int32, c_int32]),
     "pegncde_vf_fwd": (c_int, [_P, _DIMS, _CTL, _P, c_float, _P, _P, _P, c_size_t]),

@@ -117,6 +117,7 @@ class PackedControl:
         self.adj_diag = torch.empty((B, T - 1, 4, n), **f)
         self.adj_total = torch.empty((B, T - 1, 4), **f)
         self.tch_coef = torch.empty((B, T - 1, 3, n), **f)
+        self.adj_absmax = torch.empty((B, T - 1, 4), **f)   # max |entry| of each plane: range bound of the fp16x2 operand format
         self.x_coef = torch.empty((B, T - 1, 3, n, 2 * e), **f) if e > 0 else None
         self.x_packed = None   # differentiable source of x_coef when the node-signal coefficients require grad
         # state of the adjacency part, SHARED by every view made with with_x(): column sums of the planes ([B,T-1,4,n], built on
@@ -133,7 +134,7 @@ class PackedControl:
         node-signal coefficients ``x_coeffs = (d,c,b,a)``, each ``[T-1,n,e,2]`` or ``[B,T-1,n,e,2]``."""
         v = PackedControl.__new__(PackedControl)
         v.B, v.n, v.T, v.ldn = self.B, self.n, self.T, self.ldn
-        for name in ("ts", "adj_coef", "adj_rowsum", "adj_diag", "adj_total", "tch_coef"):
+        for name in ("ts", "adj_coef", "adj_rowsum", "adj_diag", "adj_total", "tch_coef", "adj_absmax"):
             setattr(v, name, getattr(self, name))
         v._adj = self._adj
         v._keepalive = self
@@ -146,6 +147,14 @@ class PackedControl:
                                            staging[2].data_ptr(), staging[3].data_ptr(), self.adj_coef.data_ptr(),
                                            self.adj_rowsum.data_ptr(), self.adj_diag.data_ptr(), self.adj_total.data_ptr(),
                                            self.tch_coef.data_ptr()), "pegncde_pack_adj_range")
+        self.plane_maxima(begin, count, stream_ptr)
+
+    def plane_maxima(self, begin: int = 0, count: int = -1, stream_ptr: Optional[int] = None) -> None:
+        """``adj_absmax`` of the cubic pieces [begin, begin+count) from the tiled planes (``pegncde_adj_absmax``)."""
+        count = self.T - 1 - begin if count < 0 else count
+        st = _stream_ptr(self.device) if stream_ptr is None else stream_ptr
+        check(lib().pegncde_adj_absmax(st, self.dims(h=4, L=1), begin, count, self.adj_coef.data_ptr(), self.adj_absmax.data_ptr()),
+              "pegncde_adj_absmax")
 
     def materialize(self) -> "PackedControl":
         """Copies and packs every pending piece now (adaptive solves, single evaluations, ragged time grids)."""
@@ -164,7 +173,7 @@ class PackedControl:
         """View of graph ``b`` as a batch of one (no copy): adaptive solves step every trajectory on its own."""
         v = PackedControl.__new__(PackedControl)
         v.B, v.n, v.T, v.e, v.ldn = 1, self.n, self.T, self.e, self.ldn
-        for name in ("ts", "adj_coef", "adj_rowsum", "adj_diag", "adj_total", "tch_coef"):
+        for name in ("ts", "adj_coef", "adj_rowsum", "adj_diag", "adj_total", "tch_coef", "adj_absmax"):
             setattr(v, name, getattr(self, name)[b:b + 1])
         v.x_coef = self.x_coef[b:b + 1] if self.x_coef is not None else None
         v.x_packed = None
@@ -187,6 +196,7 @@ class PackedControl:
             self.ts.data_ptr(), self.adj_coef.data_ptr(), self.adj_rowsum.data_ptr(), self.adj_diag.data_ptr(),
             self.adj_total.data_ptr(), self.tch_coef.data_ptr(), self.x_coef.data_ptr() if self.x_coef is not None else None,
             self.adj_colsum.data_ptr() if self.adj_colsum is not None else None,
+            self.adj_absmax.data_ptr() if getattr(self, "adj_absmax", None) is not None else None,
         )
 
     def ensure_colsums(self) -> "PackedControl":
@@ -266,6 +276,7 @@ def pack_control(
                                pc.adj_total.data_ptr(), pc.tch_coef.data_ptr()),
         "pegncde_pack_adj",
     )
+    pc.plane_maxima()
     _attach_x(pc, x_coeffs, device)
     pc._keepalive = cad   # keep the sources alive until the pack kernels have run (stream-ordered)
     return pc
@@ -320,6 +331,7 @@ def build_control(ts: torch.Tensor, snapshots: torch.Tensor, x_t: Optional[torch
     check(lib().pegncde_build_adj(_stream_ptr(device), pc.dims(h=4, L=1), pc.ts.data_ptr(), A.data_ptr(), pc.adj_coef.data_ptr(),
                                   pc.adj_rowsum.data_ptr(), pc.adj_diag.data_ptr(), pc.adj_total.data_ptr(), pc.tch_coef.data_ptr()),
           "pegncde_build_adj")
+    pc.plane_maxima()
     _attach_x(pc, cx, device)
     pc._keepalive = A
     return pc

@@ -33,6 +33,7 @@ struct StageScalars {
   float wD[4];      // A'_s  = sum_p wD[p] * plane_p            -> (0, 1, 2s, 3s^2)
   float totA, totD; // sum(A_s), sum(A'_s)
   float kappa[PEG_MAX_LAYERS];  // (p7_0 + p7_1) * totA / n^2   (reference quirk: both use sum(A))
+  float amax[4];    // max |entry| of the four planes of this cubic piece (0 when the control carries no adj_absmax)
   float pad[2];
 };
 
@@ -162,11 +163,18 @@ __device__ __forceinline__ float block_sum(float v, float* sh /* >= 33 floats */
 //   * V^T split into tf32 hi / lo, [B][d][npad] (the TMA-loaded K-major B operand of peg_tc.cu), zero padded;
 //   * column sums cb[b][0][c] = sum_i V[b,i,c], cb[b][1][c] = sum_i vec[b][i] V[b,i,c], reduced deterministically:
 //     every block writes its partial, the last block of a column group (ticket) adds them in block order.
+// Operand formats of the tcgen05 contraction (peg_tc.cu).  All three split x = hi + lo and run hi*hi + lo*hi + hi*lo with fp32 accumulation.
+enum { PEG_FMT_TF32X3 = 0,   // tf32 parts in fp32 words, kind::tf32
+       PEG_FMT_BF16X2 = 1,   // bf16 parts, kind::f16; no range management, 16 mantissa bits
+       PEG_FMT_FP16X2 = 2 }; // fp16 parts, kind::f16, 22 mantissa bits; block floating point: V^T carries one power-of-two scale per
+                             // 128-node block (vexp), the interpolated adjacency one scale per launch (from the plane maxima)
 struct ProducerOut {
-  float* Thi;             // nullable; t16 == 0: fp32 words holding tf32-rounded values, t16 == 1: packed bf16 (same buffer)
+  float* Thi;             // nullable; fmt 0: fp32 words holding tf32-rounded values, fmt 1 / 2: packed bf16 / fp16 (same buffer)
   float* Tlo;
   int npad;
-  int t16;                // operand format of the contraction that will read V^T: 0 = 3xTF32 (peg_tc.cu), 1 = bf16x2 (peg_tc16.cu)
+  int t16;                // operand format of the contraction that will read V^T (PEG_FMT_*)
+  int* vexp;              // fmt 2: [B][vexp_stride] power-of-two exponent of every 128-node block: V^T holds V * 2^vexp
+  int vexp_stride;
   float* cb;              // nullable
   float* partial;         // [B][chunks][2][d]
   unsigned int* tickets;  // self-resetting, one per (b, column group)
@@ -185,7 +193,40 @@ __device__ __forceinline__ unsigned short bf16_bits_rn(float x) {
   asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(x));
   return r;
 }
+__device__ __forceinline__ unsigned short f16_bits_rn(float x) {
+  unsigned short r;
+  asm("cvt.rn.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float f16_bits_to_f32(unsigned short h) {
+  float r;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(r) : "h"(h));
+  return r;
+}
+// Block exponent of the fp16x2 format: the power of two that brings a block whose largest magnitude is `amax` into [2^14, 2^15)
+// (fp16 overflows at 65504), clamped so that 2^e and 2^-e stay normal fp32 numbers; an all-zero block gets the largest exponent.
+#define PEG_VEXP_MAX 60
+__device__ __forceinline__ int block_exponent(float amax) {
+  if (!(amax > 0.f)) return PEG_VEXP_MAX;
+  const int e = 14 - ((int)((__float_as_uint(amax) >> 23) & 0xffu) - 127);
+  return max(-PEG_VEXP_MAX, min(PEG_VEXP_MAX, e));
+}
+__device__ __forceinline__ float exp2_int(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }   // e in [-126, 127]
+// one element of V^T in the fp16x2 format: `vs` = v * 2^(block exponent)
+__device__ __forceinline__ void store_vt_f16(const ProducerOut& po, size_t o, float vs) {
+  const unsigned short h = f16_bits_rn(vs);
+  reinterpret_cast<unsigned short*>(po.Thi)[o] = h;
+  reinterpret_cast<unsigned short*>(po.Tlo)[o] = f16_bits_rn(vs - f16_bits_to_f32(h));
+}
+// max over the warp of a non-negative value
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
 // one element of V^T (hi + lo parts) at element offset o of the [B][d][npad] operand arrays, in the format the contraction reads
+// (tf32 or bf16 parts; the fp16x2 format needs the block scale: store_vt_f16)
 __device__ __forceinline__ void store_vt(const ProducerOut& po, size_t o, float v) {
   if (po.t16) {
     const unsigned short h = bf16_bits_rn(v);

@@ -158,6 +158,39 @@ __global__ void __launch_bounds__(256) k_adj_totals(const float* __restrict__ ro
   if (threadIdx.x == 0) total[idx] = t;
 }
 
+// max |entry| of each of the four planes of one cubic piece.  grid (tile chunks, pieces, B), block 256; fmaxf is order
+// independent, so the atomicMax on the bit pattern (non-negative floats order like unsigned integers) is reproducible.
+__global__ void __launch_bounds__(256) k_adj_absmax(const float* __restrict__ adj_coef, int npad, int Tm1, int piece0,
+                                                    float* __restrict__ absmax) {
+  __shared__ float sh[8][4];
+  const int b = blockIdx.z, iv = piece0 + blockIdx.y;
+  const int nt = npad >> 5, ntiles = nt * nt, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t slab = (size_t)b * Tm1 + iv;
+  const float4* base = reinterpret_cast<const float4*>(adj_coef + slab * 4 * (size_t)npad * npad);
+  float mx[4] = {0.f, 0.f, 0.f, 0.f};
+  // a tile is 1024 float4: index i -> plane (i >> 7) & 3   ([g][plane][m][lane] with 4 floats per lane)
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+    for (int i = threadIdx.x; i < 1024; i += 256) {
+      const float4 v = __ldg(base + (size_t)t * 1024 + i);
+      const int q = (i >> 7) & 3;       // warp-uniform per iteration? i = tid + 256 k: (i >> 7) & 3 depends on tid >> 7 -> two values per block
+      const float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) mx[qq] = (q == qq) ? fmaxf(mx[qq], m) : mx[qq];
+    }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float m = warp_max(mx[q]);
+    if (lane == 0) sh[warp][q] = m;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float m = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) m = fmaxf(m, sh[w8][threadIdx.x]);
+    atomicMax(reinterpret_cast<unsigned int*>(absmax + slab * 4 + threadIdx.x), __float_as_uint(m));
+  }
+}
+
 __global__ void k_fill_tch_unit(float* __restrict__ tch, int n, size_t slabs) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= slabs * 3 * n) return;
@@ -252,6 +285,7 @@ __global__ void __launch_bounds__(256) k_stage_prep(PrepArgs a) {
     for (int p = 0; p < 4; ++p) { S.wA[p] = wA[p]; S.wD[p] = wD[p]; }
     S.totA = totA;
     S.totD = totD;
+    for (int p = 0; p < 4; ++p) S.amax[p] = a.ctl.adj_absmax ? a.ctl.adj_absmax[slab * 4 + p] : 0.f;
     for (int l = 0; l < L; ++l) {
       const float* f = a.params + a.model.layer[l].fus_off;
       S.kappa[l] = (f[12] + f[13]) * totA * inv_n2;

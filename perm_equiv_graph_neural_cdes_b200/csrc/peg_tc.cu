@@ -34,13 +34,12 @@ namespace peg {
 // V [B,n,d] -> V^T split into tf32 hi / lo, [B][d][npad] (zero padded): the K-major B operand
 // grid (npad/32, ceil(d/32), B), block (32, 8)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_split_transpose(const float* __restrict__ V, int n, int d, int npad,
-                                                         float* __restrict__ Thi, float* __restrict__ Tlo, int t16) {
-  ProducerOut po;
-  po.Thi = Thi; po.Tlo = Tlo; po.t16 = t16;
+__global__ void __launch_bounds__(256) k_split_transpose(const float* __restrict__ V, int n, int d, int npad, const ProducerOut po) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, i0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const float* Vb = V + (size_t)b * n * d;
+  // fp16x2: the block exponent of this tile's 128-node block (written by k_block_exponent just before)
+  const float vscale = po.t16 == PEG_FMT_FP16X2 ? exp2_int(po.vexp[(size_t)b * po.vexp_stride + (i0 >> 7)]) : 1.f;
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int i = i0 + r, c = c0 + threadIdx.x;
     tile[r][threadIdx.x] = (i < n && c < d) ? Vb[(size_t)i * d + c] : 0.f;
@@ -49,8 +48,36 @@ __global__ void __launch_bounds__(256) k_split_transpose(const float* __restrict
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int c = c0 + r, i = i0 + threadIdx.x;
     if (c < d) {
-      store_vt(po, ((size_t)b * d + c) * npad + i, tile[threadIdx.x][r]);
+      const size_t o = ((size_t)b * d + c) * npad + i;
+      if (po.t16 == PEG_FMT_FP16X2) store_vt_f16(po, o, tile[threadIdx.x][r] * vscale);
+      else store_vt(po, o, tile[threadIdx.x][r]);
     }
+  }
+}
+
+// fp16x2 operand format: block exponent e of every 128-node block of V [B,n,d] (vexp[b][block]); k_split_transpose then writes
+// V^T * 2^e.  One CTA per block reads its 128 x d slab once.  grid (ceil(npad/128), B), block 256
+__global__ void __launch_bounds__(256) k_block_exponent(const float* __restrict__ V, int n, int d, int* __restrict__ vexp, int vexp_stride) {
+  __shared__ float bmax_s[8];
+  const int b = blockIdx.y, blk = blockIdx.x, i0 = blk * 128;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rows = min(128, n - i0);
+  float mx = 0.f;
+  if (rows > 0) {
+    const size_t cnt4 = (size_t)rows * d / 4;      // d % 4 == 0
+    const float4* src = reinterpret_cast<const float4*>(V + ((size_t)b * n + i0) * d);
+    for (size_t i = tid; i < cnt4; i += 256) {
+      const float4 v = __ldg(src + i);
+      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+  }
+  mx = warp_max(mx);
+  if (lane == 0) bmax_s[warp] = mx;
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) mx = fmaxf(mx, bmax_s[w8]);
+    vexp[(size_t)b * vexp_stride + blk] = block_exponent(mx);
   }
 }
 
@@ -88,6 +115,8 @@ struct TcParams {
                  // 2 = epilogue only, accumulators read from `partial`  (split-K for grids far smaller than the GPU)
   int ksplit;    // K slices per row block in mode 1 (blockIdx.x = row block * ksplit + slice)
   int pairs_per_slice;
+  const int* vexp; // fp16x2 format: [B][vexp_stride] block exponents of V^T (one per 128 nodes)
+  int vexp_stride;
   float* partial; // [B][accumulators][n][d] fp32, zeroed by the host before mode 1
   int experiment; // timing experiments, compiled in only with -DPEG_TC_EXPERIMENTS (never in the shipped library):
                   // 1 = B operand loaded for the first pairs only, 2 = no MMAs.  Always 0 otherwise.
@@ -118,8 +147,11 @@ template <int KIND, int FMT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const TcParams p) {
   constexpr bool BWD = KIND != 0, LIGHT = KIND == 2;
-  constexpr bool F16 = FMT == 1;
+  constexpr bool F16 = FMT != PEG_FMT_TF32X3;       // 16-bit parts: bf16x2 or fp16x2
+  constexpr bool BFP = FMT == PEG_FMT_FP16X2;       // block floating point (see PEG_FMT_FP16X2)
   static_assert(!(F16 && LIGHT), "the LIGHT adjoint exists for the tf32 operand format only");
+  __shared__ float fblk_s[BFP ? 512 : 1];           // BFP: 2^(E - e_J) of every 128-node block J of this graph (E = min_J e_J)
+  __shared__ int emin_s;
   constexpr int ATILE = F16 ? TC_BM * TC_BK * 2 : TC_ATILE;   // one A-operand tile (hi or lo part)
   constexpr int ESZ = F16 ? 2 : 4;                            // operand element size
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -179,6 +211,24 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
+  int Emin = 0;
+  if constexpr (BFP) {
+    // V^T holds V * 2^(e_J) per 128-node block J.  The blocks are aligned to the smallest exponent E inside the A operand (its
+    // plane weights are multiplied by 2^(E - e_J) <= 1, exact), so every accumulator ends up scaled by 2^E times the A scale.
+    const int nblk = (a.ldn + 127) >> 7;
+    const int* ve = p.vexp + (size_t)b * p.vexp_stride;
+    if (warp == 0) {
+      int e = PEG_VEXP_MAX;
+      for (int J = lane; J < nblk; J += 32) e = min(e, ve[J]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) e = min(e, __shfl_xor_sync(0xffffffffu, e, o));
+      if (lane == 0) emin_s = e;
+    }
+    __syncthreads();
+    Emin = emin_s;
+    for (int J = tid; J < nblk; J += TC_THREADS) fblk_s[J] = exp2_int(max(Emin - ve[J], -120));
+    __syncthreads();
+  }
   const StageScalars* scp = a.sc + b;
   struct { float wA[4], wD[4]; int interval; } sc;
 #pragma unroll
@@ -204,6 +254,33 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   const float alpha = 1.f + a.fus[0], beta = 1.f + a.fus[1], gamma = a.fus[2], delta = a.fus[3];
   // adjoint: direct items (A V, A' V) enter the output with (gamma, delta), transposed items (A^T V, A'^T V) with (alpha, beta)
   const LightCoef lc_d = light_coef(gamma, delta), lc_t = light_coef(alpha, beta);
+  // BFP: power-of-two scale of every A-operand variant from the bound sum_q |w_q| max|plane_q| >= max |combined tile entry|
+  // (forward: ONE accumulator takes the direct X items and the transposed Y items, so both share the larger bound)
+  float ascale[NA], descale[NA];
+#pragma unroll
+  for (int v = 0; v < NA; ++v) { ascale[v] = 1.f; descale[v] = 1.f; }
+  if constexpr (BFP) {
+    float bound[NA];
+    const float* am = scp->amax;
+    if (BWD) {
+      bound[0] = fabsf(sc.wA[0]) * am[0] + fabsf(sc.wA[1]) * am[1] + fabsf(sc.wA[2]) * am[2] + fabsf(sc.wA[3]) * am[3];
+      bound[NA - 1] = fabsf(sc.wD[1]) * am[1] + fabsf(sc.wD[2]) * am[2] + fabsf(sc.wD[3]) * am[3];
+    } else {
+      float bx = 0.f, by = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        bx += fabsf(alpha * sc.wA[q] + beta * sc.wD[q]) * am[q];
+        by += fabsf(gamma * sc.wA[q] + delta * sc.wD[q]) * am[q];
+      }
+      bound[0] = fmaxf(bx, by);
+    }
+#pragma unroll
+    for (int v = 0; v < NA; ++v) {
+      const int e = block_exponent(bound[v]);
+      ascale[v] = exp2_int(e);
+      descale[v] = exp2_int(-e) * exp2_int(-Emin);     // |e|, |Emin| <= 60: both factors are normal numbers
+    }
+  }
 
   if (warp < 16) {
     // =========================== converters ===========================
@@ -355,20 +432,36 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     const uint32_t o_hi = o_row + (uint32_t)(((kq >> 1) ^ (((r0 >> 1) & 3) + 1)) << 4);    // rows r0 + 2, r0 + 3
     // store of row r0 + (m ^ sw) (held in register row m)
     const uint32_t o_m[4] = {o_lo + (uint32_t)(0 ^ sw) * 64u, o_lo + (uint32_t)(1 ^ sw) * 64u, o_hi + (uint32_t)(2 ^ sw) * 64u, o_hi + (uint32_t)(3 ^ sw) * 64u};
+    auto split16 = [&](float x0, float x1, uint32_t& hi, uint32_t& lo) {
+      if constexpr (BFP) split_f16x2(x0, x1, hi, lo);
+      else split_bf16x2(x0, x1, hi, lo);
+    };
+    // BFP: the launch-wide A scale rides in the (warp-uniform) weights; the per-item block alignment 2^(E - e_J) is one extra
+    // multiply per value (a power of two: exact) -- keeping it out of the weights keeps them in uniform registers
+    if constexpr (BFP) {
+#pragma unroll
+      for (int v = 0; v < NA; ++v)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[v][q] *= ascale[v];
+    }
+    float fitem = 1.f;
     auto put16 = [&](uint32_t addr, float x0, float x1, float x2, float x3) {
       uint32_t h01, l01, h23, l23;
-      split_bf16x2(x0, x1, h01, l01);
-      split_bf16x2(x2, x3, h23, l23);
+      split16(x0, x1, h01, l01);
+      split16(x2, x3, h23, l23);
       asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(h01), "r"(h23) : "memory");
       asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr + ATILE), "r"(l01), "r"(l23) : "memory");
     };
     auto comb = [&](int v, float e0, float e1, float e2, float e3) -> float {
-      if (BWD && v == NA - 1) return w[v][1] * e1 + w[v][2] * e2 + w[v][3] * e3;    // A'_s has no `a` term (wD[0] == 0)
-      return w[v][0] * e0 + w[v][1] * e1 + w[v][2] * e2 + w[v][3] * e3;
+      float r;
+      if (BWD && v == NA - 1) r = w[v][1] * e1 + w[v][2] * e2 + w[v][3] * e3;    // A'_s has no `a` term (wD[0] == 0)
+      else r = w[v][0] * e0 + w[v][1] * e1 + w[v][2] * e2 + w[v][3] * e3;
+      return BFP ? r * fitem : r;
     };
     auto convert16 = [&](int j, bool transposed) {
       const int st = j % SA;
       const uint32_t a_base = smem_base + st * a_bytes;
+      if constexpr (BFP) fitem = fblk_s[kc_of(pr0 + (j >> 1)) >> 2];
       mbar_wait(empty_a(st, 0), ((uint32_t)(j / SA) & 1u) ^ 1u);   // the MMAs that read this slot's previous contents have completed
       if (!transposed) {
 #pragma unroll
@@ -389,10 +482,10 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
           const float4 c0 = buf[0 * 4 + 2 * mp + 1], c1 = buf[1 * 4 + 2 * mp + 1], c2 = buf[2 * 4 + 2 * mp + 1], c3 = buf[3 * 4 + 2 * mp + 1];
 #pragma unroll
           for (int v = 0; v < NA; ++v) {
-            split_bf16x2(comb(v, a0.x, a1.x, a2.x, a3.x), comb(v, c0.x, c1.x, c2.x, c3.x), ph[v][0][mp], pl[v][0][mp]);
-            split_bf16x2(comb(v, a0.y, a1.y, a2.y, a3.y), comb(v, c0.y, c1.y, c2.y, c3.y), ph[v][1][mp], pl[v][1][mp]);
-            split_bf16x2(comb(v, a0.z, a1.z, a2.z, a3.z), comb(v, c0.z, c1.z, c2.z, c3.z), ph[v][2][mp], pl[v][2][mp]);
-            split_bf16x2(comb(v, a0.w, a1.w, a2.w, a3.w), comb(v, c0.w, c1.w, c2.w, c3.w), ph[v][3][mp], pl[v][3][mp]);
+            split16(comb(v, a0.x, a1.x, a2.x, a3.x), comb(v, c0.x, c1.x, c2.x, c3.x), ph[v][0][mp], pl[v][0][mp]);
+            split16(comb(v, a0.y, a1.y, a2.y, a3.y), comb(v, c0.y, c1.y, c2.y, c3.y), ph[v][1][mp], pl[v][1][mp]);
+            split16(comb(v, a0.z, a1.z, a2.z, a3.z), comb(v, c0.z, c1.z, c2.z, c3.z), ph[v][2][mp], pl[v][2][mp]);
+            split16(comb(v, a0.w, a1.w, a2.w, a3.w), comb(v, c0.w, c1.w, c2.w, c3.w), ph[v][3][mp], pl[v][3][mp]);
           }
         }
 #pragma unroll
@@ -445,7 +538,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       // instruction descriptor: fp32 accumulate, K-major A and B, N = nd, M = 128; operand format tf32 (2) or bf16 (1)
-      const uint32_t fmt = F16 ? 1u : 2u;
+      const uint32_t fmt = BFP ? 0u : (F16 ? 1u : 2u);   // F16 = 0, BF16 = 1, TF32 = 2
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nd >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       uint32_t started = 0u;  // bit acc set once the accumulator has been written (first MMA overwrites)
       for (int j = 0; j < items; ++j) {
@@ -554,6 +647,17 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
           tmem_ld16(taddr + 3 * nd, r3);
         }
         tmem_wait_ld();
+        if constexpr (BFP) {   // undo the block scales (powers of two: exact); accumulator acc = type * 2 + v carries the scale of variant v
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            r0[u] = __float_as_uint(__uint_as_float(r0[u]) * descale[0]);
+            if (BWD) {
+              r1[u] = __float_as_uint(__uint_as_float(r1[u]) * descale[NA - 1]);
+              r2[u] = __float_as_uint(__uint_as_float(r2[u]) * descale[0]);
+              r3[u] = __float_as_uint(__uint_as_float(r3[u]) * descale[NA - 1]);
+            }
+          }
+        }
       }
       if (p.mode == 1) {   // split-K: add this slice's accumulators into the partial buffer, epilogue runs in the mode-2 launch
         if (rowok && items > 0) {
@@ -751,7 +855,7 @@ static int get_maps(const float* hi, const float* lo, uint64_t cols, uint64_t ro
     const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     for (int which = 0; which < 2; ++which) {
-      if (enc(which ? &ent->mlo : &ent->mhi, fmt16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)(which ? lo : hi), gdim, gstr, box, estr,
+      if (enc(which ? &ent->mlo : &ent->mhi, fmt16 == PEG_FMT_BF16X2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : (fmt16 == PEG_FMT_FP16X2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 2, (void*)(which ? lo : hi), gdim, gstr, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, fmt16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
         fprintf(stderr, "pegncde: cuTensorMapEncodeTiled failed: dims %llu x %llu, box 32 x %d\n", (unsigned long long)cols,
@@ -797,19 +901,27 @@ static inline int npad_of(int n) { return peg_npad(n); }
 
 void tc_carve(Bump& bp, const PegDims& d, int dmax, TcWs& w) {
   w.npad = npad_of(d.n);
+  w.fmt = PEG_FMT_TF32X3;
+  w.vexp = nullptr;
+  w.vexp_stride = (w.npad + 127) / 128;
   if ((d.flags & PEG_FLAG_TENSOR_CORES) == 0) {
     w.Vt_hi = w.Vt_lo = w.partial = nullptr;
     return;
   }
+  w.vexp = bp.take<int>((size_t)d.B * w.vexp_stride);
   const size_t cnt = (size_t)d.B * dmax * w.npad;
   w.Vt_hi = bp.take<float>(cnt);
   w.Vt_lo = bp.take<float>(cnt);
   w.partial = bp.take<float>((size_t)d.B * 4 * d.n * dmax);   // split-K accumulators (small grids only)
 }
 
-// operand format of the n x n x d contraction: bf16x2 unless the caller asks for 3xTF32 operands (PEG_FLAG_TF32X3) or for one of
-// the tf32-only accuracy modes
-bool tc_fmt16(int flags) { return (flags & (PEG_FLAG_TF32X3 | PEG_FLAG_TF32_FAST | PEG_FLAG_ADJ_LIGHT)) == 0; }
+// operand format of the n x n x d contraction (PEG_FMT_*): fp16x2 with block exponents by default; 3xTF32 on request, for the
+// tf32-only accuracy modes, when the control carries no plane maxima, or beyond 65536 nodes (512 block exponents per graph)
+int tc_fmt(const PegDims& d, bool have_absmax) {
+  if (d.flags & (PEG_FLAG_TF32X3 | PEG_FLAG_TF32_FAST | PEG_FLAG_ADJ_LIGHT)) return PEG_FMT_TF32X3;
+  if (d.flags & PEG_FLAG_BF16X2) return PEG_FMT_BF16X2;
+  return (have_absmax && d.ldn <= 65536) ? PEG_FMT_FP16X2 : PEG_FMT_TF32X3;
+}
 
 bool tc_supported(const PegDims& d, int dcols) {
   if (d.n < 128) return false;
@@ -830,10 +942,17 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   const int n = a.n, d = a.d, npad = w.npad;
   if (!w.Vt_hi || !w.Vt_lo) return PEG_ERR_WORKSPACE;
   if (!get_encode()) return PEG_ERR_UNSUPPORTED;
-  const int f16 = tc_fmt16(dm.flags) ? 1 : 0;
+  const int fmt = w.fmt, f16 = fmt != PEG_FMT_TF32X3 ? 1 : 0;
   if (!a.vt_ready) {
+    ProducerOut po;
+    memset(&po, 0, sizeof(po));
+    po.Thi = w.Vt_hi; po.Tlo = w.Vt_lo; po.npad = npad; po.t16 = fmt; po.vexp = w.vexp; po.vexp_stride = w.vexp_stride;
+    if (fmt == PEG_FMT_FP16X2) {
+      k_block_exponent<<<dim3((npad + 127) / 128, dm.B), 256, 0, st>>>(a.V, n, d, w.vexp, w.vexp_stride);
+      if (cudaPeekAtLastError() != cudaSuccess) { set_last_cuda((int)cudaGetLastError()); fprintf(stderr, "pegncde: k_block_exponent launch failed\n"); return PEG_ERR_CUDA; }
+    }
     dim3 grid(npad / 32, (d + 31) / 32, dm.B), block(32, 8);
-    k_split_transpose<<<grid, block, 0, st>>>(a.V, n, d, npad, w.Vt_hi, w.Vt_lo, f16);
+    k_split_transpose<<<grid, block, 0, st>>>(a.V, n, d, npad, po);
     if (cudaPeekAtLastError() != cudaSuccess) { set_last_cuda((int)cudaGetLastError()); fprintf(stderr, "pegncde: k_split_transpose launch failed\n"); return PEG_ERR_CUDA; }
   }
   TcParams p;
@@ -866,12 +985,14 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   while (cluster > 1 && (nblk < cluster || (p.nd / cluster) % 8 != 0)) cluster >>= 1;
   p.cluster = cluster;
   p.experiment = g_env.experiment;
+  p.vexp = w.vexp;
+  p.vexp_stride = w.vexp_stride;
   const int nv = PEG_TC_VARIANT_SLOTS ? na : 1;   // barrier pairs per A slot (see the kernel)
   const size_t smem = (size_t)sa * a_bytes + (size_t)sb * b_bytes + 1024 + 8 * (2 * sa * nv + 2 * sb + 2) + 64;
 
   const CUtensorMap* mhi_p = nullptr;
   const CUtensorMap* mlo_p = nullptr;
-  PEG_TC_TRY(get_maps(w.Vt_hi, w.Vt_lo, (uint64_t)npad, (uint64_t)dm.B * d, p.nd / cluster, &mhi_p, &mlo_p, f16));
+  PEG_TC_TRY(get_maps(w.Vt_hi, w.Vt_lo, (uint64_t)npad, (uint64_t)dm.B * d, p.nd / cluster, &mhi_p, &mlo_p, fmt));
   const CUtensorMap& mhi = *mhi_p;
   const CUtensorMap& mlo = *mlo_p;
 
@@ -905,14 +1026,20 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   // PEG_FLAG_ADJ_LIGHT (two of the four adjoint products single-pass): measured on B200 at n=2048, d=128, B=9 the adjoint launch
   // goes 213 -> 199 us (+5 % solver steps/s) but the param1/param2 gradients of a whole solve are off by up to 2.5e-3 (the rounding
   // of the slowly varying planes is correlated across launches, it does not average out) -> an accuracy mode the caller asks for
-  const int kind = bwd ? ((dm.flags & PEG_FLAG_ADJ_LIGHT) ? 2 : 1) : 0;   // tc_fmt16() is false whenever ADJ_LIGHT is set
+  const int kind = bwd ? ((dm.flags & PEG_FLAG_ADJ_LIGHT) ? 2 : 1) : 0;   // tc_fmt() is 3xTF32 whenever ADJ_LIGHT is set
+  // the instantiation for (kind, format): 0..2 = 3xTF32 forward / adjoint / LIGHT adjoint, then bf16x2 and fp16x2 forward / adjoint
+  const int inst = fmt == PEG_FMT_TF32X3 ? kind : 3 + 2 * (fmt - 1) + kind;
   {
-    static std::atomic<unsigned> done[5] = {{0u}, {0u}, {0u}, {0u}, {0u}};
-    if (kind == 2) PEG_TC_TRY(optin_smem(k_tc_contract<2, 0>, done[2]));
-    else if (kind == 1 && f16) PEG_TC_TRY(optin_smem(k_tc_contract<1, 1>, done[4]));
-    else if (kind == 1) PEG_TC_TRY(optin_smem(k_tc_contract<1, 0>, done[1]));
-    else if (f16) PEG_TC_TRY(optin_smem(k_tc_contract<0, 1>, done[3]));
-    else PEG_TC_TRY(optin_smem(k_tc_contract<0, 0>, done[0]));
+    static std::atomic<unsigned> done[7] = {{0u}, {0u}, {0u}, {0u}, {0u}, {0u}, {0u}};
+    switch (inst) {
+      case 0: PEG_TC_TRY(optin_smem(k_tc_contract<0, 0>, done[0])); break;
+      case 1: PEG_TC_TRY(optin_smem(k_tc_contract<1, 0>, done[1])); break;
+      case 2: PEG_TC_TRY(optin_smem(k_tc_contract<2, 0>, done[2])); break;
+      case 3: PEG_TC_TRY(optin_smem(k_tc_contract<0, 1>, done[3])); break;
+      case 4: PEG_TC_TRY(optin_smem(k_tc_contract<1, 1>, done[4])); break;
+      case 5: PEG_TC_TRY(optin_smem(k_tc_contract<0, 2>, done[5])); break;
+      default: PEG_TC_TRY(optin_smem(k_tc_contract<1, 2>, done[6])); break;
+    }
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -928,9 +1055,15 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   auto launch = [&]() -> cudaError_t {
-    return kind == 2 ? cudaLaunchKernelEx(&cfg, k_tc_contract<2, 0>, mhi, mlo, p)
-         : kind == 1 ? (f16 ? cudaLaunchKernelEx(&cfg, k_tc_contract<1, 1>, mhi, mlo, p) : cudaLaunchKernelEx(&cfg, k_tc_contract<1, 0>, mhi, mlo, p))
-                     : (f16 ? cudaLaunchKernelEx(&cfg, k_tc_contract<0, 1>, mhi, mlo, p) : cudaLaunchKernelEx(&cfg, k_tc_contract<0, 0>, mhi, mlo, p));
+    switch (inst) {
+      case 0: return cudaLaunchKernelEx(&cfg, k_tc_contract<0, 0>, mhi, mlo, p);
+      case 1: return cudaLaunchKernelEx(&cfg, k_tc_contract<1, 0>, mhi, mlo, p);
+      case 2: return cudaLaunchKernelEx(&cfg, k_tc_contract<2, 0>, mhi, mlo, p);
+      case 3: return cudaLaunchKernelEx(&cfg, k_tc_contract<0, 1>, mhi, mlo, p);
+      case 4: return cudaLaunchKernelEx(&cfg, k_tc_contract<1, 1>, mhi, mlo, p);
+      case 5: return cudaLaunchKernelEx(&cfg, k_tc_contract<0, 2>, mhi, mlo, p);
+      default: return cudaLaunchKernelEx(&cfg, k_tc_contract<1, 2>, mhi, mlo, p);
+    }
   };
   const cudaError_t le = launch();
   if (le != cudaSuccess) {
@@ -1007,6 +1140,7 @@ __global__ void __launch_bounds__(NL_THREADS, 1)
 k_tc_norm_linear(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const NlParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ float rinv_s[128];
+  __shared__ float bmax_s[8];
   __shared__ bool is_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, rb = blockIdx.x, ntile = blockIdx.y;
@@ -1143,6 +1277,30 @@ k_tc_norm_linear(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     const float vv = (p.po.vec && rowok) ? p.po.vec[(size_t)b * p.po.vec_stride + gi] : 0.f;
     float* Mrow = p.M + ((size_t)b * n + (rowok ? gi : 0)) * dout;
     const int cols_per_half = nd / 2;
+    // fp16x2 operand format: V^T of this 128-node block is stored as M * 2^e with one block exponent e (a first pass over the
+    // accumulators finds the block maximum; the host hands out Thi only when this CTA holds every column of the block)
+    float vscale = 1.f;
+    if (p.po.Thi != nullptr && p.po.t16 == PEG_FMT_FP16X2) {
+      float mx = 0.f;
+      for (int cc = 0; cc < cols_per_half; cc += 16) {
+        const int col = half * cols_per_half + cc, gc = ntile * nd + col;
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
+        tmem_wait_ld();
+        if (rowok) {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) mx = fmaxf(mx, fabsf(fmaf(ri, __uint_as_float(r[u]), __ldg(p.cvec + gc + u))));
+        }
+      }
+      mx = warp_max(mx);
+      if (lane == 0) bmax_s[warp] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) mx = fmaxf(mx, bmax_s[w8]);
+      const int e = block_exponent(mx);
+      vscale = exp2_int(e);
+      if (tid == 0) p.po.vexp[(size_t)b * p.po.vexp_stride + rb] = e;
+    }
     for (int cc = 0; cc < cols_per_half; cc += 16) {
       const int col = half * cols_per_half + cc, gc = ntile * nd + col;
       uint32_t r[16];
@@ -1157,9 +1315,12 @@ k_tc_norm_linear(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
           *reinterpret_cast<float4*>(Mrow + gc + 4 * v4) = make_float4(m[4 * v4], m[4 * v4 + 1], m[4 * v4 + 2], m[4 * v4 + 3]);
       }
       if (p.po.Thi != nullptr && gi < p.po.npad) {   // V^T hi/lo: the 32 lanes of a warp are 32 consecutive nodes
+        if (p.po.t16 == PEG_FMT_FP16X2) {
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          store_vt(p.po, ((size_t)b * dout + gc + u) * p.po.npad + gi, m[u]);
+          for (int u = 0; u < 16; ++u) store_vt_f16(p.po, ((size_t)b * dout + gc + u) * p.po.npad + gi, m[u] * vscale);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) store_vt(p.po, ((size_t)b * dout + gc + u) * p.po.npad + gi, m[u]);
         }
       }
       if (p.po.cb != nullptr) {   // column sums over this warp's 32 nodes (fixed butterfly order)
@@ -1254,6 +1415,8 @@ static int nl_pick_nd(int dout) {
   return 0;
 }
 
+bool tc_norm_linear_full_columns(int dout) { return nl_pick_nd(dout) == dout; }
+
 bool tc_linear_supported(int din, int dout) {
   if (g_env.no_linear) return false;
   return din % 32 == 0 && din >= 32 && nl_pick_nd(dout) != 0 && get_encode() != nullptr;
@@ -1331,6 +1494,7 @@ __global__ void __launch_bounds__(NL_THREADS, 1)
 k_tc_linear_bwd(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const LbParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ float red_s[2][2][128];   // [column half][ss, dot][node]
+  __shared__ float bmax_s[8];
   __shared__ bool is_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, rb = blockIdx.x;
@@ -1484,6 +1648,7 @@ k_tc_linear_bwd(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     const float vv = (p.po.vec && rowok) ? p.po.vec[(size_t)b * p.po.vec_stride + gi] : 0.f;
     float* Zbrow = p.Zbar + ((size_t)b * n + (rowok ? gi : 0)) * din;
     // pass 2: Zbar, its producer outputs, and the per-column sums (g_nw, g_nb, column sums of Zbar)
+    float zmax = 0.f;   // max |Zbar| of this thread's entries (block exponent of the fp16x2 operand format)
     for (int cc = 0; cc < cols_per_half; cc += 16) {
       const int col = half * cols_per_half + cc;
       uint32_t r[16];
@@ -1513,12 +1678,14 @@ k_tc_linear_bwd(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         for (int v4 = 0; v4 < 4; ++v4)
           *reinterpret_cast<float4*>(Zbrow + col + 4 * v4) = make_float4(zb[4 * v4], zb[4 * v4 + 1], zb[4 * v4 + 2], zb[4 * v4 + 3]);
       }
-      if (p.po.Thi != nullptr && gi < p.po.npad) {
+      if (p.po.Thi != nullptr && gi < p.po.npad && p.po.t16 != PEG_FMT_FP16X2) {
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
           store_vt(p.po, ((size_t)b * din + col + u) * p.po.npad + gi, zb[u]);
         }
       }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) zmax = fmaxf(zmax, fabsf(zb[u]));
       warp_colsum16(gw, lane);
       warp_colsum16(gb, lane);
       warp_colsum16(zb, lane);
@@ -1529,6 +1696,39 @@ k_tc_linear_bwd(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         csum[(q * 4 + 1) * nd + c] = gb[0];
         csum[(q * 4 + 2) * nd + c] = zb[0];
         csum[(q * 4 + 3) * nd + c] = s1[0];
+      }
+    }
+    if (p.po.Thi != nullptr && p.po.t16 == PEG_FMT_FP16X2) {
+      // pass 3 (fp16x2 operand format): the block maximum is known only now -> V^T = Zbar * 2^e from a third walk over the accumulators
+      zmax = warp_max(zmax);
+      if (lane == 0) bmax_s[warp] = zmax;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) zmax = fmaxf(zmax, bmax_s[w8]);
+      const int e = block_exponent(zmax);
+      const float vscale = exp2_int(e);
+      if (tid == 0) p.po.vexp[(size_t)b * p.po.vexp_stride + rb] = e;
+      if (gi < p.po.npad) {
+        for (int cc = 0; cc < cols_per_half; cc += 16) {
+          const int col = half * cols_per_half + cc;
+          uint32_t r[16];
+          tmem_ld16(trow + (uint32_t)col, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rowok) z4 = *reinterpret_cast<const float4*>(Zrow + col + 4 * v4);
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.nw + col + 4 * v4));
+            const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float nbar = rowok ? __uint_as_float(r[4 * v4 + u]) : 0.f;
+              float v = rinv * ww[u] * nbar - zz[u] * coef;   // the same expression as pass 2: bit-identical Zbar
+              if (!rowok || (p.relu_mask && !(zz[u] > 0.f))) v = 0.f;
+              store_vt_f16(p.po, ((size_t)b * din + col + 4 * v4 + u) * p.po.npad + gi, v * vscale);
+            }
+          }
+        }
       }
     }
     tc_fence_before();

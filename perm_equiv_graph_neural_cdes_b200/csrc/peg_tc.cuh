@@ -11,6 +11,9 @@ struct TcWs {
   float* Vt_lo;  // [B][dmax][npad]  residual V - high part, same format
   float* partial;  // [B][4][n][dmax] split-K accumulators (grids far smaller than the GPU)
   int npad;
+  int fmt;          // operand format of this call (PEG_FMT_*), set by make_ctx from the flags and the control
+  int* vexp;        // [B][vexp_stride] block exponents of V^T (fp16x2 format)
+  int vexp_stride;  // = ceil(npad / 128)
 };
 
 // per-layer tf32 hi/lo copies of the Linear weights (built once per API call by tc_prep_weights):
@@ -32,6 +35,7 @@ bool tc_linear_supported(int din, int dout);
 // splits the weights of every layer (enqueue only); call once per API entry before the first evaluation
 int tc_prep_weights(cudaStream_t st, const Model& m, const float* params, const TcLinear& w);
 // M = rmsnorm(Z) W^T + b on tcgen05 (3xTF32), fused producer outputs as k_norm_linear (peg_kernels.cuh)
+bool tc_norm_linear_full_columns(int dout);   // one CTA holds every output column of its 128 nodes (it can emit fp16x2 V^T)
 // backward of Linear + RMSNorm wrt the layer input on tcgen05, epilogue as k_linear_bwd (peg_kernels.cuh)
 int tc_linear_bwd(cudaStream_t st, const PegDims& d, const TcLinear& w, int layer, const float* Mbar, const float* Z,
                   const float* nw, int din, int dout, int relu_mask, float* Zbar, float* g_nw, float* g_nb, const ProducerOut& po);
@@ -43,7 +47,7 @@ int tc_weight_grad(cudaStream_t st, const PegDims& d, const float* Mbar, const f
 int tc_norm_linear(cudaStream_t st, const PegDims& d, const TcLinear& w, int layer, const float* Z, int din, int dout,
                    const float* nw, const float* nb, float* M, float* Nout, const ProducerOut& po);
 bool tc_supported(const PegDims& d, int dcols);
-bool tc_fmt16(int flags);   // contraction operands as bf16x2 (default) rather than 3xTF32
+int tc_fmt(const PegDims& d, bool have_absmax);   // operand format of the contraction (PEG_FMT_*)
 int tc_contract(cudaStream_t st, const PegDims& d, const TcWs& w, const ContractArgs& a, bool bwd);
 int tc_launches_per_contract(bool bwd);
 void set_last_cuda(int err);   // records a cudaError_t for pegncde_last_cuda_error() (defined in pegncde.cu)

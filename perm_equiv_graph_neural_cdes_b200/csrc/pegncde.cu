@@ -169,6 +169,7 @@ struct Ctx {
   FevalWs w;
   size_t sv_stride;
   bool use_tc;
+  int fmt;   // operand format of the tensor-core contraction for this call (set by make_ctx, copied into w.tc after plan())
 };
 
 // ------------------------------------------------------------------------------------------
@@ -195,15 +196,19 @@ static int stage_prep(Ctx& c, float t) {
   return PEG_OK;
 }
 
-// producer-side fused outputs (V^T hi/lo for the tensor-core contraction, deterministic column sums)
-static ProducerOut producer_out(Ctx& c, int dcols, bool want_vt, float* cb, bool with_vec, size_t vec_off) {
+// producer-side fused outputs (V^T hi/lo for the tensor-core contraction, deterministic column sums).
+// `bfp_capable`: the producer kernel that will run can emit the fp16x2 format (a tcgen05 producer whose CTA holds every column of
+// its 128 nodes, so it knows the block maximum); otherwise the contraction converts V itself (k_split_transpose16).
+static ProducerOut producer_out(Ctx& c, int dcols, bool want_vt, float* cb, bool with_vec, size_t vec_off, bool bfp_capable) {
   ProducerOut po;
   memset(&po, 0, sizeof(po));
-  if (want_vt && c.use_tc && tc_supported(c.d, dcols)) {
+  if (want_vt && c.use_tc && tc_supported(c.d, dcols) && (c.w.tc.fmt != PEG_FMT_FP16X2 || bfp_capable)) {
     po.Thi = c.w.tc.Vt_hi;
     po.Tlo = c.w.tc.Vt_lo;
     po.npad = c.w.tc.npad;
-    po.t16 = tc_fmt16(c.d.flags) ? 1 : 0;
+    po.t16 = c.w.tc.fmt;
+    po.vexp = c.w.tc.vexp;
+    po.vexp_stride = c.w.tc.vexp_stride;
   }
   po.cb = cb;
   po.partial = c.w.colPart;
@@ -212,10 +217,13 @@ static ProducerOut producer_out(Ctx& c, int dcols, bool want_vt, float* cb, bool
   po.vec_stride = c.sv_stride;
   return po;
 }
+static bool norm_linear_on_tc(const Ctx& c, int l) {
+  return c.use_tc && c.w.lin.ready && tc_linear_supported(c.m.layer[l].din, c.m.layer[l].dout);
+}
 
 static int norm_linear(Ctx& c, int l, const float* Zin, float* M, float* Nout, const ProducerOut& po) {
   const LayerDesc& ld = c.m.layer[l];
-  if (c.use_tc && c.w.lin.ready && tc_linear_supported(ld.din, ld.dout)) {
+  if (norm_linear_on_tc(c, l)) {
     const int rc = tc_norm_linear(c.st, c.d, c.w.lin, l, Zin, ld.din, ld.dout, c.params + ld.nw_off, c.params + ld.nb_off, M, Nout, po);
     if (rc == PEG_OK) g_launches.fetch_add(1);
     return rc;
@@ -271,7 +279,7 @@ static int contract(Ctx& c, int l, bool bwd, const float* V, const float* Mref, 
   int rc = PEG_OK;
   if (c.use_tc && tc_supported(c.d, ld.dout)) {
     rc = tc_contract(c.st, c.d, c.w.tc, a, bwd);
-    if (rc == PEG_OK) g_launches.fetch_add(vt_ready ? 1 : 2);
+    if (rc == PEG_OK) g_launches.fetch_add(vt_ready ? 1 : (c.w.tc.fmt == PEG_FMT_FP16X2 ? 3 : 2));
   } else {
     dim3 grid((c.d.n + CT_TI - 1) / CT_TI, (ld.dout + CT_TC - 1) / CT_TC, c.d.B);
     if (!bwd)
@@ -294,7 +302,7 @@ static int feval_fwd(Ctx& c, float t, const float* yin, float* dy, float* const*
   for (int l = 0; l < nlayers; ++l) {
     const LayerDesc& ld = c.m.layer[l];
     const bool last = (l == d.L - 1);
-    const ProducerOut po = producer_out(c, ld.dout, true, c.w.colM, true, svec_c(d.n, l));
+    const ProducerOut po = producer_out(c, ld.dout, true, c.w.colM, true, svec_c(d.n, l), norm_linear_on_tc(c, l) && tc_norm_linear_full_columns(ld.dout));
     PEG_TRY(norm_linear(c, l, Zin, c.w.M, nullptr, po));
     float* out;
     if (!last) {
@@ -326,7 +334,7 @@ static int feval_vjp(Ctx& c, float t, float* const* zin, const float* kbar, floa
     if (d.e == 0) return PEG_ERR_BAD_DIMS;
     // recompute the (tg-scaled) last-layer output, then contract it with kbar
     const int l = d.L - 1;
-    const ProducerOut po = producer_out(c, dL, true, c.w.colM, true, svec_c(d.n, l));
+    const ProducerOut po = producer_out(c, dL, true, c.w.colM, true, svec_c(d.n, l), norm_linear_on_tc(c, l) && tc_norm_linear_full_columns(dL));
     PEG_TRY(norm_linear(c, l, zin[l], c.w.M, nullptr, po));
     PEG_TRY(contract(c, l, false, c.w.M, nullptr, c.w.colM, c.w.OL, false, true, nullptr, po.Thi != nullptr));
     const size_t cnt = (size_t)d.B * d.n * 2 * d.e;
@@ -346,7 +354,7 @@ static int feval_vjp(Ctx& c, float t, float* const* zin, const float* kbar, floa
     const LayerDesc& ld = c.m.layer[l];
     float* g_fus = g_params + ld.fus_off;
     // recompute M_l (and the normalised input N_l) from the saved layer input; 1^T M comes out of the same kernel
-    PEG_TRY(norm_linear(c, l, zin[l], c.w.M, c.w.N, producer_out(c, ld.dout, false, c.w.colM, false, 0)));
+    PEG_TRY(norm_linear(c, l, zin[l], c.w.M, c.w.N, producer_out(c, ld.dout, false, c.w.colM, false, 0, false)));
     if (!obar_ready) PEG_TRY(colsums(c, c.w.Obar, ld.dout, svec_r(d.n, l), true, c.w.colG));
     // the tcgen05 adjoint epilogue also emits the param3..8 gradients (undirected layer; the directed one keeps the separate kernel)
     const bool fused_vec_grads = contract_on_tc(c, l) && !c.m.directed;
@@ -382,8 +390,9 @@ static int feval_vjp(Ctx& c, float t, float* const* zin, const float* kbar, floa
       // for l > 0 the output is the cotangent Obar of layer l-1: emit its column sums (vec = r_{l-1}) and V^T here
       ProducerOut po;
       memset(&po, 0, sizeof(po));
-      if (l > 0) po = producer_out(c, ld.din, true, c.w.colG, true, svec_r(d.n, l - 1));
-      if (c.use_tc && c.w.lin.ready && tc_linear_bwd_supported(ld.din, ld.dout)) {
+      const bool lb_tc = c.use_tc && c.w.lin.ready && tc_linear_bwd_supported(ld.din, ld.dout);
+      if (l > 0) po = producer_out(c, ld.din, true, c.w.colG, true, svec_r(d.n, l - 1), lb_tc);
+      if (lb_tc) {
         PEG_TRY(tc_linear_bwd(c.st, c.d, c.w.lin, l, c.w.Mbar, zin[l], c.params + ld.nw_off, ld.din, ld.dout, l > 0 ? 1 : 0, zb,
                               g_params + ld.nw_off, g_params + ld.nb_off, po));
         g_launches.fetch_add(1);
@@ -434,12 +443,14 @@ static int make_ctx(Ctx& c, peg_stream_t stream, const PegDims* dims, const PegC
   c.sv_stride = svec_stride(dims->n, dims->L, dims->e);
   c.use_tc = (dims->flags & PEG_FLAG_TENSOR_CORES) != 0;
   if (c.use_tc) tc_refresh_env();
+  c.fmt = tc_fmt(*dims, ctl->adj_absmax != nullptr);
   return PEG_OK;
 }
 
 // start of every compute entry point: arrival counters zeroed, tensor-core weight copies refreshed (params may have
 // changed since the previous call; the copies live in the caller's workspace)
 static int reset_tickets(Ctx& c) {
+  c.w.tc.fmt = c.fmt;   // plan() carved the workspace after make_ctx chose the format
   PEG_CUDA(cudaMemsetAsync(c.w.tickets, 0, c.w.tickets_count * sizeof(unsigned int), c.st));
   if (c.use_tc) {
     PEG_TRY(tc_prep_weights(c.st, c.m, c.params, c.w.lin));
@@ -593,6 +604,21 @@ int pegncde_adj_colsums(peg_stream_t stream, const PegDims* dims, const float* a
   if (!adj_coef || !adj_colsum) return PEG_ERR_NULL_POINTER;
   const int nt = dims->ldn / 32;
   k_adj_colsums<<<dim3(nt, dims->T - 1, dims->B), 256, 0, (cudaStream_t)stream>>>(adj_coef, dims->n, dims->ldn, dims->T - 1, adj_colsum);
+  PEG_LAUNCH_CHECK();
+  return PEG_OK;
+}
+
+int pegncde_adj_absmax(peg_stream_t stream, const PegDims* dims, int32_t piece_begin, int32_t piece_count, const float* adj_coef,
+                       float* adj_absmax) {
+  PEG_TRY(check_dims(dims));
+  if (!adj_coef || !adj_absmax) return PEG_ERR_NULL_POINTER;
+  const int Tm1 = dims->T - 1;
+  if (piece_begin < 0 || piece_count < 1 || piece_begin + piece_count > Tm1) return PEG_ERR_BAD_DIMS;
+  cudaStream_t st = (cudaStream_t)stream;
+  PEG_CUDA(cudaMemset2DAsync(adj_absmax + (size_t)piece_begin * 4, (size_t)Tm1 * 4 * sizeof(float), 0, (size_t)piece_count * 4 * sizeof(float),
+                             dims->B, st));
+  const int nt = dims->ldn / 32, ntiles = nt * nt;
+  k_adj_absmax<<<dim3(ntiles < 64 ? ntiles : 64, piece_count, dims->B), 256, 0, st>>>(adj_coef, dims->ldn, Tm1, piece_begin, adj_absmax);
   PEG_LAUNCH_CHECK();
   return PEG_OK;
 }

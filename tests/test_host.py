@@ -190,7 +190,7 @@ def test_packed_control_select_is_a_view():
     pc = P.PackedControl.__new__(P.PackedControl)
     pc.B, pc.n, pc.T, pc.e, pc.ldn = 3, 5, 4, 0, 32
     for name, shape in (("ts", (3, 4)), ("adj_coef", (3, 3, 4 * 32 * 32)), ("adj_rowsum", (3, 3, 4, 5)), ("adj_diag", (3, 3, 4, 5)),
-                        ("adj_total", (3, 3, 4)), ("tch_coef", (3, 3, 3, 5))):
+                        ("adj_total", (3, 3, 4)), ("tch_coef", (3, 3, 3, 5)), ("adj_absmax", (3, 3, 4))):
         setattr(pc, name, torch.zeros(shape))
     pc.x_coef = None
     pc._adj = {"colsum": None, "pending": None, "host_ts": None}
