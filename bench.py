@@ -181,6 +181,10 @@ def run_ours(args):
     flags = 0 if args.no_tensor_cores else _lib.PEG_FLAG_TENSOR_CORES
     if args.tf32_fast:
         flags |= _lib.PEG_FLAG_TF32_FAST
+    if args.operands == "tf32x3":
+        flags |= _lib.PEG_FLAG_TF32X3
+    elif args.operands == "bf16x2":
+        flags |= _lib.PEG_FLAG_BF16X2
 
     widths_out = 2 * h * e if e > 0 else h
     vf = P.PermEquivGraphVectorField(h, h, widths_out, L, e, n, key=1234).to(dev)
@@ -468,6 +472,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="graphs per GPU (default: the workload's)")
     ap.add_argument("--no-tensor-cores", action="store_true")
     ap.add_argument("--tf32-fast", action="store_true")
+    ap.add_argument("--operands", default="fp16x2", choices=["fp16x2", "bf16x2", "tf32x3"],
+                    help="operand format of the tcgen05 contraction: fp16x2 with block exponents (default), bf16x2 (looser tolerance), 3xTF32")
     ap.add_argument("--profile-stride", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample-steps", type=int, default=24, help="solver steps of one graph the CPU baseline runs (~15 s of CPU work at the default workload)")

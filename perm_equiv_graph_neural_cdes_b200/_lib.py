@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpegncde.so")
+LIB_PATH = os.environ.get("PEGNCDE_LIB") or os.path.join(_HERE, "libpegncde.so")   # PEGNCDE_LIB: A/B builds of the same ABI (tools/)
 
 PEG_FLAG_TENSOR_CORES = 1
 PEG_FLAG_TF32_FAST = 2

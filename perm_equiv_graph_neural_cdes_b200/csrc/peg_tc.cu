@@ -187,6 +187,10 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   const uint32_t accum_bar = bar_base + 8u * (2 * SAV + 2 * SB);
   const uint32_t tmem_slot = accum_bar + 8u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
+  // 16-bit formats: the chunk schedule of this CTA as a table (pair -> K chunk; BFP: + per A-operand variant the factor
+  // (A scale) * 2^(E - e_J) as float bits), so the conversion loop spends one LDS.128 per item instead of re-deriving the schedule
+  // and the plane weights stay warp-uniform (uniform registers): fewer instructions, a dozen fewer live vector registers
+  int4* sched_s = reinterpret_cast<int4*>(smem_gen + (((tmem_slot + 8u - smem_base) + 15u) & ~15u));
 
   if (tid == 0) {
     for (int s = 0; s < SA; ++s)
@@ -211,7 +215,6 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-  int Emin = 0;
   if constexpr (BFP) {
     // V^T holds V * 2^(e_J) per 128-node block J.  The blocks are aligned to the smallest exponent E inside the A operand (its
     // plane weights are multiplied by 2^(E - e_J) <= 1, exact), so every accumulator ends up scaled by 2^E times the A scale.
@@ -225,8 +228,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       if (lane == 0) emin_s = e;
     }
     __syncthreads();
-    Emin = emin_s;
-    for (int J = tid; J < nblk; J += TC_THREADS) fblk_s[J] = exp2_int(max(Emin - ve[J], -120));
+    for (int J = tid; J < nblk; J += TC_THREADS) fblk_s[J] = exp2_int(max(emin_s - ve[J], -120));
     __syncthreads();
   }
   const StageScalars* scp = a.sc + b;
@@ -255,16 +257,17 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   // adjoint: direct items (A V, A' V) enter the output with (gamma, delta), transposed items (A^T V, A'^T V) with (alpha, beta)
   const LightCoef lc_d = light_coef(gamma, delta), lc_t = light_coef(alpha, beta);
   // BFP: power-of-two scale of every A-operand variant from the bound sum_q |w_q| max|plane_q| >= max |combined tile entry|
-  // (forward: ONE accumulator takes the direct X items and the transposed Y items, so both share the larger bound)
-  float ascale[NA], descale[NA];
-#pragma unroll
-  for (int v = 0; v < NA; ++v) { ascale[v] = 1.f; descale[v] = 1.f; }
-  if constexpr (BFP) {
-    float bound[NA];
+  // (forward: ONE accumulator takes the direct X items and the transposed Y items, so both share the larger bound).
+  // Evaluated twice -- by the converters for their weights and again by the epilogue for the inverse -- rather than kept in
+  // registers across the conversion loop (every live register there is a spill at the 96 registers 18 warps allow, and with the
+  // whole L1 carved out as shared memory a spill is an L2 round trip on the converters' critical path).
+  auto a_scale_exponent = [&](int v) -> int {
+    if constexpr (!BFP) return 0;
     const float* am = scp->amax;
+    float bound;
     if (BWD) {
-      bound[0] = fabsf(sc.wA[0]) * am[0] + fabsf(sc.wA[1]) * am[1] + fabsf(sc.wA[2]) * am[2] + fabsf(sc.wA[3]) * am[3];
-      bound[NA - 1] = fabsf(sc.wD[1]) * am[1] + fabsf(sc.wD[2]) * am[2] + fabsf(sc.wD[3]) * am[3];
+      bound = v == 0 ? fabsf(sc.wA[0]) * am[0] + fabsf(sc.wA[1]) * am[1] + fabsf(sc.wA[2]) * am[2] + fabsf(sc.wA[3]) * am[3]
+                     : fabsf(sc.wD[1]) * am[1] + fabsf(sc.wD[2]) * am[2] + fabsf(sc.wD[3]) * am[3];
     } else {
       float bx = 0.f, by = 0.f;
 #pragma unroll
@@ -272,16 +275,20 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         bx += fabsf(alpha * sc.wA[q] + beta * sc.wD[q]) * am[q];
         by += fabsf(gamma * sc.wA[q] + delta * sc.wD[q]) * am[q];
       }
-      bound[0] = fmaxf(bx, by);
+      bound = fmaxf(bx, by);
     }
-#pragma unroll
-    for (int v = 0; v < NA; ++v) {
-      const int e = block_exponent(bound[v]);
-      ascale[v] = exp2_int(e);
-      descale[v] = exp2_int(-e) * exp2_int(-Emin);     // |e|, |Emin| <= 60: both factors are normal numbers
-    }
-  }
+    return block_exponent(bound);
+  };
 
+  if constexpr (F16) {
+    const float as0 = BFP ? exp2_int(a_scale_exponent(0)) : 1.f, as1 = (BFP && BWD) ? exp2_int(a_scale_exponent(NA - 1)) : 1.f;
+    for (int pr = tid; pr < npairs; pr += TC_THREADS) {
+      const int kc = kc_of(pr0 + pr);
+      const float f = BFP ? fblk_s[kc >> 2] : 1.f;
+      sched_s[pr] = make_int4(kc, (int)__float_as_uint(f * as0), (int)__float_as_uint(f * as1), 0);
+    }
+    __syncthreads();
+  }
   if (warp < 16) {
     // =========================== converters ===========================
     const int grp = warp >> 3, w8 = warp & 7;   // group 0: direct items (even j); group 1: transposed items (odd j)
@@ -322,6 +329,18 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     auto load_tile = [&](int rt, int ct, int half) {
       constexpr int ME = PEG_TC_BWD_HALF_EARLY > 0 ? PEG_TC_BWD_HALF_EARLY : 2;
       const int m0 = half == 1 ? ME : 0, m1 = half == 0 ? ME : 4;
+      if constexpr (F16) {
+        // row tiles beyond the padded matrix (last 128-row block of a ragged n: 4 I + u >= nt, a per-warp, loop-invariant condition)
+        // are read from row tile 0 and their weights are zero: no zero-fill path, the loads stay unconditional
+        const float* base = P + ((size_t)rt * nt + ct) * 4096 + cv_off;
+        const float* base_even = base + sw * 128;
+        const float* base_odd = base - sw * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int m = 0; m < 4; ++m) buf[q * 4 + m] = ldg_stream(((m & 1) ? base_odd : base_even) + (q * 4 + m) * 128);
+        return;
+      }
       if (rt < nt && ct < nt) {
         const float* base = P + ((size_t)rt * nt + ct) * 4096 + cv_off;
         const float* base_even = base + sw * 128;   // register row m <- tile row m ^ sw: even m read one row up, odd m one row down
@@ -340,10 +359,12 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       }
     };
     // item j -> its plane tile: direct = rows of block I x chunk kc, transposed = chunk kc x columns of block I
+    const bool tile_ok = 4 * I + cv_u < nt;            // this warp's 32-row (direct) / 32-column (transposed) strip exists
+    const int my_tile = tile_ok ? 4 * I + cv_u : 0;
     auto load_item = [&](int j, int half) {
-      const int kc = kc_of(pr0 + (j >> 1));
-      if ((j & 1) == 0) load_tile(4 * I + cv_u, kc, half);
-      else load_tile(kc, 4 * I + cv_u, half);
+      const int kc = F16 ? sched_s[j >> 1].x : kc_of(pr0 + (j >> 1));
+      if ((j & 1) == 0) load_tile(F16 ? my_tile : 4 * I + cv_u, kc, half);
+      else load_tile(kc, F16 ? my_tile : 4 * I + cv_u, half);
     };
     // store 4 consecutive k (k = 4 * chunk .. 4 * chunk + 3) of operand row r as hi (+ lo) parts into the swizzled K-major tile:
     // tf32: one 16-byte chunk of a 128-byte row (SWIZZLE_128B); bf16x2: 8 bytes of a 64-byte row (SWIZZLE_64B: 16-byte chunk
@@ -438,39 +459,57 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     };
     // BFP: the launch-wide A scale rides in the (warp-uniform) weights; the per-item block alignment 2^(E - e_J) is one extra
     // multiply per value (a power of two: exact) -- keeping it out of the weights keeps them in uniform registers
-    if constexpr (BFP) {
+    float fitem[NA];   // BFP: (A scale of variant v) * 2^(E - e_J) of the current item
 #pragma unroll
-      for (int v = 0; v < NA; ++v)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) w[v][q] *= ascale[v];
-    }
-    float fitem = 1.f;
-    auto put16 = [&](uint32_t addr, float x0, float x1, float x2, float x3) {
-      uint32_t h01, l01, h23, l23;
-      split16(x0, x1, h01, l01);
-      split16(x2, x3, h23, l23);
-      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(h01), "r"(h23) : "memory");
-      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr + ATILE), "r"(l01), "r"(l23) : "memory");
-    };
+    for (int v = 0; v < NA; ++v) fitem[v] = 1.f;
     auto comb = [&](int v, float e0, float e1, float e2, float e3) -> float {
       float r;
       if (BWD && v == NA - 1) r = w[v][1] * e1 + w[v][2] * e2 + w[v][3] * e3;    // A'_s has no `a` term (wD[0] == 0)
       else r = w[v][0] * e0 + w[v][1] * e1 + w[v][2] * e2 + w[v][3] * e3;
-      return BFP ? r * fitem : r;
+      return BFP ? r * fitem[v] : r;
+    };
+    // slot / phase of this group's current item, advanced incrementally (SA is a run-time value: no division per item)
+    int cur_st = grp % SA;
+    uint32_t cur_ph = 0u;
+    auto sts2 = [&](uint32_t addr, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory"); };
+    // A warp whose 32-row / 32-column strip lies beyond the padded matrix (last 128-row block of a ragged n) converts nothing: it
+    // zeroes its rows of each A slot the first time its group uses the slot (a slot is only ever written by one group) and then
+    // just keeps the barrier protocol going.  This keeps the plane weights of every working warp warp-uniform (uniform registers).
+    auto idle16 = [&](int j) {
+      mbar_wait(empty_a(cur_st, 0), cur_ph ^ 1u);
+      if (j < SA) {
+        const uint32_t a_base = smem_base + cur_st * a_bytes;
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int t = 0; t < 2 * NA; ++t) asm volatile("st.shared.v2.b32 [%0], {%1, %1};" ::"r"(a_base + o_m[m] + t * ATILE), "r"(0u) : "memory");
+      }
+      fence_proxy_async();
+      mbar_arrive(full_a(cur_st, 0));
+      cur_st += 2;
+      if (cur_st >= SA) { cur_st -= SA; cur_ph ^= 1u; }
     };
     auto convert16 = [&](int j, bool transposed) {
-      const int st = j % SA;
-      const uint32_t a_base = smem_base + st * a_bytes;
-      if constexpr (BFP) fitem = fblk_s[kc_of(pr0 + (j >> 1)) >> 2];
-      mbar_wait(empty_a(st, 0), ((uint32_t)(j / SA) & 1u) ^ 1u);   // the MMAs that read this slot's previous contents have completed
+      if constexpr (BFP) {
+        const int4 e = sched_s[j >> 1];
+        fitem[0] = __uint_as_float((uint32_t)e.y);
+        if (NA > 1) fitem[NA - 1] = __uint_as_float((uint32_t)e.z);
+      }
+      const uint32_t a_base = smem_base + cur_st * a_bytes;
+      mbar_wait(empty_a(cur_st, 0), cur_ph ^ 1u);   // the MMAs that read this slot's previous contents have completed
       if (!transposed) {
 #pragma unroll
         for (int m = 0; m < 4; ++m) {   // operand row = tile row, the four k values are the columns 4 cq .. 4 cq + 3
           const float4 e0 = buf[0 * 4 + m], e1 = buf[1 * 4 + m], e2 = buf[2 * 4 + m], e3 = buf[3 * 4 + m];
+          const uint32_t addr = a_base + o_m[m];
 #pragma unroll
-          for (int v = 0; v < NA; ++v)
-            put16(a_base + v * 2 * ATILE + o_m[m], comb(v, e0.x, e1.x, e2.x, e3.x), comb(v, e0.y, e1.y, e2.y, e3.y),
-                  comb(v, e0.z, e1.z, e2.z, e3.z), comb(v, e0.w, e1.w, e2.w, e3.w));
+          for (int v = 0; v < NA; ++v) {
+            uint32_t h01, l01, h23, l23;
+            split16(comb(v, e0.x, e1.x, e2.x, e3.x), comb(v, e0.y, e1.y, e2.y, e3.y), h01, l01);
+            split16(comb(v, e0.z, e1.z, e2.z, e3.z), comb(v, e0.w, e1.w, e2.w, e3.w), h23, l23);
+            sts2(addr + v * 2 * ATILE, h01, h23);
+            sts2(addr + v * 2 * ATILE + ATILE, l01, l23);
+          }
         }
       } else {
         // operand row = tile column 4 cq + e, the four k values are the tile rows 4 rq + m: rows (0,1) and (2,3) are packed as they
@@ -489,25 +528,33 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
           }
         }
 #pragma unroll
-        for (int v = 0; v < NA; ++v)
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t addr = a_base + o_m[e];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const uint32_t addr = a_base + v * 2 * ATILE + o_m[e];
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(ph[v][e][0]), "r"(ph[v][e][1]) : "memory");
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr + ATILE), "r"(pl[v][e][0]), "r"(pl[v][e][1]) : "memory");
+          for (int v = 0; v < NA; ++v) {
+            sts2(addr + v * 2 * ATILE, ph[v][e][0], ph[v][e][1]);
+            sts2(addr + v * 2 * ATILE + ATILE, pl[v][e][0], pl[v][e][1]);
           }
+        }
       }
       fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(full_a(st, 0));
+      mbar_arrive(full_a(cur_st, 0));
+      cur_st += 2;               // this group's next item is j + 2
+      if (cur_st >= SA) { cur_st -= SA; cur_ph ^= 1u; }
       if (j + 2 < items) load_item(j + 2, 2);
     };
 
-    if (items > 0) load_item(grp, 2);   // group 0: direct items (even j); group 1: transposed items (odd j)
     if constexpr (F16) {
       static_assert(!F16 || PEG_TC_VARIANT_SLOTS == 0, "per-variant slot barriers exist for the 3xTF32 format only");
-      if (grp == 0) for (int j = 0; j < items; j += 2) convert16(j, false);
-      else          for (int j = 1; j < items; j += 2) convert16(j, true);
+      if (!tile_ok) {
+        for (int j = grp; j < items; j += 2) idle16(j);
+      } else {
+        if (items > 0) load_item(grp, 2);   // group 0: direct items (even j); group 1: transposed items (odd j)
+        if (grp == 0) for (int j = 0; j < items; j += 2) convert16(j, false);
+        else          for (int j = 1; j < items; j += 2) convert16(j, true);
+      }
     } else {
+      if (items > 0) load_item(grp, 2);
       if (grp == 0) for (int j = 0; j < items; j += 2) convert(j, false);
       else          for (int j = 1; j < items; j += 2) convert(j, true);
     }
@@ -648,13 +695,15 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         }
         tmem_wait_ld();
         if constexpr (BFP) {   // undo the block scales (powers of two: exact); accumulator acc = type * 2 + v carries the scale of variant v
+          // |exponents| <= 60: both factors are normal numbers
+          const float d0 = exp2_int(-a_scale_exponent(0)) * exp2_int(-emin_s), d1 = BWD ? exp2_int(-a_scale_exponent(NA - 1)) * exp2_int(-emin_s) : 1.f;
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
-            r0[u] = __float_as_uint(__uint_as_float(r0[u]) * descale[0]);
+            r0[u] = __float_as_uint(__uint_as_float(r0[u]) * d0);
             if (BWD) {
-              r1[u] = __float_as_uint(__uint_as_float(r1[u]) * descale[NA - 1]);
-              r2[u] = __float_as_uint(__uint_as_float(r2[u]) * descale[0]);
-              r3[u] = __float_as_uint(__uint_as_float(r3[u]) * descale[NA - 1]);
+              r1[u] = __float_as_uint(__uint_as_float(r1[u]) * d1);
+              r2[u] = __float_as_uint(__uint_as_float(r2[u]) * d0);
+              r3[u] = __float_as_uint(__uint_as_float(r3[u]) * d1);
             }
           }
         }
@@ -988,7 +1037,8 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   p.vexp = w.vexp;
   p.vexp_stride = w.vexp_stride;
   const int nv = PEG_TC_VARIANT_SLOTS ? na : 1;   // barrier pairs per A slot (see the kernel)
-  const size_t smem = (size_t)sa * a_bytes + (size_t)sb * b_bytes + 1024 + 8 * (2 * sa * nv + 2 * sb + 2) + 64;
+  const size_t sched_bytes = f16 ? (size_t)16 * p.nkc + 16 : 0;   // chunk-schedule table of the 16-bit formats (at most nkc pairs per CTA)
+  const size_t smem = (size_t)sa * a_bytes + (size_t)sb * b_bytes + 1024 + 8 * (2 * sa * nv + 2 * sb + 2) + 64 + sched_bytes;
 
   const CUtensorMap* mhi_p = nullptr;
   const CUtensorMap* mlo_p = nullptr;

@@ -835,6 +835,7 @@ def test_benchmarked_instantiations_one_evaluation_and_vjp(cuda, n, h, e, B, fla
     (dy * torch.stack([p.gyT for p in ps]).to(cuda)).sum().backward()
     got = product_grads_as_oracle(vf)
     layers = R.params_to(R.params_to(ps[0].layers, torch.float64), requires_grad=True)
+    flipped = 0
     for b, p in enumerate(ps):
         p64 = R.problem_to(p, torch.float64)
         q = R.Problem(p64.n, p64.h, p64.e, p64.L, p64.ts, p64.coeffs_adj, p64.x_coeffs, p64.y0, layers, p64.step_ts, p64.gyT)
@@ -849,9 +850,13 @@ def test_benchmarked_instantiations_one_evaluation_and_vjp(cuda, n, h, e, B, fla
         assert float(err.flatten().median()) < 5e-6 and float(err.flatten().quantile(0.9)) < 5e-5, b
         assert bad_rows <= 0.15 * n, (b, bad_rows)
         assert _rel_l2(y.grad[b], y64.grad) < 2e-2, b
+        flipped += bad_rows
+    worst = max(rel_err(g, r.grad) for g_l, lp in zip(got, layers) for g, r in zip(g_l, lp.tensors()))
+    print(f"[n={n} h={h} e={e}] parameter gradients, worst leaf: {worst:.1e} (rows touched by ReLU flips: {flipped})")
+    tol_p = 3e-4 if flipped == 0 else 5e-3      # a flipped unit also moves the gradients of the layers below it
     for l, (g_l, lp) in enumerate(zip(got, layers)):
         for name, g, r in zip(("fusion", "W", "b", "nw", "nb"), g_l, lp.tensors()):
-            assert rel_err(g, r.grad) < 3e-4, (l, name)
+            assert rel_err(g, r.grad) < tol_p, (l, name)
 
 
 @pytest.mark.parametrize("flags", OPERAND_FORMATS)
