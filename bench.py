@@ -30,6 +30,10 @@ WORKLOADS = {
     "twitter": dict(n=1000, h=64, e=16, L=3, T=9, t1=8.0, dt0=0.1, B=1),
     # graphs per GPU are chosen so that (row blocks of 128) x B is just under a multiple of the 148 SMs
     "sweep_n1024_h64": dict(n=1024, h=64, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=18),
+    "sweep_n1024_h256": dict(n=1024, h=256, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=18),
+    "sweep_n1024_h128_e8": dict(n=1024, h=128, e=8, L=3, T=9, t1=8.0, dt0=0.1, B=18),
+    "sweep_n4096_h64": dict(n=4096, h=64, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=9),
+    "sweep_n16384_h64": dict(n=16384, h=64, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=1),
     "sweep_n2048_h64": dict(n=2048, h=64, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=9),
     "sweep_n2048_h128": dict(n=2048, h=128, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=9),
     "sweep_n4096_h128": dict(n=4096, h=128, e=0, L=3, T=9, t1=8.0, dt0=0.1, B=9),
@@ -116,7 +120,7 @@ def synth_adjacency(n, T, seed, device):
     return out
 
 
-def make_inputs(wl, seed, device, host_copy):
+def make_inputs(wl, seed, device, host_copy, coeff_budget=None):
     """Inputs of one rank.  Reference layout: ts [T], coeffs_adj (d,c,b,a) each [B,T-1,n,n,2], x_coeffs, y0, cotangent -- plus the
     graph snapshots A_k [B,T,n,n] they were built from.  The reference-layout arrays are 32 n^2 (T-1) bytes per graph; past
     COEFF_BUDGET bytes (n = 16384: 69 GB) only the snapshots are kept and the control path is built on the device
@@ -126,7 +130,7 @@ def make_inputs(wl, seed, device, host_copy):
     n, h, e, T, B = wl["n"], wl["h"], wl["e"], wl["T"], wl["B"]
     ts = torch.linspace(0.0, wl["t1"], T, device=device) if wl.get("float_ts") else torch.arange(T, device=device, dtype=torch.float32) * (wl["t1"] / (T - 1))
     coeff_bytes = 4 * B * (T - 1) * n * n * 2 * 4
-    with_coeffs = coeff_bytes <= COEFF_BUDGET
+    with_coeffs = coeff_bytes <= (COEFF_BUDGET if coeff_budget is None else coeff_budget)
     cadj = [torch.empty((B, T - 1, n, n, 2), device=device) for _ in range(4)] if with_coeffs else None
     snaps_dev = None if with_coeffs else torch.empty((B, T, n, n), device=device)
     snaps = torch.empty((B, T, n, n), dtype=torch.float32).pin_memory() if host_copy else None
@@ -161,23 +165,59 @@ def make_inputs(wl, seed, device, host_copy):
 COEFF_BUDGET = 40e9
 
 
-def run_ours(args):
-    import perm_equiv_graph_neural_cdes_b200 as P
+def tensor_peaks(dev):
+    """Dense GEMM throughput of cuBLAS on this GPU, measured live (8192^3, best of 5 after warm-up): tf32 (fp32 inputs with
+    allow_tf32) and fp16 / bf16 -- the denominators of the executed-tensor-work fractions reported beside the HBM roofline."""
+    out = {}
+    N = 8192
+    for name, dt, tf in (("tf32", torch.float32, True), ("fp16", torch.float16, False), ("bf16", torch.bfloat16, False)):
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf
+        a = torch.randn((N, N), device=dev, dtype=dt)
+        b = torch.randn((N, N), device=dev, dtype=dt)
+        c = torch.empty((N, N), device=dev, dtype=dt)
+        for _ in range(2):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        out[name] = 2.0 * N ** 3 / (best * 1e-3) / 1e12
+        torch.backends.cuda.matmul.allow_tf32 = prev
+        del a, b, c
+    torch.cuda.empty_cache()
+    return out
+
+
+class Dist:
+    """Rank bookkeeping of one bench process (torchrun env: RANK / LOCAL_RANK / WORLD_SIZE)."""
+
+    def __init__(self):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            torch.distributed.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def max_ms(self, ms):
+        t = torch.tensor([ms], device=self.dev)
+        if self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+
+def operand_flags(args):
     from perm_equiv_graph_neural_cdes_b200 import _lib
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=dev)
-    wl = dict(WORKLOADS[args.workload])
-    if args.batch:
-        wl["B"] = args.batch
-    if args.t1 > 0:
-        wl["t1_solve"] = args.t1
-    n, h, e, L, T, B = wl["n"], wl["h"], wl["e"], wl["L"], wl["T"], wl["B"]
     flags = 0 if args.no_tensor_cores else _lib.PEG_FLAG_TENSOR_CORES
     if args.tf32_fast:
         flags |= _lib.PEG_FLAG_TF32_FAST
@@ -185,12 +225,23 @@ def run_ours(args):
         flags |= _lib.PEG_FLAG_TF32X3
     elif args.operands == "bf16x2":
         flags |= _lib.PEG_FLAG_BF16X2
+    return flags
 
+
+def measure_fixed(D, wl_name, wl, args, steps, warmup, with_e2e, tpeaks, e2e_steps, coeff_budget=None):
+    """One fixed-step workload on this rank's GPU: device-resident value (CUDA-graph replay), the roofline of the contraction
+    launches, and (optionally) the end-to-end legs from pinned host buffers.  Returns a dict (rank-local; times are max over ranks)."""
+    import perm_equiv_graph_neural_cdes_b200 as P
+    from perm_equiv_graph_neural_cdes_b200 import _lib
+    from perm_equiv_graph_neural_cdes_b200 import dist as pdist
+
+    dev, world, rank = D.dev, D.world, D.rank
+    n, h, e, L, T, B = wl["n"], wl["h"], wl["e"], wl["L"], wl["T"], wl["B"]
+    flags = operand_flags(args)
     widths_out = 2 * h * e if e > 0 else h
-    vf = P.PermEquivGraphVectorField(h, h, widths_out, L, e, n, key=1234).to(dev)
-    vf.flags = flags
+    vf = P.PermEquivGraphVectorField(h, h, widths_out, L, e, n, key=1234, flags=flags).to(dev)
     term = P.ODETerm(P.CDEWrapperVectorField(vf, h) if e > 0 else vf)
-    ts, cadj, xco, y0, gy, host, snaps_dev, x_t = make_inputs(wl, 1234 + rank, dev, host_copy=True)
+    ts, cadj, xco, y0, gy, host, snaps_dev, x_t = make_inputs(wl, 1234 + rank, dev, host_copy=with_e2e, coeff_budget=coeff_budget)
     pc = P.pack_control(ts, cadj, xco) if cadj is not None else P.build_control(ts, snaps_dev, x_t)
     torch.cuda.synchronize()
     del cadj, xco, snaps_dev
@@ -199,6 +250,7 @@ def run_ours(args):
     step_ts = P.constant_step_table(0.0, t1_solve, wl["dt0"])
     S = len(step_ts) - 1
     l = _lib.lib()
+    params = list(vf.parameters())
 
     def solve_step(pc_, y0_, reduce=True):
         vf.zero_grad(set_to_none=True)
@@ -207,22 +259,13 @@ def run_ours(args):
                             stepsize_controller=P.ConstantStepSize(), saveat=P.SaveAt(t1=True))
         loss = (sol.ys[-1] * gy).sum()
         loss.backward()
-        flat_g = torch.cat([p.grad.reshape(-1) for p in vf.parameters()])
-        if world > 1 and reduce:
-            torch.distributed.all_reduce(flat_g)
-        return loss, flat_g
+        if reduce:   # ONE all-reduce of the flat parameter-gradient buffer (dist.allreduce_gradients; a no-op at world size 1)
+            return loss, pdist.allreduce_gradients(params)
+        return loss, torch.cat([p.grad.reshape(-1) for p in params])
 
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- device-resident leg: `value` ----------------
-    # The C-ABI only enqueues kernels, so one whole forward + adjoint solve is captured once into a CUDA graph and
-    # replayed: ~2.5k dependent launches per step are otherwise host-launch-bound for the smaller shapes.
-    for _ in range(max(args.warmup, 1)):
+    for _ in range(max(warmup, 1)):
         solve_step(pc, y0)
-    barrier()
+    D.barrier()
     graph = None
     l.pegncde_profile_enable(args.profile_stride)
     launches0 = l.pegncde_launch_count()
@@ -241,161 +284,250 @@ def run_ours(args):
         launches_per_step = l.pegncde_launch_count() - launches0
         for _ in range(2):
             graph.replay()
-        barrier()
+        D.barrier()
 
     def timed_step():
         if graph is not None:
             graph.replay()
             if world > 1:
                 torch.distributed.all_reduce(g_flat)
-        else:
-            solve_step(pc, y0)
+            return g_flat
+        return solve_step(pc, y0)[1]
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(D.local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     host_t0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
-        timed_step()
+    for _ in range(steps):
+        reduced = timed_step()
     e1.record()
-    host_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps
-    barrier()
+    host_ms = (time.perf_counter() - host_t0) * 1e3 / steps
+    D.barrier()
     clocks = sampler.summary()
     ms = e0.elapsed_time(e1)
+    # the reduced gradient buffer must be finite and identical on every rank
+    grad_check = {"finite": bool(torch.isfinite(reduced).all())}
+    if world > 1:
+        lo, hi = reduced.clone(), reduced.clone()
+        torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+        torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+        grad_check["identical_across_ranks"] = bool(torch.equal(lo, hi))
+    if not grad_check["finite"] or grad_check.get("identical_across_ranks") is False:
+        raise RuntimeError(f"{wl_name}: reduced parameter gradients failed the sanity check {grad_check}")
     if graph is None:
-        launches_per_step = (l.pegncde_launch_count() - launches0) // max(args.steps, 1)
-    launches = launches_per_step * args.steps
+        launches_per_step = (l.pegncde_launch_count() - launches0) // max(steps, 1)
     prof = {}
     for d, nm in ((0, "fwd"), (1, "bwd")):
         a, b_, c_, by, fl = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
         l.pegncde_profile_read(d, a, b_, c_, by, fl)
         prof[nm] = dict(launches=a.value, timed=b_.value, ms=c_.value, bytes=by.value, flops=fl.value)
     l.pegncde_profile_enable(0)
-    prof_steps = 1 if graph is not None else args.steps   # a replayed graph re-records the same event pairs
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
+    prof_steps = 1 if graph is not None else steps   # a replayed graph re-records the same event pairs
+    ms_per_step = D.max_ms(ms) / steps
     value = world * B * S / (ms_per_step * 1e-3)
+    res = {"workload": wl_name, "value": value, "ms_per_step": ms_per_step, "solver_steps": S, "graphs_per_gpu": B, "host_ms_per_step": host_ms,
+           "launches": int(launches_per_step * steps), "cuda_graph": graph is not None, "clocks": clocks, "grad_check": grad_check,
+           "n_params": int(sum(p.numel() for p in params)), "planes_mb": pc.adj_coef.numel() * 4 / 1e6}
 
-    # ---------------- end-to-end leg: host buffers through the public API ----------------
-    def e2e_step():
-        # host buffers go straight into the public API: pack_control keeps the (pinned) coefficient arrays on the host and the
-        # solve streams them piece by piece (copy + pack of piece i+1 overlap the steps inside piece i)
-        y0_d = host["y0"].to(dev, non_blocking=True)
-        pc_ = P.pack_control(host["ts"], host["cadj"], host["xco"], device=dev)
-        loss, flat_g = solve_step(pc_, y0_d)
-        return float(loss.item()), flat_g.cpu()
+    # ---------------- end-to-end legs: host buffers through the public API ----------------
+    if with_e2e:
+        d2h = res["n_params"] * 4 + 4
 
-    k_e2e = max(1, min(args.steps, args.e2e_steps))
-    e2e_val, h2d = None, None
-    if host["cadj"] is not None:
-        h2d = sum(c.numel() * 4 for c in host["cadj"]) + host["y0"].numel() * 4 + host["ts"].numel() * 4
-        if host["xco"] is not None:
-            h2d += sum(c.numel() * 4 for c in host["xco"])
-        e2e_step()
-        barrier()
-        e0.record()
-        for _ in range(k_e2e):
-            e2e_step()
-        e1.record()
-        barrier()
-        t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            torch.distributed.all_reduce(t2, op=torch.distributed.ReduceOp.MAX)
-        e2e_val = world * B * S / (float(t2.item()) / k_e2e * 1e-3)
-    d2h = vf.flat_params().numel() * 4 + 4
+        def e2e_coeff_step():
+            # reference-layout coefficient arrays (pinned host memory) -> pack_control keeps them on the host and the solve
+            # streams them piece by piece (copy + pack of piece i+1 overlap the steps inside piece i)
+            y0_d = host["y0"].to(dev, non_blocking=True)
+            pc_ = P.pack_control(host["ts"], host["cadj"], host["xco"], device=dev)
+            loss, flat_g = solve_step(pc_, y0_d)
+            return float(loss.item()), flat_g.cpu()
 
-    # same end-to-end step, but entering one stage earlier: the host ships the graph SNAPSHOTS A_k [B,T,n,n] and
-    # the control path (Hermite coefficients + tiling) is built on the device by pegncde_build_adj
-    def e2e_snap_step():
-        ts_d = host["ts"].to(dev, non_blocking=True)
-        A_d = host["snaps"].to(dev, non_blocking=True)
-        x_d = None if host["x_t"] is None else host["x_t"].to(dev, non_blocking=True)
-        y0_d = host["y0"].to(dev, non_blocking=True)
-        pc_ = P.build_control(ts_d, A_d, x_d)
-        loss, flat_g = solve_step(pc_, y0_d)
-        return float(loss.item()), flat_g.cpu()
+        def e2e_snap_step():
+            # one stage earlier: graph SNAPSHOTS A_k [B,T,n,n] from the host; Hermite coefficients + tiling on the device
+            ts_d = host["ts"].to(dev, non_blocking=True)
+            A_d = host["snaps"].to(dev, non_blocking=True)
+            x_d = None if host["x_t"] is None else host["x_t"].to(dev, non_blocking=True)
+            y0_d = host["y0"].to(dev, non_blocking=True)
+            pc_ = P.build_control(ts_d, A_d, x_d)
+            loss, flat_g = solve_step(pc_, y0_d)
+            return float(loss.item()), flat_g.cpu()
 
-    e2e_snap_step()
-    barrier()
-    e0.record()
-    for _ in range(k_e2e):
-        e2e_snap_step()
-    e1.record()
-    barrier()
-    t3 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(t3, op=torch.distributed.ReduceOp.MAX)
-    e2e_snap_val = world * B * S / (float(t3.item()) / k_e2e * 1e-3)
-    h2d_snap = host["snaps"].numel() * 4 + host["y0"].numel() * 4 + host["ts"].numel() * 4 + (0 if host["x_t"] is None else host["x_t"].numel() * 4)
+        def time_leg(fn):
+            fn()
+            D.barrier()
+            e0.record()
+            for _ in range(e2e_steps):
+                fn()
+            e1.record()
+            D.barrier()
+            return world * B * S / (D.max_ms(e0.elapsed_time(e1)) / e2e_steps * 1e-3)
+
+        base_h2d = host["y0"].numel() * 4 + host["ts"].numel() * 4
+        legs = {}
+        if host["cadj"] is not None:
+            h2d = base_h2d + sum(c.numel() * 4 for c in host["cadj"]) + (sum(c.numel() * 4 for c in host["xco"]) if host["xco"] is not None else 0)
+            legs["coefficients"] = {"value": time_leg(e2e_coeff_step), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                                    "input": "reference-layout coefficient arrays (d,c,b,a) [B,T-1,n,n,2] in pinned host memory -> pack_control / diffeqsolve (streamed: copy + pack of cubic piece i+1 overlap the steps inside piece i)"}
+        h2d_snap = base_h2d + host["snaps"].numel() * 4 + (0 if host["x_t"] is None else host["x_t"].numel() * 4)
+        legs["snapshots"] = {"value": time_leg(e2e_snap_step), "unit": UNIT, "h2d_bytes_per_step": h2d_snap, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                             "input": "graph snapshots A_k [B,T,n,n] in pinned host memory -> build_control (pegncde_build_adj: Hermite coefficients + tiling on the device) / diffeqsolve"}
+        res["e2e_legs"] = legs
 
     # ---------------- roofline of the dominant kernel (the n x n x d contraction) ----------------
     pk = peaks()
     tot_ms = prof["fwd"]["ms"] + prof["bwd"]["ms"]
     tot_timed = prof["fwd"]["timed"] + prof["bwd"]["timed"]
-    roof = None
     if tot_timed:
         by = (prof["fwd"]["bytes"] * prof["fwd"]["timed"] + prof["bwd"]["bytes"] * prof["bwd"]["timed"])
         fl = (prof["fwd"]["flops"] * prof["fwd"]["timed"] + prof["bwd"]["flops"] * prof["bwd"]["timed"])
         gbs = by / (tot_ms * 1e-3) / 1e9
         tfs = fl / (tot_ms * 1e-3) / 1e12
-        # The planes stream from HBM once per launch; the tensor pipe executes `passes` tf32 MMAs per algorithmic product
-        # (3xTF32 split = fp32 parity; 1 with --tf32-fast).  tf32 dense peak ~ 1/2 of the measured bf16 peak.
-        tf32_peak = pk["bf16"] / 2.0
-        passes = 1 if (flags & 2) or not (flags & 1) else 3
-        # the opt-in LIGHT adjoint (PEG_TC_ADJ_LIGHT=1) runs two of its four products single-pass: 8 MMA passes instead of 12
-        bwd_passes = 2.0 if (passes == 3 and os.environ.get("PEG_TC_ADJ_LIGHT")) else passes
-        exec_tfs = (passes * prof["fwd"]["flops"] * prof["fwd"]["timed"] + bwd_passes * prof["bwd"]["flops"] * prof["bwd"]["timed"]) / (tot_ms * 1e-3) / 1e12
-        # the bound is decided by ALGORITHMIC intensity (flops / bytes against the tf32 ridge); the executed tensor work
-        # (passes x) is reported beside it: with 3xTF32 the adjoint (four products) is co-limited by the tensor pipe
-        t_hbm, t_tc = by / (pk["hbm"] * 1e9), fl / (tf32_peak * 1e12)
+        # The planes stream from HBM once per launch; the tensor pipe executes `passes` MMAs per algorithmic product (x = hi + lo
+        # split of both operands: hi*hi + lo*hi + hi*lo; 1 with --tf32-fast).  The tensor peak is the cuBLAS GEMM rate of the
+        # operand type, measured in this run (tensor_peaks).
+        use_tc = bool(flags & 1)
+        passes = 1 if (flags & 2) or not use_tc else 3
+        fmt = "fp32 FFMA" if not use_tc else ("tf32" if flags & (2 | 8 | 16) else ("bf16" if flags & 32 else "fp16"))
+        tpeak = tpeaks.get(fmt) if tpeaks else None
+        if tpeak is None:
+            tpeak = pk["bf16"] / 2.0 if fmt == "tf32" else pk["bf16"]
+        exec_tfs = passes * tfs
+        t_hbm, t_tc = by / (pk["hbm"] * 1e9), passes * fl / (tpeak * 1e12)
         bound = "hbm" if t_hbm >= t_tc else "tensor"
         share = tot_ms * (prof["fwd"]["launches"] + prof["bwd"]["launches"]) / max(tot_timed, 1) / (ms_per_step * prof_steps)
-        roof = {"bound": bound, "kernel": "k_tc_contract<fwd> + k_tc_contract<adjoint> (the n x n x d contraction)" if flags & 1 else "k_dual_contract (FFMA)",
-                "achieved": gbs if bound == "hbm" else tfs, "peak": pk["hbm"] if bound == "hbm" else tf32_peak,
-                "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": (gbs / pk["hbm"]) if bound == "hbm" else (tfs / tf32_peak),
-                "peak_source": pk["src"] + (" hbm_gbs" if bound == "hbm" else " bf16_tflops_sustained/2 (tf32)"),
-                "traffic": measured_traffic(args.workload), "achieved_gbs": gbs, "achieved_tflops": tfs,
-                "tensor_passes": passes, "adjoint_tensor_passes": bwd_passes, "executed_tflops": exec_tfs, "executed_tensor_frac": exec_tfs / tf32_peak,
-                "fwd_executed_tensor_frac": passes * prof["fwd"]["flops"] * prof["fwd"]["timed"] / max(prof["fwd"]["ms"], 1e-9) / 1e9 / tf32_peak,
-                "bwd_executed_tensor_frac": bwd_passes * prof["bwd"]["flops"] * prof["bwd"]["timed"] / max(prof["bwd"]["ms"], 1e-9) / 1e9 / tf32_peak,
-                "avg_launch_us": tot_ms / tot_timed * 1e3,
-                "launches_timed": tot_timed, "share_of_step": share,
-                "fwd_avg_us": prof["fwd"]["ms"] / max(prof["fwd"]["timed"], 1) * 1e3, "bwd_avg_us": prof["bwd"]["ms"] / max(prof["bwd"]["timed"], 1) * 1e3,
-                "fwd_gbs": prof["fwd"]["bytes"] * prof["fwd"]["timed"] / max(prof["fwd"]["ms"], 1e-9) / 1e6,
-                "bwd_gbs": prof["bwd"]["bytes"] * prof["bwd"]["timed"] / max(prof["bwd"]["ms"], 1e-9) / 1e6,
-                "algorithmic_bytes_per_launch": {"fwd": prof["fwd"]["bytes"], "adjoint": prof["bwd"]["bytes"]},
-                "algorithmic_flops_per_launch": {"fwd": prof["fwd"]["flops"], "adjoint": prof["bwd"]["flops"]},
-                "l2_note": "planes %s L2 (126 MB)" % ("fit in" if 16.0 * n * n * B <= 126e6 else "exceed")}
+        res["roofline"] = {
+            "bound": bound, "kernel": "k_tc_contract<fwd> + k_tc_contract<adjoint> (the n x n x d contraction)" if use_tc else "k_dual_contract (FFMA)",
+            "achieved": gbs if bound == "hbm" else exec_tfs, "peak": pk["hbm"] if bound == "hbm" else tpeak,
+            "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": (gbs / pk["hbm"]) if bound == "hbm" else (exec_tfs / tpeak),
+            "peak_source": pk["src"] + " hbm_gbs (MEASURED_PEAKS.json)" if bound == "hbm" else "cuBLAS %s GEMM 8192^3 measured in this run" % fmt,
+            "traffic": measured_traffic(wl_name), "achieved_gbs": gbs, "hbm_frac": gbs / pk["hbm"], "algorithmic_tflops": tfs,
+            "operand_format": fmt, "tensor_passes": passes, "executed_tflops": exec_tfs, "tensor_peak_tflops": tpeak, "executed_tensor_frac": exec_tfs / tpeak,
+            "avg_launch_us": tot_ms / tot_timed * 1e3, "launches_timed": tot_timed, "share_of_step": share,
+            "fwd_avg_us": prof["fwd"]["ms"] / max(prof["fwd"]["timed"], 1) * 1e3, "bwd_avg_us": prof["bwd"]["ms"] / max(prof["bwd"]["timed"], 1) * 1e3,
+            "fwd_gbs": prof["fwd"]["bytes"] * prof["fwd"]["timed"] / max(prof["fwd"]["ms"], 1e-9) / 1e6,
+            "bwd_gbs": prof["bwd"]["bytes"] * prof["bwd"]["timed"] / max(prof["bwd"]["ms"], 1e-9) / 1e6,
+            "algorithmic_bytes_per_launch": {"fwd": prof["fwd"]["bytes"], "adjoint": prof["bwd"]["bytes"]},
+            "algorithmic_flops_per_launch": {"fwd": prof["fwd"]["flops"], "adjoint": prof["bwd"]["flops"]},
+            "whole_step_gbs": (prof["fwd"]["bytes"] * prof["fwd"]["launches"] + prof["bwd"]["bytes"] * prof["bwd"]["launches"]) / prof_steps / (ms_per_step * 1e-3) / 1e9,
+            "l2_note": "planes %s L2 (126 MB)" % ("fit in" if 16.0 * n * n * B <= 126e6 else "exceed")}
+    else:
+        res["roofline"] = None
+    del pc, vf, graph
+    torch.cuda.empty_cache()
+    return res
+
+
+def measure_heat(D, args, steps, warmup):
+    """BASELINE.json configs[0]: the dynamical-systems default (perm_equiv_gncde_config.yaml): heat diffusion on n = 400 nodes, B = 4
+    trajectories, h = 16, L = 2, Tsit5 + PIDController(1e-3, 1e-6), dt0 = None, SaveAt(ts = ts) (dense output at the 20 knots),
+    forward + exact adjoint over the accepted steps.  value = attempted solver steps of all trajectories per second."""
+    import perm_equiv_graph_neural_cdes_b200 as P
+
+    dev = D.dev
+    n, h, L, T, B = 400, 16, 2, 20, 4
+    g = torch.Generator(device=dev).manual_seed(99 + D.rank)
+    ts = torch.linspace(0.0, 5.0, T, device=dev)
+    A = torch.stack([synth_adjacency(n, T, 700 + 10 * D.rank + b, dev) for b in range(B)])
+    vf = P.PermEquivGraphVectorField(h, h, h, L, 0, n, key=1234, flags=operand_flags(args)).to(dev)
+    pc = P.build_control(ts, A)
+    y0 = torch.randn((B, n, h), generator=g, device=dev)
+    params = list(vf.parameters())
+    from perm_equiv_graph_neural_cdes_b200 import dist as pdist
+
+    def step():
+        vf.zero_grad(set_to_none=True)
+        y = y0.detach().requires_grad_(True)
+        sol = P.diffeqsolve(P.ODETerm(vf), P.Tsit5(), 0.0, 5.0, None, y, pc, stepsize_controller=P.PIDController(rtol=1e-3, atol=1e-6), saveat=P.SaveAt(ts=ts))
+        sol.ys.square().mean().backward()
+        pdist.allreduce_gradients(params)
+        st = sol.stats["num_steps"]
+        return int(sum(st)) if isinstance(st, (list, tuple)) else int(st) * B
+
+    for _ in range(max(warmup, 1)):
+        attempted = step()
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        attempted = step()
+    e1.record()
+    D.barrier()
+    ms = D.max_ms(e0.elapsed_time(e1)) / steps
+    return {"workload": "heat (configs[0]: n=400, B=4, h=16, L=2, adaptive Tsit5 rtol 1e-3, SaveAt(ts))", "value": D.world * attempted / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step": ms, "attempted_solver_steps_per_gpu": attempted, "graphs_per_gpu": B,
+            "note": "adaptive path: per-trajectory step sequences, host-side controller (one scaled-error read-back per attempted step)"}
+
+
+def run_ours(args):
+    import perm_equiv_graph_neural_cdes_b200 as P  # noqa: F401  (raises if libpegncde.so is missing: no CPU fallback)
+
+    D = Dist()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["B"] = args.batch
+    if args.t1 > 0:
+        wl["t1_solve"] = args.t1
+    tpeaks = None if args.no_tensor_peaks else tensor_peaks(D.dev)
+    head = measure_fixed(D, args.workload, wl, args, args.steps, args.warmup, with_e2e=True, tpeaks=tpeaks,
+                         e2e_steps=max(1, min(args.steps, args.e2e_steps)))
+
+    # ---- the other points of BASELINE.json configs[4] (short solves: t1 = 0.5 -> 5 solver steps, T = 3 knots) and configs[0..3] ----
+    sweep, configs = [], []
+    if not args.no_sweep:
+        for name in SWEEP_POINTS:
+            w2 = dict(WORKLOADS[name], T=3, t1=2.0, t1_solve=0.5)
+            r = measure_fixed(D, name, w2, args, 2, 3, with_e2e=True, tpeaks=tpeaks, e2e_steps=1, coeff_budget=0)   # snapshots only
+            rf = r["roofline"] or {}
+            sweep.append({"workload": name, "n": w2["n"], "hidden": w2["h"], "data_embed_dim": w2["e"], "graphs_per_gpu": w2["B"], "solver_steps": r["solver_steps"],
+                          "value": r["value"], "unit": UNIT, "frac": rf.get("frac"), "bound": rf.get("bound"), "hbm_frac": rf.get("hbm_frac"),
+                          "executed_tensor_frac": rf.get("executed_tensor_frac"), "fwd_gbs": rf.get("fwd_gbs"), "bwd_gbs": rf.get("bwd_gbs"),
+                          "share_of_step": rf.get("share_of_step"), "e2e": r["e2e_legs"]["snapshots"]["value"],
+                          "e2e_input": "graph snapshots from pinned host memory", "note": "short solve: 3 knots, t1 = 0.5 (5 solver steps), 2 timed steps"})
+        for name in ("sir", "england", "twitter"):
+            r = measure_fixed(D, name, dict(WORKLOADS[name]), args, 3, 3, with_e2e=True, tpeaks=tpeaks, e2e_steps=1)
+            legs = r["e2e_legs"]
+            configs.append({"workload": name, "config": CONFIG_OF[name], "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "graphs_per_gpu": r["graphs_per_gpu"],
+                            "solver_steps": r["solver_steps"], "e2e": max(v["value"] for v in legs.values()), "cuda_graph": r["cuda_graph"],
+                            "frac": (r["roofline"] or {}).get("frac")})
+        heat = dict(measure_heat(D, args, 2, 1), config="configs[0]")
+        if D.rank == 0 and D.world == 1 and not args.no_cpu_baseline:
+            heat["cpu_baseline"] = cpu_baseline_heat()
+        configs.insert(0, heat)
 
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if D.rank == 0 and D.world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline(wl, args)
 
-    if rank == 0:
+    if D.rank == 0:
+        n, h, e, L, T, B = wl["n"], wl["h"], wl["e"], wl["L"], wl["T"], wl["B"]
+        flags = operand_flags(args)
+        legs = head["e2e_legs"]
+        best = max(legs, key=lambda k: legs[k]["value"])   # the headline end-to-end number is the faster public entry point; both are reported
+        fmt = (head["roofline"] or {}).get("operand_format", "fp32 FFMA")
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" + (" (contraction: 3xTF32 tcgen05, fp32 accumulate)" if flags & 1 and not flags & 2 else
-                               " (contraction: 1xTF32 tcgen05)" if flags & 2 else " (CUDA-core FFMA)"),
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": D.world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (n x n x d contraction on tcgen05: %s split operands, three products, fp32 accumulate)" % fmt if flags & 1 and not flags & 2 else
+                     ("f32 (contraction: 1xTF32 tcgen05)" if flags & 2 else "f32 (CUDA-core FFMA)"),
             "data": "synthetic",
             "config": {"workload": args.workload, "n": n, "hidden": h, "data_embed_dim": e, "layers": L, "knots": T,
-                       "solver": "Tsit5 fixed dt0=%g" % wl["dt0"], "solver_steps": S, "graphs_per_gpu": B,
-                       "parallelism": "batch of trajectories sharded over %d GPU(s); NCCL all-reduce of %d param grads" % (world, vf.flat_params().numel()),
-                       "l2": "inputs per GPU %.0f MB of coefficient planes (> L2 126 MB: %s)" % (pc.adj_coef.numel() * 4 / 1e6, pc.adj_coef.numel() * 4 > 126e6)},
-            "e2e": {"value": e2e_val if e2e_val is not None else e2e_snap_val, "unit": UNIT,
-                    "h2d_bytes_per_step": h2d if e2e_val is not None else h2d_snap, "d2h_bytes_per_step": d2h, "steps": k_e2e,
-                    "input": "reference-layout coefficient arrays (d,c,b,a) [B,T-1,n,n,2] in pinned host memory handed to pack_control / diffeqsolve; the solve streams them: copy + pack of cubic piece i+1 overlap the steps inside piece i" if e2e_val is not None else
-                             "graph snapshots A_k [B,T,n,n] from pinned host memory (the coefficient arrays of this workload exceed the 40 GB input budget)"},
-            "e2e_from_snapshots": {"value": e2e_snap_val, "unit": UNIT, "h2d_bytes_per_step": h2d_snap, "d2h_bytes_per_step": d2h, "steps": k_e2e,
-                                   "input": "graph snapshots A_k [B,T,n,n]; control path built on the device (pegncde_build_adj)"},
-            "gpu_launches": int(launches), "cuda_graph": graph is not None, "host_ms_per_step": host_ms, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+                       "solver": "Tsit5 fixed dt0=%g" % wl["dt0"], "solver_steps": head["solver_steps"], "graphs_per_gpu": B,
+                       "parallelism": "batch of trajectories sharded over %d GPU(s); NCCL all-reduce of %d param grads" % (D.world, head["n_params"]),
+                       "l2": "inputs per GPU %.0f MB of coefficient planes (> L2 126 MB: %s)" % (head["planes_mb"], head["planes_mb"] * 1e6 > 126e6)},
+            "e2e": dict(legs[best], entry=best),
+            "e2e_from_coefficients": legs.get("coefficients"), "e2e_from_snapshots": legs.get("snapshots"),
+            "gpu_launches": head["launches"], "cuda_graph": head["cuda_graph"], "host_ms_per_step": head["host_ms_per_step"], "clocks": head["clocks"],
+            "grad_check": head["grad_check"], "tensor_peaks_tflops": tpeaks, "roofline": head["roofline"], "cpu_baseline": cpu_base,
+            "sweep": sweep, "configs": configs,
         }
         print(json.dumps(line))
-    if world > 1:
+    if D.world > 1:
         torch.distributed.destroy_process_group()
+
+
+# points of BASELINE.json configs[4] reported in the `sweep` array of every run (n in {1k, 4k, 16k} x h in {64, 256} + the wide last layer)
+SWEEP_POINTS = ["sweep_n1024_h64", "sweep_n1024_h256", "sweep_n4096_h64", "sweep_n4096_h256", "sweep_n16384_h64", "sweep_n16384_h256", "sweep_n1024_h128_e8"]
+CONFIG_OF = {"sir": "configs[1] (SIR, n=100, B=50 per GPU)", "england": "configs[2] (PGT England shape, n=129)", "twitter": "configs[3] (PGT Twitter shape, n=1000, e=16)"}
 
 
 def cpu_problem(wl, seed, sample_steps):
@@ -427,6 +559,35 @@ def cpu_baseline(wl, args):
     v, dt = time_oracle(wl, sample_steps, 1, threads)
     return {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": "1 graph x %d solver steps fwd+bwd of the same workload shape, torch-CPU restatement (oracle), %.1f s" % (sample_steps, dt)}
+
+
+def cpu_baseline_heat():
+    """The heat configuration (configs[0]) on the host cores: ONE trajectory of the restated adaptive solve (oracle), forward + autograd
+    backward, timed once after a short warm-up; value = attempted solver steps per second."""
+    import numpy as np
+
+    from oracle import reference_path as R
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n, h, L, T = 400, 16, 2, 20
+    p = R.make_problem(n=n, h=h, e=0, L=L, T=T, t1=5.0, dt0=0.1, seed=99, float_ts=True, randomize_norm=False)
+
+    def run():
+        layers = R.params_to(p.layers, requires_grad=True)
+        y0 = p.y0.clone().requires_grad_(True)
+        ca = R.CubicInterpolation(p.ts, p.coeffs_adj)
+        f = lambda t, y: R.perm_equiv_vector_field(t, y, ca, layers)
+        ys, table, stats = R.tsit5_solve_adaptive(f, y0, float(p.ts[0]), float(p.ts[-1]), rtol=1e-3, atol=1e-6, dt0=None, save_ts=[float(t) for t in p.ts])
+        ys.square().mean().backward()
+        return int(stats["num_steps"])
+
+    run()
+    t0 = time.perf_counter()
+    attempts = run()
+    dt = time.perf_counter() - t0
+    return {"value": attempts / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "1 trajectory (n=400, h=16, L=2) adaptive fwd+bwd, torch-CPU restatement (oracle), %d attempted steps in %.1f s" % (attempts, dt)}
 
 
 def run_reference(args):
@@ -480,7 +641,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     ap.add_argument("--t1", type=float, default=0.0, help="profiling only: shorten the solve to [0, t1] (fewer solver steps)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the `sweep` / `configs` arrays (the other BASELINE.json configurations)")
+    ap.add_argument("--no-tensor-peaks", action="store_true", help="skip the live cuBLAS tf32 / fp16 / bf16 GEMM measurement")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "ours" and args.gpus > 1 and world == 1 and "RANK" not in os.environ:
+        # `python bench.py --gpus N` outside torchrun: launch the ranks ourselves (one per GPU, NCCL, loopback rendezvous)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if world > 1 and args.gpus not in (1, world):
+        raise SystemExit(f"--gpus {args.gpus} contradicts WORLD_SIZE={world}")
     if args.impl == "reference":
         run_reference(args)
     else:
