@@ -88,6 +88,30 @@ typedef struct PegDims {
 } PegDims;
 /* width of the last layer: h if e == 0 else 2*h*e (vector_field_configs.py:71) */
 
+/* Row-sharded mode (one graph too large for / spread over several GPUs).  Rank r of `world` holds the rows
+ * [row0, row0 + PegDims.n) of the n_glob x n_glob adjacency path -- and, to avoid a reduce-scatter, the same rows of its TRANSPOSE
+ * (adj_coef_t) -- plus the matching rows of every state / cotangent array.  RMSNorm -> Linear, the Runge-Kutta updates and the
+ * weight gradients are row-local; the only exchange step is per layer: the operand V^T of the n x n x d contraction (every rank
+ * needs all rows of V) and two d-vectors of column sums.  The library does that exchange itself over peer memory: the producer
+ * kernels write this rank's slice of V^T, k_shard_push copies it with 128-bit stores into every peer's buffer over NVLink and
+ * raises an epoch flag there, k_shard_wait spins on the local flags and adds the column-sum slots in rank order.  No NCCL on the
+ * data path; parameter gradients come out as per-rank partial sums (the caller all-reduces them like in batch-sharded mode).
+ * All pointer tables are HOST arrays of `world` (<= 8) device pointers to peer-visible (symmetric) buffers of identical layout.
+ * Restrictions: PEG_FLAG_TENSOR_CORES with fp16x2 or 3xTF32 operands, e == 0, undirected layer, PegDims.n a multiple of 128,
+ * fixed-step entry points (vf_fwd / vf_vjp / solve_fwd / solve_bwd).  Not capturable in a CUDA graph (epochs are launch arguments). */
+typedef struct PegShard {
+  int32_t rank, world;
+  int32_t n_glob;            /* global node count = world * PegDims.n                                                  */
+  int32_t row0;              /* first global row of this rank = rank * PegDims.n                                        */
+  const float* adj_coef_t;   /* [B, T-1, 4 * ldn * n_glob] tiled planes of rows [row0, row0 + n) of the TRANSPOSED path   */
+  void* const* vt_hi;        /* [world] -> [2][B * dmax * n_glob] V^T high parts, two epoch-parity halves (bytes: 4 * that) */
+  void* const* vt_lo;        /* [world] -> same, low parts                                                              */
+  int32_t* const* vexp;      /* [world] -> [2][B * n_glob / 128] block exponents (fp16x2 operands)                        */
+  float* const* colsum;      /* [world] -> [2][world][2][B * 2 * dmax] column-sum slots (two vectors per exchange)        */
+  uint32_t* const* flags;    /* [world] -> [world + 1] epoch counters (one per source rank) + an error word              */
+  uint32_t* epoch;           /* HOST counter of exchanges enqueued so far on this rank (in / out; same on every rank)     */
+} PegShard;
+
 /* Planar control path, built once per batch by pegncde_pack_adj / pegncde_pack_x.
  * Coefficient order everywhere is (a, b, c, d):  X(t) = a + s(b + s(c + s d)), s = t - ts[i]. */
 typedef struct PegControl {
@@ -106,6 +130,9 @@ typedef struct PegControl {
                               PEG_FLAG_DIRECTED, NULL otherwise                                     */
   const float* adj_absmax; /* [B, T-1, 4]       max |entry| of each plane (pegncde_adj_absmax): the range bound the fp16x2 operand
                               format scales the interpolated adjacency with; NULL = not available (3xTF32 operands are used) */
+  const PegShard* shard;   /* NULL = the whole graph lives on this GPU; otherwise row-sharded mode (see PegShard): every array
+                              above holds this rank's rows only (adj_coef: [B, T-1, 4 * ldn * n_glob]), adj_total / adj_absmax are
+                              already reduced over the ranks, adj_diag[i] = entry (row0 + i) of local row i                  */
 } PegControl;
 
 /* ---- parameter packing ---------------------------------------------------------------
@@ -142,6 +169,15 @@ int pegncde_adj_stats(peg_stream_t stream, const PegDims* dims, const float* adj
  * The time channel is implied (X_time(t) = t): tch_coef is written as (1, 0, 0). */
 int pegncde_build_adj(peg_stream_t stream, const PegDims* dims, const float* ts, const float* snapshots, float* adj_coef,
                       float* adj_rowsum, float* adj_diag, float* adj_total, float* tch_coef);
+/* Rectangular variant for row-sharded controls: snapshots [B, T, n, n_cols] = this rank's rows of the path (or of its transpose),
+ * planes tiled with n_cols/32 tiles per row, diagonal taken at column diag_col0 + i (pass -1 to skip it), adj_total = the partial
+ * totals of these rows.  n_cols must be a multiple of 32.  adj_rowsum / adj_diag / adj_total / tch_coef may be NULL (transpose). */
+int pegncde_build_adj_rect(peg_stream_t stream, const PegDims* dims, int32_t n_cols, int32_t diag_col0, const float* ts,
+                           const float* snapshots, float* adj_coef, float* adj_rowsum, float* adj_diag, float* adj_total, float* tch_coef,
+                           float* adj_absmax);
+/* bytes of each symmetric buffer of a PegShard for these dims (dmax = widest layer): out[0] = vt_hi (= vt_lo), out[1] = vexp,
+ * out[2] = colsum, out[3] = flags */
+int pegncde_shard_buffer_bytes(const PegDims* dims, int32_t world, size_t* out /* [4] */);
 /* column sums of the tiled planes (fixed summation order) -> adj_colsum [B, T-1, 4, n]; needed by PEG_FLAG_DIRECTED only */
 int pegncde_adj_colsums(peg_stream_t stream, const PegDims* dims, const float* adj_coef, float* adj_colsum);
 /* max |entry| of the tiled planes of the cubic pieces [piece_begin, piece_begin + piece_count) -> adj_absmax [B, T-1, 4] (order

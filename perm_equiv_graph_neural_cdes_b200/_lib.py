@@ -26,8 +26,15 @@ class PegDims(Structure):
     _fields_ = [(k, c_int32) for k in ("B", "n", "ldn", "h", "e", "L", "T", "flags")]
 
 
+class PegShard(Structure):
+    """Row-sharded mode (include/pegncde.h): the pointer tables are HOST arrays of `world` device pointers."""
+    _fields_ = [("rank", c_int32), ("world", c_int32), ("n_glob", c_int32), ("row0", c_int32), ("adj_coef_t", c_void_p),
+                ("vt_hi", POINTER(c_void_p)), ("vt_lo", POINTER(c_void_p)), ("vexp", POINTER(c_void_p)), ("colsum", POINTER(c_void_p)),
+                ("flags", POINTER(c_void_p)), ("epoch", POINTER(ctypes.c_uint32))]
+
+
 class PegControl(Structure):
-    _fields_ = [(k, c_void_p) for k in ("ts", "adj_coef", "adj_rowsum", "adj_diag", "adj_total", "tch_coef", "x_coef", "adj_colsum", "adj_absmax")]
+    _fields_ = [(k, c_void_p) for k in ("ts", "adj_coef", "adj_rowsum", "adj_diag", "adj_total", "tch_coef", "x_coef", "adj_colsum", "adj_absmax")] + [("shard", POINTER(PegShard))]
 
 
 class PegError(RuntimeError):
@@ -54,6 +61,8 @@ SIGNATURES = {
     "pegncde_adj_stats": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P]),
     "pegncde_build_adj": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P, _P, _P]),
     "pegncde_adj_colsums": (c_int, [_P, _DIMS, _P, _P]),
+    "pegncde_build_adj_rect": (c_int, [_P, _DIMS, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pegncde_shard_buffer_bytes": (c_int, [_DIMS, c_int32, POINTER(c_size_t)]),
     "pegncde_adj_absmax": (c_int, [_P, _DIMS, c_int32, c_int32, _P, _P]),
     "pegncde_pack_x": (c_int, [_P, _DIMS, _P, _P, _P, _P, _P]),
     "pegncde_workspace_bytes": (c_size_t, [_DIMS, c_int32, c_int32]),

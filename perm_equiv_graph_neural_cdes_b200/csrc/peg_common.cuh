@@ -118,6 +118,11 @@ struct ContractArgs {
   int n, ldn /* = npad */, d, layer, L;
   int relu, scale_tg;
   int vt_ready;          // the producer kernel already wrote V^T hi/lo (tensor-core path skips its own transpose pass)
+  // row-sharded mode (PegShard): n / ldn are this rank's rows, the K dimension runs over all ldk = n_glob columns, the transposed
+  // products read the rank's rows of the TRANSPOSED path (planes_t) like direct ones.  Whole graph on one GPU: planes_t = nullptr,
+  // ldk = ldn, n_glob = n, row_block0 = 0.
+  const float* planes_t;
+  int ldk, n_glob, row_block0;
 };
 
 struct Bump {
@@ -175,6 +180,8 @@ struct ProducerOut {
   int t16;                // operand format of the contraction that will read V^T (PEG_FMT_*)
   int* vexp;              // fmt 2: [B][vexp_stride] power-of-two exponent of every 128-node block: V^T holds V * 2^vexp
   int vexp_stride;
+  int col0, blk0;         // row-sharded mode: this rank's rows are columns [col0, col0 + rows_pad) of V^T, blocks from blk0 (else 0, 0)
+  int rows_pad;           // padded local row count (== npad unless row-sharded)
   float* cb;              // nullable
   float* partial;         // [B][chunks][2][d]
   unsigned int* tickets;  // self-resetting, one per (b, column group)

@@ -27,13 +27,16 @@ __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, 
                                                   const float* __restrict__ ts, int n, int npad, int Tm1, int piece0,
                                                   int in_Tm1, float* __restrict__ adj_coef, float* __restrict__ rowsum,
                                                   float* __restrict__ diag, float* __restrict__ total,
-                                                  float* __restrict__ tch) {
+                                                  float* __restrict__ tch, int ncols, int diag_col0) {
+  // rectangular shards (row-sharded mode): n rows x ncols columns (ncols a multiple of 32), diagonal at column diag_col0 + i;
+  // the square case is ncols == n, diag_col0 == 0
   __shared__ __align__(16) float tile[4096];   // the tile in its final element order
   __shared__ float tcol[8][3][32];             // per-warp column sums of the time channel of (b,c,d)
   // blockIdx.y walks `gridDim.y` cubic pieces starting at piece0; the reference-layout source holds in_Tm1 pieces per
   // graph (== Tm1 for a whole path, == the count of a streamed range: pegncde_pack_adj_range)
   const int b = blockIdx.z, iv = piece0 + blockIdx.y;
-  const int nt = npad >> 5;
+  const int nt = npad >> 5;                       // row tiles
+  const int ncpad = peg_npad(ncols), ntc = ncpad >> 5;   // column tiles per row of tiles
   const int ct = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t slab = ((size_t)b * Tm1 + iv);
@@ -47,7 +50,7 @@ __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, 
     dtp = iv > 0 ? tb[iv] - tb[iv - 1] : dt;
   }
   for (int rt = 0; rt < nt; ++rt) {
-    const size_t tile_base = slab * 4 * (size_t)npad * npad + ((size_t)rt * nt + ct) * 4096;
+    const size_t tile_base = slab * 4 * (size_t)npad * ncpad + ((size_t)rt * ntc + ct) * 4096;
     if (tiled_in) {
       for (int idx = threadIdx.x; idx < 1024; idx += 256)
         *reinterpret_cast<float4*>(&tile[4 * idx]) = *reinterpret_cast<const float4*>(tiled_in + tile_base + 4 * idx);
@@ -57,11 +60,11 @@ __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, 
       const int r = idx >> 5, c = idx & 31;      // r is warp-uniform, c == lane
       const int i = rt * 32 + r, k = ct * 32 + c;
       float hv[4] = {0.f, 0.f, 0.f, 0.f};
-      if (snap && i < n && k < n) {
+      if (snap && i < n && k < ncols) {
         // diffrax.backward_hermite_coefficients per element: a = y_i, b = previous secant (first piece: own secant),
         // c = 2 (m - b) / dt, d = -(m - b) / dt^2
-        const float* Ab = snap + ((size_t)b * (Tm1 + 1) * n + i) * (size_t)n + k;
-        const size_t knot = (size_t)n * n;
+        const float* Ab = snap + ((size_t)b * (Tm1 + 1) * n + i) * (size_t)ncols + k;
+        const size_t knot = (size_t)n * ncols;
         const float y0 = __ldg(Ab + (size_t)iv * knot), y1 = __ldg(Ab + (size_t)(iv + 1) * knot);
         const float m = (y1 - y0) / dt;
         const float bb = iv > 0 ? (y0 - __ldg(Ab + (size_t)(iv - 1) * knot)) / dtp : m;
@@ -74,17 +77,17 @@ __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, 
       for (int p = 0; p < 4; ++p) {
         float v = 0.f;
         const int to = (int)peg_tile_off(r, c, p, 1);   // offset inside the tile
-        if (i < n && k < n) {
+        if (i < n && k < ncols) {
           if (tiled_in) {
             v = tile[to];
           } else if (snap) {
             v = hv[p];
           } else {
-            const float2 tv = __ldg(reinterpret_cast<const float2*>(src[p]) + (in_slab * n + i) * (size_t)n + k);
+            const float2 tv = __ldg(reinterpret_cast<const float2*>(src[p]) + (in_slab * n + i) * (size_t)ncols + k);
             v = tv.y;
             if (p > 0) tsum[p - 1] += tv.x;
           }
-          if (i == k) diag[(slab * 4 + p) * n + i] = v;
+          if (diag != nullptr && diag_col0 >= 0 && k == diag_col0 + i) diag[(slab * 4 + p) * n + i] = v;
         }
         if (!tiled_in) tile[to] = v;
       }
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, 
       float t = 0.f;
 #pragma unroll
       for (int w8 = 0; w8 < 8; ++w8) t += tcol[w8][p][lane];
-      if (k < n) tch[(slab * 3 + p) * n + k] = t / (float)n;
+      if (k < ncols) tch[(slab * 3 + p) * ncols + k] = t / (float)n;
     }
   }
 }
@@ -114,12 +117,12 @@ __global__ void __launch_bounds__(256) k_pack_adj(const float* __restrict__ cd, 
 // (fixed-order warp reductions, no float atomics), so the packed control -- and every accept / reject decision of an
 // adaptive solve built on it -- is reproducible run to run.  grid (nt, T-1, B), block 256.
 __global__ void __launch_bounds__(256) k_adj_rowsums(const float* __restrict__ adj_coef, int n, int npad, int Tm1, int piece0,
-                                                     float* __restrict__ rowsum) {
+                                                     float* __restrict__ rowsum, int ncpad) {
   __shared__ __align__(16) float tile[4096];
   const int b = blockIdx.z, iv = piece0 + blockIdx.y, rt = blockIdx.x;
-  const int nt = npad >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = ncpad >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // nt = column tiles (ncpad == npad for a square path)
   const size_t slab = (size_t)b * Tm1 + iv;
-  const float* base = adj_coef + slab * 4 * (size_t)npad * npad + (size_t)rt * nt * 4096;
+  const float* base = adj_coef + slab * 4 * (size_t)npad * ncpad + (size_t)rt * nt * 4096;
   float acc[4][4];
 #pragma unroll
   for (int p = 0; p < 4; ++p)
@@ -161,12 +164,12 @@ __global__ void __launch_bounds__(256) k_adj_totals(const float* __restrict__ ro
 // max |entry| of each of the four planes of one cubic piece.  grid (tile chunks, pieces, B), block 256; fmaxf is order
 // independent, so the atomicMax on the bit pattern (non-negative floats order like unsigned integers) is reproducible.
 __global__ void __launch_bounds__(256) k_adj_absmax(const float* __restrict__ adj_coef, int npad, int Tm1, int piece0,
-                                                    float* __restrict__ absmax) {
+                                                    float* __restrict__ absmax, int ncpad) {
   __shared__ float sh[8][4];
   const int b = blockIdx.z, iv = piece0 + blockIdx.y;
-  const int nt = npad >> 5, ntiles = nt * nt, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = (npad >> 5) * (ncpad >> 5), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t slab = (size_t)b * Tm1 + iv;
-  const float4* base = reinterpret_cast<const float4*>(adj_coef + slab * 4 * (size_t)npad * npad);
+  const float4* base = reinterpret_cast<const float4*>(adj_coef + slab * 4 * (size_t)npad * ncpad);
   float mx[4] = {0.f, 0.f, 0.f, 0.f};
   // a tile is 1024 float4: index i -> plane (i >> 7) & 3   ([g][plane][m][lane] with 4 floats per lane)
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
@@ -232,6 +235,118 @@ __global__ void __launch_bounds__(256) k_adj_colsums(const float* __restrict__ a
   }
 }
 
+// =====================================================================================
+// row-sharded mode: the per-layer exchange over peer memory (PegShard in pegncde.h)
+// =====================================================================================
+#define PEG_MAX_WORLD 8
+struct ShardXchg {
+  void* vt_hi[PEG_MAX_WORLD];        // peer bases of the V^T halves (bytes), copied from the host tables of PegShard
+  void* vt_lo[PEG_MAX_WORLD];
+  int32_t* vexp[PEG_MAX_WORLD];
+  float* colsum[PEG_MAX_WORLD];
+  uint32_t* flags[PEG_MAX_WORLD];
+  int rank, world;
+  uint32_t epoch;            // value raised in the peers' flags by this exchange
+  size_t half_bytes;         // bytes of one epoch-parity half of a V^T buffer
+  int push_vt;               // 0: only the column sums travel (no V^T in this exchange)
+  int rows;                  // B * d rows of V^T
+  size_t pitch_bytes;        // row pitch of V^T in bytes (= n_glob * element size)
+  size_t col0_bytes, slice_bytes;   // this rank's columns of every row
+  int vexp_half, vexp_stride, blk0, nblk_loc, B;   // block exponents: [2][B * vexp_stride], this rank owns blocks [blk0, blk0 + nblk_loc)
+  int push_vexp;
+  const float* cs_src[2];    // local column-sum vectors (nullable), cs_len floats each
+  float* cs_dst[2];          // where the rank-ordered sums go (k_shard_wait)
+  int cs_len;
+  size_t cs_half;            // floats of one epoch-parity half of the column-sum slots = world * 2 * cs_cap
+  size_t cs_cap;             // floats reserved per (rank, vector)
+  unsigned int* ticket;      // local arrival counter of k_shard_push (self-resetting)
+};
+
+// Copies this rank's slice of V^T (both parts), its block exponents and its column-sum vectors into every peer's buffers with
+// 128-bit stores over NVLink, then raises flags[rank] = epoch on every peer (release at system scope).  grid (blocks, world - 1... the
+// local copy needs no transfer: the producers wrote the local buffer in place), block 256.  blockIdx.y = peer slot.
+__global__ void __launch_bounds__(256) k_shard_push(const ShardXchg x) {
+  const int par = (int)(x.epoch & 1u);
+  const int peer = blockIdx.y;                  // every rank, including this one (column sums go to the own slot too)
+  const bool remote = peer != x.rank;
+  if (x.push_vt && remote) {
+    const char* src_hi = (const char*)x.vt_hi[x.rank] + par * x.half_bytes, *src_lo = (const char*)x.vt_lo[x.rank] + par * x.half_bytes;
+    char* dst_hi = (char*)x.vt_hi[peer] + par * x.half_bytes, *dst_lo = (char*)x.vt_lo[peer] + par * x.half_bytes;
+    const size_t v16 = x.slice_bytes / 16;      // the slice is a multiple of 128 nodes x >= 2 bytes
+    const size_t total = (size_t)x.rows * v16;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+      const size_t r = i / v16, c = i - r * v16;
+      const size_t off = r * x.pitch_bytes + x.col0_bytes + c * 16;
+      *reinterpret_cast<uint4*>(dst_hi + off) = *reinterpret_cast<const uint4*>(src_hi + off);
+      *reinterpret_cast<uint4*>(dst_lo + off) = *reinterpret_cast<const uint4*>(src_lo + off);
+    }
+    if (x.push_vexp && blockIdx.x == 0) {
+      const int32_t* s = x.vexp[x.rank] + (size_t)par * x.vexp_half;
+      int32_t* d = x.vexp[peer] + (size_t)par * x.vexp_half;
+      for (int i = threadIdx.x; i < x.B * x.nblk_loc; i += blockDim.x) {
+        const int b = i / x.nblk_loc, k = i - b * x.nblk_loc;
+        d[(size_t)b * x.vexp_stride + x.blk0 + k] = s[(size_t)b * x.vexp_stride + x.blk0 + k];
+      }
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (int v = 0; v < 2; ++v) {
+      if (!x.cs_src[v]) continue;
+      float* d = x.colsum[peer] + (size_t)par * x.cs_half + ((size_t)x.rank * 2 + v) * x.cs_cap;
+      for (int i = threadIdx.x; i < x.cs_len; i += blockDim.x) d[i] = x.cs_src[v][i];
+    }
+  }
+  // all blocks of this launch done -> publish
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(x.ticket, 1u);
+    last = (t == gridDim.x * gridDim.y - 1u);
+    if (last) *x.ticket = 0u;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    for (int q = threadIdx.x; q < x.world; q += blockDim.x) {
+      volatile uint32_t* f = x.flags[q] + x.rank;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(x.epoch) : "memory");
+    }
+  }
+}
+
+// Waits until every rank has raised this exchange's epoch in the local flags, then adds the column-sum slots in rank order
+// (deterministic) into the local vectors.  One block.  A peer that never arrives (an error on another rank) must not hang the
+// GPU: after ~2 s of spinning the kernel gives up and records the failure in the error word flags[world] (checked by the host).
+__global__ void __launch_bounds__(256) k_shard_wait(const ShardXchg x) {
+  const int par = (int)(x.epoch & 1u);
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = 1;
+  __syncthreads();
+  if (threadIdx.x < x.world) {
+    const uint32_t* f = x.flags[x.rank] + threadIdx.x;
+    const long long t0 = clock64();
+    uint32_t v;
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if ((int32_t)(v - x.epoch) >= 0) break;
+      if (clock64() - t0 > 4000000000ll) { ok = 0; x.flags[x.rank][x.world] = 1u; break; }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  if (!ok) return;
+  for (int v = 0; v < 2; ++v) {
+    if (!x.cs_dst[v]) continue;
+    const float* base = x.colsum[x.rank] + (size_t)par * x.cs_half + (size_t)v * x.cs_cap;
+    for (int i = threadIdx.x; i < x.cs_len; i += blockDim.x) {
+      float t = 0.f;
+      for (int q = 0; q < x.world; ++q) t += __ldcg(base + (size_t)q * 2 * x.cs_cap + i);
+      x.cs_dst[v][i] = t;
+    }
+  }
+}
+
 // x coeffs: d,c,b,a each [B,T-1,n,e,2] -> x_coef [B,T-1,3,n,2e] (b,c,d)
 __global__ void k_pack_x(const float* __restrict__ cd, const float* __restrict__ cc, const float* __restrict__ cb,
                          int n, int e2, size_t slabs, float* __restrict__ x_coef) {
@@ -252,6 +367,7 @@ struct PrepArgs {
   PegControl ctl;
   const float* params;
   Model model;
+  int n_glob;   // node count the 1/n, 1/n^2 factors refer to (== n unless row-sharded)
   int B, n, e, T;
   float t;
   StageScalars* sc;
@@ -278,7 +394,7 @@ __global__ void __launch_bounds__(256) k_stage_prep(PrepArgs a) {
   const float* tot = a.ctl.adj_total + slab * 4;
   const float totA = wA[0] * tot[0] + wA[1] * tot[1] + wA[2] * tot[2] + wA[3] * tot[3];
   const float totD = wD[1] * tot[1] + wD[2] * tot[2] + wD[3] * tot[3];
-  const float inv_n = 1.f / (float)n, inv_n2 = inv_n * inv_n;
+  const float inv_n = 1.f / (float)a.n_glob, inv_n2 = inv_n * inv_n;
   if (tid == 0 && blockIdx.x == 0) {
     S.interval = iv;
     S.s = s;

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) k_split_transpose(const float* __restrict
   const int b = blockIdx.z, i0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const float* Vb = V + (size_t)b * n * d;
   // fp16x2: the block exponent of this tile's 128-node block (written by k_block_exponent just before)
-  const float vscale = po.t16 == PEG_FMT_FP16X2 ? exp2_int(po.vexp[(size_t)b * po.vexp_stride + (i0 >> 7)]) : 1.f;
+  const float vscale = po.t16 == PEG_FMT_FP16X2 ? exp2_int(po.vexp[(size_t)b * po.vexp_stride + po.blk0 + (i0 >> 7)]) : 1.f;
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int i = i0 + r, c = c0 + threadIdx.x;
     tile[r][threadIdx.x] = (i < n && c < d) ? Vb[(size_t)i * d + c] : 0.f;
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) k_split_transpose(const float* __restrict
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int c = c0 + r, i = i0 + threadIdx.x;
     if (c < d) {
-      const size_t o = ((size_t)b * d + c) * npad + i;
+      const size_t o = ((size_t)b * d + c) * po.npad + po.col0 + i;     // npad = this rank's padded rows, po.npad = the row pitch of V^T
       if (po.t16 == PEG_FMT_FP16X2) store_vt_f16(po, o, tile[threadIdx.x][r] * vscale);
       else store_vt(po, o, tile[threadIdx.x][r]);
     }
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) k_split_transpose(const float* __restrict
 
 // fp16x2 operand format: block exponent e of every 128-node block of V [B,n,d] (vexp[b][block]); k_split_transpose then writes
 // V^T * 2^e.  One CTA per block reads its 128 x d slab once.  grid (ceil(npad/128), B), block 256
-__global__ void __launch_bounds__(256) k_block_exponent(const float* __restrict__ V, int n, int d, int* __restrict__ vexp, int vexp_stride) {
+__global__ void __launch_bounds__(256) k_block_exponent(const float* __restrict__ V, int n, int d, int* __restrict__ vexp, int vexp_stride, int blk0) {
   __shared__ float bmax_s[8];
   const int b = blockIdx.y, blk = blockIdx.x, i0 = blk * 128;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) k_block_exponent(const float* __restrict_
   if (tid == 0) {
 #pragma unroll
     for (int w8 = 0; w8 < 8; ++w8) mx = fmaxf(mx, bmax_s[w8]);
-    vexp[(size_t)b * vexp_stride + blk] = block_exponent(mx);
+    vexp[(size_t)b * vexp_stride + blk0 + blk] = block_exponent(mx);
   }
 }
 
@@ -218,7 +218,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   if constexpr (BFP) {
     // V^T holds V * 2^(e_J) per 128-node block J.  The blocks are aligned to the smallest exponent E inside the A operand (its
     // plane weights are multiplied by 2^(E - e_J) <= 1, exact), so every accumulator ends up scaled by 2^E times the A scale.
-    const int nblk = (a.ldn + 127) >> 7;
+    const int nblk = (a.ldk + 127) >> 7;
     const int* ve = p.vexp + (size_t)b * p.vexp_stride;
     if (warp == 0) {
       int e = PEG_VEXP_MAX;
@@ -243,7 +243,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   const int items = 2 * npairs;   // local item j = 2 * local pair + type (0 direct, 1 transposed); pair works on chunk kc_of(pr0 + pair)
   // chunk order: 128-column blocks J(S) = (S - Ibase) mod nb, four 32-chunks each (the last block may hold fewer)
   const int nb = (nkc + 3) >> 2, r_last = nkc - 4 * (nb - 1);
-  const int Imod = Ibase % nb, Sstar = (nb - 1 + Imod) % nb;
+  const int Imod = (Ibase + a.row_block0) % nb, Sstar = (nb - 1 + Imod) % nb;   // keyed on the GLOBAL row block (row-sharded mode)
   auto kc_of = [&](int pr) -> int {
     int S, u;
     if (pr < 4 * Sstar) { S = pr >> 2; u = pr & 3; }
@@ -292,6 +292,10 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   if (warp < 16) {
     // =========================== converters ===========================
     const int grp = warp >> 3, w8 = warp & 7;   // group 0: direct items (even j); group 1: transposed items (odd j)
+    // row-sharded mode: the transposed products read this rank's rows of the TRANSPOSED path, i.e. they are converted like direct
+    // items (operand row = tile row) from planes_t; `dirlike` selects the direct conversion, `tposed` the transposed one
+    const bool sharded = a.planes_t != nullptr;
+    const bool dirlike = grp == 0 || sharded, tposed = !dirlike;
     // weights of the four planes for each A-operand variant and item type
     float w[NA][4];   // this group's weights: direct items use X (fwd) / (A_s, A'_s) (bwd); transposed items use Y / the same pair
 #pragma unroll
@@ -307,8 +311,8 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
                            : gamma * sc.wA[q] + delta * sc.wD[q];   // Y = p2_0 A + p2_1 A'
       }
     }
-    const int npad = a.ldn, nt = npad >> 5;
-    const float* P = a.planes + (size_t)b * a.graph_stride + (size_t)sc.interval * 4 * npad * npad;
+    const int ntr = a.ldn >> 5, nt = a.ldk >> 5;      // row tiles of this rank's strip, tiles per row of tiles (= K chunks)
+    const float* P = ((grp == 1 && sharded) ? a.planes_t : a.planes) + (size_t)b * a.graph_stride + (size_t)sc.interval * 4 * a.ldn * a.ldk;
     // Tiled plane layout (peg_common.cuh): an item is four 16-KB tiles; warp w loads half (g) of tile u, every
     // warp-level LDG.128 is 512 contiguous bytes and the thread ends up with the 4x4 micro tile (rq, cq) of all
     // four planes: buf[plane*4 + m] = row 4*rq + m, columns 4*cq .. 4*cq+3 of the 32x32 tile.
@@ -323,7 +327,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     // 16-bit operand formats, direct items: the 8-byte operand stores of one instruction must hit rows of both parities to be
     // bank-conflict-free (rows are 64 bytes), so the lanes with sw = 1 keep the rows of their micro tile in swapped order
     // (register row m holds tile row m ^ 1).  It costs nothing: only the load addresses and the store offsets change.
-    const int sw = (F16 && grp == 0) ? ((lane >> 3) & 1) : 0;
+    const int sw = (F16 && dirlike) ? ((lane >> 3) & 1) : 0;
     // `half`: 0 = the first PEG_TC_BWD_HALF_EARLY rows m of the micro tile, 1 = the remaining rows, 2 = all four (the adjoint can
     // issue the two parts at different times)
     auto load_tile = [&](int rt, int ct, int half) {
@@ -341,7 +345,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
           for (int m = 0; m < 4; ++m) buf[q * 4 + m] = ldg_stream(((m & 1) ? base_odd : base_even) + (q * 4 + m) * 128);
         return;
       }
-      if (rt < nt && ct < nt) {
+      if (rt < (tposed ? nt : ntr) && ct < (tposed ? ntr : nt)) {
         const float* base = P + ((size_t)rt * nt + ct) * 4096 + cv_off;
         const float* base_even = base + sw * 128;   // register row m <- tile row m ^ sw: even m read one row up, odd m one row down
         const float* base_odd = base - sw * 128;
@@ -359,11 +363,11 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       }
     };
     // item j -> its plane tile: direct = rows of block I x chunk kc, transposed = chunk kc x columns of block I
-    const bool tile_ok = 4 * I + cv_u < nt;            // this warp's 32-row (direct) / 32-column (transposed) strip exists
+    const bool tile_ok = 4 * I + cv_u < ntr;           // this warp's 32-row (direct) / 32-column (transposed) strip exists
     const int my_tile = tile_ok ? 4 * I + cv_u : 0;
     auto load_item = [&](int j, int half) {
       const int kc = F16 ? sched_s[j >> 1].x : kc_of(pr0 + (j >> 1));
-      if ((j & 1) == 0) load_tile(F16 ? my_tile : 4 * I + cv_u, kc, half);
+      if (dirlike) load_tile(F16 ? my_tile : 4 * I + cv_u, kc, half);
       else load_tile(kc, F16 ? my_tile : 4 * I + cv_u, half);
     };
     // store 4 consecutive k (k = 4 * chunk .. 4 * chunk + 3) of operand row r as hi (+ lo) parts into the swizzled K-major tile:
@@ -446,8 +450,8 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     // slot wait and keeps 32 combined values live, which spills at the 96 registers 18 warps allow).
     // Operand-tile offsets (SWIZZLE_64B): row r, 16-byte chunk c, half hf -> (r >> 3) * 512 + (r & 7) * 64 + ((c ^ ((r >> 1) & 3)) << 4)
     // + 8 hf.  For the four rows r0 + m' (r0 multiple of 4) of one micro tile only (m' >> 1) enters the XOR: two base offsets.
-    const int r0 = 32 * cv_u + 4 * (grp == 0 ? cv_rq : cv_cq);     // first operand row of this thread (direct: tile rows, transposed: tile columns)
-    const int kq = grp == 0 ? cv_cq : cv_rq;                        // its K quad: k = 4 kq .. 4 kq + 3
+    const int r0 = 32 * cv_u + 4 * (dirlike ? cv_rq : cv_cq);      // first operand row of this thread (direct: tile rows, transposed: tile columns)
+    const int kq = dirlike ? cv_cq : cv_rq;                         // its K quad: k = 4 kq .. 4 kq + 3
     const uint32_t o_row = (uint32_t)(r0 >> 3) * 512u + (uint32_t)(r0 & 7) * 64u + (uint32_t)(kq & 1) * 8u;
     const uint32_t o_lo = o_row + (uint32_t)(((kq >> 1) ^ ((r0 >> 1) & 3)) << 4);          // rows r0, r0 + 1
     const uint32_t o_hi = o_row + (uint32_t)(((kq >> 1) ^ (((r0 >> 1) & 3) + 1)) << 4);    // rows r0 + 2, r0 + 3
@@ -551,12 +555,12 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       } else {
         if (items > 0) load_item(grp, 2);   // group 0: direct items (even j); group 1: transposed items (odd j)
         if (grp == 0) for (int j = 0; j < items; j += 2) convert16(j, false);
-        else          for (int j = 1; j < items; j += 2) convert16(j, true);
+        else          for (int j = 1; j < items; j += 2) convert16(j, tposed);
       }
     } else {
       if (items > 0) load_item(grp, 2);
       if (grp == 0) for (int j = 0; j < items; j += 2) convert(j, false);
-      else          for (int j = 1; j < items; j += 2) convert(j, true);
+      else          for (int j = 1; j < items; j += 2) convert(j, tposed);
     }
   } else if (warp == 16) {
     // =========================== TMA producer (B operand) ===========================
@@ -777,7 +781,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         part[10] = rA * fq; part[11] = rD * fq;    // param6 (/n)
         part[12] = fq;                              // param8 (* tot / n^2)
       }
-      if (cbM && I == 0 && q == 0) {               // param7: tot_A / n^2 * <1^T G, 1^T M>, this CTA's columns once
+      if (cbM && I + a.row_block0 == 0 && q == 0) {   // param7: tot_A / n^2 * <1^T G, 1^T M>, this CTA's columns once per graph
         float t = 0.f;
         for (int c = half * cols_per_half + lane; c < (half + 1) * cols_per_half; c += 32) t = fmaf(cb0[ntile * nd + c], cbM[ntile * nd + c], t);
         part[13] = t;
@@ -797,7 +801,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     float t = 0.f;
 #pragma unroll
     for (int w8i = 0; w8i < 8; ++w8i) t += fsum[w8i][tid];
-    const float inv_n = 1.f / (float)n, inv_n2 = inv_n * inv_n;
+    const float inv_n = 1.f / (float)a.n_glob, inv_n2 = inv_n * inv_n;
     const float totA = scp->totA, totD = scp->totD;
     if (tid < 4) {
       if (LIGHT) {   // (<combined V, M>, <sep V, M>) -> (<A V, M>, <A' V, M>) of this thread's item type (0,1: transposed; 2,3: direct)
@@ -952,6 +956,8 @@ void tc_carve(Bump& bp, const PegDims& d, int dmax, TcWs& w) {
   w.npad = npad_of(d.n);
   w.fmt = PEG_FMT_TF32X3;
   w.vexp = nullptr;
+  w.ldk = w.npad;
+  w.col0 = w.blk0 = 0;
   w.vexp_stride = (w.npad + 127) / 128;
   if ((d.flags & PEG_FLAG_TENSOR_CORES) == 0) {
     w.Vt_hi = w.Vt_lo = w.partial = nullptr;
@@ -987,30 +993,37 @@ static int tmem_cols_pow2(int cols) {
   return c;
 }
 
+// V [B,n,d] -> the K-major B operand V^T (hi / lo parts in the call's operand format) when no producer kernel wrote it
+int tc_convert_v(cudaStream_t st, const PegDims& dm, const TcWs& w, const ContractArgs& a) {
+  const int n = a.n, d = a.d, npad = w.npad, ldk = w.ldk, fmt = w.fmt;
+  if (!w.Vt_hi || !w.Vt_lo) return PEG_ERR_WORKSPACE;
+  ProducerOut po;
+  memset(&po, 0, sizeof(po));
+  po.Thi = w.Vt_hi; po.Tlo = w.Vt_lo; po.npad = ldk; po.t16 = fmt; po.vexp = w.vexp; po.vexp_stride = w.vexp_stride;
+  po.col0 = w.col0; po.blk0 = w.blk0; po.rows_pad = npad;
+  if (fmt == PEG_FMT_FP16X2) {
+    k_block_exponent<<<dim3((npad + 127) / 128, dm.B), 256, 0, st>>>(a.V, n, d, w.vexp, w.vexp_stride, w.blk0);
+    if (cudaPeekAtLastError() != cudaSuccess) { set_last_cuda((int)cudaGetLastError()); fprintf(stderr, "pegncde: k_block_exponent launch failed\n"); return PEG_ERR_CUDA; }
+  }
+  dim3 grid(npad / 32, (d + 31) / 32, dm.B), block(32, 8);
+  k_split_transpose<<<grid, block, 0, st>>>(a.V, n, d, npad, po);
+  if (cudaPeekAtLastError() != cudaSuccess) { set_last_cuda((int)cudaGetLastError()); fprintf(stderr, "pegncde: k_split_transpose launch failed\n"); return PEG_ERR_CUDA; }
+  return PEG_OK;
+}
+
 int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const ContractArgs& a, bool bwd) {
-  const int n = a.n, d = a.d, npad = w.npad;
+  const int n = a.n, d = a.d, npad = w.npad, ldk = w.ldk;
   if (!w.Vt_hi || !w.Vt_lo) return PEG_ERR_WORKSPACE;
   if (!get_encode()) return PEG_ERR_UNSUPPORTED;
   const int fmt = w.fmt, f16 = fmt != PEG_FMT_TF32X3 ? 1 : 0;
-  if (!a.vt_ready) {
-    ProducerOut po;
-    memset(&po, 0, sizeof(po));
-    po.Thi = w.Vt_hi; po.Tlo = w.Vt_lo; po.npad = npad; po.t16 = fmt; po.vexp = w.vexp; po.vexp_stride = w.vexp_stride;
-    if (fmt == PEG_FMT_FP16X2) {
-      k_block_exponent<<<dim3((npad + 127) / 128, dm.B), 256, 0, st>>>(a.V, n, d, w.vexp, w.vexp_stride);
-      if (cudaPeekAtLastError() != cudaSuccess) { set_last_cuda((int)cudaGetLastError()); fprintf(stderr, "pegncde: k_block_exponent launch failed\n"); return PEG_ERR_CUDA; }
-    }
-    dim3 grid(npad / 32, (d + 31) / 32, dm.B), block(32, 8);
-    k_split_transpose<<<grid, block, 0, st>>>(a.V, n, d, npad, po);
-    if (cudaPeekAtLastError() != cudaSuccess) { set_last_cuda((int)cudaGetLastError()); fprintf(stderr, "pegncde: k_split_transpose launch failed\n"); return PEG_ERR_CUDA; }
-  }
+  if (!a.vt_ready) PEG_TC_TRY(tc_convert_v(st, dm, w, a));
   TcParams p;
   p.a = a;
   int nd_max = bwd ? 128 : 256;
   { const int v = g_env.nd_max; if (v >= 32 && v <= nd_max) nd_max = v; }
   p.nd = pick_nd(d, nd_max);
   p.nsplit = (dm.flags & PEG_FLAG_TF32_FAST) ? 1 : 3;
-  p.nkc = npad / 32;
+  p.nkc = ldk / 32;
   const int na = bwd ? 2 : 1, sp = (f16 || p.nsplit == 3) ? 2 : 1;
   const int a_bytes = na * sp * (f16 ? TC_ATILE / 2 : TC_ATILE), b_bytes = sp * p.nd * TC_BK * (f16 ? 2 : 4);
   // smem rings: two B slots (one per pair in flight), the rest of ~208 KB goes to A slots (even count, at most 4)
@@ -1042,7 +1055,7 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
 
   const CUtensorMap* mhi_p = nullptr;
   const CUtensorMap* mlo_p = nullptr;
-  PEG_TC_TRY(get_maps(w.Vt_hi, w.Vt_lo, (uint64_t)npad, (uint64_t)dm.B * d, p.nd / cluster, &mhi_p, &mlo_p, fmt));
+  PEG_TC_TRY(get_maps(w.Vt_hi, w.Vt_lo, (uint64_t)ldk, (uint64_t)dm.B * d, p.nd / cluster, &mhi_p, &mlo_p, fmt));
   const CUtensorMap& mhi = *mhi_p;
   const CUtensorMap& mlo = *mlo_p;
 
@@ -1349,7 +1362,7 @@ k_tc_norm_linear(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
       for (int w8 = 0; w8 < 8; ++w8) mx = fmaxf(mx, bmax_s[w8]);
       const int e = block_exponent(mx);
       vscale = exp2_int(e);
-      if (tid == 0) p.po.vexp[(size_t)b * p.po.vexp_stride + rb] = e;
+      if (tid == 0) p.po.vexp[(size_t)b * p.po.vexp_stride + p.po.blk0 + rb] = e;
     }
     for (int cc = 0; cc < cols_per_half; cc += 16) {
       const int col = half * cols_per_half + cc, gc = ntile * nd + col;
@@ -1364,13 +1377,13 @@ k_tc_norm_linear(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
         for (int v4 = 0; v4 < 4; ++v4)
           *reinterpret_cast<float4*>(Mrow + gc + 4 * v4) = make_float4(m[4 * v4], m[4 * v4 + 1], m[4 * v4 + 2], m[4 * v4 + 3]);
       }
-      if (p.po.Thi != nullptr && gi < p.po.npad) {   // V^T hi/lo: the 32 lanes of a warp are 32 consecutive nodes
+      if (p.po.Thi != nullptr && gi < p.po.rows_pad) {   // V^T hi/lo: the 32 lanes of a warp are 32 consecutive nodes
         if (p.po.t16 == PEG_FMT_FP16X2) {
 #pragma unroll
-          for (int u = 0; u < 16; ++u) store_vt_f16(p.po, ((size_t)b * dout + gc + u) * p.po.npad + gi, m[u] * vscale);
+          for (int u = 0; u < 16; ++u) store_vt_f16(p.po, ((size_t)b * dout + gc + u) * p.po.npad + p.po.col0 + gi, m[u] * vscale);
         } else {
 #pragma unroll
-          for (int u = 0; u < 16; ++u) store_vt(p.po, ((size_t)b * dout + gc + u) * p.po.npad + gi, m[u]);
+          for (int u = 0; u < 16; ++u) store_vt(p.po, ((size_t)b * dout + gc + u) * p.po.npad + p.po.col0 + gi, m[u]);
         }
       }
       if (p.po.cb != nullptr) {   // column sums over this warp's 32 nodes (fixed butterfly order)
@@ -1728,10 +1741,10 @@ k_tc_linear_bwd(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         for (int v4 = 0; v4 < 4; ++v4)
           *reinterpret_cast<float4*>(Zbrow + col + 4 * v4) = make_float4(zb[4 * v4], zb[4 * v4 + 1], zb[4 * v4 + 2], zb[4 * v4 + 3]);
       }
-      if (p.po.Thi != nullptr && gi < p.po.npad && p.po.t16 != PEG_FMT_FP16X2) {
+      if (p.po.Thi != nullptr && gi < p.po.rows_pad && p.po.t16 != PEG_FMT_FP16X2) {
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-          store_vt(p.po, ((size_t)b * din + col + u) * p.po.npad + gi, zb[u]);
+          store_vt(p.po, ((size_t)b * din + col + u) * p.po.npad + p.po.col0 + gi, zb[u]);
         }
       }
 #pragma unroll
@@ -1757,8 +1770,8 @@ k_tc_linear_bwd(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       for (int w8 = 0; w8 < 8; ++w8) zmax = fmaxf(zmax, bmax_s[w8]);
       const int e = block_exponent(zmax);
       const float vscale = exp2_int(e);
-      if (tid == 0) p.po.vexp[(size_t)b * p.po.vexp_stride + rb] = e;
-      if (gi < p.po.npad) {
+      if (tid == 0) p.po.vexp[(size_t)b * p.po.vexp_stride + p.po.blk0 + rb] = e;
+      if (gi < p.po.rows_pad) {
         for (int cc = 0; cc < cols_per_half; cc += 16) {
           const int col = half * cols_per_half + cc;
           uint32_t r[16];
@@ -1775,7 +1788,7 @@ k_tc_linear_bwd(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
               const float nbar = rowok ? __uint_as_float(r[4 * v4 + u]) : 0.f;
               float v = rinv * ww[u] * nbar - zz[u] * coef;   // the same expression as pass 2: bit-identical Zbar
               if (!rowok || (p.relu_mask && !(zz[u] > 0.f))) v = 0.f;
-              store_vt_f16(p.po, ((size_t)b * din + col + 4 * v4 + u) * p.po.npad + gi, v * vscale);
+              store_vt_f16(p.po, ((size_t)b * din + col + 4 * v4 + u) * p.po.npad + p.po.col0 + gi, v * vscale);
             }
           }
         }

@@ -13,7 +13,9 @@ struct TcWs {
   int npad;
   int fmt;          // operand format of this call (PEG_FMT_*), set by make_ctx from the flags and the control
   int* vexp;        // [B][vexp_stride] block exponents of V^T (fp16x2 format)
-  int vexp_stride;  // = ceil(npad / 128)
+  int vexp_stride;  // = ceil(ldk / 128)
+  int ldk;          // row pitch of V^T in elements = padded GLOBAL node count (== npad unless row-sharded)
+  int col0, blk0;   // row-sharded mode: this rank's rows are columns [col0, col0 + npad) of V^T (else 0)
 };
 
 // per-layer tf32 hi/lo copies of the Linear weights (built once per API call by tc_prep_weights):
@@ -48,6 +50,7 @@ int tc_norm_linear(cudaStream_t st, const PegDims& d, const TcLinear& w, int lay
                    const float* nw, const float* nb, float* M, float* Nout, const ProducerOut& po);
 bool tc_supported(const PegDims& d, int dcols);
 int tc_fmt(const PegDims& d, bool have_absmax);   // operand format of the contraction (PEG_FMT_*)
+int tc_convert_v(cudaStream_t st, const PegDims& d, const TcWs& w, const ContractArgs& a);
 int tc_contract(cudaStream_t st, const PegDims& d, const TcWs& w, const ContractArgs& a, bool bwd);
 int tc_launches_per_contract(bool bwd);
 void set_last_cuda(int err);   // records a cudaError_t for pegncde_last_cuda_error() (defined in pegncde.cu)

@@ -142,7 +142,7 @@ static void carve_feval(Bump& bp, const PegDims& d, const Model& m, bool vjp, Fe
   w.colM = bp.take<float>(B * 2 * dm);
   w.colG = bp.take<float>(B * 2 * dm);
   w.colPart = bp.take<float>(B * ((n + 31) / 32) * 2 * dm);   // chunks: 256 rows (k_colsums), 64 (norm_linear), 32 (linear_bwd)
-  w.tickets_count = B * ((dm + 31) / 32);
+  w.tickets_count = B * ((dm + 31) / 32) + 1;      // + the arrival counter of k_shard_push (row-sharded mode)
   w.tickets = bp.take<unsigned int>(w.tickets_count);
   w.M = bp.take<float>(B * n * dm);
   w.Za = bp.take<float>(B * n * h);
@@ -170,6 +170,8 @@ struct Ctx {
   size_t sv_stride;
   bool use_tc;
   int fmt;   // operand format of the tensor-core contraction for this call (set by make_ctx, copied into w.tc after plan())
+  const PegShard* sh;   // row-sharded mode (nullptr otherwise)
+  unsigned int* xticket;   // arrival counter of k_shard_push (in the tickets area)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -183,6 +185,7 @@ static int stage_prep(Ctx& c, float t) {
   a.params = c.params;
   a.model = c.m;
   a.B = c.d.B; a.n = c.d.n; a.e = c.d.e; a.T = c.d.T;
+  a.n_glob = c.sh ? c.sh->n_glob : c.d.n;
   a.t = t;
   a.sc = c.w.sc;
   a.svec = c.w.svec;
@@ -209,6 +212,10 @@ static ProducerOut producer_out(Ctx& c, int dcols, bool want_vt, float* cb, bool
     po.t16 = c.w.tc.fmt;
     po.vexp = c.w.tc.vexp;
     po.vexp_stride = c.w.tc.vexp_stride;
+    po.npad = c.w.tc.ldk;            // row pitch of V^T (all nodes); this rank's rows start at column col0
+    po.col0 = c.w.tc.col0;
+    po.blk0 = c.w.tc.blk0;
+    po.rows_pad = c.w.tc.npad;
   }
   po.cb = cb;
   po.partial = c.w.colPart;
@@ -243,6 +250,53 @@ static int colsums(Ctx& c, const float* V, int dcols, size_t vec_off, bool with_
   return PEG_OK;
 }
 
+// ---- row-sharded mode: one exchange (see PegShard in pegncde.h).  `with_vt`: this rank's slice of V^T (+ block exponents) travels;
+// cs0 / cs1 (nullable): [B][2][dcols] column-sum vectors that are partial sums over this rank's rows and come back summed over all ranks.
+static int shard_exchange(Ctx& c, bool with_vt, int dcols, float* cs0, float* cs1) {
+  const PegShard& sh = *c.sh;
+  const uint32_t epoch = ++(*sh.epoch);
+  ShardXchg x;
+  memset(&x, 0, sizeof(x));
+  for (int q = 0; q < sh.world; ++q) {
+    x.vt_hi[q] = sh.vt_hi[q]; x.vt_lo[q] = sh.vt_lo[q]; x.vexp[q] = sh.vexp[q]; x.colsum[q] = sh.colsum[q]; x.flags[q] = sh.flags[q];
+  }
+  x.rank = sh.rank; x.world = sh.world; x.epoch = epoch;
+  const size_t esz = c.w.tc.fmt == PEG_FMT_TF32X3 ? 4 : 2;
+  const size_t ldk = (size_t)peg_npad(sh.n_glob);
+  x.half_bytes = (size_t)c.d.B * c.m.dmax * ldk * 4;          // the halves are sized for fp32 words (3xTF32), 16-bit parts use the front
+  x.push_vt = with_vt ? 1 : 0;
+  x.rows = c.d.B * dcols;
+  x.pitch_bytes = ldk * esz;
+  x.col0_bytes = (size_t)sh.row0 * esz;
+  x.slice_bytes = (size_t)c.d.ldn * esz;
+  x.vexp_stride = c.w.tc.vexp_stride; x.vexp_half = c.d.B * c.w.tc.vexp_stride; x.blk0 = sh.row0 / 128; x.nblk_loc = c.d.ldn / 128; x.B = c.d.B;
+  x.push_vexp = (with_vt && c.w.tc.fmt == PEG_FMT_FP16X2) ? 1 : 0;
+  x.cs_src[0] = cs0; x.cs_src[1] = cs1; x.cs_dst[0] = cs0; x.cs_dst[1] = cs1;
+  x.cs_len = c.d.B * 2 * dcols;
+  x.cs_cap = (size_t)c.d.B * 2 * c.m.dmax;
+  x.cs_half = (size_t)sh.world * 2 * x.cs_cap;
+  x.ticket = c.xticket;
+  // the producers / tc_convert_v wrote the half of parity (epoch & 1): point the local operand buffers at the other half for the next one
+  const size_t bytes = (size_t)x.rows * x.slice_bytes * 2;
+  unsigned gx = (unsigned)((bytes / 16 + 255) / 256);
+  gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);      // a few dozen CTAs saturate the NVLink ports; the copy is small next to the contraction
+  k_shard_push<<<dim3(gx, sh.world), 256, 0, c.st>>>(x);
+  PEG_LAUNCH_CHECK();
+  k_shard_wait<<<1, 256, 0, c.st>>>(x);
+  PEG_LAUNCH_CHECK();
+  return PEG_OK;
+}
+// operand buffers of the NEXT exchange: the epoch-parity half the producers must write and the contraction will read
+static void shard_select_half(Ctx& c) {
+  if (!c.sh) return;
+  const PegShard& sh = *c.sh;
+  const uint32_t next = *sh.epoch + 1;
+  const size_t half_bytes = (size_t)c.d.B * c.m.dmax * peg_npad(sh.n_glob) * 4;
+  c.w.tc.Vt_hi = (float*)((char*)sh.vt_hi[sh.rank] + (next & 1u) * half_bytes);
+  c.w.tc.Vt_lo = (float*)((char*)sh.vt_lo[sh.rank] + (next & 1u) * half_bytes);
+  c.w.tc.vexp = sh.vexp[sh.rank] + (size_t)(next & 1u) * c.d.B * c.w.tc.vexp_stride;
+}
+
 static bool contract_on_tc(const Ctx& c, int l) { return c.use_tc && tc_supported(c.d, c.m.layer[l].dout); }
 
 static int contract(Ctx& c, int l, bool bwd, const float* V, const float* Mref, const float* colbuf, float* out,
@@ -269,6 +323,11 @@ static int contract(Ctx& c, int l, bool bwd, const float* V, const float* Mref, 
   a.relu = relu ? 1 : 0;
   a.scale_tg = scale_tg ? 1 : 0;
   a.vt_ready = vt_ready ? 1 : 0;
+  a.planes_t = c.sh ? c.sh->adj_coef_t : nullptr;
+  a.ldk = c.sh ? peg_npad(c.sh->n_glob) : c.d.ldn;
+  a.n_glob = c.sh ? c.sh->n_glob : c.d.n;
+  a.row_block0 = c.sh ? c.sh->row0 / 128 : 0;
+  if (c.sh) a.graph_stride = (size_t)(c.d.T - 1) * 4 * c.d.ldn * a.ldk;
   // algorithmic work of one launch: the four coefficient planes are traversed once (16 n^2 B per graph),
   // V is read and OUT written once; 2 (fwd) or 4 (bwd) n x n x d products.
   const double nn = (double)c.d.n * c.d.n, nd = (double)c.d.n * ld.dout;
@@ -277,7 +336,16 @@ static int contract(Ctx& c, int l, bool bwd, const float* V, const float* Mref, 
   const int dir = bwd ? 1 : 0;
   const bool timed = prof_begin(dir, c.st, bytes, flops);
   int rc = PEG_OK;
-  if (c.use_tc && tc_supported(c.d, ld.dout)) {
+  if (c.sh) {
+    // row-sharded: every rank needs ALL rows of V^T and the column sums over ALL nodes -> convert V if no producer did, then the
+    // exchange over peer memory (push + flags, wait + rank-ordered column sums), then the local row blocks of the contraction
+    if (!vt_ready) { rc = tc_convert_v(c.st, c.d, c.w.tc, a); g_launches.fetch_add(c.w.tc.fmt == PEG_FMT_FP16X2 ? 2 : 1); }
+    if (rc == PEG_OK) rc = shard_exchange(c, true, ld.dout, const_cast<float*>(colbuf), const_cast<float*>(cbM));
+    a.vt_ready = 1;
+    if (rc == PEG_OK) rc = tc_contract(c.st, c.d, c.w.tc, a, bwd);
+    if (rc == PEG_OK) g_launches.fetch_add(1);
+    shard_select_half(c);     // the producers of the next layer write the other epoch-parity half
+  } else if (c.use_tc && tc_supported(c.d, ld.dout)) {
     rc = tc_contract(c.st, c.d, c.w.tc, a, bwd);
     if (rc == PEG_OK) g_launches.fetch_add(vt_ready ? 1 : (c.w.tc.fmt == PEG_FMT_FP16X2 ? 3 : 2));
   } else {
@@ -444,6 +512,14 @@ static int make_ctx(Ctx& c, peg_stream_t stream, const PegDims* dims, const PegC
   c.use_tc = (dims->flags & PEG_FLAG_TENSOR_CORES) != 0;
   if (c.use_tc) tc_refresh_env();
   c.fmt = tc_fmt(*dims, ctl->adj_absmax != nullptr);
+  c.sh = ctl->shard;
+  if (c.sh) {
+    const PegShard& sh = *c.sh;
+    if (sh.world < 1 || sh.world > PEG_MAX_WORLD || sh.rank < 0 || sh.rank >= sh.world) return PEG_ERR_BAD_DIMS;
+    if ((dims->n % 128) != 0 || sh.n_glob != sh.world * dims->n || sh.row0 != sh.rank * dims->n) return PEG_ERR_BAD_DIMS;
+    if (!c.use_tc || dims->e != 0 || (dims->flags & (PEG_FLAG_DIRECTED | PEG_FLAG_BF16X2)) || (dims->h % 32) != 0 || c.fmt == PEG_FMT_BF16X2) return PEG_ERR_UNSUPPORTED;
+    if (!sh.adj_coef_t || !sh.vt_hi || !sh.vt_lo || !sh.vexp || !sh.colsum || !sh.flags || !sh.epoch) return PEG_ERR_NULL_POINTER;
+  }
   return PEG_OK;
 }
 
@@ -451,6 +527,14 @@ static int make_ctx(Ctx& c, peg_stream_t stream, const PegDims* dims, const PegC
 // changed since the previous call; the copies live in the caller's workspace)
 static int reset_tickets(Ctx& c) {
   c.w.tc.fmt = c.fmt;   // plan() carved the workspace after make_ctx chose the format
+  c.xticket = c.w.tickets + (c.w.tickets_count - 1);
+  if (c.sh) {           // row-sharded: V^T spans all n_glob nodes and lives in the peer-visible buffers
+    c.w.tc.ldk = peg_npad(c.sh->n_glob);
+    c.w.tc.col0 = c.sh->row0;
+    c.w.tc.blk0 = c.sh->row0 / 128;
+    c.w.tc.vexp_stride = c.w.tc.ldk / 128;
+    shard_select_half(c);
+  }
   PEG_CUDA(cudaMemsetAsync(c.w.tickets, 0, c.w.tickets_count * sizeof(unsigned int), c.st));
   if (c.use_tc) {
     PEG_TRY(tc_prep_weights(c.st, c.m, c.params, c.w.lin));
@@ -528,6 +612,19 @@ int pegncde_param_offsets(const PegDims* dims, int64_t* offsets) {
   return PEG_OK;
 }
 
+int pegncde_shard_buffer_bytes(const PegDims* dims, int32_t world, size_t* out) {
+  PEG_TRY(check_dims(dims));
+  if (!out) return PEG_ERR_NULL_POINTER;
+  if (world < 1 || world > PEG_MAX_WORLD || (dims->n % 128) != 0) return PEG_ERR_BAD_DIMS;
+  const Model m = make_model(*dims);
+  const size_t ldk = (size_t)world * dims->n;
+  out[0] = 2 * (size_t)dims->B * m.dmax * ldk * 4;
+  out[1] = 2 * (size_t)dims->B * (ldk / 128) * sizeof(int32_t);
+  out[2] = 2 * (size_t)world * 2 * ((size_t)dims->B * 2 * m.dmax) * sizeof(float);
+  out[3] = ((size_t)world + 1) * sizeof(uint32_t);
+  return PEG_OK;
+}
+
 size_t pegncde_stage_store_bytes(const PegDims* dims, int32_t steps) {
   if (check_dims(dims) != PEG_OK || steps < 1) return 0;
   return (size_t)steps * 6 * dims->L * dims->B * dims->n * dims->h * sizeof(float);
@@ -541,9 +638,14 @@ size_t pegncde_workspace_bytes(const PegDims* dims, int32_t which, int32_t steps
 
 static int pack_common(peg_stream_t stream, const PegDims* dims, const float* d, const float* c, const float* b,
                        const float* a, const float* planar, const float* snap, const float* ts, float* adj_coef,
-                       float* adj_rowsum, float* adj_diag, float* adj_total, float* tch_coef, int piece0 = 0, int count = -1) {
+                       float* adj_rowsum, float* adj_diag, float* adj_total, float* tch_coef, int piece0 = 0, int count = -1,
+                       int ncols = -1, int diag_col0 = 0) {
   PEG_TRY(check_dims(dims));
-  if (!adj_rowsum || !adj_diag || !adj_total || !tch_coef) return PEG_ERR_NULL_POINTER;
+  const bool rect = ncols >= 0;          // row-sharded controls: statistics are optional (the transposed shard needs none)
+  if (!rect) ncols = dims->n;
+  if (!rect && (!adj_rowsum || !adj_diag || !adj_total || !tch_coef)) return PEG_ERR_NULL_POINTER;
+  if (rect && (ncols % 32) != 0) return PEG_ERR_BAD_DIMS;
+  const int ncpad = peg_npad(ncols);
   cudaStream_t st = (cudaStream_t)stream;
   const int Tm1 = dims->T - 1;
   if (count < 0) count = Tm1;
@@ -551,17 +653,18 @@ static int pack_common(peg_stream_t stream, const PegDims* dims, const float* d,
   const int nt = dims->ldn / 32;
   dim3 grid(nt, count, dims->B);   // one block per column of tiles (fixed-order column means of the time channel)
   const bool unit_time = planar || snap;   // no time channel in the source: d(time)/dt == 1
+  grid.x = ncpad / 32;                    // one block per column of tiles
   k_pack_adj<<<grid, 256, 0, st>>>(d, c, b, a, planar, snap, ts, dims->n, dims->ldn, Tm1, piece0, count, adj_coef, adj_rowsum,
-                                   adj_diag, adj_total, tch_coef);
+                                   adj_diag, adj_total, tch_coef, ncols, diag_col0);
   PEG_LAUNCH_CHECK();
-  {   // row sums and totals of the tiled planes, reduced in a fixed order (deterministic)
+  if (adj_rowsum && adj_total) {   // row sums and totals of the tiled planes, reduced in a fixed order (deterministic)
     const float* tiled = planar ? planar : adj_coef;
-    k_adj_rowsums<<<dim3(nt, count, dims->B), 256, 0, st>>>(tiled, dims->n, dims->ldn, Tm1, piece0, adj_rowsum);
+    k_adj_rowsums<<<dim3(nt, count, dims->B), 256, 0, st>>>(tiled, dims->n, dims->ldn, Tm1, piece0, adj_rowsum, ncpad);
     PEG_LAUNCH_CHECK();
     k_adj_totals<<<dim3(4 * count, dims->B), 256, 0, st>>>(adj_rowsum, dims->n, Tm1, piece0, adj_total);
     PEG_LAUNCH_CHECK();
   }
-  if (unit_time) {
+  if (unit_time && tch_coef) {
     const size_t slabs = (size_t)dims->B * Tm1;
     const size_t cnt = slabs * 3 * dims->n;
     k_fill_tch_unit<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(tch_coef, dims->n, slabs);
@@ -618,8 +721,26 @@ int pegncde_adj_absmax(peg_stream_t stream, const PegDims* dims, int32_t piece_b
   PEG_CUDA(cudaMemset2DAsync(adj_absmax + (size_t)piece_begin * 4, (size_t)Tm1 * 4 * sizeof(float), 0, (size_t)piece_count * 4 * sizeof(float),
                              dims->B, st));
   const int nt = dims->ldn / 32, ntiles = nt * nt;
-  k_adj_absmax<<<dim3(ntiles < 64 ? ntiles : 64, piece_count, dims->B), 256, 0, st>>>(adj_coef, dims->ldn, Tm1, piece_begin, adj_absmax);
+  k_adj_absmax<<<dim3(ntiles < 64 ? ntiles : 64, piece_count, dims->B), 256, 0, st>>>(adj_coef, dims->ldn, Tm1, piece_begin, adj_absmax, dims->ldn);
   PEG_LAUNCH_CHECK();
+  return PEG_OK;
+}
+
+int pegncde_build_adj_rect(peg_stream_t stream, const PegDims* dims, int32_t n_cols, int32_t diag_col0, const float* ts,
+                           const float* snapshots, float* adj_coef, float* adj_rowsum, float* adj_diag, float* adj_total, float* tch_coef,
+                           float* adj_absmax) {
+  if (!ts || !snapshots || !adj_coef) return PEG_ERR_NULL_POINTER;
+  if (n_cols < 32) return PEG_ERR_BAD_DIMS;
+  PEG_TRY(pack_common(stream, dims, nullptr, nullptr, nullptr, nullptr, nullptr, snapshots, ts, adj_coef, adj_rowsum, adj_diag, adj_total,
+                      tch_coef, 0, -1, n_cols, diag_col0));
+  if (adj_absmax) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Tm1 = dims->T - 1, ncpad = peg_npad(n_cols);
+    PEG_CUDA(cudaMemsetAsync(adj_absmax, 0, (size_t)dims->B * Tm1 * 4 * sizeof(float), st));
+    const int ntiles = (dims->ldn / 32) * (ncpad / 32);
+    k_adj_absmax<<<dim3(ntiles < 64 ? ntiles : 64, Tm1, dims->B), 256, 0, st>>>(adj_coef, dims->ldn, Tm1, 0, adj_absmax, ncpad);
+    PEG_LAUNCH_CHECK();
+  }
   return PEG_OK;
 }
 

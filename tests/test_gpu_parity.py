@@ -942,3 +942,98 @@ def test_reused_adjacency_control_takes_the_node_signal_of_every_call(cuda):
     # a PackedControl handed in as the adjacency control behaves the same way
     again = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), 0.0, 3.0, 0.5, pa.y0.to(cuda), [packed, cxb]).ys[-1]
     assert torch.equal(again, fresh)
+
+
+# ---------------------------------------------------------------------------------------------------
+# row-sharded mode: one graph spread over the ranks by rows, exchange over peer memory
+# ---------------------------------------------------------------------------------------------------
+def _rowshard_problem(n, h, L, T, B, seed, device):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    A = torch.stack([torch.from_numpy(R.synthetic_graph_path(n, T, seed + b)).to(torch.float32) for b in range(B)])   # [B,T,n,n]
+    ts = torch.arange(T, dtype=torch.float32)
+    y0 = torch.randn((B, n, h), generator=g)
+    gy = torch.randn((B, n, h), generator=g)
+    return ts.to(device), A.to(device), y0.to(device), gy.to(device)
+
+
+def _rowshard_reference(vf, ts, A, y0, gy, t1, dt0):
+    """The whole graph on one GPU through the ordinary path."""
+    pc = P.build_control(ts, A)
+    vf.zero_grad()
+    y = y0.clone().requires_grad_(True)
+    yT = P.diffeqsolve(P.ODETerm(vf), P.Tsit5(), 0.0, t1, dt0, y, pc).ys[-1]
+    (yT * gy).sum().backward()
+    return yT.detach(), y.grad.detach(), torch.cat([p.grad.reshape(-1) for p in vf.parameters()])
+
+
+@pytest.mark.parametrize("flags", OPERAND_FORMATS)
+@pytest.mark.parametrize("n,h,B", [(256, 64, 2), (384, 32, 1)])
+def test_row_sharded_solve_on_one_rank_matches_the_ordinary_path(cuda, n, h, B, flags):
+    """world = 1 exercises everything but the wires: rectangular strips, the transposed strip read like a direct one, V^T in the
+    peer-visible buffers, the push / wait kernels (a rank is its own peer), epoch-parity double buffering."""
+    from perm_equiv_graph_neural_cdes_b200 import rowshard as RS
+
+    ts, A, y0, gy = _rowshard_problem(n, h, 3, 4, B, 3, cuda)
+    vf = P.PermEquivGraphVectorField(h, h, h, 3, 0, n, key=5, flags=flags).to(cuda)
+    yT_ref, gy0_ref, gp_ref = _rowshard_reference(vf, ts, A, y0, gy, 1.0, 0.25)
+    ctl = RS.RowShardedControl(ts, A, A.transpose(-1, -2).contiguous(), h, 3, flags=flags)
+    dy = RS.vector_field_rowsharded(vf, ctl, 1.3, y0)
+    assert rel_err(dy, vf(1.3, y0, P.build_control(ts, A))) < 1e-6
+    vf.zero_grad()
+    y = y0.clone().requires_grad_(True)
+    yT = RS.diffeqsolve_rowsharded(vf, ctl, y, 0.0, 1.0, 0.25)
+    (yT * gy).sum().backward()
+    assert rel_err(yT.detach(), yT_ref) < 1e-6
+    assert rel_err(y.grad, gy0_ref) < 1e-5
+    assert rel_err(torch.cat([p.grad.reshape(-1) for p in vf.parameters()]), gp_ref) < 1e-5
+
+
+def _rowshard_rank(rank, world, port, n, h, B, flags, out):
+    import torch.distributed as dist
+
+    from perm_equiv_graph_neural_cdes_b200 import rowshard as RS
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        ts, A, y0, gy = _rowshard_problem(n, h, 3, 4, B, 3, dev)
+        vf = P.PermEquivGraphVectorField(h, h, h, 3, 0, n, key=5, flags=flags).to(dev)
+        r0, r1 = RS.row_range(n, rank, world)
+        ctl = RS.RowShardedControl(ts, A[:, :, r0:r1].contiguous(), A[:, :, :, r0:r1].transpose(-1, -2).contiguous(), h, 3, flags=flags)
+        y = y0[:, r0:r1].clone().requires_grad_(True)
+        yT = RS.diffeqsolve_rowsharded(vf, ctl, y, 0.0, 1.0, 0.25)
+        (yT * gy[:, r0:r1]).sum().backward()
+        torch.cuda.synchronize()
+        res = [yT.detach().cpu(), y.grad.cpu(), torch.cat([p.grad.reshape(-1) for p in vf.parameters()]).cpu()]
+        if rank == 0:
+            ref = [t.cpu() for t in _rowshard_reference(vf, ts, A, y0, gy, 1.0, 0.25)]
+            res += ref
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("flags", OPERAND_FORMATS)
+def test_row_sharded_solve_over_two_gpus(cuda, flags):
+    """Two ranks, one graph: rows of Z_T and of the y0-cotangent from each rank, parameter gradients all-reduced, against the whole
+    graph solved on one GPU (1e-6 / 1e-5: the same kernels, a different summation partition of the column sums)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    n, h, B, world = 512, 64, 2, 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_rowshard_rank, args=(world, port, n, h, B, flags, out), nprocs=world, join=True)
+    yT_ref, gy0_ref, gp_ref = out[0][3], out[0][4], out[0][5]
+    yT = torch.cat([out[r][0] for r in range(world)], dim=1)
+    gy0 = torch.cat([out[r][1] for r in range(world)], dim=1)
+    assert rel_err(yT, yT_ref) < 1e-6
+    assert rel_err(gy0, gy0_ref) < 1e-5
+    for r in range(world):
+        assert rel_err(out[r][2], gp_ref) < 1e-5, r
