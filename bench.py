@@ -525,6 +525,117 @@ def run_ours(args):
         torch.distributed.destroy_process_group()
 
 
+def hashed_strip(n, rows, T, seed, device, transposed):
+    """Synthetic dynamic weighted digraph given ELEMENTWISE by a hash of (knot, i, j), so that every rank can build exactly its strip:
+    `rows` = (r0, r1); returns A_k[:, r0:r1, :] as [T, r1-r0, n], or with transposed=True the same rows of the transposed path
+    (A_k[:, :, r0:r1] transposed).  ~16 weighted out-edges per node, unit self-loops, entries drifting slowly from knot to knot."""
+    r0, r1 = rows
+    a = torch.arange(r0, r1, device=device, dtype=torch.float32)[:, None]
+    b = torch.arange(n, device=device, dtype=torch.float32)[None, :]
+    i, j = (b, a) if transposed else (a, b)       # element (i, j) of the path sits at [i - r0, j], of the transposed strip at [j - r0, i]
+    def h(k1, k2, k3):
+        return torch.frac(torch.sin(i * k1 + j * k2 + (seed % 97) * k3) * 43758.5453).abs()
+    mask = (h(12.9898, 78.233, 37.719) < 16.0 / n).to(torch.float32)
+    w0, w1 = 0.25 + h(4.898, 7.23, 1.17), h(9.12, 3.77, 2.31) - 0.5
+    eye = (i == j).to(torch.float32)
+    out = torch.empty((T, r1 - r0, n), device=device)
+    for k in range(T):
+        out[k] = (mask * (w0 + 0.15 * k * w1) + eye) / 16.0
+    return out
+
+
+def run_rowsharded(args):
+    """`--shard rows`: ONE graph trajectory of the workload spread over the ranks by rows (BASELINE.json configs[4] "row-sharded A at
+    largest n"), forward + exact adjoint; the per-layer exchange of V^T runs over peer memory (k_shard_push / k_shard_wait)."""
+    import perm_equiv_graph_neural_cdes_b200 as P
+    from perm_equiv_graph_neural_cdes_b200 import _lib, rowshard as RS
+
+    D = Dist()
+    wl = dict(WORKLOADS[args.workload])
+    n, h, L = wl["n"], wl["h"], wl["L"]
+    if wl["e"] != 0:
+        raise SystemExit("--shard rows: workloads without the CDE wrapper (e = 0)")
+    B = args.batch or 1
+    T, t1 = 3, 2.0
+    t1_solve = args.t1 if args.t1 > 0 else 1.0
+    dev = D.dev
+    flags = operand_flags(args)
+    r0, r1 = RS.row_range(n, D.rank, D.world)
+    ts = torch.arange(T, device=dev, dtype=torch.float32) * (t1 / (T - 1))
+    rows = torch.stack([hashed_strip(n, (r0, r1), T, 1234 + b, dev, False) for b in range(B)])
+    cols = torch.stack([hashed_strip(n, (r0, r1), T, 1234 + b, dev, True) for b in range(B)])
+    ctl = RS.RowShardedControl(ts, rows, cols, h, L, flags=flags)
+    del rows, cols
+    torch.cuda.empty_cache()
+    vf = P.PermEquivGraphVectorField(h, h, h, L, 0, n, key=1234, flags=flags).to(dev)
+    g = torch.Generator(device=dev).manual_seed(77)           # the same full state on every rank, each keeps its rows
+    y0 = torch.randn((B, n, h), generator=g, device=dev)[:, r0:r1].contiguous()
+    gy = torch.randn((B, n, h), generator=g, device=dev)[:, r0:r1].contiguous()
+    S = len(P.constant_step_table(0.0, t1_solve, wl["dt0"])) - 1
+    l = _lib.lib()
+
+    def step():
+        vf.zero_grad(set_to_none=True)
+        y = y0.detach().requires_grad_(True)
+        yT = RS.diffeqsolve_rowsharded(vf, ctl, y, 0.0, t1_solve, wl["dt0"])
+        (yT * gy).sum().backward()
+        return torch.cat([p.grad.reshape(-1) for p in vf.parameters()])
+
+    for _ in range(max(args.warmup, 1)):
+        flat = step()
+    D.barrier()
+    l.pegncde_profile_enable(args.profile_stride)
+    launches0 = l.pegncde_launch_count()
+    sampler = ClockSampler(D.local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        flat = step()
+    e1.record()
+    D.barrier()
+    clocks = sampler.summary()
+    ms_per_step = D.max_ms(e0.elapsed_time(e1)) / args.steps
+    launches = l.pegncde_launch_count() - launches0
+    prof = {}
+    for d_, nm in ((0, "fwd"), (1, "bwd")):
+        a, b_, c_, by, fl = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        l.pegncde_profile_read(d_, a, b_, c_, by, fl)
+        prof[nm] = dict(launches=a.value, timed=b_.value, ms=c_.value)
+    l.pegncde_profile_enable(0)
+    lo, hi = flat.clone(), flat.clone()
+    if D.world > 1:
+        torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+        torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+    grad_check = {"finite": bool(torch.isfinite(flat).all()), "identical_across_ranks": bool(torch.equal(lo, hi))}
+    if D.rank == 0:
+        pk = peaks()
+        nloc = r1 - r0
+        # per contraction launch and rank: the strip of the path AND the strip of its transpose stream from HBM once (2 x 16 nloc n B);
+        # the exchange ships this rank's slice of V^T (hi + lo parts) to every peer
+        esz = 4 if args.operands == "tf32x3" else 2
+        bytes_launch = B * 2 * 16.0 * nloc * n
+        tot_ms = prof["fwd"]["ms"] + prof["bwd"]["ms"]
+        tot_timed = prof["fwd"]["timed"] + prof["bwd"]["timed"]
+        gbs = bytes_launch * tot_timed / max(tot_ms, 1e-9) / 1e6
+        exchanges = S * (6 + 6) * L + S * 0
+        nvlink = (D.world - 1) * B * h * nloc * esz * 2
+        line = {"metric": METRIC, "value": B * S / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": D.world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32 (contraction: %s split operands on tcgen05, fp32 accumulate)" % args.operands, "data": "synthetic",
+                "config": {"workload": args.workload, "shard": "rows", "n": n, "hidden": h, "layers": L, "knots": T, "graphs": B, "solver_steps": S,
+                           "rows_per_gpu": nloc, "parallelism": "ONE graph row-sharded over %d GPU(s): strips of the path and of its transpose per rank; V^T exchanged per layer over peer memory (k_shard_push / k_shard_wait), parameter gradients all-reduced (NCCL)" % D.world},
+                "gpu_launches": int(launches), "cuda_graph": False, "clocks": clocks, "grad_check": grad_check,
+                "exchange": {"per_solver_step": 12 * L, "nvlink_bytes_per_exchange_and_rank": nvlink, "nvlink_bytes_per_step_and_rank": nvlink * exchanges},
+                "roofline": {"bound": "hbm", "kernel": "k_tc_contract (row strips)", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                             "traffic": None, "algorithmic_bytes_per_launch": bytes_launch, "fwd_avg_us": prof["fwd"]["ms"] / max(prof["fwd"]["timed"], 1) * 1e3,
+                             "bwd_avg_us": prof["bwd"]["ms"] / max(prof["bwd"]["timed"], 1) * 1e3,
+                             "note": "timed region of a launch = conversion of V (top adjoint layer only) + exchange (push, wait) + contraction"}}
+        print(json.dumps(line))
+    if D.world > 1:
+        torch.distributed.destroy_process_group()
+
+
 # points of BASELINE.json configs[4] reported in the `sweep` array of every run (n in {1k, 4k, 16k} x h in {64, 256} + the wide last layer)
 SWEEP_POINTS = ["sweep_n1024_h64", "sweep_n1024_h256", "sweep_n4096_h64", "sweep_n4096_h256", "sweep_n16384_h64", "sweep_n16384_h256", "sweep_n1024_h128_e8"]
 CONFIG_OF = {"sir": "configs[1] (SIR, n=100, B=50 per GPU)", "england": "configs[2] (PGT England shape, n=129)", "twitter": "configs[3] (PGT Twitter shape, n=1000, e=16)"}
@@ -643,6 +754,8 @@ def main():
     ap.add_argument("--t1", type=float, default=0.0, help="profiling only: shorten the solve to [0, t1] (fewer solver steps)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the `sweep` / `configs` arrays (the other BASELINE.json configurations)")
     ap.add_argument("--no-tensor-peaks", action="store_true", help="skip the live cuBLAS tf32 / fp16 / bf16 GEMM measurement")
+    ap.add_argument("--shard", default="batch", choices=["batch", "rows"],
+                    help="batch: trajectories sharded over the GPUs (default); rows: ONE graph row-sharded over the GPUs (large n)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "ours" and args.gpus > 1 and world == 1 and "RANK" not in os.environ:
@@ -654,6 +767,8 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} contradicts WORLD_SIZE={world}")
     if args.impl == "reference":
         run_reference(args)
+    elif args.shard == "rows":
+        run_rowsharded(args)
     else:
         run_ours(args)
 

@@ -39,7 +39,7 @@ def _symmetric(nbytes: int, device, group):
         t = torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=device)
         return t, [t.data_ptr()], None
     t = symm_mem.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
-    hdl = symm_mem.rendezvous(t, group=group)
+    hdl = symm_mem.rendezvous(t, group=group if group is not None else dist.group.WORLD)
     t.zero_()
     return t, [int(p) for p in hdl.buffer_ptrs], hdl
 
