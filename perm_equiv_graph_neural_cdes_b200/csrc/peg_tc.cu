@@ -190,7 +190,8 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   // 16-bit formats: the chunk schedule of this CTA as a table (pair -> K chunk; BFP: + per A-operand variant the factor
   // (A scale) * 2^(E - e_J) as float bits), so the conversion loop spends one LDS.128 per item instead of re-deriving the schedule
   // and the plane weights stay warp-uniform (uniform registers): fewer instructions, a dozen fewer live vector registers
-  int4* sched_s = reinterpret_cast<int4*>(smem_gen + (((tmem_slot + 8u - smem_base) + 15u) & ~15u));
+  int* sched_kc_s = reinterpret_cast<int*>(smem_gen + (tmem_slot + 8u - smem_base));     // [nkc] K chunk of every pair
+  float2* sched_f_s = reinterpret_cast<float2*>(sched_kc_s + ((p.nkc + 1) & ~1));           // [nkc] BFP item factors (variant 0, 1)
 
   if (tid == 0) {
     for (int s = 0; s < SA; ++s)
@@ -285,7 +286,8 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     for (int pr = tid; pr < npairs; pr += TC_THREADS) {
       const int kc = kc_of(pr0 + pr);
       const float f = BFP ? fblk_s[kc >> 2] : 1.f;
-      sched_s[pr] = make_int4(kc, (int)__float_as_uint(f * as0), (int)__float_as_uint(f * as1), 0);
+      sched_kc_s[pr] = kc;
+      if (BFP) sched_f_s[pr] = make_float2(f * as0, f * as1);
     }
     __syncthreads();
   }
@@ -363,10 +365,21 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       }
     };
     // item j -> its plane tile: direct = rows of block I x chunk kc, transposed = chunk kc x columns of block I
+    // BFP: (A scale of variant v) * 2^(E - e_J) of the item whose planes are in flight.  Fetched in load_item, ahead of the item's
+    // 16 plane loads: a shared-memory load issued at the start of the conversion instead queues behind those loads and the operand
+    // stores of the other group, and the whole conversion waits for it (measured: 197 vs 155 us per adjoint launch)
+    float fitem[NA];
+#pragma unroll
+    for (int v = 0; v < NA; ++v) fitem[v] = 1.f;
     const bool tile_ok = 4 * I + cv_u < ntr;           // this warp's 32-row (direct) / 32-column (transposed) strip exists
     const int my_tile = tile_ok ? 4 * I + cv_u : 0;
     auto load_item = [&](int j, int half) {
-      const int kc = F16 ? sched_s[j >> 1].x : kc_of(pr0 + (j >> 1));
+      const int kc = F16 ? sched_kc_s[j >> 1] : kc_of(pr0 + (j >> 1));
+      if constexpr (BFP) {
+        const float2 e = sched_f_s[j >> 1];
+        fitem[0] = e.x;
+        if (NA > 1) fitem[NA - 1] = e.y;
+      }
       if (dirlike) load_tile(F16 ? my_tile : 4 * I + cv_u, kc, half);
       else load_tile(kc, F16 ? my_tile : 4 * I + cv_u, half);
     };
@@ -463,13 +476,14 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     };
     // BFP: the launch-wide A scale rides in the (warp-uniform) weights; the per-item block alignment 2^(E - e_J) is one extra
     // multiply per value (a power of two: exact) -- keeping it out of the weights keeps them in uniform registers
-    float fitem[NA];   // BFP: (A scale of variant v) * 2^(E - e_J) of the current item
-#pragma unroll
-    for (int v = 0; v < NA; ++v) fitem[v] = 1.f;
+
     auto comb = [&](int v, float e0, float e1, float e2, float e3) -> float {
       float r;
       if (BWD && v == NA - 1) r = w[v][1] * e1 + w[v][2] * e2 + w[v][3] * e3;    // A'_s has no `a` term (wD[0] == 0)
       else r = w[v][0] * e0 + w[v][1] * e1 + w[v][2] * e2 + w[v][3] * e3;
+#if defined(PEG_EXP_B)
+      return r;
+#endif
       return BFP ? r * fitem[v] : r;
     };
     // slot / phase of this group's current item, advanced incrementally (SA is a run-time value: no division per item)
@@ -494,11 +508,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       if (cur_st >= SA) { cur_st -= SA; cur_ph ^= 1u; }
     };
     auto convert16 = [&](int j, bool transposed) {
-      if constexpr (BFP) {
-        const int4 e = sched_s[j >> 1];
-        fitem[0] = __uint_as_float((uint32_t)e.y);
-        if (NA > 1) fitem[NA - 1] = __uint_as_float((uint32_t)e.z);
-      }
+
       const uint32_t a_base = smem_base + cur_st * a_bytes;
       mbar_wait(empty_a(cur_st, 0), cur_ph ^ 1u);   // the MMAs that read this slot's previous contents have completed
       if (!transposed) {
@@ -589,7 +599,11 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       // instruction descriptor: fp32 accumulate, K-major A and B, N = nd, M = 128; operand format tf32 (2) or bf16 (1)
+#if defined(PEG_EXP_X)
+      const uint32_t fmt = F16 ? 1u : 2u;
+#else
       const uint32_t fmt = BFP ? 0u : (F16 ? 1u : 2u);   // F16 = 0, BF16 = 1, TF32 = 2
+#endif
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nd >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       uint32_t started = 0u;  // bit acc set once the accumulator has been written (first MMA overwrites)
       for (int j = 0; j < items; ++j) {
@@ -1050,7 +1064,7 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   p.vexp = w.vexp;
   p.vexp_stride = w.vexp_stride;
   const int nv = PEG_TC_VARIANT_SLOTS ? na : 1;   // barrier pairs per A slot (see the kernel)
-  const size_t sched_bytes = f16 ? (size_t)16 * p.nkc + 16 : 0;   // chunk-schedule table of the 16-bit formats (at most nkc pairs per CTA)
+  const size_t sched_bytes = f16 ? (size_t)12 * p.nkc + 32 : 0;   // chunk-schedule table of the 16-bit formats (at most nkc pairs per CTA)
   const size_t smem = (size_t)sa * a_bytes + (size_t)sb * b_bytes + 1024 + 8 * (2 * sa * nv + 2 * sb + 2) + 64 + sched_bytes;
 
   const CUtensorMap* mhi_p = nullptr;

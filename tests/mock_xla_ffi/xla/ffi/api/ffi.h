@@ -28,6 +28,7 @@ struct Buffer {
 template <typename B>
 struct Result {
   B* operator->() const { return nullptr; }
+  B& operator*() const { static B b; return b; }
 };
 template <DataType dt> using ResultBuffer = Result<Buffer<dt>>;
 

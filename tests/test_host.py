@@ -269,20 +269,24 @@ def test_jax_ffi_shim_type_checks_against_the_c_abi():
 
 
 def test_jax_wrapper_operands_match_the_shim_bindings(monkeypatch):
-    """jax_ffi/pegncde_jax.py cannot run for real here (no jax).  Imported on a recording stand-in for `jax`, every ffi_call it
-    makes must hand the handler exactly as many operands / results / attributes as the binding in pegncde_ffi.cc declares."""
+    """jax_ffi/pegncde_jax.py cannot run for real here (no jax).  Imported on recording stand-ins for jax / equinox / diffrax, every
+    ffi_call it makes -- control pre-pass, the vector field and its VJP (through the Equinox module), the whole solve and its adjoint
+    (through fused_diffeqsolve with the diffrax call-site signature) -- must hand the handler exactly as many operands / results /
+    attributes as the binding in pegncde_ffi.cc declares, with vmap_method="broadcast_all"."""
     import importlib.util
     import sys
     import types
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cc = open(os.path.join(root, "perm_equiv_graph_neural_cdes_b200", "jax_ffi", "pegncde_ffi.cc")).read()
-    cc = cc.replace(".PEG_DIM_ATTRS()", "".join(f'.Attr<int32_t>("{k}")' for k in ("B", "n", "h", "e", "L", "T", "flags")))
+    dim_attrs = "".join(f'.Attr<int32_t>("{k}")' for k in ("B", "n", "h", "e", "L", "T", "flags"))
+    cc = cc.replace(".PEG_DIM_ATTRS()", dim_attrs).replace(".PEG_CONTROL_ARGS()", ".Arg<x>()" * 9)
     bindings = {}
     for m in re.finditer(r"XLA_FFI_DEFINE_HANDLER_SYMBOL\((\w+),\s*\w+,(.*?)\);", cc, flags=re.S):
         body = m.group(2)
         bindings[m.group(1)] = (body.count(".Arg<"), body.count(".Ret<"), sorted(re.findall(r'\.Attr<[^>]*>+\("(\w+)"\)', body)))
-    assert set(bindings) == {"PegSolveFwd", "PegSolveBwd", "PegPackAdj", "PegPackX"}
+    handlers = {"PegSolveFwd", "PegSolveBwd", "PegPackAdj", "PegPackX", "PegVfFwd", "PegVfVjp", "PegStepFwd"}
+    assert set(bindings) == handlers
 
     calls, targets = [], {}
 
@@ -291,6 +295,8 @@ def test_jax_wrapper_operands_match_the_shim_bindings(monkeypatch):
             self.shape, self.dtype = tuple(shape), dtype
 
     def ffi_call(name, out_types, vmap_method=None):
+        assert vmap_method == "broadcast_all"      # the batching rule: one custom call for the whole jax.vmap batch
+
         def run(*args, **attrs):
             calls.append((name, len(args), len(out_types), sorted(attrs)))
             return tuple(np.zeros(o.shape, o.dtype) for o in out_types)
@@ -314,30 +320,70 @@ def test_jax_wrapper_operands_match_the_shim_bindings(monkeypatch):
             self.fwd, self.bwd = fwd, bwd
 
         def __call__(self, *a):
-            return self.fn(*a)
+            out, self.res = self.fwd(*a)      # run the forward rule, keep the residuals so the test can drive the backward rule
+            return out
 
     jax.custom_vjp = custom_vjp
-    monkeypatch.setitem(sys.modules, "jax", jax)
-    monkeypatch.setitem(sys.modules, "jax.numpy", jnp)
+    eqx = types.ModuleType("equinox")
+    eqx.Module = object
+    eqx.field = lambda **k: None
+    dfx = types.ModuleType("diffrax")
+    for nm in ("ConstantStepSize", "Tsit5", "PIDController"):
+        setattr(dfx, nm, type(nm, (), {}))
+    dfx.SaveAt = type("SaveAt", (), {"__init__": lambda self, t1=False, steps=False, ts=None: self.__dict__.update(t1=t1, steps=steps, ts=ts)})
+    dfx.ODETerm = type("ODETerm", (), {"__init__": lambda self, vector_field: setattr(self, "vector_field", vector_field)})
+    dfx.diffeqsolve = lambda *a, **k: (_ for _ in ()).throw(AssertionError("the fused combination must not fall back to diffrax"))
+    for name, mod_ in (("jax", jax), ("jax.numpy", jnp), ("equinox", eqx), ("diffrax", dfx)):
+        monkeypatch.setitem(sys.modules, name, mod_)
     real_cdll = ctypes.CDLL
-    monkeypatch.setattr(ctypes, "CDLL", lambda path, *a, **k: types.SimpleNamespace(PegSolveFwd="PegSolveFwd", PegSolveBwd="PegSolveBwd", PegPackAdj="PegPackAdj", PegPackX="PegPackX")
+    monkeypatch.setattr(ctypes, "CDLL", lambda path, *a, **k: types.SimpleNamespace(**{h: h for h in handlers})
                         if str(path).endswith("libpegncde_ffi.so") else real_cdll(path, *a, **k))
     spec = importlib.util.spec_from_file_location("pegncde_jax_under_test", os.path.join(root, "perm_equiv_graph_neural_cdes_b200", "jax_ffi", "pegncde_jax.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    assert targets == {"peg_solve_fwd": "PegSolveFwd", "peg_solve_bwd": "PegSolveBwd", "peg_pack_adj": "PegPackAdj", "peg_pack_x": "PegPackX"}
+    assert set(targets.values()) == handlers and targets["peg_vf_fwd"] == "PegVfFwd" and targets["peg_step_fwd"] == "PegStepFwd"
 
-    dims = dict(B=2, n=40, h=8, e=3, L=2, T=4, flags=0)
     f = lambda *s: np.zeros(s, np.float32)
-    control = mod.pack_control(np.arange(4), [f(2, 3, 40, 40, 2)] * 4, [f(2, 3, 40, 3, 2)] * 4, dims)
-    assert len(control) == 7 and control[0].shape == (2, 4) and control[1].shape == (2, 3, 4 * 64 * 64) and control[6].shape == (2, 3, 3, 40, 6)
-    solve = mod.make_fused_solve(dims, np.linspace(0, 3, 31), ws_bytes=1024, store_elems=16)
-    params, y0 = f(100), f(2, 40, 8)
-    y_ckpt, res = solve.fwd(params, control, y0)
-    assert y_ckpt.shape == (31, 2, 40, 8) and solve(params, control, y0).shape == (31, 2, 40, 8)
-    g_params, g_control, g_y0 = solve.bwd(res, np.zeros_like(y_ckpt))
-    assert g_params.shape == params.shape and g_y0.shape == y0.shape and len(g_control) == 7
+    n, h, e, L, T, B = 40, 8, 3, 2, 4, 2
+    pc = mod.fused_control(np.arange(T), [f(B, T - 1, n, n, 2)] * 4, [f(B, T - 1, n, e, 2)] * 4, hidden_dim=h, num_layers=L)
+    control = pc.control
+    assert pc.dims == dict(B=B, n=n, h=h, e=e, L=L, T=T, flags=1)
+    assert len(control) == 8 and control[0].shape == (B, T) and control[1].shape == (B, T - 1, 4 * 64 * 64) and control[6].shape == (B, T - 1, 3, n, 2 * e)
+    assert control[7].shape == (B, T - 1, 4)
+
+    # the Equinox module: leaves built by the (stand-in) reference class, __call__ = peg_vf_fwd, its VJP = peg_vf_vjp
+    def ref_layer(din, dout):
+        cl = types.SimpleNamespace(linear=types.SimpleNamespace(weight=f(dout, din), bias=f(dout)), norm=types.SimpleNamespace(weight=f(din), bias=f(din)))
+        return types.SimpleNamespace(conv_layer=cl, **{f"param{i}": f(2) for i in range(1, 9)})
+    ref_cls = lambda **kw: types.SimpleNamespace(gnn_layers=[ref_layer(h, h), ref_layer(h, 2 * h * e)])
+    vf = mod.FusedPermEquivGraphVectorField(h, h, 2 * h * e, L, e, n, key=0, reference_cls=ref_cls)
+    nparams = mod.pack_params(vf).shape[0]
+    assert nparams == _lib.lib().pegncde_param_count(_lib.PegDims(B, n, 64, h, e, L, T, 1))
+    dy = vf(0.5, f(B, n, h), [pc])
+    assert dy.shape == (B, n, h) and vf(0.5, f(n, h), pc).shape == (n, h)
+
+    # the diffrax call site of pgt_graph_neural_cde.py:119-129
+    sol = mod.fused_diffeqsolve(terms=dfx.ODETerm(types.SimpleNamespace(vector_field=vf)), solver=dfx.Tsit5(), t0=0.0, t1=3.0, dt0=0.1, y0=f(B, n, h),
+                                args=[pc, None], stepsize_controller=dfx.ConstantStepSize(), saveat=dfx.SaveAt(t1=True))
+    assert sol.ys.shape == (1, B, n, h) and sol.stats["num_steps"] == 30
+    solve = mod.make_fused_solve(pc.dims, np.linspace(0, 3, 31))
+    y_ckpt = solve(f(nparams), control, f(B, n, h))
+    assert y_ckpt.shape == (31, B, n, h)
+    g_params, g_control, g_y0 = solve.bwd(solve.res, np.zeros_like(y_ckpt))
+    assert g_params.shape == (nparams,) and g_y0.shape == (B, n, h) and len(g_control) == 8
+    # backward rule of the vector field
+    vfun = mod.make_fused_vf(pc.dims)
+    seen_before = len(calls)
+    vfun(0.25, f(nparams), control, f(B, n, h))
+    assert calls[seen_before][0] == "peg_vf_fwd"
     seen = {}
+    for name, nargs, nouts, attrs in calls:
+        seen[targets[name]] = (nargs, nouts, attrs)
+    # drive the VJP rule of the vector field and the step handler's operand list by hand (no tracer here)
+    mod._call("peg_vf_vjp", (Struct((B, n, h), np.float32), Struct((nparams,), np.float32), Struct((16,), np.uint8)), f(nparams), *control, f(B, n, h), f(B, n, h),
+              t=np.float32(0.1), **mod._attrs(pc.dims))
+    mod._call("peg_step_fwd", tuple(Struct((B, n, h), np.float32) for _ in range(4)) + (Struct((5, B, n, h), np.float32), Struct((16,), np.uint8)),
+              f(nparams), *control, f(B, n, h), f(B, n, h), t=np.float32(0.1), dt=np.float32(0.05), k1_valid=np.int32(1), **mod._attrs(pc.dims))
     for name, nargs, nouts, attrs in calls:
         seen[targets[name]] = (nargs, nouts, attrs)
     assert seen == bindings, (seen, bindings)
