@@ -223,7 +223,8 @@ __device__ __forceinline__ float exp2_int(int e) { return __uint_as_float((uint3
 __device__ __forceinline__ void store_vt_f16(const ProducerOut& po, size_t o, float vs) {
   const unsigned short h = f16_bits_rn(vs);
   reinterpret_cast<unsigned short*>(po.Thi)[o] = h;
-  reinterpret_cast<unsigned short*>(po.Tlo)[o] = f16_bits_rn(vs - f16_bits_to_f32(h));
+  float lo_ = vs - f16_bits_to_f32(h);
+  reinterpret_cast<unsigned short*>(po.Tlo)[o] = f16_bits_rn(lo_);
 }
 // max over the warp of a non-negative value
 __device__ __forceinline__ float warp_max(float v) {

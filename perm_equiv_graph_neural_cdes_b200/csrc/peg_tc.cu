@@ -118,6 +118,7 @@ struct TcParams {
   const int* vexp; // fp16x2 format: [B][vexp_stride] block exponents of V^T (one per 128 nodes)
   int vexp_stride;
   float* partial; // [B][accumulators][n][d] fp32, zeroed by the host before mode 1
+  int stagger_ns; // 16-bit formats: start-up delay of converter group 1 (see the conversion loop)
   int experiment; // timing experiments, compiled in only with -DPEG_TC_EXPERIMENTS (never in the shipped library):
                   // 1 = B operand loaded for the first pairs only, 2 = no MMAs.  Always 0 otherwise.
 };
@@ -138,6 +139,15 @@ __device__ __forceinline__ LightCoef light_coef(float wa, float wd) {
   return c;
 }
 
+// fp16x2 (block floating point): V^T holds V * 2^(e_J) per 128-node block J.  The blocks are aligned to the smallest exponent E
+// inside the A operand (its entries are multiplied by 2^(E - e_J) <= 1, exact), so every accumulator ends up scaled by 2^E times the
+// A scale.  E is cheap enough (one exponent per 128 nodes) for every thread that needs it to recompute it from global memory.
+__device__ __forceinline__ int bfp_min_exponent(const int* __restrict__ ve, int nblk) {
+  int e = PEG_VEXP_MAX;
+  for (int J = 0; J < nblk; ++J) e = min(e, __ldg(ve + J));
+  return e;
+}
+
 // KIND 0 = forward, 1 = adjoint with four 3xTF32 products (default), 2 = LIGHT adjoint (two 3xTF32 products + two single-pass
 // ones; PEG_TC_ADJ_LIGHT=1, looser tolerance on the param1 / param2 gradients: 2.5e-3 instead of 1e-3)
 // FMT 0 = 3xTF32 operands (fp32 words, SWIZZLE_128B tiles, kind::tf32: error ~2^-22 per product);
@@ -150,8 +160,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   constexpr bool F16 = FMT != PEG_FMT_TF32X3;       // 16-bit parts: bf16x2 or fp16x2
   constexpr bool BFP = FMT == PEG_FMT_FP16X2;       // block floating point (see PEG_FMT_FP16X2)
   static_assert(!(F16 && LIGHT), "the LIGHT adjoint exists for the tf32 operand format only");
-  __shared__ float fblk_s[BFP ? 512 : 1];           // BFP: 2^(E - e_J) of every 128-node block J of this graph (E = min_J e_J)
-  __shared__ int emin_s;
+
   constexpr int ATILE = F16 ? TC_BM * TC_BK * 2 : TC_ATILE;   // one A-operand tile (hi or lo part)
   constexpr int ESZ = F16 ? 2 : 4;                            // operand element size
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -216,22 +225,6 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-  if constexpr (BFP) {
-    // V^T holds V * 2^(e_J) per 128-node block J.  The blocks are aligned to the smallest exponent E inside the A operand (its
-    // plane weights are multiplied by 2^(E - e_J) <= 1, exact), so every accumulator ends up scaled by 2^E times the A scale.
-    const int nblk = (a.ldk + 127) >> 7;
-    const int* ve = p.vexp + (size_t)b * p.vexp_stride;
-    if (warp == 0) {
-      int e = PEG_VEXP_MAX;
-      for (int J = lane; J < nblk; J += 32) e = min(e, ve[J]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) e = min(e, __shfl_xor_sync(0xffffffffu, e, o));
-      if (lane == 0) emin_s = e;
-    }
-    __syncthreads();
-    for (int J = tid; J < nblk; J += TC_THREADS) fblk_s[J] = exp2_int(max(emin_s - ve[J], -120));
-    __syncthreads();
-  }
   const StageScalars* scp = a.sc + b;
   struct { float wA[4], wD[4]; int interval; } sc;
 #pragma unroll
@@ -283,9 +276,11 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
 
   if constexpr (F16) {
     const float as0 = BFP ? exp2_int(a_scale_exponent(0)) : 1.f, as1 = (BFP && BWD) ? exp2_int(a_scale_exponent(NA - 1)) : 1.f;
+    const int* ve = BFP ? p.vexp + (size_t)b * p.vexp_stride : nullptr;
+    const int Emin = BFP ? bfp_min_exponent(ve, (a.ldk + 127) >> 7) : 0;
     for (int pr = tid; pr < npairs; pr += TC_THREADS) {
       const int kc = kc_of(pr0 + pr);
-      const float f = BFP ? fblk_s[kc >> 2] : 1.f;
+      const float f = BFP ? exp2_int(max(Emin - __ldg(ve + (kc >> 2)), -120)) : 1.f;
       sched_kc_s[pr] = kc;
       if (BFP) sched_f_s[pr] = make_float2(f * as0, f * as1);
     }
@@ -481,9 +476,6 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       float r;
       if (BWD && v == NA - 1) r = w[v][1] * e1 + w[v][2] * e2 + w[v][3] * e3;    // A'_s has no `a` term (wD[0] == 0)
       else r = w[v][0] * e0 + w[v][1] * e1 + w[v][2] * e2 + w[v][3] * e3;
-#if defined(PEG_EXP_B)
-      return r;
-#endif
       return BFP ? r * fitem[v] : r;
     };
     // slot / phase of this group's current item, advanced incrementally (SA is a run-time value: no division per item)
@@ -563,6 +555,10 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       if (!tile_ok) {
         for (int j = grp; j < items; j += 2) idle16(j);
       } else {
+        // The two groups must run OUT of phase (one converts while the other's loads are in flight).  Started together they can
+        // lock in phase -- both wait for loads, then both convert and share the issue slots -- which costs a conversion time per
+        // item pair (measured on the fp16x2 adjoint: 195 vs 156 us per launch).  Group 1 therefore starts half a cycle late.
+        if (grp == 1 && p.stagger_ns > 0) __nanosleep((unsigned)p.stagger_ns);
         if (items > 0) load_item(grp, 2);   // group 0: direct items (even j); group 1: transposed items (odd j)
         if (grp == 0) for (int j = 0; j < items; j += 2) convert16(j, false);
         else          for (int j = 1; j < items; j += 2) convert16(j, tposed);
@@ -599,11 +595,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       // instruction descriptor: fp32 accumulate, K-major A and B, N = nd, M = 128; operand format tf32 (2) or bf16 (1)
-#if defined(PEG_EXP_X)
-      const uint32_t fmt = F16 ? 1u : 2u;
-#else
       const uint32_t fmt = BFP ? 0u : (F16 ? 1u : 2u);   // F16 = 0, BF16 = 1, TF32 = 2
-#endif
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nd >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       uint32_t started = 0u;  // bit acc set once the accumulator has been written (first MMA overwrites)
       for (int j = 0; j < items; ++j) {
@@ -714,7 +706,8 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         tmem_wait_ld();
         if constexpr (BFP) {   // undo the block scales (powers of two: exact); accumulator acc = type * 2 + v carries the scale of variant v
           // |exponents| <= 60: both factors are normal numbers
-          const float d0 = exp2_int(-a_scale_exponent(0)) * exp2_int(-emin_s), d1 = BWD ? exp2_int(-a_scale_exponent(NA - 1)) * exp2_int(-emin_s) : 1.f;
+          const int Emin = bfp_min_exponent(p.vexp + (size_t)b * p.vexp_stride, (a.ldk + 127) >> 7);
+          const float d0 = exp2_int(-a_scale_exponent(0)) * exp2_int(-Emin), d1 = BWD ? exp2_int(-a_scale_exponent(NA - 1)) * exp2_int(-Emin) : 1.f;
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
             r0[u] = __float_as_uint(__uint_as_float(r0[u]) * d0);
@@ -870,7 +863,7 @@ static EncodeTiledFn get_encode() {
 // walks the whole environment and a solve enqueues thousands of launches) into a PER-THREAD snapshot: API calls on different
 // threads never share or overwrite each other's copy.
 struct TcEnv {
-  int nd_max = 0, stages_a = 0, stages_b = 0, cluster = 0, experiment = 0, split_max = 0, split_minpairs = 0;
+  int nd_max = 0, stages_a = 0, stages_b = 0, cluster = 0, experiment = 0, split_max = 0, split_minpairs = 0, stagger_ns = -1;
   bool no_splitk = false, no_linear = false;
 };
 static thread_local TcEnv g_env;
@@ -886,6 +879,7 @@ void tc_refresh_env() {
 #endif
   e.split_max = env_int("PEG_TC_SPLIT_MAX");
   e.split_minpairs = env_int("PEG_TC_SPLIT_MINPAIRS");
+  e.stagger_ns = getenv("PEG_TC_STAGGER_NS") ? env_int("PEG_TC_STAGGER_NS") : -1;
   e.no_splitk = getenv("PEG_TC_NO_SPLITK") != nullptr;
   e.no_linear = getenv("PEG_TC_NO_LINEAR") != nullptr;
   g_env = e;
@@ -1061,6 +1055,7 @@ int tc_contract(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contrac
   while (cluster > 1 && (nblk < cluster || (p.nd / cluster) % 8 != 0)) cluster >>= 1;
   p.cluster = cluster;
   p.experiment = g_env.experiment;
+  p.stagger_ns = g_env.stagger_ns >= 0 ? g_env.stagger_ns : (bwd ? 1200 : 0);
   p.vexp = w.vexp;
   p.vexp_stride = w.vexp_stride;
   const int nv = PEG_TC_VARIANT_SLOTS ? na : 1;   // barrier pairs per A slot (see the kernel)

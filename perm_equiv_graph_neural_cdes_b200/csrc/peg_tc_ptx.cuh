@@ -159,11 +159,6 @@ __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, u
 // becomes a systematic bias and the param1/param2 gradients (sums with ~1e3-fold cancellation) lose their 3e-4 parity (measured).
 // Below the fp16 normal range (|x| < 2^-14 after scaling = 2^-28 of the block maximum) the pack rounds hi once more: <= 2^-25 absolute.
 __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-#if defined(PEG_EXP_A)
-  hi = pack_bf16x2(x0, x1);
-  lo = pack_bf16x2(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xffff0000u));
-  return;
-#endif
   const float h0 = __uint_as_float((__float_as_uint(x0) + 0x1000u) & 0xffffe000u), h1 = __uint_as_float((__float_as_uint(x1) + 0x1000u) & 0xffffe000u);
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(h1), "f"(h0));
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
