@@ -211,6 +211,33 @@ int pegncde_step_fwd(peg_stream_t stream, const PegDims* dims, const PegControl*
                      float dt, const float* y, float* k1, int32_t k1_valid, float* y1, float* y_err, float* k7,
                      float* k_stages, void* workspace, size_t workspace_bytes);
 
+/* ---- batched adaptive solves: the step-size controller on the device --------------------------------------------------
+ * diffrax PIDController(rtol, atol) (pcoeff = 0, icoeff = 1, dcoeff = 0) + _clip_to_end under jax.vmap(model)
+ * (src/models/graph_neural_cde.py:53-54,86-104; src/configs/loss_configs.py:44): every trajectory of the batch has its own step
+ * sequence.  pegncde_step_fwd_batched attempts one step of EVERY trajectory (per-trajectory start t_dev[b] and size dt_dev[b], both
+ * device arrays); pegncde_adaptive_control evaluates the scaled error norms, accepts / rejects per trajectory, emits the dense-output
+ * samples of accepted steps (SaveAt(ts)), advances y / k1 (FSAL) / the checkpoints and writes the next (t_dev, dt_dev) -- no host round
+ * trip per step; the host polls `done` every few attempts.  Finished trajectories are stepped with dt = 0 and left untouched. */
+typedef struct PegAdaptState {
+  float tprev, tnext;                        /* the step being / to be attempted (host initialises: t0, first tnext)        */
+  int32_t done, nacc, attempts, rejected;    /* host initialises to 0                                                       */
+  int32_t mi;                                /* next save time to emit (0)                                                   */
+  int32_t mi0, mi1, keep;                    /* scratch of the last decision                                                 */
+  float h;
+  int32_t overflow;                          /* set when the accepted-step table (cap entries) is full: the host must grow it */
+} PegAdaptState;
+int pegncde_step_fwd_batched(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params, const float* t_dev /* [B] */,
+                             const float* dt_dev /* [B] */, const float* y, float* k1, int32_t k1_valid, float* y1, float* y_err, float* k7,
+                             float* k_stages, void* workspace, size_t workspace_bytes);
+/* y_ckpt [B, cap+1, n, h] (slot 0 = y0, written by the host), step_tab [B, cap+1] (slot 0 = t0), ys_save [n_save, B, n, h],
+ * sample_step / sample_theta [n_save, B]: for every save time the accepted step that emitted it and the position inside it
+ * (what the adjoint needs), sumsq_scratch [B]. */
+int pegncde_adaptive_control(peg_stream_t stream, const PegDims* dims, PegAdaptState* state /* [B] device */, float rtol, float atol, float t1,
+                             float safety, float factormin, float factormax, int32_t error_order, const float* save_ts, int32_t n_save,
+                             int32_t cap, float* y, const float* y1, const float* y_err, float* k1, const float* k7, const float* k_stages,
+                             float* y_ckpt, float* ys_save, float* step_tab, int32_t* sample_step, float* sample_theta, float* t_dev,
+                             float* dt_dev, float* sumsq_scratch);
+
 /* ---- Tsit5 dense output: diffrax SaveAt(ts=...) (call site src/models/graph_neural_cde.py:86-104) ---------- */
 /* out = y + dt * sum_i b_i(theta) k_i with Tsitouras' 4th-order interpolant, theta in [0,1] inside the step
  * [t, t+dt]; k_stages = k2..k6 as written by pegncde_step_fwd. */

@@ -33,6 +33,12 @@ class PegShard(Structure):
                 ("flags", POINTER(c_void_p)), ("epoch", POINTER(ctypes.c_uint32))]
 
 
+class PegAdaptState(Structure):
+    """Per-trajectory state of the device-side step-size controller (include/pegncde.h)."""
+    _fields_ = [("tprev", c_float), ("tnext", c_float), ("done", c_int32), ("nacc", c_int32), ("attempts", c_int32), ("rejected", c_int32),
+                ("mi", c_int32), ("mi0", c_int32), ("mi1", c_int32), ("keep", c_int32), ("h", c_float), ("overflow", c_int32)]
+
+
 class PegControl(Structure):
     _fields_ = [(k, c_void_p) for k in ("ts", "adj_coef", "adj_rowsum", "adj_diag", "adj_total", "tch_coef", "x_coef", "adj_colsum", "adj_absmax")] + [("shard", POINTER(PegShard))]
 
@@ -69,6 +75,9 @@ SIGNATURES = {
     "pegncde_vf_fwd": (c_int, [_P, _DIMS, _CTL, _P, c_float, _P, _P, _P, c_size_t]),
     "pegncde_vf_vjp": (c_int, [_P, _DIMS, _CTL, _P, c_float, _P, _P, _P, _P, _P, _P, c_size_t]),
     "pegncde_step_fwd": (c_int, [_P, _DIMS, _CTL, _P, c_float, c_float, _P, _P, c_int32, _P, _P, _P, _P, _P, c_size_t]),
+    "pegncde_step_fwd_batched": (c_int, [_P, _DIMS, _CTL, _P, _P, _P, _P, _P, c_int32, _P, _P, _P, _P, _P, c_size_t]),
+    "pegncde_adaptive_control": (c_int, [_P, _DIMS, _P, c_float, c_float, c_float, c_float, c_float, c_float, c_int32, _P, c_int32, c_int32,
+                                         _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pegncde_tsit5_dense": (c_int, [_P, _DIMS, c_float, c_float, _P, _P, _P, _P, _P]),
     "pegncde_tsit5_dense_weights": (None, [c_float, POINTER(c_float)]),
     "pegncde_scaled_sumsq": (c_int, [_P, _DIMS, _P, _P, _P, _P, c_float, c_float, _P]),

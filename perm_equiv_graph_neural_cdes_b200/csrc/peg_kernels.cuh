@@ -370,6 +370,9 @@ struct PrepArgs {
   int n_glob;   // node count the 1/n, 1/n^2 factors refer to (== n unless row-sharded)
   int B, n, e, T;
   float t;
+  const float* t_dev;    // nullable: per-graph stage time = t_dev[b] + tcoef * dt_dev[b] (batched adaptive steps)
+  const float* dt_dev;
+  float tcoef;
   StageScalars* sc;
   float* svec;
 };
@@ -381,13 +384,14 @@ __global__ void __launch_bounds__(256) k_stage_prep(PrepArgs a) {
   const int b = blockIdx.y, tid = threadIdx.x;
   const int n = a.n, L = a.model.L, Tm1 = a.T - 1;
   const float* ts = a.ctl.ts + (size_t)b * a.T;
+  const float tq = a.t_dev ? a.t_dev[b] + a.tcoef * a.dt_dev[b] : a.t;      // the stage time of this graph
   // index = clip(searchsorted(ts, t, 'left') - 1, 0, T-2)  (diffrax CubicInterpolation._interpret_t)
   float cnt = 0.f;
-  for (int i = tid; i < a.T; i += blockDim.x) cnt += (ts[i] < a.t) ? 1.f : 0.f;
+  for (int i = tid; i < a.T; i += blockDim.x) cnt += (ts[i] < tq) ? 1.f : 0.f;
   cnt = block_sum(cnt, sh);
   int iv = (int)(cnt + 0.5f) - 1;
   iv = max(0, min(iv, a.T - 2));
-  const float s = a.t - ts[iv];
+  const float s = tq - ts[iv];
   const float wA[4] = {1.f, s, s * s, s * s * s};
   const float wD[4] = {0.f, 1.f, 2.f * s, 3.f * s * s};
   const size_t slab = (size_t)b * Tm1 + iv;
@@ -465,16 +469,20 @@ struct CombArgs {
   int cnt;
   float* out;
   size_t count4;
+  // batched adaptive steps: every graph has its own step size -- coefficients c[j], j >= 1, are multiplied by gscale[graph]
+  const float* gscale;   // nullable [B]
+  size_t per_graph4;     // float4 elements per graph
 };
 __global__ void __launch_bounds__(256) k_rk_combine(CombArgs a) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.count4) return;
+  const float gs = a.gscale ? a.gscale[i / a.per_graph4] : 1.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     if (j < a.cnt) {
       const float4 v = reinterpret_cast<const float4*>(a.x[j])[i];
-      const float c = a.c[j];
+      const float c = (j > 0 && a.gscale) ? a.c[j] * gs : a.c[j];
       acc.x = fmaf(c, v.x, acc.x);
       acc.y = fmaf(c, v.y, acc.y);
       acc.z = fmaf(c, v.z, acc.z);
@@ -503,6 +511,120 @@ __global__ void __launch_bounds__(1024) k_scaled_sumsq(const float* __restrict__
   }
   const float tot = block_sum(acc, sh);
   if (threadIdx.x == 0) out[blockIdx.x] = tot;
+}
+
+// =====================================================================================
+// Batched adaptive step-size control on the device (diffrax PIDController(rtol, atol) with its defaults pcoeff = 0, icoeff = 1,
+// dcoeff = 0 + _clip_to_end, call site src/models/graph_neural_cde.py:53-54,86-104): every trajectory of the batch keeps its own
+// (tprev, tnext), accepted-step table and dense-output bookkeeping in device memory, so a batch advances with ONE step launch per
+// attempt and no host round trip per step.
+// =====================================================================================
+struct AdaptState {        // one per trajectory (PegAdaptState in pegncde.h)
+  float tprev, tnext;      // the step that is being / will be attempted
+  int done, nacc, attempts, rejected;
+  int mi;                  // next save time to emit
+  int mi0, mi1;            // save indices emitted by the step just accepted: [mi0, mi1)
+  int keep;                // decision for the step just attempted
+  float h;                 // its size
+  int overflow;            // the accepted-step table is full (the host grows it)
+};
+
+// one thread per trajectory: decide, record, choose the next step
+__global__ void k_adapt_decide(AdaptState* st, const float* __restrict__ sumsq, int B, float nh, float t1, float safety, float factormin,
+                               float factormax, float inv_order, const float* __restrict__ save_ts, int M, int cap,
+                               float* __restrict__ step_tab /* [B][cap+1] */, int* __restrict__ sample_step /* [M][B] */,
+                               float* __restrict__ sample_theta /* [M][B] */, float* __restrict__ dt_out /* [B] next h */,
+                               float* __restrict__ t_out /* [B] next tprev */) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  AdaptState s = st[b];
+  s.keep = 0; s.mi0 = s.mi1 = s.mi;
+  if (!s.done && !s.overflow) {
+    const float h = s.tnext - s.tprev;
+    const float err = sqrtf(sumsq[b] / nh);
+    const bool keep = err < 1.0f;
+    float inv = 1.0f / err;
+    if (!isfinite(inv)) inv = isnan(inv) ? 1.0f : 3.402823466e+38f;
+    float factor = safety * powf(inv, inv_order);
+    factor = fminf(fmaxf(factor, keep ? 1.0f : factormin), factormax);
+    const float dt_new = h * factor;
+    s.attempts += 1;
+    s.h = h;
+    float tprev_new = s.tprev;
+    if (keep) {
+      if (s.nacc >= cap) { s.overflow = 1; s.attempts -= 1; }
+      else {
+        s.keep = 1;
+        while (s.mi1 < M && save_ts[s.mi1] <= s.tnext) {
+          const float theta = fminf(fmaxf((save_ts[s.mi1] - s.tprev) / h, 0.f), 1.f);
+          sample_step[(size_t)s.mi1 * B + b] = s.nacc;
+          sample_theta[(size_t)s.mi1 * B + b] = theta;
+          s.mi1 += 1;
+        }
+        s.mi = s.mi1;
+        s.nacc += 1;
+        step_tab[(size_t)b * (cap + 1) + s.nacc] = s.tnext;
+        tprev_new = s.tnext;
+      }
+    } else {
+      s.rejected += 1;
+    }
+    if (!s.overflow) {
+      float tn = tprev_new + dt_new;
+      if (tn > t1 - 1e-6f) tn = keep ? t1 : tprev_new + 0.5f * (t1 - tprev_new);     // diffrax _clip_to_end (fp32 times)
+      s.tprev = tprev_new;
+      s.tnext = tn;
+      if (keep && tprev_new >= t1) s.done = 1;
+    }
+  }
+  st[b] = s;
+  t_out[b] = s.tprev;
+  dt_out[b] = (s.done || s.overflow) ? 0.f : s.tnext - s.tprev;
+}
+
+// elementwise: dense-output samples of the accepted step, then y <- y1, k1 <- k7 (FSAL) and the checkpoint, per trajectory
+__global__ void __launch_bounds__(256) k_adapt_apply(const AdaptState* __restrict__ st, int B, size_t per_graph4, int cap,
+                                                     float4* __restrict__ y, const float4* __restrict__ y1, float4* __restrict__ k1,
+                                                     const float4* __restrict__ k7, const float4* __restrict__ kst /* [5][B][nh] */,
+                                                     float4* __restrict__ y_ckpt /* [B][cap+1][nh] */, float4* __restrict__ ys_save /* [M][B][nh] */,
+                                                     const float* __restrict__ sample_theta) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * per_graph4) return;
+  const int b = (int)(i / per_graph4);
+  const size_t e = i - (size_t)b * per_graph4;
+  const AdaptState s = st[b];
+  if (!s.keep) return;
+  const float4 yv = y[i], k1v = k1[i], k7v = k7[i];
+  if (s.mi1 > s.mi0) {
+    float4 ks[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) ks[q] = kst[(size_t)q * B * per_graph4 + i];
+    for (int m = s.mi0; m < s.mi1; ++m) {
+      const float th = sample_theta[(size_t)m * B + b];
+      // Tsit5 dense-output weights b_i(theta) (the expanded Horner form of pegncde_tsit5_dense_weights)
+      const float r[7][4] = {{1.0f, -2.763706197274826f, 2.9132554618219126f, -1.0530884977290216f},
+                             {0.0f, 0.13169999999999998f, -0.2234f, 0.1017f},
+                             {0.0f, 3.9302962368947516f, -5.941033872131505f, 2.490627285651253f},
+                             {0.0f, -12.411077166933676f, 30.33818863028232f, -16.548102889244902f},
+                             {0.0f, 37.50931341651104f, -88.1789048947664f, 47.37952196281928f},
+                             {0.0f, -27.896526289197286f, 65.09189467479366f, -34.87065786149661f},
+                             {0.0f, 1.5f, -4.0f, 2.5f}};
+      float w[7];
+#pragma unroll
+      for (int q = 0; q < 7; ++q) w[q] = s.h * (th * (r[q][0] + th * (r[q][1] + th * (r[q][2] + th * r[q][3]))));
+      float4 o = yv;
+      auto axpy = [&](float c, const float4& v) { o.x = fmaf(c, v.x, o.x); o.y = fmaf(c, v.y, o.y); o.z = fmaf(c, v.z, o.z); o.w = fmaf(c, v.w, o.w); };
+      axpy(w[0], k1v);
+#pragma unroll
+      for (int q = 0; q < 5; ++q) axpy(w[q + 1], ks[q]);
+      axpy(w[6], k7v);
+      ys_save[((size_t)m * B + b) * per_graph4 + e] = o;
+    }
+  }
+  const float4 ynew = y1[i];
+  y[i] = ynew;
+  k1[i] = k7v;
+  y_ckpt[((size_t)b * (cap + 1) + s.nacc) * per_graph4 + e] = ynew;
 }
 
 // =====================================================================================

@@ -171,6 +171,9 @@ struct Ctx {
   bool use_tc;
   int fmt;   // operand format of the tensor-core contraction for this call (set by make_ctx, copied into w.tc after plan())
   const PegShard* sh;   // row-sharded mode (nullptr otherwise)
+  const float* t_dev;   // batched adaptive steps: per-graph step start / size (nullptr otherwise) and the stage's c_i
+  const float* dt_dev;
+  float tcoef;
   unsigned int* xticket;   // arrival counter of k_shard_push (in the tickets area)
 };
 
@@ -181,6 +184,7 @@ struct Ctx {
 // ------------------------------------------------------------------------------------------
 static int stage_prep(Ctx& c, float t) {
   PrepArgs a;
+  a.t_dev = c.t_dev; a.dt_dev = c.dt_dev; a.tcoef = c.tcoef;
   a.ctl = c.ctl;
   a.params = c.params;
   a.model = c.m;
@@ -477,7 +481,8 @@ static int feval_vjp(Ctx& c, float t, float* const* zin, const float* kbar, floa
   return PEG_OK;
 }
 
-static int combine(Ctx& c, float* out, int cnt, const float* const* xs, const double* cs) {
+// out = sum_j cs[j] xs[j]; with `gscale` ([B], device) the coefficients of xs[1..] are multiplied by the graph's own factor (its step size)
+static int combine(Ctx& c, float* out, int cnt, const float* const* xs, const double* cs, const float* gscale = nullptr) {
   CombArgs a;
   memset(&a, 0, sizeof(a));
   int k = 0;
@@ -490,6 +495,8 @@ static int combine(Ctx& c, float* out, int cnt, const float* const* xs, const do
   a.cnt = k;
   a.out = out;
   a.count4 = (size_t)c.d.B * c.d.n * c.d.h / 4;
+  a.gscale = gscale;
+  a.per_graph4 = (size_t)c.d.n * c.d.h / 4;
   k_rk_combine<<<(unsigned)((a.count4 + 255) / 256), 256, 0, c.st>>>(a);
   PEG_LAUNCH_CHECK();
   return PEG_OK;
@@ -512,6 +519,8 @@ static int make_ctx(Ctx& c, peg_stream_t stream, const PegDims* dims, const PegC
   c.use_tc = (dims->flags & PEG_FLAG_TENSOR_CORES) != 0;
   if (c.use_tc) tc_refresh_env();
   c.fmt = tc_fmt(*dims, ctl->adj_absmax != nullptr);
+  c.t_dev = c.dt_dev = nullptr;
+  c.tcoef = 0.f;
   c.sh = ctl->shard;
   if (c.sh) {
     const PegShard& sh = *c.sh;
@@ -819,6 +828,78 @@ int pegncde_step_fwd(peg_stream_t stream, const PegDims* dims, const PegControl*
     for (int j = 0; j < 7; ++j) { xs[j] = k[j]; cs[j] = (double)dt * tb.berr[j]; }
     PEG_TRY(combine(c, y_err, 7, xs, cs));
   }
+  return PEG_OK;
+}
+
+int pegncde_step_fwd_batched(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params, const float* t_dev,
+                             const float* dt_dev, const float* y, float* k1, int32_t k1_valid, float* y1, float* y_err, float* k7,
+                             float* k_stages, void* workspace, size_t workspace_bytes) {
+  Ctx c;
+  PEG_TRY(make_ctx(c, stream, dims, ctl, params));
+  if (!t_dev || !dt_dev || !y || !k1 || !y1 || !k7 || !workspace) return PEG_ERR_NULL_POINTER;
+  if (c.sh) return PEG_ERR_UNSUPPORTED;
+  if (workspace_bytes < plan(*dims, PEG_WS_STEP, 0, nullptr, nullptr, nullptr)) return PEG_ERR_WORKSPACE;
+  SolveWs s;
+  plan(*dims, PEG_WS_STEP, 0, workspace, &c.w, &s);
+  PEG_TRY(reset_tickets(c));
+  const Tsit5& tb = tsit5();
+  const size_t st = (size_t)dims->B * dims->n * dims->h;
+  float* k[7] = {k1, s.k[1], s.k[2], s.k[3], s.k[4], s.k[5], k7};
+  if (k_stages)
+    for (int i = 1; i < 6; ++i) k[i] = k_stages + (size_t)(i - 1) * st;
+  c.t_dev = t_dev; c.dt_dev = dt_dev;
+  if (!k1_valid) { c.tcoef = 0.f; PEG_TRY(feval_fwd(c, 0.f, y, k[0], nullptr)); }
+  for (int i = 1; i < 7; ++i) {
+    const float* xs[8];
+    double cs[8];
+    xs[0] = y; cs[0] = 1.0;
+    for (int j = 0; j < i; ++j) { xs[j + 1] = k[j]; cs[j + 1] = tb.a[i][j]; }     // times the graph's own dt (gscale)
+    float* zin = (i == 6) ? y1 : s.Z0;
+    PEG_TRY(combine(c, zin, i + 1, xs, cs, dt_dev));
+    c.tcoef = (i == 6) ? 1.f : (float)tb.c[i];
+    PEG_TRY(feval_fwd(c, 0.f, zin, k[i], nullptr));
+  }
+  if (y_err) {
+    const float* xs[8];
+    double cs[8];
+    // y_err = dt sum_j berr_j k_j: entry 0 would stay unscaled, so lead with a zero-weight copy of y
+    xs[0] = y; cs[0] = 0.0;
+    CombArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x[0] = y; a.c[0] = 0.f;
+    for (int j = 0; j < 7; ++j) { a.x[j + 1] = k[j]; a.c[j + 1] = (float)tb.berr[j]; }
+    a.cnt = 8; a.out = y_err; a.count4 = st / 4; a.gscale = dt_dev; a.per_graph4 = (size_t)dims->n * dims->h / 4;
+    k_rk_combine<<<(unsigned)((a.count4 + 255) / 256), 256, 0, c.st>>>(a);
+    PEG_LAUNCH_CHECK();
+    (void)xs; (void)cs;
+  }
+  return PEG_OK;
+}
+
+int pegncde_adaptive_control(peg_stream_t stream, const PegDims* dims, PegAdaptState* state, float rtol, float atol, float t1, float safety,
+                             float factormin, float factormax, int32_t error_order, const float* save_ts, int32_t n_save, int32_t cap,
+                             float* y, const float* y1, const float* y_err, float* k1, const float* k7, const float* k_stages,
+                             float* y_ckpt, float* ys_save, float* step_tab, int32_t* sample_step, float* sample_theta, float* t_dev,
+                             float* dt_dev, float* sumsq_scratch) {
+  PEG_TRY(check_dims(dims));
+  if (!state || !y || !y1 || !y_err || !k1 || !k7 || !y_ckpt || !step_tab || !t_dev || !dt_dev || !sumsq_scratch) return PEG_ERR_NULL_POINTER;
+  if (n_save > 0 && (!save_ts || !ys_save || !sample_step || !sample_theta || !k_stages)) return PEG_ERR_NULL_POINTER;
+  if (cap < 1 || error_order < 1) return PEG_ERR_BAD_DIMS;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t per_graph = (size_t)dims->n * dims->h;
+  k_scaled_sumsq<<<dims->B, 1024, 0, st>>>(y_err, nullptr, y, y1, rtol, atol, per_graph, sumsq_scratch);
+  PEG_LAUNCH_CHECK();
+  k_adapt_decide<<<(dims->B + 63) / 64, 64, 0, st>>>(reinterpret_cast<AdaptState*>(state), sumsq_scratch, dims->B, (float)per_graph, t1, safety, factormin,
+                                                       factormax, 1.0f / (float)error_order, save_ts, n_save, cap, step_tab, sample_step, sample_theta,
+                                                       dt_dev, t_dev);
+  PEG_LAUNCH_CHECK();
+  const size_t tot4 = (size_t)dims->B * per_graph / 4;
+  k_adapt_apply<<<(unsigned)((tot4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const AdaptState*>(state), dims->B, per_graph / 4, cap,
+                                                                reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(y1),
+                                                                reinterpret_cast<float4*>(k1), reinterpret_cast<const float4*>(k7),
+                                                                reinterpret_cast<const float4*>(k_stages), reinterpret_cast<float4*>(y_ckpt),
+                                                                reinterpret_cast<float4*>(ys_save), sample_theta);
+  PEG_LAUNCH_CHECK();
   return PEG_OK;
 }
 

@@ -17,10 +17,10 @@ The adaptive call of the dynamical-systems models (src/models/graph_neural_cde.p
     diffeqsolve(ODETerm(vf), Tsit5(), t0=ts[0], t1=ts[-1], dt0=None, y0=y0, args=control,
                 stepsize_controller=PIDController(rtol=1e-3, atol=1e-6), saveat=SaveAt(ts=ts))
 
-is driven from the host: the controller logic (a handful of scalars per step) stays here, every
-array operation -- the Tsit5 step, the scaled error norm, the dense output, the adjoint over the
-accepted steps -- is a C-ABI call.  Each trajectory of a batch has its own step sequence
-(``jax.vmap`` of the reference's while-loop), so trajectories are solved one after the other.
+runs with the step-size controller ON THE DEVICE: one ``pegncde_step_fwd_batched`` launch attempts a step of every
+trajectory of the batch (each with its own start time and step size, ``jax.vmap`` of the reference's while-loop),
+``pegncde_adaptive_control`` accepts / rejects per trajectory, emits the dense-output samples and advances the state;
+the host only polls the `done` flags every few attempts.  The adjoint runs over every trajectory's accepted steps.
 """
 from __future__ import annotations
 
@@ -396,85 +396,128 @@ def dense_weights(theta: float) -> np.ndarray:
     return np.asarray(list(w), dtype=np.float32)
 
 
-def _adaptive_trajectory(dims, pc1, flat, y0, t0, t1, dt0, ctrl: PIDController, save_ts, max_steps):
-    """Forward solve of ONE trajectory (B = 1) under the PID controller.  Returns the accepted step table, the state at
-    every accepted boundary, the dense-output samples and bookkeeping for the adjoint."""
+def _initial_step(dims, pc1, flat, y, k1, t0, ctrl: PIDController):
+    """diffrax ``_select_initial_step`` (Hairer, Norsett & Wanner II.4, error order 5) for ONE trajectory (B = 1): a few scaled
+    norms and one extra evaluation, done once per solve (the only host round trips of the adaptive path besides the polling)."""
     l = lib()
-    dev = y0.device
+    dev = y.device
     f = np.float32
     st = _stream_ptr(dev)
     ctl = pc1.struct()
     ws = workspace(dev, max(l.pegncde_workspace_bytes(dims, PEG_WS_STEP, 1), l.pegncde_workspace_bytes(dims, PEG_WS_VF_FWD, 1)))
-    nh = y0[0].numel()
+    nh = y[0].numel()
     norm_out = torch.empty(1, dtype=torch.float32, device=dev)
-
-    def vf_eval(t, y):
-        dy = torch.empty_like(y)
-        check(l.pegncde_vf_fwd(st, dims, ctl, flat.data_ptr(), float(t), y.data_ptr(), dy.data_ptr(), ws.data_ptr(), ws.numel()), "pegncde_vf_fwd")
-        return dy
 
     def norm(x, x2, s0, s1):
         check(l.pegncde_scaled_sumsq(st, dims, x.data_ptr(), x2.data_ptr() if x2 is not None else None, s0.data_ptr(),
                                      s1.data_ptr() if s1 is not None else None, ctrl.rtol, ctrl.atol, norm_out.data_ptr()), "pegncde_scaled_sumsq")
         return f(np.sqrt(f(norm_out.item()) / f(nh)))
 
+    d0, d1 = norm(y, None, y, None), norm(k1, None, y, None)
+    small = d0 < f(1e-5) or d1 < f(1e-5)
+    h0 = f(1e-6) if small else f(f(0.01) * f(d0 / d1))
+    f1 = torch.empty_like(y)
+    y_probe = torch.add(y, k1, alpha=float(h0))
+    check(l.pegncde_vf_fwd(st, dims, ctl, flat.data_ptr(), float(f(t0 + h0)), y_probe.data_ptr(), f1.data_ptr(), ws.data_ptr(), ws.numel()), "pegncde_vf_fwd")
+    d2 = f(norm(f1, k1, y, None) / h0)
+    dmax = max(d1, d2)
+    h1 = max(f(1e-6), f(h0 * f(1e-3))) if dmax <= f(1e-15) else f((f(0.01) / dmax) ** f(1.0 / ctrl.error_order))
+    return min(f(100.0) * h0, h1)
+
+
+def _adaptive_batch(vf, wrapped, pc, flat, y0, t0, t1, dt0, ctrl: PIDController, save_ts, max_steps):
+    """Forward solve of ALL trajectories of the batch under the PID controller, the controller running on the device
+    (``pegncde_step_fwd_batched`` + ``pegncde_adaptive_control``): one step launch per attempt for the whole batch, every trajectory with
+    its own accepted-step sequence, the host polling the `done` flags every few attempts.  Returns per-trajectory records for the
+    adjoint (accepted step table, checkpoints, which step emitted which dense-output sample) and the saved states."""
+    from ._lib import PegAdaptState
+
+    l = lib()
+    dev = y0.device
+    f = np.float32
+    st = _stream_ptr(dev)
+    B = pc.B
+    dims = vf.dims_for(pc, with_wrapper=wrapped)
+    ctl = pc.struct()
+    ws = workspace(dev, max(l.pegncde_workspace_bytes(dims, PEG_WS_STEP, 1), l.pegncde_workspace_bytes(dims, PEG_WS_VF_FWD, 1)))
     t0, t1 = f(t0), f(t1)
     y = y0.clone()
-    k1 = vf_eval(t0, y)   # FSAL solvers evaluate f(t0, y0) at init
-    if dt0 is None:
-        # diffrax _select_initial_step (Hairer, Norsett & Wanner II.4), error order 5
-        d0, d1 = norm(y, None, y, None), norm(k1, None, y, None)
-        small = d0 < f(1e-5) or d1 < f(1e-5)
-        h0 = f(1e-6) if small else f(f(0.01) * f(d0 / d1))
-        f1 = vf_eval(f(t0 + h0), torch.add(y, k1, alpha=float(h0)))
-        d2 = f(norm(f1, k1, y, None) / h0)
-        dmax = max(d1, d2)
-        h1 = max(f(1e-6), f(h0 * f(1e-3))) if dmax <= f(1e-15) else f((f(0.01) / dmax) ** f(1.0 / ctrl.error_order))
-        dt = min(f(100.0) * h0, h1)
-    else:
-        dt = f(dt0)
+    k1 = torch.empty_like(y)
+    check(l.pegncde_vf_fwd(st, dims, ctl, flat.data_ptr(), float(t0), y.data_ptr(), k1.data_ptr(), ws.data_ptr(), ws.numel()), "pegncde_vf_fwd")   # FSAL: f(t0, y0)
+    state = np.zeros(B, dtype=np.dtype([("tprev", "<f4"), ("tnext", "<f4"), ("done", "<i4"), ("nacc", "<i4"), ("attempts", "<i4"), ("rejected", "<i4"),
+                                        ("mi", "<i4"), ("mi0", "<i4"), ("mi1", "<i4"), ("keep", "<i4"), ("h", "<f4"), ("overflow", "<i4")]))
+    assert state.dtype.itemsize == ctypes.sizeof(PegAdaptState)
+    for b in range(B):
+        if dt0 is None:
+            pc1 = pc.select(b)
+            dt = _initial_step(vf.dims_for(pc1, with_wrapper=wrapped), pc1, flat, y[b:b + 1], k1[b:b + 1], t0, ctrl)
+        else:
+            dt = f(dt0)
+        state["tprev"][b] = t0
+        state["tnext"][b] = clip_to_end(t0, f(t0 + dt), t1, True)
+    M = 0 if save_ts is None else len(save_ts)
+    save_dev = torch.from_numpy(np.ascontiguousarray(save_ts, dtype=np.float32)).to(dev) if M else None
+    shape = tuple(y.shape[1:])
+    cap = 64
+
+    def alloc(cap_):
+        return (torch.empty((B, cap_ + 1) + shape, dtype=torch.float32, device=dev), torch.zeros((B, cap_ + 1), dtype=torch.float32, device=dev))
+
+    y_ckpt, step_tab = alloc(cap)
+    y_ckpt[:, 0] = y
+    step_tab[:, 0] = float(t0)
+    ys_save = torch.empty((M, B) + shape, dtype=torch.float32, device=dev) if M else None
+    sample_step = torch.zeros((max(M, 1), B), dtype=torch.int32, device=dev)
+    sample_theta = torch.zeros((max(M, 1), B), dtype=torch.float32, device=dev)
+    state_dev = torch.from_numpy(state.view(np.uint8).copy()).to(dev)
+    t_dev = torch.from_numpy(state["tprev"].copy()).to(dev)
+    dt_dev = torch.from_numpy((state["tnext"] - state["tprev"]).astype(np.float32)).to(dev)
     y1, yerr, k7 = torch.empty_like(y), torch.empty_like(y), torch.empty_like(y)
     kst = torch.empty((5,) + tuple(y.shape), dtype=torch.float32, device=dev)
-    M = 0 if save_ts is None else len(save_ts)
-    ys_save = torch.empty((M,) + tuple(y.shape), dtype=torch.float32, device=dev) if M else None
-    samples = []   # (save index, accepted-step index, theta)
-    boundaries, ckpt = [t0], [y.clone()]
-    mi, attempts, rejected = 0, 0, 0
-    tprev = t0
-    tnext = clip_to_end(tprev, f(tprev + dt), t1, True)
-    while True:
-        attempts += 1
-        if attempts > max_steps:
+    sumsq = torch.empty(B, dtype=torch.float32, device=dev)
+    poll = 8
+    host = None
+    for it in range(max_steps + poll):
+        check(l.pegncde_step_fwd_batched(st, dims, ctl, flat.data_ptr(), t_dev.data_ptr(), dt_dev.data_ptr(), y.data_ptr(), k1.data_ptr(), 1,
+                                         y1.data_ptr(), yerr.data_ptr(), k7.data_ptr(), kst.data_ptr(), ws.data_ptr(), ws.numel()), "pegncde_step_fwd_batched")
+        check(l.pegncde_adaptive_control(st, dims, state_dev.data_ptr(), ctrl.rtol, ctrl.atol, float(t1), ctrl.safety, ctrl.factormin, ctrl.factormax,
+                                         int(ctrl.error_order), save_dev.data_ptr() if M else None, M, cap, y.data_ptr(), y1.data_ptr(), yerr.data_ptr(),
+                                         k1.data_ptr(), k7.data_ptr(), kst.data_ptr(), y_ckpt.data_ptr(), ys_save.data_ptr() if M else None,
+                                         step_tab.data_ptr(), sample_step.data_ptr(), sample_theta.data_ptr(), t_dev.data_ptr(), dt_dev.data_ptr(),
+                                         sumsq.data_ptr()), "pegncde_adaptive_control")
+        if it % poll != poll - 1:
+            continue
+        host = state_dev.cpu().numpy().view(state.dtype)        # the one synchronisation per `poll` attempts
+        if int(host["attempts"].max()) > max_steps:
             raise RuntimeError(f"max_steps={max_steps} reached")   # diffrax throw=True
-        h = f(tnext - tprev)
-        check(l.pegncde_step_fwd(st, dims, ctl, flat.data_ptr(), float(tprev), float(h), y.data_ptr(), k1.data_ptr(), 1,
-                                 y1.data_ptr(), yerr.data_ptr(), k7.data_ptr(), kst.data_ptr(), ws.data_ptr(), ws.numel()), "pegncde_step_fwd")
-        keep, dt_new = ctrl.adapt(norm(yerr, None, y, y1), h)
-        if keep:
-            s = len(boundaries) - 1
-            while mi < M and f(save_ts[mi]) <= tnext:
-                theta = f(min(max(f(f(save_ts[mi]) - tprev) / h, f(0.0)), f(1.0)))
-                check(l.pegncde_tsit5_dense(st, dims, float(h), float(theta), y.data_ptr(), k1.data_ptr(), kst.data_ptr(),
-                                            k7.data_ptr(), ys_save[mi].data_ptr()), "pegncde_tsit5_dense")
-                samples.append((mi, s, float(theta)))
-                mi += 1
-            y, y1 = y1, y
-            k1, k7 = k7, k1
-            boundaries.append(tnext)
-            ckpt.append(y.clone())
-            tprev_new = tnext
-        else:
-            rejected += 1
-            tprev_new = tprev
-        tnext = clip_to_end(tprev_new, f(tprev_new + dt_new), t1, keep)
-        tprev = tprev_new
-        if keep and tprev >= t1:
+        if host["overflow"].any():                                # grow the accepted-step tables, re-arm the stalled trajectories
+            new_cap = 2 * cap
+            y_new, tab_new = alloc(new_cap)
+            y_new[:, : cap + 1] = y_ckpt
+            tab_new[:, : cap + 1] = step_tab
+            y_ckpt, step_tab, cap = y_new, tab_new, new_cap
+            host = host.copy()
+            host["overflow"][:] = 0
+            state_dev.copy_(torch.from_numpy(host.view(np.uint8).copy()))
+            dt_dev.copy_(torch.from_numpy(np.where(host["done"] != 0, 0.0, host["tnext"] - host["tprev"]).astype(np.float32)))
+            continue
+        if host["done"].all():
             break
-    if mi < M:
+    else:
+        raise RuntimeError(f"max_steps={max_steps} reached")
+    if M and int(host["mi"].min()) < M:
         raise ValueError("SaveAt(ts=...) holds times outside [t0, t1]")
-    return dict(step_ts=np.asarray(boundaries, dtype=np.float32), y_ckpt=torch.stack(ckpt), ys_save=ys_save, samples=samples,
-                stats={"num_steps": attempts, "num_accepted_steps": attempts - rejected, "num_rejected_steps": rejected,
-                       "step_ts": np.asarray(boundaries, dtype=np.float32)})
+    tab = step_tab.cpu().numpy()
+    s_step, s_theta = sample_step.cpu().numpy(), sample_theta.cpu().numpy()
+    recs = []
+    for b in range(B):
+        S = int(host["nacc"][b])
+        table = np.ascontiguousarray(tab[b, : S + 1], dtype=np.float32)
+        recs.append(dict(step_ts=table, y_ckpt=y_ckpt[b, : S + 1].unsqueeze(1), samples=[(m, int(s_step[m, b]), float(s_theta[m, b])) for m in range(M)],
+                         stats={"num_steps": int(host["attempts"][b]), "num_accepted_steps": S, "num_rejected_steps": int(host["rejected"][b]),
+                                "step_ts": table}))
+    out = ys_save if M else y.unsqueeze(0)
+    return recs, out
 
 
 class _AdaptiveSolveFunction(torch.autograd.Function):
@@ -486,18 +529,14 @@ class _AdaptiveSolveFunction(torch.autograd.Function):
     def forward(ctx, y0, flat, vf, wrapped, pc, t0, t1, dt0, ctrl, save_ts, max_steps, stats_out):
         y0 = y0.contiguous()
         flat = flat.contiguous()
-        recs, outs = [], []
-        for b in range(pc.B):
+        recs, out = _adaptive_batch(vf, wrapped, pc, flat, y0, t0, t1, dt0, ctrl, save_ts, max_steps)
+        for b, rec in enumerate(recs):
             pc1 = pc.select(b)
-            dims = vf.dims_for(pc1, with_wrapper=wrapped)
-            rec = _adaptive_trajectory(dims, pc1, flat, y0[b:b + 1], t0, t1, dt0, ctrl, save_ts, max_steps)
-            rec["dims"], rec["pc1"] = dims, pc1
-            recs.append(rec)
-            outs.append(rec["ys_save"] if save_ts is not None else rec["y_ckpt"][-1:])
+            rec["dims"], rec["pc1"] = vf.dims_for(pc1, with_wrapper=wrapped), pc1
             stats_out.append(rec["stats"])
         ctx.recs, ctx.has_ts = recs, save_ts is not None
         ctx.save_for_backward(flat)
-        return torch.cat(outs, dim=1)   # [M or 1, B, n, h]
+        return out   # [M or 1, B, n, h]
 
     @staticmethod
     def backward(ctx, g_out):
