@@ -56,18 +56,26 @@ __global__ void __launch_bounds__(256) k_split_transpose(const float* __restrict
 }
 
 // fp16x2 operand format: block exponent e of every 128-node block of V [B,n,d] (vexp[b][block]); k_split_transpose then writes
-// V^T * 2^e.  One CTA per block reads its 128 x d slab once.  grid (ceil(npad/128), B), block 256
-__global__ void __launch_bounds__(256) k_block_exponent(const float* __restrict__ V, int n, int d, int* __restrict__ vexp, int vexp_stride, int blk0) {
+// V^T * 2^e.  grid (ceil(npad/128), column slices, B), block 256: the CTAs of a block combine their maxima with an atomicMax on the
+// bit pattern (non-negative floats order like unsigned integers: order independent) and the last one to arrive turns it into the
+// exponent -- a wide layer (d = 2 h e >= 1024 of the control models) no longer hangs on one CTA reading 128 x d values.
+// vmax / vtick: [B][vexp_stride] scratch, zero on entry, left zero on exit.
+__global__ void __launch_bounds__(256) k_block_exponent(const float* __restrict__ V, int n, int d, int* __restrict__ vexp, int vexp_stride, int blk0,
+                                                        unsigned int* __restrict__ vmax, unsigned int* __restrict__ vtick) {
+  // vmax / vtick are indexed with the LOCAL block count (gridDim.x blocks per graph); vexp with its own stride and block offset
   __shared__ float bmax_s[8];
-  const int b = blockIdx.y, blk = blockIdx.x, i0 = blk * 128;
+  const int b = blockIdx.z, blk = blockIdx.x, i0 = blk * 128;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows = min(128, n - i0);
+  const int c4 = d / 4, per = (c4 + gridDim.y - 1) / gridDim.y;       // float4 columns of this slice
+  const int cb = blockIdx.y * per, ce = min(c4, cb + per);
   float mx = 0.f;
-  if (rows > 0) {
-    const size_t cnt4 = (size_t)rows * d / 4;      // d % 4 == 0
+  if (rows > 0 && ce > cb) {
     const float4* src = reinterpret_cast<const float4*>(V + ((size_t)b * n + i0) * d);
-    for (size_t i = tid; i < cnt4; i += 256) {
-      const float4 v = __ldg(src + i);
+    const int w = ce - cb;
+    for (int i = tid; i < rows * w; i += 256) {
+      const int r = i / w, c = cb + (i - r * w);
+      const float4 v = __ldg(src + (size_t)r * c4 + c);
       mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
   }
@@ -77,7 +85,15 @@ __global__ void __launch_bounds__(256) k_block_exponent(const float* __restrict_
   if (tid == 0) {
 #pragma unroll
     for (int w8 = 0; w8 < 8; ++w8) mx = fmaxf(mx, bmax_s[w8]);
-    vexp[(size_t)b * vexp_stride + blk0 + blk] = block_exponent(mx);
+    const size_t slot = (size_t)b * gridDim.x + blk;
+    atomicMax(vmax + slot, __float_as_uint(mx));
+    __threadfence();
+    if (atomicAdd(vtick + slot, 1u) == gridDim.y - 1) {     // last slice of this block: publish the exponent, reset the scratch
+      __threadfence();
+      const unsigned int bits = atomicExch(vmax + slot, 0u);
+      vexp[(size_t)b * vexp_stride + blk0 + blk] = block_exponent(__uint_as_float(bits));
+      vtick[slot] = 0u;
+    }
   }
 }
 
@@ -964,6 +980,7 @@ void tc_carve(Bump& bp, const PegDims& d, int dmax, TcWs& w) {
   w.npad = npad_of(d.n);
   w.fmt = PEG_FMT_TF32X3;
   w.vexp = nullptr;
+  w.vmax = nullptr;
   w.ldk = w.npad;
   w.col0 = w.blk0 = 0;
   w.vexp_stride = (w.npad + 127) / 128;
@@ -972,6 +989,7 @@ void tc_carve(Bump& bp, const PegDims& d, int dmax, TcWs& w) {
     return;
   }
   w.vexp = bp.take<int>((size_t)d.B * w.vexp_stride);
+  w.vmax = bp.take<unsigned int>(2 * (size_t)d.B * ((w.npad + 127) / 128));     // block maxima + arrival counters of k_block_exponent (zeroed per API call)
   const size_t cnt = (size_t)d.B * dmax * w.npad;
   w.Vt_hi = bp.take<float>(cnt);
   w.Vt_lo = bp.take<float>(cnt);
@@ -1010,7 +1028,8 @@ int tc_convert_v(cudaStream_t st, const PegDims& dm, const TcWs& w, const Contra
   po.Thi = w.Vt_hi; po.Tlo = w.Vt_lo; po.npad = ldk; po.t16 = fmt; po.vexp = w.vexp; po.vexp_stride = w.vexp_stride;
   po.col0 = w.col0; po.blk0 = w.blk0; po.rows_pad = npad;
   if (fmt == PEG_FMT_FP16X2) {
-    k_block_exponent<<<dim3((npad + 127) / 128, dm.B), 256, 0, st>>>(a.V, n, d, w.vexp, w.vexp_stride, w.blk0);
+    const int slices = d >= 1024 ? 8 : (d >= 256 ? 2 : 1);
+    k_block_exponent<<<dim3((npad + 127) / 128, slices, dm.B), 256, 0, st>>>(a.V, n, d, w.vexp, w.vexp_stride, w.blk0, w.vmax, w.vmax + (size_t)dm.B * ((npad + 127) / 128));
     if (cudaPeekAtLastError() != cudaSuccess) { set_last_cuda((int)cudaGetLastError()); fprintf(stderr, "pegncde: k_block_exponent launch failed\n"); return PEG_ERR_CUDA; }
   }
   dim3 grid(npad / 32, (d + 31) / 32, dm.B), block(32, 8);

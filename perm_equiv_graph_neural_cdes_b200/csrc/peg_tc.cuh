@@ -13,6 +13,7 @@ struct TcWs {
   int npad;
   int fmt;          // operand format of this call (PEG_FMT_*), set by make_ctx from the flags and the control
   int* vexp;        // [B][vexp_stride] block exponents of V^T (fp16x2 format)
+  unsigned int* vmax;   // [2][B][vexp_stride] scratch of k_block_exponent (maxima, arrival counters), zero between launches
   int vexp_stride;  // = ceil(ldk / 128)
   int ldk;          // row pitch of V^T in elements = padded GLOBAL node count (== npad unless row-sharded)
   int col0, blk0;   // row-sharded mode: this rank's rows are columns [col0, col0 + npad) of V^T (else 0)

@@ -545,6 +545,7 @@ static int reset_tickets(Ctx& c) {
     shard_select_half(c);
   }
   PEG_CUDA(cudaMemsetAsync(c.w.tickets, 0, c.w.tickets_count * sizeof(unsigned int), c.st));
+  if (c.w.tc.vmax) PEG_CUDA(cudaMemsetAsync(c.w.tc.vmax, 0, 2 * (size_t)c.d.B * ((c.w.tc.npad + 127) / 128) * sizeof(unsigned int), c.st));
   if (c.use_tc) {
     PEG_TRY(tc_prep_weights(c.st, c.m, c.params, c.w.lin));
     g_launches.fetch_add(c.m.L);
