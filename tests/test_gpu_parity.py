@@ -1037,3 +1037,56 @@ def test_row_sharded_solve_over_two_gpus(cuda, flags):
     assert rel_err(gy0, gy0_ref) < 1e-5
     for r in range(world):
         assert rel_err(out[r][2], gp_ref) < 1e-5, r
+
+
+# ---------------------------------------------------------------------------------------------------
+# batch-sharded data parallelism on real GPUs: NCCL all-reduce of the sharded gradients == the full-batch gradients
+# ---------------------------------------------------------------------------------------------------
+def _dp_rank(rank, world, port, out):
+    import torch.distributed as dist
+
+    from perm_equiv_graph_neural_cdes_b200 import dist as pdist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        n, h, B = 256, 64, 4
+        ts, A, y0, gy = _rowshard_problem(n, h, 3, 4, B, 11, dev)
+        vf = P.PermEquivGraphVectorField(h, h, h, 3, 0, n, key=5).to(dev)
+
+        def grads(sel):
+            vf.zero_grad()
+            y = y0[sel].clone().requires_grad_(True)
+            yT = P.diffeqsolve(P.ODETerm(vf), P.Tsit5(), 0.0, 1.0, 0.25, y, P.build_control(ts, A[sel])).ys[-1]
+            (yT * gy[sel]).sum().backward()
+            return yT.detach()
+
+        b0, b1 = pdist.shard_range(B, rank, world)
+        yT = grads(slice(b0, b1))
+        flat = pdist.allreduce_gradients(list(vf.parameters()))        # ONE NCCL all-reduce of the flat buffer
+        res = [flat.cpu(), yT.cpu()]
+        if rank == 0:
+            yT_full = grads(slice(0, B))
+            res += [torch.cat([p.grad.reshape(-1) for p in vf.parameters()]).cpu(), yT_full.cpu()]
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_reduced_sharded_gradients_equal_the_full_batch_gradients(cuda):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dp_rank, args=(2, port, out), nprocs=2, join=True)
+    full_g, full_y = out[0][2], out[0][3]
+    assert torch.equal(out[0][0], out[1][0])                                   # every rank holds the same reduced buffer
+    assert rel_err(out[0][0], full_g) < 1e-5
+    assert rel_err(torch.cat([out[0][1], out[1][1]]), full_y) < 1e-6          # the shards are the rows of the full batch
