@@ -160,7 +160,7 @@ __device__ __forceinline__ LightCoef light_coef(float wa, float wd) {
 // A scale.  E is cheap enough (one exponent per 128 nodes) for every thread that needs it to recompute it from global memory.
 __device__ __forceinline__ int bfp_min_exponent(const int* __restrict__ ve, int nblk) {
   int e = PEG_VEXP_MAX;
-  for (int J = 0; J < nblk; ++J) e = min(e, __ldg(ve + J));
+  for (int J = 0; J < nblk; ++J) e = min(e, __ldcg(ve + J));     // L2: in row-sharded mode peers write these entries over NVLink
   return e;
 }
 
@@ -296,7 +296,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     const int Emin = BFP ? bfp_min_exponent(ve, (a.ldk + 127) >> 7) : 0;
     for (int pr = tid; pr < npairs; pr += TC_THREADS) {
       const int kc = kc_of(pr0 + pr);
-      const float f = BFP ? exp2_int(max(Emin - __ldg(ve + (kc >> 2)), -120)) : 1.f;
+      const float f = BFP ? exp2_int(max(Emin - __ldcg(ve + (kc >> 2)), -120)) : 1.f;
       sched_kc_s[pr] = kc;
       if (BFP) sched_f_s[pr] = make_float2(f * as0, f * as1);
     }
