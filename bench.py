@@ -50,9 +50,9 @@ UNIT = "solver steps/s"
 
 def measured_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (mean of one forward and one
-    adjoint launch), from the committed `ncu --set full` captures of this workload (profiles/r01_traffic.json);
+    adjoint launch), from the committed `ncu --set full` captures of this workload (profiles/r02_traffic.json);
     None if no capture exists."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(path):
         ent = json.load(open(path)).get(workload)
         return ent["mean_bytes_per_launch"] if isinstance(ent, dict) else ent
