@@ -72,8 +72,15 @@ enum {
   PEG_FLAG_BF16X2 = 32,         /* with TENSOR_CORES: x = hi + lo with bf16 parts (no block exponents needed; 8 + 8 mantissa bits:
                                    rounding ~2^-17 per product).  A separately stated looser-tolerance mode: Z_T within 1e-4,
                                    gradients within 2e-3 */
-  PEG_FLAG_ADJ_LIGHT = 8        /* with TENSOR_CORES: the adjoint contraction runs two of its four products single-pass; looser
+  PEG_FLAG_ADJ_LIGHT = 8,       /* with TENSOR_CORES: the adjoint contraction runs two of its four products single-pass; looser
                                    stated tolerance on the param1 / param2 gradients (2.5e-3 instead of 1e-3).  Off by default. */
+  PEG_FLAG_NO_FUSED_SMALL = 64, /* opt out of the small-graph path.  By default, graphs with n < 128 (undirected layer, h <= 128; the
+                                   shapes the tcgen05 contraction does not take) run a whole evaluation f(t, y) -- and a whole
+                                   VJP -- in ONE fp32 kernel, a thread-block cluster per graph with cluster barriers between
+                                   the layer phases instead of ~15 / ~40 dependent launches; same arithmetic as the
+                                   per-operator fp32 kernels, so the same parity bound */
+  PEG_FLAG_FUSED_SMALL = 128    /* take the small-graph path up to n <= 256 (it loses to the per-operator tcgen05 path when one
+                                   graph has a wide last layer, e.g. England n=129, 2he=1024: measured in DESIGN.md) */
 };
 
 typedef struct PegDims {

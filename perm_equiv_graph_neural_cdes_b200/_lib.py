@@ -16,6 +16,8 @@ PEG_FLAG_TENSOR_CORES = 1
 PEG_FLAG_TF32_FAST = 2
 PEG_FLAG_DIRECTED = 4
 PEG_FLAG_ADJ_LIGHT = 8
+PEG_FLAG_NO_FUSED_SMALL = 64
+PEG_FLAG_FUSED_SMALL = 128
 PEG_FLAG_TF32X3 = 16
 PEG_FLAG_BF16X2 = 32
 

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "peg_kernels.cuh"
+#include "peg_small.cuh"
 #include "peg_tc.cuh"
 
 namespace peg {
@@ -175,6 +176,8 @@ struct Ctx {
   const float* dt_dev;
   float tcoef;
   unsigned int* xticket;   // arrival counter of k_shard_push (in the tickets area)
+  int small_C;             // > 0: the cluster-per-graph kernels of peg_small.cuh evaluate f and its VJP (CTAs per graph)
+  size_t small_smem;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -366,9 +369,91 @@ static int contract(Ctx& c, int l, bool bwd, const float* V, const float* Mref, 
   return rc;
 }
 
+// ------------------------------------------------------------------------------------------
+// small graphs: one cluster kernel per evaluation / per VJP (peg_small.cuh)
+// ------------------------------------------------------------------------------------------
+struct SmallEnv { int max_n = 0, cluster = 0; bool off = false; };
+static thread_local SmallEnv g_small_env;
+static void small_refresh_env() {
+  SmallEnv e;
+  if (const char* v = getenv("PEG_SMALL_MAX_N")) e.max_n = atoi(v);
+  if (const char* v = getenv("PEG_SMALL_CLUSTER")) e.cluster = atoi(v);
+  e.off = getenv("PEG_SMALL_OFF") != nullptr;
+  g_small_env = e;
+}
+
+// decides whether this call runs on the small-graph kernels and with how many CTAs per graph
+static void small_plan(Ctx& c) {
+  c.small_C = 0;
+  c.small_smem = 0;
+  const PegDims& d = c.d;
+  if (g_small_env.off || (d.flags & PEG_FLAG_NO_FUSED_SMALL)) return;
+  // default: below the smallest tcgen05 shape; PEG_FLAG_FUSED_SMALL widens it (PEG_SMALL_MAX_N: experiments)
+  const int max_n = g_small_env.max_n > 0 ? g_small_env.max_n : ((d.flags & PEG_FLAG_FUSED_SMALL) ? 256 : 127);
+  if (c.sh || c.m.directed || d.n > max_n || d.n > SG_MAX_N || d.h > SG_MAX_DIN) return;
+  const size_t smem = small_smem_floats(d.n, d.L) * sizeof(float);
+  if (smem > 220 * 1024) return;
+  static int sm_count = 0;
+  static bool attr_done = false, nonportable = false;
+  if (!attr_done) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    bool ok = cudaFuncSetAttribute(k_small_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) == cudaSuccess &&
+              cudaFuncSetAttribute(k_small_vjp, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) == cudaSuccess;
+    if (!ok) { (void)cudaGetLastError(); return; }
+    nonportable = cudaFuncSetAttribute(k_small_fwd, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_small_vjp, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (!nonportable) (void)cudaGetLastError();
+    attr_done = true;
+  }
+  // CTAs per graph: as many as keep the batch within one wave of SMs, no more than the widest phase has work items
+  const int dL = c.m.layer[d.L - 1].dout;
+  const int items = ((d.n + SG_RB - 1) / SG_RB) * ((dL + SG_WB - 1) / SG_WB);
+  int C = 1;
+  for (int cand = nonportable ? 16 : 8; cand >= 1; cand >>= 1)
+    if ((long long)d.B * cand <= sm_count && cand <= items) { C = cand; break; }
+  if (g_small_env.cluster > 0) C = g_small_env.cluster;
+  c.small_C = C;
+  c.small_smem = smem;
+}
+
+static void small_args(const Ctx& c, float t, SmallArgs& a) {
+  memset(&a, 0, sizeof(a));
+  a.ctl = c.ctl; a.params = c.params; a.model = c.m;
+  a.B = c.d.B; a.n = c.d.n; a.e = c.d.e; a.T = c.d.T; a.L = c.d.L; a.h = c.d.h; a.npad = c.d.ldn; a.C = c.small_C;
+  a.t = t;
+  a.sc = c.w.sc;
+  a.M = c.w.M; a.Za = c.w.Za; a.Zb = c.w.Zb; a.OL = c.w.OL; a.Obar = c.w.Obar; a.Mbar = c.w.Mbar; a.N = c.w.N;
+}
+
+static int small_launch(Ctx& c, const SmallArgs& a, bool vjp) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(c.d.B * c.small_C));
+  cfg.blockDim = dim3(SG_THREADS);
+  cfg.dynamicSmemBytes = c.small_smem;
+  cfg.stream = c.st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)c.small_C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const cudaError_t e = vjp ? cudaLaunchKernelEx(&cfg, k_small_vjp, a) : cudaLaunchKernelEx(&cfg, k_small_fwd, a);
+  g_launches.fetch_add(1);
+  if (e != cudaSuccess) { g_last_cuda = (int)e; (void)cudaGetLastError(); return PEG_ERR_CUDA; }
+  return PEG_OK;
+}
+
 static int feval_fwd(Ctx& c, float t, const float* yin, float* dy, float* const* save, int nlayers = -1) {
   const PegDims& d = c.d;
   if (nlayers < 0) nlayers = d.L;
+  if (c.small_C > 0 && !c.t_dev) {
+    SmallArgs a;
+    small_args(c, t, a);
+    a.yin = yin; a.dy = dy; a.nlayers = nlayers;
+    for (int l = 0; l < d.L; ++l) a.save[l] = save ? save[l] : nullptr;
+    return small_launch(c, a, false);
+  }
   PEG_TRY(stage_prep(c, t));
   const float* Zin = yin;
   for (int l = 0; l < nlayers; ++l) {
@@ -401,6 +486,14 @@ static int feval_vjp(Ctx& c, float t, float* const* zin, const float* kbar, floa
                      float* g_xd) {
   const PegDims& d = c.d;
   const int dL = last_width(d);
+  if (g_xd != nullptr && d.e == 0) return PEG_ERR_BAD_DIMS;
+  if (c.small_C > 0 && !c.t_dev) {
+    SmallArgs a;
+    small_args(c, t, a);
+    for (int l = 0; l < d.L; ++l) a.zin[l] = zin[l];
+    a.kbar = kbar; a.ybar = ybar; a.g_params = g_params; a.g_xd = g_xd;
+    return small_launch(c, a, true);
+  }
   PEG_TRY(stage_prep(c, t));
   if (g_xd != nullptr) {
     if (d.e == 0) return PEG_ERR_BAD_DIMS;
@@ -522,6 +615,8 @@ static int make_ctx(Ctx& c, peg_stream_t stream, const PegDims* dims, const PegC
   c.t_dev = c.dt_dev = nullptr;
   c.tcoef = 0.f;
   c.sh = ctl->shard;
+  small_refresh_env();
+  small_plan(c);
   if (c.sh) {
     const PegShard& sh = *c.sh;
     if (sh.world < 1 || sh.world > PEG_MAX_WORLD || sh.rank < 0 || sh.rank >= sh.world) return PEG_ERR_BAD_DIMS;
@@ -546,7 +641,7 @@ static int reset_tickets(Ctx& c) {
   }
   PEG_CUDA(cudaMemsetAsync(c.w.tickets, 0, c.w.tickets_count * sizeof(unsigned int), c.st));
   if (c.w.tc.vmax) PEG_CUDA(cudaMemsetAsync(c.w.tc.vmax, 0, 2 * (size_t)c.d.B * ((c.w.tc.npad + 127) / 128) * sizeof(unsigned int), c.st));
-  if (c.use_tc) {
+  if (c.use_tc && c.small_C == 0) {
     PEG_TRY(tc_prep_weights(c.st, c.m, c.params, c.w.lin));
     g_launches.fetch_add(c.m.L);
   }
@@ -837,6 +932,7 @@ int pegncde_step_fwd_batched(peg_stream_t stream, const PegDims* dims, const Peg
                              float* k_stages, void* workspace, size_t workspace_bytes) {
   Ctx c;
   PEG_TRY(make_ctx(c, stream, dims, ctl, params));
+  c.small_C = 0;    // per-trajectory stage times: the per-operator kernels
   if (!t_dev || !dt_dev || !y || !k1 || !y1 || !k7 || !workspace) return PEG_ERR_NULL_POINTER;
   if (c.sh) return PEG_ERR_UNSUPPORTED;
   if (workspace_bytes < plan(*dims, PEG_WS_STEP, 0, nullptr, nullptr, nullptr)) return PEG_ERR_WORKSPACE;

@@ -13,6 +13,21 @@ GOLDEN_CASES = {
 }
 
 
+FUSED = "fused"     # device_model(flags=FUSED): the product default, selected by name in parametrised tests
+
+
+def per_operator(flags):
+    """flags of a test that names a per-operator path: the small-graph cluster kernels are switched off"""
+    from perm_equiv_graph_neural_cdes_b200 import _lib
+    return int(flags) | _lib.PEG_FLAG_NO_FUSED_SMALL
+
+
+def fused_flags():
+    """the product default plus PEG_FLAG_FUSED_SMALL: the small-graph cluster kernels up to n = 256 (default: n < 128)"""
+    from perm_equiv_graph_neural_cdes_b200 import _lib
+    return _lib.PEG_FLAG_TENSOR_CORES | _lib.PEG_FLAG_FUSED_SMALL
+
+
 def device_model(p, device, flags=None):
     """(vf, wrapped_vf_or_vf, control objects) of the product API for an oracle Problem."""
     import perm_equiv_graph_neural_cdes_b200 as P
@@ -21,8 +36,14 @@ def device_model(p, device, flags=None):
     vf = P.PermEquivGraphVectorField(p.h, p.h, widths[-1], p.L, p.e, p.n, key=0)
     vf.load_oracle_layers([lp.tensors() for lp in p.layers])
     vf = vf.to(device)
-    if flags is not None:   # None = the product default (tcgen05 wherever the shape allows it)
-        vf.flags = flags
+    # None = the product default: the cluster-per-graph kernels for n < 128, tcgen05 wherever the shape allows it.
+    # An explicit value names a per-operator path ("ffma" = 0, "tcgen05" = PEG_FLAG_TENSOR_CORES ...): the small-graph path is
+    # switched off so that the test exercises the kernels it names at any n.  FUSED = the small-graph path up to n = 256.
+    if isinstance(flags, str):
+        assert flags == FUSED
+        vf.flags = fused_flags()
+    elif flags is not None:
+        vf.flags = per_operator(flags)
     ts = p.ts.to(torch.float32)
     cadj = P.CubicInterpolation(ts.to(device), tuple(c.to(torch.float32).to(device) for c in p.coeffs_adj))
     cx = None

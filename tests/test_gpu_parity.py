@@ -14,7 +14,7 @@ import torch
 import perm_equiv_graph_neural_cdes_b200 as P
 from perm_equiv_graph_neural_cdes_b200 import _lib
 from oracle import reference_path as R
-from tests.helpers import GOLDEN_CASES, device_model, product_grads_as_oracle, rel_err
+from tests.helpers import FUSED, GOLDEN_CASES, device_model, fused_flags, per_operator, product_grads_as_oracle, rel_err
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -60,11 +60,12 @@ def _vf_oracle(p64, t, y):
     return R.perm_equiv_vector_field(t, y, ca, p64.layers)
 
 
-@pytest.mark.parametrize("case", ["tiny_nocontrol", "tiny_control", "ragged_n", "sir_like"])
-def test_vector_field_forward_and_vjp(cuda, case):
+@pytest.mark.parametrize("flags", [FUSED, 0], ids=["fused-small", "ffma"])
+@pytest.mark.parametrize("case", ["tiny_nocontrol", "tiny_control", "ragged_n", "sir_like", "england_like"])
+def test_vector_field_forward_and_vjp(cuda, case, flags):
     p = R.make_problem(**GOLDEN_CASES[case])
     p64 = R.problem_to(p, torch.float64)
-    vf, term, args = device_model(p, cuda)
+    vf, term, args = device_model(p, cuda, flags=flags)
     t_lo, t_hi = float(p.ts[0]), float(p.ts[-1])
     # interior points, exact knots, and both out-of-range sides (index clipping)
     times = [t_lo + 0.37 * (t_hi - t_lo), float(p.ts[1]), t_lo, t_hi, t_lo - 0.25, t_hi + 0.25]
@@ -85,15 +86,17 @@ def test_vector_field_forward_and_vjp(cuda, case):
                 assert rel_err(g, r.grad) < 2e-4, (case, t, l, name)
 
 
-@pytest.mark.parametrize("flags", [0, _lib.PEG_FLAG_TENSOR_CORES, _lib.PEG_FLAG_TENSOR_CORES | _lib.PEG_FLAG_TF32X3, _lib.PEG_FLAG_TENSOR_CORES | _lib.PEG_FLAG_BF16X2],
-                         ids=["ffma", "tcgen05", "tcgen05-tf32x3", "tcgen05-bf16x2"])
+@pytest.mark.parametrize("flags", [FUSED, 0, _lib.PEG_FLAG_TENSOR_CORES, _lib.PEG_FLAG_TENSOR_CORES | _lib.PEG_FLAG_TF32X3, _lib.PEG_FLAG_TENSOR_CORES | _lib.PEG_FLAG_BF16X2],
+                         ids=["fused-small", "ffma", "tcgen05", "tcgen05-tf32x3", "tcgen05-bf16x2"])
 @pytest.mark.parametrize("case", list(GOLDEN_CASES))
 def test_solve_against_goldens(cuda, case, flags):
     g = np.load(os.path.join(GOLD, f"{case}.npz"))
     kw = GOLDEN_CASES[case]
     p = R.make_problem(**kw)
-    if flags and p.n < 128:
+    if flags != FUSED and flags and p.n < 128:
         pytest.skip("tensor-core contraction is only selected for n >= 128")
+    if flags == FUSED and p.n > 256:
+        pytest.skip("the small-graph path covers n <= 256")
     vf, term, args = device_model(p, cuda, flags=flags)
     y0 = p.y0.to(cuda).requires_grad_(True)
     sol = P.diffeqsolve(P.ODETerm(term), P.Tsit5(), float(p.ts[0]), float(p.ts[-1]), kw["dt0"], y0, args,
@@ -119,7 +122,7 @@ def test_solve_against_goldens(cuda, case, flags):
         print(f"\n[{case}] stiff-case gradient error, relative L2: y0 {rel_l2:.2e}, parameters {rel_l2_p:.2e}")
         assert rel_l2 < 2e-2 and rel_l2_p < 2e-2, (rel_l2, rel_l2_p)
         return
-    tol_g = 2e-3 if flags & _lib.PEG_FLAG_BF16X2 else TOL_G    # bf16x2: the separately stated looser-tolerance operand format
+    tol_g = 2e-3 if (flags != FUSED and flags & _lib.PEG_FLAG_BF16X2) else TOL_G    # bf16x2: the separately stated looser-tolerance operand format
     assert rel_err(y0.grad, g["gy0_64"]) < tol_g, case
     flat = torch.cat([t.reshape(-1) for layer in product_grads_as_oracle(vf) for t in layer]).cpu().double().numpy()
     ref = g["gparams64"]
@@ -469,7 +472,7 @@ def test_sibling_vector_fields_against_oracle(cuda, cls, with_derivative, flags)
             mine.linear.weight.copy_(lp.weight); mine.linear.bias.copy_(lp.bias)
             mine.norm.weight.copy_(lp.norm_weight); mine.norm.bias.copy_(lp.norm_bias)
     vf = vf.to(cuda)
-    vf.flags = flags
+    vf.flags = per_operator(flags)
     assert sorted(k for k, _ in vf.named_parameters())[:2] == ["gnn_layers.0.linear.bias", "gnn_layers.0.linear.weight"]
     ts = p.ts.to(torch.float32).to(cuda)
     ca = P.CubicInterpolation(ts, tuple(c.to(cuda) for c in p.coeffs_adj))
@@ -615,7 +618,7 @@ def test_directed_vector_field_against_oracle(cuda, flags):
             mine.conv_layer.norm.weight.copy_(lp.norm_weight); mine.conv_layer.norm.bias.copy_(lp.norm_bias)
     fus64 = [torch.stack([getattr(m, f).detach().double() for f in DIR_FIELDS]).requires_grad_(True) for m in vf.gnn_layers]
     vf = vf.to(cuda)
-    vf.flags = flags
+    vf.flags = per_operator(flags)
     assert vf.flat_params().numel() == sum(32 * 32 + 32 + 64 + 24 for _ in range(p.L))
     ts = p.ts.to(torch.float32).to(cuda)
     ca = P.CubicInterpolation(ts, tuple(c.to(cuda) for c in p.coeffs_adj))
@@ -675,6 +678,8 @@ def _refsrc_flag_cases():
     out = []
     for name, kw in PIN.REFSRC_CASES.items():
         out.append(pytest.param(name, 0, id=f"{name}-ffma"))
+        if kw["n"] <= 256:
+            out.append(pytest.param(name, FUSED, id=f"{name}-fused-small"))
         if kw["n"] >= 128:
             out.append(pytest.param(name, TC, id=f"{name}-tcgen05"))
             out.append(pytest.param(name, X3, id=f"{name}-tcgen05-tf32x3"))
@@ -708,7 +713,7 @@ def test_cuda_path_against_reference_source_fixtures(cuda, name, flags):
                 mine.linear.weight.copy_(lp.weight); mine.linear.bias.copy_(lp.bias)
                 mine.norm.weight.copy_(lp.norm_weight); mine.norm.bias.copy_(lp.norm_bias)
         sv = sv.to(cuda)
-        sv.flags = flags
+        sv.flags = fused_flags() if flags == FUSED else per_operator(flags)
         for k, t in enumerate(times):
             assert rel_err(as_term(sv)(t, y0, args), g[key][k]) < 2e-5, (name, cls, t)
     dv = P.PermEquivDirGraphVectorField(p.h, p.h, widths[-1], p.L, p.e, p.n, key=0)
@@ -720,7 +725,7 @@ def test_cuda_path_against_reference_source_fixtures(cuda, name, flags):
             for i, f in enumerate(PIN.DIRECTED_FIELDS):
                 getattr(mine, f).copy_(tab[i].to(torch.float32))
     dv = dv.to(cuda)
-    dv.flags = flags
+    dv.flags = fused_flags() if flags == FUSED else per_operator(flags)
     for k, t in enumerate(times):
         assert rel_err(as_term(dv)(t, y0, args), g["vf_perm_equiv_dir"][k]) < 2e-5, (name, "directed", t)
 
@@ -974,7 +979,7 @@ def test_row_sharded_solve_on_one_rank_matches_the_ordinary_path(cuda, n, h, B, 
     from perm_equiv_graph_neural_cdes_b200 import rowshard as RS
 
     ts, A, y0, gy = _rowshard_problem(n, h, 3, 4, B, 3, cuda)
-    vf = P.PermEquivGraphVectorField(h, h, h, 3, 0, n, key=5, flags=flags).to(cuda)
+    vf = P.PermEquivGraphVectorField(h, h, h, 3, 0, n, key=5, flags=per_operator(flags)).to(cuda)   # reference = the same tcgen05 kernels
     yT_ref, gy0_ref, gp_ref = _rowshard_reference(vf, ts, A, y0, gy, 1.0, 0.25)
     ctl = RS.RowShardedControl(ts, A, A.transpose(-1, -2).contiguous(), h, 3, flags=flags)
     dy = RS.vector_field_rowsharded(vf, ctl, 1.3, y0)
