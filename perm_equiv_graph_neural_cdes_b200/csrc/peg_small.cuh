@@ -23,6 +23,7 @@ constexpr int SG_THREADS = 256;
 constexpr int SG_RB = 64, SG_WB = 64, SG_KC = 16, SG_LD = SG_RB + 4;
 constexpr int SG_SCRATCH = 5632;     // floats: max over phases (linear backward: 32x36 + 32x128 + 2x128)
 constexpr int SG_MAX_N = 512, SG_MAX_DIN = 128;
+constexpr int SG_RES_N = 128;        // up to this many nodes the interpolated adjacency of the stage stays in shared memory
 
 struct SmallArgs {
   PegControl ctl;
@@ -48,11 +49,15 @@ struct SmallSm {
   float* rinv; float* cvec;            // [64] each
   float* red;    // [160]
   int nv;        // row pitch of vec / rows (n rounded up to 4)
+  float* As;     // resident mode (n <= SG_RES_N): A_s and A'_s of the stage, [n16][P] each, P = n16 + 1 (both orientations
+  float* Ad;     //   are read from it: the odd pitch keeps row and column walks off the same banks); nullptr otherwise
+  int P;
 };
 
 __host__ __device__ inline size_t small_smem_floats(int n, int L) {
   const size_t nv = (size_t)(n + 3) / 4 * 4, n16 = (size_t)(n + 15) / 16 * 16;
-  return (size_t)(3 * L + 1) * nv + 4 * nv + n16 * SG_WB + SG_SCRATCH + 5 * 64 + 160;
+  const size_t res = n <= SG_RES_N ? 2 * n16 * (n16 + 1) + 4 : 0;
+  return (size_t)(3 * L + 1) * nv + 4 * nv + n16 * SG_WB + SG_SCRATCH + 5 * 64 + 160 + res;
 }
 
 __device__ __forceinline__ SmallSm small_carve(float* base, int n, int L) {
@@ -64,7 +69,15 @@ __device__ __forceinline__ SmallSm small_carve(float* base, int n, int L) {
   s.Vs = base;   base += (size_t)n16 * SG_WB;
   s.S = base;    base += SG_SCRATCH;
   s.cb0 = base; s.cb1 = base + 64; s.sM = base + 128; s.rinv = base + 192; s.cvec = base + 256; base += 320;
-  s.red = base;
+  s.red = base;  base += 160;
+  if (n <= SG_RES_N) {
+    s.P = n16 + 1;
+    s.As = base;
+    s.Ad = base + (size_t)n16 * s.P;
+  } else {
+    s.P = 0;
+    s.As = s.Ad = nullptr;
+  }
   return s;
 }
 
@@ -122,6 +135,38 @@ __device__ void small_prep(const SmallArgs& a, int b, int rank, const SmallSm& s
       sm.vec[(3 * l + 2) * nv + i] = (f[8] * rA + f[9] * rD) * inv_n;
     }
     sm.vec[3 * L * nv + i] = tc[i] + s * (2.f * tc[n + i] + 3.f * s * tc[2 * n + i]);
+  }
+  __syncthreads();
+}
+
+// resident mode: A_s = sum_p wA[p] plane_p and A'_s = sum_p wD[p] plane_p of the stage's cubic piece, once per kernel.  The tiled
+// planes are read in storage order (a warp's 128-bit loads are 512 contiguous bytes); thread (g, m, lane) of a 32x32 tile holds
+// row 4 rq + m, columns 4 cq .. 4 cq + 3 of all four planes (peg_tile_off).
+__device__ void small_build_A(const SmallArgs& a, int b, const StageScalars* S, const SmallSm& sm) {
+  const int tid = threadIdx.x, n16 = (a.n + 15) / 16 * 16, nt = a.npad >> 5, tiles = (n16 + 31) >> 5, P = sm.P;
+  const float* Pl = a.ctl.adj_coef + ((size_t)b * (a.T - 1) + S->interval) * 4 * (size_t)a.npad * a.npad;
+  const int g = tid >> 7, m = (tid >> 5) & 3, lane = tid & 31;
+  const int s_ = (g << 2) | (lane >> 3), cq = lane & 7, rq = (s_ + cq) & 7;
+  const int r = rq * 4 + m, c = cq * 4;
+  const float wA0 = S->wA[0], wA1 = S->wA[1], wA2 = S->wA[2], wA3 = S->wA[3], wD1 = S->wD[1], wD2 = S->wD[2], wD3 = S->wD[3];
+#pragma unroll 2
+  for (int t = 0; t < tiles * tiles; ++t) {
+    const int rt = t / tiles, ct = t - rt * tiles;
+    const float* tb = Pl + ((size_t)rt * nt + ct) * 4096 + (size_t)(g * 16 + m) * 128 + lane * 4;
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(tb));
+    const float4 p1 = __ldg(reinterpret_cast<const float4*>(tb + 512));
+    const float4 p2 = __ldg(reinterpret_cast<const float4*>(tb + 1024));
+    const float4 p3 = __ldg(reinterpret_cast<const float4*>(tb + 1536));
+    const int gi = rt * 32 + r, gk = ct * 32 + c;
+    if (gi < n16 && gk < n16) {
+      const float e0[4] = {p0.x, p0.y, p0.z, p0.w}, e1[4] = {p1.x, p1.y, p1.z, p1.w};
+      const float e2[4] = {p2.x, p2.y, p2.z, p2.w}, e3[4] = {p3.x, p3.y, p3.z, p3.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sm.As[gi * P + gk + j] = wA0 * e0[j] + wA1 * e1[j] + wA2 * e2[j] + wA3 * e3[j];
+        sm.Ad[gi * P + gk + j] = wD1 * e1[j] + wD2 * e2[j] + wD3 * e3[j];
+      }
+    }
   }
   __syncthreads();
 }
@@ -263,6 +308,9 @@ struct SmallItem {
   int relu, scale_tg;
   float* out;           // graph base, pitch d
   // adjoint only
+  const float* As;      // resident A_s / A'_s (shared memory, pitch P) or nullptr: stream the planes
+  const float* Ad;
+  int ldA;
   const float* Mref;    // graph base, pitch d
   const float* rows;    // smem [4][nv]
   int nv;
@@ -344,11 +392,44 @@ __device__ void small_contract_item(const SmallItem& it, const StageScalars* S, 
       if (NACC == 4) *reinterpret_cast<float4*>(&Sm_[3][tkr][4 * tiq]) = make_float4(y1[0], y1[1], y1[2], y1[3]);
     }
   };
-  fetch(0);
+  const bool resident = it.As != nullptr;
+  const int n16 = (n + 15) / 16 * 16;
+  // resident mode: the operand tiles come straight from A_s / A'_s in shared memory -- no L2 round trip per K chunk
+  auto stage_res = [&](int k0) {
+    const int P = it.ldA;
+    {
+      const int gi = i0 + drow, gk = k0 + 4 * dkq;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a_ = 0.f, d_ = 0.f;
+        if (gi < n16) { a_ = it.As[gi * P + gk + j]; d_ = it.Ad[gi * P + gk + j]; }
+        if (NACC == 1) {
+          Sm_[0][4 * dkq + j][drow] = alpha * a_ + beta * d_;
+        } else {
+          Sm_[0][4 * dkq + j][drow] = a_;
+          Sm_[1][4 * dkq + j][drow] = d_;
+        }
+      }
+    }
+    {
+      const int gk = k0 + tkr, gi = i0 + 4 * tiq;
+      float y0[4], y1[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a_ = 0.f, d_ = 0.f;
+        if (gi + j < n16) { a_ = it.As[gk * P + gi + j]; d_ = it.Ad[gk * P + gi + j]; }
+        if (NACC == 1) { y0[j] = gamma * a_ + delta * d_; y1[j] = 0.f; }
+        else { y0[j] = a_; y1[j] = d_; }
+      }
+      *reinterpret_cast<float4*>(&Sm_[NS / 2][tkr][4 * tiq]) = make_float4(y0[0], y0[1], y0[2], y0[3]);
+      if (NACC == 4) *reinterpret_cast<float4*>(&Sm_[3][tkr][4 * tiq]) = make_float4(y1[0], y1[1], y1[2], y1[3]);
+    }
+  };
+  if (!resident) fetch(0);
   for (int k0 = 0; k0 < n; k0 += SG_KC) {
-    stage(k0);
+    if (resident) stage_res(k0); else stage(k0);
     __syncthreads();
-    if (k0 + SG_KC < n) fetch(k0 + SG_KC);     // in flight while this chunk is multiplied
+    if (!resident && k0 + SG_KC < n) fetch(k0 + SG_KC);     // in flight while this chunk is multiplied
 #pragma unroll
     for (int k = 0; k < SG_KC; ++k) {
       const float4 v4 = *reinterpret_cast<const float4*>(&sm.Vs[(k0 + k) * SG_WB + 4 * tx]);
@@ -628,6 +709,7 @@ __device__ void small_phase_contract_fwd(const SmallArgs& a, int b, int l, const
   it.kappa = S->kappa[l];
   it.relu = relu; it.scale_tg = scale_tg;
   it.out = out;
+  it.As = sm.As; it.Ad = sm.Ad; it.ldA = sm.P;
   it.Mref = nullptr; it.rows = nullptr; it.nv = sm.nv; it.totA = it.totD = 0.f; it.first_row_block = 0; it.g_fus = nullptr;
   int cur = -1;
   for (int q = lo; q < hi; ++q) {
@@ -650,6 +732,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_small_fwd(const SmallArgs a) 
   const SmallSm sm = small_carve(sg_smem, a.n, a.L);
   const int n = a.n, h = a.h, L = a.L, dmax = a.model.dmax;
   small_prep(a, b, rank, sm, &S);
+  if (sm.As) small_build_A(a, b, &S, sm);
   float* Mg = a.M + (size_t)b * n * dmax;
   const float* Zin = a.yin + (size_t)b * n * h;
   for (int l = 0; l < a.nlayers; ++l) {
@@ -693,6 +776,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_small_vjp(const SmallArgs a) 
   const int n = a.n, h = a.h, L = a.L, dmax = a.model.dmax, e2 = 2 * a.e;
   const int dL = a.model.layer[L - 1].dout;
   small_prep(a, b, rank, sm, &S);
+  if (sm.As) small_build_A(a, b, &S, sm);
   float* Mg = a.M + (size_t)b * n * dmax;
   float* Ng = a.N + (size_t)b * n * h;
   float* Og = a.Obar + (size_t)b * n * dmax;
@@ -754,6 +838,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_small_vjp(const SmallArgs a) 
       it.kappa = S.kappa[l];
       it.relu = 0; it.scale_tg = 0;
       it.out = Bg;
+      it.As = sm.As; it.Ad = sm.Ad; it.ldA = sm.P;
       it.Mref = Mg; it.rows = sm.rows; it.nv = sm.nv; it.totA = S.totA; it.totD = S.totD; it.g_fus = g_fus;
       int cur = -1;
       for (int q = lo; q < hi; ++q) {
