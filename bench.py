@@ -455,7 +455,7 @@ def measure_heat(D, args, steps, warmup):
     ms = D.max_ms(e0.elapsed_time(e1)) / steps
     return {"workload": "heat (configs[0]: n=400, B=4, h=16, L=2, adaptive Tsit5 rtol 1e-3, SaveAt(ts))", "value": D.world * attempted / (ms * 1e-3), "unit": UNIT,
             "ms_per_step": ms, "attempted_solver_steps_per_gpu": attempted, "graphs_per_gpu": B,
-            "note": "adaptive path: per-trajectory step sequences, host-side controller (one scaled-error read-back per attempted step)"}
+            "note": "adaptive path: the whole batch steps per launch with per-trajectory (t, dt) on the device (pegncde_step_fwd_batched + pegncde_adaptive_control); the host polls the done flags every 8 attempts"}
 
 
 def run_ours(args):
