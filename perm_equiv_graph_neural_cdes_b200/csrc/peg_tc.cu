@@ -165,7 +165,7 @@ __device__ __forceinline__ int bfp_min_exponent(const int* __restrict__ ve, int 
 }
 
 // KIND 0 = forward, 1 = adjoint with four 3xTF32 products (default), 2 = LIGHT adjoint (two 3xTF32 products + two single-pass
-// ones; PEG_TC_ADJ_LIGHT=1, looser tolerance on the param1 / param2 gradients: 2.5e-3 instead of 1e-3)
+// ones; PEG_FLAG_ADJ_LIGHT, looser tolerance on the param1 / param2 gradients: 2.5e-3 instead of 1e-3)
 // FMT 0 = 3xTF32 operands (fp32 words, SWIZZLE_128B tiles, kind::tf32: error ~2^-22 per product);
 // FMT 1 = bf16x2 operands (x = hi + lo, both bf16; hi*hi + lo*hi + hi*lo on kind::f16 at twice the tf32 rate and half the
 //         shared-memory traffic; SWIZZLE_64B tiles of 8 KB; error ~2^-17 per product, fp32 accumulate in TMEM)

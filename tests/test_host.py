@@ -387,3 +387,14 @@ def test_jax_wrapper_operands_match_the_shim_bindings(monkeypatch):
     for name, nargs, nouts, attrs in calls:
         seen[targets[name]] = (nargs, nouts, attrs)
     assert seen == bindings, (seen, bindings)
+
+
+def test_integration_doc_quotes_the_committed_file():
+    """INTEGRATION.md's reference-side "after" snippet is the literal body of jax_ffi/reference_integration.py."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    body = open(os.path.join(root, "perm_equiv_graph_neural_cdes_b200", "jax_ffi", "reference_integration.py")).read()
+    code = body[body.index("import diffrax"):].rstrip("\n")
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    assert code in doc
+    # and the file is valid Python (it cannot be imported here: jax / diffrax / the reference tree are absent)
+    compile(body, "reference_integration.py", "exec")
