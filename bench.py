@@ -574,29 +574,61 @@ def run_rowsharded(args):
     S = len(P.constant_step_table(0.0, t1_solve, wl["dt0"])) - 1
     l = _lib.lib()
 
-    def step():
+    def step(reduce=True):
         vf.zero_grad(set_to_none=True)
         y = y0.detach().requires_grad_(True)
-        yT = RS.diffeqsolve_rowsharded(vf, ctl, y, 0.0, t1_solve, wl["dt0"])
+        yT = RS.diffeqsolve_rowsharded(vf, ctl, y, 0.0, t1_solve, wl["dt0"], reduce_grads=False)
         (yT * gy).sum().backward()
-        return torch.cat([p.grad.reshape(-1) for p in vf.parameters()])
+        flat_ = torch.cat([p.grad.reshape(-1) for p in vf.parameters()])
+        if reduce and D.world > 1:      # per-rank partial sums over the rank's rows -> the parameter gradient
+            torch.distributed.all_reduce(flat_)
+        return flat_
 
     for _ in range(max(args.warmup, 1)):
         flat = step()
     D.barrier()
+    # the whole step (forward + adjoint, exchanges included: device-side epoch base) replays as ONE CUDA graph; the all-reduce of
+    # the flat gradient buffer stays outside, as in the batch-sharded path
+    graph = None
     l.pegncde_profile_enable(args.profile_stride)
     launches0 = l.pegncde_launch_count()
+    if not args.no_graph:
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step(reduce=False)          # warm the capture stream's workspace
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        D.barrier()
+        l.pegncde_profile_enable(args.profile_stride)
+        launches0 = l.pegncde_launch_count()
+        with torch.cuda.graph(graph):
+            g_flat = step(reduce=False)
+        launches_per_step = l.pegncde_launch_count() - launches0
+        for _ in range(2):
+            graph.replay()
+        D.barrier()
+
+    def timed_step():
+        if graph is not None:
+            graph.replay()
+            if D.world > 1:
+                torch.distributed.all_reduce(g_flat)
+            return g_flat
+        return step()
+
     sampler = ClockSampler(D.local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        flat = step()
+        flat = timed_step()
     e1.record()
     D.barrier()
     clocks = sampler.summary()
     ms_per_step = D.max_ms(e0.elapsed_time(e1)) / args.steps
-    launches = l.pegncde_launch_count() - launches0
+    launches = launches_per_step * args.steps if graph is not None else l.pegncde_launch_count() - launches0
     prof = {}
     for d_, nm in ((0, "fwd"), (1, "bwd")):
         a, b_, c_, by, fl = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
@@ -625,7 +657,7 @@ def run_rowsharded(args):
                 "dtype": "f32 (contraction: %s split operands on tcgen05, fp32 accumulate)" % args.operands, "data": "synthetic",
                 "config": {"workload": args.workload, "shard": "rows", "n": n, "hidden": h, "layers": L, "knots": T, "graphs": B, "solver_steps": S,
                            "rows_per_gpu": nloc, "parallelism": "ONE graph row-sharded over %d GPU(s): strips of the path and of its transpose per rank; V^T exchanged per layer over peer memory (k_shard_push / k_shard_wait), parameter gradients all-reduced (NCCL)" % D.world},
-                "gpu_launches": int(launches), "cuda_graph": False, "clocks": clocks, "grad_check": grad_check,
+                "gpu_launches": int(launches), "cuda_graph": graph is not None, "clocks": clocks, "grad_check": grad_check,
                 "exchange": {"per_solver_step": 12 * L, "nvlink_bytes_per_exchange_and_rank": nvlink, "nvlink_bytes_per_step_and_rank": nvlink * exchanges},
                 "roofline": {"bound": "hbm", "kernel": "k_tc_contract (row strips)", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
                              "traffic": None, "algorithmic_bytes_per_launch": bytes_launch, "fwd_avg_us": prof["fwd"]["ms"] / max(prof["fwd"]["timed"], 1) * 1e3,

@@ -105,7 +105,12 @@ typedef struct PegDims {
  * data path; parameter gradients come out as per-rank partial sums (the caller all-reduces them like in batch-sharded mode).
  * All pointer tables are HOST arrays of `world` (<= 8) device pointers to peer-visible (symmetric) buffers of identical layout.
  * Restrictions: PEG_FLAG_TENSOR_CORES with fp16x2 or 3xTF32 operands, e == 0, undirected layer, PegDims.n a multiple of 128,
- * fixed-step entry points (vf_fwd / vf_vjp / solve_fwd / solve_bwd).  Not capturable in a CUDA graph (epochs are launch arguments). */
+ * fixed-step entry points (vf_fwd / vf_vjp / solve_fwd / solve_bwd).
+ * CUDA graphs: with epoch_dev == NULL the epoch of every exchange is a launch argument taken from the host counter, so a
+ * captured call cannot be replayed.  With epoch_dev set, the kernels add the device word *epoch_dev to a per-call sequence
+ * number (the host counter restarts at 0 on every API call), and every call ends by advancing *epoch_dev by its (even; a flag-only
+ * exchange pads an odd count, which also keeps the epoch-parity halves alternating across calls) number of exchanges: replays of
+ * a captured call then use fresh epochs.  Every rank must replay the same sequence of calls. */
 typedef struct PegShard {
   int32_t rank, world;
   int32_t n_glob;            /* global node count = world * PegDims.n                                                  */
@@ -117,6 +122,7 @@ typedef struct PegShard {
   float* const* colsum;      /* [world] -> [2][world][2][B * 2 * dmax] column-sum slots (two vectors per exchange)        */
   uint32_t* const* flags;    /* [world] -> [world + 1] epoch counters (one per source rank) + an error word              */
   uint32_t* epoch;           /* HOST counter of exchanges enqueued so far on this rank (in / out; same on every rank)     */
+  uint32_t* epoch_dev;       /* nullable DEVICE word (this rank's own memory, zero-initialised): epoch base for graph replay  */
 } PegShard;
 
 /* Planar control path, built once per batch by pegncde_pack_adj / pegncde_pack_x.

@@ -32,7 +32,7 @@ class PegShard(Structure):
     """Row-sharded mode (include/pegncde.h): the pointer tables are HOST arrays of `world` device pointers."""
     _fields_ = [("rank", c_int32), ("world", c_int32), ("n_glob", c_int32), ("row0", c_int32), ("adj_coef_t", c_void_p),
                 ("vt_hi", POINTER(c_void_p)), ("vt_lo", POINTER(c_void_p)), ("vexp", POINTER(c_void_p)), ("colsum", POINTER(c_void_p)),
-                ("flags", POINTER(c_void_p)), ("epoch", POINTER(ctypes.c_uint32))]
+                ("flags", POINTER(c_void_p)), ("epoch", POINTER(ctypes.c_uint32)), ("epoch_dev", c_void_p)]
 
 
 class PegAdaptState(Structure):

@@ -246,7 +246,8 @@ struct ShardXchg {
   float* colsum[PEG_MAX_WORLD];
   uint32_t* flags[PEG_MAX_WORLD];
   int rank, world;
-  uint32_t epoch;            // value raised in the peers' flags by this exchange
+  uint32_t epoch;            // value raised in the peers' flags by this exchange (plus *epoch_base when that is set)
+  const uint32_t* epoch_base;   // nullable device word: exchanges completed by earlier calls / graph replays (even)
   size_t half_bytes;         // bytes of one epoch-parity half of a V^T buffer
   int push_vt;               // 0: only the column sums travel (no V^T in this exchange)
   int rows;                  // B * d rows of V^T
@@ -308,9 +309,10 @@ __global__ void __launch_bounds__(256) k_shard_push(const ShardXchg x) {
   __syncthreads();
   if (last) {
     __threadfence_system();
+    const uint32_t epoch = x.epoch + (x.epoch_base ? *reinterpret_cast<const volatile uint32_t*>(x.epoch_base) : 0u);
     for (int q = threadIdx.x; q < x.world; q += blockDim.x) {
       volatile uint32_t* f = x.flags[q] + x.rank;
-      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(x.epoch) : "memory");
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
     }
   }
 }
@@ -324,12 +326,13 @@ __global__ void __launch_bounds__(256) k_shard_wait(const ShardXchg x) {
   if (threadIdx.x == 0) ok = 1;
   __syncthreads();
   if (threadIdx.x < x.world) {
+    const uint32_t epoch = x.epoch + (x.epoch_base ? *reinterpret_cast<const volatile uint32_t*>(x.epoch_base) : 0u);
     const uint32_t* f = x.flags[x.rank] + threadIdx.x;
     const long long t0 = clock64();
     uint32_t v;
     while (true) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-      if ((int32_t)(v - x.epoch) >= 0) break;
+      if ((int32_t)(v - epoch) >= 0) break;
       if (clock64() - t0 > 4000000000ll) { ok = 0; x.flags[x.rank][x.world] = 1u; break; }
       __nanosleep(200);
     }
@@ -346,6 +349,9 @@ __global__ void __launch_bounds__(256) k_shard_wait(const ShardXchg x) {
     }
   }
 }
+
+// end of an API call in graph-replayable mode: the epoch base moves past this call's exchanges
+__global__ void k_epoch_advance(uint32_t* base, uint32_t count) { *base += count; }
 
 // x coeffs: d,c,b,a each [B,T-1,n,e,2] -> x_coef [B,T-1,3,n,2e] (b,c,d)
 __global__ void k_pack_x(const float* __restrict__ cd, const float* __restrict__ cc, const float* __restrict__ cb,

@@ -158,6 +158,9 @@ __device__ __forceinline__ LightCoef light_coef(float wa, float wd) {
 // fp16x2 (block floating point): V^T holds V * 2^(e_J) per 128-node block J.  The blocks are aligned to the smallest exponent E
 // inside the A operand (its entries are multiplied by 2^(E - e_J) <= 1, exact), so every accumulator ends up scaled by 2^E times the
 // A scale.  E is cheap enough (one exponent per 128 nodes) for every thread that needs it to recompute it from global memory.
+#ifndef PEG_VEXP_LOAD
+#define PEG_VEXP_LOAD __ldcg      // (A/B builds only: -DPEG_VEXP_LOAD=__ldg measures what the coherent path costs; wrong on >1 rank)
+#endif
 __device__ __forceinline__ int bfp_min_exponent(const int* __restrict__ ve, int nblk) {
   int e = PEG_VEXP_MAX;
   for (int J = 0; J < nblk; ++J) e = min(e, __ldcg(ve + J));     // L2: in row-sharded mode peers write these entries over NVLink
@@ -217,6 +220,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   // and the plane weights stay warp-uniform (uniform registers): fewer instructions, a dozen fewer live vector registers
   int* sched_kc_s = reinterpret_cast<int*>(smem_gen + (tmem_slot + 8u - smem_base));     // [nkc] K chunk of every pair
   float2* sched_f_s = reinterpret_cast<float2*>(sched_kc_s + ((p.nkc + 1) & ~1));           // [nkc] BFP item factors (variant 0, 1)
+  int* emin_s = reinterpret_cast<int*>(sched_f_s + p.nkc);                                   // smallest block exponent of this graph's V^T
 
   if (tid == 0) {
     for (int s = 0; s < SA; ++s)
@@ -296,10 +300,11 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     const int Emin = BFP ? bfp_min_exponent(ve, (a.ldk + 127) >> 7) : 0;
     for (int pr = tid; pr < npairs; pr += TC_THREADS) {
       const int kc = kc_of(pr0 + pr);
-      const float f = BFP ? exp2_int(max(Emin - __ldcg(ve + (kc >> 2)), -120)) : 1.f;
+      const float f = BFP ? exp2_int(max(Emin - PEG_VEXP_LOAD(ve + (kc >> 2)), -120)) : 1.f;
       sched_kc_s[pr] = kc;
       if (BFP) sched_f_s[pr] = make_float2(f * as0, f * as1);
     }
+    if (BFP && tid == 0) *emin_s = Emin;
     __syncthreads();
   }
   if (warp < 16) {
@@ -722,7 +727,7 @@ k_tc_contract(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         tmem_wait_ld();
         if constexpr (BFP) {   // undo the block scales (powers of two: exact); accumulator acc = type * 2 + v carries the scale of variant v
           // |exponents| <= 60: both factors are normal numbers
-          const int Emin = bfp_min_exponent(p.vexp + (size_t)b * p.vexp_stride, (a.ldk + 127) >> 7);
+          const int Emin = *emin_s;
           const float d0 = exp2_int(-a_scale_exponent(0)) * exp2_int(-Emin), d1 = BWD ? exp2_int(-a_scale_exponent(NA - 1)) * exp2_int(-Emin) : 1.f;
 #pragma unroll
           for (int u = 0; u < 16; ++u) {

@@ -267,7 +267,7 @@ static int shard_exchange(Ctx& c, bool with_vt, int dcols, float* cs0, float* cs
   for (int q = 0; q < sh.world; ++q) {
     x.vt_hi[q] = sh.vt_hi[q]; x.vt_lo[q] = sh.vt_lo[q]; x.vexp[q] = sh.vexp[q]; x.colsum[q] = sh.colsum[q]; x.flags[q] = sh.flags[q];
   }
-  x.rank = sh.rank; x.world = sh.world; x.epoch = epoch;
+  x.rank = sh.rank; x.world = sh.world; x.epoch = epoch; x.epoch_base = sh.epoch_dev;
   const size_t esz = c.w.tc.fmt == PEG_FMT_TF32X3 ? 4 : 2;
   const size_t ldk = (size_t)peg_npad(sh.n_glob);
   x.half_bytes = (size_t)c.d.B * c.m.dmax * ldk * 4;          // the halves are sized for fp32 words (3xTF32), 16-bit parts use the front
@@ -290,6 +290,14 @@ static int shard_exchange(Ctx& c, bool with_vt, int dcols, float* cs0, float* cs
   k_shard_push<<<dim3(gx, sh.world), 256, 0, c.st>>>(x);
   PEG_LAUNCH_CHECK();
   k_shard_wait<<<1, 256, 0, c.st>>>(x);
+  PEG_LAUNCH_CHECK();
+  return PEG_OK;
+}
+// graph-replayable mode: every API call leaves the epoch base even and past its own exchanges
+static int shard_finish(Ctx& c) {
+  if (!c.sh || !c.sh->epoch_dev) return PEG_OK;
+  if (*c.sh->epoch & 1u) PEG_TRY(shard_exchange(c, false, 0, nullptr, nullptr));     // flag-only exchange: keeps the parity halves alternating
+  k_epoch_advance<<<1, 1, 0, c.st>>>(c.sh->epoch_dev, *c.sh->epoch);
   PEG_LAUNCH_CHECK();
   return PEG_OK;
 }
@@ -632,6 +640,7 @@ static int make_ctx(Ctx& c, peg_stream_t stream, const PegDims* dims, const PegC
 static int reset_tickets(Ctx& c) {
   c.w.tc.fmt = c.fmt;   // plan() carved the workspace after make_ctx chose the format
   c.xticket = c.w.tickets + (c.w.tickets_count - 1);
+  if (c.sh && c.sh->epoch_dev) *c.sh->epoch = 0;     // per-call sequence numbers on top of the device-side base
   if (c.sh) {           // row-sharded: V^T spans all n_glob nodes and lives in the peer-visible buffers
     c.w.tc.ldk = peg_npad(c.sh->n_glob);
     c.w.tc.col0 = c.sh->row0;
@@ -871,7 +880,8 @@ int pegncde_vf_fwd(peg_stream_t stream, const PegDims* dims, const PegControl* c
   if (workspace_bytes < plan(*dims, PEG_WS_VF_FWD, 0, nullptr, nullptr, nullptr)) return PEG_ERR_WORKSPACE;
   plan(*dims, PEG_WS_VF_FWD, 0, workspace, &c.w, nullptr);
   PEG_TRY(reset_tickets(c));
-  return feval_fwd(c, t, y, dy, nullptr);
+  PEG_TRY(feval_fwd(c, t, y, dy, nullptr));
+  return shard_finish(c);
 }
 
 int pegncde_vf_vjp(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params, float t,
@@ -889,7 +899,8 @@ int pegncde_vf_vjp(peg_stream_t stream, const PegDims* dims, const PegControl* c
   for (int l = 1; l < dims->L; ++l) save[l] = s.save[0][l];
   // forward over the first L-1 layers only: the VJP needs the layer inputs, not the evaluation's output
   PEG_TRY(feval_fwd(c, t, y, nullptr, save, dims->L - 1));
-  return feval_vjp(c, t, save, g_dy, g_y, g_params, g_xdot);
+  PEG_TRY(feval_vjp(c, t, save, g_dy, g_y, g_params, g_xdot));
+  return shard_finish(c);
 }
 
 int pegncde_step_fwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params, float t,
@@ -1095,7 +1106,7 @@ int pegncde_solve_fwd(peg_stream_t stream, const PegDims* dims, const PegControl
     float* tmp = k[0]; k[0] = k[6]; k[6] = tmp;  // FSAL
   }
   if (yT) PEG_CUDA(cudaMemcpyAsync(yT, y_ckpt + (size_t)steps * st, st * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
-  return PEG_OK;
+  return shard_finish(c);
 }
 
 int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl* ctl, const float* params,
@@ -1204,7 +1215,7 @@ int pegncde_solve_bwd(peg_stream_t stream, const PegDims* dims, const PegControl
       float* tmp = s.gcur; s.gcur = s.gnext; s.gnext = tmp;
     }
   }
-  return PEG_OK;
+  return shard_finish(c);
 }
 
 const char* pegncde_strerror(int code) {

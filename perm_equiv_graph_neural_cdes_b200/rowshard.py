@@ -103,8 +103,11 @@ class RowShardedControl:
             self._handles.append(hdl)
             self._ptr_tables.append((ctypes.c_void_p * self.world)(*ptrs))
         self._epoch = ctypes.c_uint32(0)
+        # device-side epoch base: every call advances it past its own exchanges, so a captured solve can be replayed as a CUDA graph
+        self._epoch_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self.shard = PegShard(self.rank, self.world, n, r0, self.adj_coef_t.data_ptr(), self._ptr_tables[0], self._ptr_tables[1],
-                              self._ptr_tables[2], self._ptr_tables[3], self._ptr_tables[4], ctypes.pointer(self._epoch))
+                              self._ptr_tables[2], self._ptr_tables[3], self._ptr_tables[4], ctypes.pointer(self._epoch),
+                              self._epoch_dev.data_ptr())
         self._keep = (A, At)
         if self.world > 1:
             dist.barrier(group=group)     # every rank's buffers exist (and are zeroed) before the first push
@@ -120,7 +123,7 @@ class RowShardedControl:
 
 class _RowShardedSolve(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y0, flat, ctl: RowShardedControl, dims, step_ts):
+    def forward(ctx, y0, flat, ctl: RowShardedControl, dims, step_ts, reduce_grads=True):
         y0, flat = y0.contiguous(), flat.contiguous()
         l, dev = lib(), y0.device
         S = len(step_ts) - 1
@@ -133,7 +136,7 @@ class _RowShardedSolve(torch.autograd.Function):
                                   y0.data_ptr(), None, y_ckpt.data_ptr(), store.data_ptr() if store is not None else None, ws.data_ptr(), ws.numel()),
               "pegncde_solve_fwd (row-sharded)")
         ctx.save_for_backward(flat, y_ckpt)
-        ctx.store, ctx.ctl, ctx.dims, ctx.host_ts, ctx.S = store, ctl, dims, host_ts, S
+        ctx.store, ctx.ctl, ctx.dims, ctx.host_ts, ctx.S, ctx.reduce_grads = store, ctl, dims, host_ts, S, reduce_grads
         return y_ckpt[S]
 
     @staticmethod
@@ -149,23 +152,24 @@ class _RowShardedSolve(torch.autograd.Function):
                                   y_ckpt.data_ptr(), store.data_ptr() if store is not None else None, g_yT.data_ptr(), None, None, g_y0.data_ptr(),
                                   g_flat.data_ptr(), None, ws.data_ptr(), ws.numel()), "pegncde_solve_bwd (row-sharded)")
         ctx.store = None
-        if ctl.world > 1:      # every rank holds the partial sums over its rows: the parameter gradient is their sum
+        if ctl.world > 1 and ctx.reduce_grads:      # every rank holds the partial sums over its rows: the parameter gradient is their sum
             dist.all_reduce(g_flat, op=dist.ReduceOp.SUM, group=ctl.group)
-        return g_y0, g_flat, None, None, None
+        return g_y0, g_flat, None, None, None, None
 
 
 def diffeqsolve_rowsharded(vf: PermEquivGraphVectorField, ctl: RowShardedControl, y0_rows: torch.Tensor, t0: float, t1: float, dt0: float,
-                           max_steps: int = 4096) -> torch.Tensor:
+                           max_steps: int = 4096, reduce_grads: bool = True) -> torch.Tensor:
     """Fixed-step Tsit5 solve of the row-sharded graph: ``y0_rows`` = this rank's rows ``[n_loc, h]`` (or ``[B, n_loc, h]``) of the initial
     state; returns the same rows of ``y(t1)``.  Differentiable: the cotangent w.r.t. ``y0_rows`` is row-local, the parameter gradients
-    are all-reduced over the group (every rank ends up with the full gradient)."""
+    are all-reduced over the group (every rank ends up with the full gradient) unless ``reduce_grads=False`` (the caller then reduces
+    the per-rank partial sums itself, e.g. outside a captured CUDA graph; the solve itself -- exchanges included -- is capturable)."""
     if vf.uses_control() or vf.directed:
         raise NotImplementedError("row-sharded mode: ODETerm(PermEquivGraphVectorField) without the CDE wrapper, undirected layer")
     unb = y0_rows.dim() == 2
     yb = (y0_rows.unsqueeze(0) if unb else y0_rows).to(torch.float32)
     dims = ctl.dims(vf.hidden_dim, vf.num_layers, vf.flags)
     step_ts = constant_step_table(float(t0), float(t1), float(dt0), "state", max_steps)
-    out = _RowShardedSolve.apply(yb, vf.checked_flat_params(dims), ctl, dims, step_ts)
+    out = _RowShardedSolve.apply(yb, vf.checked_flat_params(dims), ctl, dims, step_ts, reduce_grads)
     return out.squeeze(0) if unb else out
 
 

@@ -993,6 +993,46 @@ def test_row_sharded_solve_on_one_rank_matches_the_ordinary_path(cuda, n, h, B, 
     assert rel_err(torch.cat([p.grad.reshape(-1) for p in vf.parameters()]), gp_ref) < 1e-5
 
 
+def test_row_sharded_solve_replays_as_a_cuda_graph(cuda):
+    """The exchange's epochs come from a device-side base that every call advances, so a captured forward + adjoint solve can be
+    replayed: every replay must reproduce the eager result (an exchange that reused stale epochs would read V^T before it is
+    written, or -- with an odd number of exchanges per call -- overwrite the half a peer still reads)."""
+    from perm_equiv_graph_neural_cdes_b200 import rowshard as RS
+
+    n, h, B = 256, 64, 2
+    ts, A, y0, gy = _rowshard_problem(n, h, 3, 4, B, 7, cuda)
+    vf = P.PermEquivGraphVectorField(h, h, h, 3, 0, n, key=5).to(cuda)
+    ctl = RS.RowShardedControl(ts, A, A.transpose(-1, -2).contiguous(), h, 3, flags=vf.flags)
+
+    def step(dt0):
+        vf.zero_grad(set_to_none=True)
+        y = y0.detach().requires_grad_(True)
+        yT = RS.diffeqsolve_rowsharded(vf, ctl, y, 0.0, 1.0, dt0, reduce_grads=False)
+        (yT * gy).sum().backward()
+        return yT.detach(), y.grad, torch.cat([p.grad.reshape(-1) for p in vf.parameters()])
+
+    for dt0 in (1.0, 0.25):      # 1 step = 18 + 18 exchanges; dt0 = 1.0 also covers calls right after one another
+        ref = [t.clone() for t in step(dt0)]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step(dt0)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = step(dt0)
+        for _ in range(3):
+            graph.replay()
+            torch.cuda.synchronize()
+            assert rel_err(out[0], ref[0]) < 1e-6
+            assert rel_err(out[1], ref[1]) < 1e-5
+            assert rel_err(out[2], ref[2]) < 1e-5
+        assert int(ctl._bufs[4].view(torch.int32)[ctl.world].item()) == 0      # the exchange's error word
+        eager = step(dt0)       # and an eager call after the replays still lines up with the epoch base
+        assert rel_err(eager[0], ref[0]) < 1e-6
+
+
 def _rowshard_rank(rank, world, port, n, h, B, flags, out):
     import torch.distributed as dist
 
