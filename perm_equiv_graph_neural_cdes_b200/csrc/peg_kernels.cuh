@@ -1077,6 +1077,75 @@ __global__ void __launch_bounds__(256) k_wrapper_bwd(const float* __restrict__ k
   }
 }
 
+// Top layer of a VJP without the CDE wrapper (e = 0), tensor-core path: ONE kernel instead of k_wrapper_bwd -> k_colsums ->
+// k_block_exponent -> k_split_transpose.  A CTA owns a 128-node block with ALL d columns (d <= 256) in shared memory:
+//   Obar = tg (.) kbar (written out), its block exponent (fp16x2 operands), V^T hi / lo in the contraction's operand format
+//   (lane = node: coalesced), and the deterministic column sums 1^T Obar, r^T Obar (partials per block, last block adds them in
+//   block order).  grid (ceil(rows_pad / 128), B), block 256, dynamic smem 128 * (d + 1) floats.
+__global__ void __launch_bounds__(256) k_top_producer(const float* __restrict__ kbar, const float* __restrict__ svec, size_t sv_stride,
+                                                      size_t tg_off, int n, int d, float* __restrict__ Obar, const ProducerOut po) {
+  extern __shared__ __align__(16) float tp_tile[];     // [128][d + 1]
+  __shared__ float bmax_s[8];
+  __shared__ bool is_last;
+  const int b = blockIdx.y, blk = blockIdx.x, i0 = blk * 128, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pitch = d + 1, c4n = d >> 2;
+  const float* sv = svec + (size_t)b * sv_stride;
+  const float4* src = reinterpret_cast<const float4*>(kbar + (size_t)b * n * d);
+  float4* dst = reinterpret_cast<float4*>(Obar + (size_t)b * n * d);
+  float mx = 0.f;
+  for (int idx = tid; idx < 128 * c4n; idx += 256) {
+    const int r = idx / c4n, c4 = idx - r * c4n, i = i0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) {
+      const float tg = sv[tg_off + i];
+      const float4 k = __ldg(src + (size_t)i * c4n + c4);
+      v = make_float4(tg * k.x, tg * k.y, tg * k.z, tg * k.w);
+      dst[(size_t)i * c4n + c4] = v;
+    }
+    float* t = tp_tile + r * pitch + 4 * c4;
+    t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  mx = warp_max(mx);
+  if (lane == 0) bmax_s[warp] = mx;
+  __syncthreads();
+  float vscale = 1.f;
+  if (po.t16 == PEG_FMT_FP16X2) {
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) mx = fmaxf(mx, bmax_s[w8]);
+    const int e = block_exponent(mx);
+    vscale = exp2_int(e);
+    if (tid == 0) po.vexp[(size_t)b * po.vexp_stride + po.blk0 + blk] = e;
+  }
+  // V^T: warp w owns columns w, w + 8, ...; a lane owns nodes lane, lane + 32, ... of the block (odd pitch: conflict-free column walk)
+  for (int c = warp; c < d; c += 8) {
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int r = lane + 32 * rr;
+      if (i0 + r >= po.rows_pad) continue;
+      const size_t o = ((size_t)b * d + c) * po.npad + po.col0 + i0 + r;
+      const float v = tp_tile[r * pitch + c];
+      if (po.t16 == PEG_FMT_FP16X2) store_vt_f16(po, o, v * vscale);
+      else store_vt(po, o, v);
+    }
+  }
+  // column sums over this block's nodes, rows in ascending order
+  const int chunks = gridDim.x;
+  const float* vb = po.vec ? po.vec + (size_t)b * po.vec_stride : nullptr;
+  float* part = po.partial + (((size_t)b * chunks + blk) * 2) * d;
+  for (int c = tid; c < d; c += 256) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int r = 0; r < 128; ++r) {
+      const float v = tp_tile[r * pitch + c];
+      s0 += v;
+      if (vb && i0 + r < n) s1 = fmaf(vb[i0 + r], v, s1);
+    }
+    part[c] = s0;
+    part[d + c] = s1;
+  }
+  finalize_colsums(po, b, chunks, d, 0, d, po.tickets + b, &is_last);
+}
+
 // cotangent of control_data.derivative(t): g_xd[n,j] = sum_m tg_n kbar[n,m] OL[n, m*2e+j]  (OL = unscaled last-layer output)
 __global__ void __launch_bounds__(256) k_wrapper_xbar(const float* __restrict__ kbar, const float* __restrict__ OLtg,
                                                       int n, int h, int e2, int B, float* __restrict__ gxd) {

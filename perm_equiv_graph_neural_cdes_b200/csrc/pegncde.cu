@@ -514,15 +514,31 @@ static int feval_vjp(Ctx& c, float t, float* const* zin, const float* kbar, floa
     k_wrapper_xbar<<<(unsigned)((cnt + 255) / 256), 256, 0, c.st>>>(kbar, c.w.OL, d.n, d.h, 2 * d.e, d.B, g_xd);
     PEG_LAUNCH_CHECK();
   }
-  {
+  bool obar_ready = false;   // column sums / V^T of Obar already produced by the previous k_linear_bwd
+  bool obar_vt = false;
+  // without the CDE wrapper the top cotangent is tg (.) kbar: on the tensor-core path one kernel writes it together with its
+  // column sums, block exponents and V^T (otherwise: k_wrapper_bwd here, k_colsums / tc_convert_v further down)
+  const bool top_fused = d.e == 0 && contract_on_tc(c, d.L - 1) && dL <= 256 && (dL % 4) == 0;
+  if (top_fused) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      PEG_CUDA(cudaFuncSetAttribute(k_top_producer, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 257 * (int)sizeof(float)));
+      attr_done = true;
+    }
+    const ProducerOut po = producer_out(c, dL, true, c.w.colG, true, svec_r(d.n, d.L - 1), true);
+    if (po.Thi == nullptr) return PEG_ERR_WORKSPACE;
+    dim3 grid((unsigned)((po.rows_pad + 127) / 128), d.B);
+    k_top_producer<<<grid, 256, 128 * (dL + 1) * sizeof(float), c.st>>>(kbar, c.w.svec, c.sv_stride, svec_tg(d.n, d.L), d.n, dL, c.w.Obar, po);
+    PEG_LAUNCH_CHECK();
+    obar_ready = true;
+    obar_vt = true;
+  } else {
     const size_t cnt = (size_t)d.B * d.n * dL;
     k_wrapper_bwd<<<(unsigned)((cnt + 255) / 256), 256, 0, c.st>>>(kbar, c.w.svec, c.sv_stride, svec_xd(d.n, d.L),
                                                                    svec_tg(d.n, d.L), d.n, d.h, 2 * d.e, d.B,
                                                                    c.w.Obar);
     PEG_LAUNCH_CHECK();
   }
-  bool obar_ready = false;   // column sums / V^T of Obar already produced by the previous k_linear_bwd
-  bool obar_vt = false;
   for (int l = d.L - 1; l >= 0; --l) {
     const LayerDesc& ld = c.m.layer[l];
     float* g_fus = g_params + ld.fus_off;
