@@ -398,3 +398,35 @@ def test_integration_doc_quotes_the_committed_file():
     assert code in doc
     # and the file is valid Python (it cannot be imported here: jax / diffrax / the reference tree are absent)
     compile(body, "reference_integration.py", "exec")
+
+
+def test_ctypes_mirror_has_the_layout_and_flag_values_of_the_header(tmp_path):
+    """Every struct of include/pegncde.h: size and the offset of every field as gcc lays them out == the ctypes mirror in _lib.py
+    (a field added to one side only would shift everything behind it silently); same for the PEG_FLAG_* / PEG_WS_* values."""
+    import subprocess
+
+    from perm_equiv_graph_neural_cdes_b200 import _lib
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {"PegDims": _lib.PegDims, "PegShard": _lib.PegShard, "PegControl": _lib.PegControl, "PegAdaptState": _lib.PegAdaptState}
+    enums = [k for k in dir(_lib) if k.startswith(("PEG_FLAG_", "PEG_WS_"))]
+    assert "PEG_FLAG_FUSED_SMALL" in enums and "PEG_WS_SOLVE_BWD" in enums
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "pegncde.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    for k in enums:
+        lines.append(f'  printf("{k} %d\\n", (int){k});')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == ctypes.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(got[f"{name}.{field}"]) == getattr(cls, field).offset, (name, field)
+    for k in enums:
+        assert int(got[k]) == getattr(_lib, k), k
