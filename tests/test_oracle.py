@@ -447,3 +447,53 @@ def test_rms_norm_matches_torch_rms_norm():
     w, b = torch.randn(16, generator=g, dtype=torch.float64), torch.randn(16, generator=g, dtype=torch.float64)
     ref = torch.nn.functional.rms_norm(x, (16,), weight=w, eps=1e-5) + b
     assert torch.allclose(R.rms_norm(x, w, b), ref, rtol=0, atol=1e-14)
+
+
+def test_fp16x2_block_floating_point_scheme_reaches_fp32_accuracy():
+    """CPU emulation (numpy) of the default operand format of the tensor-core contraction (csrc/peg_tc.cu, DESIGN.md "Operand formats"):
+    V^T is stored as V * 2^e_J with one power-of-two exponent per 128-node block and split hi + lo into two fp16 numbers; the
+    interpolated adjacency gets one power-of-two scale, is aligned to the smallest block exponent by an exact factor 2^(E - e_J) per
+    K block, and is split with the symmetric rounding ((bits + 0x1000) & 0xffffe000); the products hi*hi + lo*hi + hi*lo accumulate in
+    fp32 and the scales are divided out (exactly) at the end.  The scheme must reproduce the fp64 product to fp32-level accuracy on
+    operands with England's dynamic range and block magnitudes that differ by 1e6, where single-pass fp16 is off by > 1e-4."""
+    rng = np.random.default_rng(5)
+    n, m, d, VEXP_MAX = 512, 96, 24, 60
+
+    def block_exponent(amax):
+        if not amax > 0:
+            return VEXP_MAX
+        e = 14 - (int((np.float32(amax).view(np.uint32) >> 23) & 0xFF) - 127)
+        return max(-VEXP_MAX, min(VEXP_MAX, e))
+
+    A = (rng.lognormal(0.0, 2.0, (m, n)) * (rng.random((m, n)) < 0.1) * rng.choice([-1.0, 1.0], (m, n))).astype(np.float32)     # sparse-ish, 1e4 range
+    V = rng.standard_normal((n, d)).astype(np.float32)
+    V *= np.repeat(np.float32(10.0) ** rng.integers(-3, 4, n // 128), 128)[:, None]                     # block magnitudes 1e-3 .. 1e3
+    V[128:256] = 0.0                                                                                   # an all-zero block never wins the minimum
+    ref = A.astype(np.float64) @ V.astype(np.float64)
+    # V side: per-block exponents, hi = rn_f16(v 2^e), lo = rn_f16(v 2^e - hi)
+    eJ = np.array([block_exponent(np.abs(V[j * 128:(j + 1) * 128]).max()) for j in range(n // 128)])
+    Vs = V * np.repeat(np.exp2(eJ.astype(np.float64)), 128)[:, None].astype(np.float32)                 # exact: power of two
+    assert np.abs(Vs).max() < 65504
+    v_hi = Vs.astype(np.float16)
+    v_lo = (Vs - v_hi.astype(np.float32)).astype(np.float16)
+    # A side: one scale for the launch, aligned per K block to the smallest exponent
+    E = int(eJ.min())
+    eA = block_exponent(np.abs(A).max())
+    As = A * np.float32(np.exp2(eA)) * np.repeat(np.exp2((E - eJ).astype(np.float64)), 128)[None, :].astype(np.float32)
+    bits = As.view(np.uint32)
+    a_hi32 = ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    a_hi = a_hi32.astype(np.float16)
+    big = np.abs(As) >= 2.0 ** -14                  # hi is exact in fp16 wherever it is a normal fp16 number
+    assert np.array_equal(a_hi.astype(np.float32)[big], a_hi32[big])
+    a_lo = (As - a_hi32).astype(np.float16)
+    f32 = lambda x: x.astype(np.float32)
+    acc = f32(a_hi) @ f32(v_hi) + f32(a_lo) @ f32(v_hi) + f32(a_hi) @ f32(v_lo)                         # fp32 accumulation
+    got = acc.astype(np.float64) * np.exp2(-float(eA)) * np.exp2(-float(E))
+    scale = np.abs(ref).max()
+    err3 = np.abs(got - ref).max() / scale
+    err1 = np.abs((f32(a_hi) @ f32(v_hi)).astype(np.float64) * np.exp2(-float(eA)) * np.exp2(-float(E)) - ref).max() / scale
+    assert err3 < 5e-6, err3
+    assert err1 > 1e-4, err1        # the split is what buys the accuracy
+    # column-wise too (every column of V has its own magnitude profile): no column is worse than 2e-5 of its own maximum
+    col = np.abs(got - ref).max(axis=0) / np.abs(ref).max(axis=0)
+    assert col.max() < 2e-5, col.max()
